@@ -1,0 +1,67 @@
+"""Builds the in-tree native libraries (sm_100a only).
+
+  dali_b200/lib/libdali_b200.so        CUDA kernels + the C-ABI of include/dali_b200.h   (nvcc)
+
+`python -m dali_b200.build` or __graft_entry__.build().  nvcc cross-compiles without a GPU.
+"""
+import concurrent.futures as cf
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _newer(src, dst, extra=()):
+    if not os.path.exists(dst):
+        return True
+    t = os.path.getmtime(dst)
+    return any(os.path.getmtime(s) > t for s in (src,) + tuple(extra))
+
+
+def build_kernels(verbose=False, force=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    hdrs = tuple(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
+                 glob.glob(os.path.join(HERE, "..", "include", "*.h")))
+    objs = []
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, os.path.basename(src) + ".o")
+        if force or _newer(src, obj, hdrs):
+            cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            log = r.stdout + r.stderr
+            with open(obj + ".log", "w") as f:
+                f.write(log)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {src}:\n{log[-4000:]}")
+            if verbose:
+                print(log)
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs) or 1)) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    lib = os.path.join(LIBDIR, "libdali_b200.so")
+    if force or any(_newer(o, lib) for o in objs):
+        cmd = [NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return lib
+
+
+def build_all(verbose=False, force=False):
+    return build_kernels(verbose=verbose, force=force)
+
+
+if __name__ == "__main__":
+    print(build_all(verbose="-v" in sys.argv, force="-f" in sys.argv))

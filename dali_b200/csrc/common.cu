@@ -1,0 +1,63 @@
+// dali_b200/csrc/common.cu -- error state, descriptor arena, launch accounting.
+#include "common.cuh"
+#include <cstring>
+
+namespace dalib200 {
+
+static thread_local std::string tls_error;
+std::atomic<uint64_t> g_launch_count{0};
+
+void SetLastError(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  tls_error = buf;
+}
+
+int DescArena::Reserve(size_t bytes) {
+  if (bytes <= cap) return DALIB200_SUCCESS;
+  size_t ncap = cap ? cap : 4096;
+  while (ncap < bytes) ncap *= 2;
+  uint8_t *nh = nullptr, *nd = nullptr;
+  DB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&nh), ncap));
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&nd), ncap);
+  if (e != cudaSuccess) { cudaFreeHost(nh); DB_CUDA(e); }
+  // NOTE: a previous launch may still be reading the old device arena; cudaFree synchronises the
+  // device implicitly, so growing is safe (it only happens while shapes are still warming up).
+  if (host) cudaFreeHost(host);
+  if (dev) cudaFree(dev);
+  host = nh; dev = nd; cap = ncap;
+  return DALIB200_SUCCESS;
+}
+
+int DescArena::Upload(size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return DALIB200_SUCCESS;
+  DB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s));
+  return DALIB200_SUCCESS;
+}
+
+void DescArena::Free() {
+  if (host) cudaFreeHost(host);
+  if (dev) cudaFree(dev);
+  host = dev = nullptr; cap = 0;
+}
+
+int NumSMs() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+}  // namespace dalib200
+
+extern "C" {
+const char *dalib200GetLastError(void) { return dalib200::tls_error.c_str(); }
+int dalib200GetVersion(void) { return 100; }
+uint64_t dalib200GetLaunchCount(void) { return dalib200::g_launch_count.load(); }
+}

@@ -1,0 +1,101 @@
+// dali_b200/csrc/common.cuh -- shared host/device helpers for the sm_100a kernels.
+#ifndef DALI_B200_CSRC_COMMON_CUH_
+#define DALI_B200_CSRC_COMMON_CUH_
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include "../../include/dali_b200.h"
+
+namespace dalib200 {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing (thread-local message, as the reference C API does: dali/c_api_2/error_handling.cc)
+void SetLastError(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+inline void CountLaunch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+#define DB_CHECK_ARG(cond, ...)                                   \
+  do { if (!(cond)) { ::dalib200::SetLastError(__VA_ARGS__); return DALIB200_ERROR_INVALID_ARGUMENT; } } while (0)
+
+#define DB_CUDA(call)                                                                           \
+  do { cudaError_t e__ = (call); if (e__ != cudaSuccess) {                                      \
+    ::dalib200::SetLastError("CUDA error %s at %s:%d (%s)", cudaGetErrorName(e__), __FILE__, __LINE__, \
+                             cudaGetErrorString(e__));                                          \
+    return DALIB200_ERROR_CUDA; } } while (0)
+
+// A grow-only pinned-host + device arena for per-batch descriptors: one H2D copy per launch.
+struct DescArena {
+  uint8_t *host = nullptr, *dev = nullptr;
+  size_t cap = 0;
+  int Reserve(size_t bytes);
+  int Upload(size_t bytes, cudaStream_t s);   // async H2D of the first `bytes`
+  void Free();
+};
+
+int NumSMs();
+
+// ---------------------------------------------------------------------------------------------
+// numerics shared by the kernels -- these restate the reference HOST (CPU backend) conventions,
+// which are the parity target.
+#ifdef __CUDACC__
+
+// include/dali/core/convert.h:306-324: host ConvertSat<uint8_t>(float) = clamp(std::round(x)) -- half AWAY.
+__device__ __forceinline__ uint8_t sat_u8_half_away(float x) {
+  float t = truncf(x);
+  float d = x - t;                               // exact for |x| < 2^23
+  if (d >= 0.5f) t += 1.0f; else if (d <= -0.5f) t -= 1.0f;
+  t = fminf(fmaxf(t, 0.0f), 255.0f);
+  return (uint8_t)(int)t;
+}
+// dali/kernels/common/simd.h:233-263: the SSE2 store path rounds half to EVEN (cvtps2dq) then saturates.
+__device__ __forceinline__ uint8_t sat_u8_half_even(float x) {
+  x = fminf(fmaxf(x, 0.0f), 255.0f);
+  return (uint8_t)__float2int_rn(x);
+}
+
+// include/dali/util/half.hpp:464-540 (HALF_ROUND_STYLE=1, HALF_ROUND_TIES_TO_EVEN=0 at :233,:242):
+// float -> half, round to nearest, ties AWAY from zero; after the +-65504 clamp of
+// include/dali/core/convert.h:168-176.
+__device__ __forceinline__ uint16_t float2half_ties_away(float f) {
+  f = fminf(fmaxf(f, -65504.0f), 65504.0f);     // NaN propagates through fminf/fmaxf as the other operand: documented deviation
+  uint32_t bits = __float_as_uint(f);
+  uint32_t sign = (bits >> 16) & 0x8000u, e = (bits >> 23) & 0xFFu, mant = bits & 0x7FFFFFu;
+  uint32_t base, shift;
+  if (e < 103u)       { base = 0u; shift = 24u; }
+  else if (e < 113u)  { base = 1u << (e - 103u); shift = 126u - e; }
+  else                { base = (e - 112u) << 10; shift = 13u; }   // e <= 142 after the clamp
+  uint32_t h = sign + base + (mant >> shift);
+  uint32_t rnd = ((mant >> (shift - 1u)) | (uint32_t)(e == 102u)) & 1u;
+  return (uint16_t)(h + rnd);
+}
+
+template <typename T> struct OutConv;
+template <> struct OutConv<float> {
+  __device__ __forceinline__ static float cvt(float v) { return v; }
+};
+template <> struct OutConv<uint16_t> {   // float16 bits
+  __device__ __forceinline__ static uint16_t cvt(float v) { return float2half_ties_away(v); }
+};
+
+// mul and add that the compiler may NOT contract into an FMA: the reference CPU binary targets
+// baseline x86-64 (no FMA), so a*b+c is rounded twice there.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace dalib200
+#endif  // DALI_B200_CSRC_COMMON_CUH_

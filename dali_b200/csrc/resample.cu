@@ -1,0 +1,584 @@
+// dali_b200/csrc/resample.cu -- fused two-pass separable resampling for sm_100a.
+//
+// Parity target: the reference CPU kernel SeparableResampleCPU (dali/kernels/imgproc/resample/
+// separable_cpu.h:149-249) driven by SeparableResamplingSetup<2>::SetupSample (resampling_setup.cc:271-337):
+//   * per-axis filter choice / radius / LUT rescale            (resampling_setup.cc:27-76, params.h:40-56,
+//                                                                resampling_filters.cu:66-142)
+//   * pass order from the cost model                            (resampling_setup.cc:131-192)
+//   * coefficient tables: idx = ceil(x*scale + s0), c_k = f((idx - sx + k)*fscale), normalised BEFORE
+//     accumulation                                              (resampling_impl_cpu.cc:22-47)
+//   * acc = sum_k c_k * src[clamp(idx+k)]   k ascending, mul and add rounded separately (SSE2, no FMA)
+//   * fp32 intermediate between the passes; final u8 store rounds half-to-even where the reference runs
+//     its SSE path and half-away in its scalar tails            (simd.h:233-263, convert.h:306-324,
+//                                                                resampling_impl_cpu.h:95-124,126-222,245-336)
+// The reference GPU kernel (resampling_impl.cuh) normalises after accumulation with FMAs and writes
+// the fp32 intermediate to HBM; here BOTH passes of an output tile run in one CTA with the
+// intermediate held in shared memory, so HBM sees the input once and the output once.
+//
+// Algorithmic bytes per unit: in_h*in_w*C*sizeof(In) + out_h*out_w*C*sizeof(Out).
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+namespace dalib200 {
+
+// ---------------------------------------------------------------------------------------------
+// host: filters (resampling_filters.cuh / .cu restated for the host-side table builder)
+struct RFilter {
+  const float *coeffs; int num_coeffs; float anchor; float scale;
+  void rescale(float support) { float old = scale; scale = (num_coeffs - 1) / support; anchor = anchor * old / scale; }
+  int support() const { return (int)ceilf((num_coeffs - 1) / scale); }
+  float operator()(float x) const {
+    if (!(x > -1)) return 0;
+    if (x >= num_coeffs) return 0;
+    int x0 = (int)std::floor(x), x1 = x0 + 1;
+    float d = x - x0;
+    float f0 = x0 < 0.0f ? 0 : coeffs[x0];
+    float f1 = x1 >= num_coeffs ? 0.0f : coeffs[x1];
+    float t = f1 - f0;
+    float m = d * t;
+    return f0 + m;
+  }
+};
+
+struct FilterBank {
+  float tri[3], gauss[65], lanczos[193], cubic[129];
+  RFilter base[4];
+  FilterBank() {
+    tri[0] = 0; tri[1] = 1; tri[2] = 0;
+    for (int i = 0; i < 65; i++) { float x = 4 * (i - 64 * 0.5f) / 64; gauss[i] = expf(-x * x); }
+    auto sinc = [](float x) { x = (float)(x * M_PI); if (std::fabs(x) < 1e-5f) return 1.0f - x * x * (1.0f / 6); return sinf(x) / x; };
+    for (int i = 0; i < 193; i++) {
+      float x = 2 * 3.0f * (i - 192 * 0.5f) / 192;
+      lanczos[i] = std::fabs(x) >= 3.0f ? 0.0f : sinc(x) * sinc(x / 3.0f);
+    }
+    for (int i = 0; i < 129; i++) {
+      float x = std::fabs(4 * (i - 128 * 0.5f) / 128), v;
+      if (x >= 2) v = 0;
+      else { float x2 = x * x, x3 = x2 * x; v = x > 1 ? -0.5f * x3 + 2.5f * x2 - 4.0f * x + 2.0f : 1.5f * x3 - 2.5f * x2 + 1.0f; }
+      cubic[i] = v;
+    }
+    base[0] = { tri, 3, 1, 1.0f };
+    base[1] = { gauss, 65, 1, 32.0f };
+    base[2] = { lanczos, 193, 1, 96.0f };
+    base[3] = { cubic, 129, 1, 64.0f };
+    base[2].rescale(6);
+    base[3].rescale(4);
+  }
+  RFilter get(int type, float radius) const {
+    RFilter f;
+    switch (type) {
+      case DALIB200_FILTER_LINEAR:     f = base[0]; f.rescale(std::max(1.0f, 2 * 1.0f)); return f;
+      case DALIB200_FILTER_TRIANGULAR: f = base[0]; f.rescale(std::max(1.0f, 2 * radius)); return f;
+      case DALIB200_FILTER_GAUSSIAN: { float sigma = (float)(radius * 0.5f / M_SQRT2);
+                                       f = base[1]; f.rescale(std::max(1.0f, static_cast<float>(4 * M_SQRT2) * sigma)); return f; }
+      case DALIB200_FILTER_CUBIC:      f = base[3]; f.rescale(2.0f * std::max(2.0f, radius)); return f;
+      case DALIB200_FILTER_LANCZOS3:   f = base[2]; f.rescale(2.0f * std::max(3.0f, radius)); return f;
+      default:                         f = { nullptr, 0, 0, 1 }; return f;
+    }
+  }
+};
+static const FilterBank &Filters() { static FilterBank fb; return fb; }
+
+static float DefaultRadius(int type, bool antialias, float in_size, float out_size) {
+  antialias = antialias && in_size > out_size;
+  switch (type) {
+    case DALIB200_FILTER_TRIANGULAR: return antialias ? in_size / out_size : 1;
+    case DALIB200_FILTER_GAUSSIAN:   return antialias ? in_size / out_size : 1;
+    case DALIB200_FILTER_CUBIC:      return antialias ? (2 * in_size / out_size) : 2;
+    case DALIB200_FILTER_LANCZOS3:   return antialias ? (3 * in_size / out_size) : 3;
+    default: return 1;
+  }
+}
+
+// One axis of one sample after setup.  Axis 0 = x (width), 1 = y (height) -- the reference's vec order.
+struct AxisSetup {
+  int in_size, out_size;
+  int ftype;
+  RFilter filter;
+  float origin, scale;       // origin already shifted by roi_lo when the axis is cropped
+  int roi_lo, roi_hi;
+  int base, extent;          // absolute source index = base + clamp(idx, 0, extent-1)
+  int support;               // >= 1 (NN -> 1)
+};
+
+struct AxisTableRef { int idx_off, coef_off, support; };   // offsets (in 4-byte words) into the table arena
+
+struct RsDesc {
+  const void *in;
+  void *out;
+  int32_t in_h, in_w, C, out_h, out_w;
+  int32_t vfirst;
+  int32_t idx_off[2], coef_off[2], support[2], base[2], extent[2];   // [0] = x, [1] = y
+  int32_t flags_off;         // per-output-column rounding flags (horizontal last pass, u8 out) or -1
+  int32_t simd_flat_end;     // vertical last pass, u8 out: flat x*C+c < this -> half-to-even
+  int32_t tile_h, tile_w, tiles_x, tiles_y;
+  int64_t first_tile;
+};
+
+// ---------------------------------------------------------------------------------------------
+// device
+__device__ __forceinline__ int find_tile_sample(const RsDesc *d, int n, int64_t t) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (d[mid].first_tile <= t) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+template <typename T> __device__ __forceinline__ float ld_as_float(const T *p);
+template <> __device__ __forceinline__ float ld_as_float<uint8_t>(const uint8_t *p) { return (float)__ldg(p); }
+template <> __device__ __forceinline__ float ld_as_float<float>(const float *p) { return __ldg(p); }
+
+template <typename Out> __device__ __forceinline__ Out rs_store_cvt(float v, bool half_even);
+template <> __device__ __forceinline__ float rs_store_cvt<float>(float v, bool) { return v; }
+template <> __device__ __forceinline__ uint8_t rs_store_cvt<uint8_t>(float v, bool half_even) {
+  return half_even ? sat_u8_half_even(v) : sat_u8_half_away(v);
+}
+
+// One CTA = one output tile of one sample.  smem: fp32 intermediate of the tile.
+template <typename In, typename Out>
+__global__ void __launch_bounds__(256) resample_fused_kernel(const RsDesc *__restrict__ descs, const int32_t *__restrict__ tab,
+                                                             int n, int64_t total_tiles) {
+  extern __shared__ float tmp[];
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int s = find_tile_sample(descs, n, tile);
+    const RsDesc &d = descs[s];
+    const int64_t tl = tile - d.first_tile;
+    const int ty = (int)(tl / d.tiles_x), tx = (int)(tl % d.tiles_x);
+    const int oy0 = ty * d.tile_h, ox0 = tx * d.tile_w;
+    const int th = min(d.tile_h, d.out_h - oy0), tw = min(d.tile_w, d.out_w - ox0);
+    const int C = d.C;
+    const int Sx = d.support[0], Sy = d.support[1];
+    const int32_t *idx_x = tab + d.idx_off[0], *idx_y = tab + d.idx_off[1];
+    const float *coef_x = reinterpret_cast<const float *>(tab + d.coef_off[0]);
+    const float *coef_y = reinterpret_cast<const float *>(tab + d.coef_off[1]);
+    const int bx = d.base[0], ex = d.extent[0], by = d.base[1], ey = d.extent[1];
+    const In *in = static_cast<const In *>(d.in);
+    Out *out = static_cast<Out *>(d.out);
+    const int64_t pitch = (int64_t)d.in_w * C;
+    const uint8_t *flags = d.flags_off >= 0 ? reinterpret_cast<const uint8_t *>(tab + d.flags_off) : nullptr;
+
+    if (d.vfirst) {
+      // absolute column span needed by this tile (indices are monotonic in x)
+      const int ia = idx_x[ox0], ib = idx_x[ox0 + tw - 1];
+      const int cmin = bx + min(max(min(ia, ib), 0), ex - 1);
+      const int cmax = bx + min(max(max(ia, ib) + Sx - 1, 0), ex - 1);
+      const int span = cmax - cmin + 1;
+      const int row_elems = span * C;
+      // stage A: vertical FIR   tmp[t][j] = sum_k cy[t][k] * in[row(t,k)][cmin*C + j]
+      for (int e = threadIdx.x; e < th * row_elems; e += blockDim.x) {
+        const int t = e / row_elems, j = e - t * row_elems;
+        const int oy = oy0 + t;
+        const int i0 = idx_y[oy];
+        const float *cy = coef_y + (int64_t)oy * Sy;
+        const In *col = in + (int64_t)cmin * C + j;
+        float acc = 0.0f;
+        for (int k = 0; k < Sy; k++) {
+          const int r = by + min(max(i0 + k, 0), ey - 1);
+          acc = add_rn(acc, mul_rn(ld_as_float<In>(col + r * pitch), cy[k]));
+        }
+        tmp[e] = acc;
+      }
+      __syncthreads();
+      // stage B: horizontal FIR from the smem intermediate
+      for (int e = threadIdx.x; e < th * tw * C; e += blockDim.x) {
+        const int c = e % C;
+        const int x = (e / C) % tw;
+        const int t = e / (C * tw);
+        const int ox = ox0 + x;
+        const int i0 = idx_x[ox];
+        const float *cx = coef_x + (int64_t)ox * Sx;
+        const float *row = tmp + t * row_elems + c;
+        float acc = 0.0f;
+        for (int k = 0; k < Sx; k++) {
+          const int sx = bx + min(max(i0 + k, 0), ex - 1) - cmin;
+          acc = add_rn(acc, mul_rn(cx[k], row[sx * C]));
+        }
+        const bool he = flags ? flags[ox] != 0 : false;
+        out[((int64_t)(oy0 + t) * d.out_w + ox) * C + c] = rs_store_cvt<Out>(acc, he);
+      }
+    } else {
+      const int ia = idx_y[oy0], ib = idx_y[oy0 + th - 1];
+      const int rmin = by + min(max(min(ia, ib), 0), ey - 1);
+      const int rmax = by + min(max(max(ia, ib) + Sy - 1, 0), ey - 1);
+      const int rows = rmax - rmin + 1;
+      const int row_elems = tw * C;
+      // stage A: horizontal FIR   tmp[r][x*C+c] = sum_k cx[x][k] * in[rmin + r][col(x,k)][c]
+      for (int e = threadIdx.x; e < rows * row_elems; e += blockDim.x) {
+        const int c = e % C;
+        const int x = (e / C) % tw;
+        const int r = e / row_elems;
+        const int ox = ox0 + x;
+        const int i0 = idx_x[ox];
+        const float *cx = coef_x + (int64_t)ox * Sx;
+        const In *rowp = in + (int64_t)(rmin + r) * pitch + c;
+        float acc = 0.0f;
+        for (int k = 0; k < Sx; k++) {
+          const int sx = bx + min(max(i0 + k, 0), ex - 1);
+          acc = add_rn(acc, mul_rn(cx[k], ld_as_float<In>(rowp + (int64_t)sx * C)));
+        }
+        tmp[e] = acc;
+      }
+      __syncthreads();
+      // stage B: vertical FIR from the smem intermediate
+      for (int e = threadIdx.x; e < th * row_elems; e += blockDim.x) {
+        const int t = e / row_elems, j = e - t * row_elems;
+        const int oy = oy0 + t;
+        const int i0 = idx_y[oy];
+        const float *cy = coef_y + (int64_t)oy * Sy;
+        float acc = 0.0f;
+        for (int k = 0; k < Sy; k++) {
+          const int r = by + min(max(i0 + k, 0), ey - 1) - rmin;
+          acc = add_rn(acc, mul_rn(tmp[r * row_elems + j], cy[k]));
+        }
+        const int flat = ox0 * C + j;
+        out[((int64_t)oy * d.out_w + ox0) * C + j] = rs_store_cvt<Out>(acc, flat < d.simd_flat_end);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace dalib200
+
+using namespace dalib200;  // NOLINT
+
+namespace {
+
+constexpr int kTmpFloats = 24 * 1024;     // 96 KB of fp32 intermediate per CTA -> 2 CTAs / SM
+
+struct TableKey {
+  int in_size, out_size, ftype, base, extent;
+  uint32_t origin_bits, scale_bits, fscale_bits, fanchor_bits;
+  bool operator<(const TableKey &o) const {
+    return std::tie(in_size, out_size, ftype, base, extent, origin_bits, scale_bits, fscale_bits, fanchor_bits) <
+           std::tie(o.in_size, o.out_size, o.ftype, o.base, o.extent, o.origin_bits, o.scale_bits, o.fscale_bits, o.fanchor_bits);
+  }
+};
+inline uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+}  // namespace
+
+struct dalib200ResamplePlan {
+  int max_batch = 0, n = 0;
+  int in_dtype = DALIB200_UINT8, out_dtype = DALIB200_UINT8;
+  std::vector<RsDesc> descs;
+  std::vector<int32_t> tables;                 // host copy of the table arena (idx, coef bits, flags)
+  std::vector<int32_t> uploaded_tables;        // what the device arena currently holds
+  std::map<TableKey, AxisTableRef> cache;      // dedup of axis tables within a batch
+  std::vector<int> order0;
+  int64_t total_tiles = 0;
+  DescArena desc_arena, table_arena;
+  size_t tables_uploaded_words = 0;
+  bool tables_dirty = true;
+  cudaEvent_t uploaded = nullptr;
+  bool pending = false;
+  bool smem_opted[4] = { false, false, false, false };
+};
+
+namespace {
+
+// resampling_setup.cc:47-122 for one axis (dim: 0 = y params index, axis = 1 - dim)
+int SetupAxis(AxisSetup &a, int in_size, int out_size, bool use_roi, float roi_start, float roi_end,
+              dalib200FilterDesc minf, dalib200FilterDesc magf) {
+  a.in_size = in_size; a.out_size = out_size;
+  float fin = use_roi ? std::abs(roi_end - roi_start) : (float)in_size;
+  dalib200FilterDesc fd = out_size < fin ? minf : magf;
+  if (fd.antialias && fd.type == DALIB200_FILTER_LINEAR) fd.type = DALIB200_FILTER_TRIANGULAR;
+  else if (!fd.antialias && fd.type == DALIB200_FILTER_TRIANGULAR) fd.type = DALIB200_FILTER_LINEAR;
+  if (fd.radius == 0) fd.radius = DefaultRadius(fd.type, fd.antialias != 0, fin, (float)out_size);
+  a.ftype = fd.type;
+  a.filter = Filters().get(fd.type, fd.radius);
+  float rs = use_roi ? roi_start : 0, re = use_roi ? roi_end : (float)in_size;
+  a.origin = rs;
+  a.scale = (re - rs) / out_size;
+  int support = a.filter.num_coeffs ? a.filter.support() : 1;
+  if (support > 8192) a.filter.rescale(8192);
+  float lo, hi;
+  if (rs <= re) { lo = rs - a.filter.anchor; hi = re - a.filter.anchor + support; }
+  else          { lo = re - a.filter.anchor; hi = rs - a.filter.anchor + support; }
+  a.roi_lo = std::max<int>(0, std::min<int>(in_size, (int)std::floor(lo)));
+  a.roi_hi = std::max<int>(0, std::min<int>(in_size, (int)std::ceil(hi)));
+  a.support = std::max(1, a.filter.num_coeffs ? a.filter.support() : 1);
+  return 0;
+}
+
+// resampling_setup.cc:131-192 (2-D): returns the first-pass axis (0 = x / horizontal first)
+int ProcessingOrder(const AxisSetup ax[2]) {
+  float best = 1e+30f; int best_first = 0;
+  for (int first = 0; first < 2; first++) {
+    int64_t sz[2] = { ax[0].roi_hi - ax[0].roi_lo, ax[1].roi_hi - ax[1].roi_lo };
+    int axes[2] = { first, 1 - first };
+    float total = 0; bool ok = true;
+    for (int p = 0; p < 2; p++) {
+      if (total >= best) { ok = false; break; }
+      int a = axes[p];
+      sz[a] = ax[a].out_size;
+      int64_t vol = sz[0] * sz[1];
+      float mul = a == 0 ? 1.4f : 1.0f;
+      float base = (float)(ax[a].support * vol);
+      total += mul * base + vol * 3.0f;
+    }
+    if (ok && !(total >= best)) { best = total; best_first = first; }
+  }
+  return best_first;
+}
+
+// Coefficient / index table of one axis.  FIR: resampling_impl_cpu.cc:22-47.  NN (1 tap, weight 1):
+// resampling_impl_cpu.h:522-606 -- note the y coordinate is accumulated incrementally there.
+void BuildTable(std::vector<int32_t> &arena, AxisTableRef &ref, const AxisSetup &a, int axis) {
+  const int n = a.out_size, S = a.support;
+  ref.support = S;
+  ref.idx_off = (int)arena.size();
+  arena.resize(arena.size() + n);
+  ref.coef_off = (int)arena.size();
+  arena.resize(arena.size() + (size_t)n * S);
+  int32_t *idx = arena.data() + ref.idx_off;
+  float *coef = reinterpret_cast<float *>(arena.data() + ref.coef_off);
+  if (a.ftype == DALIB200_FILTER_NN) {
+    if (axis == 1) {
+      float sy = a.origin + 0.5f * a.scale;
+      for (int y = 0; y < n; y++, sy += a.scale) { idx[y] = (int)std::floor(sy); coef[y] = 1.0f; }
+    } else if (a.scale == 1) {
+      int sx0 = (int)std::floor(a.origin + 0.5f);
+      for (int x = 0; x < n; x++) { idx[x] = sx0 + x; coef[x] = 1.0f; }
+    } else {
+      for (int x = 0; x < n; x++) { idx[x] = (int)std::floor(a.origin + (x + 0.5f) * a.scale); coef[x] = 1.0f; }
+    }
+    return;
+  }
+  const RFilter &f = a.filter;
+  float s0 = a.origin;
+  s0 += 0.5f * a.scale - 0.5f - f.anchor;
+  for (int x = 0; x < n; x++) {
+    float sx0f = x * a.scale + s0;
+    int sx0 = (int)ceilf(sx0f);
+    idx[x] = sx0;
+    const float f0 = sx0 - sx0f;
+    float sum = 0;
+    for (int k = 0; k < S; k++) {
+      float c = f((f0 + k) * f.scale);
+      coef[(size_t)S * x + k] = c;
+      sum += c;
+    }
+    if (sum) for (int k = 0; k < S; k++) coef[(size_t)S * x + k] /= sum;
+  }
+}
+
+// Which output columns does the reference's horizontal pass compute in its 16-lane SSE path?
+// (resampling_impl_cpu.h:126-222,225-336) -- those round half-to-even when storing u8.
+int BuildHorzFlags(std::vector<int32_t> &arena, int idx_off, int ow, int iw, int support) {
+  int off = (int)arena.size();
+  arena.resize(arena.size() + (ow + 3) / 4);
+  const int32_t *idx = arena.data() + idx_off;      // after the resize: the arena may have moved
+  uint8_t *fl = reinterpret_cast<uint8_t *>(arena.data() + off);
+  memset(fl, 0, (size_t)((ow + 3) / 4) * 4);
+  bool flipped = idx[ow - 1] < idx[0];
+  int first = 0, last = ow - 1;
+  if (flipped) {
+    while (first < ow && idx[first] + support > iw) first++;
+    while (last >= 0 && idx[last] < 0) last--;
+  } else {
+    while (first < ow && idx[first] < 0) first++;
+    while (last >= 0 && idx[last] + support > iw) last--;
+  }
+  int bounds[4] = { std::min(first, last + 1), first, last + 1, ow };
+  int x = 0;
+  for (int r = 0; r < 4; r++) {
+    int ox1 = bounds[r];
+    for (; x + 16 <= ox1; x += 16) memset(fl + x, 1, 16);
+    for (; x < ox1; x++) fl[x] = 0;
+  }
+  return off;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dalib200ResamplePlanCreate(dalib200ResamplePlan **plan, int max_batch) {
+  DB_CHECK_ARG(plan && max_batch > 0, "ResamplePlanCreate: bad arguments");
+  auto *p = new dalib200ResamplePlan();
+  p->max_batch = max_batch;
+  int rc = p->desc_arena.Reserve(sizeof(RsDesc) * max_batch);
+  if (rc) { delete p; return rc; }
+  if (cudaEventCreateWithFlags(&p->uploaded, cudaEventDisableTiming) != cudaSuccess) {
+    SetLastError("ResamplePlanCreate: cudaEventCreate failed"); p->desc_arena.Free(); delete p; return DALIB200_ERROR_CUDA;
+  }
+  *plan = p;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200ResamplePlanDestroy(dalib200ResamplePlan *p) {
+  if (!p) return DALIB200_SUCCESS;
+  if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
+  p->desc_arena.Free(); p->table_arena.Free();
+  delete p;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200ResamplePlanGetOrder(const dalib200ResamplePlan *p, int sample) {
+  if (!p || sample < 0 || sample >= p->n) return -1;
+  return p->order0[sample];
+}
+
+int dalib200ResamplePlanSetup(dalib200ResamplePlan *p, int n, const dalib200ResampleSample *samples, int in_dtype, int out_dtype) {
+  DB_CHECK_ARG(p && samples && n >= 0, "ResamplePlanSetup: null argument");
+  DB_CHECK_ARG(n <= p->max_batch, "ResamplePlanSetup: batch %d exceeds plan capacity %d", n, p->max_batch);
+  DB_CHECK_ARG((in_dtype == DALIB200_UINT8 && (out_dtype == DALIB200_UINT8 || out_dtype == DALIB200_FLOAT)) ||
+               (in_dtype == DALIB200_FLOAT && out_dtype == DALIB200_FLOAT),
+               "Resize: unsupported type combination in=%d out=%d (u8->u8, u8->f32, f32->f32)", in_dtype, out_dtype);
+  p->descs.assign(n, RsDesc());
+  p->order0.assign(n, 0);
+  p->tables.clear();
+  p->cache.clear();
+  int64_t tiles = 0;
+  for (int i = 0; i < n; i++) {
+    const auto &s = samples[i];
+    DB_CHECK_ARG(s.in_h > 0 && s.in_w > 0 && s.channels >= 1 && s.channels <= 16,
+                 "Resize: sample %d has unsupported input shape %dx%dx%d", i, s.in_h, s.in_w, s.channels);
+    DB_CHECK_ARG(s.out_h >= 0 && s.out_w >= 0, "Resize: sample %d has negative output size", i);
+    RsDesc &d = p->descs[i];
+    memset(&d, 0, sizeof(d));
+    d.in_h = s.in_h; d.in_w = s.in_w; d.C = s.channels; d.out_h = s.out_h; d.out_w = s.out_w;
+    d.flags_off = -1; d.simd_flat_end = 0;
+    d.first_tile = tiles;
+    d.tile_h = d.tile_w = 1; d.tiles_x = d.tiles_y = 0;
+    if (s.out_h == 0 || s.out_w == 0) continue;
+    AxisSetup ax[2];
+    // axis 0 = x <- params index 1 ; axis 1 = y <- params index 0
+    SetupAxis(ax[0], s.in_w, s.out_w, s.use_roi[1] != 0, s.roi_start[1], s.roi_end[1], s.min_filter[1], s.mag_filter[1]);
+    SetupAxis(ax[1], s.in_h, s.out_h, s.use_roi[0] != 0, s.roi_start[0], s.roi_end[0], s.min_filter[0], s.mag_filter[0]);
+    const int first = ProcessingOrder(ax);
+    p->order0[i] = first;
+    d.vfirst = first == 1;
+    for (int a = 0; a < 2; a++) {
+      if (a != first) {          // cropped to the filter footprint, origin moved (setup.cc:323-336)
+        ax[a].origin -= ax[a].roi_lo;
+        ax[a].base = ax[a].roi_lo; ax[a].extent = ax[a].roi_hi - ax[a].roi_lo;
+      } else {
+        ax[a].base = 0; ax[a].extent = ax[a].in_size;
+      }
+      DB_CHECK_ARG(ax[a].extent > 0, "Resize: sample %d has an empty region of interest", i);
+      TableKey key{ ax[a].in_size, ax[a].out_size, ax[a].ftype * 2 + a, ax[a].base, ax[a].extent, fbits(ax[a].origin),
+                    fbits(ax[a].scale), fbits(ax[a].filter.scale), fbits(ax[a].filter.anchor) };
+      auto it = p->cache.find(key);
+      AxisTableRef ref;
+      if (it == p->cache.end()) {
+        BuildTable(p->tables, ref, ax[a], a);
+        p->cache[key] = ref;
+      } else {
+        ref = it->second;
+      }
+      d.idx_off[a] = ref.idx_off; d.coef_off[a] = ref.coef_off; d.support[a] = ref.support;
+      d.base[a] = ax[a].base; d.extent[a] = ax[a].extent;
+    }
+    if (out_dtype == DALIB200_UINT8) {
+      if (first == 1) {   // horizontal pass is last
+        if (ax[0].ftype != DALIB200_FILTER_NN)
+          d.flags_off = BuildHorzFlags(p->tables, d.idx_off[0], s.out_w, ax[0].extent, d.support[0]);
+      } else {            // vertical pass is last: SSE over flat_w in groups of 16 (cpu.h:95-124,362-390)
+        if (ax[1].ftype != DALIB200_FILTER_NN) d.simd_flat_end = (s.out_w * s.channels / 16) * 16;
+      }
+    }
+    // ---- tiling: the fp32 intermediate of a tile must fit kTmpFloats
+    const int C = s.channels;
+    const int32_t *ix = p->tables.data() + d.idx_off[0], *iy = p->tables.data() + d.idx_off[1];
+    auto span_of = [](const int32_t *idx, int o0, int cnt, int S, int extent) {
+      int a = idx[o0], b = idx[o0 + cnt - 1];
+      int lo = std::min(std::max(std::min(a, b), 0), extent - 1);
+      int hi = std::min(std::max(std::max(a, b) + S - 1, 0), extent - 1);
+      return hi - lo + 1;
+    };
+    auto max_span = [&](const int32_t *idx, int out, int t, int S, int extent) {
+      int m = 0;
+      for (int o = 0; o < out; o += t) m = std::max(m, span_of(idx, o, std::min(t, out - o), S, extent));
+      return m;
+    };
+    int th, tw;
+    bool fits = false;
+    if (d.vfirst) {
+      tw = s.out_w; th = 0;
+      for (;;) {
+        int span = max_span(ix, s.out_w, tw, d.support[0], d.extent[0]);
+        th = std::min({ kTmpFloats / std::max(1, span * C), 32, s.out_h });
+        if (th >= std::min(8, s.out_h) || tw == 1) { fits = th >= 1; break; }
+        tw = (tw + 1) / 2;
+      }
+    } else {
+      th = std::min(s.out_h, 32); tw = 0;
+      for (;;) {
+        int span = max_span(iy, s.out_h, th, d.support[1], d.extent[1]);
+        tw = std::min(kTmpFloats / std::max(1, span * C), s.out_w);
+        if (tw >= std::min(16, s.out_w) || th == 1) { fits = tw >= 1; break; }
+        th = (th + 1) / 2;
+      }
+    }
+    if (!fits) {
+      SetLastError("Resize: sample %d: filter footprint (%d x %d taps, %d channels) does not fit the on-chip tile",
+                   i, d.support[0], d.support[1], C);
+      return DALIB200_ERROR_UNSUPPORTED;
+    }
+    d.tile_h = th; d.tile_w = tw;
+    d.tiles_x = (s.out_w + tw - 1) / tw; d.tiles_y = (s.out_h + th - 1) / th;
+    tiles += (int64_t)d.tiles_x * d.tiles_y;
+  }
+  p->n = n; p->in_dtype = in_dtype; p->out_dtype = out_dtype; p->total_tiles = tiles;
+  // identical tables (the common fixed-size case) are not uploaded again
+  p->tables_dirty = p->tables != p->uploaded_tables;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200ResampleLaunch(dalib200ResamplePlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+  DB_CHECK_ARG(p && in_ptrs && out_ptrs, "ResampleLaunch: null argument");
+  if (p->n == 0 || p->total_tiles == 0) return DALIB200_SUCCESS;
+  if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
+  int rc = p->desc_arena.Reserve(sizeof(RsDesc) * p->n);
+  if (rc) return rc;
+  auto *hd = reinterpret_cast<RsDesc *>(p->desc_arena.host);
+  for (int i = 0; i < p->n; i++) {
+    hd[i] = p->descs[i];
+    hd[i].in = in_ptrs[i];
+    hd[i].out = out_ptrs[i];
+  }
+  rc = p->desc_arena.Upload(sizeof(RsDesc) * p->n, stream);
+  if (rc) return rc;
+  if (p->tables_dirty) {
+    size_t bytes = p->tables.size() * sizeof(int32_t);
+    rc = p->table_arena.Reserve(bytes);
+    if (rc) return rc;
+    memcpy(p->table_arena.host, p->tables.data(), bytes);
+    rc = p->table_arena.Upload(bytes, stream);
+    if (rc) return rc;
+    p->uploaded_tables = p->tables;
+    p->tables_dirty = false;
+  }
+  DB_CUDA(cudaEventRecord(p->uploaded, stream));
+  p->pending = true;
+  const auto *dd = reinterpret_cast<const RsDesc *>(p->desc_arena.dev);
+  const auto *tb = reinterpret_cast<const int32_t *>(p->table_arena.dev);
+  const int smem = kTmpFloats * sizeof(float);
+  int grid = (int)std::min<int64_t>(p->total_tiles, (int64_t)NumSMs() * 2 * 8);
+  auto launch = [&](auto kern, int slot) -> int {
+    if (!p->smem_opted[slot]) {
+      DB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      p->smem_opted[slot] = true;
+    }
+    kern<<<grid, 256, smem, stream>>>(dd, tb, p->n, p->total_tiles);
+    return DALIB200_SUCCESS;
+  };
+  if (p->in_dtype == DALIB200_UINT8 && p->out_dtype == DALIB200_UINT8) rc = launch(resample_fused_kernel<uint8_t, uint8_t>, 0);
+  else if (p->in_dtype == DALIB200_UINT8) rc = launch(resample_fused_kernel<uint8_t, float>, 1);
+  else rc = launch(resample_fused_kernel<float, float>, 2);
+  if (rc) return rc;
+  CountLaunch();
+  DB_CUDA(cudaGetLastError());
+  return DALIB200_SUCCESS;
+}
+
+}  // extern "C"

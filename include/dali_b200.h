@@ -1,0 +1,217 @@
+/*
+ * include/dali_b200.h -- the thin C-ABI under the reference's operator boundary.
+ *
+ * Every hot-path kernel family is exposed as   plan create -> plan setup (host, per batch: shapes and
+ * per-sample arguments) -> launch (enqueue on a caller stream, no host sync) -> plan destroy.
+ * POD arguments only, caller owns every data buffer, the callee owns the plan and its pinned /
+ * device descriptor arena.  Non-zero return = error; dalib200GetLastError() returns a thread-local
+ * message (conventions follow the reference's C API: include/dali/dali.h:43-164).
+ *
+ * The reference has no such ABI (its kernels are C++ templates: Setup()/Run(ctx,out,in,args),
+ * dali/kernels/kernel.h); each entry point below names the reference interface it replaces.
+ * The C++ operators in dali_b200/host (Operator<GPUBackend>::SetupImpl / RunImpl, reference
+ * dali/pipeline/operator/operator.h:117-123) call PlanSetup from SetupImpl and Launch from RunImpl.
+ */
+#ifndef DALI_B200_H_
+#define DALI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *dalib200Stream_t;   /* == cudaStream_t */
+
+/* Data type ids equal the reference's DALIDataType (include/dali/core/dali_data_type.h:44-57). */
+enum { DALIB200_UINT8 = 0, DALIB200_INT16 = 3, DALIB200_FLOAT16 = 8, DALIB200_FLOAT = 9 };
+/* Image types equal DALIImageType (include/dali/core/common.h:156-162). */
+enum { DALIB200_RGB = 0, DALIB200_BGR = 1, DALIB200_GRAY = 2, DALIB200_YCbCr = 3 };
+/* Resampling filters equal kernels::ResamplingFilterType (dali/kernels/imgproc/resample/params.h:27-34). */
+enum { DALIB200_FILTER_NN = 0, DALIB200_FILTER_LINEAR = 1, DALIB200_FILTER_TRIANGULAR = 2,
+       DALIB200_FILTER_GAUSSIAN = 3, DALIB200_FILTER_CUBIC = 4, DALIB200_FILTER_LANCZOS3 = 5 };
+enum { DALIB200_LAYOUT_HWC = 0, DALIB200_LAYOUT_CHW = 1 };
+
+enum {
+  DALIB200_SUCCESS = 0,
+  DALIB200_ERROR_INVALID_ARGUMENT = 1,
+  DALIB200_ERROR_UNSUPPORTED = 2,
+  DALIB200_ERROR_CUDA = 3,
+  DALIB200_ERROR_BAD_DATA = 4,
+  DALIB200_ERROR_INTERNAL = 5
+};
+
+const char *dalib200GetLastError(void);
+int dalib200GetVersion(void);
+/* number of kernels this library has launched from the calling process (bench.py's gpu_launches) */
+uint64_t dalib200GetLaunchCount(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * JPEG decode (Huffman + dequant + IDCT + chroma upsampling + YCbCr->RGB), baseline sequential.
+ * Replaces: imgcodec::ImageDecoder<MixedBackend>::RunImplImpl -> nvimgcodecDecoderDecode
+ *           (dali/operators/imgcodec/image_decoder.h:613-882) and ParseSample (:473-499).
+ * Host work: marker/table parse only.  Device work: everything arithmetic. */
+typedef struct dalib200JpegPlan dalib200JpegPlan;
+
+typedef struct {
+  int32_t width, height;        /* decoded image size */
+  int32_t components;           /* 1 or 3 */
+  int32_t subsampling;          /* (hmax<<4)|vmax of the luma sampling factors, e.g. 0x22 = 4:2:0 */
+  int32_t restart_interval;
+  int32_t orientation;          /* EXIF orientation, 1 = none */
+} dalib200JpegInfo;
+
+/* header-only parse: the analogue of nvimgcodecCodeStreamGetImageInfo (image_decoder.h:482) */
+int dalib200JpegGetInfo(const uint8_t *data, size_t len, dalib200JpegInfo *info);
+
+int dalib200JpegPlanCreate(dalib200JpegPlan **plan, int max_batch);
+int dalib200JpegPlanDestroy(dalib200JpegPlan *plan);
+/* Parses n encoded streams (host pointers), builds the per-sample descriptors and packs the
+ * entropy-coded segments into the plan's pinned staging buffer.  Output shapes via ...GetInfo().
+ * fancy_upsampling != 0 selects libjpeg "fancy" (triangle) chroma upsampling -- the reference CPU
+ * backend's behaviour; 0 = box replication. */
+int dalib200JpegPlanSetup(dalib200JpegPlan *plan, int n, const uint8_t *const *streams, const size_t *lengths,
+                          int output_type /* DALIB200_RGB | BGR | GRAY | YCbCr */, int fancy_upsampling);
+int dalib200JpegPlanGetInfo(const dalib200JpegPlan *plan, int sample, dalib200JpegInfo *info);
+/* Bytes of packed entropy-coded data + tables staged for the batch (the H2D payload). */
+size_t dalib200JpegPlanStagedBytes(const dalib200JpegPlan *plan);
+/* H2D copy of the staged batch (async on stream).  Split from Launch so that a caller can time the
+ * device-resident decode separately from the transfer. */
+int dalib200JpegUpload(dalib200JpegPlan *plan, dalib200Stream_t stream);
+/* Enqueues the decode of the uploaded batch; out_ptrs[i] -> device buffer H*W*C u8 (HWC). */
+int dalib200JpegLaunch(dalib200JpegPlan *plan, void *const *out_ptrs, dalib200Stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Separable resampling (fused two-pass).  Replaces kernels::ResampleGPU / SeparableResamplingGPUImpl::Run
+ * (dali/kernels/imgproc/resample/separable_impl.h:110-203) and BatchResamplingSetup::SetupBatch
+ * (resampling_setup.cc:347-418); numerics follow the CPU kernel SeparableResampleCPU
+ * (separable_cpu.h:124-249) -- the parity target. */
+typedef struct dalib200ResamplePlan dalib200ResamplePlan;
+
+typedef struct { int32_t type; int32_t antialias; float radius; } dalib200FilterDesc;
+
+typedef struct {
+  int32_t in_h, in_w, channels;
+  int32_t out_h, out_w;
+  /* index [0] = vertical (y), [1] = horizontal (x): the reference's ResamplingParams2D order */
+  int32_t use_roi[2];
+  float roi_start[2], roi_end[2];
+  dalib200FilterDesc min_filter[2], mag_filter[2];
+} dalib200ResampleSample;
+
+int dalib200ResamplePlanCreate(dalib200ResamplePlan **plan, int max_batch);
+int dalib200ResamplePlanDestroy(dalib200ResamplePlan *plan);
+int dalib200ResamplePlanSetup(dalib200ResamplePlan *plan, int n, const dalib200ResampleSample *samples,
+                              int in_dtype /* UINT8 | FLOAT */, int out_dtype /* UINT8 | FLOAT */);
+/* in_ptrs[i]: device HWC in_dtype; out_ptrs[i]: device HWC out_dtype [out_h][out_w][channels] */
+int dalib200ResampleLaunch(dalib200ResamplePlan *plan, const void *const *in_ptrs, void *const *out_ptrs,
+                           dalib200Stream_t stream);
+/* introspection used by the tests: processing order chosen for a sample (0 = horizontal pass first) */
+int dalib200ResamplePlanGetOrder(const dalib200ResamplePlan *plan, int sample);
+
+/* ------------------------------------------------------------------------------------------------
+ * CropMirrorNormalize.  Replaces kernels::SliceHwc2HwcChwNormalizeGPU::Run
+ * (dali/kernels/slice/slice_hwc2chw_normalize_gpu.cu:863-1020) and the generic SliceFlipNormalize kernels;
+ * numerics follow SliceFlipNormalizePermutePadCpu (slice_flip_normalize_permute_pad_cpu.h:37-46). */
+typedef struct dalib200CmnPlan dalib200CmnPlan;
+
+typedef struct {
+  int32_t in_h, in_w, channels;              /* u8 HWC input */
+  int32_t anchor_y, anchor_x, crop_h, crop_w;/* window in input coordinates; may leave the image (padding) */
+  int32_t mirror;                            /* flip the cropped window horizontally */
+  float mean[4], inv_std[4], fill[4];        /* per OUTPUT channel */
+} dalib200CmnSample;
+
+int dalib200CmnPlanCreate(dalib200CmnPlan **plan, int max_batch);
+int dalib200CmnPlanDestroy(dalib200CmnPlan *plan);
+int dalib200CmnPlanSetup(dalib200CmnPlan *plan, int n, const dalib200CmnSample *samples,
+                         int out_dtype /* FLOAT | FLOAT16 */, int out_layout /* HWC | CHW */, int out_channels);
+int dalib200CmnLaunch(dalib200CmnPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * WarpAffine.  Replaces kernels::WarpGPU<AffineMapping2D,...> (dali/kernels/imgproc/warp_gpu.h,
+ * warp/warp_variable_size_impl.cuh:31-42); numerics follow WarpCPU (warp_cpu.h:143-178) and
+ * Sampler (sampler.h:122-330). */
+typedef struct dalib200WarpPlan dalib200WarpPlan;
+
+typedef struct {
+  int32_t in_h, in_w, channels;
+  int32_t out_h, out_w;
+  float matrix[6];            /* 2x3 row-major DESTINATION -> SOURCE map (already inverted if needed) */
+} dalib200WarpSample;
+
+int dalib200WarpPlanCreate(dalib200WarpPlan **plan, int max_batch);
+int dalib200WarpPlanDestroy(dalib200WarpPlan *plan);
+int dalib200WarpPlanSetup(dalib200WarpPlan *plan, int n, const dalib200WarpSample *samples,
+                          int interp /* NN | LINEAR */, int use_fill, float fill_value,
+                          int out_dtype /* UINT8 | FLOAT */);
+int dalib200WarpLaunch(dalib200WarpPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
+/* host helper: include/dali/core/geom/transform.h:166-174 */
+void dalib200AffineInverse(const float *m2x3, float *out2x3);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-pixel 3x3 linear colour transform (Hsv / ColorTwist) and colour-space conversion.
+ * Replaces kernels::LinearTransformationGpu (pointwise/linear_transformation_gpu.h:47-79) and
+ * ColorSpaceConvKernel (color_manipulation/color_space_conversion_kernel.cuh:139-211). */
+typedef struct dalib200PointwisePlan dalib200PointwisePlan;
+
+typedef struct {
+  int64_t num_pixels;
+  float matrix[9];          /* row-major 3x3 */
+  float offset[3];
+} dalib200ColorSample;
+
+int dalib200PointwisePlanCreate(dalib200PointwisePlan **plan, int max_batch);
+int dalib200PointwisePlanDestroy(dalib200PointwisePlan *plan);
+int dalib200LinearTransformSetup(dalib200PointwisePlan *plan, int n, const dalib200ColorSample *samples,
+                                 int out_dtype /* UINT8 | FLOAT */);
+int dalib200ColorSpaceSetup(dalib200PointwisePlan *plan, int n, const int64_t *num_pixels, int in_type, int out_type);
+int dalib200PointwiseLaunch(dalib200PointwisePlan *plan, const void *const *in_ptrs, void *const *out_ptrs,
+                            dalib200Stream_t stream);
+/* host helper: dali/operators/image/color/color_twist.h:50-83,156-170 */
+void dalib200ColorTwistMatrix(float hue, float saturation, float value, float brightness, float contrast,
+                              float half_range, float *m3x3, float *offset3);
+
+/* ------------------------------------------------------------------------------------------------
+ * Spectrogram (window extraction + FFT + |X|^p) and MelFilterBank.
+ * Replaces kernels::signal::fft::StftGPU (dali/kernels/signal/fft/stft_gpu_impl.cu:200-294, cuFFT) and
+ * kernels::audio::MelFilterBankGpu (audio/mel_scale/mel_filter_bank_gpu.cu:76-261). */
+typedef struct dalib200SpectrogramPlan dalib200SpectrogramPlan;
+
+typedef struct {
+  int32_t nfft, window_length, window_step;
+  int32_t power;             /* 1 = magnitude, 2 = power */
+  int32_t center, reflect;   /* center_windows / reflect_padding */
+  int32_t layout_ft;         /* 1: [freq][time] (default "ft"), 0: [time][freq] */
+} dalib200SpectrogramArgs;
+
+int dalib200SpectrogramPlanCreate(dalib200SpectrogramPlan **plan, int max_batch);
+int dalib200SpectrogramPlanDestroy(dalib200SpectrogramPlan *plan);
+/* window_fn: host pointer to window_length floats, or NULL for the reference's Hann window */
+int dalib200SpectrogramPlanSetup(dalib200SpectrogramPlan *plan, const dalib200SpectrogramArgs *args,
+                                 const float *window_fn, int n, const int64_t *lengths);
+int64_t dalib200SpectrogramNumWindows(const dalib200SpectrogramPlan *plan, int sample);
+int dalib200SpectrogramLaunch(dalib200SpectrogramPlan *plan, const void *const *in_ptrs, void *const *out_ptrs,
+                              dalib200Stream_t stream);
+void dalib200HannWindow(float *out, int n);
+
+typedef struct dalib200MelPlan dalib200MelPlan;
+
+typedef struct {
+  int32_t nfilter;
+  float sample_rate, freq_low, freq_high;
+  int32_t htk;               /* mel_formula == "htk" */
+  int32_t normalize;
+} dalib200MelArgs;
+
+int dalib200MelPlanCreate(dalib200MelPlan **plan, int max_batch);
+int dalib200MelPlanDestroy(dalib200MelPlan *plan);
+/* input spectrograms are [nbin][nwin[i]] f32 ("ft"); outputs [nfilter][nwin[i]] */
+int dalib200MelPlanSetup(dalib200MelPlan *plan, const dalib200MelArgs *args, int nbin, int n, const int64_t *nwin);
+int dalib200MelLaunch(dalib200MelPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DALI_B200_H_ */

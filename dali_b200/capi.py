@@ -21,6 +21,7 @@ EXPORTS = [
     "dalib200GetLastError", "dalib200GetVersion", "dalib200GetLaunchCount",
     "dalib200JpegGetInfo", "dalib200JpegPlanCreate", "dalib200JpegPlanDestroy", "dalib200JpegPlanSetup",
     "dalib200JpegPlanGetInfo", "dalib200JpegPlanStagedBytes", "dalib200JpegUpload", "dalib200JpegLaunch",
+    "dalib200JpegGetStatus", "dalib200JpegDebugGetCoefficients",
     "dalib200ResamplePlanCreate", "dalib200ResamplePlanDestroy", "dalib200ResamplePlanSetup", "dalib200ResampleLaunch",
     "dalib200ResamplePlanGetOrder",
     "dalib200CmnPlanCreate", "dalib200CmnPlanDestroy", "dalib200CmnPlanSetup", "dalib200CmnLaunch",

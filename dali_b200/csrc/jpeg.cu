@@ -1,0 +1,1221 @@
+// dali_b200/csrc/jpeg.cu -- baseline JPEG decode on sm_100a: Huffman + dequant + IDCT + upsample + colour.
+//
+// Replaces the reference's mixed-backend image decoder (dali/operators/imgcodec/image_decoder.h:613-882), whose
+// arithmetic lives in nvImageCodec / nvJPEG / libjpeg-turbo (not in the reference tree).  Parity target =
+// the reference CPU backend = libjpeg-turbo defaults: islow integer IDCT, "fancy" (triangle) chroma
+// upsampling (image_decoder.h:297-304: CPU always fancy), fixed-point YCbCr->RGB; oracle/jpeg_oracle.c
+// restates it and is pinned bit-exactly against cv2.imdecode.
+//
+// Host (PlanSetup): marker / table parse only (ITU-T T.81 Annex B), packing of the entropy-coded
+// segments into pinned staging.  Everything else runs on the device:
+//   U1/U2/U3  byte un-stuffing (FF 00 -> FF) of every entropy-coded segment into a clean, word-swapped stream
+//   H1        speculative Huffman decode of 2^k-byte subsequences + intra-block self-synchronisation
+//   H2        inter-block synchronisation, per-segment exclusive scan of the coefficient counts
+//   H3        final decode pass writing quantised coefficients (natural order, DC still differential)
+//   D1        DC prediction (prefix sum per component, reset at restart intervals)
+//   I1        dequantisation + islow IDCT -> planar component samples
+//   C1        chroma upsampling (fancy / box) + colour conversion -> interleaved HWC u8
+// The parallel entropy decode follows the self-synchronising scheme of Weissenberger & Schmidt
+// ("Accelerating JPEG decompression on GPUs", 2021): a decoder started at a wrong bit position
+// re-synchronises with the true symbol sequence after a few symbols, so every subsequence is first
+// decoded speculatively and the exit states are then chained until they agree.
+//
+// Algorithmic bytes per unit: J (encoded bytes) + H*W*3 (decoded image).
+#include "common.cuh"
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <thread>
+
+namespace dalib200 {
+
+constexpr int kLutBits = 10;                 // first-level Huffman lookup width
+constexpr int kLutSize = 1 << kLutBits;
+constexpr int kSyncThreads = 128;            // subsequences per synchronisation block
+constexpr int kChunkBytes = 4096;            // un-stuffing chunk
+constexpr int kMaxBlocksPerMcu = 10;
+
+// One Huffman table as the device sees it.
+struct HuffTable {
+  uint16_t lut[kLutSize];     // (len << 8) | symbol for codes of length <= kLutBits, 0 otherwise
+  int32_t maxcode[18];        // T.81 F.2.2.3: maxcode[l] left-aligned to 16 bits (+1), for the slow path
+  int32_t valoff[18];         // valptr[l] - mincode[l]
+  uint8_t vals[256];
+};
+
+struct TableSet {             // the 4 tables a baseline scan can reference: DC0, DC1, AC0, AC1
+  HuffTable t[4];
+};
+
+struct QuantSet { uint16_t q[4][64]; };       // natural order
+
+struct JpegImage {
+  uint8_t *out;               // HWC u8
+  int32_t width, height, ncomp;
+  int32_t hs[3], vs[3], hmax, vmax;
+  int32_t mcux, mcuy, bpm;    // MCUs per row / column, blocks per MCU
+  int32_t blk_comp[kMaxBlocksPerMcu];      // component of each block in the MCU
+  int32_t blk_dc[kMaxBlocksPerMcu], blk_ac[kMaxBlocksPerMcu];   // table index (0..3) into TableSet
+  int32_t blk_x[kMaxBlocksPerMcu], blk_y[kMaxBlocksPerMcu];     // block offset inside the MCU (in blocks)
+  int32_t tq[3];
+  int32_t restart_interval;
+  int32_t table_set, quant_set;
+  int32_t unit_begin, unit_end;            // segments (restart intervals or the whole scan)
+  int32_t subseq_begin;                    // first global subsequence
+  int32_t nsub;                            // upper bound of subsequences (from raw length)
+  int32_t block_begin;                     // first sync block
+  int64_t coef_off;                        // int16 offset into the coefficient arena
+  int64_t plane_off[3];                    // byte offsets into the plane arena
+  int32_t plane_w[3], plane_h[3];          // padded plane sizes (multiples of the MCU)
+  int32_t out_type, fancy;
+  int32_t is_rgb;                          // Adobe transform 0 / RGB ids: no YCbCr conversion
+};
+
+struct JpegUnit {
+  uint32_t raw_off, raw_len;               // in the staged byte buffer
+  uint32_t clean_off;                      // in the clean buffer (bytes, 16-aligned)
+  uint32_t first_chunk;                    // global chunk index
+  int32_t image;
+  int32_t first_subseq;                    // image-local
+  int32_t nsub_max;
+  int64_t slot_base;                       // first coefficient slot of this unit (image-local)
+  int64_t nslots;                          // expected number of slots (= MCUs * bpm * 64)
+};
+
+__constant__ uint8_t c_zigzag[64] = {
+   0,  1,  8, 16,  9,  2,  3, 10, 17, 24, 32, 25, 18, 11,  4,  5,
+  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,  6,  7, 14, 21, 28,
+  35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+  58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
+
+// ============================================================================================
+// U1..U3: byte un-stuffing
+__device__ __forceinline__ int find_unit_by_chunk(const JpegUnit *u, int n, uint32_t chunk) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (u[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// a byte is dropped when it is the 0x00 that follows a 0xFF
+__device__ __forceinline__ bool dropped(const uint8_t *raw, uint32_t off, uint32_t i) {
+  return i > 0 && raw[off + i] == 0x00 && raw[off + i - 1] == 0xFF;
+}
+
+__global__ void __launch_bounds__(256) unstuff_count_kernel(const uint8_t *__restrict__ raw, const JpegUnit *__restrict__ units,
+                                                            int nunits, uint32_t nchunks, uint32_t *__restrict__ chunk_cnt) {
+  __shared__ int wsum[8];
+  for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int ui = find_unit_by_chunk(units, nunits, chunk);
+    const JpegUnit &u = units[ui];
+    const uint32_t c0 = (chunk - u.first_chunk) * kChunkBytes;
+    const uint32_t len = min((uint32_t)kChunkBytes, u.raw_len - c0);
+    int cnt = 0;
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) cnt += dropped(raw, u.raw_off, c0 + i) ? 1 : 0;
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 8; w++) s += wsum[w]; chunk_cnt[chunk] = (uint32_t)s; }
+    __syncthreads();
+  }
+}
+
+// one thread per unit: exclusive scan of the dropped-byte counts of its chunks (units are short lists)
+__global__ void unstuff_scan_kernel(const JpegUnit *__restrict__ units, int nunits, uint32_t *__restrict__ chunk_cnt,
+                                    uint32_t *__restrict__ unit_clean_len) {
+  for (int ui = blockIdx.x * blockDim.x + threadIdx.x; ui < nunits; ui += gridDim.x * blockDim.x) {
+    const JpegUnit &u = units[ui];
+    const uint32_t nch = (u.raw_len + kChunkBytes - 1) / kChunkBytes;
+    uint32_t run = 0;
+    for (uint32_t c = 0; c < nch; c++) { uint32_t v = chunk_cnt[u.first_chunk + c]; chunk_cnt[u.first_chunk + c] = run; run += v; }
+    unit_clean_len[ui] = u.raw_len - run;
+  }
+}
+
+// Writes the clean stream with every 32-bit word byte-swapped (address ^ 3), so that a plain 32-bit
+// load returns the big-endian bit order the Huffman reader wants.
+__global__ void __launch_bounds__(256) unstuff_scatter_kernel(const uint8_t *__restrict__ raw, const JpegUnit *__restrict__ units,
+                                                              int nunits, uint32_t nchunks, const uint32_t *__restrict__ chunk_drop,
+                                                              uint8_t *__restrict__ clean) {
+  __shared__ int wsum[8];
+  __shared__ int carry_s;
+  for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int ui = find_unit_by_chunk(units, nunits, chunk);
+    const JpegUnit &u = units[ui];
+    const uint32_t c0 = (chunk - u.first_chunk) * kChunkBytes;
+    const uint32_t len = min((uint32_t)kChunkBytes, u.raw_len - c0);
+    uint32_t out_base = u.clean_off + c0 - chunk_drop[chunk];
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < len; base += blockDim.x * 4) {
+      // each thread owns 4 consecutive bytes
+      const uint32_t i0 = base + threadIdx.x * 4;
+      uint8_t b[4]; bool keep[4]; int nk = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t i = i0 + k;
+        keep[k] = false;
+        if (i < len) { b[k] = raw[u.raw_off + c0 + i]; keep[k] = !dropped(raw, u.raw_off, c0 + i); nk += keep[k]; }
+      }
+      int incl = nk;
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += v; }
+      if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+      __syncthreads();
+      int woff = 0, tot = 0;
+      for (int w = 0; w < 8; w++) { if (w < (int)(threadIdx.x >> 5)) woff += wsum[w]; tot += wsum[w]; }
+      uint32_t pos = out_base + carry_s + woff + incl - nk;
+#pragma unroll
+      for (int k = 0; k < 4; k++) if (keep[k]) { clean[(pos & ~3u) | (3u - (pos & 3u))] = b[k]; pos++; }
+      __syncthreads();
+      if (threadIdx.x == 0) carry_s += tot;
+      __syncthreads();
+    }
+  }
+}
+
+// ============================================================================================
+// Huffman decoding
+struct BitReader {
+  const uint32_t *words;    // clean stream (word-swapped), 16-byte aligned, padded
+  __device__ __forceinline__ uint32_t peek32(uint32_t p) const {
+    const uint32_t wi = p >> 5, sh = p & 31;
+    const uint32_t w0 = __ldg(words + wi), w1 = __ldg(words + wi + 1);
+    return __funnelshift_l(w1, w0, sh);          // next 32 bits, MSB first
+  }
+};
+
+struct DecState { uint32_t p; int c; int z; uint32_t n; };
+
+__device__ __forceinline__ uint64_t pack_state(uint32_t p, int c, int z) {
+  return (uint64_t)p | ((uint64_t)(uint32_t)c << 32) | ((uint64_t)(uint32_t)z << 40);
+}
+
+// Decodes symbols that START before end_bit.  When WRITE, stores coefficients (natural order inside the block)
+// at slot indices slot0 + n; never writes at or beyond slot_limit.
+template <bool WRITE>
+__device__ __forceinline__ void decode_range(const BitReader &br, const TableSet *__restrict__ ts, const JpegImage &im,
+                                             DecState &st, uint32_t end_bit, int16_t *__restrict__ coef, int64_t slot0,
+                                             int64_t slot_limit) {
+  uint32_t p = st.p; int c = st.c, z = st.z; uint32_t n = st.n;
+  const int bpm = im.bpm;
+  while (p < end_bit) {
+    if (WRITE && slot0 + n >= slot_limit) break;
+    const HuffTable &ht = ts->t[z == 0 ? im.blk_dc[c] : im.blk_ac[c]];
+    const uint32_t w = br.peek32(p);
+    uint32_t e = ht.lut[w >> (32 - kLutBits)];
+    uint32_t len = e >> 8, sym = e & 0xFF;
+    if (len == 0) {                                  // slow path: codes longer than kLutBits
+      const int32_t code16 = (int32_t)(w >> 16);
+      len = kLutBits + 1;
+      while (len <= 16 && code16 >= ht.maxcode[len]) len++;
+      if (len > 16) { len = 16; sym = 0; }
+      else sym = ht.vals[(ht.valoff[len] + (code16 >> (16 - len))) & 0xFF];
+    }
+    int s;
+    if (z == 0) {
+      s = sym & 15;
+    } else {
+      const int r = sym >> 4;
+      s = sym & 15;
+      if (s == 0) {
+        p += len;
+        if (r == 15) { z += 16; n += 16; }
+        else { n += 64 - z; z = 64; }
+        if (z >= 64) { z = 0; c = c + 1 == bpm ? 0 : c + 1; }
+        continue;
+      }
+      z += r; n += r;
+      if (z > 63) { n -= (z - 63); z = 63; }         // corrupt / speculative: stay inside the block
+    }
+    int v = 0;
+    if (s) {
+      // code (<=16 bits) + magnitude (<=11 valid, <=15 possible) may exceed the 32-bit window: refetch
+      const uint32_t w2 = (len + s > 32) ? br.peek32(p + len) : (w << len);
+      const int bits = (int)(w2 >> (32 - s));
+      v = bits < (1 << (s - 1)) ? bits - (1 << s) + 1 : bits;
+    }
+    p += len + s;
+    if (WRITE && slot0 + n < slot_limit) {
+      const int64_t slot = slot0 + n;
+      coef[(slot & ~(int64_t)63) | c_zigzag[z]] = (int16_t)v;
+    }
+    z++; n++;
+    if (z >= 64) { z = 0; c = c + 1 == bpm ? 0 : c + 1; }
+  }
+  st.p = p; st.c = c; st.z = z; st.n = n;
+}
+
+__device__ __forceinline__ int find_image_by_block(const JpegImage *im, int n, int blk) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (im[mid].block_begin <= blk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+__device__ __forceinline__ int find_unit_by_subseq(const JpegUnit *u, int ub, int ue, int j) {
+  int lo = ub, hi = ue - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (u[mid].first_subseq <= j) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+struct HuffCtx {
+  const JpegImage *images; int nimages;
+  const JpegUnit *units;
+  const uint32_t *unit_clean_len;
+  const TableSet *tables;
+  const uint8_t *clean;
+  uint64_t *s_state; uint32_t *s_n;
+  int16_t *coef;
+  int log2_sub;            // log2 of the subsequence size in BITS
+  int32_t *status;         // per image: 0 ok, 1 = slot count mismatch (corrupt stream)
+};
+
+// H1: every thread decodes its own subsequence speculatively, then the exit states are chained inside the block.
+__global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx cx) {
+  __shared__ TableSet ts;
+  const int img_i = find_image_by_block(cx.images, cx.nimages, blockIdx.x);
+  const JpegImage &im = cx.images[img_i];
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(cx.tables + im.table_set);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&ts);
+    for (int i = threadIdx.x; i < (int)(sizeof(TableSet) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int j = (blockIdx.x - im.block_begin) * kSyncThreads + threadIdx.x;     // image-local subsequence
+  bool valid = j < im.nsub;
+  int ui = 0; uint32_t nsub_eff = 0, jl = 0, clean_bits = 0;
+  BitReader br{nullptr};
+  DecState st{0, 0, 0, 0};
+  const uint32_t sub_bits = 1u << cx.log2_sub;
+  if (valid) {
+    ui = find_unit_by_subseq(cx.units, im.unit_begin, im.unit_end, j);
+    const JpegUnit &u = cx.units[ui];
+    clean_bits = cx.unit_clean_len[ui] * 8u;
+    nsub_eff = (clean_bits + sub_bits - 1) >> cx.log2_sub;
+    jl = (uint32_t)(j - u.first_subseq);
+    valid = jl < nsub_eff;
+    br.words = reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off);
+  }
+  const int64_t g = (int64_t)im.subseq_begin + j;
+  if (valid) {
+    st.p = jl << cx.log2_sub;
+    decode_range<false>(br, &ts, im, st, min((jl + 1) << cx.log2_sub, clean_bits), nullptr, 0, 0);
+    cx.s_state[g] = pack_state(st.p, st.c, st.z);
+    cx.s_n[g] = st.n;
+  }
+  __syncthreads();
+  bool active = valid;
+  int t = 1;
+  while (__syncthreads_or(active)) {
+    if (active) {
+      const uint32_t nxt = jl + t;
+      if (nxt >= nsub_eff || threadIdx.x + t >= kSyncThreads) {
+        active = false;
+      } else {
+        st.n = 0;
+        decode_range<false>(br, &ts, im, st, min((nxt + 1) << cx.log2_sub, clean_bits), nullptr, 0, 0);
+        const uint64_t ns = pack_state(st.p, st.c, st.z);
+        if (cx.s_state[g + t] == ns) active = false;
+        else { cx.s_state[g + t] = ns; cx.s_n[g + t] = st.n; }
+        t++;
+      }
+    }
+  }
+}
+
+// H2: one CTA per image.  (a) chain the states across sync-block boundaries until nothing changes,
+// (b) per-unit exclusive scan of the slot counts.
+__global__ void __launch_bounds__(1024) huff_sync_inter_kernel(HuffCtx cx) {
+  __shared__ TableSet ts;
+  __shared__ int changed;
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t carry;
+  const JpegImage &im = cx.images[blockIdx.x];
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(cx.tables + im.table_set);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&ts);
+    for (int i = threadIdx.x; i < (int)(sizeof(TableSet) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  const uint32_t sub_bits = 1u << cx.log2_sub;
+  const int nblocks = (im.nsub + kSyncThreads - 1) / kSyncThreads;
+  for (int round = 0; round < nblocks + 1; round++) {
+    __syncthreads();
+    if (threadIdx.x == 0) changed = 0;
+    __syncthreads();
+    for (int b = 1 + threadIdx.x; b < nblocks; b += blockDim.x) {
+      const int j0 = b * kSyncThreads;
+      const int ui = find_unit_by_subseq(cx.units, im.unit_begin, im.unit_end, j0);
+      const JpegUnit &u = cx.units[ui];
+      if (u.first_subseq == j0) continue;                        // a unit starts here: true entry state known
+      const uint32_t clean_bits = cx.unit_clean_len[ui] * 8u;
+      const uint32_t nsub_eff = (clean_bits + sub_bits - 1) >> cx.log2_sub;
+      uint32_t jl = (uint32_t)(j0 - u.first_subseq);
+      if (jl >= nsub_eff) continue;
+      BitReader br{reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off)};
+      const int64_t g0 = (int64_t)im.subseq_begin + j0;
+      const uint64_t prev = cx.s_state[g0 - 1];
+      DecState st{(uint32_t)prev, (int)((prev >> 32) & 0xFF), (int)((prev >> 40) & 0xFF), 0};
+      bool synced = false;
+      for (int k = 0; k < kSyncThreads && jl + k < nsub_eff; k++) {
+        st.n = 0;
+        decode_range<false>(br, &ts, im, st, min((jl + k + 1) << cx.log2_sub, clean_bits), nullptr, 0, 0);
+        const uint64_t ns = pack_state(st.p, st.c, st.z);
+        if (cx.s_state[g0 + k] == ns) { synced = true; break; }
+        cx.s_state[g0 + k] = ns; cx.s_n[g0 + k] = st.n;
+      }
+      if (!synced) changed = 1;     // the exit state of this block moved: the next boundary must be redone
+    }
+    __syncthreads();
+    if (!changed) break;
+  }
+  // ---- exclusive scan of s_n per unit (in place)
+  for (int ui = im.unit_begin; ui < im.unit_end; ui++) {
+    const JpegUnit &u = cx.units[ui];
+    const uint32_t clean_bits = cx.unit_clean_len[ui] * 8u;
+    const uint32_t nsub_eff = (clean_bits + sub_bits - 1) >> cx.log2_sub;
+    const int64_t g0 = (int64_t)im.subseq_begin + u.first_subseq;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nsub_eff; base += blockDim.x) {
+      const uint32_t i = base + threadIdx.x;
+      const uint32_t v = i < nsub_eff ? cx.s_n[g0 + i] : 0u;
+      uint32_t incl = v;
+      for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += x; }
+      if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+      __syncthreads();
+      uint32_t woff = 0, tot = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) { if (w < (int)(threadIdx.x >> 5)) woff += warp_tot[w]; tot += warp_tot[w]; }
+      if (i < nsub_eff) cx.s_n[g0 + i] = carry + woff + incl - v;
+      __syncthreads();
+      if (threadIdx.x == 0) carry += tot;
+      __syncthreads();
+    }
+    // trailing pad bits may decode into a few extra symbols, so only a SHORT count is an error
+    if (threadIdx.x == 0 && (int64_t)carry < u.nslots) cx.status[blockIdx.x] = 1;
+  }
+}
+
+// H3: final pass -- every subsequence is decoded from its now-correct entry state and writes coefficients.
+__global__ void __launch_bounds__(kSyncThreads) huff_write_kernel(HuffCtx cx) {
+  __shared__ TableSet ts;
+  const int img_i = find_image_by_block(cx.images, cx.nimages, blockIdx.x);
+  const JpegImage &im = cx.images[img_i];
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(cx.tables + im.table_set);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&ts);
+    for (int i = threadIdx.x; i < (int)(sizeof(TableSet) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int j = (blockIdx.x - im.block_begin) * kSyncThreads + threadIdx.x;
+  if (j >= im.nsub) return;
+  const int ui = find_unit_by_subseq(cx.units, im.unit_begin, im.unit_end, j);
+  const JpegUnit &u = cx.units[ui];
+  const uint32_t sub_bits = 1u << cx.log2_sub;
+  const uint32_t clean_bits = cx.unit_clean_len[ui] * 8u;
+  const uint32_t nsub_eff = (clean_bits + sub_bits - 1) >> cx.log2_sub;
+  const uint32_t jl = (uint32_t)(j - u.first_subseq);
+  if (jl >= nsub_eff) return;
+  const int64_t g = (int64_t)im.subseq_begin + j;
+  DecState st{0, 0, 0, 0};
+  if (jl > 0) {
+    const uint64_t prev = cx.s_state[g - 1];
+    st.p = (uint32_t)prev; st.c = (int)((prev >> 32) & 0xFF); st.z = (int)((prev >> 40) & 0xFF);
+  }
+  BitReader br{reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off)};
+  int16_t *coef = cx.coef + im.coef_off;
+  decode_range<true>(br, &ts, im, st, min((jl + 1) << cx.log2_sub, clean_bits), coef, u.slot_base + cx.s_n[g],
+                     u.slot_base + u.nslots);
+}
+
+// ============================================================================================
+// D1: DC prediction.  One CTA per image; the blocks of each component are visited in scan order.
+__global__ void __launch_bounds__(1024) dc_scan_kernel(const JpegImage *__restrict__ images, int16_t *__restrict__ coef_arena) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const JpegImage &im = images[blockIdx.x];
+  int16_t *coef = coef_arena + im.coef_off;
+  const int nmcu = im.mcux * im.mcuy;
+  const int ri = im.restart_interval > 0 ? im.restart_interval : nmcu;
+  for (int comp = 0; comp < im.ncomp; comp++) {
+    // blocks of this component inside one MCU
+    int nb = 0, bidx[kMaxBlocksPerMcu];
+    for (int b = 0; b < im.bpm; b++) if (im.blk_comp[b] == comp) bidx[nb++] = b;
+    const int total = nmcu * nb;
+    if (ri >= nmcu) {
+      // single segment: block-wide inclusive scan
+      __syncthreads();
+      if (threadIdx.x == 0) carry = 0;
+      __syncthreads();
+      for (int base = 0; base < total; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        int64_t slot = 0; int v = 0;
+        if (i < total) { slot = ((int64_t)(i / nb) * im.bpm + bidx[i % nb]) * 64; v = coef[slot]; }
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += x; }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { if (w < (int)(threadIdx.x >> 5)) woff += warp_tot[w]; tot += warp_tot[w]; }
+        if (i < total) coef[slot] = (int16_t)(carry + woff + incl);
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+      }
+    } else {
+      // restart intervals: one thread per interval, sequential inside
+      const int nseg = (nmcu + ri - 1) / ri;
+      for (int sgi = threadIdx.x; sgi < nseg; sgi += blockDim.x) {
+        int pred = 0;
+        const int m1 = min(nmcu, (sgi + 1) * ri);
+        for (int m = sgi * ri; m < m1; m++)
+          for (int k = 0; k < nb; k++) {
+            const int64_t slot = ((int64_t)m * im.bpm + bidx[k]) * 64;
+            pred += coef[slot];
+            coef[slot] = (int16_t)pred;
+          }
+      }
+    }
+  }
+}
+
+// ============================================================================================
+// I1: dequantisation + islow IDCT (libjpeg jidctint: CONST_BITS 13, PASS1_BITS 2).  One thread per 8x8 block.
+#define FIX_0_298631336 2446
+#define FIX_0_390180644 3196
+#define FIX_0_541196100 4433
+#define FIX_0_765366865 6270
+#define FIX_0_899976223 7373
+#define FIX_1_175875602 9633
+#define FIX_1_501321110 12299
+#define FIX_1_847759065 15137
+#define FIX_1_961570560 16069
+#define FIX_2_053119869 16819
+#define FIX_2_562915447 20995
+#define FIX_3_072711026 25172
+
+template <int SHIFT>
+__device__ __forceinline__ void idct8(int i0, int i1, int i2, int i3, int i4, int i5, int i6, int i7, int *o) {
+  int z1, z2, z3, z4, z5, tmp0, tmp1, tmp2, tmp3, tmp10, tmp11, tmp12, tmp13;
+  z2 = i2; z3 = i6;
+  z1 = (z2 + z3) * FIX_0_541196100;
+  tmp2 = z1 + z3 * (-FIX_1_847759065);
+  tmp3 = z1 + z2 * FIX_0_765366865;
+  z2 = i0; z3 = i4;
+  tmp0 = (int)((unsigned)(z2 + z3) << 13);
+  tmp1 = (int)((unsigned)(z2 - z3) << 13);
+  tmp10 = tmp0 + tmp3; tmp13 = tmp0 - tmp3; tmp11 = tmp1 + tmp2; tmp12 = tmp1 - tmp2;
+  tmp0 = i7; tmp1 = i5; tmp2 = i3; tmp3 = i1;
+  z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2; z4 = tmp1 + tmp3;
+  z5 = (z3 + z4) * FIX_1_175875602;
+  tmp0 *= FIX_0_298631336; tmp1 *= FIX_2_053119869; tmp2 *= FIX_3_072711026; tmp3 *= FIX_1_501321110;
+  z1 *= -FIX_0_899976223; z2 *= -FIX_2_562915447; z3 *= -FIX_1_961570560; z4 *= -FIX_0_390180644;
+  z3 += z5; z4 += z5;
+  tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+  const int r = 1 << (SHIFT - 1);
+  o[0] = (tmp10 + tmp3 + r) >> SHIFT; o[7] = (tmp10 - tmp3 + r) >> SHIFT;
+  o[1] = (tmp11 + tmp2 + r) >> SHIFT; o[6] = (tmp11 - tmp2 + r) >> SHIFT;
+  o[2] = (tmp12 + tmp1 + r) >> SHIFT; o[5] = (tmp12 - tmp1 + r) >> SHIFT;
+  o[3] = (tmp13 + tmp0 + r) >> SHIFT; o[4] = (tmp13 - tmp0 + r) >> SHIFT;
+}
+
+__device__ __forceinline__ uint32_t range_limit(int x) {     // libjpeg range_limit[(x) & RANGE_MASK], table centred on 128
+  const int idx = x & 1023;
+  return idx < 128 ? idx + 128 : idx < 512 ? 255 : idx < 896 ? 0 : idx - 896;
+}
+
+__device__ __forceinline__ int find_image_by_coefblock(const JpegImage *im, int n, int64_t blk) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (im[mid].coef_off / 64 <= blk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(128) idct_kernel(const JpegImage *__restrict__ images, int nimages, int64_t total_blocks,
+                                                   const int16_t *__restrict__ coef_arena, const QuantSet *__restrict__ quants,
+                                                   uint8_t *__restrict__ planes) {
+  for (int64_t gb = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gb < total_blocks; gb += (int64_t)gridDim.x * blockDim.x) {
+    const int ii = find_image_by_coefblock(images, nimages, gb);
+    const JpegImage &im = images[ii];
+    const int64_t lb = gb - im.coef_off / 64;          // block index in scan (MCU) order
+    const int mcu = (int)(lb / im.bpm), b = (int)(lb % im.bpm);
+    const int comp = im.blk_comp[b];
+    const int mx = mcu % im.mcux, my = mcu / im.mcux;
+    const int bx = mx * im.hs[comp] + im.blk_x[b], by = my * im.vs[comp] + im.blk_y[b];
+    const uint16_t *q = quants[im.quant_set].q[im.tq[comp]];
+    const int4 *src = reinterpret_cast<const int4 *>(coef_arena + gb * 64);
+    int ws[64];
+    {
+      int in[64];
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const int4 v = __ldg(src + r);
+        const int w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          in[r * 8 + 2 * k] = (int)(int16_t)(w[k] & 0xFFFF) * (int)q[r * 8 + 2 * k];
+          in[r * 8 + 2 * k + 1] = (w[k] >> 16) * (int)q[r * 8 + 2 * k + 1];
+        }
+      }
+#pragma unroll
+      for (int x = 0; x < 8; x++) {       // pass 1: columns
+        int o[8];
+        idct8<11>(in[x], in[8 + x], in[16 + x], in[24 + x], in[32 + x], in[40 + x], in[48 + x], in[56 + x], o);
+#pragma unroll
+        for (int y = 0; y < 8; y++) ws[y * 8 + x] = o[y];
+      }
+    }
+    uint8_t *dst = planes + im.plane_off[comp] + ((int64_t)by * 8) * im.plane_w[comp] + bx * 8;
+#pragma unroll
+    for (int y = 0; y < 8; y++) {         // pass 2: rows
+      int o[8];
+      idct8<18>(ws[y * 8], ws[y * 8 + 1], ws[y * 8 + 2], ws[y * 8 + 3], ws[y * 8 + 4], ws[y * 8 + 5], ws[y * 8 + 6], ws[y * 8 + 7], o);
+      const uint32_t lo = range_limit(o[0]) | (range_limit(o[1]) << 8) | (range_limit(o[2]) << 16) | (range_limit(o[3]) << 24);
+      const uint32_t hi = range_limit(o[4]) | (range_limit(o[5]) << 8) | (range_limit(o[6]) << 16) | (range_limit(o[7]) << 24);
+      *reinterpret_cast<uint2 *>(dst + (int64_t)y * im.plane_w[comp]) = make_uint2(lo, hi);
+    }
+  }
+}
+
+// ============================================================================================
+// C1: chroma upsampling + colour conversion.  One thread per 4 output pixels of a row.
+__device__ __forceinline__ int up_sample(const uint8_t *__restrict__ pl, int pw, int dw, int dh, int hexp, int vexp, int fancy,
+                                         int x, int y) {
+  if (hexp == 1 && vexp == 1) return pl[(int64_t)y * pw + x];
+  if (fancy && hexp == 2 && vexp == 1 && dw > 2) {                 // h2v1 fancy (jdsample.c h2v1_fancy_upsample)
+    const uint8_t *r = pl + (int64_t)y * pw;
+    const int i = x >> 1;
+    if (x & 1) return i == dw - 1 ? r[i] : (r[i] * 3 + r[i + 1] + 2) >> 2;
+    return i == 0 ? r[i] : (r[i] * 3 + r[i - 1] + 1) >> 2;
+  }
+  if (fancy && hexp == 2 && vexp == 2 && dw > 2) {                 // h2v2 fancy (triangle)
+    const int i0 = y >> 1;
+    int i1 = (y & 1) ? i0 + 1 : i0 - 1;
+    i1 = min(max(i1, 0), dh - 1);
+    const uint8_t *r0 = pl + (int64_t)i0 * pw, *r1 = pl + (int64_t)i1 * pw;
+    const int i = x >> 1;
+    const int cur = r0[i] * 3 + r1[i];
+    if (x & 1) return i == dw - 1 ? (cur * 4 + 7) >> 4 : (cur * 3 + r0[i + 1] * 3 + r1[i + 1] + 7) >> 4;
+    return i == 0 ? (cur * 4 + 8) >> 4 : (cur * 3 + r0[i - 1] * 3 + r1[i - 1] + 8) >> 4;
+  }
+  if (fancy && hexp == 1 && vexp == 2) {                           // h1v2 fancy
+    const int i0 = y >> 1;
+    int i1 = (y & 1) ? i0 + 1 : i0 - 1;
+    i1 = min(max(i1, 0), dh - 1);
+    return (pl[(int64_t)i0 * pw + x] * 3 + pl[(int64_t)i1 * pw + x] + ((y & 1) ? 2 : 1)) >> 2;
+  }
+  return pl[(int64_t)(y / vexp) * pw + x / hexp];                  // box replication
+}
+
+__device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
+
+__global__ void __launch_bounds__(256) color_kernel(const JpegImage *__restrict__ images, const int64_t *__restrict__ first_quad,
+                                                    int nimages, int64_t total_quads, const uint8_t *__restrict__ planes) {
+  for (int64_t gq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gq < total_quads; gq += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = nimages - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (first_quad[mid] <= gq) lo = mid; else hi = mid - 1; }
+    const JpegImage &im = images[lo];
+    const int64_t q = gq - first_quad[lo];
+    const int qpr = (im.width + 3) >> 2;
+    const int y = (int)(q / qpr), x0 = (int)(q % qpr) << 2;
+    const int W = im.width, H = im.height;
+    const int nout = im.out_type == DALIB200_GRAY ? 1 : 3;
+    uint8_t px[12];
+    const int nx = min(4, W - x0);
+    for (int k = 0; k < nx; k++) {
+      const int x = x0 + k;
+      int v[3];
+      for (int c = 0; c < im.ncomp; c++) {
+        const int hexp = im.hmax / im.hs[c], vexp = im.vmax / im.vs[c];
+        const int dw = (W * im.hs[c] + im.hmax - 1) / im.hmax, dh = (H * im.vs[c] + im.vmax - 1) / im.vmax;
+        v[c] = up_sample(planes + im.plane_off[c], im.plane_w[c], dw, dh, hexp, vexp, im.fancy, x, y);
+      }
+      int r, g, b, yy, cb, cr;
+      if (im.ncomp == 1) { r = g = b = yy = v[0]; cb = cr = 128; }
+      else if (im.is_rgb) { r = v[0]; g = v[1]; b = v[2]; yy = cb = cr = 0; }
+      else {
+        yy = v[0]; cb = v[1]; cr = v[2];
+        const int cbm = cb - 128, crm = cr - 128;                   // jdcolor.c, SCALEBITS = 16
+        r = clamp255(yy + ((91881 * crm + 32768) >> 16));
+        g = clamp255(yy + ((-22554 * cbm + 32768 - 46802 * crm) >> 16));
+        b = clamp255(yy + ((116130 * cbm + 32768) >> 16));
+      }
+      if (im.out_type == DALIB200_RGB) { px[3 * k] = r; px[3 * k + 1] = g; px[3 * k + 2] = b; }
+      else if (im.out_type == DALIB200_BGR) { px[3 * k] = b; px[3 * k + 1] = g; px[3 * k + 2] = r; }
+      else if (im.out_type == DALIB200_YCbCr) { px[3 * k] = yy; px[3 * k + 1] = cb; px[3 * k + 2] = cr; }
+      else px[k] = (im.ncomp == 1 || !im.is_rgb) ? yy : ((r * 19595 + g * 38470 + b * 7471 + 32768) >> 16);
+    }
+    uint8_t *o = im.out + ((int64_t)y * W + x0) * nout;
+    const int nb = nx * nout;
+    if (nb == 12 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+      uint32_t *o4 = reinterpret_cast<uint32_t *>(o);
+      o4[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
+      o4[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
+      o4[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
+    } else {
+      for (int k = 0; k < nb; k++) o[k] = px[k];
+    }
+  }
+}
+
+}  // namespace dalib200
+
+// ============================================================================================
+// host side
+using namespace dalib200;  // NOLINT
+
+namespace {
+
+struct HostHuff { uint8_t bits[17]; uint8_t vals[256]; bool present = false; };
+
+struct ParsedJpeg {
+  int width = 0, height = 0, ncomp = 0, precision = 8;
+  int cid[4] = {0}, hs[4] = {0}, vs[4] = {0}, tq[4] = {0};
+  int hmax = 0, vmax = 0;
+  bool progressive = false, jfif = false;
+  int adobe_transform = -1, orientation = 1, restart_interval = 0;
+  uint16_t qt[4][64]; bool qt_present[4] = {false, false, false, false};
+  HostHuff dc[4], ac[4];
+  int scan_ncomp = 0, scan_comp[4] = {0}, td[4] = {0}, ta[4] = {0};
+  size_t scan_begin = 0, scan_end = 0;
+};
+
+const uint8_t kZigzag[64] = {
+   0,  1,  8, 16,  9,  2,  3, 10, 17, 24, 32, 25, 18, 11,  4,  5,
+  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,  6,  7, 14, 21, 28,
+  35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+  58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
+
+inline int rd16(const uint8_t *p) { return (p[0] << 8) | p[1]; }
+
+int ParseExifOrientation(const uint8_t *p, int len) {
+  if (len < 8) return 1;
+  bool le;
+  if (p[0] == 'I' && p[1] == 'I') le = true; else if (p[0] == 'M' && p[1] == 'M') le = false; else return 1;
+  auto r16 = [&](unsigned o) { return le ? (p[o] | (p[o + 1] << 8)) : ((p[o] << 8) | p[o + 1]); };
+  auto r32 = [&](unsigned o) { return le ? (unsigned)(p[o] | (p[o + 1] << 8) | (p[o + 2] << 16) | ((unsigned)p[o + 3] << 24))
+                                         : (((unsigned)p[o] << 24) | (p[o + 1] << 16) | (p[o + 2] << 8) | p[o + 3]); };
+  unsigned ifd = r32(4);
+  if (ifd + 2 > (unsigned)len) return 1;
+  int n = r16(ifd);
+  for (int i = 0; i < n; i++) {
+    unsigned e = ifd + 2 + 12 * i;
+    if (e + 12 > (unsigned)len) return 1;
+    if (r16(e) == 0x0112) { int v = r16(e + 8); return (v >= 1 && v <= 8) ? v : 1; }
+  }
+  return 1;
+}
+
+// T.81 Annex B marker walk up to and including SOS.  Returns a DALIB200 status.
+int ParseHeaders(const uint8_t *p, size_t n, ParsedJpeg &j, bool need_scan) {
+  size_t pos = 2;
+  if (n < 4 || p[0] != 0xFF || p[1] != 0xD8) { SetLastError("not a JPEG stream (missing SOI)"); return DALIB200_ERROR_BAD_DATA; }
+  bool got_sof = false;
+  while (pos + 4 <= n) {
+    if (p[pos] != 0xFF) { SetLastError("JPEG: marker expected at offset %zu", pos); return DALIB200_ERROR_BAD_DATA; }
+    while (pos < n && p[pos] == 0xFF) pos++;
+    if (pos >= n) break;
+    int m = p[pos++];
+    if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
+    if (m == 0xD9) break;
+    if (pos + 2 > n) break;
+    int L = rd16(p + pos);
+    if (L < 2 || pos + L > n) { SetLastError("JPEG: truncated segment (marker 0x%02X)", m); return DALIB200_ERROR_BAD_DATA; }
+    const uint8_t *s = p + pos + 2;
+    int sl = L - 2;
+    if (m == 0xDB) {
+      int o = 0;
+      while (o < sl) {
+        int pq = s[o] >> 4, tq = s[o] & 15; o++;
+        if (tq > 3 || o + (pq ? 128 : 64) > sl) { SetLastError("JPEG: bad DQT"); return DALIB200_ERROR_BAD_DATA; }
+        for (int i = 0; i < 64; i++) { int v; if (pq) { v = rd16(s + o); o += 2; } else v = s[o++]; j.qt[tq][kZigzag[i]] = (uint16_t)v; }
+        j.qt_present[tq] = true;
+      }
+    } else if (m == 0xC4) {
+      int o = 0;
+      while (o < sl) {
+        if (o + 17 > sl) { SetLastError("JPEG: bad DHT"); return DALIB200_ERROR_BAD_DATA; }
+        int tc = s[o] >> 4, th = s[o] & 15; o++;
+        if (th > 3 || tc > 1) { SetLastError("JPEG: bad DHT id"); return DALIB200_ERROR_BAD_DATA; }
+        HostHuff &h = tc ? j.ac[th] : j.dc[th];
+        int cnt = 0; h.bits[0] = 0;
+        for (int i = 1; i <= 16; i++) { h.bits[i] = s[o++]; cnt += h.bits[i]; }
+        if (cnt > 256 || o + cnt > sl) { SetLastError("JPEG: bad DHT counts"); return DALIB200_ERROR_BAD_DATA; }
+        memset(h.vals, 0, sizeof(h.vals));
+        memcpy(h.vals, s + o, cnt); o += cnt;
+        h.present = true;
+      }
+    } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
+      if (sl < 6) { SetLastError("JPEG: bad SOF"); return DALIB200_ERROR_BAD_DATA; }
+      j.progressive = m == 0xC2;
+      j.precision = s[0]; j.height = rd16(s + 1); j.width = rd16(s + 3); j.ncomp = s[5];
+      if (j.ncomp < 1 || j.ncomp > 4 || sl < 6 + 3 * j.ncomp) { SetLastError("JPEG: bad SOF component count"); return DALIB200_ERROR_BAD_DATA; }
+      for (int c = 0; c < j.ncomp; c++) {
+        j.cid[c] = s[6 + 3 * c]; j.hs[c] = s[7 + 3 * c] >> 4; j.vs[c] = s[7 + 3 * c] & 15; j.tq[c] = s[8 + 3 * c];
+        if (j.hs[c] < 1 || j.hs[c] > 4 || j.vs[c] < 1 || j.vs[c] > 4 || j.tq[c] > 3) { SetLastError("JPEG: bad sampling factors"); return DALIB200_ERROR_BAD_DATA; }
+        j.hmax = std::max(j.hmax, j.hs[c]); j.vmax = std::max(j.vmax, j.vs[c]);
+      }
+      got_sof = true;
+    } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+      SetLastError("JPEG: coding process 0x%02X (lossless / arithmetic / hierarchical) is not supported", m);
+      return DALIB200_ERROR_UNSUPPORTED;
+    } else if (m == 0xDD) {
+      if (sl >= 2) j.restart_interval = rd16(s);
+    } else if (m == 0xE0) {
+      if (sl >= 5 && !memcmp(s, "JFIF\0", 5)) j.jfif = true;
+    } else if (m == 0xE1) {
+      if (sl >= 6 && !memcmp(s, "Exif\0\0", 6)) j.orientation = ParseExifOrientation(s + 6, sl - 6);
+    } else if (m == 0xEE) {
+      if (sl >= 12 && !memcmp(s, "Adobe", 5)) j.adobe_transform = s[11];
+    } else if (m == 0xDA) {
+      if (!got_sof) { SetLastError("JPEG: SOS before SOF"); return DALIB200_ERROR_BAD_DATA; }
+      j.scan_ncomp = s[0];
+      if (j.scan_ncomp < 1 || j.scan_ncomp > 4 || sl < 1 + 2 * j.scan_ncomp) { SetLastError("JPEG: bad SOS"); return DALIB200_ERROR_BAD_DATA; }
+      for (int i = 0; i < j.scan_ncomp; i++) {
+        int cs = s[1 + 2 * i], ci = -1;
+        for (int c = 0; c < j.ncomp; c++) if (j.cid[c] == cs) ci = c;
+        if (ci < 0) { SetLastError("JPEG: SOS references an unknown component"); return DALIB200_ERROR_BAD_DATA; }
+        j.scan_comp[i] = ci; j.td[i] = s[2 + 2 * i] >> 4; j.ta[i] = s[2 + 2 * i] & 15;
+      }
+      j.scan_begin = pos + L;
+      break;
+    }
+    pos += L;
+    if (!need_scan && got_sof && m == 0xC0 + (j.progressive ? 2 : 0)) {
+      // info-only callers may stop at SOF, but EXIF/Adobe can follow: keep walking until SOS (cheap)
+    }
+  }
+  if (!got_sof) { SetLastError("JPEG: no frame header found"); return DALIB200_ERROR_BAD_DATA; }
+  if (j.width == 0 || j.height == 0) { SetLastError("JPEG: zero image size"); return DALIB200_ERROR_BAD_DATA; }
+  if (need_scan && !j.scan_begin) { SetLastError("JPEG: no scan found"); return DALIB200_ERROR_BAD_DATA; }
+  return DALIB200_SUCCESS;
+}
+
+void FillInfo(const ParsedJpeg &j, dalib200JpegInfo *info) {
+  info->width = j.width; info->height = j.height;
+  info->components = j.ncomp;
+  info->subsampling = (j.hs[0] << 4) | j.vs[0];
+  info->restart_interval = j.restart_interval;
+  info->orientation = j.orientation;
+}
+
+void BuildDeviceTable(const HostHuff &h, HuffTable &t) {
+  memset(&t, 0, sizeof(t));
+  int code = 0, k = 0;
+  for (int l = 1; l <= 16; l++) {
+    const int mincode = code;
+    t.valoff[l] = k - mincode;
+    for (int i = 0; i < h.bits[l]; i++, k++, code++) {
+      if (l <= kLutBits) {
+        const int lo = code << (kLutBits - l), cnt = 1 << (kLutBits - l);
+        for (int e = 0; e < cnt && lo + e < kLutSize; e++) t.lut[lo + e] = (uint16_t)((l << 8) | h.vals[k & 255]);
+      }
+    }
+    // a 16-bit window belongs to length l iff it is < maxcode[l] (exclusive bound, left-aligned) and matched
+    // no shorter length; for an empty length the bound equals the previous one, so nothing matches
+    t.maxcode[l] = code << (16 - l);
+    code <<= 1;
+  }
+  t.maxcode[17] = 0x7fffffff;
+  memcpy(t.vals, h.vals, 256);
+}
+
+}  // namespace
+
+struct dalib200JpegPlan {
+  int max_batch = 0, n = 0;
+  int output_type = DALIB200_RGB, fancy = 1;
+  std::vector<ParsedJpeg> parsed;
+  std::vector<JpegImage> images;
+  std::vector<JpegUnit> units;
+  std::vector<TableSet> tables;
+  std::vector<QuantSet> quants;
+  std::vector<int64_t> first_quad;
+  std::vector<const uint8_t *> src_ptr;     // host pointers of the scan data (for staging)
+  size_t raw_bytes = 0, clean_bytes = 0;
+  uint32_t nchunks = 0;
+  int64_t total_subseq = 0, total_coefs = 0, total_plane_bytes = 0, total_quads = 0;
+  int total_blocks_sync = 0;
+  int log2_sub = 10;
+  // staging (pinned) and device buffers -- grow only
+  uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;
+  uint8_t *d_stage = nullptr; size_t d_stage_cap = 0;
+  size_t desc_bytes = 0, off_images = 0, off_units = 0, off_tables = 0, off_quants = 0, off_quads = 0, off_raw = 0;
+  uint8_t *d_clean = nullptr; size_t d_clean_cap = 0;
+  uint32_t *d_chunk = nullptr; size_t d_chunk_cap = 0;
+  uint32_t *d_unit_len = nullptr; size_t d_unit_cap = 0;
+  uint64_t *d_state = nullptr; uint32_t *d_n = nullptr; size_t d_sub_cap = 0;
+  int16_t *d_coef = nullptr; size_t d_coef_cap = 0;
+  uint8_t *d_planes = nullptr; size_t d_planes_cap = 0;
+  int32_t *d_status = nullptr; size_t d_status_cap = 0;
+  cudaEvent_t uploaded = nullptr;
+  bool pending = false, staged = false;
+};
+
+namespace {
+
+template <typename T>
+int GrowDevice(T *&ptr, size_t &cap, size_t need) {
+  if (need <= cap) return DALIB200_SUCCESS;
+  size_t ncap = std::max(need + need / 4, (size_t)4096);
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr; cap = 0;
+  DB_CUDA(cudaMalloc(reinterpret_cast<void **>(&ptr), ncap * sizeof(T)));
+  cap = ncap;
+  return DALIB200_SUCCESS;
+}
+
+inline size_t Align(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" {
+
+int dalib200JpegGetInfo(const uint8_t *data, size_t len, dalib200JpegInfo *info) {
+  DB_CHECK_ARG(data && info, "JpegGetInfo: null argument");
+  ParsedJpeg j;
+  int rc = ParseHeaders(data, len, j, false);
+  if (rc) return rc;
+  FillInfo(j, info);
+  return DALIB200_SUCCESS;
+}
+
+int dalib200JpegPlanCreate(dalib200JpegPlan **plan, int max_batch) {
+  DB_CHECK_ARG(plan && max_batch > 0, "JpegPlanCreate: bad arguments");
+  auto *p = new dalib200JpegPlan();
+  p->max_batch = max_batch;
+  if (cudaEventCreateWithFlags(&p->uploaded, cudaEventDisableTiming) != cudaSuccess) {
+    SetLastError("JpegPlanCreate: cudaEventCreate failed"); delete p; return DALIB200_ERROR_CUDA;
+  }
+  *plan = p;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200JpegPlanDestroy(dalib200JpegPlan *p) {
+  if (!p) return DALIB200_SUCCESS;
+  if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
+  if (p->h_stage) cudaFreeHost(p->h_stage);
+  void *bufs[] = { p->d_stage, p->d_clean, p->d_chunk, p->d_unit_len, p->d_state, p->d_n, p->d_coef, p->d_planes, p->d_status };
+  for (void *b : bufs) if (b) cudaFree(b);
+  delete p;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200JpegPlanGetInfo(const dalib200JpegPlan *p, int sample, dalib200JpegInfo *info) {
+  DB_CHECK_ARG(p && info && sample >= 0 && sample < p->n, "JpegPlanGetInfo: bad sample index");
+  FillInfo(p->parsed[sample], info);
+  return DALIB200_SUCCESS;
+}
+
+size_t dalib200JpegPlanStagedBytes(const dalib200JpegPlan *p) { return p ? p->desc_bytes + p->raw_bytes : 0; }
+
+int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *streams, const size_t *lengths, int output_type,
+                          int fancy_upsampling) {
+  DB_CHECK_ARG(p && (n == 0 || (streams && lengths)) && n >= 0, "JpegPlanSetup: null argument");
+  DB_CHECK_ARG(n <= p->max_batch, "JpegPlanSetup: batch %d exceeds plan capacity %d", n, p->max_batch);
+  DB_CHECK_ARG(output_type == DALIB200_RGB || output_type == DALIB200_BGR || output_type == DALIB200_GRAY,
+               "decoders.image: output_type %d is not supported by the GPU decoder (RGB, BGR, GRAY)", output_type);
+  p->staged = false;
+  p->n = n; p->output_type = output_type; p->fancy = fancy_upsampling != 0;
+  p->parsed.assign(n, ParsedJpeg());
+  p->images.assign(n, JpegImage());
+  p->units.clear(); p->tables.clear(); p->quants.clear(); p->src_ptr.clear();
+  p->first_quad.assign(n, 0);
+  std::map<std::string, int> table_cache, quant_cache;
+  size_t raw = 0, clean = 0;
+  uint32_t chunks = 0;
+  int64_t subseq = 0, coefs = 0, planes = 0, quads = 0;
+  int sync_blocks = 0;
+  // subsequence size: aim for >= ~300k subsequences per batch, between 32 and 256 bytes
+  size_t total_len = 0;
+  for (int i = 0; i < n; i++) total_len += lengths[i];
+  int log2_bytes = 7;
+  while (log2_bytes > 5 && (total_len >> log2_bytes) < 300000) log2_bytes--;
+  p->log2_sub = log2_bytes + 3;
+  const size_t sub_bytes = (size_t)1 << log2_bytes;
+  for (int i = 0; i < n; i++) {
+    ParsedJpeg &j = p->parsed[i];
+    DB_CHECK_ARG(streams[i] && lengths[i] > 0, "decoders.image: sample %d is empty", i);
+    int rc = ParseHeaders(streams[i], lengths[i], j, true);
+    if (rc) { std::string m = dalib200GetLastError(); SetLastError("decoders.image: sample %d: %s", i, m.c_str()); return rc; }
+    auto unsupported = [&](const char *what) { SetLastError("decoders.image: sample %d: %s", i, what); return DALIB200_ERROR_UNSUPPORTED; };
+    if (j.progressive) return unsupported("progressive JPEG is not supported by the GPU decoder yet");
+    if (j.precision != 8) return unsupported("only 8-bit baseline JPEG is supported");
+    if (j.ncomp != 1 && j.ncomp != 3) return unsupported("only 1- or 3-component JPEG is supported");
+    if (j.scan_ncomp != j.ncomp) return unsupported("multi-scan (non-interleaved) baseline JPEG is not supported yet");
+    if (j.orientation != 1) return unsupported("EXIF orientation other than 1 is not applied yet (adjust_orientation)");
+    for (int c = 1; c < j.ncomp; c++)
+      if (j.hs[c] != 1 || j.vs[c] != 1) return unsupported("chroma sampling factors other than 1x1 are not supported");
+    if (j.ncomp == 1) { j.hs[0] = j.vs[0] = 1; j.hmax = j.vmax = 1; }     // a single-component scan is never interleaved
+    if (!(j.hmax == 1 || j.hmax == 2 || j.hmax == 4) || !(j.vmax == 1 || j.vmax == 2)) return unsupported("unsupported luma sampling factor");
+    JpegImage &im = p->images[i];
+    memset(&im, 0, sizeof(im));
+    im.width = j.width; im.height = j.height; im.ncomp = j.ncomp;
+    im.hmax = j.hmax; im.vmax = j.vmax;
+    im.mcux = (j.width + 8 * j.hmax - 1) / (8 * j.hmax);
+    im.mcuy = (j.height + 8 * j.vmax - 1) / (8 * j.vmax);
+    im.restart_interval = j.restart_interval;
+    im.out_type = output_type; im.fancy = p->fancy;
+    im.is_rgb = j.ncomp == 3 && (j.adobe_transform == 0 ||
+                (j.adobe_transform < 0 && !j.jfif && j.cid[0] == 'R' && j.cid[1] == 'G' && j.cid[2] == 'B'));
+    int bpm = 0;
+    for (int si = 0; si < j.scan_ncomp; si++) {
+      const int c = j.scan_comp[si];
+      im.hs[c] = j.hs[c]; im.vs[c] = j.vs[c]; im.tq[c] = j.tq[c];
+      if (!j.qt_present[j.tq[c]]) { SetLastError("decoders.image: sample %d: missing quantisation table", i); return DALIB200_ERROR_BAD_DATA; }
+      if (j.td[si] > 1 || j.ta[si] > 1) return unsupported("Huffman table ids above 1 are not supported (baseline allows 0..1)");
+      if (!j.dc[j.td[si]].present || !j.ac[j.ta[si]].present) { SetLastError("decoders.image: sample %d: missing Huffman table", i); return DALIB200_ERROR_BAD_DATA; }
+      for (int v = 0; v < j.vs[c]; v++)
+        for (int h = 0; h < j.hs[c]; h++) {
+          if (bpm >= kMaxBlocksPerMcu) return unsupported("too many blocks per MCU");
+          im.blk_comp[bpm] = c; im.blk_dc[bpm] = j.td[si]; im.blk_ac[bpm] = 2 + j.ta[si]; im.blk_x[bpm] = h; im.blk_y[bpm] = v;
+          bpm++;
+        }
+    }
+    im.bpm = bpm;
+    // Huffman tables (dedup by content)
+    {
+      std::string key;
+      for (int t = 0; t < 2; t++) { key.append(reinterpret_cast<const char *>(j.dc[t].bits), 17); key.append(reinterpret_cast<const char *>(j.dc[t].vals), 256); key.push_back(j.dc[t].present); }
+      for (int t = 0; t < 2; t++) { key.append(reinterpret_cast<const char *>(j.ac[t].bits), 17); key.append(reinterpret_cast<const char *>(j.ac[t].vals), 256); key.push_back(j.ac[t].present); }
+      auto it = table_cache.find(key);
+      if (it == table_cache.end()) {
+        TableSet ts;
+        for (int t = 0; t < 2; t++) { BuildDeviceTable(j.dc[t], ts.t[t]); BuildDeviceTable(j.ac[t], ts.t[2 + t]); }
+        p->tables.push_back(ts);
+        it = table_cache.emplace(key, (int)p->tables.size() - 1).first;
+      }
+      im.table_set = it->second;
+      std::string qk(reinterpret_cast<const char *>(j.qt), sizeof(j.qt));
+      auto qi = quant_cache.find(qk);
+      if (qi == quant_cache.end()) {
+        QuantSet qs; memcpy(qs.q, j.qt, sizeof(j.qt));
+        p->quants.push_back(qs);
+        qi = quant_cache.emplace(qk, (int)p->quants.size() - 1).first;
+      }
+      im.quant_set = qi->second;
+    }
+    // entropy-coded segment(s)
+    const uint8_t *d = streams[i];
+    size_t sb = j.scan_begin, se = lengths[i];
+    // trim at EOI if present at the very end (common case); otherwise the decoder stops on slot count
+    if (se >= sb + 2 && d[se - 2] == 0xFF && d[se - 1] == 0xD9) se -= 2;
+    j.scan_end = se;
+    const int64_t nmcu = (int64_t)im.mcux * im.mcuy;
+    im.unit_begin = (int)p->units.size();
+    im.subseq_begin = (int)subseq;
+    im.block_begin = sync_blocks;
+    int32_t local_sub = 0;
+    auto add_unit = [&](size_t b, size_t e, int64_t mcu0, int64_t mcus) {
+      JpegUnit u;
+      memset(&u, 0, sizeof(u));
+      u.raw_off = (uint32_t)(raw + (b - sb));
+      u.raw_len = (uint32_t)(e - b);
+      u.clean_off = (uint32_t)clean;
+      u.first_chunk = chunks;
+      u.image = i;
+      u.first_subseq = local_sub;
+      u.nsub_max = (int32_t)((u.raw_len + sub_bytes - 1) / sub_bytes);
+      u.slot_base = mcu0 * bpm * 64;
+      u.nslots = mcus * bpm * 64;
+      clean += Align(u.raw_len + 32, 16);
+      chunks += (u.raw_len + kChunkBytes - 1) / kChunkBytes;
+      local_sub += u.nsub_max;
+      p->units.push_back(u);
+    };
+    if (j.restart_interval == 0) {
+      add_unit(sb, se, 0, nmcu);
+    } else {
+      // split at RSTn markers (host scan; only images that carry DRI pay for it)
+      size_t b = sb; int64_t mcu0 = 0;
+      const uint8_t *q = d + sb, *end = d + se;
+      while (true) {
+        const uint8_t *f = q < end ? static_cast<const uint8_t *>(memchr(q, 0xFF, end - q)) : nullptr;
+        if (!f || f + 1 >= end) break;
+        if (f[1] >= 0xD0 && f[1] <= 0xD7) {
+          const int64_t mcus = std::min<int64_t>(j.restart_interval, nmcu - mcu0);
+          if (mcus > 0) add_unit(b, f - d, mcu0, mcus);
+          mcu0 += mcus;
+          b = (f - d) + 2; q = f + 2;
+        } else {
+          q = f + 1;
+        }
+      }
+      if (mcu0 < nmcu) add_unit(b, se, mcu0, std::min<int64_t>(j.restart_interval, nmcu - mcu0));
+    }
+    im.unit_end = (int)p->units.size();
+    im.nsub = local_sub;
+    p->src_ptr.push_back(d + sb);
+    raw += Align(se - sb, 16);
+    subseq += local_sub;
+    sync_blocks += (local_sub + kSyncThreads - 1) / kSyncThreads;
+    im.coef_off = coefs;
+    coefs += nmcu * bpm * 64;
+    for (int c = 0; c < j.ncomp; c++) {
+      im.plane_w[c] = im.mcux * j.hs[c] * 8; im.plane_h[c] = im.mcuy * j.vs[c] * 8;
+      im.plane_off[c] = planes;
+      planes += Align((size_t)im.plane_w[c] * im.plane_h[c], 16);
+    }
+    p->first_quad[i] = quads;
+    quads += (int64_t)((j.width + 3) / 4) * j.height;
+  }
+  DB_CHECK_ARG(raw < (1ull << 32) && clean < (1ull << 32), "decoders.image: batch of encoded data exceeds 4 GiB");
+  p->raw_bytes = raw; p->clean_bytes = clean; p->nchunks = chunks;
+  p->total_subseq = subseq; p->total_coefs = coefs; p->total_plane_bytes = planes; p->total_quads = quads;
+  p->total_blocks_sync = sync_blocks;
+  // ---- pack descriptors + raw scan bytes into pinned staging
+  size_t off = 0;
+  p->off_images = off; off += Align(sizeof(JpegImage) * n, 16);
+  p->off_units = off; off += Align(sizeof(JpegUnit) * p->units.size(), 16);
+  p->off_tables = off; off += Align(sizeof(TableSet) * p->tables.size(), 16);
+  p->off_quants = off; off += Align(sizeof(QuantSet) * p->quants.size(), 16);
+  p->off_quads = off; off += Align(sizeof(int64_t) * n, 16);
+  p->off_raw = off;
+  p->desc_bytes = off;
+  const size_t total = off + raw + 64;
+  if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
+  if (total > p->h_stage_cap) {
+    if (p->h_stage) cudaFreeHost(p->h_stage);
+    p->h_stage = nullptr; p->h_stage_cap = 0;
+    size_t ncap = total + total / 4;
+    DB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->h_stage), ncap));
+    p->h_stage_cap = ncap;
+  }
+  memcpy(p->h_stage + p->off_units, p->units.data(), sizeof(JpegUnit) * p->units.size());
+  memcpy(p->h_stage + p->off_tables, p->tables.data(), sizeof(TableSet) * p->tables.size());
+  memcpy(p->h_stage + p->off_quants, p->quants.data(), sizeof(QuantSet) * p->quants.size());
+  memcpy(p->h_stage + p->off_quads, p->first_quad.data(), sizeof(int64_t) * n);
+  // scan bytes: parallel memcpy (the host is otherwise the bottleneck at batch 256 x 0.5 MB)
+  {
+    std::vector<size_t> dst_off(n);
+    size_t o = 0;
+    for (int i = 0; i < n; i++) { dst_off[i] = o; o += Align(p->parsed[i].scan_end - p->parsed[i].scan_begin, 16); }
+    const int nthreads = std::max(1, std::min<int>({ (int)std::thread::hardware_concurrency(), 8, n }));
+    auto work = [&](int t) {
+      for (int i = t; i < n; i += nthreads) {
+        const size_t len = p->parsed[i].scan_end - p->parsed[i].scan_begin;
+        uint8_t *dstp = p->h_stage + p->off_raw + dst_off[i];
+        memcpy(dstp, p->src_ptr[i], len);
+        memset(dstp + len, 0, Align(len, 16) - len);
+      }
+    };
+    if (nthreads == 1 || raw < (1u << 20)) { for (int t = 0; t < nthreads; t++) work(t); }
+    else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
+      for (auto &t : th) t.join();
+    }
+  }
+  p->staged = true;
+  return DALIB200_SUCCESS;
+}
+
+// test / debug accessor: quantised coefficients of one sample after DC prediction, MCU order, natural order in
+// each block.  Synchronises the device.
+int dalib200JpegDebugGetCoefficients(dalib200JpegPlan *p, int sample, int16_t *out, size_t count) {
+  DB_CHECK_ARG(p && out && sample >= 0 && sample < p->n && p->d_coef, "JpegDebugGetCoefficients: bad arguments");
+  const JpegImage &im = p->images[sample];
+  const size_t have = (size_t)im.mcux * im.mcuy * im.bpm * 64;
+  DB_CHECK_ARG(count <= have, "JpegDebugGetCoefficients: sample has %zu coefficients", have);
+  DB_CUDA(cudaDeviceSynchronize());
+  DB_CUDA(cudaMemcpy(out, p->d_coef + im.coef_off, count * sizeof(int16_t), cudaMemcpyDeviceToHost));
+  return DALIB200_SUCCESS;
+}
+
+// per-sample decode status written by the device (0 = ok, 1 = entropy-coded data ended early).  Synchronises.
+int dalib200JpegGetStatus(dalib200JpegPlan *p, int32_t *status_out) {
+  DB_CHECK_ARG(p && status_out && p->d_status, "JpegGetStatus: bad arguments");
+  DB_CUDA(cudaDeviceSynchronize());
+  DB_CUDA(cudaMemcpy(status_out, p->d_status, sizeof(int32_t) * p->n, cudaMemcpyDeviceToHost));
+  return DALIB200_SUCCESS;
+}
+
+int dalib200JpegUpload(dalib200JpegPlan *p, dalib200Stream_t stream) {
+  DB_CHECK_ARG(p && p->staged, "JpegUpload: call JpegPlanSetup first");
+  if (p->n == 0) return DALIB200_SUCCESS;
+  const size_t total = p->desc_bytes + p->raw_bytes;
+  int rc = GrowDevice(p->d_stage, p->d_stage_cap, total + 64);
+  if (rc) return rc;
+  // output pointers are patched at launch: images are uploaded there.  Everything else goes now.
+  DB_CUDA(cudaMemcpyAsync(p->d_stage + p->off_units, p->h_stage + p->off_units, total - p->off_units, cudaMemcpyHostToDevice, stream));
+  DB_CUDA(cudaEventRecord(p->uploaded, stream));
+  p->pending = true;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Stream_t stream) {
+  DB_CHECK_ARG(p && p->staged && out_ptrs, "JpegLaunch: call JpegPlanSetup / JpegUpload first");
+  if (p->n == 0) return DALIB200_SUCCESS;
+  DB_CHECK_ARG(p->d_stage && p->d_stage_cap >= p->desc_bytes + p->raw_bytes, "JpegLaunch: JpegUpload has not been called for this batch");
+  int rc;
+  if ((rc = GrowDevice(p->d_clean, p->d_clean_cap, p->clean_bytes + 64))) return rc;
+  if ((rc = GrowDevice(p->d_chunk, p->d_chunk_cap, (size_t)p->nchunks + 1))) return rc;
+  if ((rc = GrowDevice(p->d_unit_len, p->d_unit_cap, p->units.size() + 1))) return rc;
+  {
+    size_t cap2 = p->d_sub_cap;
+    if ((rc = GrowDevice(p->d_state, p->d_sub_cap, (size_t)p->total_subseq + 1))) return rc;
+    if ((rc = GrowDevice(p->d_n, cap2, (size_t)p->total_subseq + 1))) return rc;
+  }
+  if ((rc = GrowDevice(p->d_coef, p->d_coef_cap, (size_t)p->total_coefs + 64))) return rc;
+  if ((rc = GrowDevice(p->d_planes, p->d_planes_cap, (size_t)p->total_plane_bytes + 64))) return rc;
+  if ((rc = GrowDevice(p->d_status, p->d_status_cap, (size_t)p->n + 1))) return rc;
+  // image descriptors carry the output pointers: small separate upload from a scratch area of the pinned buffer
+  // (the area [off_images, off_units) is not touched by JpegUpload)
+  {
+    // wait until a previous launch's copy of this area has completed
+    if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
+    JpegImage *hi = reinterpret_cast<JpegImage *>(p->h_stage + p->off_images);
+    for (int i = 0; i < p->n; i++) { hi[i] = p->images[i]; hi[i].out = static_cast<uint8_t *>(out_ptrs[i]); }
+    DB_CUDA(cudaMemcpyAsync(p->d_stage + p->off_images, hi, sizeof(JpegImage) * p->n, cudaMemcpyHostToDevice, stream));
+    DB_CUDA(cudaEventRecord(p->uploaded, stream));
+    p->pending = true;
+  }
+  const auto *d_images = reinterpret_cast<const JpegImage *>(p->d_stage + p->off_images);
+  const auto *d_units = reinterpret_cast<const JpegUnit *>(p->d_stage + p->off_units);
+  const auto *d_tables = reinterpret_cast<const TableSet *>(p->d_stage + p->off_tables);
+  const auto *d_quants = reinterpret_cast<const QuantSet *>(p->d_stage + p->off_quants);
+  const auto *d_quads = reinterpret_cast<const int64_t *>(p->d_stage + p->off_quads);
+  const uint8_t *d_raw = p->d_stage + p->off_raw;
+  const int nunits = (int)p->units.size();
+  const int sms = NumSMs();
+  cudaStream_t s = stream;
+  // the clean stream must be zero-padded behind every unit (the bit reader peeks ahead)
+  DB_CUDA(cudaMemsetAsync(p->d_clean, 0, p->clean_bytes + 64, s));
+  DB_CUDA(cudaMemsetAsync(p->d_coef, 0, (size_t)p->total_coefs * sizeof(int16_t), s));
+  DB_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * p->n, s));
+  {
+    const int grid = (int)std::min<uint32_t>(p->nchunks, (uint32_t)sms * 16);
+    unstuff_count_kernel<<<grid, 256, 0, s>>>(d_raw, d_units, nunits, p->nchunks, p->d_chunk);
+    unstuff_scan_kernel<<<(nunits + 127) / 128, 128, 0, s>>>(d_units, nunits, p->d_chunk, p->d_unit_len);
+    unstuff_scatter_kernel<<<grid, 256, 0, s>>>(d_raw, d_units, nunits, p->nchunks, p->d_chunk, p->d_clean);
+    CountLaunch(3);
+  }
+  HuffCtx cx;
+  cx.images = d_images; cx.nimages = p->n; cx.units = d_units; cx.unit_clean_len = p->d_unit_len; cx.tables = d_tables;
+  cx.clean = p->d_clean; cx.s_state = p->d_state; cx.s_n = p->d_n; cx.coef = p->d_coef; cx.log2_sub = p->log2_sub;
+  cx.status = p->d_status;
+  huff_sync_intra_kernel<<<p->total_blocks_sync, kSyncThreads, 0, s>>>(cx);
+  huff_sync_inter_kernel<<<p->n, 1024, 0, s>>>(cx);
+  huff_write_kernel<<<p->total_blocks_sync, kSyncThreads, 0, s>>>(cx);
+  dc_scan_kernel<<<p->n, 1024, 0, s>>>(d_images, p->d_coef);
+  {
+    const int64_t total_blocks = p->total_coefs / 64;
+    const int grid = (int)std::min<int64_t>((total_blocks + 127) / 128, (int64_t)sms * 32);
+    idct_kernel<<<grid, 128, 0, s>>>(d_images, p->n, total_blocks, p->d_coef, d_quants, p->d_planes);
+    const int grid2 = (int)std::min<int64_t>((p->total_quads + 255) / 256, (int64_t)sms * 32);
+    color_kernel<<<grid2, 256, 0, s>>>(d_images, d_quads, p->n, p->total_quads, p->d_planes);
+  }
+  CountLaunch(6);
+  DB_CUDA(cudaGetLastError());
+  return DALIB200_SUCCESS;
+}
+
+}  // extern "C"

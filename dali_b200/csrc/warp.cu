@@ -1,0 +1,217 @@
+// dali_b200/csrc/warp.cu -- WarpAffine for sm_100a.
+//
+// Parity target: reference CPU kernel WarpCPU<AffineMapping2D>::RunImpl (dali/kernels/imgproc/warp_cpu.h:143-178)
+// with Sampler<NN|LINEAR> (dali/kernels/imgproc/sampler.h:122-330):
+//   * source coordinates: src_tile = M * (0.5, y + 0.5)        (transform.h:134-145: t + m0*x + m1*y, left to right)
+//     then per 256-pixel tile   src_tile += 256 * dsdx          and per pixel   src += dsdx    -- the CPU kernel
+//     ACCUMULATES coordinates; to be bit-exact the accumulation is replayed: one thread per output row walks the
+//     tile and leaves the coordinates in shared memory, the whole CTA then samples from them.
+//     (The reference GPU kernel recomputes M*(x+0.5, y+0.5) per pixel, block_warp.cuh:54-58, and therefore differs
+//      from its own CPU backend in the last coordinate bits.)
+//   * bilinear: x-=0.5; x0=floor; s0 = s00*(1-qx) + s01*qx; s1 = ...; out = s0 + (s1-s0)*qy   (mul/add unfused)
+//   * border: clamp, or constant = ConvertSat<In>(fill_value)
+//
+// Algorithmic bytes per unit: in_h*in_w*C + out_h*out_w*C*sizeof(Out).
+#include "common.cuh"
+#include <algorithm>
+#include <cstring>
+
+namespace dalib200 {
+
+constexpr int kWarpTileW = 256;     // the reference's coordinate re-anchoring period (warp_cpu.h:160)
+constexpr int kWarpTileH = 8;
+
+struct WarpDesc {
+  const uint8_t *in;
+  void *out;
+  int32_t in_h, in_w, C, out_h, out_w;
+  int32_t tiles_x, tiles_y;
+  int64_t first_tile;
+  float m[6];
+};
+
+__device__ __forceinline__ int find_warp_sample(const WarpDesc *d, int n, int64_t t) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (d[mid].first_tile <= t) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+template <bool CLAMP>
+__device__ __forceinline__ float warp_fetch(const uint8_t *__restrict__ in, int H, int W, int C, int x, int y, int c, float border) {
+  if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) return (float)__ldg(in + ((int64_t)y * W + x) * C + c);
+  if (CLAMP) {
+    const int cx = min(max(x, 0), W - 1), cy = min(max(y, 0), H - 1);
+    return (float)__ldg(in + ((int64_t)cy * W + cx) * C + c);
+  }
+  return border;
+}
+
+template <typename Out> __device__ __forceinline__ Out warp_cvt(float v);
+template <> __device__ __forceinline__ float warp_cvt<float>(float v) { return v; }
+template <> __device__ __forceinline__ uint8_t warp_cvt<uint8_t>(float v) { return sat_u8_half_away(v); }
+
+template <typename Out, bool LINEAR, bool CLAMP>
+__global__ void __launch_bounds__(256) warp_affine_kernel(const WarpDesc *__restrict__ descs, int n, int64_t total_tiles,
+                                                          float border) {
+  __shared__ float2 coords[kWarpTileH][kWarpTileW];
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int s = find_warp_sample(descs, n, tile);
+    const WarpDesc &d = descs[s];
+    const int64_t tl = tile - d.first_tile;
+    const int ty = (int)(tl / d.tiles_x), tx = (int)(tl % d.tiles_x);
+    const int y0 = ty * kWarpTileH, x0 = tx * kWarpTileW;
+    const int th = min(kWarpTileH, d.out_h - y0), tw = min(kWarpTileW, d.out_w - x0);
+    // ---- stage 1: replay the reference's coordinate accumulation, one thread per row
+    if (threadIdx.x < th) {
+      const int y = y0 + threadIdx.x;
+      const float vx = 0.5f, vy = (float)y + 0.5f;
+      float sx = add_rn(add_rn(d.m[2], mul_rn(d.m[0], vx)), mul_rn(d.m[1], vy));
+      float sy = add_rn(add_rn(d.m[5], mul_rn(d.m[3], vx)), mul_rn(d.m[4], vy));
+      const float dx = d.m[0], dy = d.m[3];
+      const float tdx = mul_rn(256.0f, dx), tdy = mul_rn(256.0f, dy);
+      for (int t = 0; t < tx; t++) { sx = add_rn(sx, tdx); sy = add_rn(sy, tdy); }
+      for (int j = 0; j < tw; j++) {
+        coords[threadIdx.x][j] = make_float2(sx, sy);
+        sx = add_rn(sx, dx); sy = add_rn(sy, dy);
+      }
+    }
+    __syncthreads();
+    // ---- stage 2: sample
+    const int C = d.C;
+    Out *out = static_cast<Out *>(d.out);
+    for (int e = threadIdx.x; e < th * tw; e += blockDim.x) {
+      const int r = e / tw, j = e - r * tw;
+      const float2 src = coords[r][j];
+      Out *o = out + ((int64_t)(y0 + r) * d.out_w + x0 + j) * C;
+      if (!LINEAR) {
+        const int ix = (int)floorf(src.x), iy = (int)floorf(src.y);
+        for (int c = 0; c < C; c++) o[c] = warp_cvt<Out>(warp_fetch<CLAMP>(d.in, d.in_h, d.in_w, C, ix, iy, c, border));
+      } else {
+        const float fx = sub_rn(src.x, 0.5f), fy = sub_rn(src.y, 0.5f);
+        const float flx = floorf(fx), fly = floorf(fy);
+        const int ix = (int)flx, iy = (int)fly;
+        const float qx = sub_rn(fx, flx), px = sub_rn(1.0f, qx), qy = sub_rn(fy, fly);
+        for (int c = 0; c < C; c++) {
+          const float s00 = warp_fetch<CLAMP>(d.in, d.in_h, d.in_w, C, ix, iy, c, border);
+          const float s01 = warp_fetch<CLAMP>(d.in, d.in_h, d.in_w, C, ix + 1, iy, c, border);
+          const float s10 = warp_fetch<CLAMP>(d.in, d.in_h, d.in_w, C, ix, iy + 1, c, border);
+          const float s11 = warp_fetch<CLAMP>(d.in, d.in_h, d.in_w, C, ix + 1, iy + 1, c, border);
+          const float s0 = add_rn(mul_rn(s00, px), mul_rn(s01, qx));
+          const float s1 = add_rn(mul_rn(s10, px), mul_rn(s11, qx));
+          o[c] = warp_cvt<Out>(add_rn(s0, mul_rn(sub_rn(s1, s0), qy)));
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace dalib200
+
+using namespace dalib200;  // NOLINT
+
+struct dalib200WarpPlan {
+  int max_batch = 0, n = 0;
+  int interp = 1, use_fill = 0, out_dtype = DALIB200_UINT8;
+  float border = 0;
+  int64_t total_tiles = 0;
+  DescArena arena;
+  cudaEvent_t uploaded = nullptr;
+  bool pending = false;
+};
+
+extern "C" {
+
+void dalib200AffineInverse(const float *M, float *out) {
+  // include/dali/core/geom/transform.h:166-174 + mat.h:611-623: m = adj(2x2)/det ; t = (-m) * t
+  const float det = M[0] * M[4] - M[1] * M[3];
+  const float m00 = M[4] / det, m01 = -M[1] / det, m10 = -M[3] / det, m11 = M[0] / det;
+  const float n00 = -m00, n01 = -m01, n10 = -m10, n11 = -m11;
+  volatile float a = n00 * M[2], b = n01 * M[5];
+  const float t0 = a + b;
+  volatile float c = n10 * M[2], d = n11 * M[5];
+  const float t1 = c + d;
+  out[0] = m00; out[1] = m01; out[2] = t0; out[3] = m10; out[4] = m11; out[5] = t1;
+}
+
+int dalib200WarpPlanCreate(dalib200WarpPlan **plan, int max_batch) {
+  DB_CHECK_ARG(plan && max_batch > 0, "WarpPlanCreate: bad arguments");
+  auto *p = new dalib200WarpPlan();
+  p->max_batch = max_batch;
+  int rc = p->arena.Reserve(sizeof(WarpDesc) * max_batch);
+  if (rc) { delete p; return rc; }
+  if (cudaEventCreateWithFlags(&p->uploaded, cudaEventDisableTiming) != cudaSuccess) {
+    SetLastError("WarpPlanCreate: cudaEventCreate failed"); p->arena.Free(); delete p; return DALIB200_ERROR_CUDA;
+  }
+  *plan = p;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200WarpPlanDestroy(dalib200WarpPlan *p) {
+  if (!p) return DALIB200_SUCCESS;
+  if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
+  p->arena.Free();
+  delete p;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200WarpPlanSetup(dalib200WarpPlan *p, int n, const dalib200WarpSample *samples, int interp, int use_fill,
+                          float fill_value, int out_dtype) {
+  DB_CHECK_ARG(p && samples && n >= 0, "WarpPlanSetup: null argument");
+  DB_CHECK_ARG(n <= p->max_batch, "WarpPlanSetup: batch %d exceeds plan capacity %d", n, p->max_batch);
+  DB_CHECK_ARG(interp == 0 || interp == 1, "WarpAffine: only NN and LINEAR interpolation are supported (got %d)", interp);
+  DB_CHECK_ARG(out_dtype == DALIB200_UINT8 || out_dtype == DALIB200_FLOAT, "WarpAffine: output type %d not supported", out_dtype);
+  if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
+  auto *descs = reinterpret_cast<WarpDesc *>(p->arena.host);
+  int64_t tiles = 0;
+  for (int i = 0; i < n; i++) {
+    const auto &s = samples[i];
+    DB_CHECK_ARG(s.in_h > 0 && s.in_w > 0 && s.channels >= 1 && s.channels <= 8 && s.out_h >= 0 && s.out_w >= 0,
+                 "WarpAffine: sample %d has unsupported shapes", i);
+    WarpDesc &d = descs[i];
+    memset(&d, 0, sizeof(d));
+    d.in_h = s.in_h; d.in_w = s.in_w; d.C = s.channels; d.out_h = s.out_h; d.out_w = s.out_w;
+    d.tiles_x = (s.out_w + kWarpTileW - 1) / kWarpTileW;
+    d.tiles_y = (s.out_h + kWarpTileH - 1) / kWarpTileH;
+    d.first_tile = tiles;
+    tiles += (int64_t)d.tiles_x * d.tiles_y;
+    memcpy(d.m, s.matrix, sizeof(d.m));
+  }
+  p->n = n; p->interp = interp; p->use_fill = use_fill != 0; p->out_dtype = out_dtype; p->total_tiles = tiles;
+  // ConvertSat<uint8_t>(fill_value): round half away, clamp (warp.h:268, convert.h:306-324)
+  float r = std::round(fill_value);
+  p->border = r <= 0 ? 0.0f : r >= 255 ? 255.0f : r;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200WarpLaunch(dalib200WarpPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+  DB_CHECK_ARG(p && in_ptrs && out_ptrs, "WarpLaunch: null argument");
+  if (p->n == 0 || p->total_tiles == 0) return DALIB200_SUCCESS;
+  if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
+  auto *descs = reinterpret_cast<WarpDesc *>(p->arena.host);
+  for (int i = 0; i < p->n; i++) { descs[i].in = static_cast<const uint8_t *>(in_ptrs[i]); descs[i].out = out_ptrs[i]; }
+  int rc = p->arena.Upload(sizeof(WarpDesc) * p->n, stream);
+  if (rc) return rc;
+  DB_CUDA(cudaEventRecord(p->uploaded, stream));
+  p->pending = true;
+  const auto *dd = reinterpret_cast<const WarpDesc *>(p->arena.dev);
+  const int grid = (int)std::min<int64_t>(p->total_tiles, (int64_t)NumSMs() * 16);
+  const bool lin = p->interp == 1, clampb = !p->use_fill, u8 = p->out_dtype == DALIB200_UINT8;
+#define LAUNCH(O, L, Cc) warp_affine_kernel<O, L, Cc><<<grid, 256, 0, stream>>>(dd, p->n, p->total_tiles, p->border)
+  if (u8) {
+    if (lin) { if (clampb) LAUNCH(uint8_t, true, true); else LAUNCH(uint8_t, true, false); }
+    else     { if (clampb) LAUNCH(uint8_t, false, true); else LAUNCH(uint8_t, false, false); }
+  } else {
+    if (lin) { if (clampb) LAUNCH(float, true, true); else LAUNCH(float, true, false); }
+    else     { if (clampb) LAUNCH(float, false, true); else LAUNCH(float, false, false); }
+  }
+#undef LAUNCH
+  CountLaunch();
+  DB_CUDA(cudaGetLastError());
+  return DALIB200_SUCCESS;
+}
+
+}  // extern "C"

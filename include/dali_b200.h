@@ -72,7 +72,7 @@ int dalib200JpegPlanDestroy(dalib200JpegPlan *plan);
  * fancy_upsampling != 0 selects libjpeg "fancy" (triangle) chroma upsampling -- the reference CPU
  * backend's behaviour; 0 = box replication. */
 int dalib200JpegPlanSetup(dalib200JpegPlan *plan, int n, const uint8_t *const *streams, const size_t *lengths,
-                          int output_type /* DALIB200_RGB | BGR | GRAY | YCbCr */, int fancy_upsampling);
+                          int output_type /* DALIB200_RGB | BGR | GRAY */, int fancy_upsampling);
 int dalib200JpegPlanGetInfo(const dalib200JpegPlan *plan, int sample, dalib200JpegInfo *info);
 /* Bytes of packed entropy-coded data + tables staged for the batch (the H2D payload). */
 size_t dalib200JpegPlanStagedBytes(const dalib200JpegPlan *plan);
@@ -81,6 +81,10 @@ size_t dalib200JpegPlanStagedBytes(const dalib200JpegPlan *plan);
 int dalib200JpegUpload(dalib200JpegPlan *plan, dalib200Stream_t stream);
 /* Enqueues the decode of the uploaded batch; out_ptrs[i] -> device buffer H*W*C u8 (HWC). */
 int dalib200JpegLaunch(dalib200JpegPlan *plan, void *const *out_ptrs, dalib200Stream_t stream);
+/* Per-sample device status after a launch (0 ok, 1 = entropy-coded data ended early).  Synchronises. */
+int dalib200JpegGetStatus(dalib200JpegPlan *plan, int32_t *status_out);
+/* Test accessor: quantised coefficients of one sample (MCU order, natural order per block).  Synchronises. */
+int dalib200JpegDebugGetCoefficients(dalib200JpegPlan *plan, int sample, int16_t *out, size_t count);
 
 /* ------------------------------------------------------------------------------------------------
  * Separable resampling (fused two-pass).  Replaces kernels::ResampleGPU / SeparableResamplingGPUImpl::Run

@@ -78,3 +78,140 @@ def resample(imgs, out_hws, min_filter=(capi.FILTER_LINEAR, 1, 0.0), mag_filter=
     if want_order:
         return res, [capi.lib().dalib200ResamplePlanGetOrder(plan.handle, i) for i in range(n)]
     return res
+
+
+def synth_image(h, w, seed):
+    """SURVEY.md 8(d) C2 recipe: bicubic-upsampled low-frequency noise + sigma=5 gaussian noise."""
+    import cv2
+    r = np.random.default_rng(seed)
+    lo = r.uniform(0, 255, (max(2, h // 32), max(2, w // 32), 3)).astype(np.float32)
+    img = cv2.resize(lo, (w, h), interpolation=cv2.INTER_CUBIC) + r.normal(0, 5, (h, w, 3))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def jpeg_decode(streams, output_type=capi.RGB, fancy=True, plan=None, want_coefs=False):
+    torch = _torch()
+    n = len(streams)
+    bufs = [np.frombuffer(bytes(s), np.uint8) for s in streams]
+    ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    lens = (C.c_size_t * n)(*[b.size for b in bufs])
+    plan = plan or capi.Plan("Jpeg", max(n, 1))
+    capi.check(capi.lib().dalib200JpegPlanSetup(plan.handle, n, ptrs, lens, output_type, int(fancy)))
+    outs, infos = [], []
+    for i in range(n):
+        info = capi.JpegInfo()
+        capi.check(capi.lib().dalib200JpegPlanGetInfo(plan.handle, i, C.byref(info)))
+        infos.append(info)
+        ch = 1 if output_type == capi.GRAY else 3
+        outs.append(torch.empty((info.height, info.width, ch), dtype=torch.uint8, device="cuda"))
+    capi.check(capi.lib().dalib200JpegUpload(plan.handle, capi.stream_handle()))
+    capi.check(capi.lib().dalib200JpegLaunch(plan.handle, capi.ptr_array(outs), capi.stream_handle()))
+    torch.cuda.synchronize()
+    status = (C.c_int32 * n)()
+    capi.check(capi.lib().dalib200JpegGetStatus(plan.handle, status))
+    res = [o.cpu().numpy() for o in outs]
+    if want_coefs:
+        return res, list(status), plan
+    return res, list(status)
+
+
+def jpeg_coefs(plan, sample, count):
+    out = np.empty(count, np.int16)
+    capi.check(capi.lib().dalib200JpegDebugGetCoefficients(plan.handle, sample, out.ctypes.data_as(C.c_void_p), C.c_size_t(count)))
+    return out
+
+
+def warp_affine(imgs, mats, out_hws=None, interp=1, fill=None, out_dtype=np.uint8):
+    torch = _torch()
+    n = len(imgs)
+    samples = (capi.WarpSample * n)()
+    for i, im in enumerate(imgs):
+        s = samples[i]
+        s.in_h, s.in_w, s.channels = im.shape
+        s.out_h, s.out_w = out_hws[i] if out_hws else im.shape[:2]
+        s.matrix[:] = [float(v) for v in np.asarray(mats[i], np.float32).reshape(6)]
+    plan = capi.Plan("Warp", max(n, 1))
+    odt = capi.UINT8 if np.dtype(out_dtype) == np.uint8 else capi.FLOAT
+    capi.check(capi.lib().dalib200WarpPlanSetup(plan.handle, n, samples, int(interp), int(fill is not None), C.c_float(fill or 0.0), odt))
+    din = to_dev(imgs)
+    outs = [torch.empty((samples[i].out_h, samples[i].out_w, imgs[i].shape[2]), dtype=torch.uint8 if odt == capi.UINT8 else torch.float32,
+                        device="cuda") for i in range(n)]
+    capi.check(capi.lib().dalib200WarpLaunch(plan.handle, capi.ptr_array(din), capi.ptr_array(outs), capi.stream_handle()))
+    torch.cuda.synchronize()
+    return [o.cpu().numpy() for o in outs]
+
+
+def color_twist_matrix(hue=0.0, saturation=1.0, value=1.0, brightness=1.0, contrast=1.0, half_range=128.0):
+    M, T = np.empty(9, np.float32), np.empty(3, np.float32)
+    capi.lib().dalib200ColorTwistMatrix(C.c_float(hue), C.c_float(saturation), C.c_float(value), C.c_float(brightness),
+                                       C.c_float(contrast), C.c_float(half_range), M.ctypes.data_as(C.c_void_p), T.ctypes.data_as(C.c_void_p))
+    return M.reshape(3, 3), T
+
+
+def linear_transform(imgs, mats, offs, out_dtype=np.uint8):
+    torch = _torch()
+    n = len(imgs)
+    samples = (capi.ColorSample * n)()
+    for i, im in enumerate(imgs):
+        samples[i].num_pixels = im.size // 3
+        samples[i].matrix[:] = [float(v) for v in np.asarray(mats[i], np.float32).reshape(9)]
+        samples[i].offset[:] = [float(v) for v in np.asarray(offs[i], np.float32).reshape(3)]
+    plan = capi.Plan("Pointwise", max(n, 1))
+    odt = capi.UINT8 if np.dtype(out_dtype) == np.uint8 else capi.FLOAT
+    capi.check(capi.lib().dalib200LinearTransformSetup(plan.handle, n, samples, odt))
+    din = to_dev(imgs)
+    outs = [torch.empty(im.shape, dtype=torch.uint8 if odt == capi.UINT8 else torch.float32, device="cuda") for im in imgs]
+    capi.check(capi.lib().dalib200PointwiseLaunch(plan.handle, capi.ptr_array(din), capi.ptr_array(outs), capi.stream_handle()))
+    torch.cuda.synchronize()
+    return [o.cpu().numpy() for o in outs]
+
+
+def csc(imgs, in_type, out_type):
+    torch = _torch()
+    n = len(imgs)
+    ic = 1 if in_type == capi.GRAY else 3
+    oc = 1 if out_type == capi.GRAY else 3
+    npx = (C.c_int64 * n)(*[im.size // ic for im in imgs])
+    plan = capi.Plan("Pointwise", max(n, 1))
+    capi.check(capi.lib().dalib200ColorSpaceSetup(plan.handle, n, npx, in_type, out_type))
+    din = to_dev(imgs)
+    outs = [torch.empty(im.shape[:-1] + (oc,), dtype=torch.uint8, device="cuda") for im in imgs]
+    capi.check(capi.lib().dalib200PointwiseLaunch(plan.handle, capi.ptr_array(din), capi.ptr_array(outs), capi.stream_handle()))
+    torch.cuda.synchronize()
+    return [o.cpu().numpy() for o in outs]
+
+
+def spectrogram(sigs, nfft=None, window_length=512, window_step=256, power=2, center=True, reflect=True, layout="ft", window_fn=None):
+    torch = _torch()
+    n = len(sigs)
+    args = capi.SpectrogramArgs(nfft or window_length, window_length, window_step, power, int(center), int(reflect), int(layout == "ft"))
+    lens = (C.c_int64 * n)(*[int(s.size) for s in sigs])
+    plan = capi.Plan("Spectrogram", max(n, 1))
+    wf = None
+    if window_fn is not None:
+        wfa = np.ascontiguousarray(window_fn, np.float32)
+        wf = wfa.ctypes.data_as(C.c_void_p)
+    capi.check(capi.lib().dalib200SpectrogramPlanSetup(plan.handle, C.byref(args), wf, n, lens))
+    nbin = args.nfft // 2 + 1
+    din = to_dev([np.ascontiguousarray(s, np.float32) for s in sigs])
+    outs = []
+    for i in range(n):
+        nw = capi.lib().dalib200SpectrogramNumWindows(plan.handle, i)
+        outs.append(torch.empty((nbin, nw) if layout == "ft" else (nw, nbin), dtype=torch.float32, device="cuda"))
+    capi.check(capi.lib().dalib200SpectrogramLaunch(plan.handle, capi.ptr_array(din), capi.ptr_array(outs), capi.stream_handle()))
+    torch.cuda.synchronize()
+    return [o.cpu().numpy() for o in outs]
+
+
+def mel_filter_bank(specs, nfilter=128, sample_rate=44100.0, freq_low=0.0, freq_high=0.0, mel_formula="slaney", normalize=True):
+    torch = _torch()
+    n = len(specs)
+    args = capi.MelArgs(nfilter, sample_rate, freq_low, freq_high, int(mel_formula == "htk"), int(bool(normalize)))
+    nwin = (C.c_int64 * n)(*[int(s.shape[1]) for s in specs])
+    plan = capi.Plan("Mel", max(n, 1))
+    capi.check(capi.lib().dalib200MelPlanSetup(plan.handle, C.byref(args), int(specs[0].shape[0]), n, nwin))
+    din = to_dev([np.ascontiguousarray(s, np.float32) for s in specs])
+    outs = [torch.empty((nfilter, s.shape[1]), dtype=torch.float32, device="cuda") for s in specs]
+    capi.check(capi.lib().dalib200MelLaunch(plan.handle, capi.ptr_array(din), capi.ptr_array(outs), capi.stream_handle()))
+    torch.cuda.synchronize()
+    return [o.cpu().numpy() for o in outs]

@@ -1,0 +1,135 @@
+"""-m gpu parity tests for the JPEG decoder: CUDA path (through the C-ABI) vs the oracle / libjpeg-turbo.
+Bit-exact on every byte (integer pipeline)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from dali_b200 import capi  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+
+def _enc(img, q=90, ss=None, rst=0):
+    import cv2
+    params = [cv2.IMWRITE_JPEG_QUALITY, q]
+    if ss is not None:
+        params += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, ss]
+    if rst:
+        params += [cv2.IMWRITE_JPEG_RST_INTERVAL, rst]
+    ok, enc = cv2.imencode(".jpg", img, params)
+    assert ok
+    return enc.tobytes()
+
+
+def test_golden_libjpeg_turbo(golden_dir):
+    import gpu_helpers as g
+    gz = np.load(os.path.join(golden_dir, "jpeg_cv2.npz"))
+    n = len([k for k in gz.files if k.startswith("enc_")])
+    streams = [gz[f"enc_{i}"].tobytes() for i in range(n)]
+    outs, status = g.jpeg_decode(streams)
+    assert status == [0] * n
+    for i in range(n):
+        assert np.array_equal(outs[i], gz[f"dec_{i}"]), f"golden case {i}"
+
+
+def test_huffman_stage_coefficients_match_oracle():
+    import gpu_helpers as g
+    import cv2
+    streams = [_enc(g.synth_image(136, 200, 3), 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420),
+               _enc(g.synth_image(97, 61, 4), 50, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444),
+               _enc(g.synth_image(480, 640, 5), 95, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420)]
+    outs, status, plan = g.jpeg_decode(streams, want_coefs=True)
+    assert status == [0, 0, 0]
+    for si, s in enumerate(streams):
+        comps = po.jpeg_coeffs(s)
+        info = po.jpeg_info(s)
+        hs, vs, mcux, mcuy = info["hs"], info["vs"], info["mcux"], info["mcuy"]
+        # oracle layout: per component [bh][bw][64] -> MCU order
+        blocks = []
+        for my in range(mcuy):
+            for mx in range(mcux):
+                for c in range(info["ncomp"]):
+                    for v in range(vs[c]):
+                        for h in range(hs[c]):
+                            blocks.append(comps[c][my * vs[c] + v, mx * hs[c] + h])
+        want = np.stack(blocks).reshape(-1)
+        got = g.jpeg_coefs(plan, si, want.size)
+        assert np.array_equal(got, want), f"coefficients of stream {si}"
+
+
+def test_all_samplings_qualities_sizes_vs_oracle():
+    import gpu_helpers as g
+    import cv2
+    ss = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+          cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411]
+    streams = []
+    for hw in [(480, 640), (33, 47), (17, 16), (8, 8), (1, 1), (250, 3), (3, 250), (100, 101), (9, 5), (2, 2), (260, 517)]:
+        for s in ss:
+            for q in (30, 90, 100):
+                streams.append(_enc(g.synth_image(hw[0], hw[1], hw[0] * 7 + hw[1] + q), q, s))
+    outs, status = g.jpeg_decode(streams)
+    assert all(s == 0 for s in status)
+    for s, o in zip(streams, outs):
+        assert np.array_equal(o, po.jpeg_decode(s)), po.jpeg_info(s)
+
+
+def test_restart_intervals_and_gray():
+    import gpu_helpers as g
+    import cv2
+    streams = []
+    for rst in (1, 3, 7, 40):
+        for s in (cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444):
+            streams.append(_enc(g.synth_image(150, 210, rst), 85, s, rst))
+    streams.append(_enc(g.synth_image(123, 77, 9)[..., 0], 85))          # grayscale JPEG -> RGB
+    streams.append(_enc(g.synth_image(64, 64, 10)[..., 0], 70, rst=2))
+    outs, status = g.jpeg_decode(streams)
+    assert all(s == 0 for s in status)
+    for s, o in zip(streams, outs):
+        assert np.array_equal(o, po.jpeg_decode(s)), po.jpeg_info(s)
+
+
+def test_output_types_and_box_upsampling():
+    import gpu_helpers as g
+    import cv2
+    s = _enc(g.synth_image(90, 130, 11), 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420)
+    rgb = po.jpeg_decode(s)
+    (bgr,), _ = g.jpeg_decode([s], capi.BGR)
+    assert np.array_equal(bgr, rgb[..., ::-1])
+    (gray,), _ = g.jpeg_decode([s], capi.GRAY)
+    assert np.array_equal(gray[..., 0], cv2.imdecode(np.frombuffer(s, np.uint8), cv2.IMREAD_GRAYSCALE))
+    (box,), _ = g.jpeg_decode([s], capi.RGB, fancy=False)
+    assert np.array_equal(box, po.jpeg_decode(s, fancy=False))
+
+
+def test_1080p_batch_and_plan_reuse():
+    """C2-sized images, batch of 6, plan reused for a second (different) batch."""
+    import gpu_helpers as g
+    plan = capi.Plan("Jpeg", 8)
+    for base in (0, 100):
+        streams = [_enc(g.synth_image(1080, 1920, base + i), 90) for i in range(6)]
+        outs, status = g.jpeg_decode(streams, plan=plan)
+        assert status == [0] * 6
+        for s, o in zip(streams, outs):
+            assert np.array_equal(o, po.jpeg_decode(s))
+
+
+def test_truncated_stream_is_flagged_not_crashing():
+    import gpu_helpers as g
+    s = _enc(g.synth_image(200, 300, 12), 90)
+    cut = s[: len(s) // 2]
+    outs, status = g.jpeg_decode([cut, s])
+    assert status[0] == 1 and status[1] == 0
+    assert np.array_equal(outs[1], po.jpeg_decode(s))
+
+
+def test_unsupported_streams_fail_loudly():
+    import gpu_helpers as g
+    import cv2
+    img = g.synth_image(64, 64, 13)
+    ok, prog = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    with pytest.raises(capi.DaliB200Error, match="progressive"):
+        g.jpeg_decode([prog.tobytes()])
+    with pytest.raises(capi.DaliB200Error):
+        g.jpeg_decode([b"\xff\xd8\xff\xd9"])

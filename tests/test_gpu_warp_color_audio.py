@@ -1,0 +1,165 @@
+"""-m gpu parity tests for WarpAffine, Hsv / linear colour transform, ColorSpaceConversion, Spectrogram and
+MelFilterBank: CUDA path (through the C-ABI) vs the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from dali_b200 import capi  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+def _rot(rng, h, w):
+    ang, s = rng.uniform(-0.5, 0.5), rng.uniform(0.7, 1.4)
+    c, si = np.cos(ang) * s, np.sin(ang) * s
+    cx, cy = w / 2, h / 2
+    return np.float32([[c, -si, cx - c * cx + si * cy + rng.uniform(-5, 5)], [si, c, cy - si * cx - c * cy + rng.uniform(-5, 5)]])
+
+
+def test_warp_golden(golden_dir):
+    import gpu_helpers as g
+    gz = np.load(os.path.join(golden_dir, "warp_color_ref.npz"))
+    img, M = gz["in"], gz["M"]
+    for interp in (0, 1):
+        for fill, fn in ((None, "clamp"), (0.0, "fill0")):
+            (out,) = g.warp_affine([img], [M], None, interp, fill)
+            assert np.array_equal(out, gz[f"out_{interp}_{fn}"]), (interp, fn)
+
+
+def test_warp_random_batch_bit_exact():
+    """Includes outputs wider than 256 px: the reference's incremental coordinates are replayed exactly."""
+    import gpu_helpers as g
+    rng = np.random.default_rng(51)
+    for interp in (0, 1):
+        for fill in (None, 42.0):
+            for odt in (np.uint8, np.float32):
+                imgs, mats, outs = [], [], []
+                for it in range(10):
+                    H, W = [int(v) for v in rng.integers(2, 400, 2)]
+                    C = 3 if it % 4 else 1
+                    imgs.append(rng.integers(0, 256, (H, W, C)).astype(np.uint8))
+                    mats.append(_rot(rng, H, W))
+                    outs.append((int(rng.integers(1, 300)), int(rng.integers(1, 900))) if it % 2 else (H, W))
+                got = g.warp_affine(imgs, mats, outs, interp, fill, odt)
+                for im, M, hw, o in zip(imgs, mats, outs, got):
+                    want = po.warp_affine(im, M, hw, interp, fill, odt)
+                    assert np.array_equal(bits(o), bits(want)), (im.shape, hw, interp, fill, odt)
+
+
+def test_warp_c3_frame():
+    import gpu_helpers as g
+    rng = np.random.default_rng(52)
+    img = rng.integers(0, 256, (720, 1280, 3)).astype(np.uint8)
+    M = _rot(rng, 720, 1280)
+    (o,) = g.warp_affine([img], [M], None, 1, 0.0)
+    assert np.array_equal(o, po.warp_affine(img, M, None, 1, 0.0))
+
+
+def test_hsv_and_linear_transform():
+    import gpu_helpers as g
+    rng = np.random.default_rng(53)
+    imgs, Ms, Ts = [], [], []
+    for it in range(12):
+        H, W = [int(v) for v in rng.integers(1, 200, 2)]
+        imgs.append(rng.integers(0, 256, (H, W, 3)).astype(np.uint8))
+        M, T = g.color_twist_matrix(rng.uniform(-30, 30), rng.uniform(0.7, 1.3), rng.uniform(0.8, 1.2))
+        Mo, To = po.color_twist_matrix(0, 1, 1)
+        Ms.append(M); Ts.append(T)
+    for odt in (np.uint8, np.float32):
+        got = g.linear_transform(imgs, Ms, Ts, odt)
+        for im, M, T, o in zip(imgs, Ms, Ts, got):
+            assert np.array_equal(bits(o), bits(po.linear_transform(im, M, T, odt)))
+    # identity
+    Mi, Ti = g.color_twist_matrix(0.0, 1.0, 1.0)
+    (o,) = g.linear_transform([imgs[0]], [Mi], [Ti])
+    assert np.array_equal(o, imgs[0])
+
+
+def test_hsv_golden(golden_dir):
+    import gpu_helpers as g
+    gz = np.load(os.path.join(golden_dir, "warp_color_ref.npz"))
+    for i, (h, s, v) in enumerate(gz["hsv_args"]):
+        M, T = g.color_twist_matrix(float(h), float(s), float(v))
+        assert np.array_equal(M, gz[f"hsv_M_{i}"])
+        (o,) = g.linear_transform([gz["in"]], [M], [T])
+        assert np.array_equal(o, gz[f"hsv_out_{i}"])
+
+
+def test_color_space_conversion_all_pairs():
+    import gpu_helpers as g
+    rng = np.random.default_rng(54)
+    cube = np.stack(np.meshgrid(np.arange(0, 256, 5), np.arange(0, 256, 3), np.arange(0, 256, 7), indexing="ij"), -1)
+    cube = cube.reshape(-1, 1, 3).astype(np.uint8)
+    rgb = [cube, rng.integers(0, 256, (33, 47, 3)).astype(np.uint8), rng.integers(0, 256, (1, 1, 3)).astype(np.uint8)]
+    gray = [np.arange(256, dtype=np.uint8).reshape(16, 16, 1), rng.integers(0, 256, (5, 7, 1)).astype(np.uint8)]
+    T = {"RGB": (capi.RGB, po.IT_RGB), "BGR": (capi.BGR, po.IT_BGR), "GRAY": (capi.GRAY, po.IT_GRAY), "YCbCr": (capi.YCbCr, po.IT_YCBCR)}
+    for a in T:
+        for b in T:
+            ins = gray if a == "GRAY" else rgb
+            got = g.csc(ins, T[a][0], T[b][0])
+            for im, o in zip(ins, got):
+                assert np.array_equal(o, po.csc(im, T[a][1], T[b][1])), (a, b)
+
+
+def _clip(rng, n, sr=16000):
+    t = np.arange(n) / sr
+    x = sum(rng.uniform(0.05, 0.3) * np.sin(2 * np.pi * rng.uniform(50, 7000) * t + rng.uniform(0, 6)) for _ in range(5))
+    return np.clip(x + 0.05 * rng.normal(0, 1, n), -1, 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("cfg", [dict(nfft=1024, window_length=1024, window_step=256), dict(nfft=1024, window_length=512, window_step=256),
+                                 dict(nfft=512, window_length=400, window_step=160, center=False),
+                                 dict(nfft=2048, window_length=2048, window_step=512, reflect=False),
+                                 dict(nfft=256, window_length=256, window_step=64, power=1, layout="tf")])
+def test_spectrogram_vs_oracle(cfg):
+    """Stated tolerance: 2e-4 of the spectrogram maximum (the reference's own STFT GPU test bound,
+    dali/kernels/signal/fft/stft_gpu_test.cu:246: EqualEpsRel(2e-5, 2e-4)); the oracle is a double-precision DFT."""
+    import gpu_helpers as g
+    rng = np.random.default_rng(61)
+    sigs = [_clip(rng, n) for n in (16000, 4000, 2048 + 7, 33001)]
+    got = g.spectrogram(sigs, **cfg)
+    for s, o in zip(sigs, got):
+        want = po.spectrogram(s, **cfg)
+        assert o.shape == want.shape
+        assert np.abs(o - want).max() <= 2e-4 * want.max()
+        # and far tighter in practice
+        assert np.abs(o - want).max() <= 5e-6 * want.max()
+
+
+def test_spectrogram_c4_shape_and_unsupported():
+    import gpu_helpers as g
+    rng = np.random.default_rng(62)
+    (o,) = g.spectrogram([_clip(rng, 160000)], nfft=1024, window_length=1024, window_step=256)
+    assert o.shape == (513, 626)
+    with pytest.raises(capi.DaliB200Error, match="powers of two"):
+        g.spectrogram([_clip(rng, 4000)], nfft=400, window_length=400, window_step=160)
+
+
+def test_mel_filter_bank_bit_exact():
+    import gpu_helpers as g
+    rng = np.random.default_rng(63)
+    specs = [po.spectrogram(_clip(rng, n), nfft=1024, window_length=1024, window_step=256) for n in (16000, 5000, 160000)]
+    for (nf, sr, fl, fh, formula, norm) in [(128, 16000.0, 0.0, 8000.0, "slaney", True), (80, 16000.0, 20.0, 7600.0, "htk", False),
+                                            (64, 44100.0, 0.0, 0.0, "slaney", True), (40, 22050.0, 100.0, 9000.0, "htk", True)]:
+        got = g.mel_filter_bank(specs, nf, sr, fl, fh, formula, norm)
+        for s, o in zip(specs, got):
+            assert np.array_equal(bits(o), bits(po.mel_filter_bank(s, nf, sr, fl, fh, formula, norm))), (nf, formula)
+
+
+def test_audio_golden(golden_dir):
+    import gpu_helpers as g
+    gz = np.load(os.path.join(golden_dir, "audio_ref.npz"))
+    (spec,) = g.spectrogram([gz["sig"]], nfft=1024, window_length=512, window_step=256)
+    want = gz["spec_nfft1024_power2_float64"]
+    assert np.abs(spec - want).max() <= 5e-6 * want.max()
+    s32 = want.astype(np.float32)
+    (m,) = g.mel_filter_bank([s32], 128, 16000.0, 0.0, 8000.0, "slaney", True)
+    assert np.array_equal(bits(m), bits(gz["mel_128_16k_slaney_norm"]))
+    (m2,) = g.mel_filter_bank([s32], 40, 16000.0, 20.0, 7600.0, "htk", False)
+    assert np.array_equal(bits(m2), bits(gz["mel_40_16k_htk_nonorm"]))

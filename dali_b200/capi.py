@@ -12,13 +12,13 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdali_b200.so")
 
-UINT8, INT16, FLOAT16, FLOAT = 0, 3, 8, 9
+UINT8, INT16, FLOAT16, FLOAT = 0, 5, 8, 9
 RGB, BGR, GRAY, YCbCr = 0, 1, 2, 3
 FILTER_NN, FILTER_LINEAR, FILTER_TRIANGULAR, FILTER_GAUSSIAN, FILTER_CUBIC, FILTER_LANCZOS3 = range(6)
 LAYOUT_HWC, LAYOUT_CHW = 0, 1
 
 EXPORTS = [
-    "dalib200GetLastError", "dalib200GetVersion", "dalib200GetLaunchCount",
+    "dalib200GetLastError", "dalib200GetVersion", "dalib200GetLaunchCount", "dalib200ProfilingEnable", "dalib200ProfilingCollect",
     "dalib200JpegGetInfo", "dalib200JpegPlanCreate", "dalib200JpegPlanDestroy", "dalib200JpegPlanSetup",
     "dalib200JpegPlanGetInfo", "dalib200JpegPlanStagedBytes", "dalib200JpegUpload", "dalib200JpegLaunch",
     "dalib200JpegGetStatus", "dalib200JpegDebugGetCoefficients",
@@ -98,6 +98,20 @@ def lib():
 def check(rc):
     if rc != 0:
         raise DaliB200Error(lib().dalib200GetLastError().decode("utf-8", "replace") + f" (status {rc})")
+
+
+def profiling(on):
+    check(lib().dalib200ProfilingEnable(int(bool(on))))
+
+
+def profiling_collect(max_records=65536):
+    """[(kernel name, ms)] of every launch since the last collect (device-timed with CUDA events)."""
+    names = C.create_string_buffer(max_records * 32)
+    ms = (C.c_float * max_records)()
+    cnt = C.c_int(0)
+    check(lib().dalib200ProfilingCollect(names, 32, ms, max_records, C.byref(cnt)))
+    raw = names.raw
+    return [(raw[i * 32:(i + 1) * 32].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(cnt.value)]
 
 
 def launch_count():

@@ -373,6 +373,7 @@ int dalib200SpectrogramLaunch(dalib200SpectrogramPlan *p, const void *const *in_
     p->smem_set = true;
   }
   const int grid = (int)std::min<int64_t>(p->total_groups, (int64_t)NumSMs() * 8);
+  ProfScope ps_("spectrogram_stft", stream);
   spectrogram_kernel<<<grid, 256, p->smem, stream>>>(reinterpret_cast<const SpecDesc *>(p->arena.dev), p->n, p->total_groups, P,
                                                     p->d_window, p->d_twiddle);
   CountLaunch();
@@ -452,6 +453,7 @@ int dalib200MelLaunch(dalib200MelPlan *p, const void *const *in_ptrs, void *cons
   DB_CUDA(cudaEventRecord(p->uploaded, stream));
   p->pending = true;
   const int grid = (int)std::min<int64_t>(p->total_items, (int64_t)NumSMs() * 32);
+  ProfScope ps_("mel_filter_bank", stream);
   mel_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const MelDesc *>(p->arena.dev), p->n, p->total_items, p->nfilter,
                                        reinterpret_cast<const int32_t *>(p->tables.dev),
                                        reinterpret_cast<const float *>(p->tables.dev + o_up),

@@ -291,6 +291,7 @@ int dalib200CmnLaunch(dalib200CmnPlan *p, const void *const *in_ptrs, void *cons
   if (p->total_units > 0) {
     int64_t blocks = (p->total_units + 7) / 8;
     int grid = (int)std::min<int64_t>(blocks, (int64_t)sms * 8);
+    ProfScope ps_("cmn_hwc2chw", stream);
     if (p->out_dtype == DALIB200_FLOAT)
       cmn_hwc2chw_kernel<float><<<grid, 256, 0, stream>>>(dd, p->n, p->total_units, p->out_c);
     else
@@ -301,6 +302,7 @@ int dalib200CmnLaunch(dalib200CmnPlan *p, const void *const *in_ptrs, void *cons
     int64_t blocks = (p->total_elems + 255) / 256;
     int grid = (int)std::min<int64_t>(blocks, (int64_t)sms * 16);
     const int chw = p->out_layout == DALIB200_LAYOUT_CHW;
+    ProfScope ps_("cmn_generic", stream);
     if (p->out_dtype == DALIB200_FLOAT)
       cmn_generic_kernel<float><<<grid, 256, 0, stream>>>(dd, p->n, p->total_elems, p->out_c, chw);
     else

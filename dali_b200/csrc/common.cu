@@ -54,9 +54,51 @@ int NumSMs() {
   return n;
 }
 
+// ---------------------------------------------------------------------------------------------
+static bool g_prof_on = false;
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t ProfEvent() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void ProfBegin(const char *name, cudaStream_t s) {
+  if (!g_prof_on) return;
+  ProfRec r{name, ProfEvent(), ProfEvent()};
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+}
+void ProfEnd(cudaStream_t s) {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().b, s);
+}
+
 }  // namespace dalib200
 
 extern "C" {
+int dalib200ProfilingEnable(int on) { dalib200::g_prof_on = on != 0; return DALIB200_SUCCESS; }
+// Synchronises, writes up to `max` records (names: `name_stride` bytes each, NUL terminated) and clears the log.
+int dalib200ProfilingCollect(char *names, int name_stride, float *ms, int max, int *count) {
+  using namespace dalib200;  // NOLINT
+  int n = 0;
+  for (auto &r : g_prof) {
+    cudaEventSynchronize(r.b);
+    float t = 0;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    if (n < max) {
+      if (names && name_stride > 0) { snprintf(names + (size_t)n * name_stride, name_stride, "%s", r.name); }
+      if (ms) ms[n] = t;
+      n++;
+    }
+    g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+  }
+  g_prof.clear();
+  if (count) *count = n;
+  return DALIB200_SUCCESS;
+}
 const char *dalib200GetLastError(void) { return dalib200::tls_error.c_str(); }
 int dalib200GetVersion(void) { return 100; }
 uint64_t dalib200GetLaunchCount(void) { return dalib200::g_launch_count.load(); }

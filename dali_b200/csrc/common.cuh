@@ -40,6 +40,16 @@ struct DescArena {
 
 int NumSMs();
 
+// Optional per-launch timing (CUDA events on the launching stream), switched on by dalib200ProfilingEnable.
+// bench.py uses it to time the dominant kernel live inside the timed region.
+void ProfBegin(const char *name, cudaStream_t s);
+void ProfEnd(cudaStream_t s);
+struct ProfScope {
+  cudaStream_t s;
+  ProfScope(const char *name, cudaStream_t st) : s(st) { ProfBegin(name, s); }
+  ~ProfScope() { ProfEnd(s); }
+};
+
 // ---------------------------------------------------------------------------------------------
 // numerics shared by the kernels -- these restate the reference HOST (CPU backend) conventions,
 // which are the parity target.

@@ -321,8 +321,12 @@ __global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx c
         st.n = 0;
         decode_range<false>(br, &ts, im, st, min((nxt + 1) << cx.log2_sub, clean_bits), nullptr, 0, 0);
         const uint64_t ns = pack_state(st.p, st.c, st.z);
-        if (cx.s_state[g + t] == ns) active = false;
-        else { cx.s_state[g + t] = ns; cx.s_n[g + t] = st.n; }
+        // The slot count is ALWAYS written: a chain that merely converged inside this subsequence left a
+        // count computed from a wrong entry state; the last visitor of an entry is the one whose entry state
+        // is right (chains started further left arrive later), so the last write wins.
+        const bool same = cx.s_state[g + t] == ns;
+        cx.s_state[g + t] = ns; cx.s_n[g + t] = st.n;
+        if (same) active = false;
         t++;
       }
     }
@@ -366,8 +370,9 @@ __global__ void __launch_bounds__(1024) huff_sync_inter_kernel(HuffCtx cx) {
         st.n = 0;
         decode_range<false>(br, &ts, im, st, min((jl + k + 1) << cx.log2_sub, clean_bits), nullptr, 0, 0);
         const uint64_t ns = pack_state(st.p, st.c, st.z);
-        if (cx.s_state[g0 + k] == ns) { synced = true; break; }
-        cx.s_state[g0 + k] = ns; cx.s_n[g0 + k] = st.n;
+        const bool same = cx.s_state[g0 + k] == ns;
+        cx.s_state[g0 + k] = ns; cx.s_n[g0 + k] = st.n;     // always: see huff_sync_intra_kernel
+        if (same) { synced = true; break; }
       }
       if (!synced) changed = 1;     // the exit state of this block moved: the next boundary must be redone
     }
@@ -1189,29 +1194,29 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   cudaStream_t s = stream;
   // the clean stream must be zero-padded behind every unit (the bit reader peeks ahead)
   DB_CUDA(cudaMemsetAsync(p->d_clean, 0, p->clean_bytes + 64, s));
-  DB_CUDA(cudaMemsetAsync(p->d_coef, 0, (size_t)p->total_coefs * sizeof(int16_t), s));
+  { ProfScope ps_("jpeg_memset_coef", s); DB_CUDA(cudaMemsetAsync(p->d_coef, 0, (size_t)p->total_coefs * sizeof(int16_t), s)); }
   DB_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * p->n, s));
   {
     const int grid = (int)std::min<uint32_t>(p->nchunks, (uint32_t)sms * 16);
-    unstuff_count_kernel<<<grid, 256, 0, s>>>(d_raw, d_units, nunits, p->nchunks, p->d_chunk);
-    unstuff_scan_kernel<<<(nunits + 127) / 128, 128, 0, s>>>(d_units, nunits, p->d_chunk, p->d_unit_len);
-    unstuff_scatter_kernel<<<grid, 256, 0, s>>>(d_raw, d_units, nunits, p->nchunks, p->d_chunk, p->d_clean);
+    { ProfScope ps_("jpeg_unstuff_count", s); unstuff_count_kernel<<<grid, 256, 0, s>>>(d_raw, d_units, nunits, p->nchunks, p->d_chunk); }
+    { ProfScope ps_("jpeg_unstuff_scan", s); unstuff_scan_kernel<<<(nunits + 127) / 128, 128, 0, s>>>(d_units, nunits, p->d_chunk, p->d_unit_len); }
+    { ProfScope ps_("jpeg_unstuff_scatter", s); unstuff_scatter_kernel<<<grid, 256, 0, s>>>(d_raw, d_units, nunits, p->nchunks, p->d_chunk, p->d_clean); }
     CountLaunch(3);
   }
   HuffCtx cx;
   cx.images = d_images; cx.nimages = p->n; cx.units = d_units; cx.unit_clean_len = p->d_unit_len; cx.tables = d_tables;
   cx.clean = p->d_clean; cx.s_state = p->d_state; cx.s_n = p->d_n; cx.coef = p->d_coef; cx.log2_sub = p->log2_sub;
   cx.status = p->d_status;
-  huff_sync_intra_kernel<<<p->total_blocks_sync, kSyncThreads, 0, s>>>(cx);
-  huff_sync_inter_kernel<<<p->n, 1024, 0, s>>>(cx);
-  huff_write_kernel<<<p->total_blocks_sync, kSyncThreads, 0, s>>>(cx);
-  dc_scan_kernel<<<p->n, 1024, 0, s>>>(d_images, p->d_coef);
+  { ProfScope ps_("jpeg_huff_sync_intra", s); huff_sync_intra_kernel<<<p->total_blocks_sync, kSyncThreads, 0, s>>>(cx); }
+  { ProfScope ps_("jpeg_huff_sync_inter", s); huff_sync_inter_kernel<<<p->n, 1024, 0, s>>>(cx); }
+  { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_sync, kSyncThreads, 0, s>>>(cx); }
+  { ProfScope ps_("jpeg_dc_scan", s); dc_scan_kernel<<<p->n, 1024, 0, s>>>(d_images, p->d_coef); }
   {
     const int64_t total_blocks = p->total_coefs / 64;
     const int grid = (int)std::min<int64_t>((total_blocks + 127) / 128, (int64_t)sms * 32);
-    idct_kernel<<<grid, 128, 0, s>>>(d_images, p->n, total_blocks, p->d_coef, d_quants, p->d_planes);
+    { ProfScope ps_("jpeg_idct", s); idct_kernel<<<grid, 128, 0, s>>>(d_images, p->n, total_blocks, p->d_coef, d_quants, p->d_planes); }
     const int grid2 = (int)std::min<int64_t>((p->total_quads + 255) / 256, (int64_t)sms * 32);
-    color_kernel<<<grid2, 256, 0, s>>>(d_images, d_quads, p->n, p->total_quads, p->d_planes);
+    { ProfScope ps_("jpeg_upsample_color", s); color_kernel<<<grid2, 256, 0, s>>>(d_images, d_quads, p->n, p->total_quads, p->d_planes); }
   }
   CountLaunch(6);
   DB_CUDA(cudaGetLastError());

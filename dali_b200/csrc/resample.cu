@@ -569,7 +569,7 @@ int dalib200ResampleLaunch(dalib200ResamplePlan *p, const void *const *in_ptrs, 
       DB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       p->smem_opted[slot] = true;
     }
-    kern<<<grid, 256, smem, stream>>>(dd, tb, p->n, p->total_tiles);
+    { ProfScope ps_("resample_fused", stream); kern<<<grid, 256, smem, stream>>>(dd, tb, p->n, p->total_tiles); }
     return DALIB200_SUCCESS;
   };
   if (p->in_dtype == DALIB200_UINT8 && p->out_dtype == DALIB200_UINT8) rc = launch(resample_fused_kernel<uint8_t, uint8_t>, 0);

@@ -199,6 +199,7 @@ int dalib200WarpLaunch(dalib200WarpPlan *p, const void *const *in_ptrs, void *co
   p->pending = true;
   const auto *dd = reinterpret_cast<const WarpDesc *>(p->arena.dev);
   const int grid = (int)std::min<int64_t>(p->total_tiles, (int64_t)NumSMs() * 16);
+  ProfScope ps_("warp_affine", stream);
   const bool lin = p->interp == 1, clampb = !p->use_fill, u8 = p->out_dtype == DALIB200_UINT8;
 #define LAUNCH(O, L, Cc) warp_affine_kernel<O, L, Cc><<<grid, 256, 0, stream>>>(dd, p->n, p->total_tiles, p->border)
   if (u8) {

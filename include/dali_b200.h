@@ -25,7 +25,7 @@ extern "C" {
 typedef struct CUstream_st *dalib200Stream_t;   /* == cudaStream_t */
 
 /* Data type ids equal the reference's DALIDataType (include/dali/core/dali_data_type.h:44-57). */
-enum { DALIB200_UINT8 = 0, DALIB200_INT16 = 3, DALIB200_FLOAT16 = 8, DALIB200_FLOAT = 9 };
+enum { DALIB200_UINT8 = 0, DALIB200_INT16 = 5, DALIB200_FLOAT16 = 8, DALIB200_FLOAT = 9 };
 /* Image types equal DALIImageType (include/dali/core/common.h:156-162). */
 enum { DALIB200_RGB = 0, DALIB200_BGR = 1, DALIB200_GRAY = 2, DALIB200_YCbCr = 3 };
 /* Resampling filters equal kernels::ResamplingFilterType (dali/kernels/imgproc/resample/params.h:27-34). */
@@ -46,6 +46,10 @@ const char *dalib200GetLastError(void);
 int dalib200GetVersion(void);
 /* number of kernels this library has launched from the calling process (bench.py's gpu_launches) */
 uint64_t dalib200GetLaunchCount(void);
+/* Per-launch device timing with CUDA events on the launching stream (off by default).  Collect synchronises,
+ * returns the records in launch order and clears the log. */
+int dalib200ProfilingEnable(int on);
+int dalib200ProfilingCollect(char *names, int name_stride, float *ms, int max, int *count);
 
 /* ------------------------------------------------------------------------------------------------
  * JPEG decode (Huffman + dequant + IDCT + chroma upsampling + YCbCr->RGB), baseline sequential.

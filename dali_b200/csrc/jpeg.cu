@@ -69,6 +69,7 @@ struct JpegImage {
   int32_t plane_w[3], plane_h[3];          // padded plane sizes (multiples of the MCU)
   int32_t out_type, fancy;
   int32_t is_rgb;                          // Adobe transform 0 / RGB ids: no YCbCr conversion
+  int32_t fast_color;                      // eligible for color_fast_kernel
 };
 
 struct JpegUnit {
@@ -628,6 +629,7 @@ __global__ void __launch_bounds__(256) color_kernel(const JpegImage *__restrict_
     int lo = 0, hi = nimages - 1;
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (first_quad[mid] <= gq) lo = mid; else hi = mid - 1; }
     const JpegImage &im = images[lo];
+    if (im.fast_color) continue;
     const int64_t q = gq - first_quad[lo];
     const int qpr = (im.width + 3) >> 2;
     const int y = (int)(q / qpr), x0 = (int)(q % qpr) << 2;
@@ -668,6 +670,135 @@ __global__ void __launch_bounds__(256) color_kernel(const JpegImage *__restrict_
     } else {
       for (int k = 0; k < nb; k++) o[k] = px[k];
     }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// C1 fast path: 3-component YCbCr -> RGB/BGR.  One CTA = one output row segment of 1024 pixels of one image,
+// one thread = 8 consecutive pixels: one 8-byte luma load, word loads of the two chroma rows, 24 output bytes.
+constexpr int kColorSeg = 1024;
+
+template <int HEXP, int VEXP>
+__device__ __forceinline__ void chroma8(const uint8_t *__restrict__ pl, int pw, int dw, int dh, int fancy, int x0, int y, int *v) {
+  if (HEXP == 1 && VEXP == 1) {
+    const uint2 w = *reinterpret_cast<const uint2 *>(pl + (int64_t)y * pw + x0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = (w.x >> (8 * k)) & 0xFF; v[4 + k] = (w.y >> (8 * k)) & 0xFF; }
+    return;
+  }
+  if (HEXP == 2) {
+    const int i0 = x0 >> 1;                       // 4 chroma samples i0..i0+3 (+ one neighbour each side)
+    const bool fy = fancy && dw > 2;
+    int cs[6];
+    if (VEXP == 2) {
+      const int r0i = y >> 1;
+      int r1i = (y & 1) ? r0i + 1 : r0i - 1;
+      r1i = min(max(r1i, 0), dh - 1);
+      const uint8_t *r0 = pl + (int64_t)r0i * pw, *r1 = pl + (int64_t)r1i * pw;
+      const uint32_t a = *reinterpret_cast<const uint32_t *>(r0 + i0), b = *reinterpret_cast<const uint32_t *>(r1 + i0);
+      if (!fy) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[2 * k] = v[2 * k + 1] = (a >> (8 * k)) & 0xFF;
+        return;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) cs[1 + k] = 3 * (int)((a >> (8 * k)) & 0xFF) + (int)((b >> (8 * k)) & 0xFF);
+      cs[0] = i0 > 0 ? 3 * r0[i0 - 1] + r1[i0 - 1] : 0;
+      cs[5] = i0 + 4 < dw ? 3 * r0[i0 + 4] + r1[i0 + 4] : 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int i = i0 + k, cur = cs[1 + k];
+        v[2 * k] = i == 0 ? (cur * 4 + 8) >> 4 : (cur * 3 + cs[k] + 8) >> 4;
+        v[2 * k + 1] = i >= dw - 1 ? (cur * 4 + 7) >> 4 : (cur * 3 + cs[2 + k] + 7) >> 4;
+      }
+    } else {
+      const uint8_t *r = pl + (int64_t)y * pw;
+      const uint32_t a = *reinterpret_cast<const uint32_t *>(r + i0);
+      if (!fy) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[2 * k] = v[2 * k + 1] = (a >> (8 * k)) & 0xFF;
+        return;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) cs[1 + k] = (a >> (8 * k)) & 0xFF;
+      cs[0] = i0 > 0 ? r[i0 - 1] : 0;
+      cs[5] = i0 + 4 < dw ? r[i0 + 4] : 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int i = i0 + k, cur = cs[1 + k];
+        v[2 * k] = i == 0 ? cur : (cur * 3 + cs[k] + 1) >> 2;
+        v[2 * k + 1] = i >= dw - 1 ? cur : (cur * 3 + cs[2 + k] + 2) >> 2;
+      }
+    }
+    return;
+  }
+  // HEXP == 1, VEXP == 2 (4:4:0)
+  {
+    const int r0i = y >> 1;
+    int r1i = (y & 1) ? r0i + 1 : r0i - 1;
+    r1i = min(max(r1i, 0), dh - 1);
+    const uint2 a = *reinterpret_cast<const uint2 *>(pl + (int64_t)r0i * pw + x0);
+    const uint2 b = *reinterpret_cast<const uint2 *>(pl + (int64_t)r1i * pw + x0);
+    const int bias = (y & 1) ? 2 : 1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int p0 = ((k < 4 ? a.x : a.y) >> (8 * (k & 3))) & 0xFF, p1 = ((k < 4 ? b.x : b.y) >> (8 * (k & 3))) & 0xFF;
+      v[k] = fancy ? (p0 * 3 + p1 + bias) >> 2 : p0;
+    }
+  }
+}
+
+template <int HEXP, int VEXP>
+__device__ __forceinline__ void color_row8(const JpegImage &im, const uint8_t *__restrict__ planes, int x0, int y) {
+  const int W = im.width, H = im.height;
+  const uint2 yw = *reinterpret_cast<const uint2 *>(planes + im.plane_off[0] + (int64_t)y * im.plane_w[0] + x0);
+  const int dw = (W + HEXP - 1) / HEXP, dh = (H + VEXP - 1) / VEXP;
+  int cb[8], cr[8];
+  chroma8<HEXP, VEXP>(planes + im.plane_off[1], im.plane_w[1], dw, dh, im.fancy, x0, y, cb);
+  chroma8<HEXP, VEXP>(planes + im.plane_off[2], im.plane_w[2], dw, dh, im.fancy, x0, y, cr);
+  uint8_t px[24];
+  const bool bgr = im.out_type == DALIB200_BGR;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int yy = ((k < 4 ? yw.x : yw.y) >> (8 * (k & 3))) & 0xFF;
+    const int cbm = cb[k] - 128, crm = cr[k] - 128;
+    const int r = clamp255(yy + ((91881 * crm + 32768) >> 16));
+    const int g = clamp255(yy + ((-22554 * cbm + 32768 - 46802 * crm) >> 16));
+    const int b = clamp255(yy + ((116130 * cbm + 32768) >> 16));
+    px[3 * k] = bgr ? b : r; px[3 * k + 1] = g; px[3 * k + 2] = bgr ? r : b;
+  }
+  uint8_t *o = im.out + ((int64_t)y * W + x0) * 3;
+  const int nx = min(8, W - x0);
+  if (nx == 8 && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+    uint2 *o8 = reinterpret_cast<uint2 *>(o);
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const uint32_t lo = px[8 * q] | (px[8 * q + 1] << 8) | (px[8 * q + 2] << 16) | ((uint32_t)px[8 * q + 3] << 24);
+      const uint32_t hi = px[8 * q + 4] | (px[8 * q + 5] << 8) | (px[8 * q + 6] << 16) | ((uint32_t)px[8 * q + 7] << 24);
+      o8[q] = make_uint2(lo, hi);
+    }
+  } else {
+    for (int k = 0; k < nx * 3; k++) o[k] = px[k];
+  }
+}
+
+// items: per image height * ceil(width / kColorSeg); images not eligible for the fast path own zero items
+__global__ void __launch_bounds__(128) color_fast_kernel(const JpegImage *__restrict__ images, const int64_t *__restrict__ first_item,
+                                                         int nimages, int64_t total_items, const uint8_t *__restrict__ planes) {
+  for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+    int lo = 0, hi = nimages - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (first_item[mid] <= item) lo = mid; else hi = mid - 1; }
+    const JpegImage &im = images[lo];
+    const int64_t li = item - first_item[lo];
+    const int segs = (im.width + kColorSeg - 1) / kColorSeg;
+    const int y = (int)(li / segs), x0 = (int)(li % segs) * kColorSeg + threadIdx.x * 8;
+    if (x0 >= im.width) continue;
+    const int hexp = im.hmax, vexp = im.vmax;     // chroma is 1x1 (checked on the host)
+    if (hexp == 2 && vexp == 2) color_row8<2, 2>(im, planes, x0, y);
+    else if (hexp == 1 && vexp == 1) color_row8<1, 1>(im, planes, x0, y);
+    else if (hexp == 2 && vexp == 1) color_row8<2, 1>(im, planes, x0, y);
+    else color_row8<1, 2>(im, planes, x0, y);
   }
 }
 
@@ -843,17 +974,17 @@ struct dalib200JpegPlan {
   std::vector<JpegUnit> units;
   std::vector<TableSet> tables;
   std::vector<QuantSet> quants;
-  std::vector<int64_t> first_quad;
+  std::vector<int64_t> first_quad, first_item;
   std::vector<const uint8_t *> src_ptr;     // host pointers of the scan data (for staging)
   size_t raw_bytes = 0, clean_bytes = 0;
   uint32_t nchunks = 0;
-  int64_t total_subseq = 0, total_coefs = 0, total_plane_bytes = 0, total_quads = 0;
+  int64_t total_subseq = 0, total_coefs = 0, total_plane_bytes = 0, total_quads = 0, total_items = 0;
   int total_blocks_sync = 0;
   int log2_sub = 10;
   // staging (pinned) and device buffers -- grow only
   uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;
   uint8_t *d_stage = nullptr; size_t d_stage_cap = 0;
-  size_t desc_bytes = 0, off_images = 0, off_units = 0, off_tables = 0, off_quants = 0, off_quads = 0, off_raw = 0;
+  size_t desc_bytes = 0, off_images = 0, off_units = 0, off_tables = 0, off_quants = 0, off_quads = 0, off_items = 0, off_raw = 0;
   uint8_t *d_clean = nullptr; size_t d_clean_cap = 0;
   uint32_t *d_chunk = nullptr; size_t d_chunk_cap = 0;
   uint32_t *d_unit_len = nullptr; size_t d_unit_cap = 0;
@@ -934,10 +1065,11 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
   p->images.assign(n, JpegImage());
   p->units.clear(); p->tables.clear(); p->quants.clear(); p->src_ptr.clear();
   p->first_quad.assign(n, 0);
+  p->first_item.assign(n, 0);
   std::map<std::string, int> table_cache, quant_cache;
   size_t raw = 0, clean = 0;
   uint32_t chunks = 0;
-  int64_t subseq = 0, coefs = 0, planes = 0, quads = 0;
+  int64_t subseq = 0, coefs = 0, planes = 0, quads = 0, items = 0;
   int sync_blocks = 0;
   // subsequence size: aim for >= ~300k subsequences per batch, between 32 and 256 bytes
   size_t total_len = 0;
@@ -1069,12 +1201,16 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
       im.plane_off[c] = planes;
       planes += Align((size_t)im.plane_w[c] * im.plane_h[c], 16);
     }
+    im.fast_color = j.ncomp == 3 && !im.is_rgb && (output_type == DALIB200_RGB || output_type == DALIB200_BGR) &&
+                    ((j.hmax == 2 && j.vmax <= 2) || (j.hmax == 1 && j.vmax <= 2));
     p->first_quad[i] = quads;
-    quads += (int64_t)((j.width + 3) / 4) * j.height;
+    p->first_item[i] = items;
+    if (im.fast_color) items += (int64_t)((j.width + kColorSeg - 1) / kColorSeg) * j.height;
+    else quads += (int64_t)((j.width + 3) / 4) * j.height;
   }
   DB_CHECK_ARG(raw < (1ull << 32) && clean < (1ull << 32), "decoders.image: batch of encoded data exceeds 4 GiB");
   p->raw_bytes = raw; p->clean_bytes = clean; p->nchunks = chunks;
-  p->total_subseq = subseq; p->total_coefs = coefs; p->total_plane_bytes = planes; p->total_quads = quads;
+  p->total_subseq = subseq; p->total_coefs = coefs; p->total_plane_bytes = planes; p->total_quads = quads; p->total_items = items;
   p->total_blocks_sync = sync_blocks;
   // ---- pack descriptors + raw scan bytes into pinned staging
   size_t off = 0;
@@ -1083,6 +1219,7 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
   p->off_tables = off; off += Align(sizeof(TableSet) * p->tables.size(), 16);
   p->off_quants = off; off += Align(sizeof(QuantSet) * p->quants.size(), 16);
   p->off_quads = off; off += Align(sizeof(int64_t) * n, 16);
+  p->off_items = off; off += Align(sizeof(int64_t) * n, 16);
   p->off_raw = off;
   p->desc_bytes = off;
   const size_t total = off + raw + 64;
@@ -1098,6 +1235,7 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
   memcpy(p->h_stage + p->off_tables, p->tables.data(), sizeof(TableSet) * p->tables.size());
   memcpy(p->h_stage + p->off_quants, p->quants.data(), sizeof(QuantSet) * p->quants.size());
   memcpy(p->h_stage + p->off_quads, p->first_quad.data(), sizeof(int64_t) * n);
+  memcpy(p->h_stage + p->off_items, p->first_item.data(), sizeof(int64_t) * n);
   // scan bytes: parallel memcpy (the host is otherwise the bottleneck at batch 256 x 0.5 MB)
   {
     std::vector<size_t> dst_off(n);
@@ -1188,6 +1326,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   const auto *d_tables = reinterpret_cast<const TableSet *>(p->d_stage + p->off_tables);
   const auto *d_quants = reinterpret_cast<const QuantSet *>(p->d_stage + p->off_quants);
   const auto *d_quads = reinterpret_cast<const int64_t *>(p->d_stage + p->off_quads);
+  const auto *d_items = reinterpret_cast<const int64_t *>(p->d_stage + p->off_items);
   const uint8_t *d_raw = p->d_stage + p->off_raw;
   const int nunits = (int)p->units.size();
   const int sms = NumSMs();
@@ -1215,10 +1354,18 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
     const int64_t total_blocks = p->total_coefs / 64;
     const int grid = (int)std::min<int64_t>((total_blocks + 127) / 128, (int64_t)sms * 32);
     { ProfScope ps_("jpeg_idct", s); idct_kernel<<<grid, 128, 0, s>>>(d_images, p->n, total_blocks, p->d_coef, d_quants, p->d_planes); }
-    const int grid2 = (int)std::min<int64_t>((p->total_quads + 255) / 256, (int64_t)sms * 32);
-    { ProfScope ps_("jpeg_upsample_color", s); color_kernel<<<grid2, 256, 0, s>>>(d_images, d_quads, p->n, p->total_quads, p->d_planes); }
+    if (p->total_quads > 0) {
+      const int grid2 = (int)std::min<int64_t>((p->total_quads + 255) / 256, (int64_t)sms * 32);
+      { ProfScope ps_("jpeg_upsample_color_generic", s); color_kernel<<<grid2, 256, 0, s>>>(d_images, d_quads, p->n, p->total_quads, p->d_planes); }
+      CountLaunch();
+    }
+    if (p->total_items > 0) {
+      const int grid3 = (int)std::min<int64_t>(p->total_items, (int64_t)sms * 64);
+      { ProfScope ps_("jpeg_upsample_color", s); color_fast_kernel<<<grid3, 128, 0, s>>>(d_images, d_items, p->n, p->total_items, p->d_planes); }
+      CountLaunch();
+    }
   }
-  CountLaunch(6);
+  CountLaunch(5);
   DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
 }

@@ -105,7 +105,12 @@ struct AxisSetup {
   int support;               // >= 1 (NN -> 1)
 };
 
-struct AxisTableRef { int idx_off, coef_off, support; };   // offsets (in 4-byte words) into the table arena
+struct AxisTableRef { int idx_off, coef_off, support; };
+
+constexpr int kTmpFloats = 24 * 1024;     // 96 KB of fp32 intermediate per CTA -> 2 CTAs / SM
+constexpr int kMaxTileH = 16;             // output rows per tile in the vertical-first order
+constexpr int kMaxSupportSmem = 64;       // vertical taps whose coefficients are staged in smem
+constexpr int kTileTableBytes = kMaxTileH * kMaxSupportSmem * 8;   // offsets (in 4-byte words) into the table arena
 
 struct RsDesc {
   const void *in;
@@ -116,6 +121,7 @@ struct RsDesc {
   int32_t flags_off;         // per-output-column rounding flags (horizontal last pass, u8 out) or -1
   int32_t simd_flat_end;     // vertical last pass, u8 out: flat x*C+c < this -> half-to-even
   int32_t tile_h, tile_w, tiles_x, tiles_y;
+  int32_t aligned4;          // input base and row pitch are multiples of 4 bytes (filled at launch)
   int64_t first_tile;
 };
 
@@ -138,6 +144,30 @@ template <typename Out> __device__ __forceinline__ Out rs_store_cvt(float v, boo
 template <> __device__ __forceinline__ float rs_store_cvt<float>(float v, bool) { return v; }
 template <> __device__ __forceinline__ uint8_t rs_store_cvt<uint8_t>(float v, bool half_even) {
   return half_even ? sat_u8_half_even(v) : sat_u8_half_away(v);
+}
+
+
+// ---- packed fp32x2 arithmetic (sm_100a): two independent IEEE mul / add per instruction, no contraction
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+// exact u8 -> f32 without the (slow) I2F pipe: 0x4B000000 | b is the float 2^23 + b; subtracting 2^23 is exact
+__device__ __forceinline__ float2 bytes01_to_float(uint32_t w) {
+  const float2 m = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)));
+  return add2_rn(m, make_float2(-8388608.0f, -8388608.0f));
+}
+__device__ __forceinline__ float2 bytes23_to_float(uint32_t w) {
+  const float2 m = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)), __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)));
+  return add2_rn(m, make_float2(-8388608.0f, -8388608.0f));
 }
 
 // One CTA = one output tile of one sample.  smem: fp32 intermediate of the tile.
@@ -168,39 +198,82 @@ __global__ void __launch_bounds__(256) resample_fused_kernel(const RsDesc *__res
       const int ia = idx_x[ox0], ib = idx_x[ox0 + tw - 1];
       const int cmin = bx + min(max(min(ia, ib), 0), ex - 1);
       const int cmax = bx + min(max(max(ia, ib) + Sx - 1, 0), ex - 1);
-      const int span = cmax - cmin + 1;
-      const int row_elems = span * C;
-      // stage A: vertical FIR   tmp[t][j] = sum_k cy[t][k] * in[row(t,k)][cmin*C + j]
-      for (int e = threadIdx.x; e < th * row_elems; e += blockDim.x) {
-        const int t = e / row_elems, j = e - t * row_elems;
-        const int oy = oy0 + t;
-        const int i0 = idx_y[oy];
-        const float *cy = coef_y + (int64_t)oy * Sy;
-        const In *col = in + (int64_t)cmin * C + j;
-        float acc = 0.0f;
-        for (int k = 0; k < Sy; k++) {
-          const int r = by + min(max(i0 + k, 0), ey - 1);
-          acc = add_rn(acc, mul_rn(ld_as_float<In>(col + r * pitch), cy[k]));
+      // byte span of a row, widened to whole 32-bit words (stays inside the row: pitch % 4 == 0 on the fast path)
+      const bool fast = sizeof(In) == 1 && d.aligned4;
+      const int e0 = fast ? ((cmin * C) & ~3) : cmin * C;
+      const int e1 = fast ? (((cmax + 1) * C + 3) & ~3) : (cmax + 1) * C;
+      const int row_elems = e1 - e0;
+      // ---- per-tile tables in smem: vertical coefficients and clamped source rows of the th output rows
+      float *s_cy = tmp + kTmpFloats;
+      int *s_row = reinterpret_cast<int *>(s_cy + kMaxTileH * kMaxSupportSmem);
+      const bool tables = Sy <= kMaxSupportSmem;
+      if (tables) {
+        for (int e = threadIdx.x; e < th * Sy; e += blockDim.x) {
+          const int t = e / Sy, k = e - t * Sy;
+          s_cy[e] = coef_y[(int64_t)(oy0 + t) * Sy + k];
+          s_row[e] = by + min(max(idx_y[oy0 + t] + k, 0), ey - 1);
         }
-        tmp[e] = acc;
+        __syncthreads();
+      }
+      if (fast && tables) {
+        // stage A (fast): one thread = one 32-bit word column, all th output rows; u8 -> f32 via byte_perm,
+        // packed f32x2 mul / add (two roundings, exactly like the reference's SSE mul + add)
+        const int words = row_elems >> 2;
+        const uint8_t *in8 = reinterpret_cast<const uint8_t *>(in) + e0;
+        for (int jw = threadIdx.x; jw < words; jw += blockDim.x) {
+          const uint8_t *colp = in8 + 4 * jw;
+          for (int t = 0; t < th; t++) {
+            float2 a01 = make_float2(0.0f, 0.0f), a23 = make_float2(0.0f, 0.0f);
+            const float *cy = s_cy + t * Sy;
+            const int *rr = s_row + t * Sy;
+#pragma unroll 2
+            for (int k = 0; k < Sy; k++) {
+              const uint32_t w = ld_nc_u32(reinterpret_cast<const uint32_t *>(colp + (int64_t)rr[k] * pitch));
+              const float2 c2 = make_float2(cy[k], cy[k]);
+              a01 = add2_rn(a01, mul2_rn(bytes01_to_float(w), c2));
+              a23 = add2_rn(a23, mul2_rn(bytes23_to_float(w), c2));
+            }
+            *reinterpret_cast<float4 *>(tmp + t * row_elems + 4 * jw) = make_float4(a01.x, a01.y, a23.x, a23.y);
+          }
+        }
+      } else {
+        // stage A (generic): vertical FIR   tmp[t][j] = sum_k cy[t][k] * in[row(t,k)][e0 + j]
+        for (int e = threadIdx.x; e < th * row_elems; e += blockDim.x) {
+          const int t = e / row_elems, j = e - t * row_elems;
+          const int oy = oy0 + t;
+          const int i0 = idx_y[oy];
+          const float *cy = coef_y + (int64_t)oy * Sy;
+          const In *col = in + e0 + j;
+          float acc = 0.0f;
+          for (int k = 0; k < Sy; k++) {
+            const int r = by + min(max(i0 + k, 0), ey - 1);
+            acc = add_rn(acc, mul_rn(ld_as_float<In>(col + r * pitch), cy[k]));
+          }
+          tmp[e] = acc;
+        }
       }
       __syncthreads();
-      // stage B: horizontal FIR from the smem intermediate
-      for (int e = threadIdx.x; e < th * tw * C; e += blockDim.x) {
-        const int c = e % C;
-        const int x = (e / C) % tw;
-        const int t = e / (C * tw);
+      // stage B: horizontal FIR from the smem intermediate; one thread = one (x, c) column of the tile, all th rows,
+      // so every coefficient is fetched once and reused th times
+      for (int e = threadIdx.x; e < tw * C; e += blockDim.x) {
+        const int c = e % C, x = e / C;
         const int ox = ox0 + x;
         const int i0 = idx_x[ox];
         const float *cx = coef_x + (int64_t)ox * Sx;
-        const float *row = tmp + t * row_elems + c;
-        float acc = 0.0f;
-        for (int k = 0; k < Sx; k++) {
-          const int sx = bx + min(max(i0 + k, 0), ex - 1) - cmin;
-          acc = add_rn(acc, mul_rn(cx[k], row[sx * C]));
-        }
         const bool he = flags ? flags[ox] != 0 : false;
-        out[((int64_t)(oy0 + t) * d.out_w + ox) * C + c] = rs_store_cvt<Out>(acc, he);
+        float acc[kMaxTileH];
+#pragma unroll
+        for (int t = 0; t < kMaxTileH; t++) acc[t] = 0.0f;
+        for (int k = 0; k < Sx; k++) {
+          const int sx = (bx + min(max(i0 + k, 0), ex - 1)) * C + c - e0;
+          const float ck = cx[k];
+#pragma unroll
+          for (int t = 0; t < kMaxTileH; t++)
+            if (t < th) acc[t] = add_rn(acc[t], mul_rn(ck, tmp[t * row_elems + sx]));
+        }
+#pragma unroll
+        for (int t = 0; t < kMaxTileH; t++)
+          if (t < th) out[((int64_t)(oy0 + t) * d.out_w + ox) * C + c] = rs_store_cvt<Out>(acc[t], he);
       }
     } else {
       const int ia = idx_y[oy0], ib = idx_y[oy0 + th - 1];
@@ -250,7 +323,7 @@ using namespace dalib200;  // NOLINT
 
 namespace {
 
-constexpr int kTmpFloats = 24 * 1024;     // 96 KB of fp32 intermediate per CTA -> 2 CTAs / SM
+// (kTmpFloats etc. are defined next to the kernel)
 
 struct TableKey {
   int in_size, out_size, ftype, base, extent;
@@ -506,7 +579,7 @@ int dalib200ResamplePlanSetup(dalib200ResamplePlan *p, int n, const dalib200Resa
       tw = s.out_w; th = 0;
       for (;;) {
         int span = max_span(ix, s.out_w, tw, d.support[0], d.extent[0]);
-        th = std::min({ kTmpFloats / std::max(1, span * C), 32, s.out_h });
+        th = std::min({ kTmpFloats / std::max(1, span * C + 8), kMaxTileH, s.out_h });
         if (th >= std::min(8, s.out_h) || tw == 1) { fits = th >= 1; break; }
         tw = (tw + 1) / 2;
       }
@@ -545,6 +618,7 @@ int dalib200ResampleLaunch(dalib200ResamplePlan *p, const void *const *in_ptrs, 
     hd[i] = p->descs[i];
     hd[i].in = in_ptrs[i];
     hd[i].out = out_ptrs[i];
+    hd[i].aligned4 = (reinterpret_cast<uintptr_t>(in_ptrs[i]) % 4 == 0) && ((int64_t)hd[i].in_w * hd[i].C % 4 == 0);
   }
   rc = p->desc_arena.Upload(sizeof(RsDesc) * p->n, stream);
   if (rc) return rc;
@@ -562,7 +636,7 @@ int dalib200ResampleLaunch(dalib200ResamplePlan *p, const void *const *in_ptrs, 
   p->pending = true;
   const auto *dd = reinterpret_cast<const RsDesc *>(p->desc_arena.dev);
   const auto *tb = reinterpret_cast<const int32_t *>(p->table_arena.dev);
-  const int smem = kTmpFloats * sizeof(float);
+  const int smem = kTmpFloats * sizeof(float) + kTileTableBytes;
   int grid = (int)std::min<int64_t>(p->total_tiles, (int64_t)NumSMs() * 2 * 8);
   auto launch = [&](auto kern, int slot) -> int {
     if (!p->smem_opted[slot]) {

@@ -68,12 +68,14 @@ class ImagePipelineC2:
         oh, ow = self.out_hw
         rs = (capi.ResampleSample * n)()
         cm = (capi.CmnSample * n)()
-        lin = capi.FilterDesc(capi.FILTER_LINEAR, 1, 0.0)
+        # what fn.resize passes by default (resampling_attr.cc:76-133): min = Triangular + antialias, mag = Linear
+        fmin = capi.FilterDesc(capi.FILTER_TRIANGULAR, 1, 0.0)
+        fmag = capi.FilterDesc(capi.FILTER_LINEAR, 0, 0.0)
         for i, (h, w) in enumerate(shapes):
             r = rs[i]
             r.in_h, r.in_w, r.channels, r.out_h, r.out_w = h, w, 3, oh, ow
             for d in range(2):
-                r.min_filter[d] = lin; r.mag_filter[d] = lin; r.use_roi[d] = 0
+                r.min_filter[d] = fmin; r.mag_filter[d] = fmag; r.use_roi[d] = 0
             c = cm[i]
             c.in_h, c.in_w, c.channels = oh, ow, 3
             c.anchor_y, c.anchor_x, c.crop_h, c.crop_w = 0, 0, oh, ow

@@ -16,7 +16,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-fmad=false", "-Xptxas", "-v"]
 
 
 def _newer(src, dst, extra=()):
@@ -59,8 +59,42 @@ def build_kernels(verbose=False, force=False):
     return lib
 
 
+def build_host(verbose=False, force=False):
+    """libdali_b200_host.so: the dali:: operator boundary, the operators and the pipeline C API (g++; links the kernel library)."""
+    hdir = os.path.join(HERE, "host")
+    srcs = sorted(glob.glob(os.path.join(hdir, "*.cc")))
+    hdrs = tuple(glob.glob(os.path.join(hdir, "*.h")) + glob.glob(os.path.join(HERE, "..", "include", "*.h")))
+    os.makedirs(OBJDIR, exist_ok=True)
+    cxx = os.environ.get("CXX", "g++")
+    flags = ["-std=c++17", "-O2", "-fPIC", "-Wall", "-Wno-unused-function", "-I/usr/local/cuda/include"]
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, "host_" + os.path.basename(src) + ".o")
+        if force or _newer(src, obj, hdrs):
+            r = subprocess.run([cxx] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"{cxx} failed for {src}:\n{(r.stdout + r.stderr)[-4000:]}")
+            if verbose and r.stderr:
+                print(r.stderr)
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    lib = os.path.join(LIBDIR, "libdali_b200_host.so")
+    klib = os.path.join(LIBDIR, "libdali_b200.so")
+    if force or any(_newer(o, lib) for o in objs) or _newer(klib, lib):
+        cmd = [cxx, "-shared", "-o", lib] + objs + ["-L" + LIBDIR, "-ldali_b200", "-L/usr/local/cuda/lib64", "-lcudart",
+                                                    "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,/usr/local/cuda/lib64", "-Wl,--no-undefined"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("host link failed:\n" + r.stdout + r.stderr)
+    return lib
+
+
 def build_all(verbose=False, force=False):
-    return build_kernels(verbose=verbose, force=force)
+    k = build_kernels(verbose=verbose, force=force)
+    build_host(verbose=verbose, force=force)
+    return k
 
 
 if __name__ == "__main__":

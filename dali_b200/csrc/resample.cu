@@ -230,8 +230,11 @@ __global__ void __launch_bounds__(256) resample_fused_kernel(const RsDesc *__res
             for (int k = 0; k < Sy; k++) {
               const uint32_t w = ld_nc_u32(reinterpret_cast<const uint32_t *>(colp + (int64_t)rr[k] * pitch));
               const float2 c2 = make_float2(cy[k], cy[k]);
-              a01 = add2_rn(a01, mul2_rn(bytes01_to_float(w), c2));
-              a23 = add2_rn(a23, mul2_rn(bytes23_to_float(w), c2));
+              // NOTE: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false, which
+              // would round once instead of twice; the products therefore use the scalar (never contracted) mul.rn.
+              const float2 f01 = bytes01_to_float(w), f23 = bytes23_to_float(w);
+              a01 = add2_rn(a01, make_float2(mul_rn(f01.x, c2.x), mul_rn(f01.y, c2.x)));
+              a23 = add2_rn(a23, make_float2(mul_rn(f23.x, c2.x), mul_rn(f23.y, c2.x)));
             }
             *reinterpret_cast<float4 *>(tmp + t * row_elems + 4 * jw) = make_float4(a01.x, a01.y, a23.x, a23.y);
           }

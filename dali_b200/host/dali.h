@@ -209,6 +209,22 @@ class OpSpec {
   std::map<std::string, std::string> arg_inputs_;
 };
 
+
+// explicit specialisations (defined in pipeline.cc)
+#define DALI_DECL_GETARG(T) template <> T OpSpec::GetArgument<T>(const std::string &n, const Workspace *ws, int idx) const;
+DALI_DECL_GETARG(double) DALI_DECL_GETARG(float) DALI_DECL_GETARG(int) DALI_DECL_GETARG(int64_t) DALI_DECL_GETARG(bool)
+DALI_DECL_GETARG(DALIDataType) DALI_DECL_GETARG(DALIInterpType) DALI_DECL_GETARG(DALIImageType) DALI_DECL_GETARG(std::string)
+DALI_DECL_GETARG(TensorLayout)
+#undef DALI_DECL_GETARG
+template <> bool OpSpec::TryGetArgument<float>(float &, const std::string &) const;
+template <> bool OpSpec::TryGetArgument<int>(int &, const std::string &) const;
+template <> bool OpSpec::TryGetArgument<bool>(bool &, const std::string &) const;
+template <> bool OpSpec::TryGetArgument<std::string>(std::string &, const std::string &) const;
+template <> bool OpSpec::TryGetArgument<DALIDataType>(DALIDataType &, const std::string &) const;
+template <> bool OpSpec::TryGetArgument<std::vector<float>>(std::vector<float> &, const std::string &) const;
+template <> std::vector<float> OpSpec::GetRepeatedArgument<float>(const std::string &) const;
+template <> std::vector<int> OpSpec::GetRepeatedArgument<int>(const std::string &) const;
+
 // ---------------------------------------------------------------------------------------------- OpSchema
 class OpSchema {
  public:

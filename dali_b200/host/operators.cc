@@ -1,0 +1,932 @@
+// dali_b200/host/operators.cc -- the hot-path operators behind the reference's operator boundary
+// (Operator<GPUBackend>::SetupImpl / RunImpl + DALI_SCHEMA + DALI_REGISTER_OPERATOR), each a thin argument layer
+// over the C-ABI of include/dali_b200.h:  SetupImpl -> ...PlanSetup (host, shapes + per-sample args),
+// RunImpl -> ...Launch (enqueue on ws.stream(), no host sync).
+//
+// Argument handling restates the reference operators (schema names, defaults, meaning, error behaviour):
+//   decoders__Image        dali/operators/imgcodec/decoder_schema.cc:21-168, mixed_decoder.cc:35-51
+//   Resize                 dali/operators/image/resize/resize.cc:21-41, resize_attr.cc:23-259, resize_attr_base.{h,cc},
+//                          resampling_attr.cc:22-133
+//   CropMirrorNormalize    dali/operators/image/crop/crop_mirror_normalize.{h,cc}, crop_attr.cc:21-245
+//   WarpAffine             dali/operators/image/remap/warp_affine.cc:19-57, warp_affine_params.h:50-83,
+//                          warp_param_provider.h:234-314
+//   Hsv                    dali/operators/image/color/color_twist.{h,cc}
+//   ColorSpaceConversion   dali/operators/image/color/color_space_conversion.{h,cc}
+//   Spectrogram            dali/operators/signal/fft/spectrogram.cc:30-311
+//   MelFilterBank          dali/operators/audio/mel_scale/mel_filter_bank.cc:22-117
+// There is no CPU implementation: the ops are registered for GPU / Mixed only.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include "dali.h"
+#include "../../include/dali_b200.h"
+
+namespace dali {
+
+static void CheckStatus(int rc, const char *what) {
+  if (rc != DALIB200_SUCCESS) throw DALIException(make_string(what, ": ", dalib200GetLastError()));
+}
+
+// frames of a (F)HWC batch flattened into independent 2-D samples (SequenceOperator, sequence_operator.h:57-110)
+struct FrameList {
+  int first_spatial = 0;                       // index of H in the sample shape
+  std::vector<int> sample_of_frame;            // frame -> sample
+  std::vector<int64_t> frame_offset_elems;     // element offset of the frame inside its sample
+  std::vector<int> h, w, c;
+  int num_frames() const { return static_cast<int>(h.size()); }
+};
+
+static FrameList ExpandFrames(const TensorListShape &shape, const TensorLayout &layout, const char *op) {
+  FrameList f;
+  const int nd = shape.sample_dim();
+  std::string l = layout.str();
+  if (l.empty()) l = nd == 3 ? "HWC" : nd == 4 ? "FHWC" : "";
+  DALI_ENFORCE(l == "HWC" || l == "FHWC", op, ": the GPU path supports HWC and FHWC inputs, got layout \"", l, "\" (", nd, "-D)");
+  DALI_ENFORCE(static_cast<int>(l.size()) == nd, op, ": layout \"", l, "\" does not match a ", nd, "-D input");
+  f.first_spatial = l == "HWC" ? 0 : 1;
+  for (int i = 0; i < shape.num_samples(); i++) {
+    const int64_t *s = shape.tensor_shape_span(i);
+    const int64_t frames = f.first_spatial ? s[0] : 1;
+    const int64_t H = s[f.first_spatial], W = s[f.first_spatial + 1], C = s[f.first_spatial + 2];
+    for (int64_t k = 0; k < frames; k++) {
+      f.sample_of_frame.push_back(i);
+      f.frame_offset_elems.push_back(k * H * W * C);
+      f.h.push_back(static_cast<int>(H)); f.w.push_back(static_cast<int>(W)); f.c.push_back(static_cast<int>(C));
+    }
+  }
+  return f;
+}
+
+template <typename TL>
+static std::vector<const void *> FramePtrs(const TL &tl, const FrameList &f, size_t elem_size) {
+  std::vector<const void *> p(f.num_frames());
+  for (int k = 0; k < f.num_frames(); k++)
+    p[k] = static_cast<const uint8_t *>(tl.raw_tensor(f.sample_of_frame[k])) + f.frame_offset_elems[k] * elem_size;
+  return p;
+}
+
+// =============================================================================================== decoders.image
+DALI_SCHEMA(decoders__Image)
+    .DocStr("Decodes JPEG images on the GPU (Huffman + IDCT + upsampling + colour conversion in CUDA).")
+    .NumInput(1).NumOutput(1)
+    .AddOptionalArg("output_type", "Colour space of the output image.", DALI_RGB)
+    .AddOptionalArg("dtype", "Output data type.", DALI_UINT8)
+    .AddOptionalArg("adjust_orientation", "Use EXIF orientation metadata to rectify the images.", true)
+    .AddOptionalArg("use_fast_idct", "ignored (the islow integer IDCT is always used)", false)
+    // NOTE: the reference's mixed default is False (nvJPEG box upsampling); this build defaults to the CPU
+    // backend's libjpeg-turbo "fancy" upsampling so that mixed == cpu bit-exactly (deviations).
+    .AddOptionalArg("jpeg_fancy_upsampling", "Use libjpeg-turbo fancy (triangle) chroma upsampling.", true)
+    .AddOptionalArg("hybrid_huffman_threshold", "ignored", 1000000)
+    .AddOptionalArg("hw_decoder_load", "ignored (no hardware engine is used)", 0.9f)
+    .AddOptionalArg("device_memory_padding", "ignored", 16777216)
+    .AddOptionalArg("host_memory_padding", "ignored", 8388608)
+    .AddOptionalArg("device_memory_padding_jpeg2k", "ignored", 0)
+    .AddOptionalArg("host_memory_padding_jpeg2k", "ignored", 0)
+    .AddOptionalArg("preallocate_width_hint", "ignored", 0)
+    .AddOptionalArg("preallocate_height_hint", "ignored", 0)
+    .AddOptionalArg("affine", "ignored", true)
+    .AddOptionalArg("split_stages", "ignored", false)
+    .AddOptionalArg("use_chunk_allocator", "ignored", false)
+    .AddOptionalArg("memory_stats", "ignored", false)
+    .AddOptionalArg("cache_size", "ignored (no decoder cache)", 0)
+    .AddOptionalArg("cache_threshold", "ignored", 0)
+    .AddOptionalArg("cache_debug", "ignored", false)
+    .AddOptionalArg("cache_batch_copy", "ignored", true)
+    .AddOptionalArg("cache_type", "ignored", std::string(""));
+
+class ImageDecoderMixed : public Operator<MixedBackend> {
+ public:
+  explicit ImageDecoderMixed(const OpSpec &spec) : Operator<MixedBackend>(spec) {
+    output_type_ = spec.GetArgument<DALIImageType>("output_type");
+    DALI_ENFORCE(spec.GetArgument<DALIDataType>("dtype") == DALI_UINT8, "decoders.image: only dtype=UINT8 is supported");
+    fancy_ = spec.GetArgument<bool>("jpeg_fancy_upsampling");
+    CheckStatus(dalib200JpegPlanCreate(&plan_, max_batch_size_), "decoders.image");
+  }
+  ~ImageDecoderMixed() override { dalib200JpegPlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<CPUBackend>(0);
+    const int n = in.num_samples();
+    DALI_ENFORCE(in.type() == DALI_UINT8, "decoders.image expects encoded streams as 1-D uint8 tensors");
+    std::vector<const uint8_t *> ptrs(n);
+    std::vector<size_t> lens(n);
+    for (int i = 0; i < n; i++) { ptrs[i] = in.tensor<uint8_t>(i); lens[i] = static_cast<size_t>(in.shape().tensor_size(i)); }
+    CheckStatus(dalib200JpegPlanSetup(plan_, n, ptrs.data(), lens.data(), output_type_, fancy_), "decoders.image");
+    out.resize(1);
+    out[0].type = DALI_UINT8;
+    out[0].shape.resize(n, 3);
+    const int ch = output_type_ == DALI_GRAY ? 1 : 3;
+    for (int i = 0; i < n; i++) {
+      dalib200JpegInfo info;
+      CheckStatus(dalib200JpegPlanGetInfo(plan_, i, &info), "decoders.image");
+      out[0].shape.set_tensor_shape(i, { info.height, info.width, ch });
+    }
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout("HWC");
+    std::vector<void *> optr(out.num_samples());
+    for (int i = 0; i < out.num_samples(); i++) optr[i] = out.raw_mutable_tensor(i);
+    CheckStatus(dalib200JpegUpload(plan_, ws.stream()), "decoders.image");
+    CheckStatus(dalib200JpegLaunch(plan_, optr.data(), ws.stream()), "decoders.image");
+  }
+ private:
+  dalib200JpegPlan *plan_ = nullptr;
+  int output_type_ = DALI_RGB;
+  bool fancy_ = true;
+};
+DALI_REGISTER_OPERATOR(decoders__Image, ImageDecoderMixed, Mixed);
+
+// =============================================================================================== Resize
+DALI_SCHEMA(Resize)
+    .DocStr("Resizes images (separable resampling, fused two-pass CUDA kernel).")
+    .NumInput(1).NumOutput(1).AllowSequences()
+    .AddOptionalArgNoDefault("resize_x", "Length of the X dimension of the resized image (0 = keep aspect).", true)
+    .AddOptionalArgNoDefault("resize_y", "Length of the Y dimension of the resized image (0 = keep aspect).", true)
+    .AddOptionalArgNoDefault("resize_z", "not supported by the GPU path (2-D images only)", true)
+    .AddOptionalArgNoDefault("size", "Desired output size (H, W).", true)
+    .AddOptionalArgNoDefault("resize_shorter", "Length of the shorter dimension of the resized image.", true)
+    .AddOptionalArgNoDefault("resize_longer", "Length of the longer dimension of the resized image.", true)
+    .AddOptionalArgNoDefault("mode", "default | stretch | not_larger | not_smaller")
+    .AddOptionalArgNoDefault("max_size", "Limit of the output size.")
+    .AddOptionalArg("subpixel_scale", "Adjust the ROI so that fractional sizes keep the scale.", true)
+    .AddOptionalArgNoDefault("roi_start", "Origin of the input region of interest.", true)
+    .AddOptionalArgNoDefault("roi_end", "End of the input region of interest.", true)
+    .AddOptionalArg("roi_relative", "ROI given in relative coordinates.", false)
+    .AddOptionalArg("interp_type", "Type of interpolation.", DALI_INTERP_LINEAR, true)
+    .AddOptionalArg("mag_filter", "Filter used when scaling up.", DALI_INTERP_LINEAR, true)
+    .AddOptionalArg("min_filter", "Filter used when scaling down.", DALI_INTERP_LINEAR, true)
+    .AddOptionalArg("antialias", "Apply an antialiasing filter when scaling down.", true)
+    .AddOptionalArgNoDefault("dtype", "Output type: same as input or FLOAT.")
+    .AddOptionalArg("minibatch_size", "ignored (the whole batch is one launch)", 32)
+    .AddOptionalArg("temp_buffer_hint", "ignored (the intermediate lives in shared memory)", 0)
+    .AddOptionalArg("save_attrs", "not supported", false);
+
+namespace resize_detail {
+enum class Mode { Default, Stretch, NotLarger, NotSmaller };
+
+// resize_attr_base.cc:86-188
+void AdjustOutputSize(float *out_size, const float *in_size, int ndim, Mode mode, const float *max_size) {
+  double scale[3] = {1, 1, 1};
+  bool mask[3] = {false, false, false};
+  int provided = 0;
+  for (int d = 0; d < ndim; d++) {
+    mask[d] = (out_size[d] != 0 && in_size[d] != 0);
+    scale[d] = in_size[d] ? out_size[d] / in_size[d] : 1;
+    provided += mask[d];
+  }
+  if (provided == 0) {
+    for (int d = 0; d < ndim; d++) out_size[d] = in_size[d];
+    return;
+  }
+  if (mode == Mode::Default || mode == Mode::Stretch) {
+    if (provided < ndim) {
+      double avg = 1;
+      if (mode == Mode::Default) {
+        for (int d = 0; d < ndim; d++) if (mask[d]) avg *= std::abs(scale[d]);
+        if (provided > 1) avg = std::pow(avg, 1.0 / provided);
+      }
+      for (int d = 0; d < ndim; d++) if (!mask[d]) { scale[d] = avg; out_size[d] = mode == Mode::Default ? in_size[d] * scale[d] : in_size[d]; }
+    }
+    if (max_size)
+      for (int d = 0; d < ndim; d++)
+        if (max_size[d] > 0 && std::abs(out_size[d]) > max_size[d]) { out_size[d] = std::copysignf(max_size[d], out_size[d]); scale[d] = out_size[d] / in_size[d]; }
+  } else {
+    double fs = 0; bool first = true;
+    for (int d = 0; d < ndim; d++) if (mask[d]) {
+      float s = std::abs(scale[d]);
+      if (first || (mode == Mode::NotSmaller && s > fs) || (mode == Mode::NotLarger && s < fs)) fs = s;
+      first = false;
+    }
+    if (max_size) for (int d = 0; d < ndim; d++) if (max_size[d] > 0) { double s = static_cast<double>(max_size[d]) / in_size[d]; if (s < fs) fs = s; }
+    for (int d = 0; d < ndim; d++) if (!mask[d] || std::abs(scale[d]) != fs) { scale[d] = std::copysign(fs, scale[d]); out_size[d] = in_size[d] * scale[d]; }
+  }
+}
+
+struct Params { int dst[2]; float lo[2], hi[2]; };
+
+// resize_attr_base.h:51-119 (alignment = centre, size_round_fn = round_int)
+void CalculateSampleParams(Params &p, float req[2], float in_lo[2], float in_hi[2], bool adjust_roi, bool empty_input, Mode mode,
+                           const float *max_size) {
+  float in_size[2];
+  for (int d = 0; d < 2; d++) {
+    float sz = in_hi[d] - in_lo[d];
+    if (sz < 0) { std::swap(in_hi[d], in_lo[d]); req[d] = -req[d]; sz = -sz; }
+    in_size[d] = sz;
+  }
+  AdjustOutputSize(req, in_size, 2, mode, max_size);
+  for (int d = 0; d < 2; d++) DALI_ENFORCE(in_lo[d] != in_hi[d] || req[d] == 0, "Cannot produce non-empty output from empty input");
+  const int min_size = empty_input ? 0 : 1;
+  for (int d = 0; d < 2; d++) {
+    p.lo[d] = in_lo[d]; p.hi[d] = in_hi[d];
+    const float out_sz = req[d];
+    const bool flip = out_sz < 0;
+    p.dst[d] = std::max(min_size, static_cast<int>(std::roundf(std::fabs(out_sz))));
+    if (flip) std::swap(p.lo[d], p.hi[d]);
+    if (adjust_roi && p.dst[d] != std::fabs(out_sz)) {
+      const double real_size = p.dst[d];
+      double adjustment = real_size / std::fabs(out_sz);
+      adjustment = std::min(std::max(adjustment, -10.0), 10.0);
+      const double a = 0.5f;
+      const double center = (1.0 - a) * p.lo[d] + a * p.hi[d];
+      p.lo[d] = static_cast<float>(std::min(std::max(center + (p.lo[d] - center) * adjustment, -1e+9), 1e+9));
+      p.hi[d] = static_cast<float>(std::min(std::max(center + (p.hi[d] - center) * adjustment, -1e+9), 1e+9));
+    }
+  }
+}
+}  // namespace resize_detail
+
+static int Interp2Filter(int interp) {      // resampling_attr.cc:60-74
+  switch (interp) {
+    case DALI_INTERP_NN: return DALIB200_FILTER_NN;
+    case DALI_INTERP_LINEAR: return DALIB200_FILTER_LINEAR;
+    case DALI_INTERP_CUBIC: return DALIB200_FILTER_CUBIC;
+    case DALI_INTERP_LANCZOS3: return DALIB200_FILTER_LANCZOS3;
+    case DALI_INTERP_GAUSSIAN: return DALIB200_FILTER_GAUSSIAN;
+    case DALI_INTERP_TRIANGULAR: return DALIB200_FILTER_TRIANGULAR;
+    default: DALI_FAIL("Unknown interpolation type");
+  }
+}
+
+class ResizeGPU : public Operator<GPUBackend> {
+ public:
+  explicit ResizeGPU(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    using resize_detail::Mode;
+    has_shorter_ = spec.ArgumentDefined("resize_shorter"); has_longer_ = spec.ArgumentDefined("resize_longer");
+    has_x_ = spec.ArgumentDefined("resize_x"); has_y_ = spec.ArgumentDefined("resize_y");
+    has_size_ = spec.ArgumentDefined("size"); has_max_ = spec.ArgumentDefined("max_size");
+    const bool has_mode = spec.ArgumentDefined("mode");
+    DALI_ENFORCE(!spec.ArgumentDefined("resize_z"), "Resize: `resize_z` (volumetric data) is not supported by the GPU path");
+    DALI_ENFORCE(!spec.GetArgument<bool>("save_attrs"), "Resize: `save_attrs` is not supported");
+    DALI_ENFORCE((has_x_ || has_y_) + has_size_ + has_shorter_ + has_longer_ == 1,
+                 "Exactly one method of specifying size must be used. The available methods:\n"
+                 "    - separate resize_x, resize_y, resize_z arguments\n    - size argument\n    - resize_longer\n    - resize_shorter");
+    DALI_ENFORCE(has_shorter_ + has_longer_ + has_mode <= 1, "`resize_shorter`, ``resize_longer`` and ``mode`` arguments are mutually exclusive");
+    DALI_ENFORCE(spec.ArgumentDefined("roi_start") == spec.ArgumentDefined("roi_end"), "``roi_start`` and ``roi_end`` must be specified together");
+    has_roi_ = spec.ArgumentDefined("roi_start");
+    roi_relative_ = spec.GetArgument<bool>("roi_relative");
+    subpixel_scale_ = spec.GetArgument<bool>("subpixel_scale");
+    if (has_shorter_) mode_ = Mode::NotSmaller;
+    else if (has_longer_) mode_ = Mode::NotLarger;
+    else if (has_mode) {
+      const std::string m = spec.GetArgument<std::string>("mode");
+      if (m == "default") mode_ = Mode::Default; else if (m == "stretch") mode_ = Mode::Stretch;
+      else if (m == "not_larger") mode_ = Mode::NotLarger; else if (m == "not_smaller") mode_ = Mode::NotSmaller;
+      else DALI_FAIL(make_string("Invalid resize mode: \"", m, "\""));
+    }
+    antialias_ = spec.GetArgument<bool>("antialias");
+    CheckStatus(dalib200ResamplePlanCreate(&plan_, max_batch_size_ * 64), "Resize");
+    plan_cap_ = max_batch_size_ * 64;
+  }
+  ~ResizeGPU() override { dalib200ResamplePlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    const int n = in.num_samples();
+    DALI_ENFORCE(in.type() == DALI_UINT8 || in.type() == DALI_FLOAT, "Resize: the GPU path supports uint8 and float inputs");
+    DALIDataType out_type = in.type();
+    if (spec_.ArgumentDefined("dtype")) out_type = spec_.GetArgument<DALIDataType>("dtype");
+    DALI_ENFORCE(out_type == in.type() || out_type == DALI_FLOAT, "Resize: output type must be the same as input or FLOAT");
+    frames_ = ExpandFrames(in.shape(), in.GetLayout(), "Resize");
+    const int nf = frames_.num_frames();
+    if (nf > plan_cap_) { dalib200ResamplePlanDestroy(plan_); plan_ = nullptr; plan_cap_ = nf; CheckStatus(dalib200ResamplePlanCreate(&plan_, nf), "Resize"); }
+    std::vector<float> max_size(2, std::nextafter(static_cast<float>(std::numeric_limits<int>::max()), 0.0f));
+    if (has_max_) max_size = spec_.GetFloatVecArgument("max_size", &ws, 0, 2);
+    const bool has_interp = spec_.ArgumentDefined("interp_type"), has_min = spec_.ArgumentDefined("min_filter"),
+               has_mag = spec_.ArgumentDefined("mag_filter");
+    samples_.assign(nf, dalib200ResampleSample());
+    out_hw_.assign(n, {0, 0});
+    int fk = 0;
+    for (int i = 0; i < n; i++) {
+      const int64_t *s = in.shape().tensor_shape_span(i);
+      const int fs = frames_.first_spatial;
+      const float in_h = static_cast<float>(s[fs]), in_w = static_cast<float>(s[fs + 1]);
+      float req[2] = {0, 0};     // (H, W) order
+      if (has_x_ || has_y_) {
+        if (has_y_) req[0] = spec_.GetArgument<float>("resize_y", &ws, i);
+        if (has_x_) req[1] = spec_.GetArgument<float>("resize_x", &ws, i);
+      } else if (has_shorter_ || has_longer_) {
+        req[0] = req[1] = spec_.GetArgument<float>(has_shorter_ ? "resize_shorter" : "resize_longer", &ws, i);
+      } else {
+        auto v = spec_.GetFloatVecArgument("size", &ws, i, 2);
+        req[0] = v[0]; req[1] = v[1];
+      }
+      float lo[2] = {0, 0}, hi[2] = {in_h, in_w};
+      if (has_roi_) {          // resize_attr.cc:125-160
+        auto rs = spec_.GetFloatVecArgument("roi_start", &ws, i, 2), re = spec_.GetFloatVecArgument("roi_end", &ws, i, 2);
+        const float isz[2] = {in_h, in_w};
+        for (int d = 0; d < 2; d++) if (isz[d] > 0) {
+          double l = rs[d], h = re[d];
+          if (roi_relative_) { l *= isz[d]; h *= isz[d]; }
+          if (std::fabs(h - l) < 1e-3f) { float off = l <= h ? 0.5f * 1e-3f : -0.5f * 1e-3f; l -= off; h += off; }
+          lo[d] = static_cast<float>(l); hi[d] = static_cast<float>(h);
+        }
+      }
+      resize_detail::Params p;
+      const bool empty_input = in.shape().tensor_size(i) == 0;
+      resize_detail::CalculateSampleParams(p, req, lo, hi, subpixel_scale_, empty_input, mode_, has_max_ ? max_size.data() : nullptr);
+      // filters (resampling_attr.cc:76-133)
+      int interp = spec_.GetArgument<int>("interp_type", &ws, i);
+      int minf = DALIB200_FILTER_TRIANGULAR, magf = DALIB200_FILTER_LINEAR;
+      auto conv = [](int t, bool aa) {
+        if (aa && t == DALI_INTERP_LINEAR) t = DALI_INTERP_TRIANGULAR; else if (!aa && t == DALI_INTERP_TRIANGULAR) t = DALI_INTERP_LINEAR;
+        return Interp2Filter(t);
+      };
+      if (has_min) minf = conv(spec_.GetArgument<int>("min_filter", &ws, i), antialias_); else if (has_interp) minf = conv(interp, antialias_);
+      if (has_mag) magf = conv(spec_.GetArgument<int>("mag_filter", &ws, i), false); else if (has_interp) magf = conv(interp, false);
+      out_hw_[i] = { p.dst[0], p.dst[1] };
+      const int64_t frames = fs ? s[0] : 1;
+      for (int64_t k = 0; k < frames; k++, fk++) {
+        auto &r = samples_[fk];
+        r.in_h = static_cast<int>(s[fs]); r.in_w = static_cast<int>(s[fs + 1]); r.channels = static_cast<int>(s[fs + 2]);
+        r.out_h = p.dst[0]; r.out_w = p.dst[1];
+        for (int d = 0; d < 2; d++) {
+          r.use_roi[d] = p.lo[d] != p.hi[d];            // GetResamplingParams: roi only when non-degenerate
+          r.roi_start[d] = p.lo[d]; r.roi_end[d] = p.hi[d];
+          r.min_filter[d] = { minf, antialias_ ? 1 : 0, 0.0f };
+          r.mag_filter[d] = { magf, 0, 0.0f };
+        }
+      }
+    }
+    CheckStatus(dalib200ResamplePlanSetup(plan_, nf, samples_.data(), in.type() == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT,
+                                          out_type == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT), "Resize");
+    out.resize(1);
+    out[0].type = out_type;
+    out[0].shape.resize(n, in.shape().sample_dim());
+    for (int i = 0; i < n; i++) {
+      TensorShape sh = in.shape().tensor_shape(i);
+      sh[frames_.first_spatial] = out_hw_[i].first; sh[frames_.first_spatial + 1] = out_hw_[i].second;
+      out[0].shape.set_tensor_shape(i, sh);
+    }
+    out_type_ = out_type;
+    return true;
+  }
+
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout().empty() ? TensorLayout(frames_.first_spatial ? "FHWC" : "HWC") : in.GetLayout());
+    auto ip = FramePtrs(in, frames_, TypeSize(in.type()));
+    std::vector<void *> op(frames_.num_frames());
+    std::vector<int64_t> next(out.num_samples(), 0);
+    for (int k = 0; k < frames_.num_frames(); k++) {
+      const int s = frames_.sample_of_frame[k];
+      const int64_t fr = static_cast<int64_t>(out_hw_[s].first) * out_hw_[s].second * frames_.c[k] * TypeSize(out_type_);
+      op[k] = static_cast<uint8_t *>(out.raw_mutable_tensor(s)) + next[s];
+      next[s] += fr;
+    }
+    CheckStatus(dalib200ResampleLaunch(plan_, ip.data(), op.data(), ws.stream()), "Resize");
+  }
+
+ private:
+  dalib200ResamplePlan *plan_ = nullptr;
+  int plan_cap_ = 0;
+  bool has_shorter_ = false, has_longer_ = false, has_x_ = false, has_y_ = false, has_size_ = false, has_max_ = false, has_roi_ = false;
+  bool roi_relative_ = false, subpixel_scale_ = true, antialias_ = true;
+  resize_detail::Mode mode_ = resize_detail::Mode::Default;
+  FrameList frames_;
+  std::vector<dalib200ResampleSample> samples_;
+  std::vector<std::pair<int, int>> out_hw_;
+  DALIDataType out_type_ = DALI_UINT8;
+};
+DALI_REGISTER_OPERATOR(Resize, ResizeGPU, GPU);
+
+// =============================================================================================== CropMirrorNormalize
+DALI_SCHEMA(CropMirrorNormalize)
+    .DocStr("Fused cropping, horizontal mirroring, normalisation, layout permutation and type conversion.")
+    .NumInput(1).NumOutput(1).AllowSequences()
+    .AddOptionalArg("dtype", "Output data type (FLOAT or FLOAT16).", DALI_FLOAT)
+    .AddOptionalArg("output_layout", "Tensor data layout for the output.", std::string("CHW"))
+    .AddOptionalArg("pad_output", "Pad the channel dimension to the next power of two.", false)
+    .AddOptionalArg("mirror", "Flip horizontally.", 0, true)
+    .AddOptionalArg("mean", "Mean pixel values.", std::vector<float>{0.0f}, true)
+    .AddOptionalArg("std", "Standard deviation values.", std::vector<float>{1.0f}, true)
+    .AddOptionalArg("scale", "Value by which the result is multiplied.", 1.0f)
+    .AddOptionalArg("shift", "Value added to the (scaled) result.", 0.0f)
+    .AddOptionalArgNoDefault("crop", "Shape of the cropped image (H, W).", true)
+    .AddOptionalArgNoDefault("crop_h", "Cropping window height.", true)
+    .AddOptionalArgNoDefault("crop_w", "Cropping window width.", true)
+    .AddOptionalArgNoDefault("crop_d", "not supported (2-D images only)", true)
+    .AddOptionalArg("crop_pos_x", "Normalised horizontal position of the window.", 0.5f, true)
+    .AddOptionalArg("crop_pos_y", "Normalised vertical position of the window.", 0.5f, true)
+    .AddOptionalArg("crop_pos_z", "unused", 0.5f, true)
+    .AddOptionalArg("rounding", "round | truncate", std::string("round"))
+    .AddOptionalArg("out_of_bounds_policy", "error | pad | trim_to_shape", std::string("error"))
+    .AddOptionalArg("fill_values", "Fill values for padding.", std::vector<float>{0.0f});
+
+class CropMirrorNormalizeGPU : public Operator<GPUBackend> {
+ public:
+  explicit CropMirrorNormalizeGPU(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    out_type_ = spec.GetArgument<DALIDataType>("dtype");
+    DALI_ENFORCE(out_type_ == DALI_FLOAT || out_type_ == DALI_FLOAT16, "CropMirrorNormalize: the GPU path supports dtype FLOAT and FLOAT16");
+    out_layout_ = spec.GetArgument<std::string>("output_layout");
+    pad_output_ = spec.GetArgument<bool>("pad_output");
+    scale_ = spec.GetArgument<float>("scale"); shift_ = spec.GetArgument<float>("shift");
+    const std::string r = spec.GetArgument<std::string>("rounding");
+    DALI_ENFORCE(r == "round" || r == "truncate", "``rounding`` value ", r, " is not supported. Supported values are \"round\", or \"truncate\".");
+    truncate_ = r == "truncate";
+    oob_ = spec.GetArgument<std::string>("out_of_bounds_policy");
+    DALI_ENFORCE(oob_ == "error" || oob_ == "pad" || oob_ == "trim_to_shape", "Unsupported out_of_bounds_policy: ", oob_);
+    fill_values_ = spec.GetRepeatedArgument<float>("fill_values");
+    DALI_ENFORCE(!spec.ArgumentDefined("crop_d"), "CropMirrorNormalize: `crop_d` is not supported by the GPU path");
+    const bool has_crop = spec.ArgumentDefined("crop");
+    DALI_ENFORCE(!(has_crop && (spec.ArgumentDefined("crop_h") || spec.ArgumentDefined("crop_w"))),
+                 "`crop` argument is not compatible with `crop_h`, `crop_w`, `crop_d`");
+    DALI_ENFORCE(spec.ArgumentDefined("crop_h") == spec.ArgumentDefined("crop_w"), "`crop_h` and `crop_w` arguments must be provided together");
+    CheckStatus(dalib200CmnPlanCreate(&plan_, max_batch_size_ * 64), "CropMirrorNormalize");
+    plan_cap_ = max_batch_size_ * 64;
+  }
+  ~CropMirrorNormalizeGPU() override { dalib200CmnPlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_UINT8, "CropMirrorNormalize: the GPU path expects uint8 input");
+    const int n = in.num_samples();
+    frames_ = ExpandFrames(in.shape(), in.GetLayout(), "CropMirrorNormalize");
+    const bool seq = frames_.first_spatial == 1;
+    std::string ol = out_layout_.empty() ? (seq ? "FHWC" : "HWC") : out_layout_;
+    if (seq && (ol == "CHW" || ol == "HWC")) ol = "F" + ol;       // fn.crop_mirror_normalize(output_layout="CHW") on FHWC -> FCHW
+    DALI_ENFORCE(ol == (seq ? "FCHW" : "CHW") || ol == (seq ? "FHWC" : "HWC"),
+                 "The requested output layout is not supported by the GPU path (", ol, ")");
+    chw_ = ol.find("CHW") != std::string::npos;
+    resolved_layout_ = ol;
+    const int nf = frames_.num_frames();
+    if (nf > plan_cap_) { dalib200CmnPlanDestroy(plan_); plan_ = nullptr; plan_cap_ = nf; CheckStatus(dalib200CmnPlanCreate(&plan_, nf), "CropMirrorNormalize"); }
+    samples_.assign(nf, dalib200CmnSample());
+    crop_hw_.assign(n, {0, 0});
+    int out_c = 0, fk = 0;
+    for (int i = 0; i < n; i++) {
+      const int64_t *s = in.shape().tensor_shape_span(i);
+      const int fs = frames_.first_spatial;
+      const int64_t H = s[fs], W = s[fs + 1], C = s[fs + 2];
+      DALI_ENFORCE(C >= 1 && C <= 4, "CropMirrorNormalize: 1..4 channels supported, got ", C);
+      // ---- crop window (crop_attr.cc:100-239)
+      int64_t ch = H, cw = W;
+      float px = 0.5f, py = 0.5f;
+      bool has_h = false, has_w = false;
+      if (spec_.ArgumentDefined("crop")) {
+        auto c = spec_.GetFloatVecArgument("crop", &ws, i);
+        DALI_ENFORCE(c.size() == 2, "`crop` argument should have 2 or 3 elements depending on the input data shape");
+        ch = static_cast<int>(c[0]); cw = static_cast<int>(c[1]); has_h = has_w = true;
+      } else if (spec_.ArgumentDefined("crop_h")) {
+        ch = static_cast<int>(spec_.GetArgument<float>("crop_h", &ws, i)); cw = static_cast<int>(spec_.GetArgument<float>("crop_w", &ws, i));
+        has_h = has_w = true;
+      }
+      if (!(has_h && ch > 0)) { ch = H; } else { py = spec_.GetArgument<float>("crop_pos_y", &ws, i); }
+      if (!(has_w && cw > 0)) { cw = W; } else { px = spec_.GetArgument<float>("crop_pos_x", &ws, i); }
+      DALI_ENFORCE(px >= 0.0f && px <= 1.0f && py >= 0.0f && py <= 1.0f, "Anchor for dimension is out of range [0.0, 1.0]");
+      auto rnd = [&](double v) { return truncate_ ? static_cast<int64_t>(v) : static_cast<int64_t>(std::round(v)); };
+      int64_t ay = rnd(static_cast<double>(py) * (H - ch)), ax = rnd(static_cast<double>(px) * (W - cw));
+      // ---- out of bounds policy (generic/slice/out_of_bounds_policy.h)
+      const bool oob = ay < 0 || ax < 0 || ay + ch > H || ax + cw > W;
+      if (oob) {
+        if (oob_ == "error") {
+          DALI_FAIL(make_string("Slice can't be placed out of bounds with current policy. Got: input_shape={", H, ", ", W, ", ", C,
+                                "}, slice_anchor={", ay, ", ", ax, ", 0}, slice_shape={", ch, ", ", cw, ", ", C, "}"));
+        } else if (oob_ == "trim_to_shape") {
+          const int64_t y0 = std::min(std::max<int64_t>(ay, 0), H), x0 = std::min(std::max<int64_t>(ax, 0), W);
+          const int64_t y1 = std::min(std::max<int64_t>(ay + ch, 0), H), x1 = std::min(std::max<int64_t>(ax + cw, 0), W);
+          ay = y0; ax = x0; ch = y1 - y0; cw = x1 - x0;
+        }
+      }
+      // ---- normalisation args (crop_mirror_normalize.h:120-149)
+      auto mean_arg = spec_.GetFloatVecArgument("mean", &ws, i), std_arg = spec_.GetFloatVecArgument("std", &ws, i);
+      DALI_ENFORCE(mean_arg.size() == std_arg.size() || mean_arg.size() == 1 || std_arg.size() == 1,
+                   "``mean`` and ``std`` must either be of the same size, be scalars, or one of them can be a vector and the other a scalar.");
+      const int nargs = static_cast<int>(std::max(mean_arg.size(), std_arg.size()));
+      DALI_ENFORCE(nargs == 1 || nargs == C, "The number of per-channel arguments should match the number of channels");
+      int oc = static_cast<int>(C);
+      if (pad_output_) { oc = 1; while (oc < C) oc *= 2; }          // next power of two (crop_mirror_normalize.h:69-77)
+      out_c = oc;
+      const bool mirror = spec_.GetArgument<int>("mirror", &ws, i) != 0;
+      const int64_t frames = fs ? s[0] : 1;
+      for (int64_t k = 0; k < frames; k++, fk++) {
+        auto &c = samples_[fk];
+        c.in_h = static_cast<int>(H); c.in_w = static_cast<int>(W); c.channels = static_cast<int>(C);
+        c.anchor_y = static_cast<int>(ay); c.anchor_x = static_cast<int>(ax); c.crop_h = static_cast<int>(ch); c.crop_w = static_cast<int>(cw);
+        c.mirror = mirror;
+        for (int d = 0; d < 4; d++) {
+          if (d < C) {
+            const double mean_val = mean_arg[d % mean_arg.size()], std_val = std_arg[d % std_arg.size()];
+            c.mean[d] = static_cast<float>(std::fma(-static_cast<double>(shift_), std_val / scale_, mean_val));
+            c.inv_std[d] = static_cast<float>(scale_ / std_val);
+          } else { c.mean[d] = 0.0f; c.inv_std[d] = 1.0f; }
+          c.fill[d] = fill_values_.empty() ? 0.0f : fill_values_.size() == 1 ? fill_values_[0] : (d < static_cast<int>(fill_values_.size()) ? fill_values_[d] : 0.0f);
+        }
+      }
+      crop_hw_[i] = { static_cast<int>(ch), static_cast<int>(cw) };
+    }
+    if (n > 0) {
+      for (int i = 0; i < n; i++) {
+        int oc = static_cast<int>(in.shape().tensor_shape_span(i)[frames_.first_spatial + 2]);
+        if (pad_output_) { int p2 = 1; while (p2 < oc) p2 *= 2; oc = p2; }
+        DALI_ENFORCE(oc == out_c, "CropMirrorNormalize: all samples of a batch must have the same number of channels");
+      }
+    }
+    out_c_ = out_c;
+    CheckStatus(dalib200CmnPlanSetup(plan_, nf, samples_.data(), out_type_ == DALI_FLOAT ? DALIB200_FLOAT : DALIB200_FLOAT16,
+                                     chw_ ? DALIB200_LAYOUT_CHW : DALIB200_LAYOUT_HWC, std::max(out_c, 1)), "CropMirrorNormalize");
+    out.resize(1);
+    out[0].type = out_type_;
+    out[0].shape.resize(n, in.shape().sample_dim());
+    for (int i = 0; i < n; i++) {
+      TensorShape sh;
+      if (seq) sh.push_back(in.shape().tensor_shape_span(i)[0]);
+      if (chw_) { sh.push_back(out_c); sh.push_back(crop_hw_[i].first); sh.push_back(crop_hw_[i].second); }
+      else { sh.push_back(crop_hw_[i].first); sh.push_back(crop_hw_[i].second); sh.push_back(out_c); }
+      out[0].shape.set_tensor_shape(i, sh);
+    }
+    return true;
+  }
+
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(resolved_layout_);
+    auto ip = FramePtrs(in, frames_, 1);
+    std::vector<void *> op(frames_.num_frames());
+    std::vector<int64_t> next(out.num_samples(), 0);
+    for (int k = 0; k < frames_.num_frames(); k++) {
+      const int s = frames_.sample_of_frame[k];
+      op[k] = static_cast<uint8_t *>(out.raw_mutable_tensor(s)) + next[s];
+      next[s] += static_cast<int64_t>(crop_hw_[s].first) * crop_hw_[s].second * out_c_ * TypeSize(out_type_);
+    }
+    CheckStatus(dalib200CmnLaunch(plan_, ip.data(), op.data(), ws.stream()), "CropMirrorNormalize");
+  }
+
+ private:
+  dalib200CmnPlan *plan_ = nullptr;
+  int plan_cap_ = 0, out_c_ = 3;
+  DALIDataType out_type_ = DALI_FLOAT;
+  std::string out_layout_, oob_, resolved_layout_;
+  bool pad_output_ = false, truncate_ = false, chw_ = true;
+  float scale_ = 1, shift_ = 0;
+  std::vector<float> fill_values_;
+  FrameList frames_;
+  std::vector<dalib200CmnSample> samples_;
+  std::vector<std::pair<int, int>> crop_hw_;
+};
+DALI_REGISTER_OPERATOR(CropMirrorNormalize, CropMirrorNormalizeGPU, GPU);
+
+// =============================================================================================== WarpAffine
+DALI_SCHEMA(WarpAffine)
+    .DocStr("Applies an affine transformation to images.")
+    .NumInput(1, 2).NumOutput(1).AllowSequences()
+    .AddOptionalArgNoDefault("matrix", "2x3 transform matrix (row-major).", true)
+    .AddOptionalArg("inverse_map", "True: the matrix maps destination to source coordinates.", true)
+    .AddOptionalArgNoDefault("size", "Output size (H, W); default: input size.", true)
+    .AddOptionalArgNoDefault("fill_value", "Value used outside the source image; absent = clamp to border.")
+    .AddOptionalArgNoDefault("dtype", "Output type (same as input or FLOAT).")
+    .AddOptionalArg("interp_type", "NN or LINEAR.", DALI_INTERP_LINEAR);
+
+class WarpAffineGPU : public Operator<GPUBackend> {
+ public:
+  explicit WarpAffineGPU(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    DALI_ENFORCE(spec.NumInput() == 1, "WarpAffine: passing the matrices as a second regular input is not supported; use the `matrix` argument");
+    const int it = spec.GetArgument<int>("interp_type");
+    DALI_ENFORCE(it == DALI_INTERP_NN || it == DALI_INTERP_LINEAR, "Unsupported interpolation type");   // warp_cpu.h:84-87
+    interp_ = it == DALI_INTERP_LINEAR;
+    invert_ = !spec.GetArgument<bool>("inverse_map");
+    use_fill_ = spec.ArgumentDefined("fill_value");
+    if (use_fill_) fill_ = spec.GetArgument<float>("fill_value");
+    CheckStatus(dalib200WarpPlanCreate(&plan_, max_batch_size_ * 64), "WarpAffine");
+    plan_cap_ = max_batch_size_ * 64;
+  }
+  ~WarpAffineGPU() override { dalib200WarpPlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_UINT8, "WarpAffine: the GPU path expects uint8 input");
+    out_type_ = spec_.ArgumentDefined("dtype") ? spec_.GetArgument<DALIDataType>("dtype") : DALI_UINT8;
+    DALI_ENFORCE(out_type_ == DALI_UINT8 || out_type_ == DALI_FLOAT, "WarpAffine: output type must be UINT8 or FLOAT");
+    DALI_ENFORCE(spec_.ArgumentDefined("matrix"), "`matrix` argument must be provided when transforms are not passed as a regular input.");
+    const int n = in.num_samples();
+    frames_ = ExpandFrames(in.shape(), in.GetLayout(), "WarpAffine");
+    const int nf = frames_.num_frames();
+    if (nf > plan_cap_) { dalib200WarpPlanDestroy(plan_); plan_ = nullptr; plan_cap_ = nf; CheckStatus(dalib200WarpPlanCreate(&plan_, nf), "WarpAffine"); }
+    samples_.assign(nf, dalib200WarpSample());
+    out_hw_.assign(n, {0, 0});
+    int fk = 0;
+    for (int i = 0; i < n; i++) {
+      const int64_t *s = in.shape().tensor_shape_span(i);
+      const int fs = frames_.first_spatial;
+      auto m = spec_.GetFloatVecArgument("matrix", &ws, i);
+      DALI_ENFORCE(m.size() == 6, "`matrix` parameter must have 6 elements");
+      float M[6];
+      if (invert_) dalib200AffineInverse(m.data(), M); else std::copy(m.begin(), m.end(), M);
+      int oh = static_cast<int>(s[fs]), ow = static_cast<int>(s[fs + 1]);
+      if (spec_.ArgumentDefined("size")) {
+        auto sz = spec_.GetFloatVecArgument("size", &ws, i);
+        DALI_ENFORCE(sz.size() == 2, "output_size must specify same number of dimensions as the input (excluding channels)");
+        DALI_ENFORCE(sz[0] > 0 && sz[1] > 0, "Output size must be positive");
+        oh = std::max<int>(static_cast<int>(std::roundf(sz[0])), 1); ow = std::max<int>(static_cast<int>(std::roundf(sz[1])), 1);
+      }
+      out_hw_[i] = { oh, ow };
+      const int64_t frames = fs ? s[0] : 1;
+      for (int64_t k = 0; k < frames; k++, fk++) {
+        auto &w = samples_[fk];
+        w.in_h = static_cast<int>(s[fs]); w.in_w = static_cast<int>(s[fs + 1]); w.channels = static_cast<int>(s[fs + 2]);
+        w.out_h = oh; w.out_w = ow;
+        std::copy(M, M + 6, w.matrix);
+      }
+    }
+    CheckStatus(dalib200WarpPlanSetup(plan_, nf, samples_.data(), interp_, use_fill_, fill_, out_type_ == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT),
+                "WarpAffine");
+    out.resize(1);
+    out[0].type = out_type_;
+    out[0].shape.resize(n, in.shape().sample_dim());
+    for (int i = 0; i < n; i++) {
+      TensorShape sh = in.shape().tensor_shape(i);
+      sh[frames_.first_spatial] = out_hw_[i].first; sh[frames_.first_spatial + 1] = out_hw_[i].second;
+      out[0].shape.set_tensor_shape(i, sh);
+    }
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout().empty() ? TensorLayout(frames_.first_spatial ? "FHWC" : "HWC") : in.GetLayout());
+    auto ip = FramePtrs(in, frames_, 1);
+    std::vector<void *> op(frames_.num_frames());
+    std::vector<int64_t> next(out.num_samples(), 0);
+    for (int k = 0; k < frames_.num_frames(); k++) {
+      const int s = frames_.sample_of_frame[k];
+      op[k] = static_cast<uint8_t *>(out.raw_mutable_tensor(s)) + next[s];
+      next[s] += static_cast<int64_t>(out_hw_[s].first) * out_hw_[s].second * frames_.c[k] * TypeSize(out_type_);
+    }
+    CheckStatus(dalib200WarpLaunch(plan_, ip.data(), op.data(), ws.stream()), "WarpAffine");
+  }
+ private:
+  dalib200WarpPlan *plan_ = nullptr;
+  int plan_cap_ = 0;
+  bool interp_ = true, invert_ = false, use_fill_ = false;
+  float fill_ = 0;
+  DALIDataType out_type_ = DALI_UINT8;
+  FrameList frames_;
+  std::vector<dalib200WarpSample> samples_;
+  std::vector<std::pair<int, int>> out_hw_;
+};
+DALI_REGISTER_OPERATOR(WarpAffine, WarpAffineGPU, GPU);
+
+// =============================================================================================== Hsv
+DALI_SCHEMA(Hsv)
+    .DocStr("Adjusts hue, saturation and value (brightness) of the images.")
+    .NumInput(1).NumOutput(1).AllowSequences()
+    .AddOptionalArg("hue", "Hue delta, in degrees.", 0.0f, true)
+    .AddOptionalArg("saturation", "Saturation multiplier.", 1.0f, true)
+    .AddOptionalArg("value", "Value multiplier.", 1.0f, true)
+    .AddOptionalArg("dtype", "Output data type.", DALI_UINT8);
+
+class PointwiseBase : public Operator<GPUBackend> {
+ public:
+  explicit PointwiseBase(const OpSpec &spec, const char *name) : Operator<GPUBackend>(spec), name_(name) {
+    CheckStatus(dalib200PointwisePlanCreate(&plan_, max_batch_size_), name_);
+    plan_cap_ = max_batch_size_;
+  }
+  ~PointwiseBase() override { dalib200PointwisePlanDestroy(plan_); }
+ protected:
+  void EnsureCap(int n) {
+    if (n > plan_cap_) { dalib200PointwisePlanDestroy(plan_); plan_ = nullptr; plan_cap_ = n; CheckStatus(dalib200PointwisePlanCreate(&plan_, n), name_); }
+  }
+  void Launch(Workspace &ws) {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    std::vector<const void *> ip(in.num_samples());
+    std::vector<void *> op(in.num_samples());
+    for (int i = 0; i < in.num_samples(); i++) { ip[i] = in.raw_tensor(i); op[i] = out.raw_mutable_tensor(i); }
+    CheckStatus(dalib200PointwiseLaunch(plan_, ip.data(), op.data(), ws.stream()), name_);
+  }
+  dalib200PointwisePlan *plan_ = nullptr;
+  int plan_cap_ = 0;
+  const char *name_;
+};
+
+class HsvGPU : public PointwiseBase {
+ public:
+  explicit HsvGPU(const OpSpec &spec) : PointwiseBase(spec, "Hsv") {
+    out_type_ = spec.GetArgument<DALIDataType>("dtype");
+    DALI_ENFORCE(out_type_ == DALI_UINT8 || out_type_ == DALI_FLOAT, "Hsv: the GPU path supports dtype UINT8 and FLOAT");
+  }
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_UINT8, "Hsv: the GPU path expects uint8 input");
+    const int n = in.num_samples();
+    EnsureCap(n);
+    std::vector<dalib200ColorSample> cs(n);
+    for (int i = 0; i < n; i++) {
+      const int nd = in.shape().sample_dim();
+      DALI_ENFORCE(in.shape().tensor_shape_span(i)[nd - 1] == 3, "Hsv expects 3-channel (channel-last) images");
+      cs[i].num_pixels = in.shape().tensor_size(i) / 3;
+      // half_range = 128 for integer inputs (color_twist.h:141-146)
+      dalib200ColorTwistMatrix(spec_.GetArgument<float>("hue", &ws, i), spec_.GetArgument<float>("saturation", &ws, i),
+                               spec_.GetArgument<float>("value", &ws, i), 1.0f, 1.0f, 128.0f, cs[i].matrix, cs[i].offset);
+    }
+    CheckStatus(dalib200LinearTransformSetup(plan_, n, cs.data(), out_type_ == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT), "Hsv");
+    out.resize(1);
+    out[0].shape = in.shape(); out[0].type = out_type_;
+    return true;
+  }
+  void RunImpl(Workspace &ws) override { Launch(ws); }
+ private:
+  DALIDataType out_type_ = DALI_UINT8;
+};
+DALI_REGISTER_OPERATOR(Hsv, HsvGPU, GPU);
+
+// =============================================================================================== ColorSpaceConversion
+DALI_SCHEMA(ColorSpaceConversion)
+    .DocStr("Converts between various image color models.")
+    .NumInput(1).NumOutput(1).AllowSequences()
+    .AddArg("image_type", "The color space of the input image.")
+    .AddArg("output_type", "The color space of the output image.");
+
+class ColorSpaceConversionGPU : public PointwiseBase {
+ public:
+  explicit ColorSpaceConversionGPU(const OpSpec &spec) : PointwiseBase(spec, "ColorSpaceConversion") {
+    in_t_ = spec.GetArgument<int>("image_type"); out_t_ = spec.GetArgument<int>("output_type");
+    DALI_ENFORCE(in_t_ >= 0 && in_t_ <= 3 && out_t_ >= 0 && out_t_ <= 3, "ColorSpaceConversion: unsupported image type");
+  }
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_UINT8, "Color space conversion accept only uint8 tensors");    // color_space_conversion.h:49
+    const int n = in.num_samples(), nd = in.shape().sample_dim();
+    EnsureCap(n);
+    const int ic = in_t_ == DALI_GRAY ? 1 : 3, oc = out_t_ == DALI_GRAY ? 1 : 3;
+    std::vector<int64_t> npx(n);
+    out.resize(1);
+    out[0].type = DALI_UINT8;
+    out[0].shape.resize(n, nd);
+    for (int i = 0; i < n; i++) {
+      TensorShape sh = in.shape().tensor_shape(i);
+      DALI_ENFORCE(sh[nd - 1] == ic, "Incorrect number of channels: expected ", ic, ", got ", sh[nd - 1]);
+      npx[i] = in.shape().tensor_size(i) / ic;
+      sh[nd - 1] = oc;
+      out[0].shape.set_tensor_shape(i, sh);
+    }
+    CheckStatus(dalib200ColorSpaceSetup(plan_, n, npx.data(), in_t_, out_t_), "ColorSpaceConversion");
+    return true;
+  }
+  void RunImpl(Workspace &ws) override { Launch(ws); }
+ private:
+  int in_t_ = 0, out_t_ = 0;
+};
+DALI_REGISTER_OPERATOR(ColorSpaceConversion, ColorSpaceConversionGPU, GPU);
+
+// =============================================================================================== Spectrogram
+DALI_SCHEMA(Spectrogram)
+    .DocStr("Produces a spectrogram from a 1D signal.")
+    .NumInput(1).NumOutput(1)
+    .AddOptionalArgNoDefault("nfft", "Size of the FFT (default: window_length).")
+    .AddOptionalArg("window_length", "Window size in number of samples.", 512)
+    .AddOptionalArg("window_step", "Step between the STFT windows in number of samples.", 256)
+    .AddOptionalArgNoDefault("window_fn", "Samples of the window function (default: Hann).")
+    .AddOptionalArg("power", "Exponent of the magnitude of the spectrum (1 or 2).", 2)
+    .AddOptionalArg("center_windows", "Pad the signal so that windows are centred.", true)
+    .AddOptionalArg("reflect_padding", "Reflect (True) or zero (False) padding.", true)
+    .AddOptionalArg("layout", "Output layout: \"ft\" or \"tf\".", std::string("ft"));
+
+class SpectrogramGPU : public Operator<GPUBackend> {
+ public:
+  explicit SpectrogramGPU(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    args_.window_length = spec.GetArgument<int>("window_length");
+    args_.window_step = spec.GetArgument<int>("window_step");
+    args_.power = spec.GetArgument<int>("power");
+    DALI_ENFORCE(args_.window_length > 0, "Invalid window length: ", args_.window_length);
+    DALI_ENFORCE(args_.window_step > 0, "Invalid window step: ", args_.window_step);
+    DALI_ENFORCE(args_.power == 1 || args_.power == 2, "Power argument should be either `2` for energy or `1` for complex magnitude.");
+    args_.nfft = spec.ArgumentDefined("nfft") ? spec.GetArgument<int>("nfft") : args_.window_length;
+    args_.center = spec.GetArgument<bool>("center_windows"); args_.reflect = spec.GetArgument<bool>("reflect_padding");
+    layout_ = spec.GetArgument<std::string>("layout");
+    DALI_ENFORCE(layout_ == "ft" || layout_ == "tf", "Unexpected layout: ", layout_);
+    args_.layout_ft = layout_ == "ft";
+    if (spec.ArgumentDefined("window_fn")) {
+      window_ = spec.GetRepeatedArgument<float>("window_fn");
+      DALI_ENFORCE(static_cast<int>(window_.size()) == args_.window_length, "Window function should match the specified `window_length`");
+    }
+    CheckStatus(dalib200SpectrogramPlanCreate(&plan_, max_batch_size_), "Spectrogram");
+  }
+  ~SpectrogramGPU() override { dalib200SpectrogramPlanDestroy(plan_); }
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_FLOAT, "Spectrogram: the GPU path expects float input");
+    const int n = in.num_samples();
+    std::vector<int64_t> lens(n);
+    for (int i = 0; i < n; i++) {
+      const int64_t vol = in.shape().tensor_size(i);
+      const int64_t *s = in.shape().tensor_shape_span(i);
+      for (int d = 0; d < in.shape().sample_dim(); d++)
+        DALI_ENFORCE(s[d] == 1 || s[d] == vol, "Input data must be 1D or all but one dimensions must be degenerate (extent 1).");
+      lens[i] = vol;
+    }
+    CheckStatus(dalib200SpectrogramPlanSetup(plan_, &args_, window_.empty() ? nullptr : window_.data(), n, lens.data()), "Spectrogram");
+    out.resize(1);
+    out[0].type = DALI_FLOAT;
+    out[0].shape.resize(n, 2);
+    const int nbin = args_.nfft / 2 + 1;
+    for (int i = 0; i < n; i++) {
+      const int64_t nw = dalib200SpectrogramNumWindows(plan_, i);
+      out[0].shape.set_tensor_shape(i, args_.layout_ft ? TensorShape{nbin, nw} : TensorShape{nw, nbin});
+    }
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(layout_);
+    std::vector<const void *> ip(in.num_samples());
+    std::vector<void *> op(in.num_samples());
+    for (int i = 0; i < in.num_samples(); i++) { ip[i] = in.raw_tensor(i); op[i] = out.raw_mutable_tensor(i); }
+    CheckStatus(dalib200SpectrogramLaunch(plan_, ip.data(), op.data(), ws.stream()), "Spectrogram");
+  }
+ private:
+  dalib200SpectrogramPlan *plan_ = nullptr;
+  dalib200SpectrogramArgs args_{};
+  std::vector<float> window_;
+  std::string layout_;
+};
+DALI_REGISTER_OPERATOR(Spectrogram, SpectrogramGPU, GPU);
+
+// =============================================================================================== MelFilterBank
+DALI_SCHEMA(MelFilterBank)
+    .DocStr("Converts a spectrogram to a mel spectrogram by applying a bank of triangular filters.")
+    .NumInput(1).NumOutput(1)
+    .AddOptionalArg("nfilter", "Number of mel filters.", 128)
+    .AddOptionalArg("sample_rate", "Sampling rate of the audio signal.", 44100.0f)
+    .AddOptionalArg("freq_low", "The minimum frequency.", 0.0f)
+    .AddOptionalArg("freq_high", "The maximum frequency (0 = sample_rate / 2).", 0.0f)
+    .AddOptionalArg("normalize", "Normalise the triangular filter weights by the width of their bands.", true)
+    .AddOptionalArg("mel_formula", "slaney | htk", std::string("slaney"));
+
+class MelFilterBankGPU : public Operator<GPUBackend> {
+ public:
+  explicit MelFilterBankGPU(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    args_.nfilter = spec.GetArgument<int>("nfilter");
+    args_.sample_rate = spec.GetArgument<float>("sample_rate");
+    args_.freq_low = spec.GetArgument<float>("freq_low"); args_.freq_high = spec.GetArgument<float>("freq_high");
+    args_.normalize = spec.GetArgument<bool>("normalize");
+    const std::string f = spec.GetArgument<std::string>("mel_formula");
+    DALI_ENFORCE(f == "slaney" || f == "htk", "Unsupported mel_formula value \"", f, "\". Supported values are: \"slaney\", \"htk\"");
+    args_.htk = f == "htk";
+    CheckStatus(dalib200MelPlanCreate(&plan_, max_batch_size_), "MelFilterBank");
+  }
+  ~MelFilterBankGPU() override { dalib200MelPlanDestroy(plan_); }
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_FLOAT, "MelFilterBank: the GPU path expects float input");
+    DALI_ENFORCE(in.shape().sample_dim() == 2, "MelFilterBank: the GPU path expects 2-D (frequency, time) spectrograms");
+    const std::string l = in.GetLayout().str();
+    DALI_ENFORCE(l.empty() || l == "ft", "MelFilterBank: the GPU path expects the \"ft\" layout, got \"", l, "\"");
+    const int n = in.num_samples();
+    std::vector<int64_t> nwin(n);
+    int nbin = n ? static_cast<int>(in.shape().tensor_shape_span(0)[0]) : 2;
+    for (int i = 0; i < n; i++) {
+      DALI_ENFORCE(in.shape().tensor_shape_span(i)[0] == nbin, "MelFilterBank: all spectrograms of a batch must have the same number of bins");
+      nwin[i] = in.shape().tensor_shape_span(i)[1];
+    }
+    CheckStatus(dalib200MelPlanSetup(plan_, &args_, nbin, n, nwin.data()), "MelFilterBank");
+    out.resize(1);
+    out[0].type = DALI_FLOAT;
+    out[0].shape.resize(n, 2);
+    for (int i = 0; i < n; i++) out[0].shape.set_tensor_shape(i, { args_.nfilter, nwin[i] });
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout("ft");
+    std::vector<const void *> ip(in.num_samples());
+    std::vector<void *> op(in.num_samples());
+    for (int i = 0; i < in.num_samples(); i++) { ip[i] = in.raw_tensor(i); op[i] = out.raw_mutable_tensor(i); }
+    CheckStatus(dalib200MelLaunch(plan_, ip.data(), op.data(), ws.stream()), "MelFilterBank");
+  }
+ private:
+  dalib200MelPlan *plan_ = nullptr;
+  dalib200MelArgs args_{};
+};
+DALI_REGISTER_OPERATOR(MelFilterBank, MelFilterBankGPU, GPU);
+
+}  // namespace dali
+
+// ---------------------------------------------------------------------------------------------------------------
+// Test hook (CPU): the Resize size / ROI arithmetic without a pipeline, so that the reference's known-answer vectors
+// (dali/operators/image/resize/resize_attr_test.cc) can be checked where no GPU exists.
+extern "C" int dalihTestResizeParams(int mode, const float *requested_hw, const float *in_lo_hw, const float *in_hi_hw,
+                                     int subpixel_scale, const float *max_size_hw_or_null, int *dst_hw, float *lo_hw, float *hi_hw) {
+  try {
+    float req[2] = { requested_hw[0], requested_hw[1] }, lo[2] = { in_lo_hw[0], in_lo_hw[1] }, hi[2] = { in_hi_hw[0], in_hi_hw[1] };
+    dali::resize_detail::Params p;
+    dali::resize_detail::CalculateSampleParams(p, req, lo, hi, subpixel_scale != 0, false, static_cast<dali::resize_detail::Mode>(mode),
+                                               max_size_hw_or_null);
+    for (int d = 0; d < 2; d++) { dst_hw[d] = p.dst[d]; lo_hw[d] = p.lo[d]; hi_hw[d] = p.hi[d]; }
+    return 0;
+  } catch (...) { return 1; }
+}

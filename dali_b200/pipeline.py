@@ -1,0 +1,333 @@
+"""Pipeline definition and execution -- the nvidia.dali.pipeline surface for the hot path
+(dali/python/nvidia/dali/pipeline.py: Pipeline :1202 build, :1515 run; pipeline_def).
+
+Graph construction mirrors the reference: fn.* calls executed inside a pipeline definition create operator nodes in
+the *current* pipeline and return DataNodes; build() hands the OpSpecs to the C++ Pipeline (dali_b200/host), which
+instantiates the operators through the registry (DALI_REGISTER_OPERATOR) and runs them in order on one CUDA stream.
+"""
+import functools
+import threading
+
+import numpy as np
+
+from . import backend, types
+
+_tls = threading.local()
+
+
+def _current():
+    return getattr(_tls, "pipe", None)
+
+
+class DataNode:
+    """An edge of the graph (dali/python/nvidia/dali/data_node.py)."""
+
+    def __init__(self, name, device, source=None):
+        self.name, self.device, self.source = name, device, source
+
+    def gpu(self):
+        if self.device == "gpu":
+            return self
+        pipe = _current()
+        if pipe is None:
+            raise RuntimeError("DataNode.gpu() must be called inside a pipeline definition")
+        return pipe._to_gpu(self)
+
+    def __repr__(self):
+        return f"DataNode(name={self.name!r}, device={self.device!r})"
+
+
+class TensorListGPU:
+    """Output batch living in device memory.  Uniform batches expose __cuda_array_interface__ (zero copy into torch)."""
+
+    def __init__(self, dtype, layout, contiguous, shapes, ptrs, stream):
+        self._dtype, self._layout, self._contig, self._shapes, self._ptrs, self._stream = dtype, layout, contiguous, shapes, ptrs, stream
+
+    def __len__(self):
+        return len(self._ptrs)
+
+    def shape(self):
+        return [tuple(int(v) for v in s) for s in self._shapes]
+
+    @property
+    def dtype(self):
+        return types.DALIDataType(self._dtype)
+
+    def layout(self):
+        return self._layout
+
+    def is_dense_tensor(self):
+        return len(self._ptrs) > 0 and all(tuple(s) == tuple(self._shapes[0]) for s in self._shapes)
+
+    def sample(self, i):
+        return _CudaArray(self._ptrs[i], tuple(int(v) for v in self._shapes[i]), self._dtype)
+
+    def __getitem__(self, i):
+        return self.sample(i)
+
+    def as_tensor(self):
+        """The batch as one [N, ...] device tensor.  Samples are stored 256-byte aligned, so a zero-copy dense view
+        exists only when the per-sample byte size is a multiple of 256; otherwise the samples are gathered."""
+        if not self.is_dense_tensor():
+            raise RuntimeError("The batch is not uniform; use .sample(i) / at(i)")
+        shp = tuple(int(v) for v in self._shapes[0])
+        nbytes = int(np.prod(shp)) * types.to_numpy_type(self._dtype).itemsize
+        if self._contig and (len(self._ptrs) == 1 or self._ptrs[1] - self._ptrs[0] == nbytes):
+            return _CudaArray(self._ptrs[0], (len(self._ptrs),) + shp, self._dtype)
+        import torch
+        return torch.stack([torch.as_tensor(self.sample(i), device="cuda") for i in range(len(self))])
+
+    def as_cpu(self):
+        import torch
+        return [torch.as_tensor(self.sample(i), device="cuda").cpu().numpy() for i in range(len(self))]
+
+
+class _CudaArray:
+    def __init__(self, ptr, shape, dtype):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": types.to_numpy_type(dtype).str, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class TensorListCPU:
+    def __init__(self, arrays, layout):
+        self._arrays, self._layout = arrays, layout
+
+    def __len__(self):
+        return len(self._arrays)
+
+    def at(self, i):
+        return self._arrays[i]
+
+    def __getitem__(self, i):
+        return self._arrays[i]
+
+    def layout(self):
+        return self._layout
+
+
+class _ExternalSourceGroup:
+    def __init__(self, source, outputs, batch, cycle, layout, dtype, device, batch_info):
+        self.source, self.outputs, self.batch, self.cycle = source, outputs, batch, cycle
+        self.layout, self.dtype, self.device, self.batch_info = layout, dtype, device, batch_info
+        self.iterator = None
+        self.is_callable = callable(source) and not hasattr(source, "__iter__")
+
+
+class Pipeline:
+    def __init__(self, batch_size=-1, num_threads=-1, device_id=-1, seed=-1, exec_pipelined=True, prefetch_queue_depth=2,
+                 exec_async=True, exec_dynamic=False, **_ignored):
+        if batch_size is None or batch_size <= 0:
+            raise ValueError("batch_size must be a positive integer")
+        self.max_batch_size = int(batch_size)
+        self.num_threads = max(1, int(num_threads) if num_threads and num_threads > 0 else 1)
+        self.device_id = None if device_id is None or device_id < 0 else int(device_id)
+        self._nodes = []            # (schema, inst_name, spec)
+        self._externals = []        # _ExternalSourceGroup
+        self._ext_names = {}
+        self._outputs = []
+        self._counter = 0
+        self._built = False
+        self._backend = None
+        self._definition = None
+        self._iteration = 0
+        self._epoch_idx = 0
+        self._sample_idx = 0
+        self._keepalive = []
+
+    # ---- context management (with pipe: ...)
+    def __enter__(self):
+        self._prev = _current()
+        _tls.pipe = self
+        return self
+
+    def __exit__(self, *exc):
+        _tls.pipe = self._prev
+        return False
+
+    @property
+    def batch_size(self):
+        return self.max_batch_size
+
+    def _new_name(self, base):
+        self._counter += 1
+        return f"__{base}_{self._counter}"
+
+    def _to_gpu(self, node):
+        # An external-source output that has not been consumed on the CPU is simply produced on the GPU
+        # (the reference inserts a MakeContiguous copy node; the H2D copy happens in feed_input here).
+        if isinstance(node.source, _ExternalSourceGroup) and not getattr(node, "_consumed_cpu", False):
+            node.device = "gpu"
+            node.source.device = "gpu"
+            return node
+        raise RuntimeError(".gpu() is supported on fn.external_source outputs only; use device='mixed' / 'gpu' operators")
+
+    def set_outputs(self, *nodes):
+        self._outputs = list(nodes)
+
+    # ---- build: python graph -> C++ pipeline
+    def build(self):
+        if self._built:
+            return self
+        if self._definition is not None and not self._outputs:
+            with self:
+                outs = self._definition()
+            if isinstance(outs, DataNode):
+                outs = (outs,)
+            self._outputs = list(outs)
+        if not self._outputs:
+            raise RuntimeError("Pipeline has no outputs; call set_outputs() or use @pipeline_def")
+        for o in self._outputs:
+            if not isinstance(o, DataNode):
+                raise TypeError(f"Pipeline outputs must be DataNodes, got {type(o).__name__}")
+        be = backend.Pipeline(self.max_batch_size, self.num_threads, self.device_id)
+        for g in self._externals:
+            for o in g.outputs:
+                be.add_external_input(o.name, o.device, g.layout or "")
+        for schema, inst, spec in self._nodes:
+            be.add_operator(spec, inst)
+        be.set_outputs([(o.name, o.device) for o in self._outputs])
+        be.build()
+        self._backend = be
+        self._built = True
+        return self
+
+    # ---- external source feeding (external_source.py:312-1150, _run_input_callbacks)
+    def _next_batch(self, g):
+        if g.is_callable:
+            if g.batch:
+                arg = types.BatchInfo(self._iteration, self._epoch_idx) if g.batch_info else self._iteration
+                try:
+                    return g.source(arg)
+                except TypeError:
+                    return g.source()
+            res = []
+            for i in range(self.max_batch_size):
+                res.append(g.source(types.SampleInfo(self._sample_idx + i, i, self._iteration, self._epoch_idx)))
+            return res
+        if g.iterator is None:
+            g.iterator = iter(g.source)
+        try:
+            return next(g.iterator)
+        except StopIteration:
+            if g.cycle in (True, "quiet", "raise"):
+                g.iterator = iter(g.source)
+                if g.cycle == "raise":
+                    raise
+                return next(g.iterator)
+            raise
+
+    def feed_input(self, name_or_node, data, layout=None):
+        name = name_or_node.name if isinstance(name_or_node, DataNode) else self._ext_names.get(name_or_node, name_or_node)
+        self._feed(name, data, layout or "")
+
+    def _feed(self, name, data, layout):
+        if hasattr(data, "cpu") and hasattr(data, "numpy") and not isinstance(data, np.ndarray):     # torch tensor batch
+            data = data.cpu().numpy()
+        if isinstance(data, np.ndarray):
+            samples = [data[i] for i in range(data.shape[0])]
+        else:
+            samples = [s.cpu().numpy() if hasattr(s, "cpu") and not isinstance(s, np.ndarray) else np.asarray(s) for s in data]
+        if len(samples) == 0:
+            raise RuntimeError("External source returned an empty batch")
+        if len(samples) > self.max_batch_size:
+            raise RuntimeError(f"External source batch ({len(samples)}) exceeds max batch size ({self.max_batch_size})")
+        dt = samples[0].dtype
+        nd = samples[0].ndim
+        arrs = []
+        for s in samples:
+            if s.dtype != dt or s.ndim != nd:
+                raise TypeError("All samples of an external source batch must have the same type and dimensionality")
+            arrs.append(np.ascontiguousarray(s))
+        self._keepalive.append(arrs)
+        shapes = np.array([a.shape for a in arrs], np.int64).reshape(len(arrs), nd)
+        self._backend.feed_input(name, [a.ctypes.data for a in arrs], shapes, nd, int(types.from_numpy_type(dt)), layout)
+
+    def _run_input_callbacks(self):
+        self._keepalive = []
+        for g in self._externals:
+            if g.source is None:
+                continue
+            batch = self._next_batch(g)
+            if len(g.outputs) == 1:
+                batch = (batch,)
+            for o, b in zip(g.outputs, batch):
+                self._feed(o.name, b, g.layout or "")
+
+    # ---- run
+    def run(self):
+        if not self._built:
+            self.build()
+        self._run_input_callbacks()
+        self._backend.run()
+        self._backend.wait()
+        self._iteration += 1
+        self._sample_idx += self.max_batch_size
+        return self._collect_outputs()
+
+    def schedule_run(self):
+        if not self._built:
+            self.build()
+        self._run_input_callbacks()
+        self._backend.run()
+        self._iteration += 1
+        self._sample_idx += self.max_batch_size
+
+    def share_outputs(self):
+        self._backend.wait()
+        return self._collect_outputs()
+
+    def release_outputs(self):
+        pass
+
+    def outputs(self):
+        return self.share_outputs()
+
+    def _collect_outputs(self):
+        outs = []
+        stream = self._backend.stream()
+        for i in range(self._backend.num_outputs()):
+            gpu, dt, lay, cont, shapes, ptrs = self._backend.output(i)
+            if gpu:
+                outs.append(TensorListGPU(dt, lay, cont, shapes, ptrs, stream))
+            else:
+                import ctypes as C
+                npdt = types.to_numpy_type(dt)
+                arrs = []
+                for s, p in zip(shapes, ptrs):
+                    n = int(np.prod(s)) if len(s) else 1
+                    buf = (C.c_char * (n * npdt.itemsize)).from_address(p) if n else b""
+                    arrs.append(np.frombuffer(buf, npdt, n).reshape(tuple(int(v) for v in s)).copy())
+                outs.append(TensorListCPU(arrs, lay))
+        return tuple(outs)
+
+    def reset(self):
+        self._epoch_idx += 1
+        self._sample_idx = 0
+        for g in self._externals:
+            g.iterator = None
+
+    def epoch_size(self, name=None):
+        return {}
+
+    def reader_meta(self, name=None):
+        return {}
+
+    def executor_statistics(self):
+        return {}
+
+
+def pipeline_def(fn=None, **pipeline_kwargs):
+    """@pipeline_def(batch_size=..., num_threads=..., device_id=...)"""
+    def actual(func):
+        @functools.wraps(func)
+        def create(*args, **kwargs):
+            ctor = dict(pipeline_kwargs)
+            for k in ("batch_size", "num_threads", "device_id", "seed", "prefetch_queue_depth", "exec_async", "exec_pipelined",
+                      "exec_dynamic", "py_num_workers", "py_start_method", "enable_conditionals"):
+                if k in kwargs:
+                    ctor[k] = kwargs.pop(k)
+            pipe = Pipeline(**ctor)
+            pipe._definition = lambda: func(*args, **kwargs)
+            return pipe
+        return create
+    return actual(fn) if fn is not None else actual

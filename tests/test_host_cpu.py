@@ -1,0 +1,130 @@
+"""CPU tests of the host layer: schema registry -> fn.* generation, graph construction, argument validation, the Resize
+size arithmetic against the reference's own known-answer vectors, and the 'no CPU fallback' contract."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from dali_b200 import backend, fn, types, pipeline_def, Pipeline
+
+
+def test_schema_registry_and_fn_names():
+    names = set(backend.schema_names())
+    assert {"decoders__Image", "Resize", "CropMirrorNormalize", "WarpAffine", "Hsv", "ColorSpaceConversion", "Spectrogram",
+            "MelFilterBank"} <= names
+    # ops/_names.py:24-72 naming
+    for f in (fn.decoders.image, fn.resize, fn.crop_mirror_normalize, fn.warp_affine, fn.hsv, fn.color_space_conversion, fn.spectrogram,
+              fn.mel_filter_bank, fn.external_source):
+        assert callable(f)
+    assert fn.crop_mirror_normalize.schema_name == "CropMirrorNormalize"
+    # registered for GPU / mixed only: the product has no CPU implementation of the hot-path ops
+    assert backend.operator_registered("decoders__Image", "mixed") and not backend.operator_registered("decoders__Image", "cpu")
+    for s in ("Resize", "CropMirrorNormalize", "WarpAffine", "Hsv", "ColorSpaceConversion", "Spectrogram", "MelFilterBank"):
+        assert backend.operator_registered(s, "gpu") and not backend.operator_registered(s, "cpu")
+    args = backend.schema_args("Resize")
+    assert args["resize_x"][0] and "antialias" in args and "minibatch_size" in args
+    assert backend.schema_args("ColorSpaceConversion")["image_type"][1]       # required argument
+
+
+def test_nvidia_dali_alias_imports():
+    import nvidia.dali as dali
+    from nvidia.dali import fn as nfn, types as ntypes, pipeline_def as npd  # noqa: F401
+    from nvidia.dali.plugin.pytorch import DALIGenericIterator  # noqa: F401
+    assert nfn.resize is fn.resize and ntypes.FLOAT16 == 8 and dali.Pipeline is Pipeline
+
+
+def test_graph_construction_and_errors():
+    @pipeline_def(batch_size=8, num_threads=2, device_id=None)
+    def pipe():
+        j = fn.external_source(source=lambda i: [np.zeros(4, np.uint8)] * 8, name="jpegs")
+        img = fn.decoders.image(j, device="mixed")
+        img = fn.resize(img, resize_x=224, resize_y=224)
+        return fn.crop_mirror_normalize(img, dtype=types.FLOAT16, output_layout="CHW", mean=[1, 2, 3], std=[4, 5, 6])
+    p = pipe()
+    with pytest.raises(backend.BackendError, match="needs a GPU"):
+        p.build()
+    with pytest.raises(RuntimeError, match="inside a pipeline definition"):
+        fn.resize(None)
+
+    @pipeline_def(batch_size=2, num_threads=1, device_id=None)
+    def bad_arg():
+        j = fn.external_source(source=lambda i: [np.zeros((4, 4, 3), np.uint8)] * 2, device="gpu")
+        return fn.resize(j, resize_q=3)
+    with pytest.raises(TypeError, match="unexpected 'resize_q' argument"):
+        bad_arg().build()
+
+    @pipeline_def(batch_size=2, num_threads=1, device_id=None)
+    def cpu_op():
+        j = fn.external_source(source=lambda i: [np.zeros((4, 4, 3), np.uint8)] * 2)
+        return fn.resize(j, resize_x=2, device="cpu")
+    with pytest.raises(backend.BackendError, match="no CPU fallback"):
+        cpu_op().build()
+
+
+def _resize_params(mode, req, lo, hi, subpixel=True, max_size=None):
+    lib = backend.lib()
+    f2 = lambda v: (C.c_float * 2)(*v)
+    dst, olo, ohi = (C.c_int * 2)(), (C.c_float * 2)(), (C.c_float * 2)()
+    ms = f2(max_size) if max_size is not None else None
+    assert lib.dalihTestResizeParams(mode, f2(req), f2(lo), f2(hi), int(subpixel), ms, dst, olo, ohi) == 0
+    return list(dst), list(olo), list(ohi)
+
+
+DEFAULT, STRETCH, NOT_LARGER, NOT_SMALLER = 0, 1, 2, 3
+
+
+def test_resize_size_rules_reference_kats():
+    """dali/operators/image/resize/resize_attr_test.cc (2-D cases) and test_resize.py:303-315 (H, W order)."""
+    # resize_x=480 (:97-113): (768,1024) -> {360,480}; (320,240) -> {640,480}
+    assert _resize_params(DEFAULT, (0, 480), (0, 0), (768, 1024))[0] == [360, 480]
+    assert _resize_params(DEFAULT, (0, 480), (0, 0), (320, 240))[0] == [640, 480]
+    # resize_y=480 (:114-129): -> {480,640}, {480,360}
+    assert _resize_params(DEFAULT, (480, 0), (0, 0), (768, 1024))[0] == [480, 640]
+    assert _resize_params(DEFAULT, (480, 0), (0, 0), (320, 240))[0] == [480, 360]
+    # resize_shorter=600 (:425-454): (400,800) -> {600,1200}; (500,250) -> {1200,600}; with max_size [800,1000] -> {500,1000}, {800,400}
+    assert _resize_params(NOT_SMALLER, (600, 600), (0, 0), (400, 800))[0] == [600, 1200]
+    assert _resize_params(NOT_SMALLER, (600, 600), (0, 0), (500, 250))[0] == [1200, 600]
+    assert _resize_params(NOT_SMALLER, (600, 600), (0, 0), (400, 800), max_size=(800, 1000))[0] == [500, 1000]
+    assert _resize_params(NOT_SMALLER, (600, 600), (0, 0), (500, 250), max_size=(800, 1000))[0] == [800, 400]
+    # resize_longer=600 (:456-475): (400,800) -> {300,600}; (500,250) -> {600,300}
+    assert _resize_params(NOT_LARGER, (600, 600), (0, 0), (400, 800))[0] == [300, 600]
+    assert _resize_params(NOT_LARGER, (600, 600), (0, 0), (500, 250))[0] == [600, 300]
+    # python mirror (test_resize.py:303-315), (W,H) there -> (H,W) here
+    assert _resize_params(NOT_SMALLER, (600, 600), (0, 0), (480, 640), max_size=(720, 720))[0] == [540, 720]
+    assert _resize_params(DEFAULT, (0, 600), (0, 0), (480, 640))[0] == [450, 600]
+    assert _resize_params(DEFAULT, (600, 0), (0, 0), (480, 640))[0] == [600, 800]
+    # ROI + flip (:477-515): resize_x=200, resize_y=-100, roi (7,200)-(330,40) on (400,800) -> dst {100,200}, lo {330,200}, hi {7,40}
+    dst, lo, hi = _resize_params(DEFAULT, (-100, 200), (7, 200), (330, 40))
+    assert dst == [100, 200] and lo == [330.0, 200.0] and hi == [7.0, 40.0]
+    # C2: resize_x = resize_y = 224 on 1080p
+    assert _resize_params(DEFAULT, (224, 224), (0, 0), (1080, 1920)) == ([224, 224], [0.0, 0.0], [1080.0, 1920.0])
+
+
+def test_resize_subpixel_roi_adjustment():
+    """resize_attr_base.h:97-113: when the rounded size differs from the requested fractional size the ROI is scaled
+    about its centre.  (:368-423, last axes of the not_smaller / max_size case: dst 384x288 from 320x240.)"""
+    dst, lo, hi = _resize_params(NOT_SMALLER, (480, 600), (0, 0), (320, 240), max_size=(384, 400))
+    assert dst == [384, 288] and lo == [0.0, 0.0] and hi == [320.0, 240.0]
+    dst, lo, hi = _resize_params(DEFAULT, (0, 100.4), (0, 0), (30, 40))      # height 75.3 -> 75: ROI shrinks about the centre
+    assert dst == [75, 100]
+    assert lo[0] > 0 and abs((hi[0] - lo[0]) - 30 * 75 / 75.3) < 1e-3 and abs((lo[0] + hi[0]) / 2 - 15) < 1e-4
+
+
+def test_external_source_feeding_modes():
+    calls = []
+
+    def per_sample(info):
+        calls.append((info.idx_in_epoch, info.idx_in_batch, info.iteration))
+        return np.full((2, 2, 3), info.idx_in_batch, np.uint8)
+    with Pipeline(batch_size=4, num_threads=1, device_id=None) as p:
+        a = fn.external_source(source=per_sample, batch=False)
+        b = fn.external_source(source=iter([[np.zeros(3, np.float32)] * 4] * 2), name="b")
+        p.set_outputs(a, b)
+    p.build()
+    outs = p.run()
+    assert [o.shape for o in (outs[0].at(0), outs[1].at(3))] == [(2, 2, 3), (3,)]
+    assert outs[0].at(2)[0, 0, 0] == 2 and calls[:4] == [(0, 0, 0), (1, 1, 0), (2, 2, 0), (3, 3, 0)]
+    p.run()
+    assert calls[4] == (4, 0, 1)
+    with pytest.raises(StopIteration):
+        p.run()

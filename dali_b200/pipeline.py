@@ -239,7 +239,7 @@ class Pipeline:
                 raise TypeError("All samples of an external source batch must have the same type and dimensionality")
             arrs.append(np.ascontiguousarray(s))
         self._keepalive.append(arrs)
-        shapes = np.array([a.shape for a in arrs], np.int64).reshape(len(arrs), nd)
+        shapes = np.array([a.shape for a in arrs], np.int64).reshape(len(arrs), nd) if nd else np.zeros((len(arrs), 0), np.int64)
         self._backend.feed_input(name, [a.ctypes.data for a in arrs], shapes, nd, int(types.from_numpy_type(dt)), layout)
 
     def _run_input_callbacks(self):

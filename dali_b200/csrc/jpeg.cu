@@ -179,11 +179,34 @@ __global__ void __launch_bounds__(256) unstuff_scatter_kernel(const uint8_t *__r
 // ============================================================================================
 // Huffman decoding
 struct BitReader {
-  const uint32_t *words;    // clean stream (word-swapped), 16-byte aligned, padded
-  __device__ __forceinline__ uint32_t peek32(uint32_t p) const {
-    const uint32_t wi = p >> 5, sh = p & 31;
-    const uint32_t w0 = __ldg(words + wi), w1 = __ldg(words + wi + 1);
-    return __funnelshift_l(w1, w0, sh);          // next 32 bits, MSB first
+  const uint32_t *words;    // clean stream (word-swapped), 16-byte aligned, zero padded
+};
+
+// 64-bit MSB-aligned window over the stream: one 32-bit load per 32 consumed bits (instead of two loads per symbol --
+// per-thread streams are 128 B apart, so every load is 32 L1 wavefronts per warp; they, not the ALU, were the bound).
+struct BitWindow {
+  const uint32_t *words;
+  uint64_t acc;
+  int nbits;
+  uint32_t wi;
+  __device__ __forceinline__ void init(const uint32_t *w, uint32_t p) {
+    words = w;
+    wi = p >> 5;
+    const uint32_t sh = p & 31;
+    const uint64_t two = ((uint64_t)__ldg(words + wi) << 32) | __ldg(words + wi + 1);
+    acc = two << sh;
+    nbits = 64 - (int)sh;
+    wi += 2;
+  }
+  __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(acc >> 32); }
+  __device__ __forceinline__ void consume(int n) {      // n <= 31
+    acc <<= n;
+    nbits -= n;
+    if (nbits < 32) {
+      acc |= (uint64_t)__ldg(words + wi) << (32 - nbits);
+      wi++;
+      nbits += 32;
+    }
   }
 };
 
@@ -194,55 +217,54 @@ __device__ __forceinline__ uint64_t pack_state(uint32_t p, int c, int z) {
 }
 
 // Decodes symbols that START before end_bit.  When WRITE, stores coefficients (natural order inside the block)
-// at slot indices slot0 + n; never writes at or beyond slot_limit.
+// at slot indices slot0 + n (AC) or into the compact per-block DC array; never writes at or beyond slot_limit.
+// The symbol loop is written with selects instead of branches: the 32 lanes of a warp decode unrelated bit patterns.
 template <bool WRITE>
 __device__ __forceinline__ void decode_range(const BitReader &br, const TableSet *__restrict__ ts, const JpegImage &im,
-                                             DecState &st, uint32_t end_bit, int16_t *__restrict__ coef, int64_t slot0,
-                                             int64_t slot_limit) {
+                                             DecState &st, uint32_t end_bit, int16_t *__restrict__ coef, int16_t *__restrict__ dcv,
+                                             int64_t slot0, int64_t slot_limit) {
   uint32_t p = st.p; int c = st.c, z = st.z; uint32_t n = st.n;
   const int bpm = im.bpm;
+  if (p >= end_bit) return;
+  BitWindow bw;
+  bw.init(br.words, p);
   while (p < end_bit) {
     if (WRITE && slot0 + n >= slot_limit) break;
-    const HuffTable &ht = ts->t[z == 0 ? im.blk_dc[c] : im.blk_ac[c]];
-    const uint32_t w = br.peek32(p);
-    uint32_t e = ht.lut[w >> (32 - kLutBits)];
+    const bool is_dc = z == 0;
+    const HuffTable &ht = ts->t[is_dc ? im.blk_dc[c] : im.blk_ac[c]];
+    const uint32_t w = bw.peek32();
+    const uint32_t e = ht.lut[w >> (32 - kLutBits)];
     uint32_t len = e >> 8, sym = e & 0xFF;
-    if (len == 0) {                                  // slow path: codes longer than kLutBits
+    if (len == 0) {                                  // slow path: codes longer than kLutBits (rare)
       const int32_t code16 = (int32_t)(w >> 16);
       len = kLutBits + 1;
       while (len <= 16 && code16 >= ht.maxcode[len]) len++;
       if (len > 16) { len = 16; sym = 0; }
       else sym = ht.vals[(ht.valoff[len] + (code16 >> (16 - len))) & 0xFF];
     }
-    int s;
-    if (z == 0) {
-      s = sym & 15;
-    } else {
-      const int r = sym >> 4;
-      s = sym & 15;
-      if (s == 0) {
-        p += len;
-        if (r == 15) { z += 16; n += 16; }
-        else { n += 64 - z; z = 64; }
-        if (z >= 64) { z = 0; c = c + 1 == bpm ? 0 : c + 1; }
-        continue;
+    const int s = sym & 15;
+    const int r = is_dc ? 0 : (int)(sym >> 4);
+    // magnitude bits (EXTEND, T.81 F.2.2.1); s == 0 -> v = 0
+    const int bits = (int)((w << len) >> 1 >> (31 - s));          // (w << len) >> (32 - s) without an undefined shift for s == 0
+    const int v = s ? (bits < (1 << (s - 1)) ? bits - (1 << s) + 1 : bits) : 0;
+    // slots skipped before the coefficient: run (AC), 16 (ZRL) or the rest of the block (EOB)
+    const bool eob_like = !is_dc && s == 0;
+    int adv = eob_like ? (r == 15 ? 16 : 64 - z) : r;
+    int zz = z + adv;
+    if (!eob_like && zz > 63) { adv -= zz - 63; zz = 63; }        // corrupt / speculative: stay inside the block
+    n += adv;
+    const int used = (int)len + s;
+    p += used;
+    bw.consume(used);
+    if (!eob_like) {
+      if (WRITE && slot0 + n < slot_limit) {
+        const int64_t slot = slot0 + n;
+        if (is_dc) dcv[slot >> 6] = (int16_t)v;
+        else if (v != 0 || true) coef[(slot & ~(int64_t)63) | c_zigzag[zz]] = (int16_t)v;
       }
-      z += r; n += r;
-      if (z > 63) { n -= (z - 63); z = 63; }         // corrupt / speculative: stay inside the block
+      zz++; n++;
     }
-    int v = 0;
-    if (s) {
-      // code (<=16 bits) + magnitude (<=11 valid, <=15 possible) may exceed the 32-bit window: refetch
-      const uint32_t w2 = (len + s > 32) ? br.peek32(p + len) : (w << len);
-      const int bits = (int)(w2 >> (32 - s));
-      v = bits < (1 << (s - 1)) ? bits - (1 << s) + 1 : bits;
-    }
-    p += len + s;
-    if (WRITE && slot0 + n < slot_limit) {
-      const int64_t slot = slot0 + n;
-      coef[(slot & ~(int64_t)63) | c_zigzag[z]] = (int16_t)v;
-    }
-    z++; n++;
+    z = zz;
     if (z >= 64) { z = 0; c = c + 1 == bpm ? 0 : c + 1; }
   }
   st.p = p; st.c = c; st.z = z; st.n = n;
@@ -273,6 +295,7 @@ struct HuffCtx {
   const uint8_t *clean;
   uint64_t *s_state; uint32_t *s_n;
   int16_t *coef;
+  int16_t *dc;             // compact DC array: one int16 per block, same block order as coef
   int log2_sub;            // log2 of the subsequence size in BITS
   int32_t *status;         // per image: 0 ok, 1 = slot count mismatch (corrupt stream)
 };
@@ -306,7 +329,7 @@ __global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx c
   const int64_t g = (int64_t)im.subseq_begin + j;
   if (valid) {
     st.p = jl << cx.log2_sub;
-    decode_range<false>(br, &ts, im, st, min((jl + 1) << cx.log2_sub, clean_bits), nullptr, 0, 0);
+    decode_range<false>(br, &ts, im, st, min((jl + 1) << cx.log2_sub, clean_bits), nullptr, nullptr, 0, 0);
     cx.s_state[g] = pack_state(st.p, st.c, st.z);
     cx.s_n[g] = st.n;
   }
@@ -320,7 +343,7 @@ __global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx c
         active = false;
       } else {
         st.n = 0;
-        decode_range<false>(br, &ts, im, st, min((nxt + 1) << cx.log2_sub, clean_bits), nullptr, 0, 0);
+        decode_range<false>(br, &ts, im, st, min((nxt + 1) << cx.log2_sub, clean_bits), nullptr, nullptr, 0, 0);
         const uint64_t ns = pack_state(st.p, st.c, st.z);
         // The slot count is ALWAYS written: a chain that merely converged inside this subsequence left a
         // count computed from a wrong entry state; the last visitor of an entry is the one whose entry state
@@ -369,7 +392,7 @@ __global__ void __launch_bounds__(1024) huff_sync_inter_kernel(HuffCtx cx) {
       bool synced = false;
       for (int k = 0; k < kSyncThreads && jl + k < nsub_eff; k++) {
         st.n = 0;
-        decode_range<false>(br, &ts, im, st, min((jl + k + 1) << cx.log2_sub, clean_bits), nullptr, 0, 0);
+        decode_range<false>(br, &ts, im, st, min((jl + k + 1) << cx.log2_sub, clean_bits), nullptr, nullptr, 0, 0);
         const uint64_t ns = pack_state(st.p, st.c, st.z);
         const bool same = cx.s_state[g0 + k] == ns;
         cx.s_state[g0 + k] = ns; cx.s_n[g0 + k] = st.n;     // always: see huff_sync_intra_kernel
@@ -436,55 +459,54 @@ __global__ void __launch_bounds__(kSyncThreads) huff_write_kernel(HuffCtx cx) {
   }
   BitReader br{reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off)};
   int16_t *coef = cx.coef + im.coef_off;
-  decode_range<true>(br, &ts, im, st, min((jl + 1) << cx.log2_sub, clean_bits), coef, u.slot_base + cx.s_n[g],
+  int16_t *dcv = cx.dc + im.coef_off / 64;
+  decode_range<true>(br, &ts, im, st, min((jl + 1) << cx.log2_sub, clean_bits), coef, dcv, u.slot_base + cx.s_n[g],
                      u.slot_base + u.nslots);
 }
 
 // ============================================================================================
-// D1: DC prediction.  One CTA per image; the blocks of each component are visited in scan order.
-__global__ void __launch_bounds__(1024) dc_scan_kernel(const JpegImage *__restrict__ images, int16_t *__restrict__ coef_arena) {
+// D1: DC prediction on the compact per-block DC array (one int16 per block, MCU order).  One CTA per image; the blocks
+// of each component are visited in scan order; restart intervals reset the predictor.
+__global__ void __launch_bounds__(1024) dc_scan_kernel(const JpegImage *__restrict__ images, int16_t *__restrict__ dc_arena) {
   __shared__ int warp_tot[32];
   __shared__ int carry;
   const JpegImage &im = images[blockIdx.x];
-  int16_t *coef = coef_arena + im.coef_off;
+  int16_t *dc = dc_arena + im.coef_off / 64;
   const int nmcu = im.mcux * im.mcuy;
   const int ri = im.restart_interval > 0 ? im.restart_interval : nmcu;
   for (int comp = 0; comp < im.ncomp; comp++) {
-    // blocks of this component inside one MCU
     int nb = 0, bidx[kMaxBlocksPerMcu];
     for (int b = 0; b < im.bpm; b++) if (im.blk_comp[b] == comp) bidx[nb++] = b;
     const int total = nmcu * nb;
     if (ri >= nmcu) {
-      // single segment: block-wide inclusive scan
       __syncthreads();
       if (threadIdx.x == 0) carry = 0;
       __syncthreads();
       for (int base = 0; base < total; base += blockDim.x) {
         const int i = base + threadIdx.x;
-        int64_t slot = 0; int v = 0;
-        if (i < total) { slot = ((int64_t)(i / nb) * im.bpm + bidx[i % nb]) * 64; v = coef[slot]; }
+        int idx = 0, v = 0;
+        if (i < total) { idx = (i / nb) * im.bpm + bidx[i % nb]; v = dc[idx]; }
         int incl = v;
         for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += x; }
         if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
         __syncthreads();
         int woff = 0, tot = 0;
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) { if (w < (int)(threadIdx.x >> 5)) woff += warp_tot[w]; tot += warp_tot[w]; }
-        if (i < total) coef[slot] = (int16_t)(carry + woff + incl);
+        if (i < total) dc[idx] = (int16_t)(carry + woff + incl);
         __syncthreads();
         if (threadIdx.x == 0) carry += tot;
         __syncthreads();
       }
     } else {
-      // restart intervals: one thread per interval, sequential inside
       const int nseg = (nmcu + ri - 1) / ri;
       for (int sgi = threadIdx.x; sgi < nseg; sgi += blockDim.x) {
         int pred = 0;
         const int m1 = min(nmcu, (sgi + 1) * ri);
         for (int m = sgi * ri; m < m1; m++)
           for (int k = 0; k < nb; k++) {
-            const int64_t slot = ((int64_t)m * im.bpm + bidx[k]) * 64;
-            pred += coef[slot];
-            coef[slot] = (int16_t)pred;
+            const int idx = m * im.bpm + bidx[k];
+            pred += dc[idx];
+            dc[idx] = (int16_t)pred;
           }
       }
     }
@@ -546,8 +568,8 @@ __device__ __forceinline__ int find_image_by_coefblock(const JpegImage *im, int 
 }
 
 __global__ void __launch_bounds__(128) idct_kernel(const JpegImage *__restrict__ images, int nimages, int64_t total_blocks,
-                                                   const int16_t *__restrict__ coef_arena, const QuantSet *__restrict__ quants,
-                                                   uint8_t *__restrict__ planes) {
+                                                   const int16_t *__restrict__ coef_arena, const int16_t *__restrict__ dc_arena,
+                                                   const QuantSet *__restrict__ quants, uint8_t *__restrict__ planes) {
   for (int64_t gb = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gb < total_blocks; gb += (int64_t)gridDim.x * blockDim.x) {
     const int ii = find_image_by_coefblock(images, nimages, gb);
     const JpegImage &im = images[ii];
@@ -571,6 +593,7 @@ __global__ void __launch_bounds__(128) idct_kernel(const JpegImage *__restrict__
           in[r * 8 + 2 * k + 1] = (w[k] >> 16) * (int)q[r * 8 + 2 * k + 1];
         }
       }
+      in[0] = (int)__ldg(dc_arena + gb) * (int)q[0];        // DC lives in the compact array (after prediction)
 #pragma unroll
       for (int x = 0; x < 8; x++) {       // pass 1: columns
         int o[8];
@@ -990,6 +1013,7 @@ struct dalib200JpegPlan {
   uint32_t *d_unit_len = nullptr; size_t d_unit_cap = 0;
   uint64_t *d_state = nullptr; uint32_t *d_n = nullptr; size_t d_sub_cap = 0;
   int16_t *d_coef = nullptr; size_t d_coef_cap = 0;
+  int16_t *d_dc = nullptr; size_t d_dc_cap = 0;
   uint8_t *d_planes = nullptr; size_t d_planes_cap = 0;
   int32_t *d_status = nullptr; size_t d_status_cap = 0;
   cudaEvent_t uploaded = nullptr;
@@ -1039,7 +1063,7 @@ int dalib200JpegPlanDestroy(dalib200JpegPlan *p) {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   if (p->h_stage) cudaFreeHost(p->h_stage);
-  void *bufs[] = { p->d_stage, p->d_clean, p->d_chunk, p->d_unit_len, p->d_state, p->d_n, p->d_coef, p->d_planes, p->d_status };
+  void *bufs[] = { p->d_stage, p->d_clean, p->d_chunk, p->d_unit_len, p->d_state, p->d_n, p->d_coef, p->d_dc, p->d_planes, p->d_status };
   for (void *b : bufs) if (b) cudaFree(b);
   delete p;
   return DALIB200_SUCCESS;
@@ -1270,6 +1294,10 @@ int dalib200JpegDebugGetCoefficients(dalib200JpegPlan *p, int sample, int16_t *o
   DB_CHECK_ARG(count <= have, "JpegDebugGetCoefficients: sample has %zu coefficients", have);
   DB_CUDA(cudaDeviceSynchronize());
   DB_CUDA(cudaMemcpy(out, p->d_coef + im.coef_off, count * sizeof(int16_t), cudaMemcpyDeviceToHost));
+  // the DC terms live in the compact per-block array
+  std::vector<int16_t> dcs((count + 63) / 64);
+  DB_CUDA(cudaMemcpy(dcs.data(), p->d_dc + im.coef_off / 64, dcs.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
+  for (size_t b = 0; b * 64 < count; b++) out[b * 64] = dcs[b];
   return DALIB200_SUCCESS;
 }
 
@@ -1308,6 +1336,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
     if ((rc = GrowDevice(p->d_n, cap2, (size_t)p->total_subseq + 1))) return rc;
   }
   if ((rc = GrowDevice(p->d_coef, p->d_coef_cap, (size_t)p->total_coefs + 64))) return rc;
+  if ((rc = GrowDevice(p->d_dc, p->d_dc_cap, (size_t)p->total_coefs / 64 + 64))) return rc;
   if ((rc = GrowDevice(p->d_planes, p->d_planes_cap, (size_t)p->total_plane_bytes + 64))) return rc;
   if ((rc = GrowDevice(p->d_status, p->d_status_cap, (size_t)p->n + 1))) return rc;
   // image descriptors carry the output pointers: small separate upload from a scratch area of the pinned buffer
@@ -1334,6 +1363,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   // the clean stream must be zero-padded behind every unit (the bit reader peeks ahead)
   DB_CUDA(cudaMemsetAsync(p->d_clean, 0, p->clean_bytes + 64, s));
   { ProfScope ps_("jpeg_memset_coef", s); DB_CUDA(cudaMemsetAsync(p->d_coef, 0, (size_t)p->total_coefs * sizeof(int16_t), s)); }
+  DB_CUDA(cudaMemsetAsync(p->d_dc, 0, (size_t)(p->total_coefs / 64) * sizeof(int16_t), s));
   DB_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * p->n, s));
   {
     const int grid = (int)std::min<uint32_t>(p->nchunks, (uint32_t)sms * 16);
@@ -1344,16 +1374,16 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   }
   HuffCtx cx;
   cx.images = d_images; cx.nimages = p->n; cx.units = d_units; cx.unit_clean_len = p->d_unit_len; cx.tables = d_tables;
-  cx.clean = p->d_clean; cx.s_state = p->d_state; cx.s_n = p->d_n; cx.coef = p->d_coef; cx.log2_sub = p->log2_sub;
+  cx.clean = p->d_clean; cx.s_state = p->d_state; cx.s_n = p->d_n; cx.coef = p->d_coef; cx.dc = p->d_dc; cx.log2_sub = p->log2_sub;
   cx.status = p->d_status;
   { ProfScope ps_("jpeg_huff_sync_intra", s); huff_sync_intra_kernel<<<p->total_blocks_sync, kSyncThreads, 0, s>>>(cx); }
   { ProfScope ps_("jpeg_huff_sync_inter", s); huff_sync_inter_kernel<<<p->n, 1024, 0, s>>>(cx); }
   { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_sync, kSyncThreads, 0, s>>>(cx); }
-  { ProfScope ps_("jpeg_dc_scan", s); dc_scan_kernel<<<p->n, 1024, 0, s>>>(d_images, p->d_coef); }
+  { ProfScope ps_("jpeg_dc_scan", s); dc_scan_kernel<<<p->n, 1024, 0, s>>>(d_images, p->d_dc); }
   {
     const int64_t total_blocks = p->total_coefs / 64;
     const int grid = (int)std::min<int64_t>((total_blocks + 127) / 128, (int64_t)sms * 32);
-    { ProfScope ps_("jpeg_idct", s); idct_kernel<<<grid, 128, 0, s>>>(d_images, p->n, total_blocks, p->d_coef, d_quants, p->d_planes); }
+    { ProfScope ps_("jpeg_idct", s); idct_kernel<<<grid, 128, 0, s>>>(d_images, p->n, total_blocks, p->d_coef, p->d_dc, d_quants, p->d_planes); }
     if (p->total_quads > 0) {
       const int grid2 = (int)std::min<int64_t>((p->total_quads + 255) / 256, (int64_t)sms * 32);
       { ProfScope ps_("jpeg_upsample_color_generic", s); color_kernel<<<grid2, 256, 0, s>>>(d_images, d_quads, p->n, p->total_quads, p->d_planes); }

@@ -226,15 +226,24 @@ __global__ void __launch_bounds__(256) resample_fused_kernel(const RsDesc *__res
             float2 a01 = make_float2(0.0f, 0.0f), a23 = make_float2(0.0f, 0.0f);
             const float *cy = s_cy + t * Sy;
             const int *rr = s_row + t * Sy;
-#pragma unroll 2
-            for (int k = 0; k < Sy; k++) {
-              const uint32_t w = ld_nc_u32(reinterpret_cast<const uint32_t *>(colp + (int64_t)rr[k] * pitch));
-              const float2 c2 = make_float2(cy[k], cy[k]);
-              // NOTE: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false, which
-              // would round once instead of twice; the products therefore use the scalar (never contracted) mul.rn.
-              const float2 f01 = bytes01_to_float(w), f23 = bytes23_to_float(w);
-              a01 = add2_rn(a01, make_float2(mul_rn(f01.x, c2.x), mul_rn(f01.y, c2.x)));
-              a23 = add2_rn(a23, make_float2(mul_rn(f23.x, c2.x), mul_rn(f23.y, c2.x)));
+            // taps in chunks of 8: all loads of a chunk are issued before the first use (memory-level parallelism;
+            // with 2 CTAs x 256 threads per SM the kernel is otherwise latency bound), accumulation stays in k order
+            for (int k0 = 0; k0 < Sy; k0 += 8) {
+              uint32_t wv[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++)
+                wv[j] = k0 + j < Sy ? ld_nc_u32(reinterpret_cast<const uint32_t *>(colp + (int64_t)rr[k0 + j] * pitch)) : 0u;
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                if (k0 + j < Sy) {
+                  // NOTE: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with -fmad=false, which
+                  // would round once instead of twice; the products therefore use the scalar (never contracted) mul.rn.
+                  const float ck = cy[k0 + j];
+                  const float2 f01 = bytes01_to_float(wv[j]), f23 = bytes23_to_float(wv[j]);
+                  a01 = add2_rn(a01, make_float2(mul_rn(f01.x, ck), mul_rn(f01.y, ck)));
+                  a23 = add2_rn(a23, make_float2(mul_rn(f23.x, ck), mul_rn(f23.y, ck)));
+                }
+              }
             }
             *reinterpret_cast<float4 *>(tmp + t * row_elems + 4 * jw) = make_float4(a01.x, a01.y, a23.x, a23.y);
           }

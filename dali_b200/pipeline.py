@@ -128,11 +128,17 @@ class Pipeline:
         self._counter = 0
         self._built = False
         self._backend = None
+        self._slots = []            # one C++ pipeline (stream, buffers, operator plans) per prefetch slot
+        self._depth = max(1, int(prefetch_queue_depth) if exec_pipelined else 1)
+        self._sched = []            # slots with a batch in flight, oldest first
+        self._next_slot = 0
+        self._exhausted = False
         self._definition = None
         self._iteration = 0
         self._epoch_idx = 0
         self._sample_idx = 0
         self._keepalive = []
+        self._cur_slot = 0
 
     # ---- context management (with pipe: ...)
     def __enter__(self):
@@ -179,15 +185,20 @@ class Pipeline:
         for o in self._outputs:
             if not isinstance(o, DataNode):
                 raise TypeError(f"Pipeline outputs must be DataNodes, got {type(o).__name__}")
-        be = backend.Pipeline(self.max_batch_size, self.num_threads, self.device_id)
-        for g in self._externals:
-            for o in g.outputs:
-                be.add_external_input(o.name, o.device, g.layout or "")
-        for schema, inst, spec in self._nodes:
-            be.add_operator(spec, inst)
-        be.set_outputs([(o.name, o.device) for o in self._outputs])
-        be.build()
-        self._backend = be
+        # prefetch_queue_depth independent executor slots (the reference's queue depth, exec2.h:66-131): while the GPU works on
+        # batch i, the host parses / stages / uploads batch i+1 into the other slot.
+        for _ in range(self._depth):
+            be = backend.Pipeline(self.max_batch_size, self.num_threads, self.device_id)
+            for g in self._externals:
+                for o in g.outputs:
+                    be.add_external_input(o.name, o.device, g.layout or "")
+            for schema, inst, spec in self._nodes:
+                be.add_operator(spec, inst)
+            be.set_outputs([(o.name, o.device) for o in self._outputs])
+            be.build()
+            self._slots.append(be)
+        self._backend = self._slots[0]
+        self._keep = [[] for _ in self._slots]
         self._built = True
         return self
 
@@ -218,6 +229,7 @@ class Pipeline:
 
     def feed_input(self, name_or_node, data, layout=None):
         name = name_or_node.name if isinstance(name_or_node, DataNode) else self._ext_names.get(name_or_node, name_or_node)
+        self._cur_slot = self._next_slot
         self._feed(name, data, layout or "")
 
     def _feed(self, name, data, layout):
@@ -238,12 +250,13 @@ class Pipeline:
             if s.dtype != dt or s.ndim != nd:
                 raise TypeError("All samples of an external source batch must have the same type and dimensionality")
             arrs.append(np.ascontiguousarray(s))
-        self._keepalive.append(arrs)
+        self._keep[self._cur_slot].append(arrs)
         shapes = np.array([a.shape for a in arrs], np.int64).reshape(len(arrs), nd) if nd else np.zeros((len(arrs), 0), np.int64)
-        self._backend.feed_input(name, [a.ctypes.data for a in arrs], shapes, nd, int(types.from_numpy_type(dt)), layout)
+        self._slots[self._cur_slot].feed_input(name, [a.ctypes.data for a in arrs], shapes, nd, int(types.from_numpy_type(dt)), layout)
 
-    def _run_input_callbacks(self):
-        self._keepalive = []
+    def _run_input_callbacks(self, slot):
+        self._cur_slot = slot
+        self._keep[slot] = []
         for g in self._externals:
             if g.source is None:
                 continue
@@ -254,27 +267,26 @@ class Pipeline:
                 self._feed(o.name, b, g.layout or "")
 
     # ---- run
-    def run(self):
-        if not self._built:
-            self.build()
-        self._run_input_callbacks()
-        self._backend.run()
-        self._backend.wait()
-        self._iteration += 1
-        self._sample_idx += self.max_batch_size
-        return self._collect_outputs()
-
     def schedule_run(self):
+        """Feeds the external sources and enqueues one iteration on the next free slot (asynchronous)."""
         if not self._built:
             self.build()
-        self._run_input_callbacks()
-        self._backend.run()
+        if len(self._sched) >= self._depth:
+            raise RuntimeError("All prefetch slots are in flight; call share_outputs() / release_outputs() first")
+        slot = self._next_slot
+        self._run_input_callbacks(slot)
+        self._slots[slot].run()
+        self._sched.append(slot)
+        self._next_slot = (slot + 1) % self._depth
         self._iteration += 1
         self._sample_idx += self.max_batch_size
 
     def share_outputs(self):
-        self._backend.wait()
-        return self._collect_outputs()
+        if not self._sched:
+            raise StopIteration
+        slot = self._sched.pop(0)
+        self._slots[slot].wait()
+        return self._collect_outputs(slot)
 
     def release_outputs(self):
         pass
@@ -282,11 +294,27 @@ class Pipeline:
     def outputs(self):
         return self.share_outputs()
 
-    def _collect_outputs(self):
+    def run(self):
+        """One iteration; returns its outputs (valid until the slot is reused, i.e. for `prefetch_queue_depth` - 1 further
+        run() calls -- the reference invalidates them at the next run()).  The following batches are scheduled before waiting."""
+        if not self._built:
+            self.build()
+        while len(self._sched) < self._depth and not self._exhausted:
+            try:
+                self.schedule_run()
+            except StopIteration:
+                self._exhausted = True
+        if not self._sched:
+            self._exhausted = False
+            raise StopIteration
+        return self.share_outputs()
+
+    def _collect_outputs(self, slot=0):
         outs = []
-        stream = self._backend.stream()
-        for i in range(self._backend.num_outputs()):
-            gpu, dt, lay, cont, shapes, ptrs = self._backend.output(i)
+        be = self._slots[slot]
+        stream = be.stream()
+        for i in range(be.num_outputs()):
+            gpu, dt, lay, cont, shapes, ptrs = be.output(i)
             if gpu:
                 outs.append(TensorListGPU(dt, lay, cont, shapes, ptrs, stream))
             else:
@@ -303,6 +331,7 @@ class Pipeline:
     def reset(self):
         self._epoch_idx += 1
         self._sample_idx = 0
+        self._exhausted = False
         for g in self._externals:
             g.iterator = None
 

@@ -41,9 +41,7 @@ class DALIGenericIterator:
         torch = self._torch
         res = []
         for p in self._pipes:
-            p.schedule_run()
-        for p in self._pipes:
-            outs = p.share_outputs()
+            outs = p.run()          # keeps `prefetch_queue_depth` batches in flight and returns the oldest
             if len(outs) != len(self.output_map):
                 raise RuntimeError(f"The pipeline has {len(outs)} outputs but output_map has {len(self.output_map)} names")
             d = {}

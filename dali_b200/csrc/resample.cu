@@ -111,6 +111,10 @@ constexpr int kTmpFloats = 24 * 1024;     // 96 KB of fp32 intermediate per CTA 
 constexpr int kMaxTileH = 16;             // output rows per tile in the vertical-first order
 constexpr int kMaxSupportSmem = 64;       // vertical taps whose coefficients are staged in smem
 constexpr int kTileTableBytes = kMaxTileH * kMaxSupportSmem * 8;   // offsets (in 4-byte words) into the table arena
+constexpr int kWalkMax = 96;              // steps (source rows incl. border repeats) of one tile's row walk
+constexpr int kWalkSlots = 4;             // output rows that may be "open" at the same source row
+constexpr int kWalkWords = 3;             // 32-bit word columns per thread
+static_assert(kWalkMax * kWalkSlots * 16 + kWalkMax * 8 <= kTileTableBytes, "walk tables must fit the tile table area");
 
 struct RsDesc {
   const void *in;
@@ -122,6 +126,10 @@ struct RsDesc {
   int32_t simd_flat_end;     // vertical last pass, u8 out: flat x*C+c < this -> half-to-even
   int32_t tile_h, tile_w, tiles_x, tiles_y;
   int32_t aligned4;          // input base and row pitch are multiples of 4 bytes (filled at launch)
+  float neg_zero;            // -0.0f, read at run time: an addend ptxas cannot fold (see stage B of resample_stream_kernel)
+  int32_t use_stream;        // this sample is processed by resample_stream_kernel (decided at launch)
+  int32_t tile_walk;         // the tile kernel may use the row walk (tile step count fits)
+  int32_t walk_slots;        // > 0: vertical pass by the row walk with this many accumulator slots (see walk_vertical_u8)
   int64_t first_tile;
 };
 
@@ -170,14 +178,137 @@ __device__ __forceinline__ float2 bytes23_to_float(uint32_t w) {
   return add2_rn(m, make_float2(-8388608.0f, -8388608.0f));
 }
 
+__device__ __forceinline__ float2 fma2_rn(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vertical pass of a tile as a ROW WALK (u8 input, 32-bit aligned rows).
+//
+// The tile's output rows t = 0..th-1 read the (unclamped) source rows u in [idx[t], idx[t] + Sy).  Instead of gathering the
+// Sy taps of every output row (each source row is then fetched and converted ~Sy/scale times), the walk visits the source
+// rows umin..umax ONCE, in ascending order, and adds each of them into the output rows that are open at that row: output
+// row t lives in accumulator slot t % W, where W (host-checked) guarantees that rows t and t + W are never open together.
+// Ascending u is ascending k for every t, so the accumulation order of the reference (k = 0..Sy-1) is kept; clamped border
+// rows are simply visited once per unclamped u.
+//
+// The product is formed WITHOUT converting the byte: m = 2^23 + b (a PRMT), then fma(m, c, -2^23 c) = RN(b * c) exactly
+// (the FMA is exact before its single rounding and 2^23 c is a power-of-two multiple of c), i.e. the reference's separately
+// rounded mul; the sum is a separate add.rn -- two roundings, like SSE2 mulps + addps.  (fma followed by add cannot be
+// contracted; mul.rn.f32x2 + add.rn.f32x2 was being contracted into FFMA2 by ptxas 12.9.)
+struct WalkTables {
+  float4 ent[kWalkMax][kWalkSlots];     // (c, c, -2^23 c, -2^23 c) of the tap that slot s takes from step j, or zeros
+  int32_t row[kWalkMax];                // absolute clamped source row of step j
+  uint32_t fin[kWalkMax];               // byte s = output row (tile-local) that slot s completes at step j, 0xFF = none
+};
+
+__device__ __forceinline__ void walk_vertical_u8(const uint8_t *__restrict__ in8, int64_t pitch, int words, int row_elems,
+                                                 int th, int Sy, int W, const int32_t *__restrict__ idx_y,
+                                                 const float *__restrict__ coef_y, int oy0, int by, int ey,
+                                                 float *__restrict__ tmp, WalkTables *__restrict__ wt) {
+  const int ia = idx_y[oy0], ib = idx_y[oy0 + th - 1];
+  const int umin = min(ia, ib), J = max(ia, ib) + Sy - umin;
+  for (int e = threadIdx.x; e < J * kWalkSlots; e += blockDim.x) (&wt->ent[0][0])[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = threadIdx.x; j < J; j += blockDim.x) { wt->row[j] = by + min(max(umin + j, 0), ey - 1); wt->fin[j] = 0xFFFFFFFFu; }
+  __syncthreads();
+  for (int e = threadIdx.x; e < th * Sy; e += blockDim.x) {
+    const int t = e / Sy, k = e - t * Sy;
+    const int j = idx_y[oy0 + t] + k - umin, s = t % W;
+    const float c = coef_y[(int64_t)(oy0 + t) * Sy + k];
+    const float d = mul_rn(c, -8388608.0f);
+    wt->ent[j][s] = make_float4(c, c, d, d);
+    if (k == Sy - 1) reinterpret_cast<uint8_t *>(&wt->fin[j])[s] = (uint8_t)t;
+  }
+  __syncthreads();
+  constexpr int G = 4, NW = kWalkWords;
+  for (int jw0 = threadIdx.x; jw0 < words; jw0 += blockDim.x * NW) {
+    const uint8_t *colp[NW];
+    bool okw[NW];
+#pragma unroll
+    for (int q = 0; q < NW; q++) { okw[q] = jw0 + q * (int)blockDim.x < words; colp[q] = in8 + 4 * (jw0 + (okw[q] ? q * (int)blockDim.x : 0)); }
+    float2 acc[kWalkSlots][NW][2];
+#pragma unroll
+    for (int s = 0; s < kWalkSlots; s++)
+#pragma unroll
+      for (int q = 0; q < NW; q++) acc[s][q][0] = acc[s][q][1] = make_float2(0.f, 0.f);
+    uint32_t wa[G][NW], wb[G][NW];
+    auto load = [&](uint32_t (&w)[G][NW], int j0) {
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        if (j0 + g < J) {
+          const int64_t ro = (int64_t)wt->row[j0 + g] * pitch;
+#pragma unroll
+          for (int q = 0; q < NW; q++) w[g][q] = ld_nc_u32(reinterpret_cast<const uint32_t *>(colp[q] + ro));
+        }
+      }
+    };
+    auto process = [&](const uint32_t (&w)[G][NW], int j0) {
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const int j = j0 + g;
+        if (j < J) {
+          float2 m[NW][2];
+#pragma unroll
+          for (int q = 0; q < NW; q++) {
+            m[q][0] = make_float2(__uint_as_float(__byte_perm(w[g][q], 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(w[g][q], 0x4B000000u, 0x7441)));
+            m[q][1] = make_float2(__uint_as_float(__byte_perm(w[g][q], 0x4B000000u, 0x7442)), __uint_as_float(__byte_perm(w[g][q], 0x4B000000u, 0x7443)));
+          }
+#pragma unroll
+          for (int s = 0; s < kWalkSlots; s++) {
+            if (s < W) {
+              const float4 e = wt->ent[j][s];
+              if (e.x != 0.0f) {
+                const float2 c2 = make_float2(e.x, e.y), d2 = make_float2(e.z, e.w);
+#pragma unroll
+                for (int q = 0; q < NW; q++) {
+                  acc[s][q][0] = add2_rn(acc[s][q][0], fma2_rn(m[q][0], c2, d2));
+                  acc[s][q][1] = add2_rn(acc[s][q][1], fma2_rn(m[q][1], c2, d2));
+                }
+              }
+            }
+          }
+          const uint32_t f = wt->fin[j];
+          if (f != 0xFFFFFFFFu) {
+#pragma unroll
+            for (int s = 0; s < kWalkSlots; s++) {
+              const uint32_t t = (f >> (8 * s)) & 0xFFu;
+              if (t != 0xFFu) {
+#pragma unroll
+                for (int q = 0; q < NW; q++) {
+                  if (okw[q])
+                    *reinterpret_cast<float4 *>(tmp + t * row_elems + 4 * (jw0 + q * (int)blockDim.x)) =
+                        make_float4(acc[s][q][0].x, acc[s][q][0].y, acc[s][q][1].x, acc[s][q][1].y);
+                  acc[s][q][0] = acc[s][q][1] = make_float2(0.f, 0.f);
+                }
+              }
+            }
+          }
+        }
+      }
+    };
+    load(wa, 0);
+    for (int j0 = 0; j0 < J; j0 += 2 * G) {
+      load(wb, j0 + G);
+      process(wa, j0);
+      load(wa, j0 + 2 * G);
+      process(wb, j0 + G);
+    }
+  }
+}
+
 // One CTA = one output tile of one sample.  smem: fp32 intermediate of the tile.
 template <typename In, typename Out>
 __global__ void __launch_bounds__(256) resample_fused_kernel(const RsDesc *__restrict__ descs, const int32_t *__restrict__ tab,
                                                              int n, int64_t total_tiles) {
-  extern __shared__ float tmp[];
+  extern __shared__ __align__(16) float tmp[];
   for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int s = find_tile_sample(descs, n, tile);
     const RsDesc &d = descs[s];
+    if (d.use_stream) continue;
     const int64_t tl = tile - d.first_tile;
     const int ty = (int)(tl / d.tiles_x), tx = (int)(tl % d.tiles_x);
     const int oy0 = ty * d.tile_h, ox0 = tx * d.tile_w;
@@ -207,7 +338,11 @@ __global__ void __launch_bounds__(256) resample_fused_kernel(const RsDesc *__res
       float *s_cy = tmp + kTmpFloats;
       int *s_row = reinterpret_cast<int *>(s_cy + kMaxTileH * kMaxSupportSmem);
       const bool tables = Sy <= kMaxSupportSmem;
-      if (tables) {
+      const bool walk = fast && d.tile_walk;
+      if (walk) {
+        walk_vertical_u8(reinterpret_cast<const uint8_t *>(in) + e0, pitch, row_elems >> 2, row_elems, th, Sy, d.walk_slots, idx_y, coef_y,
+                         oy0, by, ey, tmp, reinterpret_cast<WalkTables *>(s_cy));
+      } else if (tables) {
         for (int e = threadIdx.x; e < th * Sy; e += blockDim.x) {
           const int t = e / Sy, k = e - t * Sy;
           s_cy[e] = coef_y[(int64_t)(oy0 + t) * Sy + k];
@@ -215,7 +350,9 @@ __global__ void __launch_bounds__(256) resample_fused_kernel(const RsDesc *__res
         }
         __syncthreads();
       }
-      if (fast && tables) {
+      if (walk) {
+        // done above
+      } else if (fast && tables) {
         // stage A (fast): one thread = one 32-bit word column, all th output rows; u8 -> f32 via byte_perm,
         // packed f32x2 mul / add (two roundings, exactly like the reference's SSE mul + add)
         const int words = row_elems >> 2;
@@ -329,6 +466,233 @@ __global__ void __launch_bounds__(256) resample_fused_kernel(const RsDesc *__res
   }
 }
 
+// =============================================================================================
+// STREAMING variant of the vertical-first path (u8 input, rows 16-byte aligned) -- the C2 hot case.
+//
+// A work item is a column strip x [oy0, oy1) of one sample.  A producer warp streams the strip's source rows, ONCE and in
+// order, into a shared-memory ring with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx); eight consumer warps
+// run the row walk (see walk_vertical_u8) over the ring, keep the open output rows in registers ACROSS chunks of 8 output
+// rows (so there is no vertical overlap between chunks: every source byte is loaded and converted once per strip), park each
+// finished output row in shared memory and, every 8 rows, run the horizontal pass from there.  The producer runs ahead
+// across chunk and item boundaries, so HBM latency is hidden by the ring, not by occupancy.
+constexpr int kStRowBytes = 2048;         // ring slot = one source row segment
+constexpr int kStStages = 16;
+constexpr int kStTH = 8;                  // output rows per chunk
+constexpr int kStConsumers = 256;
+constexpr int kStThreads = kStConsumers + 32;
+constexpr int kStSmemBytes = kStTH * kStRowBytes * 4 + kStStages * kStRowBytes + kWalkMax * kWalkSlots * 16 + kWalkMax * 4 +
+                             2 * kStStages * 8;
+
+struct RsItem { int32_t sample, ox0, tw, oy0, oy1; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+               :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" :: "n"(kStConsumers) : "memory"); }
+
+struct StripGeom { int e0, bytes; };
+__device__ __forceinline__ StripGeom strip_geom(const RsDesc &d, const int32_t *idx_x, int ox0, int tw) {
+  const int ia = idx_x[ox0], ib = idx_x[ox0 + tw - 1];
+  const int bx = d.base[0], ex = d.extent[0], Sx = d.support[0];
+  const int cmin = bx + min(max(min(ia, ib), 0), ex - 1);
+  const int cmax = bx + min(max(max(ia, ib) + Sx - 1, 0), ex - 1);
+  StripGeom g;
+  g.e0 = (cmin * d.C) & ~15;
+  g.bytes = (((cmax + 1) * d.C + 15) & ~15) - g.e0;
+  return g;
+}
+
+template <typename Out>
+__global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const RsDesc *__restrict__ descs, const int32_t *__restrict__ tab,
+                                                                        const RsItem *__restrict__ items, int nitems) {
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  float *tmp2 = reinterpret_cast<float *>(st_smem);                               // [4 row pairs][RE][2]
+  uint8_t *ring = st_smem + kStTH * kStRowBytes * 4;
+  float4 (*ent)[kWalkSlots] = reinterpret_cast<float4 (*)[kWalkSlots]>(ring + kStStages * kStRowBytes);
+  uint32_t *fin = reinterpret_cast<uint32_t *>(ent + kWalkMax);
+  uint64_t *full = reinterpret_cast<uint64_t *>(fin + kWalkMax);
+  uint64_t *empty = full + kStStages;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < kStStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kStConsumers / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid >= kStConsumers) {
+    // ------------------------------------------------------------------ producer warp: one lane issues the bulk copies
+    if (tid == kStConsumers) {
+      uint32_t gs = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const RsItem it = items[item];
+        const RsDesc &d = descs[it.sample];
+        if (!d.use_stream) continue;
+        const int32_t *idx_x = tab + d.idx_off[0], *idx_y = tab + d.idx_off[1];
+        const int Sy = d.support[1], by = d.base[1], ey = d.extent[1];
+        const StripGeom g = strip_geom(d, idx_x, it.ox0, it.tw);
+        const int64_t pitch = (int64_t)d.in_w * d.C;
+        const uint8_t *src0 = static_cast<const uint8_t *>(d.in) + g.e0;
+        const int ustart = idx_y[it.oy0], uend = idx_y[it.oy1 - 1] + Sy - 1;
+        for (int u = ustart; u <= uend; u++, gs++) {
+          const uint32_t stage = gs % kStStages, par = (gs / kStStages) & 1u;
+          mbar_wait(&empty[stage], par ^ 1u);
+          mbar_expect_tx(&full[stage], (uint32_t)g.bytes);
+          const int row = by + min(max(u, 0), ey - 1);
+          bulk_g2s(ring + stage * kStRowBytes, src0 + row * pitch, (uint32_t)g.bytes, &full[stage]);
+        }
+      }
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- consumers
+  constexpr int NW = 2;
+  const int lane = tid & 31;
+  uint32_t gs = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const RsItem it = items[item];
+    const RsDesc &d = descs[it.sample];
+    if (!d.use_stream) continue;
+    const int C = d.C, Sx = d.support[0], Sy = d.support[1], W = d.walk_slots;
+    const int32_t *idx_x = tab + d.idx_off[0], *idx_y = tab + d.idx_off[1];
+    const float *coef_x = reinterpret_cast<const float *>(tab + d.coef_off[0]);
+    const float *coef_y = reinterpret_cast<const float *>(tab + d.coef_off[1]);
+    const int bx = d.base[0], ex = d.extent[0];
+    const StripGeom g = strip_geom(d, idx_x, it.ox0, it.tw);
+    const int RE = g.bytes, words = g.bytes >> 2;
+    const uint8_t *flags = d.flags_off >= 0 ? reinterpret_cast<const uint8_t *>(tab + d.flags_off) : nullptr;
+    Out *out = static_cast<Out *>(d.out);
+    const int ustart = idx_y[it.oy0];
+    bool okw[NW];
+#pragma unroll
+    for (int q = 0; q < NW; q++) okw[q] = tid + q * kStConsumers < words;
+    float2 acc[kWalkSlots][NW][2];
+#pragma unroll
+    for (int s = 0; s < kWalkSlots; s++)
+#pragma unroll
+      for (int q = 0; q < NW; q++) acc[s][q][0] = acc[s][q][1] = make_float2(0.f, 0.f);
+
+    for (int cy0 = it.oy0; cy0 < it.oy1; cy0 += kStTH) {
+      const int th = min(kStTH, it.oy1 - cy0);
+      const int cs = cy0 == it.oy0 ? ustart : idx_y[cy0 - 1] + Sy;
+      const int J = idx_y[cy0 + th - 1] + Sy - cs;
+      // ---- chunk tables
+      for (int e = tid; e < J * kWalkSlots; e += kStConsumers) (&ent[0][0])[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = tid; j < J; j += kStConsumers) fin[j] = 0xFFFFFFFFu;
+      consumer_bar();
+      for (int e = tid; e < (th + kWalkSlots) * Sy; e += kStConsumers) {
+        const int tl = e / Sy, k = e - tl * Sy, t = cy0 + tl;
+        if (t < it.oy1) {
+          const int j = idx_y[t] + k - cs;
+          if (j >= 0 && j < J) {
+            const float c = coef_y[(int64_t)t * Sy + k];
+            const float dd = mul_rn(c, -8388608.0f);
+            ent[j][t % W] = make_float4(c, c, dd, dd);
+            if (k == Sy - 1) reinterpret_cast<uint8_t *>(&fin[j])[t % W] = (uint8_t)tl;
+          }
+        }
+      }
+      consumer_bar();
+      // ---- stage A: row walk over the ring
+      for (int j = 0; j < J; j++, gs++) {
+        const uint32_t stage = gs % kStStages, par = (gs / kStStages) & 1u;
+        mbar_wait(&full[stage], par);
+        const uint32_t *rw = reinterpret_cast<const uint32_t *>(ring + stage * kStRowBytes);
+        uint32_t w[NW];
+#pragma unroll
+        for (int q = 0; q < NW; q++) w[q] = okw[q] ? rw[tid + q * kStConsumers] : 0u;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        float2 m[NW][2];
+#pragma unroll
+        for (int q = 0; q < NW; q++) {
+          m[q][0] = make_float2(__uint_as_float(__byte_perm(w[q], 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(w[q], 0x4B000000u, 0x7441)));
+          m[q][1] = make_float2(__uint_as_float(__byte_perm(w[q], 0x4B000000u, 0x7442)), __uint_as_float(__byte_perm(w[q], 0x4B000000u, 0x7443)));
+        }
+#pragma unroll
+        for (int s = 0; s < kWalkSlots; s++) {
+          if (s < W) {
+            const float4 e = ent[j][s];
+            if (e.x != 0.0f) {
+              const float2 c2 = make_float2(e.x, e.y), d2 = make_float2(e.z, e.w);
+#pragma unroll
+              for (int q = 0; q < NW; q++) {
+                acc[s][q][0] = add2_rn(acc[s][q][0], fma2_rn(m[q][0], c2, d2));
+                acc[s][q][1] = add2_rn(acc[s][q][1], fma2_rn(m[q][1], c2, d2));
+              }
+            }
+          }
+        }
+        const uint32_t f = fin[j];
+        if (f != 0xFFFFFFFFu) {
+#pragma unroll
+          for (int s = 0; s < kWalkSlots; s++) {
+            const uint32_t tl = (f >> (8 * s)) & 0xFFu;
+            if (tl != 0xFFu) {
+              float *dst = tmp2 + ((size_t)(tl >> 1) * RE) * 2 + (tl & 1u);
+#pragma unroll
+              for (int q = 0; q < NW; q++) {
+                if (okw[q]) {
+                  float *p4 = dst + 8 * (tid + q * kStConsumers);
+                  p4[0] = acc[s][q][0].x; p4[2] = acc[s][q][0].y; p4[4] = acc[s][q][1].x; p4[6] = acc[s][q][1].y;
+                }
+                acc[s][q][0] = acc[s][q][1] = make_float2(0.f, 0.f);
+              }
+            }
+          }
+        }
+      }
+      consumer_bar();
+      // ---- stage B: horizontal pass of the chunk's th rows, two rows per packed operation
+      const int npair = (th + 1) >> 1;
+      for (int e = tid; e < it.tw * C; e += kStConsumers) {
+        const int x = e / C, c = e - x * C;
+        const int ox = it.ox0 + x;
+        const int i0 = idx_x[ox];
+        const float *cx = coef_x + (int64_t)ox * Sx;
+        const bool he = flags ? flags[ox] != 0 : false;
+        float2 a[kStTH / 2];
+#pragma unroll
+        for (int p = 0; p < kStTH / 2; p++) a[p] = make_float2(0.f, 0.f);
+        // fma(v, c, -0) == RN(v * c), the reference's separately rounded product.  The -0 comes from the descriptor: with a
+        // literal, ptxas 12.9 rewrites the fma as a mul and then contracts mul + add into one FFMA2 (a single rounding).
+        const float2 nz = make_float2(d.neg_zero, d.neg_zero);
+        const bool interior = i0 >= 0 && i0 + Sx <= ex;
+        const int col0 = (bx + i0) * C + c - g.e0;
+        for (int k = 0; k < Sx; k++) {
+          const int col = interior ? col0 + k * C : (bx + min(max(i0 + k, 0), ex - 1)) * C + c - g.e0;
+          const float ck = cx[k];
+          const float2 c2 = make_float2(ck, ck);
+          const float2 *src = reinterpret_cast<const float2 *>(tmp2) + col;
+#pragma unroll
+          for (int p = 0; p < kStTH / 2; p++)
+            if (p < npair) a[p] = add2_rn(a[p], fma2_rn(src[(size_t)p * RE], c2, nz));    // fma(v, c, -0) == RN(v * c): the separate mul
+        }
+#pragma unroll
+        for (int p = 0; p < kStTH / 2; p++) {
+          const int t0 = 2 * p;
+          if (t0 < th) out[((int64_t)(cy0 + t0) * d.out_w + ox) * C + c] = rs_store_cvt<Out>(a[p].x, he);
+          if (t0 + 1 < th) out[((int64_t)(cy0 + t0 + 1) * d.out_w + ox) * C + c] = rs_store_cvt<Out>(a[p].y, he);
+        }
+      }
+      // no barrier here: the next chunk's table fill is separated from its walk (which overwrites tmp2) by consumer_bar()
+    }
+  }
+}
+
 }  // namespace dalib200
 
 using namespace dalib200;  // NOLINT
@@ -358,12 +722,15 @@ struct dalib200ResamplePlan {
   std::map<TableKey, AxisTableRef> cache;      // dedup of axis tables within a batch
   std::vector<int> order0;
   int64_t total_tiles = 0;
-  DescArena desc_arena, table_arena;
+  DescArena desc_arena, table_arena, item_arena;
+  std::vector<RsItem> items;                   // strips of the samples that qualify for the streaming kernel
+  std::vector<uint8_t> stream_ok;              // structural eligibility per sample (alignment is checked at launch)
+  std::vector<int> path;                       // per sample: 0 = tile kernel, 1 = streaming kernel (last launch)
   size_t tables_uploaded_words = 0;
   bool tables_dirty = true;
   cudaEvent_t uploaded = nullptr;
   bool pending = false;
-  bool smem_opted[4] = { false, false, false, false };
+  bool smem_opted[6] = { false, false, false, false, false, false };
 };
 
 namespace {
@@ -502,9 +869,14 @@ int dalib200ResamplePlanCreate(dalib200ResamplePlan **plan, int max_batch) {
 int dalib200ResamplePlanDestroy(dalib200ResamplePlan *p) {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
-  p->desc_arena.Free(); p->table_arena.Free();
+  p->desc_arena.Free(); p->table_arena.Free(); p->item_arena.Free();
   delete p;
   return DALIB200_SUCCESS;
+}
+
+int dalib200ResamplePlanGetPath(const dalib200ResamplePlan *p, int sample) {
+  if (!p || sample < 0 || sample >= p->n) return -1;
+  return p->path[sample];
 }
 
 int dalib200ResamplePlanGetOrder(const dalib200ResamplePlan *p, int sample) {
@@ -520,6 +892,9 @@ int dalib200ResamplePlanSetup(dalib200ResamplePlan *p, int n, const dalib200Resa
                "Resize: unsupported type combination in=%d out=%d (u8->u8, u8->f32, f32->f32)", in_dtype, out_dtype);
   p->descs.assign(n, RsDesc());
   p->order0.assign(n, 0);
+  p->items.clear();
+  p->stream_ok.assign(n, 0);
+  p->path.assign(n, 0);
   p->tables.clear();
   p->cache.clear();
   int64_t tiles = 0;
@@ -611,6 +986,60 @@ int dalib200ResamplePlanSetup(dalib200ResamplePlan *p, int n, const dalib200Resa
     }
     d.tile_h = th; d.tile_w = tw;
     d.tiles_x = (s.out_w + tw - 1) / tw; d.tiles_y = (s.out_h + th - 1) / th;
+    // ---- row walk of the vertical pass (u8 input, vertical first): slots W such that output rows t and t + W never overlap
+    d.walk_slots = 0;
+    if (d.vfirst && in_dtype == DALIB200_UINT8) {
+      const int Sy = d.support[1];
+      int W = 0;
+      for (int w = 1; w <= kWalkSlots && !W; w++) {
+        bool ok = true;
+        for (int t = 0; t + w < s.out_h && ok; t++) ok = std::abs(iy[t + w] - iy[t]) >= Sy;
+        if (ok) W = w;
+      }
+      int maxJ = 0;
+      for (int o = 0; o < s.out_h; o += th) {
+        int a = iy[o], b = iy[std::min(o + th, s.out_h) - 1];
+        maxJ = std::max(maxJ, std::max(a, b) + Sy - std::min(a, b));
+      }
+      d.walk_slots = W;
+      d.tile_walk = W && maxJ <= kWalkMax;
+      // ---- streaming kernel: strictly increasing source rows, strips whose row segment fits a ring slot
+      bool inc = W > 0;
+      for (int t = 0; t + 1 < s.out_h && inc; t++) inc = iy[t + 1] > iy[t];
+      if (inc) {
+        const int Sx = d.support[0];
+        auto strip_bytes = [&](int o0, int cnt) {
+          int a = ix[o0], b = ix[o0 + cnt - 1];
+          int cmin = d.base[0] + std::min(std::max(std::min(a, b), 0), d.extent[0] - 1);
+          int cmax = d.base[0] + std::min(std::max(std::max(a, b) + Sx - 1, 0), d.extent[0] - 1);
+          return (((cmax + 1) * C + 15) & ~15) - ((cmin * C) & ~15);
+        };
+        int stw = 0;
+        for (int nx = 1; nx <= s.out_w; nx++) {
+          int t = (s.out_w + nx - 1) / nx;
+          bool ok = true;
+          for (int o = 0; o < s.out_w && ok; o += t) ok = strip_bytes(o, std::min(t, s.out_w - o)) <= kStRowBytes;
+          if (ok) { stw = t; break; }
+          if (t == 1) break;
+        }
+        const int seg = 7 * kStTH;
+        bool ok = stw > 0;
+        for (int o = 0; o < s.out_h && ok; o += seg) {
+          int o1 = std::min(o + seg, s.out_h);
+          for (int c0 = o; c0 < o1 && ok; c0 += kStTH) {
+            int c1 = std::min(c0 + kStTH, o1);
+            int cs = c0 == o ? iy[o] : iy[c0 - 1] + Sy;
+            ok = iy[c1 - 1] + Sy - cs <= kWalkMax;
+          }
+        }
+        if (ok) {
+          p->stream_ok[i] = 1;
+          for (int o = 0; o < s.out_h; o += seg)
+            for (int x0 = 0; x0 < s.out_w; x0 += stw)
+              p->items.push_back(RsItem{ i, x0, std::min(stw, s.out_w - x0), o, std::min(o + seg, s.out_h) });
+        }
+      }
+    }
     tiles += (int64_t)d.tiles_x * d.tiles_y;
   }
   p->n = n; p->in_dtype = in_dtype; p->out_dtype = out_dtype; p->total_tiles = tiles;
@@ -626,11 +1055,16 @@ int dalib200ResampleLaunch(dalib200ResamplePlan *p, const void *const *in_ptrs, 
   int rc = p->desc_arena.Reserve(sizeof(RsDesc) * p->n);
   if (rc) return rc;
   auto *hd = reinterpret_cast<RsDesc *>(p->desc_arena.host);
+  int nstream = 0;
   for (int i = 0; i < p->n; i++) {
     hd[i] = p->descs[i];
     hd[i].in = in_ptrs[i];
     hd[i].out = out_ptrs[i];
+    hd[i].neg_zero = -0.0f;
     hd[i].aligned4 = (reinterpret_cast<uintptr_t>(in_ptrs[i]) % 4 == 0) && ((int64_t)hd[i].in_w * hd[i].C % 4 == 0);
+    hd[i].use_stream = p->stream_ok[i] && (reinterpret_cast<uintptr_t>(in_ptrs[i]) % 16 == 0) && ((int64_t)hd[i].in_w * hd[i].C % 16 == 0);
+    p->path[i] = hd[i].use_stream;
+    nstream += hd[i].use_stream;
   }
   rc = p->desc_arena.Upload(sizeof(RsDesc) * p->n, stream);
   if (rc) return rc;
@@ -644,10 +1078,36 @@ int dalib200ResampleLaunch(dalib200ResamplePlan *p, const void *const *in_ptrs, 
     p->uploaded_tables = p->tables;
     p->tables_dirty = false;
   }
+  if (nstream > 0) {
+    const size_t ib = p->items.size() * sizeof(RsItem);
+    rc = p->item_arena.Reserve(ib);
+    if (rc) return rc;
+    memcpy(p->item_arena.host, p->items.data(), ib);
+    rc = p->item_arena.Upload(ib, stream);
+    if (rc) return rc;
+  }
   DB_CUDA(cudaEventRecord(p->uploaded, stream));
   p->pending = true;
   const auto *dd = reinterpret_cast<const RsDesc *>(p->desc_arena.dev);
   const auto *tb = reinterpret_cast<const int32_t *>(p->table_arena.dev);
+  if (nstream > 0) {
+    const auto *di = reinterpret_cast<const RsItem *>(p->item_arena.dev);
+    const int nitems = (int)p->items.size();
+    const int sgrid = std::min(nitems, NumSMs() * 2);
+    auto slaunch = [&](auto kern, int slot) -> int {
+      if (!p->smem_opted[slot]) {
+        DB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStSmemBytes));
+        p->smem_opted[slot] = true;
+      }
+      { ProfScope ps_("resample_stream", stream); kern<<<sgrid, kStThreads, kStSmemBytes, stream>>>(dd, tb, di, nitems); }
+      return DALIB200_SUCCESS;
+    };
+    rc = p->out_dtype == DALIB200_UINT8 ? slaunch(resample_stream_kernel<uint8_t>, 4) : slaunch(resample_stream_kernel<float>, 5);
+    if (rc) return rc;
+    CountLaunch();
+    DB_CUDA(cudaGetLastError());
+    if (nstream == p->n) return DALIB200_SUCCESS;
+  }
   const int smem = kTmpFloats * sizeof(float) + kTileTableBytes;
   int grid = (int)std::min<int64_t>(p->total_tiles, (int64_t)NumSMs() * 2 * 8);
   auto launch = [&](auto kern, int slot) -> int {

@@ -117,6 +117,8 @@ int dalib200ResampleLaunch(dalib200ResamplePlan *plan, const void *const *in_ptr
                            dalib200Stream_t stream);
 /* introspection used by the tests: processing order chosen for a sample (0 = horizontal pass first) */
 int dalib200ResamplePlanGetOrder(const dalib200ResamplePlan *plan, int sample);
+/* 1 when the sample went through the streaming (TMA ring) kernel in the last launch, 0 = tile kernel, -1 = bad index. */
+int dalib200ResamplePlanGetPath(const dalib200ResamplePlan *plan, int sample);
 
 /* ------------------------------------------------------------------------------------------------
  * CropMirrorNormalize.  Replaces kernels::SliceHwc2HwcChwNormalizeGPU::Run

@@ -58,7 +58,7 @@ def fill_resample_sample(s, shape, out_hw, min_filter, mag_filter, roi):
 
 
 def resample(imgs, out_hws, min_filter=(capi.FILTER_LINEAR, 1, 0.0), mag_filter=(capi.FILTER_LINEAR, 1, 0.0), out_dtype=None,
-             rois=None, want_order=False, plan=None):
+             rois=None, want_order=False, plan=None, want_path=False):
     torch = _torch()
     n = len(imgs)
     samples = (capi.ResampleSample * n)()
@@ -75,6 +75,8 @@ def resample(imgs, out_hws, min_filter=(capi.FILTER_LINEAR, 1, 0.0), mag_filter=
     capi.check(capi.lib().dalib200ResampleLaunch(plan.handle, capi.ptr_array(din), capi.ptr_array(outs), capi.stream_handle()))
     torch.cuda.synchronize()
     res = [o.cpu().numpy() for o in outs]
+    if want_path:
+        return res, [capi.lib().dalib200ResamplePlanGetPath(plan.handle, i) for i in range(n)]
     if want_order:
         return res, [capi.lib().dalib200ResamplePlanGetOrder(plan.handle, i) for i in range(n)]
     return res

@@ -158,3 +158,39 @@ def test_resample_large_upscale_and_odd_sizes():
     got = g.resample(imgs, [c[1] for c in cases])
     for img, c, o in zip(imgs, cases, got):
         assert np.array_equal(o, po.resample(img, c[1])), c
+
+
+def test_resample_streaming_path_vs_oracle():
+    """Down-scales of 16-byte aligned rows go through the streaming (TMA ring) kernel: mixed batches, every FIR filter,
+    u8 and f32 outputs, ROIs, strips/segments/chunks with ragged tails."""
+    import gpu_helpers as g
+    rng = np.random.default_rng(77)
+    streamed = 0
+    for trial in range(10):
+        ftype = [po.F_TRIANGULAR, po.F_LINEAR, po.F_GAUSSIAN, po.F_CUBIC, po.F_LANCZOS3][trial % 5]
+        fm = (ftype, 1, 0.0)
+        fg = (po.F_LINEAR, 0, 0.0)
+        odt = np.float32 if trial % 3 == 2 else np.uint8
+        imgs, outs, rois = [], [], []
+        for it in range(10):
+            C = int(rng.choice([1, 3, 4]))
+            W = 16 * int(rng.integers(4, 60)) if it % 4 else int(rng.integers(40, 900))
+            H = int(rng.integers(60, 700))
+            img = rng.integers(0, 256, (H, W, C)).astype(np.uint8)
+            oh = int(rng.integers(3, max(4, H // 2)))
+            ow = int(rng.integers(3, max(4, W // 2)))
+            if it == 0:
+                oh, ow = 224, 224
+                img = rng.integers(0, 256, (1080, 1920, 3)).astype(np.uint8)
+            roi = None
+            if it % 3 == 1:
+                y0, y1 = sorted(rng.uniform(0, H, 2)); x0, x1 = sorted(rng.uniform(0, W, 2))
+                if y1 - y0 >= 2 * oh and x1 - x0 >= 2 * ow:
+                    roi = ((float(y0), float(x0)), (float(y1), float(x1)))
+            imgs.append(img); outs.append((oh, ow)); rois.append(roi)
+        got, paths = g.resample(imgs, outs, fm, fg, odt, rois, want_path=True)
+        streamed += sum(paths)
+        for img, hw, roi, o in zip(imgs, outs, rois, got):
+            want = po.resample(img, hw, fm, fg, odt, roi)
+            assert np.array_equal(bits(o), bits(want)), (img.shape, hw, fm, roi, odt)
+    assert streamed >= 20, streamed

@@ -517,14 +517,14 @@ __device__ __forceinline__ StripGeom strip_geom(const RsDesc &d, const int32_t *
   return g;
 }
 
-template <typename Out>
+template <typename Out, int WMAX>
 __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const RsDesc *__restrict__ descs, const int32_t *__restrict__ tab,
                                                                         const RsItem *__restrict__ items, int nitems) {
   extern __shared__ __align__(128) uint8_t st_smem[];
   float *tmp2 = reinterpret_cast<float *>(st_smem);                               // [4 row pairs][RE][2]
   uint8_t *ring = st_smem + kStTH * kStRowBytes * 4;
-  float4 (*ent)[kWalkSlots] = reinterpret_cast<float4 (*)[kWalkSlots]>(ring + kStStages * kStRowBytes);
-  uint32_t *fin = reinterpret_cast<uint32_t *>(ent + kWalkMax);
+  float2 (*ent)[kWalkSlots] = reinterpret_cast<float2 (*)[kWalkSlots]>(ring + kStStages * kStRowBytes);   // (c, -2^23 c) per step, slot
+  uint32_t *fin = reinterpret_cast<uint32_t *>(ring + kStStages * kStRowBytes + kWalkMax * kWalkSlots * 16);
   uint64_t *full = reinterpret_cast<uint64_t *>(fin + kWalkMax);
   uint64_t *empty = full + kStStages;
   const int tid = threadIdx.x;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
   if (tid >= kStConsumers) {
     // ------------------------------------------------------------------ producer warp: one lane issues the bulk copies
     if (tid == kStConsumers) {
-      uint32_t gs = 0;
+      uint32_t stage = 0, par = 1;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const RsItem it = items[item];
         const RsDesc &d = descs[it.sample];
@@ -547,12 +547,12 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
         const int64_t pitch = (int64_t)d.in_w * d.C;
         const uint8_t *src0 = static_cast<const uint8_t *>(d.in) + g.e0;
         const int ustart = idx_y[it.oy0], uend = idx_y[it.oy1 - 1] + Sy - 1;
-        for (int u = ustart; u <= uend; u++, gs++) {
-          const uint32_t stage = gs % kStStages, par = (gs / kStStages) & 1u;
-          mbar_wait(&empty[stage], par ^ 1u);
+        for (int u = ustart; u <= uend; u++) {
+          mbar_wait(&empty[stage], par);
           mbar_expect_tx(&full[stage], (uint32_t)g.bytes);
           const int row = by + min(max(u, 0), ey - 1);
           bulk_g2s(ring + stage * kStRowBytes, src0 + row * pitch, (uint32_t)g.bytes, &full[stage]);
+          if (++stage == kStStages) { stage = 0; par ^= 1u; }
         }
       }
     }
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
   // -------------------------------------------------------------------- consumers
   constexpr int NW = 2;
   const int lane = tid & 31;
-  uint32_t gs = 0;
+  uint32_t stage = 0, par = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const RsItem it = items[item];
     const RsDesc &d = descs[it.sample];
@@ -579,9 +579,9 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
     bool okw[NW];
 #pragma unroll
     for (int q = 0; q < NW; q++) okw[q] = tid + q * kStConsumers < words;
-    float2 acc[kWalkSlots][NW][2];
+    float2 acc[WMAX][NW][2];
 #pragma unroll
-    for (int s = 0; s < kWalkSlots; s++)
+    for (int s = 0; s < WMAX; s++)
 #pragma unroll
       for (int q = 0; q < NW; q++) acc[s][q][0] = acc[s][q][1] = make_float2(0.f, 0.f);
 
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
       const int cs = cy0 == it.oy0 ? ustart : idx_y[cy0 - 1] + Sy;
       const int J = idx_y[cy0 + th - 1] + Sy - cs;
       // ---- chunk tables
-      for (int e = tid; e < J * kWalkSlots; e += kStConsumers) (&ent[0][0])[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int e = tid; e < J * kWalkSlots; e += kStConsumers) (&ent[0][0])[e] = make_float2(0.f, 0.f);
       for (int j = tid; j < J; j += kStConsumers) fin[j] = 0xFFFFFFFFu;
       consumer_bar();
       for (int e = tid; e < (th + kWalkSlots) * Sy; e += kStConsumers) {
@@ -599,23 +599,35 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
           const int j = idx_y[t] + k - cs;
           if (j >= 0 && j < J) {
             const float c = coef_y[(int64_t)t * Sy + k];
-            const float dd = mul_rn(c, -8388608.0f);
-            ent[j][t % W] = make_float4(c, c, dd, dd);
+            ent[j][t % W] = make_float2(c, mul_rn(c, -8388608.0f));
             if (k == Sy - 1) reinterpret_cast<uint8_t *>(&fin[j])[t % W] = (uint8_t)tl;
           }
         }
       }
       consumer_bar();
-      // ---- stage A: row walk over the ring
-      for (int j = 0; j < J; j++, gs++) {
-        const uint32_t stage = gs % kStStages, par = (gs / kStStages) & 1u;
+      // ---- stage A: row walk over the ring.  All WMAX slots are updated unconditionally (a closed slot has c = d = 0 and
+      //      adds +0, which is exact); the only data-dependent branch is the rare "row finished" one.
+      for (int j = 0; j < J; j++) {
         mbar_wait(&full[stage], par);
         const uint32_t *rw = reinterpret_cast<const uint32_t *>(ring + stage * kStRowBytes);
         uint32_t w[NW];
 #pragma unroll
-        for (int q = 0; q < NW; q++) w[q] = okw[q] ? rw[tid + q * kStConsumers] : 0u;
+        for (int q = 0; q < NW; q++) w[q] = rw[tid + q * kStConsumers];       // the slot is kStRowBytes long: always in bounds
+        // release the slot only once the words have ARRIVED in registers (the asm consumes them): the LDS of a warp completes
+        // for all lanes together, and the slot is rewritten by the async proxy as soon as all 8 warps have arrived
+        asm volatile("fence.proxy.async.shared::cta;" :: "r"(w[0]), "r"(w[NW - 1]) : "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == kStStages) { stage = 0; par ^= 1u; }
+        float2 cd[kWalkSlots];
+        {
+          const float4 e01 = *reinterpret_cast<const float4 *>(&ent[j][0]);
+          cd[0] = make_float2(e01.x, e01.y); cd[1] = make_float2(e01.z, e01.w);
+          if (WMAX > 2) {
+            const float4 e23 = *reinterpret_cast<const float4 *>(&ent[j][2]);
+            cd[2] = make_float2(e23.x, e23.y); cd[3] = make_float2(e23.z, e23.w);
+          }
+        }
         float2 m[NW][2];
 #pragma unroll
         for (int q = 0; q < NW; q++) {
@@ -623,23 +635,18 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
           m[q][1] = make_float2(__uint_as_float(__byte_perm(w[q], 0x4B000000u, 0x7442)), __uint_as_float(__byte_perm(w[q], 0x4B000000u, 0x7443)));
         }
 #pragma unroll
-        for (int s = 0; s < kWalkSlots; s++) {
-          if (s < W) {
-            const float4 e = ent[j][s];
-            if (e.x != 0.0f) {
-              const float2 c2 = make_float2(e.x, e.y), d2 = make_float2(e.z, e.w);
+        for (int s = 0; s < WMAX; s++) {
+          const float2 c2 = make_float2(cd[s].x, cd[s].x), d2 = make_float2(cd[s].y, cd[s].y);
 #pragma unroll
-              for (int q = 0; q < NW; q++) {
-                acc[s][q][0] = add2_rn(acc[s][q][0], fma2_rn(m[q][0], c2, d2));
-                acc[s][q][1] = add2_rn(acc[s][q][1], fma2_rn(m[q][1], c2, d2));
-              }
-            }
+          for (int q = 0; q < NW; q++) {
+            acc[s][q][0] = add2_rn(acc[s][q][0], fma2_rn(m[q][0], c2, d2));
+            acc[s][q][1] = add2_rn(acc[s][q][1], fma2_rn(m[q][1], c2, d2));
           }
         }
         const uint32_t f = fin[j];
         if (f != 0xFFFFFFFFu) {
 #pragma unroll
-          for (int s = 0; s < kWalkSlots; s++) {
+          for (int s = 0; s < WMAX; s++) {
             const uint32_t tl = (f >> (8 * s)) & 0xFFu;
             if (tl != 0xFFu) {
               float *dst = tmp2 + ((size_t)(tl >> 1) * RE) * 2 + (tl & 1u);
@@ -679,7 +686,7 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
           const float2 *src = reinterpret_cast<const float2 *>(tmp2) + col;
 #pragma unroll
           for (int p = 0; p < kStTH / 2; p++)
-            if (p < npair) a[p] = add2_rn(a[p], fma2_rn(src[(size_t)p * RE], c2, nz));    // fma(v, c, -0) == RN(v * c): the separate mul
+            if (p < npair) a[p] = add2_rn(a[p], fma2_rn(src[(size_t)p * RE], c2, nz));
         }
 #pragma unroll
         for (int p = 0; p < kStTH / 2; p++) {
@@ -730,7 +737,7 @@ struct dalib200ResamplePlan {
   bool tables_dirty = true;
   cudaEvent_t uploaded = nullptr;
   bool pending = false;
-  bool smem_opted[6] = { false, false, false, false, false, false };
+  bool smem_opted[10] = { false, false, false, false, false, false, false, false, false, false };
 };
 
 namespace {
@@ -1102,7 +1109,12 @@ int dalib200ResampleLaunch(dalib200ResamplePlan *p, const void *const *in_ptrs, 
       { ProfScope ps_("resample_stream", stream); kern<<<sgrid, kStThreads, kStSmemBytes, stream>>>(dd, tb, di, nitems); }
       return DALIB200_SUCCESS;
     };
-    rc = p->out_dtype == DALIB200_UINT8 ? slaunch(resample_stream_kernel<uint8_t>, 4) : slaunch(resample_stream_kernel<float>, 5);
+    int wmax = 1;
+    for (int i = 0; i < p->n; i++) if (hd[i].use_stream) wmax = std::max(wmax, (int)hd[i].walk_slots);
+    const bool u8o = p->out_dtype == DALIB200_UINT8;
+    if (wmax <= 2)      rc = u8o ? slaunch(resample_stream_kernel<uint8_t, 2>, 4) : slaunch(resample_stream_kernel<float, 2>, 5);
+    else if (wmax == 3) rc = u8o ? slaunch(resample_stream_kernel<uint8_t, 3>, 6) : slaunch(resample_stream_kernel<float, 3>, 7);
+    else                rc = u8o ? slaunch(resample_stream_kernel<uint8_t, 4>, 8) : slaunch(resample_stream_kernel<float, 4>, 9);
     if (rc) return rc;
     CountLaunch();
     DB_CUDA(cudaGetLastError());

@@ -194,3 +194,17 @@ def test_resample_streaming_path_vs_oracle():
             want = po.resample(img, hw, fm, fg, odt, roi)
             assert np.array_equal(bits(o), bits(want)), (img.shape, hw, fm, roi, odt)
     assert streamed >= 20, streamed
+
+
+def test_resample_streaming_many_items_per_cta():
+    """More strips than resident CTAs: every CTA walks several work items back to back (ring and accumulator hand-over
+    between items), repeated to catch ordering races."""
+    import gpu_helpers as g
+    rng = np.random.default_rng(78)
+    imgs = [rng.integers(0, 256, (1080, 1920, 3)).astype(np.uint8) for _ in range(28)]
+    want = [po.resample(im, (224, 224)) for im in imgs]
+    for rep in range(3):
+        got, paths = g.resample(imgs, [(224, 224)] * len(imgs), want_path=True)
+        assert all(paths)
+        for i, (o, w) in enumerate(zip(got, want)):
+            assert np.array_equal(o, w), (rep, i, int((o != w).sum()))

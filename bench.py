@@ -305,6 +305,21 @@ def main():
         want = np.stack(ref_out)
         cpu_baseline["parity_mismatching_elements"] = int((got.view(np.uint16) != want.view(np.uint16)).sum())
         cpu_baseline["parity_elements"] = int(want.size)
+        if os.environ.get("BENCH_DEBUG_PARITY") and cpu_baseline["parity_mismatching_elements"]:
+            import cv2
+            from oracle import pyoracle as po
+            badi = [i for i in range(sample) if (got[i].view(np.uint16) != want[i].view(np.uint16)).any()]
+            print("parity debug: mismatching images", badi, file=sys.stderr)
+            for i in badi[:4]:
+                dec = cv2.imdecode(streams[i], cv2.IMREAD_COLOR)[..., ::-1]
+                gdec = pipe.decoded(i).cpu().numpy()
+                r1 = po.ref_resample(np.ascontiguousarray(dec), (OUT, OUT)); r2 = po.resample(np.ascontiguousarray(dec), (OUT, OUT))
+                gres = pipe.resized(i).cpu().numpy()
+                print("  img", i, "decode diff", int((gdec != dec).sum()), "resize gpu-vs-ref(1 thread)", int((gres != r1).sum()),
+                      "ref-vs-port", int((r1 != r2).sum()), file=sys.stderr)
+                _, _, again = cpu_reference_pipeline([streams[i]], 1, [mirror[i]])
+                print("  threaded ref vs single-thread ref", int((again[0].view(np.uint16) != want[i].view(np.uint16)).sum()),
+                      "gpu vs single-thread ref", int((again[0].view(np.uint16) != got[i].view(np.uint16)).sum()), file=sys.stderr)
 
     if rank == 0:
         line = {"metric": "images/sec decode+resize+CMN (batch 256, 1080p JPEG)", "value": value, "unit": "images/s", "n_gpus": world,

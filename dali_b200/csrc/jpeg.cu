@@ -29,23 +29,27 @@
 
 namespace dalib200 {
 
-constexpr int kLutBits = 10;                 // first-level Huffman lookup width
-constexpr int kLutSize = 1 << kLutBits;
+constexpr int kDcLutBits = 9, kAcLutBits = 11;   // first-level Huffman lookup widths (std DC codes are <= 9 bits)
+constexpr int kDcLutSize = 1 << kDcLutBits, kAcLutSize = 1 << kAcLutBits;
+constexpr int kLutWords = 2 * kDcLutSize + 2 * kAcLutSize;          // DC0 DC1 AC0 AC1 back to back: 20 KB
 constexpr int kSyncThreads = 128;            // subsequences per synchronisation block
 constexpr int kChunkBytes = 4096;            // un-stuffing chunk
 constexpr int kMaxBlocksPerMcu = 10;
+constexpr int kMaxLog2Sub = 11;              // largest subsequence: 2^11 bits = 256 bytes
 
-// One Huffman table as the device sees it.
-struct HuffTable {
-  uint16_t lut[kLutSize];     // (len << 8) | symbol for codes of length <= kLutBits, 0 otherwise
-  int32_t maxcode[18];        // T.81 F.2.2.3: maxcode[l] left-aligned to 16 bits (+1), for the slow path
+// Huffman tables as the device sees them.  The first-level LUTs (one 32-bit entry per 10-bit prefix, see make_entry) are
+// copied to shared memory by every sync block; the canonical tables for longer codes stay in global memory.
+struct HuffSlow {
+  int32_t maxcode[18];        // T.81 F.2.2.3: maxcode[l] left-aligned to 16 bits (+1)
   int32_t valoff[18];         // valptr[l] - mincode[l]
   uint8_t vals[256];
 };
 
 struct TableSet {             // the 4 tables a baseline scan can reference: DC0, DC1, AC0, AC1
-  HuffTable t[4];
+  uint32_t lut[kLutWords];
+  HuffSlow slow[4];
 };
+__host__ __device__ inline int LutOffset(int t) { return t < 2 ? t * kDcLutSize : 2 * kDcLutSize + (t - 2) * kAcLutSize; }
 
 struct QuantSet { uint16_t q[4][64]; };       // natural order
 
@@ -178,106 +182,114 @@ __global__ void __launch_bounds__(256) unstuff_scatter_kernel(const uint8_t *__r
 
 // ============================================================================================
 // Huffman decoding
-struct BitReader {
-  const uint32_t *words;    // clean stream (word-swapped), 16-byte aligned, zero padded
+//
+// Bit source: the clean (un-stuffed, word-swapped) stream of a unit.  The sync-block kernels stage the CTA's 128
+// subsequences (+ one look-ahead column) into shared memory with coalesced 16-byte loads; word g of the staged run sits at
+// g ^ ((g >> lsw) & 31) so that the 32 lanes of a warp, each inside its own subsequence, always hit 32 different banks.
+struct SmemSrc {
+  const uint32_t *w; int lsw;
+  __device__ __forceinline__ uint32_t load(uint32_t g) const { return w[g ^ ((g >> lsw) & 31u)]; }
+};
+struct GlobalSrc {
+  const uint32_t *w;
+  __device__ __forceinline__ uint32_t load(uint32_t g) const { return __ldg(w + g); }
 };
 
-// 64-bit MSB-aligned window over the stream: one 32-bit load per 32 consumed bits (instead of two loads per symbol --
-// per-thread streams are 128 B apart, so every load is 32 L1 wavefronts per warp; they, not the ALU, were the bound).
+// 64-bit MSB-aligned window in two registers: `hi` always holds the next 32 bits.  The refill is written with selects:
+// the 32 lanes of a warp sit at unrelated bit positions, so a branch here would be divergent on almost every symbol.
+template <class Src>
 struct BitWindow {
-  const uint32_t *words;
-  uint64_t acc;
-  int nbits;
-  uint32_t wi;
-  __device__ __forceinline__ void init(const uint32_t *w, uint32_t p) {
-    words = w;
-    wi = p >> 5;
-    const uint32_t sh = p & 31;
-    const uint64_t two = ((uint64_t)__ldg(words + wi) << 32) | __ldg(words + wi + 1);
-    acc = two << sh;
-    nbits = 64 - (int)sh;
-    wi += 2;
+  uint32_t hi, lo, g;
+  int avail;
+  __device__ __forceinline__ void init(const Src &s, uint32_t word, uint32_t sh) {
+    const uint32_t w0 = s.load(word), w1 = s.load(word + 1);
+    hi = __funnelshift_l(w1, w0, sh);
+    lo = w1 << sh;
+    avail = 64 - (int)sh;
+    g = word + 2;
   }
-  __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(acc >> 32); }
-  __device__ __forceinline__ void consume(int n) {      // n <= 31
-    acc <<= n;
-    nbits -= n;
-    if (nbits < 32) {
-      acc |= (uint64_t)__ldg(words + wi) << (32 - nbits);
-      wi++;
-      nbits += 32;
-    }
+  __device__ __forceinline__ void consume(const Src &s, uint32_t t) {      // 1 <= t <= 31
+    hi = __funnelshift_l(lo, hi, t);
+    lo <<= t;
+    avail -= (int)t;
+    const uint32_t w = s.load(g);                  // the same word is re-read until it is taken
+    const bool need = avail < 32;                  // then 1 <= avail <= 31 and lo == 0
+    const uint32_t a = (uint32_t)avail & 31u;
+    hi |= (need ? w : 0u) >> a;
+    lo = need ? (w << ((32u - a) & 31u)) : lo;
+    avail += need ? 32 : 0;
+    g += need ? 1u : 0u;
   }
 };
-
-struct DecState { uint32_t p; int c; int z; uint32_t n; };
 
 __device__ __forceinline__ uint64_t pack_state(uint32_t p, int c, int z) {
   return (uint64_t)p | ((uint64_t)(uint32_t)c << 32) | ((uint64_t)(uint32_t)z << 40);
 }
 
-// Decodes symbols that START before end_bit.  When WRITE, stores coefficients (natural order inside the block)
-// at slot indices slot0 + n (AC) or into the compact per-block DC array; never writes at or beyond slot_limit.
-// The symbol loop is written with selects instead of branches: the 32 lanes of a warp decode unrelated bit patterns.
-template <bool WRITE>
-__device__ __forceinline__ void decode_range(const BitReader &br, const TableSet *__restrict__ ts, const JpegImage &im,
-                                             DecState &st, uint32_t end_bit, int16_t *__restrict__ coef, int16_t *__restrict__ dcv,
-                                             int64_t slot0, int64_t slot_limit) {
-  uint32_t p = st.p; int c = st.c, z = st.z; uint32_t n = st.n;
-  const int bpm = im.bpm;
-  if (p >= end_bit) return;
-  BitWindow bw;
-  bw.init(br.words, p);
-  while (p < end_bit) {
-    if (WRITE && slot0 + n >= slot_limit) break;
-    const bool is_dc = z == 0;
-    const HuffTable &ht = ts->t[is_dc ? im.blk_dc[c] : im.blk_ac[c]];
-    const uint32_t w = bw.peek32();
-    const uint32_t e = ht.lut[w >> (32 - kLutBits)];
-    uint32_t len = e >> 8, sym = e & 0xFF;
-    if (len == 0) {                                  // slow path: codes longer than kLutBits (rare)
-      const int32_t code16 = (int32_t)(w >> 16);
-      len = kLutBits + 1;
-      while (len <= 16 && code16 >= ht.maxcode[len]) len++;
-      if (len > 16) { len = 16; sym = 0; }
-      else sym = ht.vals[(ht.valoff[len] + (code16 >> (16 - len))) & 0xFF];
-    }
-    const int s = sym & 15;
-    const int r = is_dc ? 0 : (int)(sym >> 4);
-    // magnitude bits (EXTEND, T.81 F.2.2.1); s == 0 -> v = 0
-    const int bits = (int)((w << len) >> 1 >> (31 - s));          // (w << len) >> (32 - s) without an undefined shift for s == 0
-    const int v = s ? (bits < (1 << (s - 1)) ? bits - (1 << s) + 1 : bits) : 0;
-    // slots skipped before the coefficient: run (AC), 16 (ZRL) or the rest of the block (EOB)
-    const bool eob_like = !is_dc && s == 0;
-    int adv = eob_like ? (r == 15 ? 16 : 64 - z) : r;
-    int zz = z + adv;
-    if (!eob_like && zz > 63) { adv -= zz - 63; zz = 63; }        // corrupt / speculative: stay inside the block
-    n += adv;
-    const int used = (int)len + s;
-    p += used;
-    bw.consume(used);
-    if (!eob_like) {
-      if (WRITE && slot0 + n < slot_limit) {
-        const int64_t slot = slot0 + n;
-        if (is_dc) dcv[slot >> 6] = (int16_t)v;
-        else if (v != 0 || true) coef[(slot & ~(int64_t)63) | c_zigzag[zz]] = (int16_t)v;
-      }
-      zz++; n++;
-    }
-    z = zz;
-    if (z >= 64) { z = 0; c = c + 1 == bpm ? 0 : c + 1; }
-  }
-  st.p = p; st.c = c; st.z = z; st.n = n;
+// LUT entry (host: MakeLutEntry): [5:0] bits consumed (code + magnitude), [11:8] magnitude size s, [16:12] code length,
+// [26:20] zig-zag advance (run + 1; 16 for ZRL; 64 for EOB; 1 for DC).  0 = code longer than the first-level width.
+__device__ __forceinline__ uint32_t make_entry(uint32_t len, uint32_t sym, bool is_dc) {
+  const uint32_t s = sym & 15u, r = sym >> 4;
+  const uint32_t adv = is_dc ? 1u : (s == 0 ? (r == 15u ? 16u : 64u) : r + 1u);
+  return (len + s) | (s << 8) | (len << 12) | (adv << 20);
 }
 
-__device__ __forceinline__ int find_image_by_block(const JpegImage *im, int n, int blk) {
-  int lo = 0, hi = n - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (im[mid].block_begin <= blk) lo = mid; else hi = mid - 1;
-  }
-  return lo;
+// codes longer than the first-level LUT (std tables: AC codes of 12..16 bits, < 1 % of the symbols): canonical search,
+// T.81 F.2.2.3.  `toff` = LUT word offset of the table, which identifies it.
+__device__ __noinline__ uint32_t slow_symbol(const HuffSlow *__restrict__ slow, uint32_t toff, uint32_t hi, bool is_dc) {
+  const int tbl = toff < 2u * kDcLutSize ? (int)(toff / kDcLutSize) : 2 + (int)((toff - 2u * kDcLutSize) / kAcLutSize);
+  const HuffSlow *sl = slow + tbl;
+  const int32_t code16 = (int32_t)(hi >> 16);
+  uint32_t len = (is_dc ? kDcLutBits : kAcLutBits) + 1;
+  while (len <= 16 && code16 >= sl->maxcode[len]) len++;
+  uint32_t sym = 0;
+  if (len > 16) len = 16;                                    // corrupt / speculative: keep going deterministically
+  else sym = sl->vals[(sl->valoff[len] + (code16 >> (16 - len))) & 0xFF];
+  return make_entry(len, sym, is_dc);
 }
+
+// Decodes the symbols that START before `end` (absolute bit positions inside the unit).  State = (pos, c, z); `nb` counts
+// completed blocks.  When WRITE, stores the coefficients of block `blk0 + nb` (natural order; DC terms -- still
+// differential -- into the compact per-block array) and stops at `blk_limit`.  Branch-free apart from the loop, the rare
+// long-code path and the predicated store.
+template <bool WRITE, class Src>
+__device__ __forceinline__ void decode_span(const Src &src, BitWindow<Src> &win, const uint32_t *__restrict__ lut,
+                                            const HuffSlow *__restrict__ slow, const uint32_t *__restrict__ s_tbl, int bpm,
+                                            uint32_t &pos, uint32_t end, int &c, int &z, uint32_t &nb,
+                                            int16_t *__restrict__ coef, int16_t *__restrict__ dcv, const uint8_t *__restrict__ s_zig,
+                                            uint32_t blk0, uint32_t blk_limit) {
+  uint32_t tb12 = s_tbl[c];                                   // dc table offset | ac table offset << 16 (in LUT words)
+  while (pos < end) {
+    if (WRITE && blk0 + nb >= blk_limit) break;
+    const bool is_dc = z == 0;
+    const uint32_t toff = is_dc ? (tb12 & 0xFFFFu) : (tb12 >> 16);
+    const uint32_t idx = win.hi >> (is_dc ? 32 - kDcLutBits : 32 - kAcLutBits);
+    uint32_t e = lut[toff + idx];
+    if (__builtin_expect(e == 0, 0)) e = slow_symbol(slow, toff, win.hi, is_dc);
+    const uint32_t tb = e & 63u, adv = e >> 20;
+    if (WRITE) {
+      const uint32_t s = (e >> 8) & 15u;
+      if (s) {
+        const uint32_t len = (e >> 12) & 31u;
+        const uint32_t bits = ((win.hi << len) >> 1) >> (31u - s);
+        const int v = (int)bits - (((bits >> (s - 1u)) & 1u) ? 0 : (int)((1u << s) - 1u));     // EXTEND, T.81 F.2.2.1
+        const uint32_t blk = blk0 + nb;
+        if (is_dc) dcv[blk] = (int16_t)v;
+        else coef[(size_t)blk * 64 + s_zig[min((uint32_t)z + adv - 1u, 63u)]] = (int16_t)v;
+      }
+    }
+    win.consume(src, tb);
+    pos += tb;
+    z += (int)adv;
+    const bool endb = z >= 64;                                // block finished (EOB, 64th coefficient, or garbage overrun)
+    const int c1 = c + 1 == bpm ? 0 : c + 1;
+    nb += endb ? 1u : 0u;
+    c = endb ? c1 : c;
+    z = endb ? 0 : z;
+    tb12 = s_tbl[c];
+  }
+}
+
 __device__ __forceinline__ int find_unit_by_subseq(const JpegUnit *u, int ub, int ue, int j) {
   int lo = ub, hi = ue - 1;
   while (lo < hi) {
@@ -289,87 +301,188 @@ __device__ __forceinline__ int find_unit_by_subseq(const JpegUnit *u, int ub, in
 
 struct HuffCtx {
   const JpegImage *images; int nimages;
+  const int32_t *block_image;           // sync block -> image
   const JpegUnit *units;
   const uint32_t *unit_clean_len;
   const TableSet *tables;
   const uint8_t *clean;
-  uint64_t *s_state; uint32_t *s_n;
+  uint64_t *s_state; uint32_t *s_n;     // per subsequence: exit state; completed blocks (after H2: exclusive prefix per unit)
   int16_t *coef;
   int16_t *dc;             // compact DC array: one int16 per block, same block order as coef
   int log2_sub;            // log2 of the subsequence size in BITS
-  int32_t *status;         // per image: 0 ok, 1 = slot count mismatch (corrupt stream)
+  int32_t *status;         // per image: 0 ok, 1 = block count mismatch (corrupt stream)
 };
 
-// H1: every thread decodes its own subsequence speculatively, then the exit states are chained inside the block.
-__global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx cx) {
-  __shared__ TableSet ts;
-  const int img_i = find_image_by_block(cx.images, cx.nimages, blockIdx.x);
-  const JpegImage &im = cx.images[img_i];
+__device__ __forceinline__ uint32_t tbl_word(const JpegImage &im, int b) {
+  return (uint32_t)LutOffset(im.blk_dc[b]) | ((uint32_t)LutOffset(im.blk_ac[b]) << 16);
+}
+
+// Shared memory of the sync-block kernels.
+struct SyncSmem {
+  uint32_t *lut, *sw, *cnt, *tbl, *col_end, *col_p0, *list0, *list1, *nlist;
+  uint64_t *exitst;
+  const uint8_t **colptr;
+  uint8_t *zig, *col_cont;
+};
+__host__ __device__ inline size_t sync_sw_words(int log2_sub) { return (size_t)(kSyncThreads + 1) << (log2_sub - 5); }
+__host__ __device__ inline size_t sync_smem_bytes(int log2_sub) {
+  return kLutWords * 4 + sync_sw_words(log2_sub) * 4 + kSyncThreads * 8 /*exit*/ + (kSyncThreads + 1) * 8 /*colptr*/ +
+         kSyncThreads * 4 * 3 /*cnt, col_end, col_p0*/ + 2 * kSyncThreads * 8 /*lists: pos, czx*/ + 16 * 4 /*tbl*/ + 16 /*nlist*/ +
+         64 /*zig*/ + kSyncThreads /*col_cont*/;
+}
+__device__ __forceinline__ SyncSmem carve_sync_smem(uint32_t *base, int log2_sub) {
+  SyncSmem s;
+  s.lut = base;
+  s.sw = s.lut + kLutWords;
+  s.exitst = reinterpret_cast<uint64_t *>(s.sw + sync_sw_words(log2_sub));     // both word counts are multiples of 8
+  s.colptr = reinterpret_cast<const uint8_t **>(s.exitst + kSyncThreads);
+  s.cnt = reinterpret_cast<uint32_t *>(s.colptr + kSyncThreads + 1);
+  s.col_end = s.cnt + kSyncThreads;
+  s.col_p0 = s.col_end + kSyncThreads;
+  s.list0 = s.col_p0 + kSyncThreads;
+  s.list1 = s.list0 + 2 * kSyncThreads;
+  s.tbl = s.list1 + 2 * kSyncThreads;
+  s.nlist = s.tbl + 16;
+  s.zig = reinterpret_cast<uint8_t *>(s.nlist + 4);
+  s.col_cont = s.zig + 64;
+  return s;
+}
+
+// Common prologue of H1 / H3: tables into shared memory, per-thread subsequence geometry, cooperative staging of the stream.
+struct SubGeom { bool valid; int ui; uint32_t jl, nsub_eff, clean_bits; int64_t g; };
+
+__device__ __forceinline__ SubGeom sync_block_prologue(const HuffCtx &cx, const JpegImage &im, const SyncSmem &sm) {
+  const int lsw = cx.log2_sub - 5;
   {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(cx.tables + im.table_set);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&ts);
-    for (int i = threadIdx.x; i < (int)(sizeof(TableSet) / 4); i += blockDim.x) dst[i] = src[i];
+    const uint4 *src = reinterpret_cast<const uint4 *>(cx.tables[im.table_set].lut);
+    uint4 *dst = reinterpret_cast<uint4 *>(sm.lut);
+    for (int i = threadIdx.x; i < kLutWords / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    if (threadIdx.x < kMaxBlocksPerMcu) sm.tbl[threadIdx.x] = tbl_word(im, threadIdx.x);
+    if (threadIdx.x < 64) sm.zig[threadIdx.x] = c_zigzag[threadIdx.x];
   }
-  __syncthreads();
+  SubGeom sg;
   const int j = (blockIdx.x - im.block_begin) * kSyncThreads + threadIdx.x;     // image-local subsequence
-  bool valid = j < im.nsub;
-  int ui = 0; uint32_t nsub_eff = 0, jl = 0, clean_bits = 0;
-  BitReader br{nullptr};
-  DecState st{0, 0, 0, 0};
-  const uint32_t sub_bits = 1u << cx.log2_sub;
-  if (valid) {
-    ui = find_unit_by_subseq(cx.units, im.unit_begin, im.unit_end, j);
-    const JpegUnit &u = cx.units[ui];
-    clean_bits = cx.unit_clean_len[ui] * 8u;
-    nsub_eff = (clean_bits + sub_bits - 1) >> cx.log2_sub;
-    jl = (uint32_t)(j - u.first_subseq);
-    valid = jl < nsub_eff;
-    br.words = reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off);
+  sg.valid = j < im.nsub;
+  sg.ui = 0; sg.jl = 0; sg.nsub_eff = 0; sg.clean_bits = 0;
+  sg.g = (int64_t)im.subseq_begin + j;
+  const uint8_t *ptr = nullptr;
+  if (sg.valid) {
+    sg.ui = im.unit_end - im.unit_begin == 1 ? im.unit_begin : find_unit_by_subseq(cx.units, im.unit_begin, im.unit_end, j);
+    const JpegUnit &u = cx.units[sg.ui];
+    sg.clean_bits = cx.unit_clean_len[sg.ui] * 8u;
+    sg.nsub_eff = (sg.clean_bits + (1u << cx.log2_sub) - 1) >> cx.log2_sub;
+    sg.jl = (uint32_t)(j - u.first_subseq);
+    sg.valid = sg.jl < sg.nsub_eff;
+    if (sg.valid) ptr = cx.clean + u.clean_off + ((size_t)sg.jl << (cx.log2_sub - 3));
   }
-  const int64_t g = (int64_t)im.subseq_begin + j;
-  if (valid) {
-    st.p = jl << cx.log2_sub;
-    decode_range<false>(br, &ts, im, st, min((jl + 1) << cx.log2_sub, clean_bits), nullptr, nullptr, 0, 0);
-    cx.s_state[g] = pack_state(st.p, st.c, st.z);
-    cx.s_n[g] = st.n;
-  }
+  sm.colptr[threadIdx.x] = ptr;
+  sm.col_p0[threadIdx.x] = sg.jl << cx.log2_sub;
+  sm.col_end[threadIdx.x] = min((sg.jl + 1) << cx.log2_sub, sg.clean_bits);
+  sm.col_cont[threadIdx.x] = sg.valid && threadIdx.x + 1 < kSyncThreads && sg.jl + 1 < sg.nsub_eff;    // the NEXT column continues this unit
+  if (threadIdx.x == kSyncThreads - 1) sm.colptr[kSyncThreads] = ptr ? ptr + ((size_t)1 << (cx.log2_sub - 3)) : nullptr;   // look-ahead column
   __syncthreads();
-  bool active = valid;
-  int t = 1;
-  while (__syncthreads_or(active)) {
-    if (active) {
-      const uint32_t nxt = jl + t;
-      if (nxt >= nsub_eff || threadIdx.x + t >= kSyncThreads) {
-        active = false;
-      } else {
-        st.n = 0;
-        decode_range<false>(br, &ts, im, st, min((nxt + 1) << cx.log2_sub, clean_bits), nullptr, nullptr, 0, 0);
-        const uint64_t ns = pack_state(st.p, st.c, st.z);
-        // The slot count is ALWAYS written: a chain that merely converged inside this subsequence left a
-        // count computed from a wrong entry state; the last visitor of an entry is the one whose entry state
-        // is right (chains started further left arrive later), so the last write wins.
-        const bool same = cx.s_state[g + t] == ns;
-        cx.s_state[g + t] = ns; cx.s_n[g + t] = st.n;
-        if (same) active = false;
-        t++;
-      }
+  const int cpc = 1 << (cx.log2_sub - 7);                    // 16-byte chunks per column
+  for (int ch = threadIdx.x; ch < (kSyncThreads + 1) * cpc; ch += blockDim.x) {
+    const int col = ch / cpc, o = ch - col * cpc;
+    const uint8_t *p = sm.colptr[col];
+    if (p) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p) + o);
+      const uint32_t g = ((uint32_t)col << lsw) + 4u * o, x = (uint32_t)col & 31u;
+      sm.sw[(g + 0) ^ x] = v.x; sm.sw[(g + 1) ^ x] = v.y; sm.sw[(g + 2) ^ x] = v.z; sm.sw[(g + 3) ^ x] = v.w;
     }
   }
+  __syncthreads();
+  return sg;
+}
+
+// H1: every thread decodes its own subsequence speculatively (round 0) and the following one from its exit state (round 1);
+// chains that are still not synchronised are then COMPACTED: in round t >= 2 thread k takes the k-th live chain, so the
+// warps stay full while the number of live chains decays.  Chain i visits column i + t in round t, hence every column is
+// touched by at most one chain per round and the rounds are separated by barriers: the result is deterministic.
+__global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx cx) {
+  extern __shared__ __align__(16) uint32_t hsm[];
+  const SyncSmem sm = carve_sync_smem(hsm, cx.log2_sub);
+  const JpegImage &im = cx.images[cx.block_image[blockIdx.x]];
+  const SubGeom sg = sync_block_prologue(cx, im, sm);
+  const HuffSlow *slow = cx.tables[im.table_set].slow;
+  const int lsw = cx.log2_sub - 5;
+  const SmemSrc src{sm.sw, lsw};
+  BitWindow<SmemSrc> win;
+  uint32_t pos = sg.jl << cx.log2_sub, nb = 0;
+  int c = 0, z = 0;
+  if (threadIdx.x == 0) { sm.nlist[0] = 0; sm.nlist[1] = 0; }
+  // ---- round 0
+  if (sg.valid) {
+    win.init(src, (uint32_t)threadIdx.x << lsw, 0);
+    decode_span<false>(src, win, sm.lut, slow, sm.tbl, im.bpm, pos, sm.col_end[threadIdx.x], c, z, nb, nullptr, nullptr, nullptr, 0, 0);
+    sm.exitst[threadIdx.x] = pack_state(pos, c, z);
+    sm.cnt[threadIdx.x] = nb;
+  }
+  __syncthreads();
+  // ---- round 1 (own thread, the window simply continues)
+  if (sm.col_cont[threadIdx.x]) {
+    const uint32_t x = threadIdx.x + 1;
+    nb = 0;
+    decode_span<false>(src, win, sm.lut, slow, sm.tbl, im.bpm, pos, sm.col_end[x], c, z, nb, nullptr, nullptr, nullptr, 0, 0);
+    const uint64_t ns = pack_state(pos, c, z);
+    // The count is ALWAYS rewritten: a chain that merely converged inside this subsequence entered it in a different state
+    // than the previous visitor; chains started further left arrive later and are the better informed ones.
+    const bool same = sm.exitst[x] == ns;
+    sm.exitst[x] = ns; sm.cnt[x] = nb;
+    if (!same && sm.col_cont[x]) {
+      const uint32_t k = atomicAdd(&sm.nlist[0], 1u);
+      sm.list0[2 * k] = pos; sm.list0[2 * k + 1] = (uint32_t)c | ((uint32_t)z << 8) | ((x + 1) << 16);
+    }
+  }
+  __syncthreads();
+  // ---- rounds >= 2: compacted
+  int cur = 0;
+  for (;;) {
+    const uint32_t n = sm.nlist[cur];
+    if (n == 0) break;
+    uint32_t *lin = cur ? sm.list1 : sm.list0, *lout = cur ? sm.list0 : sm.list1;
+    __syncthreads();                                   // everybody has read the count
+    if (threadIdx.x == 0) sm.nlist[cur ^ 1] = 0;
+    __syncthreads();
+    if (threadIdx.x < n) {
+      pos = lin[2 * threadIdx.x];
+      const uint32_t czx = lin[2 * threadIdx.x + 1];
+      c = (int)(czx & 0xFF); z = (int)((czx >> 8) & 0xFF);
+      const uint32_t x = czx >> 16;
+      const uint32_t rel = pos - sm.col_p0[x];         // 0..31 bits into column x
+      win.init(src, (x << lsw) + (rel >> 5), rel & 31u);
+      nb = 0;
+      decode_span<false>(src, win, sm.lut, slow, sm.tbl, im.bpm, pos, sm.col_end[x], c, z, nb, nullptr, nullptr, nullptr, 0, 0);
+      const uint64_t ns = pack_state(pos, c, z);
+      const bool same = sm.exitst[x] == ns;
+      sm.exitst[x] = ns; sm.cnt[x] = nb;
+      if (!same && sm.col_cont[x]) {
+        const uint32_t k = atomicAdd(&sm.nlist[cur ^ 1], 1u);
+        lout[2 * k] = pos; lout[2 * k + 1] = (uint32_t)c | ((uint32_t)z << 8) | ((x + 1) << 16);
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  if (sg.valid) { cx.s_state[sg.g] = sm.exitst[threadIdx.x]; cx.s_n[sg.g] = sm.cnt[threadIdx.x]; }
 }
 
 // H2: one CTA per image.  (a) chain the states across sync-block boundaries until nothing changes,
-// (b) per-unit exclusive scan of the slot counts.
+// (b) per-unit exclusive scan of the block counts.
 __global__ void __launch_bounds__(1024) huff_sync_inter_kernel(HuffCtx cx) {
-  __shared__ TableSet ts;
+  extern __shared__ __align__(16) uint32_t lut[];          // kLutWords
+  __shared__ uint32_t s_tbl[16];
   __shared__ int changed;
   __shared__ uint32_t warp_tot[32];
   __shared__ uint32_t carry;
   const JpegImage &im = cx.images[blockIdx.x];
   {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(cx.tables + im.table_set);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&ts);
-    for (int i = threadIdx.x; i < (int)(sizeof(TableSet) / 4); i += blockDim.x) dst[i] = src[i];
+    const uint4 *src = reinterpret_cast<const uint4 *>(cx.tables[im.table_set].lut);
+    uint4 *dst = reinterpret_cast<uint4 *>(lut);
+    for (int i = threadIdx.x; i < kLutWords / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    if (threadIdx.x < kMaxBlocksPerMcu) s_tbl[threadIdx.x] = tbl_word(im, threadIdx.x);
   }
+  const HuffSlow *slow = cx.tables[im.table_set].slow;
   const uint32_t sub_bits = 1u << cx.log2_sub;
   const int nblocks = (im.nsub + kSyncThreads - 1) / kSyncThreads;
   for (int round = 0; round < nblocks + 1; round++) {
@@ -383,19 +496,23 @@ __global__ void __launch_bounds__(1024) huff_sync_inter_kernel(HuffCtx cx) {
       if (u.first_subseq == j0) continue;                        // a unit starts here: true entry state known
       const uint32_t clean_bits = cx.unit_clean_len[ui] * 8u;
       const uint32_t nsub_eff = (clean_bits + sub_bits - 1) >> cx.log2_sub;
-      uint32_t jl = (uint32_t)(j0 - u.first_subseq);
+      const uint32_t jl = (uint32_t)(j0 - u.first_subseq);
       if (jl >= nsub_eff) continue;
-      BitReader br{reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off)};
+      const GlobalSrc src{reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off)};
       const int64_t g0 = (int64_t)im.subseq_begin + j0;
       const uint64_t prev = cx.s_state[g0 - 1];
-      DecState st{(uint32_t)prev, (int)((prev >> 32) & 0xFF), (int)((prev >> 40) & 0xFF), 0};
+      uint32_t pos = (uint32_t)prev, nb = 0;
+      int c = (int)((prev >> 32) & 0xFF), z = (int)((prev >> 40) & 0xFF);
+      BitWindow<GlobalSrc> win;
+      win.init(src, pos >> 5, pos & 31u);
       bool synced = false;
-      for (int k = 0; k < kSyncThreads && jl + k < nsub_eff; k++) {
-        st.n = 0;
-        decode_range<false>(br, &ts, im, st, min((jl + k + 1) << cx.log2_sub, clean_bits), nullptr, nullptr, 0, 0);
-        const uint64_t ns = pack_state(st.p, st.c, st.z);
+      for (uint32_t k = 0; k < (uint32_t)kSyncThreads && jl + k < nsub_eff; k++) {
+        nb = 0;
+        decode_span<false>(src, win, lut, slow, s_tbl, im.bpm, pos, min((jl + k + 1) << cx.log2_sub, clean_bits), c, z, nb,
+                           nullptr, nullptr, nullptr, 0, 0);
+        const uint64_t ns = pack_state(pos, c, z);
         const bool same = cx.s_state[g0 + k] == ns;
-        cx.s_state[g0 + k] = ns; cx.s_n[g0 + k] = st.n;     // always: see huff_sync_intra_kernel
+        cx.s_state[g0 + k] = ns; cx.s_n[g0 + k] = nb;     // always: see huff_sync_intra_kernel
         if (same) { synced = true; break; }
       }
       if (!synced) changed = 1;     // the exit state of this block moved: the next boundary must be redone
@@ -403,7 +520,7 @@ __global__ void __launch_bounds__(1024) huff_sync_inter_kernel(HuffCtx cx) {
     __syncthreads();
     if (!changed) break;
   }
-  // ---- exclusive scan of s_n per unit (in place)
+  // ---- exclusive scan of the block counts per unit (in place)
   for (int ui = im.unit_begin; ui < im.unit_end; ui++) {
     const JpegUnit &u = cx.units[ui];
     const uint32_t clean_bits = cx.unit_clean_len[ui] * 8u;
@@ -427,41 +544,34 @@ __global__ void __launch_bounds__(1024) huff_sync_inter_kernel(HuffCtx cx) {
       __syncthreads();
     }
     // trailing pad bits may decode into a few extra symbols, so only a SHORT count is an error
-    if (threadIdx.x == 0 && (int64_t)carry < u.nslots) cx.status[blockIdx.x] = 1;
+    if (threadIdx.x == 0 && (int64_t)carry * 64 < u.nslots) cx.status[blockIdx.x] = 1;
   }
 }
 
 // H3: final pass -- every subsequence is decoded from its now-correct entry state and writes coefficients.
 __global__ void __launch_bounds__(kSyncThreads) huff_write_kernel(HuffCtx cx) {
-  __shared__ TableSet ts;
-  const int img_i = find_image_by_block(cx.images, cx.nimages, blockIdx.x);
-  const JpegImage &im = cx.images[img_i];
-  {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(cx.tables + im.table_set);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&ts);
-    for (int i = threadIdx.x; i < (int)(sizeof(TableSet) / 4); i += blockDim.x) dst[i] = src[i];
+  extern __shared__ __align__(16) uint32_t hsm[];
+  const SyncSmem sm = carve_sync_smem(hsm, cx.log2_sub);
+  const JpegImage &im = cx.images[cx.block_image[blockIdx.x]];
+  const SubGeom sg = sync_block_prologue(cx, im, sm);
+  if (!sg.valid) return;
+  const JpegUnit &u = cx.units[sg.ui];
+  const HuffSlow *slow = cx.tables[im.table_set].slow;
+  const SmemSrc src{sm.sw, cx.log2_sub - 5};
+  uint32_t pos = 0, nb = 0;
+  int c = 0, z = 0;
+  if (sg.jl > 0) {
+    const uint64_t prev = cx.s_state[sg.g - 1];
+    pos = (uint32_t)prev; c = (int)((prev >> 32) & 0xFF); z = (int)((prev >> 40) & 0xFF);
   }
-  __syncthreads();
-  const int j = (blockIdx.x - im.block_begin) * kSyncThreads + threadIdx.x;
-  if (j >= im.nsub) return;
-  const int ui = find_unit_by_subseq(cx.units, im.unit_begin, im.unit_end, j);
-  const JpegUnit &u = cx.units[ui];
-  const uint32_t sub_bits = 1u << cx.log2_sub;
-  const uint32_t clean_bits = cx.unit_clean_len[ui] * 8u;
-  const uint32_t nsub_eff = (clean_bits + sub_bits - 1) >> cx.log2_sub;
-  const uint32_t jl = (uint32_t)(j - u.first_subseq);
-  if (jl >= nsub_eff) return;
-  const int64_t g = (int64_t)im.subseq_begin + j;
-  DecState st{0, 0, 0, 0};
-  if (jl > 0) {
-    const uint64_t prev = cx.s_state[g - 1];
-    st.p = (uint32_t)prev; st.c = (int)((prev >> 32) & 0xFF); st.z = (int)((prev >> 40) & 0xFF);
-  }
-  BitReader br{reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off)};
-  int16_t *coef = cx.coef + im.coef_off;
-  int16_t *dcv = cx.dc + im.coef_off / 64;
-  decode_range<true>(br, &ts, im, st, min((jl + 1) << cx.log2_sub, clean_bits), coef, dcv, u.slot_base + cx.s_n[g],
-                     u.slot_base + u.nslots);
+  const uint32_t end = min((sg.jl + 1) << cx.log2_sub, sg.clean_bits);
+  if (pos >= end) return;
+  const uint32_t rel = pos - (sg.jl << cx.log2_sub);          // 0..31 bits into this thread's column
+  BitWindow<SmemSrc> win;
+  win.init(src, ((uint32_t)threadIdx.x << (cx.log2_sub - 5)) + (rel >> 5), rel & 31u);
+  const uint32_t ublk = (uint32_t)(u.slot_base >> 6);
+  decode_span<true>(src, win, sm.lut, slow, sm.tbl, im.bpm, pos, end, c, z, nb, cx.coef + im.coef_off, cx.dc + im.coef_off / 64, sm.zig,
+                    ublk + cx.s_n[sg.g], ublk + (uint32_t)(u.nslots >> 6));
 }
 
 // ============================================================================================
@@ -966,8 +1076,16 @@ void FillInfo(const ParsedJpeg &j, dalib200JpegInfo *info) {
   info->orientation = j.orientation;
 }
 
-void BuildDeviceTable(const HostHuff &h, HuffTable &t) {
+uint32_t MakeLutEntry(int len, int sym, bool is_dc) {       // keep in sync with make_entry (device)
+  const uint32_t s = sym & 15, r = (uint32_t)sym >> 4;
+  const uint32_t adv = is_dc ? 1u : (s == 0 ? (r == 15u ? 16u : 64u) : r + 1u);
+  return ((uint32_t)len + s) | (s << 8) | ((uint32_t)len << 12) | (adv << 20);
+}
+
+void BuildDeviceTable(const HostHuff &h, uint32_t *lut, HuffSlow &t, bool is_dc) {
+  const int kLutBits = is_dc ? kDcLutBits : kAcLutBits, kLutSize = 1 << kLutBits;
   memset(&t, 0, sizeof(t));
+  memset(lut, 0, sizeof(uint32_t) * kLutSize);
   int code = 0, k = 0;
   for (int l = 1; l <= 16; l++) {
     const int mincode = code;
@@ -975,7 +1093,7 @@ void BuildDeviceTable(const HostHuff &h, HuffTable &t) {
     for (int i = 0; i < h.bits[l]; i++, k++, code++) {
       if (l <= kLutBits) {
         const int lo = code << (kLutBits - l), cnt = 1 << (kLutBits - l);
-        for (int e = 0; e < cnt && lo + e < kLutSize; e++) t.lut[lo + e] = (uint16_t)((l << 8) | h.vals[k & 255]);
+        for (int e = 0; e < cnt && lo + e < kLutSize; e++) lut[lo + e] = MakeLutEntry(l, h.vals[k & 255], is_dc);
       }
     }
     // a 16-bit window belongs to length l iff it is < maxcode[l] (exclusive bound, left-aligned) and matched
@@ -998,6 +1116,7 @@ struct dalib200JpegPlan {
   std::vector<TableSet> tables;
   std::vector<QuantSet> quants;
   std::vector<int64_t> first_quad, first_item;
+  std::vector<int32_t> block_image;         // sync block -> image
   std::vector<const uint8_t *> src_ptr;     // host pointers of the scan data (for staging)
   size_t raw_bytes = 0, clean_bytes = 0;
   uint32_t nchunks = 0;
@@ -1007,7 +1126,7 @@ struct dalib200JpegPlan {
   // staging (pinned) and device buffers -- grow only
   uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;
   uint8_t *d_stage = nullptr; size_t d_stage_cap = 0;
-  size_t desc_bytes = 0, off_images = 0, off_units = 0, off_tables = 0, off_quants = 0, off_quads = 0, off_items = 0, off_raw = 0;
+  size_t desc_bytes = 0, off_images = 0, off_units = 0, off_tables = 0, off_quants = 0, off_quads = 0, off_items = 0, off_blkimg = 0, off_raw = 0;
   uint8_t *d_clean = nullptr; size_t d_clean_cap = 0;
   uint32_t *d_chunk = nullptr; size_t d_chunk_cap = 0;
   uint32_t *d_unit_len = nullptr; size_t d_unit_cap = 0;
@@ -1017,7 +1136,7 @@ struct dalib200JpegPlan {
   uint8_t *d_planes = nullptr; size_t d_planes_cap = 0;
   int32_t *d_status = nullptr; size_t d_status_cap = 0;
   cudaEvent_t uploaded = nullptr;
-  bool pending = false, staged = false;
+  bool pending = false, staged = false, smem_opted = false;
 };
 
 namespace {
@@ -1087,7 +1206,7 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
   p->n = n; p->output_type = output_type; p->fancy = fancy_upsampling != 0;
   p->parsed.assign(n, ParsedJpeg());
   p->images.assign(n, JpegImage());
-  p->units.clear(); p->tables.clear(); p->quants.clear(); p->src_ptr.clear();
+  p->units.clear(); p->tables.clear(); p->quants.clear(); p->src_ptr.clear(); p->block_image.clear();
   p->first_quad.assign(n, 0);
   p->first_item.assign(n, 0);
   std::map<std::string, int> table_cache, quant_cache;
@@ -1095,11 +1214,12 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
   uint32_t chunks = 0;
   int64_t subseq = 0, coefs = 0, planes = 0, quads = 0, items = 0;
   int sync_blocks = 0;
-  // subsequence size: aim for >= ~300k subsequences per batch, between 32 and 256 bytes
+  // subsequence size: the longer, the fewer re-decodes until the chains lock onto the MCU phase; aim for >= ~200k
+  // subsequences per batch (a full B200 holds 300k threads), between 32 and 256 bytes
   size_t total_len = 0;
   for (int i = 0; i < n; i++) total_len += lengths[i];
-  int log2_bytes = 7;
-  while (log2_bytes > 5 && (total_len >> log2_bytes) < 300000) log2_bytes--;
+  int log2_bytes = kMaxLog2Sub - 3;
+  while (log2_bytes > 5 && (total_len >> log2_bytes) < 200000) log2_bytes--;
   p->log2_sub = log2_bytes + 3;
   const size_t sub_bytes = (size_t)1 << log2_bytes;
   for (int i = 0; i < n; i++) {
@@ -1150,7 +1270,10 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
       auto it = table_cache.find(key);
       if (it == table_cache.end()) {
         TableSet ts;
-        for (int t = 0; t < 2; t++) { BuildDeviceTable(j.dc[t], ts.t[t]); BuildDeviceTable(j.ac[t], ts.t[2 + t]); }
+        for (int t = 0; t < 2; t++) {
+          BuildDeviceTable(j.dc[t], ts.lut + LutOffset(t), ts.slow[t], true);
+          BuildDeviceTable(j.ac[t], ts.lut + LutOffset(2 + t), ts.slow[2 + t], false);
+        }
         p->tables.push_back(ts);
         it = table_cache.emplace(key, (int)p->tables.size() - 1).first;
       }
@@ -1218,6 +1341,7 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
     raw += Align(se - sb, 16);
     subseq += local_sub;
     sync_blocks += (local_sub + kSyncThreads - 1) / kSyncThreads;
+    p->block_image.resize(sync_blocks, i);
     im.coef_off = coefs;
     coefs += nmcu * bpm * 64;
     for (int c = 0; c < j.ncomp; c++) {
@@ -1244,6 +1368,7 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
   p->off_quants = off; off += Align(sizeof(QuantSet) * p->quants.size(), 16);
   p->off_quads = off; off += Align(sizeof(int64_t) * n, 16);
   p->off_items = off; off += Align(sizeof(int64_t) * n, 16);
+  p->off_blkimg = off; off += Align(sizeof(int32_t) * p->block_image.size(), 16);
   p->off_raw = off;
   p->desc_bytes = off;
   const size_t total = off + raw + 64;
@@ -1260,6 +1385,7 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
   memcpy(p->h_stage + p->off_quants, p->quants.data(), sizeof(QuantSet) * p->quants.size());
   memcpy(p->h_stage + p->off_quads, p->first_quad.data(), sizeof(int64_t) * n);
   memcpy(p->h_stage + p->off_items, p->first_item.data(), sizeof(int64_t) * n);
+  memcpy(p->h_stage + p->off_blkimg, p->block_image.data(), sizeof(int32_t) * p->block_image.size());
   // scan bytes: parallel memcpy (the host is otherwise the bottleneck at batch 256 x 0.5 MB)
   {
     std::vector<size_t> dst_off(n);
@@ -1327,7 +1453,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   if (p->n == 0) return DALIB200_SUCCESS;
   DB_CHECK_ARG(p->d_stage && p->d_stage_cap >= p->desc_bytes + p->raw_bytes, "JpegLaunch: JpegUpload has not been called for this batch");
   int rc;
-  if ((rc = GrowDevice(p->d_clean, p->d_clean_cap, p->clean_bytes + 64))) return rc;
+  if ((rc = GrowDevice(p->d_clean, p->d_clean_cap, p->clean_bytes + 1024))) return rc;   // slack: the staging reads one column ahead
   if ((rc = GrowDevice(p->d_chunk, p->d_chunk_cap, (size_t)p->nchunks + 1))) return rc;
   if ((rc = GrowDevice(p->d_unit_len, p->d_unit_cap, p->units.size() + 1))) return rc;
   {
@@ -1361,7 +1487,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   const int sms = NumSMs();
   cudaStream_t s = stream;
   // the clean stream must be zero-padded behind every unit (the bit reader peeks ahead)
-  DB_CUDA(cudaMemsetAsync(p->d_clean, 0, p->clean_bytes + 64, s));
+  DB_CUDA(cudaMemsetAsync(p->d_clean, 0, p->clean_bytes + 1024, s));
   { ProfScope ps_("jpeg_memset_coef", s); DB_CUDA(cudaMemsetAsync(p->d_coef, 0, (size_t)p->total_coefs * sizeof(int16_t), s)); }
   DB_CUDA(cudaMemsetAsync(p->d_dc, 0, (size_t)(p->total_coefs / 64) * sizeof(int16_t), s));
   DB_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * p->n, s));
@@ -1373,12 +1499,18 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
     CountLaunch(3);
   }
   HuffCtx cx;
-  cx.images = d_images; cx.nimages = p->n; cx.units = d_units; cx.unit_clean_len = p->d_unit_len; cx.tables = d_tables;
+  cx.images = d_images; cx.nimages = p->n; cx.block_image = reinterpret_cast<const int32_t *>(p->d_stage + p->off_blkimg); cx.units = d_units; cx.unit_clean_len = p->d_unit_len; cx.tables = d_tables;
   cx.clean = p->d_clean; cx.s_state = p->d_state; cx.s_n = p->d_n; cx.coef = p->d_coef; cx.dc = p->d_dc; cx.log2_sub = p->log2_sub;
   cx.status = p->d_status;
-  { ProfScope ps_("jpeg_huff_sync_intra", s); huff_sync_intra_kernel<<<p->total_blocks_sync, kSyncThreads, 0, s>>>(cx); }
-  { ProfScope ps_("jpeg_huff_sync_inter", s); huff_sync_inter_kernel<<<p->n, 1024, 0, s>>>(cx); }
-  { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_sync, kSyncThreads, 0, s>>>(cx); }
+  const size_t hsmem = sync_smem_bytes(p->log2_sub);
+  if (!p->smem_opted) {
+    DB_CUDA(cudaFuncSetAttribute(huff_sync_intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_smem_bytes(kMaxLog2Sub)));
+    DB_CUDA(cudaFuncSetAttribute(huff_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_smem_bytes(kMaxLog2Sub)));
+    p->smem_opted = true;
+  }
+  { ProfScope ps_("jpeg_huff_sync_intra", s); huff_sync_intra_kernel<<<p->total_blocks_sync, kSyncThreads, hsmem, s>>>(cx); }
+  { ProfScope ps_("jpeg_huff_sync_inter", s); huff_sync_inter_kernel<<<p->n, 1024, kLutWords * 4, s>>>(cx); }
+  { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_sync, kSyncThreads, hsmem, s>>>(cx); }
   { ProfScope ps_("jpeg_dc_scan", s); dc_scan_kernel<<<p->n, 1024, 0, s>>>(d_images, p->d_dc); }
   {
     const int64_t total_blocks = p->total_coefs / 64;

@@ -208,10 +208,10 @@ struct BitWindow {
     avail = 64 - (int)sh;
     g = word + 2;
   }
-  __device__ __forceinline__ void consume(const Src &s, uint32_t t) {      // 1 <= t <= 31
-    hi = __funnelshift_l(lo, hi, t);
-    lo <<= t;
-    avail -= (int)t;
+  __device__ __forceinline__ void consume(const Src &s, uint32_t e) {      // e & 31 = bits to drop, 1..31
+    hi = __funnelshift_l(lo, hi, e);
+    lo = __funnelshift_l(0u, lo, e);
+    avail -= (int)(e & 31u);
     const uint32_t w = s.load(g);                  // the same word is re-read until it is taken
     const bool need = avail < 32;                  // then 1 <= avail <= 31 and lo == 0
     const uint32_t a = (uint32_t)avail & 31u;
@@ -226,8 +226,10 @@ __device__ __forceinline__ uint64_t pack_state(uint32_t p, int c, int z) {
   return (uint64_t)p | ((uint64_t)(uint32_t)c << 32) | ((uint64_t)(uint32_t)z << 40);
 }
 
-// LUT entry (host: MakeLutEntry): [5:0] bits consumed (code + magnitude), [11:8] magnitude size s, [16:12] code length,
-// [26:20] zig-zag advance (run + 1; 16 for ZRL; 64 for EOB; 1 for DC).  0 = code longer than the first-level width.
+// LUT entry (host: MakeLutEntry): [4:0] bits consumed (code + magnitude, <= 31), [11:8] magnitude size s, [16:12] code
+// length, [26:20] zig-zag advance (run + 1; 16 for ZRL; 64 for EOB; 1 for DC).  0 = code longer than the first-level width.
+// The funnel shifts of the bit window take the entry register itself as the shift amount (shf.wrap masks it to 5 bits),
+// which keeps the loop-carried dependency at LDS -> SHF -> SHF -> LEA -> LDS.
 __device__ __forceinline__ uint32_t make_entry(uint32_t len, uint32_t sym, bool is_dc) {
   const uint32_t s = sym & 15u, r = sym >> 4;
   const uint32_t adv = is_dc ? 1u : (s == 0 ? (r == 15u ? 16u : 64u) : r + 1u);
@@ -261,12 +263,13 @@ __device__ __forceinline__ void decode_span(const Src &src, BitWindow<Src> &win,
   uint32_t tb12 = s_tbl[c];                                   // dc table offset | ac table offset << 16 (in LUT words)
   while (pos < end) {
     if (WRITE && blk0 + nb >= blk_limit) break;
+    // both candidate entries are fetched before z is known to be 0 or not: the (p, z) recurrences then overlap
+    const uint32_t e_ac = lut[(tb12 >> 16) + (win.hi >> (32 - kAcLutBits))];
+    const uint32_t e_dc = lut[(tb12 & 0xFFFFu) + (win.hi >> (32 - kDcLutBits))];
     const bool is_dc = z == 0;
-    const uint32_t toff = is_dc ? (tb12 & 0xFFFFu) : (tb12 >> 16);
-    const uint32_t idx = win.hi >> (is_dc ? 32 - kDcLutBits : 32 - kAcLutBits);
-    uint32_t e = lut[toff + idx];
-    if (__builtin_expect(e == 0, 0)) e = slow_symbol(slow, toff, win.hi, is_dc);
-    const uint32_t tb = e & 63u, adv = e >> 20;
+    uint32_t e = is_dc ? e_dc : e_ac;
+    if (__builtin_expect(e == 0, 0)) e = slow_symbol(slow, is_dc ? (tb12 & 0xFFFFu) : (tb12 >> 16), win.hi, is_dc);
+    const uint32_t tb = e & 31u, adv = e >> 20;
     if (WRITE) {
       const uint32_t s = (e >> 8) & 15u;
       if (s) {
@@ -278,7 +281,7 @@ __device__ __forceinline__ void decode_span(const Src &src, BitWindow<Src> &win,
         else coef[(size_t)blk * 64 + s_zig[min((uint32_t)z + adv - 1u, 63u)]] = (int16_t)v;
       }
     }
-    win.consume(src, tb);
+    win.consume(src, e);
     pos += tb;
     z += (int)adv;
     const bool endb = z >= 64;                                // block finished (EOB, 64th coefficient, or garbage overrun)
@@ -298,6 +301,8 @@ __device__ __forceinline__ int find_unit_by_subseq(const JpegUnit *u, int ub, in
   }
   return lo;
 }
+
+__device__ unsigned long long g_huff_dbg[40];    // [r] = live chains entering compacted round r (debug statistics)
 
 struct HuffCtx {
   const JpegImage *images; int nimages;
@@ -437,9 +442,16 @@ __global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx c
   __syncthreads();
   // ---- rounds >= 2: compacted
   int cur = 0;
+#ifdef DALIB200_HUFF_STATS
+  int dbg_round = 0;
+#endif
   for (;;) {
     const uint32_t n = sm.nlist[cur];
     if (n == 0) break;
+#ifdef DALIB200_HUFF_STATS
+    if (threadIdx.x == 0) { atomicAdd(&g_huff_dbg[min(dbg_round, 31)], (unsigned long long)n); atomicAdd(&g_huff_dbg[32], 1ull); }
+    dbg_round++;
+#endif
     uint32_t *lin = cur ? sm.list1 : sm.list0, *lout = cur ? sm.list0 : sm.list1;
     __syncthreads();                                   // everybody has read the count
     if (threadIdx.x == 0) sm.nlist[cur ^ 1] = 0;
@@ -1219,6 +1231,7 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
   size_t total_len = 0;
   for (int i = 0; i < n; i++) total_len += lengths[i];
   int log2_bytes = kMaxLog2Sub - 3;
+  if (const char *ev = getenv("DALIB200_JPEG_SUBSEQ_BYTES")) { int v = atoi(ev); log2_bytes = v >= 256 ? 8 : v >= 128 ? 7 : v >= 64 ? 6 : 5; }
   while (log2_bytes > 5 && (total_len >> log2_bytes) < 200000) log2_bytes--;
   p->log2_sub = log2_bytes + 3;
   const size_t sub_bytes = (size_t)1 << log2_bytes;
@@ -1424,6 +1437,12 @@ int dalib200JpegDebugGetCoefficients(dalib200JpegPlan *p, int sample, int16_t *o
   std::vector<int16_t> dcs((count + 63) / 64);
   DB_CUDA(cudaMemcpy(dcs.data(), p->d_dc + im.coef_off / 64, dcs.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
   for (size_t b = 0; b * 64 < count; b++) out[b * 64] = dcs[b];
+  return DALIB200_SUCCESS;
+}
+
+int dalib200JpegDebugHuffStats(unsigned long long *out40) {
+  DB_CUDA(cudaDeviceSynchronize());
+  DB_CUDA(cudaMemcpyFromSymbol(out40, g_huff_dbg, sizeof(unsigned long long) * 40));
   return DALIB200_SUCCESS;
 }
 

@@ -5,7 +5,10 @@ rows = list(csv.reader(open(sys.argv[1])))
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.002
 hdr = rows[1]
 iS, iN, iE, iT = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
-body = rows[2:]
+body = []
+for r in rows[2:]:
+    if len(r) < len(hdr): break
+    body.append(r)
 tot_e = sum(int(r[iE]) for r in body); tot_s = sum(int(r[iN]) for r in body)
 print("total warp-inst", tot_e, "samples", tot_s)
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]

@@ -1129,7 +1129,8 @@ struct dalib200JpegPlan {
   std::vector<QuantSet> quants;
   std::vector<int64_t> first_quad, first_item;
   std::vector<int32_t> block_image;         // sync block -> image
-  std::vector<const uint8_t *> src_ptr;     // host pointers of the scan data (for staging)
+  std::vector<const uint8_t *> src_ptr;     // host pointers of the scan data (for staging; borrowed until JpegUpload returns)
+  std::vector<size_t> stage_off;            // offset of each sample's scan bytes inside the raw staging area
   size_t raw_bytes = 0, clean_bytes = 0;
   uint32_t nchunks = 0;
   int64_t total_subseq = 0, total_coefs = 0, total_plane_bytes = 0, total_quads = 0, total_items = 0;
@@ -1147,8 +1148,9 @@ struct dalib200JpegPlan {
   int16_t *d_dc = nullptr; size_t d_dc_cap = 0;
   uint8_t *d_planes = nullptr; size_t d_planes_cap = 0;
   int32_t *d_status = nullptr; size_t d_status_cap = 0;
-  cudaEvent_t uploaded = nullptr;
-  bool pending = false, staged = false, smem_opted = false;
+  cudaEvent_t uploaded = nullptr, img_uploaded = nullptr;
+  uint8_t *h_images = nullptr; size_t h_images_cap = 0;
+  bool pending = false, img_pending = false, staged = false, smem_opted = false;
 };
 
 namespace {
@@ -1183,7 +1185,8 @@ int dalib200JpegPlanCreate(dalib200JpegPlan **plan, int max_batch) {
   DB_CHECK_ARG(plan && max_batch > 0, "JpegPlanCreate: bad arguments");
   auto *p = new dalib200JpegPlan();
   p->max_batch = max_batch;
-  if (cudaEventCreateWithFlags(&p->uploaded, cudaEventDisableTiming) != cudaSuccess) {
+  if (cudaEventCreateWithFlags(&p->uploaded, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->img_uploaded, cudaEventDisableTiming) != cudaSuccess) {
     SetLastError("JpegPlanCreate: cudaEventCreate failed"); delete p; return DALIB200_ERROR_CUDA;
   }
   *plan = p;
@@ -1193,7 +1196,9 @@ int dalib200JpegPlanCreate(dalib200JpegPlan **plan, int max_batch) {
 int dalib200JpegPlanDestroy(dalib200JpegPlan *p) {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
+  if (p->img_uploaded) { cudaEventSynchronize(p->img_uploaded); cudaEventDestroy(p->img_uploaded); }
   if (p->h_stage) cudaFreeHost(p->h_stage);
+  if (p->h_images) cudaFreeHost(p->h_images);
   void *bufs[] = { p->d_stage, p->d_clean, p->d_chunk, p->d_unit_len, p->d_state, p->d_n, p->d_coef, p->d_dc, p->d_planes, p->d_status };
   for (void *b : bufs) if (b) cudaFree(b);
   delete p;
@@ -1399,26 +1404,12 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
   memcpy(p->h_stage + p->off_quads, p->first_quad.data(), sizeof(int64_t) * n);
   memcpy(p->h_stage + p->off_items, p->first_item.data(), sizeof(int64_t) * n);
   memcpy(p->h_stage + p->off_blkimg, p->block_image.data(), sizeof(int32_t) * p->block_image.size());
-  // scan bytes: parallel memcpy (the host is otherwise the bottleneck at batch 256 x 0.5 MB)
+  // the scan bytes themselves are staged by JpegUpload, chunk by chunk, so that the H2D copy starts while later samples
+  // are still being copied into the pinned buffer
+  p->stage_off.resize(n);
   {
-    std::vector<size_t> dst_off(n);
     size_t o = 0;
-    for (int i = 0; i < n; i++) { dst_off[i] = o; o += Align(p->parsed[i].scan_end - p->parsed[i].scan_begin, 16); }
-    const int nthreads = std::max(1, std::min<int>({ (int)std::thread::hardware_concurrency(), 8, n }));
-    auto work = [&](int t) {
-      for (int i = t; i < n; i += nthreads) {
-        const size_t len = p->parsed[i].scan_end - p->parsed[i].scan_begin;
-        uint8_t *dstp = p->h_stage + p->off_raw + dst_off[i];
-        memcpy(dstp, p->src_ptr[i], len);
-        memset(dstp + len, 0, Align(len, 16) - len);
-      }
-    };
-    if (nthreads == 1 || raw < (1u << 20)) { for (int t = 0; t < nthreads; t++) work(t); }
-    else {
-      std::vector<std::thread> th;
-      for (int t = 0; t < nthreads; t++) th.emplace_back(work, t);
-      for (auto &t : th) t.join();
-    }
+    for (int i = 0; i < n; i++) { p->stage_off[i] = o; o += Align(p->parsed[i].scan_end - p->parsed[i].scan_begin, 16); }
   }
   p->staged = true;
   return DALIB200_SUCCESS;
@@ -1460,8 +1451,49 @@ int dalib200JpegUpload(dalib200JpegPlan *p, dalib200Stream_t stream) {
   const size_t total = p->desc_bytes + p->raw_bytes;
   int rc = GrowDevice(p->d_stage, p->d_stage_cap, total + 64);
   if (rc) return rc;
-  // output pointers are patched at launch: images are uploaded there.  Everything else goes now.
-  DB_CUDA(cudaMemcpyAsync(p->d_stage + p->off_units, p->h_stage + p->off_units, total - p->off_units, cudaMemcpyHostToDevice, stream));
+  // output pointers are patched at launch: images are uploaded there.  Descriptors and tables go first ...
+  DB_CUDA(cudaMemcpyAsync(p->d_stage + p->off_units, p->h_stage + p->off_units, p->off_raw - p->off_units, cudaMemcpyHostToDevice, stream));
+  // ... then the scan bytes in groups of ~8 MB: worker threads copy the samples into the pinned buffer in index order, the
+  // calling thread issues the H2D copy of a group as soon as its last sample has landed (staging and PCIe transfer overlap).
+  {
+    const int n = p->n;
+    std::vector<int> group_of(n);
+    std::vector<int> group_cnt;
+    std::vector<size_t> group_begin;
+    size_t acc = 0;
+    for (int i = 0; i < n; i++) {
+      if (group_cnt.empty() || acc >= (8u << 20)) { group_cnt.push_back(0); group_begin.push_back(p->stage_off[i]); acc = 0; }
+      group_of[i] = (int)group_cnt.size() - 1;
+      group_cnt.back()++;
+      acc += p->parsed[i].scan_end - p->parsed[i].scan_begin;
+    }
+    const int G = (int)group_cnt.size();
+    std::vector<std::atomic<int>> done(G);
+    for (auto &d : done) d.store(0);
+    std::atomic<int> next{0};
+    auto work = [&]() {
+      for (int i; (i = next.fetch_add(1)) < n;) {
+        const size_t len = p->parsed[i].scan_end - p->parsed[i].scan_begin;
+        uint8_t *dstp = p->h_stage + p->off_raw + p->stage_off[i];
+        memcpy(dstp, p->src_ptr[i], len);
+        memset(dstp + len, 0, Align(len, 16) - len);
+        done[group_of[i]].fetch_add(1, std::memory_order_release);
+      }
+    };
+    const int nthreads = std::max(1, std::min<int>({ (int)std::thread::hardware_concurrency() - 1, 12, n }));
+    std::vector<std::thread> th;
+    if (p->raw_bytes >= (1u << 20)) for (int t = 0; t < nthreads; t++) th.emplace_back(work);
+    else work();
+    cudaError_t err = cudaSuccess;
+    for (int g = 0; g < G; g++) {
+      while (done[g].load(std::memory_order_acquire) < group_cnt[g]) std::this_thread::yield();
+      const size_t b0 = group_begin[g], b1 = g + 1 < G ? group_begin[g + 1] : p->raw_bytes;
+      if (err == cudaSuccess && b1 > b0)
+        err = cudaMemcpyAsync(p->d_stage + p->off_raw + b0, p->h_stage + p->off_raw + b0, b1 - b0, cudaMemcpyHostToDevice, stream);
+    }
+    for (auto &t : th) t.join();
+    DB_CUDA(err);
+  }
   DB_CUDA(cudaEventRecord(p->uploaded, stream));
   p->pending = true;
   return DALIB200_SUCCESS;
@@ -1484,16 +1516,22 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   if ((rc = GrowDevice(p->d_dc, p->d_dc_cap, (size_t)p->total_coefs / 64 + 64))) return rc;
   if ((rc = GrowDevice(p->d_planes, p->d_planes_cap, (size_t)p->total_plane_bytes + 64))) return rc;
   if ((rc = GrowDevice(p->d_status, p->d_status_cap, (size_t)p->n + 1))) return rc;
-  // image descriptors carry the output pointers: small separate upload from a scratch area of the pinned buffer
-  // (the area [off_images, off_units) is not touched by JpegUpload)
+  // image descriptors carry the output pointers: small separate upload from their own pinned buffer (waiting on the event of
+  // the big bit-stream copy here would stall the host for the whole H2D transfer)
   {
-    // wait until a previous launch's copy of this area has completed
-    if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
-    JpegImage *hi = reinterpret_cast<JpegImage *>(p->h_stage + p->off_images);
+    if (p->img_pending) { DB_CUDA(cudaEventSynchronize(p->img_uploaded)); p->img_pending = false; }
+    const size_t need = sizeof(JpegImage) * p->n;
+    if (need > p->h_images_cap) {
+      if (p->h_images) cudaFreeHost(p->h_images);
+      p->h_images = nullptr; p->h_images_cap = 0;
+      DB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->h_images), need * 2));
+      p->h_images_cap = need * 2;
+    }
+    JpegImage *hi = reinterpret_cast<JpegImage *>(p->h_images);
     for (int i = 0; i < p->n; i++) { hi[i] = p->images[i]; hi[i].out = static_cast<uint8_t *>(out_ptrs[i]); }
-    DB_CUDA(cudaMemcpyAsync(p->d_stage + p->off_images, hi, sizeof(JpegImage) * p->n, cudaMemcpyHostToDevice, stream));
-    DB_CUDA(cudaEventRecord(p->uploaded, stream));
-    p->pending = true;
+    DB_CUDA(cudaMemcpyAsync(p->d_stage + p->off_images, hi, need, cudaMemcpyHostToDevice, stream));
+    DB_CUDA(cudaEventRecord(p->img_uploaded, stream));
+    p->img_pending = true;
   }
   const auto *d_images = reinterpret_cast<const JpegImage *>(p->d_stage + p->off_images);
   const auto *d_units = reinterpret_cast<const JpegUnit *>(p->d_stage + p->off_units);

@@ -9,6 +9,9 @@
 // The reference's prefetch queues, stream assignment and thread-pool scheduling (exec2) are out of scope
 // (SURVEY.md 2.1 row 5): the hot-path ops are GPU-only and enqueue on one stream without host syncs.
 #include "dali.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <mutex>
 
@@ -374,6 +377,8 @@ void Pipeline::Run() {
       if (e.cpu) ws.AddOutput(e.cpu.get()); else ws.AddOutput(e.gpu.get());
     }
     std::vector<OutputDesc> descs;
+    static const bool timing = getenv("DALIB200_HOST_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     try {
       if (n.op->Setup(descs, ws)) {
         DALI_ENFORCE(descs.size() == outs.size(), "Operator returned ", descs.size(), " output descriptors for ", outs.size(), " outputs");
@@ -381,7 +386,13 @@ void Pipeline::Run() {
           if (outs[i]->cpu) outs[i]->cpu->Resize(descs[i].shape, descs[i].type); else outs[i]->gpu->Resize(descs[i].shape, descs[i].type);
         }
       }
+      const auto t1 = std::chrono::steady_clock::now();
       n.op->Run(ws);
+      if (timing) {
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[host timing] %-24s setup %.3f ms  run %.3f ms\n", n.spec.SchemaName().c_str(),
+                std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+      }
     } catch (const std::exception &ex) {
       throw DALIException(make_string("Error in ", n.spec.GetArgument<std::string>("device"), " operator `", n.spec.SchemaName(),
                                       "` (", n.name, "): ", ex.what()));

@@ -71,8 +71,9 @@ int dalib200JpegGetInfo(const uint8_t *data, size_t len, dalib200JpegInfo *info)
 
 int dalib200JpegPlanCreate(dalib200JpegPlan **plan, int max_batch);
 int dalib200JpegPlanDestroy(dalib200JpegPlan *plan);
-/* Parses n encoded streams (host pointers), builds the per-sample descriptors and packs the
- * entropy-coded segments into the plan's pinned staging buffer.  Output shapes via ...GetInfo().
+/* Parses n encoded streams (host pointers) and builds the per-sample descriptors.  The streams are BORROWED until
+ * dalib200JpegUpload returns (it packs the entropy-coded segments into the plan's pinned staging buffer, in groups, and
+ * issues the H2D copy of each group as soon as it is packed).  Output shapes via ...GetInfo().
  * fancy_upsampling != 0 selects libjpeg "fancy" (triangle) chroma upsampling -- the reference CPU
  * backend's behaviour; 0 = box replication. */
 int dalib200JpegPlanSetup(dalib200JpegPlan *plan, int n, const uint8_t *const *streams, const size_t *lengths,
@@ -80,8 +81,8 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *plan, int n, const uint8_t *const *s
 int dalib200JpegPlanGetInfo(const dalib200JpegPlan *plan, int sample, dalib200JpegInfo *info);
 /* Bytes of packed entropy-coded data + tables staged for the batch (the H2D payload). */
 size_t dalib200JpegPlanStagedBytes(const dalib200JpegPlan *plan);
-/* H2D copy of the staged batch (async on stream).  Split from Launch so that a caller can time the
- * device-resident decode separately from the transfer. */
+/* Pinned staging + H2D copy of the batch (async on stream, host work overlapped with the transfer).  Split from Launch
+ * so that a caller can time the device-resident decode separately from the transfer. */
 int dalib200JpegUpload(dalib200JpegPlan *plan, dalib200Stream_t stream);
 /* Enqueues the decode of the uploaded batch; out_ptrs[i] -> device buffer H*W*C u8 (HWC). */
 int dalib200JpegLaunch(dalib200JpegPlan *plan, void *const *out_ptrs, dalib200Stream_t stream);

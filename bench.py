@@ -122,6 +122,91 @@ def cpu_reference_pipeline(streams, threads, mirror=None):
     return time.perf_counter() - t0, ("reference" if use_ref else "port"), outs
 
 
+
+def secondary_workloads(hbm_peak, flush, steps, warmup):
+    """BASELINE configs[2] (C3: warp_affine + hsv + CMN over 128 x 16 frames of 720p) and configs[3] (C4: spectrogram + mel over
+    64 clips x 10 s @ 16 kHz): device-resident throughput with CUDA events, per-kernel times from the library's own launch
+    timing, and an element-wise parity check of one frame / one clip against the CPU oracle (reported, not timed)."""
+    import torch
+    from dali_b200 import capi
+    from dali_b200.hotpath import VideoPipelineC3, AudioPipelineC4, IMAGENET_MEAN, IMAGENET_STD
+    from oracle import pyoracle as po
+    out = {}
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        capi.profiling(True); capi.profiling_collect()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush.fill_(1)
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        prof = capi.profiling_collect(); capi.profiling(False)
+        agg = {}
+        for name, ms in prof:
+            agg[name] = agg.get(name, 0.0) + ms / steps
+        return float(np.mean([a.elapsed_time(b) for a, b in ev])), agg
+
+    # ---- C3
+    nseq, flen, fh, fw = 128, 16, 720, 1280
+    nfr = nseq * flen
+    rng = np.random.default_rng(3)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    frames = torch.randint(0, 256, (nfr, fh, fw, 3), dtype=torch.uint8, device="cuda", generator=g)
+    inv, hsvp, mir = [], [], []
+    for q in range(nseq):
+        ang, sc = np.deg2rad(rng.uniform(-10, 10)), rng.uniform(0.95, 1.05)
+        cx, cy = fw / 2, fh / 2
+        a, b = sc * np.cos(ang), sc * np.sin(ang)
+        fwd = np.array([[a, -b, cx - a * cx + b * cy], [b, a, cy - b * cx - a * cy]], np.float32)      # src -> dst (inverse_map=False)
+        m = po.affine_inv(fwd)                                                                            # what the kernel consumes
+        hp = (rng.uniform(-30, 30), rng.uniform(0.7, 1.3), rng.uniform(0.8, 1.2))
+        mr = int(rng.integers(0, 2))
+        inv += [m] * flen; hsvp += [hp] * flen; mir += [mr] * flen
+    v = VideoPipelineC3(nfr, (fh, fw))
+    v.setup(inv, hsvp, mir)
+    ms, kern = timed(lambda: v.launch(frames))
+    alg = 2 * fh * fw * 3 * 2 + fh * fw * 3 * 3               # warp in+out, hsv in+out, CMN in + fp16 out  (SURVEY 8d: 19 353 600 B)
+    i = 5 * flen + 3
+    f0 = frames[i].cpu().numpy()
+    w0 = po.warp_affine(f0, inv[i], None, 1, 0.0)
+    t0 = po.hsv(w0, *hsvp[i])
+    mean, istd = po.cmn_norm_args(IMAGENET_MEAN, IMAGENET_STD)
+    c0 = po.cmn(t0, (0, 0), (fh, fw), bool(mir[i]), mean, istd, np.float16, "CHW")
+    got = v.output[i].cpu().numpy()
+    out["c3_video"] = {"workload": "C3: warp_affine(LINEAR, fill 0) -> hsv -> crop_mirror_normalize(fp16 CHW), 128 x 16 frames 720p",
+                       "value": nfr / (ms / 1e3), "unit": "frames/s", "ms_per_step": ms, "kernels_ms": kern,
+                       "op_boundary_GBps": alg * nfr / (ms / 1e3) / 1e9, "op_boundary_frac_of_hbm": alg * nfr / (ms / 1e3) / 1e9 / hbm_peak,
+                       "parity_mismatching_elements": int((got.view(np.uint16) != c0.view(np.uint16)).sum()), "parity_elements": int(c0.size)}
+    del v, frames
+    torch.cuda.empty_cache()
+    # ---- C4
+    nclip, clen = 64, 160000
+    t = np.arange(clen, dtype=np.float64) / 16000.0
+    clips = np.empty((nclip, clen), np.float32)
+    for q in range(nclip):
+        r = np.random.default_rng(400 + q)
+        sig = sum(r.uniform(0.05, 0.2) * np.sin(2 * np.pi * r.uniform(50, 7000) * t + r.uniform(0, 6.28)) for _ in range(5))
+        clips[q] = np.clip(sig + r.normal(0, 0.02, clen), -1, 1)
+    dclips = torch.from_numpy(clips).cuda()
+    au = AudioPipelineC4(nclip, clen)
+    ms, kern = timed(lambda: au.launch(dclips))
+    nwin = au.nwin
+    alg = clen * 4 + 513 * nwin * 4 + 513 * nwin * 4 + 128 * nwin * 4
+    spec0 = po.spectrogram(clips[7], 1024, 1024, 256, 2)
+    mel0 = po.mel_filter_bank(spec0, 128, 16000.0, 0.0, 8000.0)
+    gs, gm = au.spectra[7].cpu().numpy(), au.output[7].cpu().numpy()
+    out["c4_audio"] = {"workload": "C4: spectrogram(nfft 1024, window 1024, step 256, power 2) -> mel_filter_bank(128, sr 16 kHz), 64 clips x 10 s",
+                       "value": nclip * nwin / (ms / 1e3), "unit": "audio frames/s", "ms_per_step": ms, "kernels_ms": kern,
+                       "op_boundary_GBps": alg * nclip / (ms / 1e3) / 1e9, "op_boundary_frac_of_hbm": alg * nclip / (ms / 1e3) / 1e9 / hbm_peak,
+                       "stft_max_abs_err_over_max": float(np.abs(gs - spec0).max() / max(1e-30, np.abs(spec0).max())),
+                       "stft_stated_tolerance": 2e-4,
+                       "mel_max_rel_err": float(np.abs(gm - mel0).max() / max(1e-30, np.abs(mel0).max()))}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -129,6 +214,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C3 (video) and C4 (audio) secondary measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -321,6 +407,13 @@ def main():
                 print("  threaded ref vs single-thread ref", int((again[0].view(np.uint16) != want[i].view(np.uint16)).sum()),
                       "gpu vs single-thread ref", int((again[0].view(np.uint16) != got[i].view(np.uint16)).sum()), file=sys.stderr)
 
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        del api_pipe
+        try:
+            secondary = secondary_workloads(hbm_peak, flush, max(3, args.steps // 2), 2)
+        except Exception as ex:           # the headline line must not depend on the secondary workloads
+            secondary = {"error": repr(ex)}
     if rank == 0:
         line = {"metric": "images/sec decode+resize+CMN (batch 256, 1080p JPEG)", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -329,7 +422,7 @@ def main():
                                                                                    mean_jpeg_bytes=J),
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "kernels": kernels, "op_boundary_GBps": op_gbs, "op_boundary_frac_of_hbm": op_gbs / hbm_peak,
-                "wall_s_timed_region": t_wall, "checksum": chk}
+                "wall_s_timed_region": t_wall, "checksum": chk, "secondary": secondary}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

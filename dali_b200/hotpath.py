@@ -132,3 +132,103 @@ class ImagePipelineC2:
         st = (C.c_int32 * self.n)()
         capi.check(capi.lib().dalib200JpegGetStatus(self.jpeg.handle, st))
         return list(st)
+
+
+class VideoPipelineC3:
+    """warp_affine(LINEAR, fill 0, same size) -> hsv(u8) -> crop_mirror_normalize(fp16, CHW) over independent HWC frames
+    (BASELINE configs[2]; FHWC sequences are flattened to frames, frames of a sequence share their parameters)."""
+
+    def __init__(self, nframes, hw=(720, 1280), mean=IMAGENET_MEAN, std=IMAGENET_STD, device=None):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.n, self.hw = nframes, tuple(hw)
+        self.warp = capi.Plan("Warp", nframes)
+        self.hsv = capi.Plan("Pointwise", nframes)
+        self.cmn = capi.Plan("Cmn", nframes)
+        self.mean, self.inv_std = cmn_norm_args(mean, std)
+        h, w = self.hw
+        self.warped = torch.empty((nframes, h, w, 3), dtype=torch.uint8, device=self.device)
+        self.twisted = torch.empty((nframes, h, w, 3), dtype=torch.uint8, device=self.device)
+        self.output = torch.empty((nframes, 3, h, w), dtype=torch.float16, device=self.device)
+
+    def setup(self, inv_matrices, hsv_params, mirror):
+        """inv_matrices[i]: 2x3 dst->src; hsv_params[i] = (hue, saturation, value); mirror[i] in {0, 1}."""
+        lib, n = capi.lib(), self.n
+        h, w = self.hw
+        ws = (capi.WarpSample * n)()
+        cs = (capi.ColorSample * n)()
+        cm = (capi.CmnSample * n)()
+        M, T = np.empty(9, np.float32), np.empty(3, np.float32)
+        last = None
+        for i in range(n):
+            s = ws[i]
+            s.in_h, s.in_w, s.channels, s.out_h, s.out_w = h, w, 3, h, w
+            s.matrix[:] = [float(v) for v in np.asarray(inv_matrices[i], np.float32).reshape(6)]
+            hp = tuple(float(v) for v in hsv_params[i])
+            if hp != last:
+                lib.dalib200ColorTwistMatrix(C.c_float(hp[0]), C.c_float(hp[1]), C.c_float(hp[2]), C.c_float(1.0), C.c_float(1.0),
+                                             C.c_float(128.0), M.ctypes.data_as(C.c_void_p), T.ctypes.data_as(C.c_void_p))
+                last = hp
+            cs[i].num_pixels = h * w
+            cs[i].matrix[:] = [float(v) for v in M]
+            cs[i].offset[:] = [0.0, 0.0, 0.0]        # Hsv has no offset term (color_twist.h:156-170)
+            c = cm[i]
+            c.in_h, c.in_w, c.channels = h, w, 3
+            c.anchor_y, c.anchor_x, c.crop_h, c.crop_w = 0, 0, h, w
+            c.mirror = int(mirror[i])
+            for k in range(3):
+                c.mean[k] = float(self.mean[k]); c.inv_std[k] = float(self.inv_std[k]); c.fill[k] = 0.0
+            c.mean[3] = 0.0; c.inv_std[3] = 1.0; c.fill[3] = 0.0
+        capi.check(lib.dalib200WarpPlanSetup(self.warp.handle, n, ws, 1, 1, C.c_float(0.0), capi.UINT8))
+        capi.check(lib.dalib200LinearTransformSetup(self.hsv.handle, n, cs, capi.UINT8))
+        capi.check(lib.dalib200CmnPlanSetup(self.cmn.handle, n, cm, capi.FLOAT16, capi.LAYOUT_CHW, 3))
+        fb = h * w * 3
+        self._w_ptrs = capi.ptr_array([self.warped.data_ptr() + i * fb for i in range(n)])
+        self._t_ptrs = capi.ptr_array([self.twisted.data_ptr() + i * fb for i in range(n)])
+        self._o_ptrs = capi.ptr_array([self.output.data_ptr() + i * fb * 2 for i in range(n)])
+
+    def launch(self, frames, stream=None):
+        """frames: uint8 CUDA tensor [n, H, W, 3]."""
+        lib, s = capi.lib(), capi.stream_handle(stream)
+        fb = self.hw[0] * self.hw[1] * 3
+        in_ptrs = capi.ptr_array([frames.data_ptr() + i * fb for i in range(self.n)])
+        capi.check(lib.dalib200WarpLaunch(self.warp.handle, in_ptrs, self._w_ptrs, s))
+        capi.check(lib.dalib200PointwiseLaunch(self.hsv.handle, self._w_ptrs, self._t_ptrs, s))
+        capi.check(lib.dalib200CmnLaunch(self.cmn.handle, self._t_ptrs, self._o_ptrs, s))
+        return self.output
+
+
+class AudioPipelineC4:
+    """spectrogram(nfft, window_length, window_step, power 2, centred, reflect) -> mel_filter_bank (BASELINE configs[3])."""
+
+    def __init__(self, nclips, clip_len, nfft=1024, window_length=1024, window_step=256, nfilter=128, sample_rate=16000.0,
+                 freq_high=8000.0, device=None):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        lib = capi.lib()
+        self.n, self.clip_len, self.nfilter = nclips, clip_len, nfilter
+        self.spec = capi.Plan("Spectrogram", nclips)
+        self.mel = capi.Plan("Mel", nclips)
+        args = capi.SpectrogramArgs(nfft, window_length, window_step, 2, 1, 1, 1)
+        lens = (C.c_int64 * nclips)(*[clip_len] * nclips)
+        capi.check(lib.dalib200SpectrogramPlanSetup(self.spec.handle, C.byref(args), None, nclips, lens))
+        self.nbin = nfft // 2 + 1
+        self.nwin = int(lib.dalib200SpectrogramNumWindows(self.spec.handle, 0))
+        margs = capi.MelArgs(nfilter, sample_rate, 0.0, freq_high, 0, 1)
+        nw = (C.c_int64 * nclips)(*[self.nwin] * nclips)
+        capi.check(lib.dalib200MelPlanSetup(self.mel.handle, C.byref(margs), self.nbin, nclips, nw))
+        self.spectra = torch.empty((nclips, self.nbin, self.nwin), dtype=torch.float32, device=self.device)
+        self.output = torch.empty((nclips, nfilter, self.nwin), dtype=torch.float32, device=self.device)
+        sb, ob = self.nbin * self.nwin * 4, nfilter * self.nwin * 4
+        self._s_ptrs = capi.ptr_array([self.spectra.data_ptr() + i * sb for i in range(nclips)])
+        self._o_ptrs = capi.ptr_array([self.output.data_ptr() + i * ob for i in range(nclips)])
+
+    def launch(self, clips, stream=None):
+        """clips: float32 CUDA tensor [n, clip_len]."""
+        lib, s = capi.lib(), capi.stream_handle(stream)
+        in_ptrs = capi.ptr_array([clips.data_ptr() + i * self.clip_len * 4 for i in range(self.n)])
+        capi.check(lib.dalib200SpectrogramLaunch(self.spec.handle, in_ptrs, self._s_ptrs, s))
+        capi.check(lib.dalib200MelLaunch(self.mel.handle, self._s_ptrs, self._o_ptrs, s))
+        return self.output

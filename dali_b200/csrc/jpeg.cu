@@ -328,12 +328,13 @@ struct SyncSmem {
   uint64_t *exitst;
   const uint8_t **colptr;
   uint8_t *zig, *col_cont;
+  HuffSlow *slow;                // shared-memory copy of the canonical tables (the long-code path is latency critical)
 };
 __host__ __device__ inline size_t sync_sw_words(int log2_sub) { return (size_t)(kSyncThreads + 1) << (log2_sub - 5); }
 __host__ __device__ inline size_t sync_smem_bytes(int log2_sub) {
   return kLutWords * 4 + sync_sw_words(log2_sub) * 4 + kSyncThreads * 8 /*exit*/ + (kSyncThreads + 1) * 8 /*colptr*/ +
          kSyncThreads * 4 * 3 /*cnt, col_end, col_p0*/ + 2 * kSyncThreads * 8 /*lists: pos, czx*/ + 16 * 4 /*tbl*/ + 16 /*nlist*/ +
-         64 /*zig*/ + kSyncThreads /*col_cont*/;
+         64 /*zig*/ + kSyncThreads /*col_cont*/ + 4 * sizeof(HuffSlow);
 }
 __device__ __forceinline__ SyncSmem carve_sync_smem(uint32_t *base, int log2_sub) {
   SyncSmem s;
@@ -350,6 +351,7 @@ __device__ __forceinline__ SyncSmem carve_sync_smem(uint32_t *base, int log2_sub
   s.nlist = s.tbl + 16;
   s.zig = reinterpret_cast<uint8_t *>(s.nlist + 4);
   s.col_cont = s.zig + 64;
+  s.slow = reinterpret_cast<HuffSlow *>(s.col_cont + kSyncThreads);       // 4-byte aligned: all sizes above are multiples of 4
   return s;
 }
 
@@ -364,6 +366,9 @@ __device__ __forceinline__ SubGeom sync_block_prologue(const HuffCtx &cx, const 
     for (int i = threadIdx.x; i < kLutWords / 4; i += blockDim.x) dst[i] = __ldg(src + i);
     if (threadIdx.x < kMaxBlocksPerMcu) sm.tbl[threadIdx.x] = tbl_word(im, threadIdx.x);
     if (threadIdx.x < 64) sm.zig[threadIdx.x] = c_zigzag[threadIdx.x];
+    const uint32_t *ssrc = reinterpret_cast<const uint32_t *>(cx.tables[im.table_set].slow);
+    uint32_t *sdst = reinterpret_cast<uint32_t *>(sm.slow);
+    for (int i = threadIdx.x; i < (int)(4 * sizeof(HuffSlow) / 4); i += blockDim.x) sdst[i] = __ldg(ssrc + i);
   }
   SubGeom sg;
   const int j = (blockIdx.x - im.block_begin) * kSyncThreads + threadIdx.x;     // image-local subsequence
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx c
   const SyncSmem sm = carve_sync_smem(hsm, cx.log2_sub);
   const JpegImage &im = cx.images[cx.block_image[blockIdx.x]];
   const SubGeom sg = sync_block_prologue(cx, im, sm);
-  const HuffSlow *slow = cx.tables[im.table_set].slow;
+  const HuffSlow *slow = sm.slow;
   const int lsw = cx.log2_sub - 5;
   const SmemSrc src{sm.sw, lsw};
   BitWindow<SmemSrc> win;
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(kSyncThreads) huff_write_kernel(HuffCtx cx) {
   const SubGeom sg = sync_block_prologue(cx, im, sm);
   if (!sg.valid) return;
   const JpegUnit &u = cx.units[sg.ui];
-  const HuffSlow *slow = cx.tables[im.table_set].slow;
+  const HuffSlow *slow = sm.slow;
   const SmemSrc src{sm.sw, cx.log2_sub - 5};
   uint32_t pos = 0, nb = 0;
   int c = 0, z = 0;
@@ -902,7 +907,7 @@ __device__ __forceinline__ void color_row8(const JpegImage &im, const uint8_t *_
   int cb[8], cr[8];
   chroma8<HEXP, VEXP>(planes + im.plane_off[1], im.plane_w[1], dw, dh, im.fancy, x0, y, cb);
   chroma8<HEXP, VEXP>(planes + im.plane_off[2], im.plane_w[2], dw, dh, im.fancy, x0, y, cr);
-  uint8_t px[24];
+  uint32_t px[24];
   const bool bgr = im.out_type == DALIB200_BGR;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -911,7 +916,7 @@ __device__ __forceinline__ void color_row8(const JpegImage &im, const uint8_t *_
     const int r = clamp255(yy + ((91881 * crm + 32768) >> 16));
     const int g = clamp255(yy + ((-22554 * cbm + 32768 - 46802 * crm) >> 16));
     const int b = clamp255(yy + ((116130 * cbm + 32768) >> 16));
-    px[3 * k] = bgr ? b : r; px[3 * k + 1] = g; px[3 * k + 2] = bgr ? r : b;
+    px[3 * k] = (uint32_t)(bgr ? b : r); px[3 * k + 1] = (uint32_t)g; px[3 * k + 2] = (uint32_t)(bgr ? r : b);
   }
   uint8_t *o = im.out + ((int64_t)y * W + x0) * 3;
   const int nx = min(8, W - x0);
@@ -919,13 +924,73 @@ __device__ __forceinline__ void color_row8(const JpegImage &im, const uint8_t *_
     uint2 *o8 = reinterpret_cast<uint2 *>(o);
 #pragma unroll
     for (int q = 0; q < 3; q++) {
-      const uint32_t lo = px[8 * q] | (px[8 * q + 1] << 8) | (px[8 * q + 2] << 16) | ((uint32_t)px[8 * q + 3] << 24);
-      const uint32_t hi = px[8 * q + 4] | (px[8 * q + 5] << 8) | (px[8 * q + 6] << 16) | ((uint32_t)px[8 * q + 7] << 24);
+      const uint32_t lo = px[8 * q] | (px[8 * q + 1] << 8) | (px[8 * q + 2] << 16) | (px[8 * q + 3] << 24);
+      const uint32_t hi = px[8 * q + 4] | (px[8 * q + 5] << 8) | (px[8 * q + 6] << 16) | (px[8 * q + 7] << 24);
       o8[q] = make_uint2(lo, hi);
     }
   } else {
-    for (int k = 0; k < nx * 3; k++) o[k] = px[k];
+    for (int k = 0; k < 24; k++) if (k < nx * 3) o[k] = (uint8_t)px[k];
   }
+}
+
+// four ints -> four saturated bytes of one word (byte 0 = p0): two cvt.pack.sat instead of eight min/max and three merges
+__device__ __forceinline__ uint32_t pack4_sat_u8(int p0, int p1, int p2, int p3) {
+  uint32_t hi, w;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(p3), "r"(p2), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(p1), "r"(p0), "r"(hi));
+  return w;
+}
+
+// 4:2:0 fancy, interior of the image: rows y (odd) and y + 1 use the SAME two chroma rows k = y >> 1 and k + 1 with swapped
+// weights (jdsample.c h2v2_fancy_upsample: near row x 3 + far row), so one thread produces a 2 x 8 pixel patch from one pair of
+// 4-sample chroma words per component.  Requires i0 >= 1, i0 + 4 <= dw - 1, k + 1 <= dh - 1, x0 + 8 <= W, y + 1 < H.
+__device__ __forceinline__ void ycc_to_rgb_store8(const JpegImage &im, uint2 yw, const int *cb, const int *cr, int x0, int y) {
+  int px[24];
+  const bool bgr = im.out_type == DALIB200_BGR;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int yy = (int)(((k < 4 ? yw.x : yw.y) >> (8 * (k & 3))) & 0xFFu);
+    const int cbm = cb[k] - 128, crm = cr[k] - 128;
+    const int r = yy + ((91881 * crm + 32768) >> 16);                    // saturated to 0..255 by the pack below (jdcolor range_limit)
+    const int g = yy + ((-22554 * cbm + 32768 - 46802 * crm) >> 16);
+    const int b = yy + ((116130 * cbm + 32768) >> 16);
+    px[3 * k] = bgr ? b : r; px[3 * k + 1] = g; px[3 * k + 2] = bgr ? r : b;
+  }
+  uint2 *o8 = reinterpret_cast<uint2 *>(im.out + ((int64_t)y * im.width + x0) * 3);       // 8-byte aligned (checked by the caller)
+#pragma unroll
+  for (int q = 0; q < 3; q++)
+    o8[q] = make_uint2(pack4_sat_u8(px[8 * q], px[8 * q + 1], px[8 * q + 2], px[8 * q + 3]),
+                       pack4_sat_u8(px[8 * q + 4], px[8 * q + 5], px[8 * q + 6], px[8 * q + 7]));
+}
+
+__device__ __forceinline__ void chroma_patch_420(const uint8_t *__restrict__ pl, int pw, int i0, int k, int *near_out, int *far_out) {
+  const uint8_t *ra = pl + (int64_t)k * pw + i0, *rb = ra + pw;
+  const uint32_t wa = *reinterpret_cast<const uint32_t *>(ra), wb = *reinterpret_cast<const uint32_t *>(rb);
+  int a[6], b[6];
+  a[0] = ra[-1]; b[0] = rb[-1]; a[5] = ra[4]; b[5] = rb[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) { a[1 + j] = (int)((wa >> (8 * j)) & 0xFFu); b[1 + j] = (int)((wb >> (8 * j)) & 0xFFu); }
+  int cn[6], cf[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) { cn[j] = 3 * a[j] + b[j]; cf[j] = 3 * b[j] + a[j]; }     // row y: near = k; row y + 1: near = k + 1
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    near_out[2 * j] = (3 * cn[1 + j] + cn[j] + 8) >> 4;
+    near_out[2 * j + 1] = (3 * cn[1 + j] + cn[2 + j] + 7) >> 4;
+    far_out[2 * j] = (3 * cf[1 + j] + cf[j] + 8) >> 4;
+    far_out[2 * j + 1] = (3 * cf[1 + j] + cf[2 + j] + 7) >> 4;
+  }
+}
+
+__device__ __forceinline__ void color_patch_420(const JpegImage &im, const uint8_t *__restrict__ planes, int x0, int y) {
+  const int i0 = x0 >> 1, k = y >> 1;
+  int cb0[8], cb1[8], cr0[8], cr1[8];
+  chroma_patch_420(planes + im.plane_off[1], im.plane_w[1], i0, k, cb0, cb1);
+  chroma_patch_420(planes + im.plane_off[2], im.plane_w[2], i0, k, cr0, cr1);
+  const uint8_t *yp = planes + im.plane_off[0] + (int64_t)y * im.plane_w[0] + x0;
+  const uint2 y0 = *reinterpret_cast<const uint2 *>(yp), y1 = *reinterpret_cast<const uint2 *>(yp + im.plane_w[0]);
+  ycc_to_rgb_store8(im, y0, cb0, cr0, x0, y);
+  ycc_to_rgb_store8(im, y1, cb1, cr1, x0, y + 1);
 }
 
 // items: per image height * ceil(width / kColorSeg); images not eligible for the fast path own zero items
@@ -937,9 +1002,25 @@ __global__ void __launch_bounds__(128) color_fast_kernel(const JpegImage *__rest
     const JpegImage &im = images[lo];
     const int64_t li = item - first_item[lo];
     const int segs = (im.width + kColorSeg - 1) / kColorSeg;
-    const int y = (int)(li / segs), x0 = (int)(li % segs) * kColorSeg + threadIdx.x * 8;
+    const int x0 = (int)(li % segs) * kColorSeg + threadIdx.x * 8;
     if (x0 >= im.width) continue;
     const int hexp = im.hmax, vexp = im.vmax;     // chroma is 1x1 (checked on the host)
+    if (im.fast_color == 2) {
+      // 4:2:0 fancy: item 0 = row 0, item r >= 1 = rows 2r - 1 and 2r (see color_patch_420)
+      const int r = (int)(li / segs);
+      if (r == 0) { color_row8<2, 2>(im, planes, x0, 0); continue; }
+      const int y = 2 * r - 1;
+      const int dw = (im.width + 1) >> 1, dh = (im.height + 1) >> 1, i0 = x0 >> 1;
+      const bool aligned = (reinterpret_cast<uintptr_t>(im.out) & 7) == 0 && (im.width & 7) == 0;
+      if (aligned && y + 1 < im.height && (y >> 1) + 1 <= dh - 1 && i0 >= 1 && i0 + 4 <= dw - 1 && x0 + 8 <= im.width) {
+        color_patch_420(im, planes, x0, y);
+      } else {
+        color_row8<2, 2>(im, planes, x0, y);
+        if (y + 1 < im.height) color_row8<2, 2>(im, planes, x0, y + 1);
+      }
+      continue;
+    }
+    const int y = (int)(li / segs);
     if (hexp == 2 && vexp == 2) color_row8<2, 2>(im, planes, x0, y);
     else if (hexp == 1 && vexp == 1) color_row8<1, 1>(im, planes, x0, y);
     else if (hexp == 2 && vexp == 1) color_row8<2, 1>(im, planes, x0, y);
@@ -1371,7 +1452,8 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
                     ((j.hmax == 2 && j.vmax <= 2) || (j.hmax == 1 && j.vmax <= 2));
     p->first_quad[i] = quads;
     p->first_item[i] = items;
-    if (im.fast_color) items += (int64_t)((j.width + kColorSeg - 1) / kColorSeg) * j.height;
+    if (im.fast_color && p->fancy && j.hmax == 2 && j.vmax == 2 && (j.width + 1) / 2 > 2) im.fast_color = 2;    // 2-row patches
+    if (im.fast_color) items += (int64_t)((j.width + kColorSeg - 1) / kColorSeg) * (im.fast_color == 2 ? 1 + j.height / 2 : j.height);
     else quads += (int64_t)((j.width + 3) / 4) * j.height;
   }
   DB_CHECK_ARG(raw < (1ull << 32) && clean < (1ull << 32), "decoders.image: batch of encoded data exceeds 4 GiB");

@@ -22,20 +22,23 @@
 //
 // Algorithmic bytes per unit: J (encoded bytes) + H*W*3 (decoded image).
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <cstring>
 #include <map>
 #include <thread>
+
+namespace cg = cooperative_groups;
 
 namespace dalib200 {
 
 constexpr int kDcLutBits = 9, kAcLutBits = 11;   // first-level Huffman lookup widths (std DC codes are <= 9 bits)
 constexpr int kDcLutSize = 1 << kDcLutBits, kAcLutSize = 1 << kAcLutBits;
 constexpr int kLutWords = 2 * kDcLutSize + 2 * kAcLutSize;          // DC0 DC1 AC0 AC1 back to back: 20 KB
-constexpr int kSyncThreads = 128;            // subsequences per synchronisation block
+constexpr int kSyncThreads = 256;            // subsequences per synchronisation block
 constexpr int kChunkBytes = 4096;            // un-stuffing chunk
 constexpr int kMaxBlocksPerMcu = 10;
-constexpr int kMaxLog2Sub = 11;              // largest subsequence: 2^11 bits = 256 bytes
+constexpr int kMaxLog2Sub = 10;              // largest subsequence: 2^10 bits = 128 bytes
 
 // Huffman tables as the device sees them.  The first-level LUTs (one 32-bit entry per 10-bit prefix, see make_entry) are
 // copied to shared memory by every sync block; the canonical tables for longer codes stay in global memory.
@@ -263,11 +266,12 @@ __device__ __forceinline__ void decode_span(const Src &src, BitWindow<Src> &win,
   uint32_t tb12 = s_tbl[c];                                   // dc table offset | ac table offset << 16 (in LUT words)
   while (pos < end) {
     if (WRITE && blk0 + nb >= blk_limit) break;
-    // both candidate entries are fetched before z is known to be 0 or not: the (p, z) recurrences then overlap
+    // the AC entry is fetched before z is known (it is the common case and sits on the loop-carried path); the DC entry only
+    // by the lanes that start a block, so that its random-bank lookup costs one shared-memory wavefront instead of three
     const uint32_t e_ac = lut[(tb12 >> 16) + (win.hi >> (32 - kAcLutBits))];
-    const uint32_t e_dc = lut[(tb12 & 0xFFFFu) + (win.hi >> (32 - kDcLutBits))];
     const bool is_dc = z == 0;
-    uint32_t e = is_dc ? e_dc : e_ac;
+    uint32_t e = e_ac;
+    if (is_dc) e = lut[(tb12 & 0xFFFFu) + (win.hi >> (32 - kDcLutBits))];
     if (__builtin_expect(e == 0, 0)) e = slow_symbol(slow, is_dc ? (tb12 & 0xFFFFu) : (tb12 >> 16), win.hi, is_dc);
     const uint32_t tb = e & 31u, adv = e >> 20;
     if (WRITE) {
@@ -289,7 +293,7 @@ __device__ __forceinline__ void decode_span(const Src &src, BitWindow<Src> &win,
     nb += endb ? 1u : 0u;
     c = endb ? c1 : c;
     z = endb ? 0 : z;
-    tb12 = s_tbl[c];
+    if (endb) tb12 = s_tbl[c];
   }
 }
 
@@ -302,8 +306,6 @@ __device__ __forceinline__ int find_unit_by_subseq(const JpegUnit *u, int ub, in
   return lo;
 }
 
-__device__ unsigned long long g_huff_dbg[40];    // [r] = live chains entering compacted round r (debug statistics)
-
 struct HuffCtx {
   const JpegImage *images; int nimages;
   const int32_t *block_image;           // sync block -> image
@@ -311,11 +313,14 @@ struct HuffCtx {
   const uint32_t *unit_clean_len;
   const TableSet *tables;
   const uint8_t *clean;
-  uint64_t *s_state; uint32_t *s_n;     // per subsequence: exit state; completed blocks (after H2: exclusive prefix per unit)
+  uint64_t *s_state; uint32_t *s_n;     // per subsequence: exit state; completed blocks (after H2b: exclusive prefix per unit)
   int16_t *coef;
   int16_t *dc;             // compact DC array: one int16 per block, same block order as coef
   int log2_sub;            // log2 of the subsequence size in BITS
   int32_t *status;         // per image: 0 ok, 1 = block count mismatch (corrupt stream)
+  // live chains of the synchronisation (H2a): record = (bit position, c | z << 8, target subsequence, image)
+  uint4 *chains[3];        // [0] = chains that leave their sync block in round 1, [1] / [2] = ping-pong lists of rounds >= 2
+  uint32_t *chain_count;   // [3]
 };
 
 __device__ __forceinline__ uint32_t tbl_word(const JpegImage &im, int b) {
@@ -324,7 +329,7 @@ __device__ __forceinline__ uint32_t tbl_word(const JpegImage &im, int b) {
 
 // Shared memory of the sync-block kernels.
 struct SyncSmem {
-  uint32_t *lut, *sw, *cnt, *tbl, *col_end, *col_p0, *list0, *list1, *nlist;
+  uint32_t *lut, *sw, *cnt, *tbl, *col_end;
   uint64_t *exitst;
   const uint8_t **colptr;
   uint8_t *zig, *col_cont;
@@ -333,8 +338,7 @@ struct SyncSmem {
 __host__ __device__ inline size_t sync_sw_words(int log2_sub) { return (size_t)(kSyncThreads + 1) << (log2_sub - 5); }
 __host__ __device__ inline size_t sync_smem_bytes(int log2_sub) {
   return kLutWords * 4 + sync_sw_words(log2_sub) * 4 + kSyncThreads * 8 /*exit*/ + (kSyncThreads + 1) * 8 /*colptr*/ +
-         kSyncThreads * 4 * 3 /*cnt, col_end, col_p0*/ + 2 * kSyncThreads * 8 /*lists: pos, czx*/ + 16 * 4 /*tbl*/ + 16 /*nlist*/ +
-         64 /*zig*/ + kSyncThreads /*col_cont*/ + 4 * sizeof(HuffSlow);
+         kSyncThreads * 4 * 2 /*cnt, col_end*/ + 16 * 4 /*tbl*/ + 64 /*zig*/ + kSyncThreads /*col_cont*/ + 4 * sizeof(HuffSlow);
 }
 __device__ __forceinline__ SyncSmem carve_sync_smem(uint32_t *base, int log2_sub) {
   SyncSmem s;
@@ -344,12 +348,8 @@ __device__ __forceinline__ SyncSmem carve_sync_smem(uint32_t *base, int log2_sub
   s.colptr = reinterpret_cast<const uint8_t **>(s.exitst + kSyncThreads);
   s.cnt = reinterpret_cast<uint32_t *>(s.colptr + kSyncThreads + 1);
   s.col_end = s.cnt + kSyncThreads;
-  s.col_p0 = s.col_end + kSyncThreads;
-  s.list0 = s.col_p0 + kSyncThreads;
-  s.list1 = s.list0 + 2 * kSyncThreads;
-  s.tbl = s.list1 + 2 * kSyncThreads;
-  s.nlist = s.tbl + 16;
-  s.zig = reinterpret_cast<uint8_t *>(s.nlist + 4);
+  s.tbl = s.col_end + kSyncThreads;
+  s.zig = reinterpret_cast<uint8_t *>(s.tbl + 16);
   s.col_cont = s.zig + 64;
   s.slow = reinterpret_cast<HuffSlow *>(s.col_cont + kSyncThreads);       // 4-byte aligned: all sizes above are multiples of 4
   return s;
@@ -386,9 +386,8 @@ __device__ __forceinline__ SubGeom sync_block_prologue(const HuffCtx &cx, const 
     if (sg.valid) ptr = cx.clean + u.clean_off + ((size_t)sg.jl << (cx.log2_sub - 3));
   }
   sm.colptr[threadIdx.x] = ptr;
-  sm.col_p0[threadIdx.x] = sg.jl << cx.log2_sub;
   sm.col_end[threadIdx.x] = min((sg.jl + 1) << cx.log2_sub, sg.clean_bits);
-  sm.col_cont[threadIdx.x] = sg.valid && threadIdx.x + 1 < kSyncThreads && sg.jl + 1 < sg.nsub_eff;    // the NEXT column continues this unit
+  sm.col_cont[threadIdx.x] = sg.valid && sg.jl + 1 < sg.nsub_eff;             // the unit continues behind this column
   if (threadIdx.x == kSyncThreads - 1) sm.colptr[kSyncThreads] = ptr ? ptr + ((size_t)1 << (cx.log2_sub - 3)) : nullptr;   // look-ahead column
   __syncthreads();
   const int cpc = 1 << (cx.log2_sub - 7);                    // 16-byte chunks per column
@@ -405,14 +404,20 @@ __device__ __forceinline__ SubGeom sync_block_prologue(const HuffCtx &cx, const 
   return sg;
 }
 
-// H1: every thread decodes its own subsequence speculatively (round 0) and the following one from its exit state (round 1);
-// chains that are still not synchronised are then COMPACTED: in round t >= 2 thread k takes the k-th live chain, so the
-// warps stay full while the number of live chains decays.  Chain i visits column i + t in round t, hence every column is
-// touched by at most one chain per round and the rounds are separated by barriers: the result is deterministic.
+__device__ __forceinline__ void push_chain(const HuffCtx &cx, int list, uint32_t pos, int c, int z, int64_t g, int img) {
+  const uint32_t k = atomicAdd(&cx.chain_count[list], 1u);
+  cx.chains[list][k] = make_uint4(pos, (uint32_t)c | ((uint32_t)z << 8), (uint32_t)g, (uint32_t)img);
+}
+
+// H1: every thread decodes its own subsequence speculatively from (c, z) = (0, 0) (round 0) and then the following one from
+// its exit state (round 1).  A chain whose exit state does not yet agree with what the owner of that subsequence found is
+// still "live": it is handed to the grid-wide rounds of H2a.  Chain i visits subsequence i + t in round t, so every
+// subsequence is touched by at most one chain per round; rounds are separated by barriers: the result is deterministic.
 __global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx cx) {
   extern __shared__ __align__(16) uint32_t hsm[];
   const SyncSmem sm = carve_sync_smem(hsm, cx.log2_sub);
-  const JpegImage &im = cx.images[cx.block_image[blockIdx.x]];
+  const int img_i = cx.block_image[blockIdx.x];
+  const JpegImage &im = cx.images[img_i];
   const SubGeom sg = sync_block_prologue(cx, im, sm);
   const HuffSlow *slow = sm.slow;
   const int lsw = cx.log2_sub - 5;
@@ -420,7 +425,6 @@ __global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx c
   BitWindow<SmemSrc> win;
   uint32_t pos = sg.jl << cx.log2_sub, nb = 0;
   int c = 0, z = 0;
-  if (threadIdx.x == 0) { sm.nlist[0] = 0; sm.nlist[1] = 0; }
   // ---- round 0
   if (sg.valid) {
     win.init(src, (uint32_t)threadIdx.x << lsw, 0);
@@ -429,115 +433,122 @@ __global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx c
     sm.cnt[threadIdx.x] = nb;
   }
   __syncthreads();
-  // ---- round 1 (own thread, the window simply continues)
+  // ---- round 1: the window simply continues into the next column; the last thread's next column belongs to the next block
   if (sm.col_cont[threadIdx.x]) {
-    const uint32_t x = threadIdx.x + 1;
-    nb = 0;
-    decode_span<false>(src, win, sm.lut, slow, sm.tbl, im.bpm, pos, sm.col_end[x], c, z, nb, nullptr, nullptr, nullptr, 0, 0);
-    const uint64_t ns = pack_state(pos, c, z);
-    // The count is ALWAYS rewritten: a chain that merely converged inside this subsequence entered it in a different state
-    // than the previous visitor; chains started further left arrive later and are the better informed ones.
-    const bool same = sm.exitst[x] == ns;
-    sm.exitst[x] = ns; sm.cnt[x] = nb;
-    if (!same && sm.col_cont[x]) {
-      const uint32_t k = atomicAdd(&sm.nlist[0], 1u);
-      sm.list0[2 * k] = pos; sm.list0[2 * k + 1] = (uint32_t)c | ((uint32_t)z << 8) | ((x + 1) << 16);
-    }
-  }
-  __syncthreads();
-  // ---- rounds >= 2: compacted
-  int cur = 0;
-#ifdef DALIB200_HUFF_STATS
-  int dbg_round = 0;
-#endif
-  for (;;) {
-    const uint32_t n = sm.nlist[cur];
-    if (n == 0) break;
-#ifdef DALIB200_HUFF_STATS
-    if (threadIdx.x == 0) { atomicAdd(&g_huff_dbg[min(dbg_round, 31)], (unsigned long long)n); atomicAdd(&g_huff_dbg[32], 1ull); }
-    dbg_round++;
-#endif
-    uint32_t *lin = cur ? sm.list1 : sm.list0, *lout = cur ? sm.list0 : sm.list1;
-    __syncthreads();                                   // everybody has read the count
-    if (threadIdx.x == 0) sm.nlist[cur ^ 1] = 0;
-    __syncthreads();
-    if (threadIdx.x < n) {
-      pos = lin[2 * threadIdx.x];
-      const uint32_t czx = lin[2 * threadIdx.x + 1];
-      c = (int)(czx & 0xFF); z = (int)((czx >> 8) & 0xFF);
-      const uint32_t x = czx >> 16;
-      const uint32_t rel = pos - sm.col_p0[x];         // 0..31 bits into column x
-      win.init(src, (x << lsw) + (rel >> 5), rel & 31u);
+    if (threadIdx.x + 1 == kSyncThreads) {
+      push_chain(cx, 0, pos, c, z, sg.g + 1, img_i);
+    } else {
+      const uint32_t x = threadIdx.x + 1;
       nb = 0;
       decode_span<false>(src, win, sm.lut, slow, sm.tbl, im.bpm, pos, sm.col_end[x], c, z, nb, nullptr, nullptr, nullptr, 0, 0);
       const uint64_t ns = pack_state(pos, c, z);
+      // The count is ALWAYS rewritten: a chain that merely converged inside this subsequence entered it in a different
+      // state than the previous visitor; chains started further left arrive later and are the better informed ones.
       const bool same = sm.exitst[x] == ns;
       sm.exitst[x] = ns; sm.cnt[x] = nb;
-      if (!same && sm.col_cont[x]) {
-        const uint32_t k = atomicAdd(&sm.nlist[cur ^ 1], 1u);
-        lout[2 * k] = pos; lout[2 * k + 1] = (uint32_t)c | ((uint32_t)z << 8) | ((x + 1) << 16);
-      }
+      if (!same && sm.col_cont[x]) push_chain(cx, 1, pos, c, z, sg.g + 2, img_i);
     }
-    __syncthreads();
-    cur ^= 1;
   }
+  __syncthreads();
   if (sg.valid) { cx.s_state[sg.g] = sm.exitst[threadIdx.x]; cx.s_n[sg.g] = sm.cnt[threadIdx.x]; }
 }
 
-// H2: one CTA per image.  (a) chain the states across sync-block boundaries until nothing changes,
-// (b) per-unit exclusive scan of the block counts.
-__global__ void __launch_bounds__(1024) huff_sync_inter_kernel(HuffCtx cx) {
-  extern __shared__ __align__(16) uint32_t lut[];          // kLutWords
-  __shared__ uint32_t s_tbl[16];
-  __shared__ int changed;
+// H2a: the remaining rounds, grid wide (cooperative launch).  One thread per live chain; a chain decodes ONE subsequence per
+// round, compares with the stored exit state, overwrites it and stays alive while they differ.  Every thread first copies
+// its subsequence (+ look-ahead) into a private shared-memory column ([word][thread]: bank = thread, conflict free), the
+// tables are shared by the CTA.  List 0 (chains that crossed a sync-block boundary in round 1) is processed first so that
+// all chains of a later round are in the same round.
+constexpr int kTailThreads = 256;
+constexpr int kTailColWords = 36;          // 128-byte subsequence + 16 bytes of look-ahead
+struct ColSrc {
+  const uint32_t *w;                       // &column[0][threadIdx.x]
+  __device__ __forceinline__ uint32_t load(uint32_t g) const { return w[g * kTailThreads]; }
+};
+
+__device__ __forceinline__ void tail_step(const HuffCtx &cx, const uint4 rec, int out_list, const uint32_t *s_lut, const HuffSlow *s_slow,
+                                          int s_table_set, uint32_t *col) {
+  const int img_i = (int)rec.w;
+  const JpegImage &im = cx.images[img_i];
+  const int64_t g = rec.z;
+  const int j = (int)(g - im.subseq_begin);
+  const int ui = im.unit_end - im.unit_begin == 1 ? im.unit_begin : find_unit_by_subseq(cx.units, im.unit_begin, im.unit_end, j);
+  const JpegUnit &u = cx.units[ui];
+  const uint32_t clean_bits = cx.unit_clean_len[ui] * 8u;
+  const uint32_t nsub_eff = (clean_bits + (1u << cx.log2_sub) - 1) >> cx.log2_sub;
+  const uint32_t jl = (uint32_t)(j - u.first_subseq);
+  uint32_t tbl[kMaxBlocksPerMcu];
+#pragma unroll
+  for (int b = 0; b < kMaxBlocksPerMcu; b++) tbl[b] = tbl_word(im, b);
+  const bool shared_tables = im.table_set == s_table_set;
+  const uint32_t *lut = shared_tables ? s_lut : cx.tables[im.table_set].lut;
+  const HuffSlow *slow = shared_tables ? s_slow : cx.tables[im.table_set].slow;
+  uint32_t pos = rec.x, nb = 0;
+  int c = (int)(rec.y & 0xFF), z = (int)((rec.y >> 8) & 0xFF);
+  const uint32_t end = min((jl + 1) << cx.log2_sub, clean_bits);
+  const int sub_words = 1 << (cx.log2_sub - 5);
+  if (sub_words + 4 <= kTailColWords) {
+    // private column: words [0, sub_words + 4) of this subsequence
+    const uint4 *p4 = reinterpret_cast<const uint4 *>(cx.clean + u.clean_off + ((size_t)jl << (cx.log2_sub - 3)));
+    for (int q = 0; q < sub_words / 4 + 1; q++) {
+      const uint4 v = __ldg(p4 + q);
+      col[(4 * q + 0) * kTailThreads] = v.x; col[(4 * q + 1) * kTailThreads] = v.y;
+      col[(4 * q + 2) * kTailThreads] = v.z; col[(4 * q + 3) * kTailThreads] = v.w;
+    }
+    const ColSrc src{col};
+    const uint32_t rel = pos - (jl << cx.log2_sub);
+    BitWindow<ColSrc> win;
+    win.init(src, rel >> 5, rel & 31u);
+    decode_span<false>(src, win, lut, slow, tbl, im.bpm, pos, end, c, z, nb, nullptr, nullptr, nullptr, 0, 0);
+  } else {
+    const GlobalSrc src{reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off)};
+    BitWindow<GlobalSrc> win;
+    win.init(src, pos >> 5, pos & 31u);
+    decode_span<false>(src, win, lut, slow, tbl, im.bpm, pos, end, c, z, nb, nullptr, nullptr, nullptr, 0, 0);
+  }
+  const uint64_t ns = pack_state(pos, c, z);
+  const bool same = cx.s_state[g] == ns;
+  cx.s_state[g] = ns; cx.s_n[g] = nb;                       // always: see huff_sync_intra_kernel
+  if (!same && jl + 1 < nsub_eff) push_chain(cx, out_list, pos, c, z, g + 1, img_i);
+}
+
+__global__ void __launch_bounds__(kTailThreads) huff_sync_tail_kernel(HuffCtx cx) {
+  extern __shared__ __align__(16) uint32_t tsm[];
+  uint32_t *s_lut = tsm;
+  HuffSlow *s_slow = reinterpret_cast<HuffSlow *>(s_lut + kLutWords);
+  uint32_t *col = reinterpret_cast<uint32_t *>(s_slow + 4) + threadIdx.x;
+  const int s_table_set = cx.images[0].table_set;
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(cx.tables[s_table_set].lut);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+    for (int i = threadIdx.x; i < kLutWords / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    const uint32_t *ssrc = reinterpret_cast<const uint32_t *>(cx.tables[s_table_set].slow);
+    uint32_t *sdst = reinterpret_cast<uint32_t *>(s_slow);
+    for (int i = threadIdx.x; i < (int)(4 * sizeof(HuffSlow) / 4); i += blockDim.x) sdst[i] = __ldg(ssrc + i);
+  }
+  __syncthreads();
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  // round 1 of the chains that left their sync block: survivors join list 1 (round 2)
+  for (uint32_t i = gtid, n = cx.chain_count[0]; i < n; i += gsize) tail_step(cx, cx.chains[0][i], 1, s_lut, s_slow, s_table_set, col);
+  grid.sync();
+  int cur = 1;
+  for (;;) {
+    const uint32_t n = cx.chain_count[cur];
+    if (n == 0) break;
+    const int nxt = cur == 1 ? 2 : 1;
+    for (uint32_t i = gtid; i < n; i += gsize) tail_step(cx, cx.chains[cur][i], nxt, s_lut, s_slow, s_table_set, col);
+    grid.sync();                                             // everybody has read chain_count[cur] and pushed its survivors
+    if (gtid == 0) cx.chain_count[cur] = 0;                  // reused two rounds later, after the next grid.sync
+    cur = nxt;
+  }
+}
+
+// H2b: one CTA per image: per-unit exclusive scan of the block counts (in place), status check.
+__global__ void __launch_bounds__(1024) huff_scan_kernel(HuffCtx cx) {
   __shared__ uint32_t warp_tot[32];
   __shared__ uint32_t carry;
   const JpegImage &im = cx.images[blockIdx.x];
-  {
-    const uint4 *src = reinterpret_cast<const uint4 *>(cx.tables[im.table_set].lut);
-    uint4 *dst = reinterpret_cast<uint4 *>(lut);
-    for (int i = threadIdx.x; i < kLutWords / 4; i += blockDim.x) dst[i] = __ldg(src + i);
-    if (threadIdx.x < kMaxBlocksPerMcu) s_tbl[threadIdx.x] = tbl_word(im, threadIdx.x);
-  }
-  const HuffSlow *slow = cx.tables[im.table_set].slow;
   const uint32_t sub_bits = 1u << cx.log2_sub;
-  const int nblocks = (im.nsub + kSyncThreads - 1) / kSyncThreads;
-  for (int round = 0; round < nblocks + 1; round++) {
-    __syncthreads();
-    if (threadIdx.x == 0) changed = 0;
-    __syncthreads();
-    for (int b = 1 + threadIdx.x; b < nblocks; b += blockDim.x) {
-      const int j0 = b * kSyncThreads;
-      const int ui = find_unit_by_subseq(cx.units, im.unit_begin, im.unit_end, j0);
-      const JpegUnit &u = cx.units[ui];
-      if (u.first_subseq == j0) continue;                        // a unit starts here: true entry state known
-      const uint32_t clean_bits = cx.unit_clean_len[ui] * 8u;
-      const uint32_t nsub_eff = (clean_bits + sub_bits - 1) >> cx.log2_sub;
-      const uint32_t jl = (uint32_t)(j0 - u.first_subseq);
-      if (jl >= nsub_eff) continue;
-      const GlobalSrc src{reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off)};
-      const int64_t g0 = (int64_t)im.subseq_begin + j0;
-      const uint64_t prev = cx.s_state[g0 - 1];
-      uint32_t pos = (uint32_t)prev, nb = 0;
-      int c = (int)((prev >> 32) & 0xFF), z = (int)((prev >> 40) & 0xFF);
-      BitWindow<GlobalSrc> win;
-      win.init(src, pos >> 5, pos & 31u);
-      bool synced = false;
-      for (uint32_t k = 0; k < (uint32_t)kSyncThreads && jl + k < nsub_eff; k++) {
-        nb = 0;
-        decode_span<false>(src, win, lut, slow, s_tbl, im.bpm, pos, min((jl + k + 1) << cx.log2_sub, clean_bits), c, z, nb,
-                           nullptr, nullptr, nullptr, 0, 0);
-        const uint64_t ns = pack_state(pos, c, z);
-        const bool same = cx.s_state[g0 + k] == ns;
-        cx.s_state[g0 + k] = ns; cx.s_n[g0 + k] = nb;     // always: see huff_sync_intra_kernel
-        if (same) { synced = true; break; }
-      }
-      if (!synced) changed = 1;     // the exit state of this block moved: the next boundary must be redone
-    }
-    __syncthreads();
-    if (!changed) break;
-  }
-  // ---- exclusive scan of the block counts per unit (in place)
   for (int ui = im.unit_begin; ui < im.unit_end; ui++) {
     const JpegUnit &u = cx.units[ui];
     const uint32_t clean_bits = cx.unit_clean_len[ui] * 8u;
@@ -1225,6 +1236,9 @@ struct dalib200JpegPlan {
   uint32_t *d_chunk = nullptr; size_t d_chunk_cap = 0;
   uint32_t *d_unit_len = nullptr; size_t d_unit_cap = 0;
   uint64_t *d_state = nullptr; uint32_t *d_n = nullptr; size_t d_sub_cap = 0;
+  uint4 *d_chain0 = nullptr, *d_chain1 = nullptr, *d_chain2 = nullptr; size_t d_chain0_cap = 0, d_chain1_cap = 0, d_chain2_cap = 0;
+  uint32_t *d_chain_count = nullptr; size_t d_chain_count_cap = 0;
+  int tail_grid = 0;
   int16_t *d_coef = nullptr; size_t d_coef_cap = 0;
   int16_t *d_dc = nullptr; size_t d_dc_cap = 0;
   uint8_t *d_planes = nullptr; size_t d_planes_cap = 0;
@@ -1280,7 +1294,8 @@ int dalib200JpegPlanDestroy(dalib200JpegPlan *p) {
   if (p->img_uploaded) { cudaEventSynchronize(p->img_uploaded); cudaEventDestroy(p->img_uploaded); }
   if (p->h_stage) cudaFreeHost(p->h_stage);
   if (p->h_images) cudaFreeHost(p->h_images);
-  void *bufs[] = { p->d_stage, p->d_clean, p->d_chunk, p->d_unit_len, p->d_state, p->d_n, p->d_coef, p->d_dc, p->d_planes, p->d_status };
+  void *bufs[] = { p->d_stage, p->d_clean, p->d_chunk, p->d_unit_len, p->d_state, p->d_n, p->d_coef, p->d_dc, p->d_planes, p->d_status,
+                   p->d_chain0, p->d_chain1, p->d_chain2, p->d_chain_count };
   for (void *b : bufs) if (b) cudaFree(b);
   delete p;
   return DALIB200_SUCCESS;
@@ -1513,12 +1528,6 @@ int dalib200JpegDebugGetCoefficients(dalib200JpegPlan *p, int sample, int16_t *o
   return DALIB200_SUCCESS;
 }
 
-int dalib200JpegDebugHuffStats(unsigned long long *out40) {
-  DB_CUDA(cudaDeviceSynchronize());
-  DB_CUDA(cudaMemcpyFromSymbol(out40, g_huff_dbg, sizeof(unsigned long long) * 40));
-  return DALIB200_SUCCESS;
-}
-
 // per-sample decode status written by the device (0 = ok, 1 = entropy-coded data ended early).  Synchronises.
 int dalib200JpegGetStatus(dalib200JpegPlan *p, int32_t *status_out) {
   DB_CHECK_ARG(p && status_out && p->d_status, "JpegGetStatus: bad arguments");
@@ -1594,6 +1603,10 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
     if ((rc = GrowDevice(p->d_state, p->d_sub_cap, (size_t)p->total_subseq + 1))) return rc;
     if ((rc = GrowDevice(p->d_n, cap2, (size_t)p->total_subseq + 1))) return rc;
   }
+  if ((rc = GrowDevice(p->d_chain0, p->d_chain0_cap, (size_t)p->total_blocks_sync + 1))) return rc;
+  if ((rc = GrowDevice(p->d_chain1, p->d_chain1_cap, (size_t)p->total_subseq + 1))) return rc;
+  if ((rc = GrowDevice(p->d_chain2, p->d_chain2_cap, (size_t)p->total_subseq + 1))) return rc;
+  if ((rc = GrowDevice(p->d_chain_count, p->d_chain_count_cap, (size_t)4))) return rc;
   if ((rc = GrowDevice(p->d_coef, p->d_coef_cap, (size_t)p->total_coefs + 64))) return rc;
   if ((rc = GrowDevice(p->d_dc, p->d_dc_cap, (size_t)p->total_coefs / 64 + 64))) return rc;
   if ((rc = GrowDevice(p->d_planes, p->d_planes_cap, (size_t)p->total_plane_bytes + 64))) return rc;
@@ -1630,6 +1643,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   { ProfScope ps_("jpeg_memset_coef", s); DB_CUDA(cudaMemsetAsync(p->d_coef, 0, (size_t)p->total_coefs * sizeof(int16_t), s)); }
   DB_CUDA(cudaMemsetAsync(p->d_dc, 0, (size_t)(p->total_coefs / 64) * sizeof(int16_t), s));
   DB_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * p->n, s));
+  DB_CUDA(cudaMemsetAsync(p->d_chain_count, 0, sizeof(uint32_t) * 4, s));
   {
     const int grid = (int)std::min<uint32_t>(p->nchunks, (uint32_t)sms * 16);
     { ProfScope ps_("jpeg_unstuff_count", s); unstuff_count_kernel<<<grid, 256, 0, s>>>(d_raw, d_units, nunits, p->nchunks, p->d_chunk); }
@@ -1641,6 +1655,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   cx.images = d_images; cx.nimages = p->n; cx.block_image = reinterpret_cast<const int32_t *>(p->d_stage + p->off_blkimg); cx.units = d_units; cx.unit_clean_len = p->d_unit_len; cx.tables = d_tables;
   cx.clean = p->d_clean; cx.s_state = p->d_state; cx.s_n = p->d_n; cx.coef = p->d_coef; cx.dc = p->d_dc; cx.log2_sub = p->log2_sub;
   cx.status = p->d_status;
+  cx.chains[0] = p->d_chain0; cx.chains[1] = p->d_chain1; cx.chains[2] = p->d_chain2; cx.chain_count = p->d_chain_count;
   const size_t hsmem = sync_smem_bytes(p->log2_sub);
   if (!p->smem_opted) {
     DB_CUDA(cudaFuncSetAttribute(huff_sync_intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_smem_bytes(kMaxLog2Sub)));
@@ -1648,7 +1663,22 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
     p->smem_opted = true;
   }
   { ProfScope ps_("jpeg_huff_sync_intra", s); huff_sync_intra_kernel<<<p->total_blocks_sync, kSyncThreads, hsmem, s>>>(cx); }
-  { ProfScope ps_("jpeg_huff_sync_inter", s); huff_sync_inter_kernel<<<p->n, 1024, kLutWords * 4, s>>>(cx); }
+  {
+    const size_t tail_smem = kLutWords * 4 + 4 * sizeof(HuffSlow) + (size_t)kTailColWords * kTailThreads * 4;
+    if (p->tail_grid == 0) {
+      int per_sm = 0;
+      DB_CUDA(cudaFuncSetAttribute(huff_sync_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
+      DB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, huff_sync_tail_kernel, kTailThreads, tail_smem));
+      p->tail_grid = std::max(1, per_sm) * sms;
+    }
+    const int64_t want = (p->total_subseq / 3 + kTailThreads - 1) / kTailThreads;          // ~30 % of the chains are still live after round 1
+    const int tgrid = (int)std::max<int64_t>(1, std::min<int64_t>(p->tail_grid, want));
+    void *args[] = { &cx };
+    ProfScope ps_("jpeg_huff_sync_tail", s);
+    DB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(huff_sync_tail_kernel), dim3(tgrid), dim3(kTailThreads), args, tail_smem, s));
+  }
+  { ProfScope ps_("jpeg_huff_scan", s); huff_scan_kernel<<<p->n, 1024, 0, s>>>(cx); }
+  CountLaunch();
   { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_sync, kSyncThreads, hsmem, s>>>(cx); }
   { ProfScope ps_("jpeg_dc_scan", s); dc_scan_kernel<<<p->n, 1024, 0, s>>>(d_images, p->d_dc); }
   {

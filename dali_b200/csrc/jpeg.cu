@@ -329,16 +329,18 @@ __device__ __forceinline__ uint32_t tbl_word(const JpegImage &im, int b) {
 
 // Shared memory of the sync-block kernels.
 struct SyncSmem {
-  uint32_t *lut, *sw, *cnt, *tbl, *col_end;
+  uint32_t *lut, *sw, *cnt, *tbl, *col_end, *blkbuf;
   uint64_t *exitst;
   const uint8_t **colptr;
   uint8_t *zig, *col_cont;
   HuffSlow *slow;                // shared-memory copy of the canonical tables (the long-code path is latency critical)
 };
-__host__ __device__ inline size_t sync_sw_words(int log2_sub) { return (size_t)(kSyncThreads + 1) << (log2_sub - 5); }
-__host__ __device__ inline size_t sync_smem_bytes(int log2_sub) {
-  return kLutWords * 4 + sync_sw_words(log2_sub) * 4 + kSyncThreads * 8 /*exit*/ + (kSyncThreads + 1) * 8 /*colptr*/ +
-         kSyncThreads * 4 * 2 /*cnt, col_end*/ + 16 * 4 /*tbl*/ + 64 /*zig*/ + kSyncThreads /*col_cont*/ + 4 * sizeof(HuffSlow);
+constexpr int kLookAheadCols = 2;             // staged behind the sync block: a block (<= 208 bytes) may run that far past the last column
+__host__ __device__ inline size_t sync_sw_words(int log2_sub) { return (size_t)(kSyncThreads + kLookAheadCols) << (log2_sub - 5); }
+__host__ __device__ inline size_t sync_smem_bytes(int log2_sub, bool with_block_buffers) {
+  return kLutWords * 4 + sync_sw_words(log2_sub) * 4 + kSyncThreads * 8 /*exit*/ + (kSyncThreads + kLookAheadCols) * 8 /*colptr*/ +
+         kSyncThreads * 4 * 2 /*cnt, col_end*/ + 16 * 4 /*tbl*/ + 64 /*zig*/ + kSyncThreads /*col_cont*/ + 4 * sizeof(HuffSlow) +
+         (with_block_buffers ? (size_t)kSyncThreads * 128 : 0) /*block buffers (H3)*/;
 }
 __device__ __forceinline__ SyncSmem carve_sync_smem(uint32_t *base, int log2_sub) {
   SyncSmem s;
@@ -346,12 +348,13 @@ __device__ __forceinline__ SyncSmem carve_sync_smem(uint32_t *base, int log2_sub
   s.sw = s.lut + kLutWords;
   s.exitst = reinterpret_cast<uint64_t *>(s.sw + sync_sw_words(log2_sub));     // both word counts are multiples of 8
   s.colptr = reinterpret_cast<const uint8_t **>(s.exitst + kSyncThreads);
-  s.cnt = reinterpret_cast<uint32_t *>(s.colptr + kSyncThreads + 1);
+  s.cnt = reinterpret_cast<uint32_t *>(s.colptr + kSyncThreads + kLookAheadCols);
   s.col_end = s.cnt + kSyncThreads;
   s.tbl = s.col_end + kSyncThreads;
   s.zig = reinterpret_cast<uint8_t *>(s.tbl + 16);
   s.col_cont = s.zig + 64;
   s.slow = reinterpret_cast<HuffSlow *>(s.col_cont + kSyncThreads);       // 4-byte aligned: all sizes above are multiples of 4
+  s.blkbuf = reinterpret_cast<uint32_t *>(s.slow + 4);
   return s;
 }
 
@@ -388,10 +391,11 @@ __device__ __forceinline__ SubGeom sync_block_prologue(const HuffCtx &cx, const 
   sm.colptr[threadIdx.x] = ptr;
   sm.col_end[threadIdx.x] = min((sg.jl + 1) << cx.log2_sub, sg.clean_bits);
   sm.col_cont[threadIdx.x] = sg.valid && sg.jl + 1 < sg.nsub_eff;             // the unit continues behind this column
-  if (threadIdx.x == kSyncThreads - 1) sm.colptr[kSyncThreads] = ptr ? ptr + ((size_t)1 << (cx.log2_sub - 3)) : nullptr;   // look-ahead column
+  if (threadIdx.x == kSyncThreads - 1)
+    for (int q = 1; q <= kLookAheadCols; q++) sm.colptr[kSyncThreads - 1 + q] = ptr ? ptr + ((size_t)q << (cx.log2_sub - 3)) : nullptr;
   __syncthreads();
   const int cpc = 1 << (cx.log2_sub - 7);                    // 16-byte chunks per column
-  for (int ch = threadIdx.x; ch < (kSyncThreads + 1) * cpc; ch += blockDim.x) {
+  for (int ch = threadIdx.x; ch < (kSyncThreads + kLookAheadCols) * cpc; ch += blockDim.x) {
     const int col = ch / cpc, o = ch - col * cpc;
     const uint8_t *p = sm.colptr[col];
     if (p) {
@@ -577,29 +581,103 @@ __global__ void __launch_bounds__(1024) huff_scan_kernel(HuffCtx cx) {
 }
 
 // H3: final pass -- every subsequence is decoded from its now-correct entry state and writes coefficients.
+//
+// A block belongs to the thread in whose subsequence it STARTS: a thread skips the tail of the block that is open at its
+// entry and runs past its own end until its last block is complete (the stream of the following subsequences is staged
+// too).  Every block therefore has exactly one writer, which assembles it in a private 128-byte shared-memory buffer
+// (word j of lane l at l * 32 + (j ^ l): conflict free for the per-symbol 16-bit scatter of all lanes to the same j and for the
+// flush) and the warp writes each finished block to HBM as ONE coalesced 128-byte line: no memset of the coefficient arena,
+// no 2-byte read-modify-write traffic, ~12x fewer store wavefronts than a per-symbol scatter.
 __global__ void __launch_bounds__(kSyncThreads) huff_write_kernel(HuffCtx cx) {
   extern __shared__ __align__(16) uint32_t hsm[];
   const SyncSmem sm = carve_sync_smem(hsm, cx.log2_sub);
   const JpegImage &im = cx.images[cx.block_image[blockIdx.x]];
   const SubGeom sg = sync_block_prologue(cx, im, sm);
-  if (!sg.valid) return;
-  const JpegUnit &u = cx.units[sg.ui];
   const HuffSlow *slow = sm.slow;
   const SmemSrc src{sm.sw, cx.log2_sub - 5};
-  uint32_t pos = 0, nb = 0;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t *wbuf = sm.blkbuf + (threadIdx.x & ~31u) * 32u;             // this warp's 32 block buffers
+  uint32_t *mybuf = wbuf + lane * 32u;
+#pragma unroll
+  for (int j = 0; j < 32; j++) mybuf[j] = 0u;
+  __syncwarp();
+  uint32_t pos = 0, nb = 0, end = 0, hard_end = 0, blk0 = 0, blk_limit = 0;
   int c = 0, z = 0;
-  if (sg.jl > 0) {
-    const uint64_t prev = cx.s_state[sg.g - 1];
-    pos = (uint32_t)prev; c = (int)((prev >> 32) & 0xFF); z = (int)((prev >> 40) & 0xFF);
+  bool active = sg.valid;
+  if (active) {
+    const JpegUnit &u = cx.units[sg.ui];
+    if (sg.jl > 0) {
+      const uint64_t prev = cx.s_state[sg.g - 1];
+      pos = (uint32_t)prev; c = (int)((prev >> 32) & 0xFF); z = (int)((prev >> 40) & 0xFF);
+    }
+    end = min((sg.jl + 1) << cx.log2_sub, sg.clean_bits);
+    hard_end = sg.clean_bits;
+    const uint32_t ublk = (uint32_t)(u.slot_base >> 6);
+    blk0 = ublk + cx.s_n[sg.g];
+    blk_limit = ublk + (uint32_t)(u.nslots >> 6);
+    active = pos < end;
   }
-  const uint32_t end = min((sg.jl + 1) << cx.log2_sub, sg.clean_bits);
-  if (pos >= end) return;
-  const uint32_t rel = pos - (sg.jl << cx.log2_sub);          // 0..31 bits into this thread's column
+  bool own = z == 0;                                          // a block starts exactly at the entry: it is ours
   BitWindow<SmemSrc> win;
-  win.init(src, ((uint32_t)threadIdx.x << (cx.log2_sub - 5)) + (rel >> 5), rel & 31u);
-  const uint32_t ublk = (uint32_t)(u.slot_base >> 6);
-  decode_span<true>(src, win, sm.lut, slow, sm.tbl, im.bpm, pos, end, c, z, nb, cx.coef + im.coef_off, cx.dc + im.coef_off / 64, sm.zig,
-                    ublk + cx.s_n[sg.g], ublk + (uint32_t)(u.nslots >> 6));
+  {
+    const uint32_t rel = active ? pos - (sg.jl << cx.log2_sub) : 0u;     // 0..31 bits into this thread's column
+    win.init(src, ((uint32_t)threadIdx.x << (cx.log2_sub - 5)) + (rel >> 5), rel & 31u);
+  }
+  int16_t *coef = cx.coef + im.coef_off;
+  int16_t *dcv = cx.dc + im.coef_off / 64;
+  const int bpm = im.bpm;
+  uint32_t tb12 = sm.tbl[c];
+  while (__any_sync(0xffffffffu, active)) {
+    bool flush = false;
+    const uint32_t blk = blk0 + nb;
+    if (active) {
+      const uint32_t e_ac = sm.lut[(tb12 >> 16) + (win.hi >> (32 - kAcLutBits))];
+      const bool is_dc = z == 0;
+      uint32_t e = e_ac;
+      if (is_dc) e = sm.lut[(tb12 & 0xFFFFu) + (win.hi >> (32 - kDcLutBits))];
+      if (__builtin_expect(e == 0, 0)) e = slow_symbol(slow, is_dc ? (tb12 & 0xFFFFu) : (tb12 >> 16), win.hi, is_dc);
+      const uint32_t tb = e & 31u, adv = e >> 20, s = (e >> 8) & 15u;
+      {
+        // magnitude bits (EXTEND, T.81 F.2.2.1), computed by every lane: s == 0 gives v == 0
+        const uint32_t len = (e >> 12) & 31u;
+        const uint32_t bits = (uint32_t)(((uint64_t)(win.hi << len)) >> (32u - s));      // 64-bit shift: s == 0 -> 0
+        const int v = (int)bits - ((s == 0 || ((bits >> (s - 1u)) & 1u)) ? 0 : (int)((1u << s) - 1u));
+        if (own) {
+          if (is_dc) {
+            dcv[blk] = (int16_t)v;                            // every block has a DC term: the compact array needs no memset
+          } else if (s) {
+            const uint32_t nat = sm.zig[min((uint32_t)z + adv - 1u, 63u)];
+            reinterpret_cast<int16_t *>(mybuf + ((nat >> 1) ^ lane))[nat & 1u] = (int16_t)v;
+          }
+        }
+      }
+      win.consume(src, e);
+      pos += tb;
+      z += (int)adv;
+      const bool endb = z >= 64;                              // block finished (EOB, 64th coefficient, or garbage overrun)
+      const int c1 = c + 1 == bpm ? 0 : c + 1;
+      flush = endb && own;
+      nb += endb ? 1u : 0u;
+      own = own || endb;                                      // the open block of the entry is over: what follows is ours
+      c = endb ? c1 : c;
+      z = endb ? 0 : z;
+      if (endb) tb12 = sm.tbl[c];
+      // keep going while symbols start inside the subsequence, then until the last own block is complete
+      active = blk0 + nb < blk_limit && (pos < end || (z != 0 && pos < hard_end));
+    }
+    // ---- flush the finished blocks of this warp, one coalesced line each
+    uint32_t m = __ballot_sync(0xffffffffu, flush);
+    while (m) {
+      const uint32_t L = __ffs(m) - 1u;
+      m &= m - 1u;
+      const uint32_t fb = __shfl_sync(0xffffffffu, blk, L);
+      uint32_t *src_w = wbuf + L * 32u + (lane ^ L);
+      const uint32_t w = *src_w;
+      *src_w = 0u;
+      reinterpret_cast<uint32_t *>(coef + (size_t)fb * 64)[lane] = w;
+    }
+    __syncwarp();
+  }
 }
 
 // ============================================================================================
@@ -1640,8 +1718,6 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   cudaStream_t s = stream;
   // the clean stream must be zero-padded behind every unit (the bit reader peeks ahead)
   DB_CUDA(cudaMemsetAsync(p->d_clean, 0, p->clean_bytes + 1024, s));
-  { ProfScope ps_("jpeg_memset_coef", s); DB_CUDA(cudaMemsetAsync(p->d_coef, 0, (size_t)p->total_coefs * sizeof(int16_t), s)); }
-  DB_CUDA(cudaMemsetAsync(p->d_dc, 0, (size_t)(p->total_coefs / 64) * sizeof(int16_t), s));
   DB_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * p->n, s));
   DB_CUDA(cudaMemsetAsync(p->d_chain_count, 0, sizeof(uint32_t) * 4, s));
   {
@@ -1656,10 +1732,10 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   cx.clean = p->d_clean; cx.s_state = p->d_state; cx.s_n = p->d_n; cx.coef = p->d_coef; cx.dc = p->d_dc; cx.log2_sub = p->log2_sub;
   cx.status = p->d_status;
   cx.chains[0] = p->d_chain0; cx.chains[1] = p->d_chain1; cx.chains[2] = p->d_chain2; cx.chain_count = p->d_chain_count;
-  const size_t hsmem = sync_smem_bytes(p->log2_sub);
+  const size_t hsmem = sync_smem_bytes(p->log2_sub, false), wsmem = sync_smem_bytes(p->log2_sub, true);
   if (!p->smem_opted) {
-    DB_CUDA(cudaFuncSetAttribute(huff_sync_intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_smem_bytes(kMaxLog2Sub)));
-    DB_CUDA(cudaFuncSetAttribute(huff_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_smem_bytes(kMaxLog2Sub)));
+    DB_CUDA(cudaFuncSetAttribute(huff_sync_intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_smem_bytes(kMaxLog2Sub, false)));
+    DB_CUDA(cudaFuncSetAttribute(huff_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_smem_bytes(kMaxLog2Sub, true)));
     p->smem_opted = true;
   }
   { ProfScope ps_("jpeg_huff_sync_intra", s); huff_sync_intra_kernel<<<p->total_blocks_sync, kSyncThreads, hsmem, s>>>(cx); }
@@ -1679,7 +1755,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   }
   { ProfScope ps_("jpeg_huff_scan", s); huff_scan_kernel<<<p->n, 1024, 0, s>>>(cx); }
   CountLaunch();
-  { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_sync, kSyncThreads, hsmem, s>>>(cx); }
+  { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_sync, kSyncThreads, wsmem, s>>>(cx); }
   { ProfScope ps_("jpeg_dc_scan", s); dc_scan_kernel<<<p->n, 1024, 0, s>>>(d_images, p->d_dc); }
   {
     const int64_t total_blocks = p->total_coefs / 64;

@@ -107,9 +107,27 @@ __device__ __forceinline__ int find_unit_by_chunk(const JpegUnit *u, int n, uint
   return lo;
 }
 
-// a byte is dropped when it is the 0x00 that follows a 0xFF
-__device__ __forceinline__ bool dropped(const uint8_t *raw, uint32_t off, uint32_t i) {
-  return i > 0 && raw[off + i] == 0x00 && raw[off + i - 1] == 0xFF;
+// a byte is dropped when it is the 0x00 that follows a 0xFF.  Word-at-a-time: bit 8k+7.. of the result marks byte k of
+// `w` as dropped; `prev` is the byte in front of the word (0 at the start of a unit).
+__device__ __forceinline__ uint32_t dropped_mask(uint32_t w, uint32_t prev) {
+  const uint32_t is00 = __vcmpeq4(w, 0u);                      // 0xFF per byte that is 0x00
+  const uint32_t pw = (w << 8) | prev;                         // byte k = the byte in front of byte k of w
+  const uint32_t isff = __vcmpeq4(pw, 0xFFFFFFFFu);
+  return is00 & isff;
+}
+
+// 4 raw bytes at offset i of a chunk (bytes at or beyond `len` read as 0x01: never dropped, never a 0xFF prefix).  Units that
+// start behind a restart marker are not word aligned: those take the byte path.
+__device__ __forceinline__ uint32_t load_raw_word(const uint8_t *p, uint32_t i, uint32_t len) {
+  uint32_t w;
+  if ((reinterpret_cast<uintptr_t>(p + i) & 3u) == 0 && i + 4 <= len) {
+    w = *reinterpret_cast<const uint32_t *>(p + i);
+  } else {
+    w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) w |= (uint32_t)(i + k < len ? p[i + k] : 1u) << (8 * k);
+  }
+  return w;
 }
 
 __global__ void __launch_bounds__(256) unstuff_count_kernel(const uint8_t *__restrict__ raw, const JpegUnit *__restrict__ units,
@@ -121,7 +139,11 @@ __global__ void __launch_bounds__(256) unstuff_count_kernel(const uint8_t *__res
     const uint32_t c0 = (chunk - u.first_chunk) * kChunkBytes;
     const uint32_t len = min((uint32_t)kChunkBytes, u.raw_len - c0);
     int cnt = 0;
-    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) cnt += dropped(raw, u.raw_off, c0 + i) ? 1 : 0;
+    for (uint32_t i = threadIdx.x * 4; i < len; i += blockDim.x * 4) {
+      const uint32_t w = load_raw_word(raw + u.raw_off + c0, i, len);
+      const uint32_t prev = c0 + i > 0 ? raw[u.raw_off + c0 + i - 1] : 0u;
+      cnt += __popc(dropped_mask(w, prev)) >> 3;
+    }
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
     __syncthreads();
@@ -158,14 +180,22 @@ __global__ void __launch_bounds__(256) unstuff_scatter_kernel(const uint8_t *__r
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     for (uint32_t base = 0; base < len; base += blockDim.x * 4) {
-      // each thread owns 4 consecutive bytes
+      // each thread owns 4 consecutive bytes (one aligned word)
       const uint32_t i0 = base + threadIdx.x * 4;
       uint8_t b[4]; bool keep[4]; int nk = 0;
+      {
+        uint32_t w = 0, dm = 0;
+        if (i0 < len) {
+          w = load_raw_word(raw + u.raw_off + c0, i0, len);
+          const uint32_t prev = c0 + i0 > 0 ? raw[u.raw_off + c0 + i0 - 1] : 0u;
+          dm = dropped_mask(w, prev);
+        }
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t i = i0 + k;
-        keep[k] = false;
-        if (i < len) { b[k] = raw[u.raw_off + c0 + i]; keep[k] = !dropped(raw, u.raw_off, c0 + i); nk += keep[k]; }
+        for (int k = 0; k < 4; k++) {
+          b[k] = (uint8_t)(w >> (8 * k));
+          keep[k] = i0 + k < len && !((dm >> (8 * k)) & 1u);
+          nk += keep[k];
+        }
       }
       int incl = nk;
       for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += v; }
@@ -770,8 +800,10 @@ __device__ __forceinline__ void idct8(int i0, int i1, int i2, int i3, int i4, in
 }
 
 __device__ __forceinline__ uint32_t range_limit(int x) {     // libjpeg range_limit[(x) & RANGE_MASK], table centred on 128
-  const int idx = x & 1023;
-  return idx < 128 ? idx + 128 : idx < 512 ? 255 : idx < 896 ? 0 : idx - 896;
+  // idx = x & 1023: [0,128) -> idx + 128, [128,512) -> 255, [512,896) -> 0, [896,1024) -> idx - 896.  With y = (x + 128) & 1023
+  // this is: y < 256 -> y, y < 640 -> 255, else 0.
+  const uint32_t y = (uint32_t)(x + 128) & 1023u;
+  return y < 640u ? min(y, 255u) : 0u;
 }
 
 __device__ __forceinline__ int find_image_by_coefblock(const JpegImage *im, int n, int64_t blk) {

@@ -67,10 +67,18 @@ template <typename Out>
 __global__ void __launch_bounds__(256) cmn_hwc2chw_kernel(const CmnDesc *__restrict__ descs, int n, int64_t total_units,
                                                           int out_c) {
   const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t unit = warp0; unit < total_units; unit += nwarps) {
-    const int s = find_sample_units(descs, n, unit);
+  // every CTA owns one contiguous range of units (its 8 warps interleaved): the sample is searched once per CTA and then only
+  // advanced -- a binary search over thousands of frame descriptors per 384-byte unit used to dominate this kernel
+  __shared__ int s_first;
+  const int wpc = blockDim.x >> 5;
+  const int64_t per_cta = ((total_units + gridDim.x - 1) / gridDim.x + wpc - 1) / wpc * wpc;
+  const int64_t u0 = (int64_t)blockIdx.x * per_cta, u1 = min(total_units, u0 + per_cta);
+  if (u0 >= u1) return;
+  if (threadIdx.x == 0) s_first = find_sample_units(descs, n, u0);
+  __syncthreads();
+  int s = s_first;
+  for (int64_t unit = u0 + (threadIdx.x >> 5); unit < u1; unit += wpc) {
+    while (s + 1 < n && descs[s + 1].first_unit <= unit) s++;
     const CmnDesc &d = descs[s];
     if (!d.fast) continue;                       // generic samples own zero units, defensive
     const int64_t u = unit - d.first_unit;
@@ -130,7 +138,7 @@ __global__ void __launch_bounds__(256) cmn_hwc2chw_kernel(const CmnDesc *__restr
       for (int p = 0; p < 4; p++) {
         const int bi = 3 * p + c;
         const uint32_t byte = (q[bi >> 2] >> ((bi & 3) * 8)) & 0xFFu;
-        const float f = mul_rn(sub_rn((float)byte, d.mean[c]), d.inv_std[c]);
+        const float f = mul_rn(sub_rn(u8_to_float(byte), d.mean[c]), d.inv_std[c]);
         v[p] = OutConv<Out>::cvt(f);
       }
       Out *orow = obase + c * plane + (int64_t)y * d.cw;

@@ -74,16 +74,24 @@ __device__ __forceinline__ uint8_t sat_u8_half_even(float x) {
 // include/dali/core/convert.h:168-176.
 __device__ __forceinline__ uint16_t float2half_ties_away(float f) {
   f = fminf(fmaxf(f, -65504.0f), 65504.0f);     // NaN propagates through fminf/fmaxf as the other operand: documented deviation
-  uint32_t bits = __float_as_uint(f);
-  uint32_t sign = (bits >> 16) & 0x8000u, e = (bits >> 23) & 0xFFu, mant = bits & 0x7FFFFFu;
+  const uint32_t bits = __float_as_uint(f);
+  const uint32_t sign = (bits >> 16) & 0x8000u, abits = bits & 0x7FFFFFFFu;
+  if (abits >= (113u << 23)) {
+    // normal half: rebias the exponent and add half an ulp of the half format (bit 12) before truncating -- the carry runs
+    // into the exponent exactly like the generic formula below (base + (mant >> 13) + ((mant >> 12) & 1))
+    return (uint16_t)(sign | ((abits - (112u << 23) + 0x1000u) >> 13));
+  }
+  const uint32_t e = abits >> 23, mant = abits & 0x7FFFFFu;
   uint32_t base, shift;
   if (e < 103u)       { base = 0u; shift = 24u; }
-  else if (e < 113u)  { base = 1u << (e - 103u); shift = 126u - e; }
-  else                { base = (e - 112u) << 10; shift = 13u; }   // e <= 142 after the clamp
-  uint32_t h = sign + base + (mant >> shift);
-  uint32_t rnd = ((mant >> (shift - 1u)) | (uint32_t)(e == 102u)) & 1u;
+  else                { base = 1u << (e - 103u); shift = 126u - e; }     // 103 <= e < 113: subnormal half
+  const uint32_t h = sign + base + (mant >> shift);
+  const uint32_t rnd = ((mant >> (shift - 1u)) | (uint32_t)(e == 102u)) & 1u;
   return (uint16_t)(h + rnd);
 }
+
+// exact u8 -> f32 on the ALU/FMA pipes (no I2F): 0x4B000000 | b is the float 2^23 + b
+__device__ __forceinline__ float u8_to_float(uint32_t b) { return __uint_as_float(0x4B000000u | b) - 8388608.0f; }
 
 template <typename T> struct OutConv;
 template <> struct OutConv<float> {

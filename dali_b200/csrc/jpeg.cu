@@ -818,8 +818,16 @@ __device__ __forceinline__ int find_image_by_coefblock(const JpegImage *im, int 
 __global__ void __launch_bounds__(128) idct_kernel(const JpegImage *__restrict__ images, int nimages, int64_t total_blocks,
                                                    const int16_t *__restrict__ coef_arena, const int16_t *__restrict__ dc_arena,
                                                    const QuantSet *__restrict__ quants, uint8_t *__restrict__ planes) {
-  for (int64_t gb = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gb < total_blocks; gb += (int64_t)gridDim.x * blockDim.x) {
-    const int ii = find_image_by_coefblock(images, nimages, gb);
+  // contiguous range of blocks per CTA: the image is searched once and then only advanced
+  __shared__ int s_first;
+  const int64_t per_cta = ((total_blocks + gridDim.x - 1) / gridDim.x + 127) / 128 * 128;
+  const int64_t b0 = (int64_t)blockIdx.x * per_cta, b1 = min(total_blocks, b0 + per_cta);
+  if (b0 >= b1) return;
+  if (threadIdx.x == 0) s_first = find_image_by_coefblock(images, nimages, b0);
+  __syncthreads();
+  int ii = s_first;
+  for (int64_t gb = b0 + threadIdx.x; gb < b1; gb += blockDim.x) {
+    while (ii + 1 < nimages && images[ii + 1].coef_off / 64 <= gb) ii++;
     const JpegImage &im = images[ii];
     const int64_t lb = gb - im.coef_off / 64;          // block index in scan (MCU) order
     const int mcu = (int)(lb / im.bpm), b = (int)(lb % im.bpm);

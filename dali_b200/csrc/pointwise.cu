@@ -67,8 +67,17 @@ __device__ __forceinline__ void store_bytes(uint8_t *p, int n, const uint8_t *b)
 
 template <typename Out>
 __global__ void __launch_bounds__(256) linear_transform_kernel(const PwDesc *__restrict__ descs, int n, int64_t total_quads) {
-  for (int64_t gq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gq < total_quads; gq += (int64_t)gridDim.x * blockDim.x) {
-    const int s = find_pw_sample(descs, n, gq);
+  // every CTA owns one contiguous range of quads: the sample is searched once per CTA and then only advanced (a per-thread
+  // binary search over thousands of frame descriptors costs more than the 4 pixels of work behind it)
+  __shared__ int s_first;
+  const int64_t per_cta = ((total_quads + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;
+  const int64_t q0 = (int64_t)blockIdx.x * per_cta, q1 = min(total_quads, q0 + per_cta);
+  if (q0 >= q1) return;
+  if (threadIdx.x == 0) s_first = find_pw_sample(descs, n, q0);
+  __syncthreads();
+  int s = s_first;
+  for (int64_t gq = q0 + threadIdx.x; gq < q1; gq += blockDim.x) {
+    while (s + 1 < n && descs[s + 1].first_quad <= gq) s++;
     const PwDesc &d = descs[s];
     const int64_t p0 = (gq - d.first_quad) * 4;
     const int np = (int)min((int64_t)4, d.npix - p0);
@@ -78,7 +87,7 @@ __global__ void __launch_bounds__(256) linear_transform_kernel(const PwDesc *__r
       uint8_t o[12];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const float v0 = b[3 * k], v1 = b[3 * k + 1], v2 = b[3 * k + 2];
+        const float v0 = u8_to_float(b[3 * k]), v1 = u8_to_float(b[3 * k + 1]), v2 = u8_to_float(b[3 * k + 2]);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           float r = mul_rn(d.m[c * 3], v0);
@@ -92,7 +101,7 @@ __global__ void __launch_bounds__(256) linear_transform_kernel(const PwDesc *__r
     } else {
       float *o = static_cast<float *>(d.out) + p0 * 3;
       for (int k = 0; k < np; k++) {
-        const float v0 = b[3 * k], v1 = b[3 * k + 1], v2 = b[3 * k + 2];
+        const float v0 = u8_to_float(b[3 * k]), v1 = u8_to_float(b[3 * k + 1]), v2 = u8_to_float(b[3 * k + 2]);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           float r = mul_rn(d.m[c * 3], v0);
@@ -113,8 +122,15 @@ __device__ __forceinline__ float dot3(float c0, float c1, float c2, float a, flo
 __global__ void __launch_bounds__(256) csc_kernel(const PwDesc *__restrict__ descs, int n, int64_t total_quads, int in_type,
                                                   int out_type) {
   const int ic = in_type == DALIB200_GRAY ? 1 : 3, oc = out_type == DALIB200_GRAY ? 1 : 3;
-  for (int64_t gq = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gq < total_quads; gq += (int64_t)gridDim.x * blockDim.x) {
-    const int s = find_pw_sample(descs, n, gq);
+  __shared__ int s_first;
+  const int64_t per_cta = ((total_quads + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;
+  const int64_t q0 = (int64_t)blockIdx.x * per_cta, q1 = min(total_quads, q0 + per_cta);
+  if (q0 >= q1) return;
+  if (threadIdx.x == 0) s_first = find_pw_sample(descs, n, q0);
+  __syncthreads();
+  int s = s_first;
+  for (int64_t gq = q0 + threadIdx.x; gq < q1; gq += blockDim.x) {
+    while (s + 1 < n && descs[s + 1].first_quad <= gq) s++;
     const PwDesc &d = descs[s];
     const int64_t p0 = (gq - d.first_quad) * 4;
     const int np = (int)min((int64_t)4, d.npix - p0);

@@ -19,7 +19,7 @@
 namespace dalib200 {
 
 constexpr int kWarpTileW = 256;     // the reference's coordinate re-anchoring period (warp_cpu.h:160)
-constexpr int kWarpTileH = 8;
+constexpr int kWarpTileH = 16;    // rows per tile: 16 threads replay coordinates while 4096 pixels are sampled by the CTA
 
 struct WarpDesc {
   const uint8_t *in;
@@ -53,12 +53,57 @@ template <typename Out> __device__ __forceinline__ Out warp_cvt(float v);
 template <> __device__ __forceinline__ float warp_cvt<float>(float v) { return v; }
 template <> __device__ __forceinline__ uint8_t warp_cvt<uint8_t>(float v) { return sat_u8_half_away(v); }
 
+// One output pixel (all channels) from its replayed source coordinate.  Interior pixels (the whole 2x2 footprint inside the
+// image) skip the per-tap bounds logic.
+template <typename Out, bool LINEAR, bool CLAMP, int CMAX>
+__device__ __forceinline__ void warp_pixel(const WarpDesc &d, float2 src, float border, int C, float *res) {
+  const uint8_t *__restrict__ in = d.in;
+  const int H = d.in_h, W = d.in_w;
+  if (!LINEAR) {
+    const int ix = (int)floorf(src.x), iy = (int)floorf(src.y);
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) if (c < C) res[c] = warp_fetch<CLAMP>(in, H, W, C, ix, iy, c, border);
+    return;
+  }
+  const float fx = sub_rn(src.x, 0.5f), fy = sub_rn(src.y, 0.5f);
+  const float flx = floorf(fx), fly = floorf(fy);
+  const int ix = (int)flx, iy = (int)fly;
+  const float qx = sub_rn(fx, flx), px = sub_rn(1.0f, qx), qy = sub_rn(fy, fly);
+  const bool interior = ix >= 0 && iy >= 0 && ix + 1 < W && iy + 1 < H;
+  const uint8_t *p0 = in + ((int64_t)iy * W + ix) * C, *p1 = p0 + (int64_t)W * C;
+#pragma unroll
+  for (int c = 0; c < CMAX; c++) {
+    if (c < C) {
+      float s00, s01, s10, s11;
+      if (interior) {
+        s00 = u8_to_float(__ldg(p0 + c)); s01 = u8_to_float(__ldg(p0 + C + c)); s10 = u8_to_float(__ldg(p1 + c)); s11 = u8_to_float(__ldg(p1 + C + c));
+      } else {
+        s00 = warp_fetch<CLAMP>(in, H, W, C, ix, iy, c, border);
+        s01 = warp_fetch<CLAMP>(in, H, W, C, ix + 1, iy, c, border);
+        s10 = warp_fetch<CLAMP>(in, H, W, C, ix, iy + 1, c, border);
+        s11 = warp_fetch<CLAMP>(in, H, W, C, ix + 1, iy + 1, c, border);
+      }
+      const float s0 = add_rn(mul_rn(s00, px), mul_rn(s01, qx));
+      const float s1 = add_rn(mul_rn(s10, px), mul_rn(s11, qx));
+      res[c] = add_rn(s0, mul_rn(sub_rn(s1, s0), qy));
+    }
+  }
+}
+
 template <typename Out, bool LINEAR, bool CLAMP>
 __global__ void __launch_bounds__(256) warp_affine_kernel(const WarpDesc *__restrict__ descs, int n, int64_t total_tiles,
                                                           float border) {
   __shared__ float2 coords[kWarpTileH][kWarpTileW];
-  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int s = find_warp_sample(descs, n, tile);
+  __shared__ int s_first;
+  // contiguous range of tiles per CTA: the sample is searched once and then only advanced
+  const int64_t per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * per_cta, t1 = min(total_tiles, t0 + per_cta);
+  if (t0 >= t1) return;
+  if (threadIdx.x == 0) s_first = find_warp_sample(descs, n, t0);
+  __syncthreads();
+  int s = s_first;
+  for (int64_t tile = t0; tile < t1; tile++) {
+    while (s + 1 < n && descs[s + 1].first_tile <= tile) s++;
     const WarpDesc &d = descs[s];
     const int64_t tl = tile - d.first_tile;
     const int ty = (int)(tl / d.tiles_x), tx = (int)(tl % d.tiles_x);
@@ -79,29 +124,32 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const WarpDesc *__rest
       }
     }
     __syncthreads();
-    // ---- stage 2: sample
+    // ---- stage 2: sample; one thread = 4 consecutive pixels of a row (u8, 3 channels: three 32-bit stores)
     const int C = d.C;
     Out *out = static_cast<Out *>(d.out);
-    for (int e = threadIdx.x; e < th * tw; e += blockDim.x) {
-      const int r = e / tw, j = e - r * tw;
-      const float2 src = coords[r][j];
-      Out *o = out + ((int64_t)(y0 + r) * d.out_w + x0 + j) * C;
-      if (!LINEAR) {
-        const int ix = (int)floorf(src.x), iy = (int)floorf(src.y);
-        for (int c = 0; c < C; c++) o[c] = warp_cvt<Out>(warp_fetch<CLAMP>(d.in, d.in_h, d.in_w, C, ix, iy, c, border));
+    const int gpr = (tw + 3) >> 2;
+    for (int e = threadIdx.x; e < th * gpr; e += blockDim.x) {
+      const int r = e / gpr, j0 = (e - r * gpr) << 2;
+      const int np = min(4, tw - j0);
+      Out *o = out + ((int64_t)(y0 + r) * d.out_w + x0 + j0) * C;
+      if (sizeof(Out) == 1 && C == 3 && np == 4 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+        uint32_t b[12];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          float res[3];
+          warp_pixel<Out, LINEAR, CLAMP, 3>(d, coords[r][j0 + k], border, 3, res);
+#pragma unroll
+          for (int c = 0; c < 3; c++) b[3 * k + c] = (uint32_t)sat_u8_half_away(res[c]);
+        }
+        uint32_t *o4 = reinterpret_cast<uint32_t *>(o);
+        o4[0] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        o4[1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+        o4[2] = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
       } else {
-        const float fx = sub_rn(src.x, 0.5f), fy = sub_rn(src.y, 0.5f);
-        const float flx = floorf(fx), fly = floorf(fy);
-        const int ix = (int)flx, iy = (int)fly;
-        const float qx = sub_rn(fx, flx), px = sub_rn(1.0f, qx), qy = sub_rn(fy, fly);
-        for (int c = 0; c < C; c++) {
-          const float s00 = warp_fetch<CLAMP>(d.in, d.in_h, d.in_w, C, ix, iy, c, border);
-          const float s01 = warp_fetch<CLAMP>(d.in, d.in_h, d.in_w, C, ix + 1, iy, c, border);
-          const float s10 = warp_fetch<CLAMP>(d.in, d.in_h, d.in_w, C, ix, iy + 1, c, border);
-          const float s11 = warp_fetch<CLAMP>(d.in, d.in_h, d.in_w, C, ix + 1, iy + 1, c, border);
-          const float s0 = add_rn(mul_rn(s00, px), mul_rn(s01, qx));
-          const float s1 = add_rn(mul_rn(s10, px), mul_rn(s11, qx));
-          o[c] = warp_cvt<Out>(add_rn(s0, mul_rn(sub_rn(s1, s0), qy)));
+        for (int k = 0; k < np; k++) {
+          float res[8];
+          warp_pixel<Out, LINEAR, CLAMP, 8>(d, coords[r][j0 + k], border, C, res);
+          for (int c = 0; c < C; c++) o[k * C + c] = warp_cvt<Out>(res[c]);
         }
       }
     }

@@ -88,7 +88,7 @@ def lib():
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise DaliB200Error(f"{LIB_PATH} is missing: run `python -m dali_b200.build` (there is no CPU fallback)")
-        _lib = C.CDLL(LIB_PATH)
+        _lib = C.CDLL(os.environ.get("DALIB200_LIB", LIB_PATH))      # override: A/B experiments with an older build
         _lib.dalib200GetLastError.restype = C.c_char_p
         _lib.dalib200GetLaunchCount.restype = C.c_uint64
         _lib.dalib200JpegPlanStagedBytes.restype = C.c_size_t

@@ -349,8 +349,8 @@ struct HuffCtx {
   int log2_sub;            // log2 of the subsequence size in BITS
   int32_t *status;         // per image: 0 ok, 1 = block count mismatch (corrupt stream)
   // live chains of the synchronisation (H2a): record = (bit position, c | z << 8, target subsequence, image)
-  uint4 *chains[3];        // [0] = chains that leave their sync block in round 1, [1] / [2] = ping-pong lists of rounds >= 2
-  uint32_t *chain_count;   // [3]
+  uint4 *chains[4];        // [0] = chains that leave their sync block in round 1, [1..3] = rotating lists of rounds >= 2
+  uint32_t *chain_count;   // [4]
 };
 
 __device__ __forceinline__ uint32_t tbl_word(const JpegImage &im, int b) {
@@ -365,10 +365,13 @@ struct SyncSmem {
   uint8_t *zig, *col_cont;
   HuffSlow *slow;                // shared-memory copy of the canonical tables (the long-code path is latency critical)
 };
-constexpr int kLookAheadCols = 2;             // staged behind the sync block: a block (<= 208 bytes) may run that far past the last column
-__host__ __device__ inline size_t sync_sw_words(int log2_sub) { return (size_t)(kSyncThreads + kLookAheadCols) << (log2_sub - 5); }
+// Columns staged behind the sync block: 256 bytes worth.  A block is at most 63 x 26 + 20 bits = 208 bytes long and the
+// write pass completes the last block of the last column past the end of the sync block.
+constexpr int kMaxLookAheadCols = 8;          // 32-byte subsequences
+__host__ __device__ inline int look_ahead_cols(int log2_sub) { return 256 >> (log2_sub - 3); }
+__host__ __device__ inline size_t sync_sw_words(int log2_sub) { return (size_t)(kSyncThreads + look_ahead_cols(log2_sub)) << (log2_sub - 5); }
 __host__ __device__ inline size_t sync_smem_bytes(int log2_sub, bool with_block_buffers) {
-  return kLutWords * 4 + sync_sw_words(log2_sub) * 4 + kSyncThreads * 8 /*exit*/ + (kSyncThreads + kLookAheadCols) * 8 /*colptr*/ +
+  return kLutWords * 4 + sync_sw_words(log2_sub) * 4 + kSyncThreads * 8 /*exit*/ + (kSyncThreads + kMaxLookAheadCols) * 8 /*colptr*/ +
          kSyncThreads * 4 * 2 /*cnt, col_end*/ + 16 * 4 /*tbl*/ + 64 /*zig*/ + kSyncThreads /*col_cont*/ + 4 * sizeof(HuffSlow) +
          (with_block_buffers ? (size_t)kSyncThreads * 128 : 0) /*block buffers (H3)*/;
 }
@@ -378,7 +381,7 @@ __device__ __forceinline__ SyncSmem carve_sync_smem(uint32_t *base, int log2_sub
   s.sw = s.lut + kLutWords;
   s.exitst = reinterpret_cast<uint64_t *>(s.sw + sync_sw_words(log2_sub));     // both word counts are multiples of 8
   s.colptr = reinterpret_cast<const uint8_t **>(s.exitst + kSyncThreads);
-  s.cnt = reinterpret_cast<uint32_t *>(s.colptr + kSyncThreads + kLookAheadCols);
+  s.cnt = reinterpret_cast<uint32_t *>(s.colptr + kSyncThreads + kMaxLookAheadCols);
   s.col_end = s.cnt + kSyncThreads;
   s.tbl = s.col_end + kSyncThreads;
   s.zig = reinterpret_cast<uint8_t *>(s.tbl + 16);
@@ -421,11 +424,12 @@ __device__ __forceinline__ SubGeom sync_block_prologue(const HuffCtx &cx, const 
   sm.colptr[threadIdx.x] = ptr;
   sm.col_end[threadIdx.x] = min((sg.jl + 1) << cx.log2_sub, sg.clean_bits);
   sm.col_cont[threadIdx.x] = sg.valid && sg.jl + 1 < sg.nsub_eff;             // the unit continues behind this column
+  const int la_cols = look_ahead_cols(cx.log2_sub);
   if (threadIdx.x == kSyncThreads - 1)
-    for (int q = 1; q <= kLookAheadCols; q++) sm.colptr[kSyncThreads - 1 + q] = ptr ? ptr + ((size_t)q << (cx.log2_sub - 3)) : nullptr;
+    for (int q = 1; q <= la_cols; q++) sm.colptr[kSyncThreads - 1 + q] = ptr ? ptr + ((size_t)q << (cx.log2_sub - 3)) : nullptr;
   __syncthreads();
   const int cpc = 1 << (cx.log2_sub - 7);                    // 16-byte chunks per column
-  for (int ch = threadIdx.x; ch < (kSyncThreads + kLookAheadCols) * cpc; ch += blockDim.x) {
+  for (int ch = threadIdx.x; ch < (kSyncThreads + la_cols) * cpc; ch += blockDim.x) {
     const int col = ch / cpc, o = ch - col * cpc;
     const uint8_t *p = sm.colptr[col];
     if (p) {
@@ -565,14 +569,17 @@ __global__ void __launch_bounds__(kTailThreads) huff_sync_tail_kernel(HuffCtx cx
   // round 1 of the chains that left their sync block: survivors join list 1 (round 2)
   for (uint32_t i = gtid, n = cx.chain_count[0]; i < n; i += gsize) tail_step(cx, cx.chains[0][i], 1, s_lut, s_slow, s_table_set, col);
   grid.sync();
+  // Three rotating lists: round r reads list `cur`, appends to `nxt`, and the third one -- read in the previous round, appended
+  // to in the next -- is reset meanwhile.  (With two lists the reset of the list just read would race with the appends of
+  // the next round, which start right behind the grid barrier.)
   int cur = 1;
   for (;;) {
     const uint32_t n = cx.chain_count[cur];
     if (n == 0) break;
-    const int nxt = cur == 1 ? 2 : 1;
+    const int nxt = cur == 3 ? 1 : cur + 1, idle = nxt == 3 ? 1 : nxt + 1;
+    if (gtid == 0) cx.chain_count[idle] = 0;
     for (uint32_t i = gtid; i < n; i += gsize) tail_step(cx, cx.chains[cur][i], nxt, s_lut, s_slow, s_table_set, col);
-    grid.sync();                                             // everybody has read chain_count[cur] and pushed its survivors
-    if (gtid == 0) cx.chain_count[cur] = 0;                  // reused two rounds later, after the next grid.sync
+    grid.sync();                                             // everybody has read chain_count[cur] and appended its survivors
     cur = nxt;
   }
 }
@@ -645,7 +652,7 @@ __global__ void __launch_bounds__(kSyncThreads) huff_write_kernel(HuffCtx cx) {
     const uint32_t ublk = (uint32_t)(u.slot_base >> 6);
     blk0 = ublk + cx.s_n[sg.g];
     blk_limit = ublk + (uint32_t)(u.nslots >> 6);
-    active = pos < end;
+    active = pos < end && blk0 < blk_limit;                  // pad bits behind the last block of a unit are not symbols
   }
   bool own = z == 0;                                          // a block starts exactly at the entry: it is ours
   BitWindow<SmemSrc> win;
@@ -1354,7 +1361,8 @@ struct dalib200JpegPlan {
   uint32_t *d_chunk = nullptr; size_t d_chunk_cap = 0;
   uint32_t *d_unit_len = nullptr; size_t d_unit_cap = 0;
   uint64_t *d_state = nullptr; uint32_t *d_n = nullptr; size_t d_sub_cap = 0;
-  uint4 *d_chain0 = nullptr, *d_chain1 = nullptr, *d_chain2 = nullptr; size_t d_chain0_cap = 0, d_chain1_cap = 0, d_chain2_cap = 0;
+  uint4 *d_chain0 = nullptr, *d_chain1 = nullptr, *d_chain2 = nullptr, *d_chain3 = nullptr;
+  size_t d_chain0_cap = 0, d_chain1_cap = 0, d_chain2_cap = 0, d_chain3_cap = 0;
   uint32_t *d_chain_count = nullptr; size_t d_chain_count_cap = 0;
   int tail_grid = 0;
   int16_t *d_coef = nullptr; size_t d_coef_cap = 0;
@@ -1413,7 +1421,7 @@ int dalib200JpegPlanDestroy(dalib200JpegPlan *p) {
   if (p->h_stage) cudaFreeHost(p->h_stage);
   if (p->h_images) cudaFreeHost(p->h_images);
   void *bufs[] = { p->d_stage, p->d_clean, p->d_chunk, p->d_unit_len, p->d_state, p->d_n, p->d_coef, p->d_dc, p->d_planes, p->d_status,
-                   p->d_chain0, p->d_chain1, p->d_chain2, p->d_chain_count };
+                   p->d_chain0, p->d_chain1, p->d_chain2, p->d_chain3, p->d_chain_count };
   for (void *b : bufs) if (b) cudaFree(b);
   delete p;
   return DALIB200_SUCCESS;
@@ -1724,7 +1732,8 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   if ((rc = GrowDevice(p->d_chain0, p->d_chain0_cap, (size_t)p->total_blocks_sync + 1))) return rc;
   if ((rc = GrowDevice(p->d_chain1, p->d_chain1_cap, (size_t)p->total_subseq + 1))) return rc;
   if ((rc = GrowDevice(p->d_chain2, p->d_chain2_cap, (size_t)p->total_subseq + 1))) return rc;
-  if ((rc = GrowDevice(p->d_chain_count, p->d_chain_count_cap, (size_t)4))) return rc;
+  if ((rc = GrowDevice(p->d_chain3, p->d_chain3_cap, (size_t)p->total_subseq + 1))) return rc;
+  if ((rc = GrowDevice(p->d_chain_count, p->d_chain_count_cap, (size_t)8))) return rc;
   if ((rc = GrowDevice(p->d_coef, p->d_coef_cap, (size_t)p->total_coefs + 64))) return rc;
   if ((rc = GrowDevice(p->d_dc, p->d_dc_cap, (size_t)p->total_coefs / 64 + 64))) return rc;
   if ((rc = GrowDevice(p->d_planes, p->d_planes_cap, (size_t)p->total_plane_bytes + 64))) return rc;
@@ -1759,7 +1768,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   // the clean stream must be zero-padded behind every unit (the bit reader peeks ahead)
   DB_CUDA(cudaMemsetAsync(p->d_clean, 0, p->clean_bytes + 1024, s));
   DB_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * p->n, s));
-  DB_CUDA(cudaMemsetAsync(p->d_chain_count, 0, sizeof(uint32_t) * 4, s));
+  DB_CUDA(cudaMemsetAsync(p->d_chain_count, 0, sizeof(uint32_t) * 8, s));
   {
     const int grid = (int)std::min<uint32_t>(p->nchunks, (uint32_t)sms * 16);
     { ProfScope ps_("jpeg_unstuff_count", s); unstuff_count_kernel<<<grid, 256, 0, s>>>(d_raw, d_units, nunits, p->nchunks, p->d_chunk); }
@@ -1771,7 +1780,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   cx.images = d_images; cx.nimages = p->n; cx.block_image = reinterpret_cast<const int32_t *>(p->d_stage + p->off_blkimg); cx.units = d_units; cx.unit_clean_len = p->d_unit_len; cx.tables = d_tables;
   cx.clean = p->d_clean; cx.s_state = p->d_state; cx.s_n = p->d_n; cx.coef = p->d_coef; cx.dc = p->d_dc; cx.log2_sub = p->log2_sub;
   cx.status = p->d_status;
-  cx.chains[0] = p->d_chain0; cx.chains[1] = p->d_chain1; cx.chains[2] = p->d_chain2; cx.chain_count = p->d_chain_count;
+  cx.chains[0] = p->d_chain0; cx.chains[1] = p->d_chain1; cx.chains[2] = p->d_chain2; cx.chains[3] = p->d_chain3; cx.chain_count = p->d_chain_count;
   const size_t hsmem = sync_smem_bytes(p->log2_sub, false), wsmem = sync_smem_bytes(p->log2_sub, true);
   if (!p->smem_opted) {
     DB_CUDA(cudaFuncSetAttribute(huff_sync_intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_smem_bytes(kMaxLog2Sub, false)));

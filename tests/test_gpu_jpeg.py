@@ -133,3 +133,46 @@ def test_unsupported_streams_fail_loudly():
         g.jpeg_decode([prog.tobytes()])
     with pytest.raises(capi.DaliB200Error):
         g.jpeg_decode([b"\xff\xd8\xff\xd9"])
+
+
+def test_mixed_huffman_tables_and_extreme_content():
+    """One batch mixing the standard tables with per-image OPTIMISED tables (several table sets: the grid-wide
+    synchronisation rounds keep only one set in shared memory), flat images (one byte per block: thousands of blocks per
+    subsequence), noise at q100 (long codes, blocks longer than a subsequence), tiny and restart-interval streams."""
+    import cv2
+    import gpu_helpers as g
+    rng = np.random.default_rng(21)
+    imgs = [g.synth_image(300, 420, 30), g.synth_image(211, 333, 31),
+            np.full((256, 384, 3), 128, np.uint8), np.zeros((64, 1024, 3), np.uint8),
+            rng.integers(0, 256, (120, 200, 3)).astype(np.uint8), rng.integers(0, 256, (64, 64, 3)).astype(np.uint8),
+            g.synth_image(17, 9, 32), g.synth_image(640, 640, 33)]
+    streams = []
+    for i, im in enumerate(imgs):
+        params = [cv2.IMWRITE_JPEG_QUALITY, [90, 75, 90, 50, 100, 98, 90, 85][i]]
+        if i % 2 == 1:
+            params += [cv2.IMWRITE_JPEG_OPTIMIZE, 1]
+        if i == 7:
+            params += [cv2.IMWRITE_JPEG_RST_INTERVAL, 3]
+        if i == 4:
+            params += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
+        ok, enc = cv2.imencode(".jpg", im, params)
+        assert ok
+        streams.append(enc.tobytes())
+    for order in (list(range(8)), [7, 5, 3, 1, 6, 4, 2, 0]):
+        outs, status = g.jpeg_decode([streams[k] for k in order])
+        assert status == [0] * 8
+        for k, o in zip(order, outs):
+            assert np.array_equal(o, po.jpeg_decode(streams[k])), f"image {k}"
+
+
+def test_decode_is_deterministic_over_repeated_batches():
+    """The self-synchronisation uses atomics for its work lists; the RESULT must not depend on their order."""
+    import gpu_helpers as g
+    streams = [_enc(g.synth_image(540, 960, 50 + i), 90) for i in range(24)]
+    want = [po.jpeg_decode(s) for s in streams]
+    plan = capi.Plan("Jpeg", 24)
+    for rep in range(5):
+        outs, status = g.jpeg_decode(streams, plan=plan)
+        assert status == [0] * 24
+        for i, (o, w) in enumerate(zip(outs, want)):
+            assert np.array_equal(o, w), (rep, i)

@@ -332,9 +332,16 @@ def main():
         dur = kernels[dom]["ms_per_step"] / max(1.0, kernels[dom]["launches_per_step"]) / 1e3
         per_launch = alg.get(dom, 0) * batch
         ach = per_launch / dur / 1e9 if dur > 0 else 0.0
+        traffic, traffic_src = None, None
+        try:       # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture (per image)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_dram_traffic_v5.json")))
+            traffic = tj["kernels"][dom]["dram_bytes_per_image"] * batch
+            traffic_src = "profiles/r1_ncu_dram_traffic_v5.json (ncu --set full at batch 64, per image x batch)"
+        except Exception:
+            pass
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": None, "peak_source": peak_src, "share_of_step": kernels[dom]["ms_per_step"] / ms_per_step,
-                    "algorithmic_bytes_per_launch": per_launch}
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "share_of_step": kernels[dom]["ms_per_step"] / ms_per_step, "algorithmic_bytes_per_launch": per_launch}
     op_gbs = (J + ALG_DECODE + ALG_RESIZE + ALG_CMN) * batch / (ms_per_step / 1e3) / 1e9
 
     # ---- end to end through the PUBLIC API (pipeline_def + fn.*): host buffers in, per step: header parse + pinned staging +
@@ -417,6 +424,25 @@ def main():
             secondary = secondary_workloads(hbm_peak, flush, max(3, args.steps // 2), 2)
         except Exception as ex:           # the headline line must not depend on the secondary workloads
             secondary = {"error": repr(ex)}
+    # ---- optional consumer-side collective (BASELINE configs[4]): all-gather of the fp16 NCHW output of every rank over NVLink.
+    #      Not part of `value` / `e2e` (each rank keeps its shard for training-style consumption); reported for the consumers that
+    #      need the full batch.
+    allgather = None
+    if world > 1:
+        from dali_b200.sharding import all_gather_output as all_gather_batch
+        out_local = pipe.launch()
+        torch.cuda.synchronize()
+        for _ in range(2):
+            full = all_gather_batch(out_local)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a, b in evs:
+            a.record(); full = all_gather_batch(out_local); b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([float(np.median([a.elapsed_time(b) for a, b in evs]))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gb = full.numel() * full.element_size() / 1e9
+        allgather = {"ms": float(t.item()), "bytes_gathered_per_rank": int(full.numel() * full.element_size()),
+                     "bus_GBps": gb * (world - 1) / world / (float(t.item()) / 1e3), "shape": list(full.shape)}
     if rank == 0:
         line = {"metric": "images/sec decode+resize+CMN (batch 256, 1080p JPEG)", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -425,7 +451,7 @@ def main():
                                                                                    mean_jpeg_bytes=J),
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "kernels": kernels, "op_boundary_GBps": op_gbs, "op_boundary_frac_of_hbm": op_gbs / hbm_peak,
-                "wall_s_timed_region": t_wall, "checksum": chk, "secondary": secondary}
+                "wall_s_timed_region": t_wall, "checksum": chk, "secondary": secondary, "allgather_fp16_nchw": allgather}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -198,12 +198,20 @@ def secondary_workloads(hbm_peak, flush, steps, warmup):
     spec0 = po.spectrogram(clips[7], 1024, 1024, 256, 2)
     mel0 = po.mel_filter_bank(spec0, 128, 16000.0, 0.0, 8000.0)
     gs, gm = au.spectra[7].cpu().numpy(), au.output[7].cpu().numpy()
+    # the same clips through the optional tensor-core mel path (dense TF32x3 GEMM, mma.sync): tolerance path, reported beside the default
+    capi.check(capi.lib().dalib200MelPlanSetTensorCores(au.mel.handle, 1))
+    ms_tc, kern_tc = timed(lambda: au.launch(dclips))
+    gm_tc = au.output[7].cpu().numpy()
+    capi.check(capi.lib().dalib200MelPlanSetTensorCores(au.mel.handle, 0))
     out["c4_audio"] = {"workload": "C4: spectrogram(nfft 1024, window 1024, step 256, power 2) -> mel_filter_bank(128, sr 16 kHz), 64 clips x 10 s",
                        "value": nclip * nwin / (ms / 1e3), "unit": "audio frames/s", "ms_per_step": ms, "kernels_ms": kern,
                        "op_boundary_GBps": alg * nclip / (ms / 1e3) / 1e9, "op_boundary_frac_of_hbm": alg * nclip / (ms / 1e3) / 1e9 / hbm_peak,
                        "stft_max_abs_err_over_max": float(np.abs(gs - spec0).max() / max(1e-30, np.abs(spec0).max())),
                        "stft_stated_tolerance": 2e-4,
-                       "mel_max_rel_err": float(np.abs(gm - mel0).max() / max(1e-30, np.abs(mel0).max()))}
+                       "mel_max_rel_err": float(np.abs(gm - mel0).max() / max(1e-30, np.abs(mel0).max())),
+                       "mel_tensor_core_path": {"kernel_ms": kern_tc.get("mel_filter_bank_mma"), "step_ms": ms_tc,
+                                                "max_rel_diff_vs_banded_kernel": float(np.abs(gm_tc - gm).max() / max(1e-30, np.abs(gm).max())),
+                                                "note": "mma.sync m16n8k8 TF32, 3-term split, FP32 accumulate; opt-in (dalib200MelPlanSetTensorCores)"}}
     return out
 
 

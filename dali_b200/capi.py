@@ -31,7 +31,7 @@ EXPORTS = [
     "dalib200PointwiseLaunch", "dalib200ColorTwistMatrix",
     "dalib200SpectrogramPlanCreate", "dalib200SpectrogramPlanDestroy", "dalib200SpectrogramPlanSetup",
     "dalib200SpectrogramNumWindows", "dalib200SpectrogramLaunch", "dalib200HannWindow",
-    "dalib200MelPlanCreate", "dalib200MelPlanDestroy", "dalib200MelPlanSetup", "dalib200MelLaunch",
+    "dalib200MelPlanCreate", "dalib200MelPlanDestroy", "dalib200MelPlanSetup", "dalib200MelLaunch", "dalib200MelPlanSetTensorCores",
 ]
 
 

@@ -151,6 +151,96 @@ __global__ void __launch_bounds__(128) mel_kernel(const MelDesc *__restrict__ de
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Optional tensor-core path of MelFilterBank (dalib200MelPlanSetTensorCores): the banded sums as ONE dense GEMM
+//   out[nfilter x nwin] = W[nfilter x nbin] * S[nbin x nwin]            per sample
+// on the tensor cores (mma.sync m16n8k8, TF32 inputs, FP32 accumulate).  FP32 accuracy is kept with the 3-term split
+// a = a_hi + a_lo (both TF32): a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, error ~2^-21 relative.  The summation ORDER differs
+// from the reference CPU kernel, so this path is a tolerance path (tests: 8e-6 of the row maximum); the default banded kernel
+// above stays bit exact.  A CTA = 128 filters x 64 windows, K streamed in chunks of 32 bins through shared memory (row pitches
+// 36 / 72 floats: the m16n8k8 fragment loads are bank-conflict free); chunks outside the filters' bands are skipped.
+constexpr int kMmM = 128, kMmN = 64, kMmK = 32, kMmWP = kMmK + 4, kMmSP = kMmN + 8;
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// dense: [mpad][kpad] row-major, zero padded; kr: per 128-row block {first chunk, end chunk}
+__global__ void __launch_bounds__(256) mel_mma_kernel(const MelDesc *__restrict__ descs, int n, int64_t total_items, int nfilter, int nbin,
+                                                      int kpad, const float *__restrict__ dense, const int2 *__restrict__ kr) {
+  __shared__ __align__(16) float s_w[kMmM * kMmWP];
+  __shared__ __align__(16) float s_s[kMmK * kMmSP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int mblocks = (nfilter + kMmM - 1) / kMmM;
+  for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const int s = find_mel_sample(descs, n, item);
+    const MelDesc &d = descs[s];
+    const int64_t li = item - d.first_item;
+    const int mb = (int)(li % mblocks);
+    const int64_t t0 = (li / mblocks) * kMmN;
+    float acc[kMmN / 8][4];
+#pragma unroll
+    for (int j = 0; j < kMmN / 8; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+    const int2 range = kr[mb];
+    for (int kc = range.x; kc < range.y; kc++) {
+      const int k0 = kc * kMmK;
+      // W chunk: 128 x 32 (float4, coalesced per row)
+      for (int e = threadIdx.x; e < kMmM * kMmK / 4; e += blockDim.x) {
+        const int r = e / (kMmK / 4), c4 = e % (kMmK / 4);
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(dense + (size_t)(mb * kMmM + r) * kpad + k0) + c4);
+        *reinterpret_cast<float4 *>(s_w + r * kMmWP + 4 * c4) = v;
+      }
+      // S chunk: 32 bins x 64 windows (zero outside the spectrogram)
+      for (int e = threadIdx.x; e < kMmK * kMmN; e += blockDim.x) {
+        const int r = e / kMmN, c = e % kMmN;
+        const int64_t t = t0 + c;
+        s_s[r * kMmSP + c] = (k0 + r < nbin && t < d.nwin) ? __ldg(d.in + (int64_t)(k0 + r) * d.nwin + t) : 0.0f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int ks = 0; ks < kMmK / 8; ks++) {
+        const float *wr = s_w + (warp * 16 + gid) * kMmWP + ks * 8 + tig;
+        const float af[4] = { wr[0], wr[8 * kMmWP], wr[4], wr[8 * kMmWP + 4] };
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { ah[q] = to_tf32(af[q]); al[q] = to_tf32(af[q] - __uint_as_float(ah[q])); }
+#pragma unroll
+        for (int j = 0; j < kMmN / 8; j++) {
+          const float *sr = s_s + (ks * 8 + tig) * kMmSP + j * 8 + gid;
+          const float bf[2] = { sr[0], sr[4 * kMmSP] };
+          uint32_t bh[2], bl[2];
+#pragma unroll
+          for (int q = 0; q < 2; q++) { bh[q] = to_tf32(bf[q]); bl[q] = to_tf32(bf[q] - __uint_as_float(bh[q])); }
+          mma_tf32(acc[j], al, bh);
+          mma_tf32(acc[j], ah, bl);
+          mma_tf32(acc[j], ah, bh);
+        }
+      }
+      __syncthreads();
+    }
+    const int m0 = mb * kMmM + warp * 16 + gid;
+#pragma unroll
+    for (int j = 0; j < kMmN / 8; j++) {
+      const int64_t t = t0 + j * 8 + 2 * tig;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int m = m0 + 8 * h;
+        if (m < nfilter) {
+          if (t < d.nwin) d.out[(int64_t)m * d.nwin + t] = acc[j][2 * h];
+          if (t + 1 < d.nwin) d.out[(int64_t)m * d.nwin + t + 1] = acc[j][2 * h + 1];
+        }
+      }
+    }
+  }
+}
+
 }  // namespace dalib200
 
 using namespace dalib200;  // NOLINT
@@ -179,6 +269,12 @@ struct dalib200MelPlan {
   DescArena tables;          // ends | w_up | w_down
   std::vector<int32_t> h_ends; std::vector<float> h_up, h_down;
   bool tables_dirty = true;
+  bool tensor_cores = false;     // dense TF32x3 GEMM on the tensor cores instead of the bit-exact banded sums
+  DescArena dense;               // [mpad][kpad] weights | int2 chunk range per 128-filter block
+  bool dense_dirty = true;
+  int kpad = 0, mpad = 0;
+  int64_t total_items_mma = 0;
+  std::vector<int64_t> first_item_mma;
   dalib200MelArgs args{};
   cudaEvent_t uploaded = nullptr;
   bool pending = false;
@@ -397,8 +493,14 @@ int dalib200MelPlanCreate(dalib200MelPlan **plan, int max_batch) {
 int dalib200MelPlanDestroy(dalib200MelPlan *p) {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
-  p->arena.Free(); p->tables.Free();
+  p->arena.Free(); p->tables.Free(); p->dense.Free();
   delete p;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200MelPlanSetTensorCores(dalib200MelPlan *p, int enable) {
+  DB_CHECK_ARG(p, "MelPlanSetTensorCores: null plan");
+  p->tensor_cores = enable != 0;
   return DALIB200_SUCCESS;
 }
 
@@ -417,7 +519,7 @@ int dalib200MelPlanSetup(dalib200MelPlan *p, const dalib200MelArgs *args, int nb
     if (a.htk) BuildMel<Htk>(a, nfft, p->h_ends, p->h_up, p->h_down);
     else BuildMel<Slaney>(a, nfft, p->h_ends, p->h_up, p->h_down);
     p->args = a; p->nbin = nbin; p->nfilter = a.nfilter;
-    p->tables_dirty = true;
+    p->tables_dirty = true; p->dense_dirty = true;
   }
   p->descs.assign(n, MelDesc());
   int64_t items = 0;
@@ -426,6 +528,13 @@ int dalib200MelPlanSetup(dalib200MelPlan *p, const dalib200MelArgs *args, int nb
     p->descs[i].nwin = nwin[i]; p->descs[i].first_item = items;
     items += (int64_t)a.nfilter * ((nwin[i] + 127) / 128);
   }
+  p->first_item_mma.assign(n, 0);
+  int64_t items2 = 0;
+  for (int i = 0; i < n; i++) {
+    p->first_item_mma[i] = items2;
+    items2 += (int64_t)((a.nfilter + kMmM - 1) / kMmM) * ((nwin[i] + kMmN - 1) / kMmN);
+  }
+  p->total_items_mma = items2;
   p->n = n; p->total_items = items;
   return DALIB200_SUCCESS;
 }
@@ -447,9 +556,45 @@ int dalib200MelLaunch(dalib200MelPlan *p, const void *const *in_ptrs, void *cons
     p->tables_dirty = false;
   }
   auto *hd = reinterpret_cast<MelDesc *>(p->arena.host);
-  for (int i = 0; i < p->n; i++) { hd[i] = p->descs[i]; hd[i].in = static_cast<const float *>(in_ptrs[i]); hd[i].out = static_cast<float *>(out_ptrs[i]); }
+  for (int i = 0; i < p->n; i++) {
+    hd[i] = p->descs[i]; hd[i].in = static_cast<const float *>(in_ptrs[i]); hd[i].out = static_cast<float *>(out_ptrs[i]);
+    if (p->tensor_cores) hd[i].first_item = p->first_item_mma[i];
+  }
   int rc = p->arena.Upload(sizeof(MelDesc) * p->n, stream);
   if (rc) return rc;
+  if (p->tensor_cores) {
+    const int mblocks = (p->nfilter + kMmM - 1) / kMmM;
+    if (p->dense_dirty) {
+      p->kpad = (p->nbin + kMmK - 1) / kMmK * kMmK; p->mpad = mblocks * kMmM;
+      const size_t wbytes = (size_t)p->mpad * p->kpad * 4, total = wbytes + sizeof(int2) * mblocks;
+      rc = p->dense.Reserve(total);
+      if (rc) return rc;
+      float *w = reinterpret_cast<float *>(p->dense.host);
+      memset(w, 0, wbytes);
+      for (int m = 0; m < p->nfilter; m++) {
+        for (int b = p->h_ends[m]; b < p->h_ends[m + 1]; b++) w[(size_t)m * p->kpad + b] = p->h_up[b];
+        for (int b = p->h_ends[m + 1]; b < p->h_ends[m + 2]; b++) w[(size_t)m * p->kpad + b] = p->h_down[b];
+      }
+      int2 *kr = reinterpret_cast<int2 *>(p->dense.host + wbytes);
+      for (int mb = 0; mb < mblocks; mb++) {
+        const int m0 = mb * kMmM, m1 = std::min(p->nfilter, m0 + kMmM);
+        kr[mb] = make_int2(p->h_ends[m0] / kMmK, (p->h_ends[m1 + 1] + kMmK - 1) / kMmK);
+      }
+      rc = p->dense.Upload(total, stream);
+      if (rc) return rc;
+      p->dense_dirty = false;
+    }
+    DB_CUDA(cudaEventRecord(p->uploaded, stream));
+    p->pending = true;
+    const int grid = (int)std::min<int64_t>(p->total_items_mma, (int64_t)NumSMs() * 8);
+    ProfScope ps_("mel_filter_bank_mma", stream);
+    mel_mma_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const MelDesc *>(p->arena.dev), p->n, p->total_items_mma, p->nfilter, p->nbin,
+                                             p->kpad, reinterpret_cast<const float *>(p->dense.dev),
+                                             reinterpret_cast<const int2 *>(p->dense.dev + (size_t)p->mpad * p->kpad * 4));
+    CountLaunch();
+    DB_CUDA(cudaGetLastError());
+    return DALIB200_SUCCESS;
+  }
   DB_CUDA(cudaEventRecord(p->uploaded, stream));
   p->pending = true;
   const int grid = (int)std::min<int64_t>(p->total_items, (int64_t)NumSMs() * 32);

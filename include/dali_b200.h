@@ -220,6 +220,10 @@ int dalib200MelPlanCreate(dalib200MelPlan **plan, int max_batch);
 int dalib200MelPlanDestroy(dalib200MelPlan *plan);
 /* input spectrograms are [nbin][nwin[i]] f32 ("ft"); outputs [nfilter][nwin[i]] */
 int dalib200MelPlanSetup(dalib200MelPlan *plan, const dalib200MelArgs *args, int nbin, int n, const int64_t *nwin);
+/* enable != 0: run the filter bank as one dense GEMM on the tensor cores (mma.sync TF32, 3-term split, FP32 accumulate).
+ * Tolerance path (summation order differs from the reference CPU kernel, ~1e-6 relative); the default (0) is the bit-exact
+ * banded kernel. */
+int dalib200MelPlanSetTensorCores(dalib200MelPlan *plan, int enable);
 int dalib200MelLaunch(dalib200MelPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
 
 #ifdef __cplusplus

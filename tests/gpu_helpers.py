@@ -205,12 +205,14 @@ def spectrogram(sigs, nfft=None, window_length=512, window_step=256, power=2, ce
     return [o.cpu().numpy() for o in outs]
 
 
-def mel_filter_bank(specs, nfilter=128, sample_rate=44100.0, freq_low=0.0, freq_high=0.0, mel_formula="slaney", normalize=True):
+def mel_filter_bank(specs, nfilter=128, sample_rate=44100.0, freq_low=0.0, freq_high=0.0, mel_formula="slaney", normalize=True,
+                    tensor_cores=False):
     torch = _torch()
     n = len(specs)
     args = capi.MelArgs(nfilter, sample_rate, freq_low, freq_high, int(mel_formula == "htk"), int(bool(normalize)))
     nwin = (C.c_int64 * n)(*[int(s.shape[1]) for s in specs])
     plan = capi.Plan("Mel", max(n, 1))
+    capi.check(capi.lib().dalib200MelPlanSetTensorCores(plan.handle, int(tensor_cores)))
     capi.check(capi.lib().dalib200MelPlanSetup(plan.handle, C.byref(args), int(specs[0].shape[0]), n, nwin))
     din = to_dev([np.ascontiguousarray(s, np.float32) for s in specs])
     outs = [torch.empty((nfilter, s.shape[1]), dtype=torch.float32, device="cuda") for s in specs]

@@ -152,6 +152,22 @@ def test_mel_filter_bank_bit_exact():
             assert np.array_equal(bits(o), bits(po.mel_filter_bank(s, nf, sr, fl, fh, formula, norm))), (nf, formula)
 
 
+def test_mel_filter_bank_tensor_core_path():
+    """The optional dense-GEMM path on the tensor cores (TF32 x 3 split, FP32 accumulate): same weights, different summation
+    order -> tolerance 8e-6 of the row maximum (the fp32 re-association error of a ~100-term banded sum), incl. nfilter not a multiple of 16 / above 128 and
+    window counts that are not multiples of the 64-column tile."""
+    import gpu_helpers as g
+    rng = np.random.default_rng(64)
+    specs = [po.spectrogram(_clip(rng, n), nfft=1024, window_length=1024, window_step=256) for n in (16000, 5000, 160000, 700)]
+    for (nf, sr, fl, fh, formula, norm) in [(128, 16000.0, 0.0, 8000.0, "slaney", True), (80, 16000.0, 20.0, 7600.0, "htk", False),
+                                            (200, 44100.0, 0.0, 0.0, "slaney", True), (13, 22050.0, 100.0, 9000.0, "htk", True)]:
+        got = g.mel_filter_bank(specs, nf, sr, fl, fh, formula, norm, tensor_cores=True)
+        for s, o in zip(specs, got):
+            want = po.mel_filter_bank(s, nf, sr, fl, fh, formula, norm)
+            tol = 8e-6 * np.abs(want).max(axis=1, keepdims=True) + 1e-30
+            assert o.shape == want.shape and np.all(np.abs(o - want) <= tol), (nf, formula, float(np.abs(o - want).max()))
+
+
 def test_audio_golden(golden_dir):
     import gpu_helpers as g
     gz = np.load(os.path.join(golden_dir, "audio_ref.npz"))

@@ -19,6 +19,7 @@
 #include <cmath>
 #include <limits>
 #include "dali.h"
+#include <cstdlib>
 #include "../../include/dali_b200.h"
 
 namespace dali {
@@ -876,6 +877,8 @@ class MelFilterBankGPU : public Operator<GPUBackend> {
     DALI_ENFORCE(f == "slaney" || f == "htk", "Unsupported mel_formula value \"", f, "\". Supported values are: \"slaney\", \"htk\"");
     args_.htk = f == "htk";
     CheckStatus(dalib200MelPlanCreate(&plan_, max_batch_size_), "MelFilterBank");
+    // opt-in: the dense-GEMM tensor-core path (tolerance ~1e-6 instead of bit-exact banded sums)
+    if (const char *e = getenv("DALIB200_MEL_TENSOR_CORES")) CheckStatus(dalib200MelPlanSetTensorCores(plan_, atoi(e)), "MelFilterBank");
   }
   ~MelFilterBankGPU() override { dalib200MelPlanDestroy(plan_); }
  protected:

@@ -55,56 +55,99 @@ __device__ __forceinline__ int64_t reflect101(int64_t i, int64_t n) {
   return i;
 }
 
-// smem: F frames x nfft complex (float2).  twiddle: cos/sin(2 pi k / nfft), k < nfft/2, computed in double on the host.
+// Two real frames per complex FFT (frame 2p = real part, 2p + 1 = imaginary part; the spectra are separated afterwards from
+// Z[k] and Z[N - k]), radix-2 DIT stages fused in pairs (a thread carries 4 points through 2 stages: half the barriers and half
+// the shared-memory traffic), twiddles in shared memory.  Element i of a buffer lives at i + (i >> 5): the bit-reversed
+// scatter of the framing step (stride N/32 elements between lanes) would otherwise hit one bank 32 times.
+// smem: [F/2 pairs][N + N/32] float2 | twiddle[N/2] = exp(-2 pi i k / N), computed in double on the host.
+__device__ __forceinline__ int pad32(int i) { return i + (i >> 5); }
+
+__device__ __forceinline__ float spec_sample(const SpecDesc &d, const SpecParams &P, const float *__restrict__ window, int64_t frame, int t) {
+  int64_t si = frame * (int64_t)P.step - P.center_off + t;
+  if (si < 0 || si >= d.len) {
+    if (P.padding != 2) return 0.0f;
+    si = reflect101(si, d.len);
+  }
+  return mul_rn(window[t], __ldg(d.in + si));
+}
+
+__device__ __forceinline__ float2 cmul(float2 c, float2 w) {          // c * (w.x - i w.y), w = (cos, sin)
+  return make_float2(c.x * w.x + c.y * w.y, c.y * w.x - c.x * w.y);
+}
+
 __global__ void __launch_bounds__(256) spectrogram_kernel(const SpecDesc *__restrict__ descs, int n, int64_t total_groups,
                                                           SpecParams P, const float *__restrict__ window,
                                                           const float2 *__restrict__ twiddle) {
   extern __shared__ float2 buf[];
-  const int N = P.nfft, F = P.frames_per_cta;
+  const int N = P.nfft, F = P.frames_per_cta, L = P.log2n, NPAD = N + (N >> 5);
+  float2 *tw = buf + (size_t)(F >> 1) * NPAD;
+  for (int i = threadIdx.x; i < (N >> 1); i += blockDim.x) tw[i] = twiddle[i];
+  __syncthreads();
   for (int64_t grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
     const int s = find_spec_sample(descs, n, grp);
     const SpecDesc &d = descs[s];
     const int64_t w0 = (grp - d.first_group) * F;
     const int nf = (int)min((int64_t)F, d.nwin - w0);
-    // ---- framing: sample t of frame f lands at bit-reversed index of (in_win_start + t); everything else is zero
-    for (int e = threadIdx.x; e < nf * N; e += blockDim.x) {
-      const int f = e / N, i = e - f * N;
+    const int np = (nf + 1) >> 1;
+    // ---- framing: sample t of a frame lands at the bit-reversed index of (in_win_start + t); everything else is zero
+    for (int e = threadIdx.x; e < np * N; e += blockDim.x) {
+      const int p = e / N, i = e - p * N;
       const int t = i - P.in_win_start;
-      float v = 0.0f;
+      float va = 0.0f, vb = 0.0f;
       if (t >= 0 && t < P.win_len) {
-        int64_t si = (w0 + f) * (int64_t)P.step - P.center_off + t;
-        if (si < 0 || si >= d.len) {
-          if (P.padding == 2) { si = reflect101(si, d.len); v = mul_rn(window[t], __ldg(d.in + si)); }
-        } else {
-          v = mul_rn(window[t], __ldg(d.in + si));
-        }
+        va = spec_sample(d, P, window, w0 + 2 * p, t);
+        if (2 * p + 1 < nf) vb = spec_sample(d, P, window, w0 + 2 * p + 1, t);
       }
-      const int r = (int)(__brev((unsigned)i) >> (32 - P.log2n));
-      buf[f * N + r] = make_float2(v, 0.0f);
+      const int r = (int)(__brev((unsigned)i) >> (32 - L));
+      buf[p * NPAD + pad32(r)] = make_float2(va, vb);
     }
     __syncthreads();
-    // ---- in-place radix-2 DIT
-    for (int st = 0; st < P.log2n; st++) {
+    // ---- in-place radix-2 DIT, two stages per pass
+    int st = 0;
+    for (; st + 1 < L; st += 2) {
       const int half = 1 << st;
-      for (int e = threadIdx.x; e < nf * (N >> 1); e += blockDim.x) {
-        const int f = e / (N >> 1), b = e - f * (N >> 1);
-        const int k = b & (half - 1);
-        const int i0 = ((b >> st) << (st + 1)) + k, i1 = i0 + half;
-        const float2 w = twiddle[k << (P.log2n - 1 - st)];     // exp(-2 pi i k / (2 half))
-        float2 *fb = buf + f * N;
-        const float2 a = fb[i0], c = fb[i1];
-        const float tr = c.x * w.x + c.y * w.y;                // (c.x + i c.y) * (w.x - i w.y)
-        const float ti = c.y * w.x - c.x * w.y;
-        fb[i0] = make_float2(a.x + tr, a.y + ti);
-        fb[i1] = make_float2(a.x - tr, a.y - ti);
+      for (int e = threadIdx.x; e < np * (N >> 2); e += blockDim.x) {
+        const int p = e / (N >> 2), q = e - p * (N >> 2);
+        const int k = q & (half - 1);
+        const int base = ((q >> st) << (st + 2)) + k;
+        float2 *fb = buf + p * NPAD;
+        const int i0 = pad32(base), i1 = pad32(base + half), i2 = pad32(base + 2 * half), i3 = pad32(base + 3 * half);
+        const float2 e0 = fb[i0], e1 = fb[i1], e2 = fb[i2], e3 = fb[i3];
+        const float2 w1 = tw[k << (L - 1 - st)];
+        const float2 t1 = cmul(e1, w1), t3 = cmul(e3, w1);
+        const float2 a0 = make_float2(e0.x + t1.x, e0.y + t1.y), a1 = make_float2(e0.x - t1.x, e0.y - t1.y);
+        const float2 a2 = make_float2(e2.x + t3.x, e2.y + t3.y), a3 = make_float2(e2.x - t3.x, e2.y - t3.y);
+        const float2 wa = tw[k << (L - 2 - st)], wb = tw[(k + half) << (L - 2 - st)];
+        const float2 ta = cmul(a2, wa), tb = cmul(a3, wb);
+        fb[i0] = make_float2(a0.x + ta.x, a0.y + ta.y);
+        fb[i2] = make_float2(a0.x - ta.x, a0.y - ta.y);
+        fb[i1] = make_float2(a1.x + tb.x, a1.y + tb.y);
+        fb[i3] = make_float2(a1.x - tb.x, a1.y - tb.y);
       }
       __syncthreads();
     }
-    // ---- magnitude / power + store
+    if (st < L) {                                            // odd log2(nfft): one plain radix-2 stage is left
+      const int half = 1 << st;
+      for (int e = threadIdx.x; e < np * (N >> 1); e += blockDim.x) {
+        const int p = e / (N >> 1), b = e - p * (N >> 1);
+        const int k = b & (half - 1);
+        const int j0 = ((b >> st) << (st + 1)) + k;
+        float2 *fb = buf + p * NPAD;
+        const int i0 = pad32(j0), i1 = pad32(j0 + half);
+        const float2 a = fb[i0], t = cmul(fb[i1], tw[k << (L - 1 - st)]);
+        fb[i0] = make_float2(a.x + t.x, a.y + t.y);
+        fb[i1] = make_float2(a.x - t.x, a.y - t.y);
+      }
+      __syncthreads();
+    }
+    // ---- separate the two frames of a pair, magnitude / power, store
     for (int e = threadIdx.x; e < nf * P.nbin; e += blockDim.x) {
       int f, k;
       if (P.layout_ft) { k = e / nf; f = e - k * nf; } else { f = e / P.nbin; k = e - f * P.nbin; }
-      const float2 x = buf[f * N + k];
+      const float2 *fb = buf + (f >> 1) * NPAD;
+      const float2 zk = fb[pad32(k)], zn = fb[pad32((N - k) & (N - 1))];
+      const float2 x = (f & 1) ? make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x))
+                               : make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
       const float pw = x.x * x.x + x.y * x.y;
       const float v = P.power == 2 ? pw : sqrtf(pw);
       if (P.layout_ft) d.out[(int64_t)k * d.nwin + w0 + f] = v;
@@ -402,8 +445,9 @@ int dalib200SpectrogramPlanSetup(dalib200SpectrogramPlan *p, const dalib200Spect
   P.layout_ft = a->layout_ft != 0;
   P.nbin = nfft / 2 + 1;
   P.in_win_start = a->window_length < nfft ? (nfft - a->window_length) / 2 : 0;
-  P.frames_per_cta = std::max(1, std::min(8, (96 * 1024) / (nfft * 8)));
-  p->smem = (size_t)P.frames_per_cta * nfft * sizeof(float2);
+  // two frames share one complex buffer: 16 frames (8 buffers of nfft + nfft/32 float2) per CTA at nfft = 1024 -> 3 CTAs / SM
+  P.frames_per_cta = 2 * std::max(1, std::min(8, (64 * 1024) / (nfft * 8)));
+  p->smem = (size_t)(P.frames_per_cta / 2) * (nfft + nfft / 32) * sizeof(float2) + (size_t)(nfft / 2) * sizeof(float2);
   std::vector<float> w(a->window_length);
   if (window_fn) memcpy(w.data(), window_fn, sizeof(float) * a->window_length);
   else dalib200HannWindow(w.data(), a->window_length);

@@ -287,13 +287,13 @@ __device__ __noinline__ uint32_t slow_symbol(const HuffSlow *__restrict__ slow, 
 // completed blocks.  When WRITE, stores the coefficients of block `blk0 + nb` (natural order; DC terms -- still
 // differential -- into the compact per-block array) and stops at `blk_limit`.  Branch-free apart from the loop, the rare
 // long-code path and the predicated store.
-template <bool WRITE, class Src>
+template <bool WRITE, class Src, int TBL_STRIDE = 1>
 __device__ __forceinline__ void decode_span(const Src &src, BitWindow<Src> &win, const uint32_t *__restrict__ lut,
                                             const HuffSlow *__restrict__ slow, const uint32_t *__restrict__ s_tbl, int bpm,
                                             uint32_t &pos, uint32_t end, int &c, int &z, uint32_t &nb,
                                             int16_t *__restrict__ coef, int16_t *__restrict__ dcv, const uint8_t *__restrict__ s_zig,
                                             uint32_t blk0, uint32_t blk_limit) {
-  uint32_t tb12 = s_tbl[c];                                   // dc table offset | ac table offset << 16 (in LUT words)
+  uint32_t tb12 = s_tbl[c * TBL_STRIDE];                      // dc table offset | ac table offset << 16 (in LUT words)
   while (pos < end) {
     if (WRITE && blk0 + nb >= blk_limit) break;
     // the AC entry is fetched before z is known (it is the common case and sits on the loop-carried path); the DC entry only
@@ -323,7 +323,7 @@ __device__ __forceinline__ void decode_span(const Src &src, BitWindow<Src> &win,
     nb += endb ? 1u : 0u;
     c = endb ? c1 : c;
     z = endb ? 0 : z;
-    if (endb) tb12 = s_tbl[c];
+    if (endb) tb12 = s_tbl[c * TBL_STRIDE];
   }
 }
 
@@ -504,7 +504,7 @@ struct ColSrc {
 };
 
 __device__ __forceinline__ void tail_step(const HuffCtx &cx, const uint4 rec, int out_list, const uint32_t *s_lut, const HuffSlow *s_slow,
-                                          int s_table_set, uint32_t *col) {
+                                          int s_table_set, uint32_t *col, uint32_t *tblcol) {
   const int img_i = (int)rec.w;
   const JpegImage &im = cx.images[img_i];
   const int64_t g = rec.z;
@@ -514,17 +514,14 @@ __device__ __forceinline__ void tail_step(const HuffCtx &cx, const uint4 rec, in
   const uint32_t clean_bits = cx.unit_clean_len[ui] * 8u;
   const uint32_t nsub_eff = (clean_bits + (1u << cx.log2_sub) - 1) >> cx.log2_sub;
   const uint32_t jl = (uint32_t)(j - u.first_subseq);
-  uint32_t tbl[kMaxBlocksPerMcu];
 #pragma unroll
-  for (int b = 0; b < kMaxBlocksPerMcu; b++) tbl[b] = tbl_word(im, b);
+  for (int b = 0; b < kMaxBlocksPerMcu; b++) tblcol[b * kTailThreads] = tbl_word(im, b);       // private column: bank = thread
   const bool shared_tables = im.table_set == s_table_set;
-  const uint32_t *lut = shared_tables ? s_lut : cx.tables[im.table_set].lut;
-  const HuffSlow *slow = shared_tables ? s_slow : cx.tables[im.table_set].slow;
   uint32_t pos = rec.x, nb = 0;
   int c = (int)(rec.y & 0xFF), z = (int)((rec.y >> 8) & 0xFF);
   const uint32_t end = min((jl + 1) << cx.log2_sub, clean_bits);
   const int sub_words = 1 << (cx.log2_sub - 5);
-  if (sub_words + 4 <= kTailColWords) {
+  if (shared_tables && sub_words + 4 <= kTailColWords) {
     // private column: words [0, sub_words + 4) of this subsequence
     const uint4 *p4 = reinterpret_cast<const uint4 *>(cx.clean + u.clean_off + ((size_t)jl << (cx.log2_sub - 3)));
     for (int q = 0; q < sub_words / 4 + 1; q++) {
@@ -536,12 +533,14 @@ __device__ __forceinline__ void tail_step(const HuffCtx &cx, const uint4 rec, in
     const uint32_t rel = pos - (jl << cx.log2_sub);
     BitWindow<ColSrc> win;
     win.init(src, rel >> 5, rel & 31u);
-    decode_span<false>(src, win, lut, slow, tbl, im.bpm, pos, end, c, z, nb, nullptr, nullptr, nullptr, 0, 0);
+    decode_span<false, ColSrc, kTailThreads>(src, win, s_lut, s_slow, tblcol, im.bpm, pos, end, c, z, nb, nullptr, nullptr, nullptr, 0, 0);
   } else {
+    // another table set than the one this CTA keeps in shared memory (mixed batches), or an oversized subsequence: global path
     const GlobalSrc src{reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off)};
     BitWindow<GlobalSrc> win;
     win.init(src, pos >> 5, pos & 31u);
-    decode_span<false>(src, win, lut, slow, tbl, im.bpm, pos, end, c, z, nb, nullptr, nullptr, nullptr, 0, 0);
+    decode_span<false, GlobalSrc, kTailThreads>(src, win, cx.tables[im.table_set].lut, cx.tables[im.table_set].slow, tblcol, im.bpm, pos, end,
+                                                c, z, nb, nullptr, nullptr, nullptr, 0, 0);
   }
   const uint64_t ns = pack_state(pos, c, z);
   const bool same = cx.s_state[g] == ns;
@@ -554,6 +553,7 @@ __global__ void __launch_bounds__(kTailThreads) huff_sync_tail_kernel(HuffCtx cx
   uint32_t *s_lut = tsm;
   HuffSlow *s_slow = reinterpret_cast<HuffSlow *>(s_lut + kLutWords);
   uint32_t *col = reinterpret_cast<uint32_t *>(s_slow + 4) + threadIdx.x;
+  uint32_t *tblcol = reinterpret_cast<uint32_t *>(s_slow + 4) + kTailColWords * kTailThreads + threadIdx.x;
   const int s_table_set = cx.images[0].table_set;
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(cx.tables[s_table_set].lut);
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(kTailThreads) huff_sync_tail_kernel(HuffCtx cx
   cg::grid_group grid = cg::this_grid();
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   // round 1 of the chains that left their sync block: survivors join list 1 (round 2)
-  for (uint32_t i = gtid, n = cx.chain_count[0]; i < n; i += gsize) tail_step(cx, cx.chains[0][i], 1, s_lut, s_slow, s_table_set, col);
+  for (uint32_t i = gtid, n = cx.chain_count[0]; i < n; i += gsize) tail_step(cx, cx.chains[0][i], 1, s_lut, s_slow, s_table_set, col, tblcol);
   grid.sync();
   // Three rotating lists: round r reads list `cur`, appends to `nxt`, and the third one -- read in the previous round, appended
   // to in the next -- is reset meanwhile.  (With two lists the reset of the list just read would race with the appends of
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(kTailThreads) huff_sync_tail_kernel(HuffCtx cx
     if (n == 0) break;
     const int nxt = cur == 3 ? 1 : cur + 1, idle = nxt == 3 ? 1 : nxt + 1;
     if (gtid == 0) cx.chain_count[idle] = 0;
-    for (uint32_t i = gtid; i < n; i += gsize) tail_step(cx, cx.chains[cur][i], nxt, s_lut, s_slow, s_table_set, col);
+    for (uint32_t i = gtid; i < n; i += gsize) tail_step(cx, cx.chains[cur][i], nxt, s_lut, s_slow, s_table_set, col, tblcol);
     grid.sync();                                             // everybody has read chain_count[cur] and appended its survivors
     cur = nxt;
   }
@@ -1789,7 +1789,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   }
   { ProfScope ps_("jpeg_huff_sync_intra", s); huff_sync_intra_kernel<<<p->total_blocks_sync, kSyncThreads, hsmem, s>>>(cx); }
   {
-    const size_t tail_smem = kLutWords * 4 + 4 * sizeof(HuffSlow) + (size_t)kTailColWords * kTailThreads * 4;
+    const size_t tail_smem = kLutWords * 4 + 4 * sizeof(HuffSlow) + (size_t)(kTailColWords + kMaxBlocksPerMcu) * kTailThreads * 4;
     if (p->tail_grid == 0) {
       int per_sm = 0;
       DB_CUDA(cudaFuncSetAttribute(huff_sync_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));

@@ -57,11 +57,14 @@ struct ProfScope {
 
 // include/dali/core/convert.h:306-324: host ConvertSat<uint8_t>(float) = clamp(std::round(x)) -- half AWAY.
 __device__ __forceinline__ uint8_t sat_u8_half_away(float x) {
-  float t = truncf(x);
-  float d = x - t;                               // exact for |x| < 2^23
-  if (d >= 0.5f) t += 1.0f; else if (d <= -0.5f) t -= 1.0f;
-  t = fminf(fmaxf(t, 0.0f), 255.0f);
-  return (uint8_t)(int)t;
+  // All on the FMA / ALU pipes (FRND and F2I run on the quarter-rate conversion pipe): x + 1.5 * 2^23 rounds x to the nearest
+  // integer, ties to EVEN, in the low mantissa bits; the exact remainder d = x - rne(x) tells a tie that went down (d == 0.5),
+  // which round-half-AWAY sends up instead.  Ties of negative x only matter below the clamp (result 0 either way).
+  x = fminf(fmaxf(x, -1.0f), 256.0f);
+  const float y = __fadd_rn(x, 12582912.0f);
+  const float d = __fsub_rn(x, __fsub_rn(y, 12582912.0f));
+  int i = __float_as_int(y) - 0x4B400000 + (d == 0.5f ? 1 : 0);
+  return (uint8_t)min(max(i, 0), 255);
 }
 // dali/kernels/common/simd.h:233-263: the SSE2 store path rounds half to EVEN (cvtps2dq) then saturates.
 __device__ __forceinline__ uint8_t sat_u8_half_even(float x) {

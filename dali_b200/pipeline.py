@@ -139,6 +139,7 @@ class Pipeline:
         self._sample_idx = 0
         self._keepalive = []
         self._cur_slot = 0
+        self._pending = []
 
     # ---- context management (with pipe: ...)
     def __enter__(self):
@@ -250,13 +251,12 @@ class Pipeline:
             if s.dtype != dt or s.ndim != nd:
                 raise TypeError("All samples of an external source batch must have the same type and dimensionality")
             arrs.append(np.ascontiguousarray(s))
-        self._keep[self._cur_slot].append(arrs)
+        self._pending.append(arrs)          # kept alive until the slot that consumes them is reused (the backend borrows the pointers)
         shapes = np.array([a.shape for a in arrs], np.int64).reshape(len(arrs), nd) if nd else np.zeros((len(arrs), 0), np.int64)
         self._slots[self._cur_slot].feed_input(name, [a.ctypes.data for a in arrs], shapes, nd, int(types.from_numpy_type(dt)), layout)
 
     def _run_input_callbacks(self, slot):
         self._cur_slot = slot
-        self._keep[slot] = []
         for g in self._externals:
             if g.source is None:
                 continue
@@ -265,6 +265,9 @@ class Pipeline:
                 batch = (batch,)
             for o, b in zip(g.outputs, batch):
                 self._feed(o.name, b, g.layout or "")
+        # everything fed for this iteration (feed_input() calls and source callbacks) replaces what the slot held before
+        self._keep[slot] = self._pending
+        self._pending = []
 
     # ---- run
     def schedule_run(self):

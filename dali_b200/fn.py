@@ -135,4 +135,68 @@ def _install():
         this.image_decoder = this.decoders.image
 
 
+
+# ---- host-side sources in front of the hot path: they feed CPU batches like an external_source callback
+def _source_group(pipe, source, n, base, layout=None, device="cpu"):
+    g = _ExternalSourceGroup(source, [], True, None, layout, None, device, False)
+    for k in range(n):
+        g.outputs.append(DataNode(base if n == 1 else f"{base}[{k}]", device, source=g))
+    pipe._externals.append(g)
+    return g
+
+
+def _readers_file(file_root=None, file_list=None, files=None, labels=None, *, random_shuffle=False, shuffle_after_epoch=False,
+                  initial_fill=1024, shard_id=0, num_shards=1, stick_to_shard=False, pad_last_batch=False, seed=-1, name=None,
+                  device="cpu", **_ignored):
+    """fn.readers.file (dali/operators/reader/file_reader_op.cc, loader/file_label_loader.h): (encoded file bytes, label)."""
+    from .readers import FileReader
+    pipe = _current()
+    if pipe is None:
+        raise RuntimeError("fn.readers.file must be called inside a pipeline definition")
+    if device != "cpu":
+        raise ValueError("readers.file produces CPU batches")
+    if seed is None or seed < 0:
+        seed = pipe.seed if getattr(pipe, "seed", -1) not in (None, -1) else -1
+    reader = FileReader(pipe.max_batch_size, file_root, file_list, files, labels, random_shuffle, shuffle_after_epoch, initial_fill,
+                        shard_id, num_shards, stick_to_shard, pad_last_batch, seed)
+    inst = name or pipe._new_name("readers__File")
+    g = _source_group(pipe, reader, 2, inst)
+    pipe._readers[inst] = reader
+    return g.outputs[0], g.outputs[1]
+
+
+def _random_coin_flip(*, probability=0.5, shape=None, seed=-1, dtype=None, name=None, device="cpu", **_ignored):
+    """fn.random.coin_flip (dali/operators/random/coin_flip_cpu.cc): 1 with `probability`, else 0; int32 by default."""
+    from .readers import CoinFlip
+    pipe = _current()
+    if pipe is None:
+        raise RuntimeError("fn.random.coin_flip must be called inside a pipeline definition")
+    npdt = np.int32 if dtype is None else _types.to_numpy_type(int(dtype))
+    return _source_group(pipe, CoinFlip(pipe.max_batch_size, probability, shape, seed, npdt), 1, name or pipe._new_name("random__CoinFlip")).outputs[0]
+
+
+def _random_uniform(*, range=(-1.0, 1.0), values=None, shape=None, seed=-1, dtype=None, name=None, device="cpu", **_ignored):
+    """fn.random.uniform (dali/operators/random/uniform_distribution_cpu.cc): `range` = [a, b) continuous, `values` = discrete."""
+    from .readers import Uniform
+    pipe = _current()
+    if pipe is None:
+        raise RuntimeError("fn.random.uniform must be called inside a pipeline definition")
+    npdt = np.float32 if dtype is None else _types.to_numpy_type(int(dtype))
+    return _source_group(pipe, Uniform(pipe.max_batch_size, range, values, shape, seed, npdt), 1, name or pipe._new_name("random__Uniform")).outputs[0]
+
+
+def _install_sources():
+    this = sys.modules[__name__]
+    for modname, entries in (("readers", {"file": _readers_file}), ("random", {"coin_flip": _random_coin_flip, "uniform": _random_uniform})):
+        sub = getattr(this, modname, None)
+        if sub is None:
+            sub = _pytypes.ModuleType(f"{this.__name__}.{modname}")
+            setattr(this, modname, sub)
+            sys.modules[sub.__name__] = sub
+        for k, f in entries.items():
+            f.__name__ = k
+            setattr(sub, k, f)
+
+
 _install()
+_install_sources()

@@ -121,6 +121,7 @@ class Pipeline:
         self.max_batch_size = int(batch_size)
         self.num_threads = max(1, int(num_threads) if num_threads and num_threads > 0 else 1)
         self.device_id = None if device_id is None or device_id < 0 else int(device_id)
+        self.seed = seed
         self._nodes = []            # (schema, inst_name, spec)
         self._externals = []        # _ExternalSourceGroup
         self._ext_names = {}
@@ -140,6 +141,7 @@ class Pipeline:
         self._keepalive = []
         self._cur_slot = 0
         self._pending = []
+        self._readers = {}          # reader instance name -> dali_b200.readers.FileReader
 
     # ---- context management (with pipe: ...)
     def __enter__(self):
@@ -339,10 +341,18 @@ class Pipeline:
             g.iterator = None
 
     def epoch_size(self, name=None):
-        return {}
+        if name is not None:
+            return self._readers[name].meta()["epoch_size_padded"]
+        return {k: r.meta()["epoch_size_padded"] for k, r in self._readers.items()}
 
     def reader_meta(self, name=None):
-        return {}
+        """dali/python/nvidia/dali/pipeline.py reader_meta: epoch_size, epoch_size_padded, number_of_shards, shard_id,
+        pad_last_batch, stick_to_shard."""
+        if name is not None:
+            if name not in self._readers:
+                raise KeyError(f"Reader '{name}' not found in the pipeline")
+            return self._readers[name].meta()
+        return {k: r.meta() for k, r in self._readers.items()}
 
     def executor_statistics(self):
         return {}

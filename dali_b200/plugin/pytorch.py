@@ -22,20 +22,55 @@ class DALIGenericIterator:
         self.output_map = list(output_map)
         if len(set(self.output_map)) != len(self.output_map):
             raise ValueError("output_map names should be distinct")
-        if reader_name is not None:
-            raise NotImplementedError("reader_name: file readers are outside the hot path; feed data through fn.external_source")
+        if fill_last_batch is not None:      # deprecated spelling (plugin/base_iterator.py)
+            last_batch_policy = LastBatchPolicy.FILL if fill_last_batch else LastBatchPolicy.PARTIAL
+        if reader_name is not None and size != -1:
+            raise ValueError("When reader_name is provided, size should not be set")
         self._size = size
         self._auto_reset = auto_reset
         self._counter = 0
+        self._policy = last_batch_policy
+        self._reader_name = reader_name
         for p in self._pipes:
             p.build()
         self.batch_size = self._pipes[0].max_batch_size
+        self._shard_size = None
+        if reader_name is not None:
+            self._init_from_reader(last_batch_padded)
         self._first = None
         if prepare_first_batch:
             try:
                 self._first = self._fetch()
             except StopIteration:
                 self._first = None
+
+    def _init_from_reader(self, last_batch_padded):
+        """plugin/base_iterator.py:_extract_from_reader_and_validate: the epoch length comes from the reader's meta data."""
+        import math
+        metas = [p.reader_meta(self._reader_name) for p in self._pipes]
+        for k, what in (("epoch_size", "size value"), ("number_of_shards", "`num_shards` argument set"),
+                        ("pad_last_batch", "`pad_last_batch` argument set"), ("stick_to_shard", "`stick_to_shard` argument set")):
+            if any(m[k] != metas[0][k] for m in metas):
+                raise AssertionError(f"Reader Operator should have the same {what} in all the pipelines.")
+        n, shards = metas[0]["epoch_size"], metas[0]["number_of_shards"]
+        self._size_no_pad, self._shards_num = n, shards
+        self._last_batch_padded = metas[0]["pad_last_batch"]
+        self._stick = metas[0]["stick_to_shard"]
+        self._shard_ids = [m["shard_id"] for m in metas]
+        if self._policy == LastBatchPolicy.DROP:
+            self._size = n // shards
+        elif self._last_batch_padded:
+            self._size = metas[0]["epoch_size_padded"] // shards
+        else:
+            self._size = int(math.ceil(math.ceil(n / shards) / self.batch_size)) * self.batch_size
+        self._epoch = 0
+
+    def _shard_sizes_now(self):
+        res = []
+        for sid in self._shard_ids:
+            v = sid if self._stick else (sid + self._epoch) % self._shards_num
+            res.append(self._size_no_pad * (v + 1) // self._shards_num - self._size_no_pad * v // self._shards_num)
+        return res
 
     def _fetch(self):
         torch = self._torch
@@ -65,6 +100,21 @@ class DALIGenericIterator:
             if self._auto_reset:
                 self.reset()
             raise StopIteration
+        if self._reader_name is not None and self._policy == LastBatchPolicy.DROP and \
+                any(self._counter + self.batch_size > s for s in self._shard_sizes_now()):
+            # the incomplete last batch is dropped: it is the next batch of the stream, so it is fetched and discarded
+            if self._counter < max(self._shard_sizes_now()):
+                try:
+                    if self._first is not None:
+                        self._first = None
+                    else:
+                        self._fetch()
+                except StopIteration:
+                    pass
+            self._counter = self._size if self._size > 0 else self._counter
+            if self._auto_reset:
+                self.reset()
+            raise StopIteration
         if self._first is not None:
             out, self._first = self._first, None
         else:
@@ -74,13 +124,24 @@ class DALIGenericIterator:
                 if self._auto_reset:
                     self.reset()
                 raise
-        self._counter += self.batch_size * len(self._pipes)
+        if self._reader_name is not None:
+            self._counter += self.batch_size                    # per-GPU counter, as in the reference
+            if self._policy == LastBatchPolicy.PARTIAL:
+                for d, ssz in zip(out, self._shard_sizes_now()):
+                    left = self.batch_size - (self._counter - ssz)
+                    if left < self.batch_size:                  # the tail of this batch is padding / wrapped-around samples
+                        for k in list(d):
+                            d[k] = d[k][:max(left, 0)]
+        else:
+            self._counter += self.batch_size * len(self._pipes)
         return out
 
     next = __next__
 
     def reset(self):
         self._counter = 0
+        if self._reader_name is not None:
+            self._epoch += 1
         for p in self._pipes:
             p.reset()
 

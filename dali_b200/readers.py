@@ -1,0 +1,196 @@
+"""fn.readers.file and the fn.random.* argument generators -- host-side input staging in front of the hot path
+(SURVEY.md 8f rank 2).  They produce CPU batches exactly like an fn.external_source callback does, so everything behind
+them (mixed decoder, GPU operators, prefetch slots) is unchanged.
+
+Reference behaviour mirrored here:
+  * file discovery      dali/operators/reader/loader/file_label_loader.{h,cc}, filesystem.cc, utils.h:28-36: `file_root` is
+                        traversed one level deep, class directories in sorted order -> label = directory index, files sorted
+                        inside a directory, only files with a known image / audio extension; `file_list` = text file of
+                        "<relative path> <label>" lines; `files` (+ optional `labels`) = explicit lists.
+  * sharding / epochs   dali/operators/reader/loader/loader.{h,cc}: a shard starts at N * shard_id / num_shards
+                        (loader.cc:78-81) and is read sequentially; behind its end the loader continues with the NEXT shard
+                        (the shards rotate from epoch to epoch) unless `stick_to_shard`, which wraps to the shard's own start;
+                        `pad_last_batch` repeats the last sample until every shard has returned ceil(N / num_shards) samples
+                        and the batch is full (loader.h:206-216, 262-283); without it batches simply run on into the next
+                        epoch's samples.  `reader_meta()` has the reference's keys (pipeline.py reader_meta).
+  * shuffling           `random_shuffle`: a buffer of `initial_fill` samples from which a random one is returned and replaced
+                        by the next one read (loader.h:218-330); `shuffle_after_epoch`: the whole file list is re-shuffled
+                        with the seed + epoch before every epoch and sharding is by stick_to_shard (file_label_loader.h).
+                        The random ORDER is not the reference's (std::mt19937 streams cannot be reproduced from numpy); the
+                        distribution and the epoch / shard structure are.
+  * random.coin_flip / random.uniform   dali/operators/random/{coin_flip,uniform_distribution}_cpu.cc: one value (or `shape`)
+                        per sample, int32 for coin_flip, float32 for uniform (`range` continuous, `values` discrete).
+"""
+import math
+import os
+
+import numpy as np
+
+KNOWN_EXTENSIONS = (".jpg", ".jpeg", ".png", ".bmp", ".tif", ".tiff", ".pnm", ".ppm", ".pgm", ".pbm", ".jp2", ".webp",
+                    ".flac", ".ogg", ".wav")
+
+
+def start_index(shard_id, num_shards, size):
+    """loader.cc:78-81."""
+    return size * shard_id // num_shards
+
+
+def discover_files(file_root=None, file_list=None, files=None, labels=None):
+    """[(path, label)] in the reference's order."""
+    if files is not None:
+        if file_list is not None:
+            raise ValueError("`files` and `file_list` are mutually exclusive")
+        paths = [os.path.join(file_root, f) if file_root else f for f in files]
+        if labels is None:
+            labels = list(range(len(paths)))
+        if len(labels) != len(paths):
+            raise ValueError(f"Provided {len(labels)} labels for {len(paths)} files")
+        return list(zip(paths, [int(v) for v in labels]))
+    if labels is not None:
+        raise ValueError("`labels` requires `files`")
+    if file_list is not None:
+        root = file_root or os.path.dirname(os.path.abspath(file_list))
+        out = []
+        with open(file_list) as f:
+            for ln in f:
+                ln = ln.strip()
+                if not ln:
+                    continue
+                path, _, lab = ln.rpartition(" ")
+                if not path:
+                    raise ValueError(f"file_list line without a label: {ln!r}")
+                out.append((os.path.join(root, path), int(lab)))
+        return out
+    if file_root is None:
+        raise ValueError("One of `file_root`, `file_list` or `files` is required")
+    out = []
+    classes = sorted(d for d in os.listdir(file_root) if os.path.isdir(os.path.join(file_root, d)))
+    for label, d in enumerate(classes):
+        for f in sorted(os.listdir(os.path.join(file_root, d))):
+            p = os.path.join(file_root, d, f)
+            if os.path.isfile(p) and f.lower().endswith(KNOWN_EXTENSIONS):
+                out.append((p, label))
+    return out
+
+
+class FileReader:
+    """Stateful batch source with the reference loader's shard / epoch / padding / shuffling rules."""
+
+    def __init__(self, batch_size, file_root=None, file_list=None, files=None, labels=None, random_shuffle=False,
+                 shuffle_after_epoch=False, initial_fill=1024, shard_id=0, num_shards=1, stick_to_shard=False, pad_last_batch=False,
+                 seed=-1):
+        if not (0 <= shard_id < num_shards):
+            raise ValueError("num_shards needs to be greater than shard_id")
+        if random_shuffle and shuffle_after_epoch:
+            raise ValueError("shuffle_after_epoch and random_shuffle cannot be both true")
+        if shuffle_after_epoch and stick_to_shard:
+            raise ValueError("shuffle_after_epoch and stick_to_shard cannot be both true")
+        self.entries = discover_files(file_root, file_list, files, labels)
+        if not self.entries:
+            raise RuntimeError("No files found.")
+        if num_shards > len(self.entries):
+            raise RuntimeError(f"The number of input samples: {len(self.entries)}, needs to be at least equal to the requested "
+                               f"number of shards: {num_shards}.")
+        self.batch_size, self.shard_id, self.num_shards = batch_size, shard_id, num_shards
+        self.random_shuffle, self.shuffle_after_epoch = random_shuffle, shuffle_after_epoch
+        self.stick_to_shard, self.pad_last_batch = stick_to_shard, pad_last_batch
+        self.initial_fill = max(1, int(initial_fill)) if random_shuffle else 1
+        self.seed = 524287 if seed is None or seed < 0 else int(seed)
+        self.rng = np.random.default_rng(self.seed)
+        self.order = list(range(len(self.entries)))
+        # read side: sequential position inside the (virtual) shard of the epoch being READ
+        self.read_epoch = 0
+        self.virtual_shard = shard_id
+        self._reshuffle()
+        self.cursor = start_index(self.virtual_shard, num_shards, len(self.entries))
+        self.read_in_shard = 0
+        # return side: the epoch whose samples are being RETURNED (the shuffle buffer lets the reads run ahead)
+        self.cur_epoch = 0
+        self.returned_in_epoch = 0
+        self.buffer = []                # (epoch tag, sample index), in read order
+        self.last = None
+
+    # ---- reference: reader_meta keys
+    def meta(self):
+        n = len(self.entries)
+        return {"epoch_size": n, "epoch_size_padded": int(math.ceil(n / self.num_shards)) * self.num_shards,
+                "number_of_shards": self.num_shards, "shard_id": self.shard_id, "pad_last_batch": self.pad_last_batch,
+                "stick_to_shard": self.stick_to_shard}
+
+    def _reshuffle(self):
+        if self.shuffle_after_epoch:
+            self.order = list(np.random.default_rng(self.seed + self.read_epoch).permutation(len(self.entries)))
+
+    def _shard_bounds(self, shard):
+        n = len(self.entries)
+        return start_index(shard, self.num_shards, n), start_index(shard + 1, self.num_shards, n)
+
+    def _read_one(self):
+        """Sequential read with the shard switch of loader.h (IncreaseReadSampleCounter / MoveToNextShard / Reset)."""
+        item = (self.read_epoch, self.order[self.cursor])
+        self.cursor += 1
+        self.read_in_shard += 1
+        lo, hi = self._shard_bounds(self.virtual_shard)
+        if self.read_in_shard >= hi - lo:                    # the shard has been read completely: next epoch
+            self.read_in_shard = 0
+            self.read_epoch += 1
+            if not self.stick_to_shard:
+                self.virtual_shard = (self.virtual_shard + 1) % self.num_shards
+            self._reshuffle()
+            self.cursor = self._shard_bounds(self.virtual_shard)[0]
+        return item
+
+    def _next_sample(self, first_in_batch):
+        while len(self.buffer) < self.initial_fill:
+            self.buffer.append(self._read_one())
+        cand = [k for k, (t, _) in enumerate(self.buffer) if t == self.cur_epoch]
+        if not cand:
+            # the epoch's samples are exhausted.  pad_last_batch (loader.h ShouldPadBatch): repeat the last sample until every
+            # shard has returned ceil(N / num_shards) samples AND the batch is complete
+            target = int(math.ceil(len(self.entries) / self.num_shards))
+            if self.pad_last_batch and (self.returned_in_epoch < target or not first_in_batch):
+                self.returned_in_epoch += 1
+                return self.last
+            self.cur_epoch += 1
+            self.returned_in_epoch = 0
+            cand = [k for k, (t, _) in enumerate(self.buffer) if t == self.cur_epoch]
+        k = cand[int(self.rng.integers(0, len(cand)))] if self.random_shuffle else cand[0]
+        idx = self.buffer.pop(k)[1]
+        self.returned_in_epoch += 1
+        self.last = idx
+        return idx
+
+    def __call__(self, _iteration=None):
+        data, labels = [], []
+        for i in range(self.batch_size):
+            idx = self._next_sample(i == 0)
+            path, lab = self.entries[idx]
+            data.append(np.fromfile(path, dtype=np.uint8))
+            labels.append(np.array([lab], np.int32))
+        return data, labels
+
+
+class CoinFlip:
+    def __init__(self, batch_size, probability=0.5, shape=None, seed=-1, dtype=np.int32):
+        self.batch_size, self.p, self.shape, self.dtype = batch_size, float(probability), shape, dtype
+        self.rng = np.random.default_rng(None if seed is None or seed < 0 else seed)
+
+    def __call__(self, _iteration=None):
+        shp = tuple(self.shape) if self.shape is not None else ()
+        return [np.asarray(self.rng.random(shp) < self.p, self.dtype) for _ in range(self.batch_size)]
+
+
+class Uniform:
+    def __init__(self, batch_size, range=(-1.0, 1.0), values=None, shape=None, seed=-1, dtype=np.float32):
+        self.batch_size, self.shape, self.dtype = batch_size, shape, dtype
+        self.values = None if values is None else np.asarray(values, dtype)
+        self.lo, self.hi = float(range[0]), float(range[1])
+        if self.values is None and not self.lo < self.hi:
+            raise ValueError(f"Invalid range. It shall be left-closed [a, b), where a < b. Got: [{self.lo}, {self.hi})")
+        self.rng = np.random.default_rng(None if seed is None or seed < 0 else seed)
+
+    def __call__(self, _iteration=None):
+        shp = tuple(self.shape) if self.shape is not None else ()
+        if self.values is not None:
+            return [np.asarray(self.values[self.rng.integers(0, len(self.values), shp)], self.dtype) for _ in range(self.batch_size)]
+        return [np.asarray(self.rng.uniform(self.lo, self.hi, shp), self.dtype) for _ in range(self.batch_size)]

@@ -1,0 +1,122 @@
+"""CPU tests of the host-side input staging: fn.readers.file (discovery order, labels, sharding, shard
+rotation, pad_last_batch, shuffling as a per-epoch permutation), fn.random.coin_flip / uniform, reader_meta and the
+DALIGenericIterator(reader_name=...) epoch logic (dali/operators/reader/loader/loader.h, plugin/base_iterator.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from dali_b200 import fn, pipeline_def
+from dali_b200.plugin.pytorch import DALIGenericIterator, LastBatchPolicy
+from dali_b200.readers import FileReader, discover_files, start_index
+
+
+@pytest.fixture()
+def tree(tmp_path):
+    """10 files, classes created in non-sorted order; file k holds 4 bytes of value k (reference order: a_cat 0-3, b_dog 4-6, c_eel 7-9)."""
+    k = 0
+    for c in ("b_dog", "a_cat", "c_eel"):
+        (tmp_path / c).mkdir()
+    for c, n in (("a_cat", 4), ("b_dog", 3), ("c_eel", 3)):
+        for i in range(n):
+            (tmp_path / c / f"img{i}.jpg").write_bytes(bytes([k] * 4))
+            k += 1
+    (tmp_path / "a_cat" / "notes.txt").write_text("not an image")
+    (tmp_path / "loose.jpg").write_bytes(b"\x00")
+    return str(tmp_path)
+
+
+def _ids(reader, nbatches):
+    out = []
+    for _ in range(nbatches):
+        data, labels = reader(0)
+        out.append([int(d[0]) for d in data])
+        assert all(l.dtype == np.int32 and l.shape == (1,) for l in labels)
+    return out
+
+
+def test_discovery_order_labels_and_lists(tree, tmp_path):
+    e = discover_files(tree)
+    assert [os.path.relpath(p, tree) for p, _ in e[:5]] == ["a_cat/img0.jpg", "a_cat/img1.jpg", "a_cat/img2.jpg", "a_cat/img3.jpg",
+                                                            "b_dog/img0.jpg"]
+    assert [l for _, l in e] == [0] * 4 + [1] * 3 + [2] * 3              # label = index of the sorted class directory
+    lst = tmp_path / "list.txt"
+    lst.write_text("c_eel/img1.jpg 7\nname with space/x.jpg 3\n\na_cat/img0.jpg 0\n")
+    assert discover_files(tree, str(lst)) == [(os.path.join(tree, "c_eel/img1.jpg"), 7), (os.path.join(tree, "name with space/x.jpg"), 3),
+                                              (os.path.join(tree, "a_cat/img0.jpg"), 0)]
+    assert discover_files(files=["/x/a.jpg", "/x/b.jpg"]) == [("/x/a.jpg", 0), ("/x/b.jpg", 1)]
+    assert discover_files(files=["a.jpg"], labels=[5], file_root="/r") == [("/r/a.jpg", 5)]
+    with pytest.raises(ValueError):
+        discover_files(files=["a"], labels=[1, 2])
+
+
+def test_sharding_rotation_and_padding(tree):
+    assert [start_index(s, 3, 10) for s in range(4)] == [0, 3, 6, 10]      # loader.cc:78-81
+    assert _ids(FileReader(2, tree, shard_id=1, num_shards=3, stick_to_shard=True, pad_last_batch=True), 4) == [[3, 4], [5, 5], [3, 4], [5, 5]]
+    assert _ids(FileReader(2, tree, shard_id=1, num_shards=3, stick_to_shard=True), 4) == [[3, 4], [5, 3], [4, 5], [3, 4]]
+    assert _ids(FileReader(2, tree, shard_id=0, num_shards=3), 6) == [[0, 1], [2, 3], [4, 5], [6, 7], [8, 9], [0, 1]]     # shards rotate
+    assert _ids(FileReader(2, tree, shard_id=0, num_shards=3, pad_last_batch=True), 7) == [[0, 1], [2, 2], [3, 4], [5, 5], [6, 7], [8, 9], [0, 1]]
+    assert _ids(FileReader(4, tree, shard_id=2, num_shards=3, stick_to_shard=True, pad_last_batch=True), 2) == [[6, 7, 8, 9], [6, 7, 8, 9]]
+    with pytest.raises(ValueError):
+        FileReader(2, tree, shard_id=3, num_shards=3)
+    with pytest.raises(RuntimeError, match="number of shards"):
+        FileReader(2, tree, shard_id=0, num_shards=11)
+
+
+def test_shuffling_is_a_permutation_per_epoch(tree):
+    for kw in (dict(random_shuffle=True, initial_fill=4, seed=3), dict(shuffle_after_epoch=True, seed=3)):
+        r = FileReader(5, tree, **kw)
+        a = _ids(r, 6)
+        epochs = [sorted(a[2 * e][:] + a[2 * e + 1][:]) for e in range(3)]
+        assert epochs == [list(range(10))] * 3
+        assert a[0] + a[1] != list(range(10)) and a[0] + a[1] != a[2] + a[3]
+        b = _ids(FileReader(5, tree, **kw), 6)
+        assert a == b                                                    # deterministic for a given seed
+    sh = _ids(FileReader(3, tree, shard_id=1, num_shards=2, stick_to_shard=True, random_shuffle=True, initial_fill=100, seed=1, pad_last_batch=True), 4)
+    assert sorted(sh[0] + sh[1][:2]) == [5, 6, 7, 8, 9] and sh[1][2] == sh[1][1]      # shard [5, 10) once, then the pad
+
+
+def test_random_generators():
+    @pipeline_def(batch_size=64, num_threads=1, device_id=None)
+    def p():
+        return (fn.random.coin_flip(probability=0.25, seed=7), fn.random.uniform(range=(2.0, 3.0), seed=8),
+                fn.random.uniform(values=[1, 5, 9], shape=[3], seed=9), fn.random.coin_flip(seed=7, probability=0.25))
+    pipe = p()
+    pipe.build()
+    c, u, v, c2 = pipe.run()
+    cs = np.array([c.at(i) for i in range(64)])
+    assert cs.dtype == np.int32 and cs.shape == (64,) and set(cs.tolist()) <= {0, 1} and 3 <= cs.sum() <= 32
+    us = np.array([u.at(i) for i in range(64)])
+    assert us.dtype == np.float32 and (us >= 2).all() and (us < 3).all() and us.std() > 0.1
+    vs = np.array([v.at(i) for i in range(64)])
+    assert vs.shape == (64, 3) and set(vs.ravel().tolist()) <= {1.0, 5.0, 9.0}
+    assert np.array_equal(cs, np.array([c2.at(i) for i in range(64)]))   # same seed, same stream
+
+
+def test_pipeline_reader_meta_and_iterator_epochs(tree):
+    def make(policy, pad, shard_id=1, num_shards=3, bs=2, stick=True):
+        @pipeline_def(batch_size=bs, num_threads=1, device_id=None, prefetch_queue_depth=2)
+        def p():
+            data, label = fn.readers.file(file_root=tree, shard_id=shard_id, num_shards=num_shards, stick_to_shard=stick, pad_last_batch=pad,
+                                          name="Reader")
+            return data, label
+        pipe = p()
+        return pipe, DALIGenericIterator(pipe, ["data", "label"], reader_name="Reader", last_batch_policy=policy, auto_reset=True)
+    pipe, it = make(LastBatchPolicy.FILL, True)
+    assert pipe.reader_meta("Reader") == {"epoch_size": 10, "epoch_size_padded": 12, "number_of_shards": 3, "shard_id": 1,
+                                          "pad_last_batch": True, "stick_to_shard": True}
+    assert pipe.epoch_size("Reader") == 12 and it.size == 4
+    for epoch in range(3):                                               # shard 1 = files 3, 4, 5 (labels 0, 1, 1), padded to 4
+        batches = [(b[0]["data"][:, 0].tolist(), b[0]["label"][:, 0].tolist()) for b in it]
+        assert batches == [([3, 4], [0, 1]), ([5, 5], [1, 1])], epoch
+    _, it = make(LastBatchPolicy.PARTIAL, True)
+    assert [b[0]["data"][:, 0].tolist() for b in it] == [[3, 4], [5]]
+    assert [b[0]["data"][:, 0].tolist() for b in it] == [[3, 4], [5]]     # next epoch: same shard again (stick_to_shard)
+    _, it = make(LastBatchPolicy.DROP, True)
+    assert [b[0]["data"][:, 0].tolist() for b in it] == [[3, 4]]
+    assert [b[0]["data"][:, 0].tolist() for b in it] == [[3, 4]]          # the dropped [5, 5] batch does not leak into the next epoch
+    _, it = make(LastBatchPolicy.FILL, False, shard_id=0, num_shards=1, bs=4, stick=False)
+    assert it.size == 12                                                 # ceil(10 / 4) * 4: the last batch wraps around
+    assert [b[0]["data"][:, 0].tolist() for b in it] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 0, 1]]
+    with pytest.raises(ValueError, match="size should not be set"):
+        DALIGenericIterator(pipe, ["data", "label"], size=10, reader_name="Reader")

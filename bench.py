@@ -28,11 +28,37 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BATCH = 256
+METRIC = "images/sec decode+resize+CMN (batch 256, 1080p JPEG)"
 H, W = 1080, 1920
 OUT = 224
 ALG_DECODE = H * W * 3            # + J
 ALG_RESIZE = H * W * 3 + OUT * OUT * 3
 ALG_CMN = OUT * OUT * 3 + OUT * OUT * 3 * 2
+
+
+def effective_cores():
+    """Host cores this process may actually use: the scheduler affinity mask, capped by the cgroup CPU quota (a container
+    that reports 128 logical CPUs can be limited to a fraction of them; the stated core count must be the usable one)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(p)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except Exception:
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n, quota
 
 
 def synth_image(h, w, seed):
@@ -100,27 +126,108 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_pipeline(streams, threads, mirror=None):
-    """The reference CPU path on the host cores: one sample per task on a pool of N threads (the reference's own
-    threading model, dali/pipeline/operator/operator.h:305-314).  Returns (seconds, kind)."""
+_CPU_STREAMS = None      # set before the worker processes are forked: they inherit the encoded batch
+
+
+def _cpu_one(i, mirror_i):
+    """One sample through the reference CPU path: libjpeg-turbo decode straight to RGB (cv2.IMREAD_COLOR_RGB: no BGR->RGB
+    copy, the reference's decoder emits RGB itself), the reference's CPU resample and CMN kernels (oracle/_ref)."""
     import cv2
     from oracle import pyoracle as po
     from dali_b200.hotpath import IMAGENET_MEAN, IMAGENET_STD
-    cv2.setNumThreads(1)
     use_ref = po.have_ref()
     rs = po.ref_resample if use_ref else po.resample
     cm = po.ref_cmn if use_ref else po.cmn
     mean, inv = po.cmn_norm_args(IMAGENET_MEAN, IMAGENET_STD)
+    img = cv2.imdecode(_CPU_STREAMS[i], cv2.IMREAD_COLOR_RGB)
+    r = rs(img, (OUT, OUT))
+    return cm(r, (0, 0), (OUT, OUT), bool(mirror_i), mean, inv, np.float16, "CHW")
 
-    def one(i):
-        img = cv2.imdecode(streams[i], cv2.IMREAD_COLOR)[..., ::-1]
-        r = rs(np.ascontiguousarray(img), (OUT, OUT))
-        return cm(r, (0, 0), (OUT, OUT), bool(mirror[i]) if mirror is not None else False, mean, inv, np.float16, "CHW")
-    t0 = time.perf_counter()
+
+def _cpu_worker(args):
+    """One worker process: its slice of the sample on a small thread pool (every stage releases the GIL)."""
+    idx, mirror, threads, keep = args
+    import cv2
+    cv2.setNumThreads(1)
     with cf.ThreadPoolExecutor(threads) as ex:
-        outs = list(ex.map(one, range(len(streams))))
-    return time.perf_counter() - t0, ("reference" if use_ref else "port"), outs
+        outs = list(ex.map(_cpu_one, idx, mirror))
+    return outs if keep else float(sum(float(o[0, 0, 0]) for o in outs))
 
+
+class CpuReference:
+    """The reference CPU path on the host cores, one sample per task (the reference's own threading model,
+    dali/pipeline/operator/operator.h:305-314).  `cores` workers in total: P forked processes x T threads, so that the Python
+    glue of one sample never waits for the GIL of another (a single 128-thread pool spent most of its time there)."""
+
+    def __init__(self, streams, cores):
+        global _CPU_STREAMS
+        import multiprocessing as mp
+        from oracle import pyoracle as po
+        _CPU_STREAMS = streams
+        self.kind = "reference" if po.have_ref() else "port"
+        self.cores = cores
+        # one single-threaded worker process per usable core (measured on the 16-core-quota B200 host: 16 x 1 = 907 img/s,
+        # 2 x 8 threads = 660); beyond 32 cores the process count is capped and threads make up the difference
+        self.procs = max(1, min(cores, 32))
+        self.threads = max(1, cores // self.procs)
+        self.pool = mp.get_context("fork").Pool(self.procs) if self.procs > 1 else None
+
+    def run(self, n, mirror, keep=False):
+        """Processes samples [0, n).  Returns (seconds, outputs or None)."""
+        idx = list(range(n))
+        parts = [(idx[k::self.procs], [int(mirror[i]) for i in idx[k::self.procs]], self.threads, keep) for k in range(self.procs)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, parts) if self.pool is not None else [_cpu_worker(parts[0])]
+        dt = time.perf_counter() - t0
+        if not keep:
+            return dt, None
+        outs = [None] * n
+        for k, part in enumerate(res):
+            for i, o in zip(idx[k::self.procs], part):
+                outs[i] = o
+        return dt, outs
+
+    def single_core(self, n, mirror):
+        global _CPU_STREAMS
+        t0 = time.perf_counter()
+        for i in range(n):
+            _cpu_one(i, mirror[i])
+        return n / (time.perf_counter() - t0)
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+            self.pool = None
+
+
+def reference_arm(batch, cores, steps, warmup, dump=None):
+    """Times the reference CPU path (bounded sample per step) and returns the JSON fields shared by `--impl reference` and
+    the `cpu_baseline` leg of our arm."""
+    sample = batch if cores >= 32 else min(batch, max(8, 2 * cores))
+    streams = make_batch(sample, 0, min(cores, 16))
+    mirror = np.random.default_rng(0).integers(0, 2, sample)
+    ref = CpuReference(streams, cores)
+    try:
+        for _ in range(max(1, min(warmup, 2))):
+            ref.run(min(sample, max(2, cores)), mirror)
+        times = []
+        for _ in range(steps):
+            dt, _ = ref.run(sample, mirror)
+            times.append(dt)
+        single = ref.single_core(min(sample, 6), mirror)
+        if dump:
+            _, outs = ref.run(sample, mirror, keep=True)
+            np.save(dump, np.stack(outs))
+    finally:
+        ref.close()
+    t = float(sum(times))
+    return {"value": sample * steps / t, "unit": "images/s", "cores": cores, "os_cpu_count": os.cpu_count(), "kind": ref.kind,
+            "workers": f"{ref.procs} processes x {ref.threads} threads", "single_core_value": single,
+            "sample": f"{sample} images per step (bounded sample of the {batch}-image batch), {steps} steps; decode = cv2.imdecode "
+                      "(libjpeg-turbo straight to RGB, stand-in for nvimgcodec's CPU backend), resize + CMN = reference CPU kernels"
+                      + (" compiled from the reference sources (oracle/_ref)" if ref.kind == "reference" else " restated (oracle port)"),
+            "ms_per_step": 1e3 * t / steps, "median_ms_per_step": 1e3 * float(np.median(times))}, sample
 
 
 def secondary_workloads(hbm_peak, flush, steps, warmup):
@@ -223,11 +330,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-secondary", action="store_true", help="skip the C3 (video) and C4 (audio) secondary measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg of our arm")
+    ap.add_argument("--dump", default=None, help="(reference arm) save the outputs of the sample as .npy")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cores = os.cpu_count() or 1
+    cores, cpu_quota = effective_cores()
+    print(f"host: os.cpu_count()={os.cpu_count()} affinity={len(os.sched_getaffinity(0))} cgroup quota={cpu_quota} -> {cores} usable cores; "
+          f"loadavg={os.getloadavg()}", file=sys.stderr)
     batch = args.batch
     config = {"workload": "C2: 1080p JPEG (q90, 4:2:0, baseline) -> decoders.image(mixed) -> resize(224x224, triangular antialias)"
                           " -> crop_mirror_normalize(fp16, CHW, mirror, ImageNet mean/std)",
@@ -237,26 +348,22 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sample = min(batch, max(8, 2 * cores))
-        streams = make_batch(sample, 0, min(cores, 16))
-        mirror = np.random.default_rng(0).integers(0, 2, sample)
-        for _ in range(min(args.warmup, 1)):
-            cpu_reference_pipeline(streams[: max(2, cores)], cores, mirror)
-        t, kind = 0.0, "port"
-        for _ in range(args.steps):
-            dt, kind, _ = cpu_reference_pipeline(streams, cores, mirror)
-            t += dt
-        ips = sample * args.steps / t
-        line = {"impl": "reference", "metric": "images/sec decode+resize+CMN (batch 256, 1080p JPEG)", "value": ips, "unit": "images/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        cb, sample = reference_arm(batch, cores, args.steps, args.warmup, dump=args.dump)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": config,
-                "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
-                                 "sample": f"{sample} images per step (bounded sample of the {batch}-image batch); decode = cv2.imdecode "
-                                           "(libjpeg-turbo, stand-in for nvimgcodec's CPU backend)"},
-                "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
+
+    # ---- CPU baseline (rank 0, N == 1 only): the same reference arm on a bounded sample, BEFORE CUDA is initialised (the
+    #      worker processes are forked); its outputs are kept for the parity check of the timed configuration
+    cpu_baseline, cpu_dump, cpu_sample = None, None, 0
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import tempfile
+        cpu_dump = os.path.join(tempfile.gettempdir(), f"dalib200_cpu_ref_{os.getpid()}.npy")
+        cpu_baseline, cpu_sample = reference_arm(batch, cores, 2, 1, dump=cpu_dump)
 
     # ------------------------------------------------------------------ our arm
     import torch
@@ -321,6 +428,7 @@ def main():
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = world * batch / (ms_per_step / 1e3)
+    ms_median = float(np.median(step_ms))
 
     # ---- kernel breakdown (live, from the same timed region)
     agg = {}
@@ -332,7 +440,8 @@ def main():
     # algorithmic bytes of each kernel per launch (DESIGN.md "kernels"): what the kernel must move at minimum
     coef_bytes = (H // 16 + (H % 16 > 0)) * (W // 16) * 6 * 64 * 2
     plane_bytes = coef_bytes // 2
-    alg = {"jpeg_unstuff_count": J, "jpeg_unstuff_scatter": 2 * J, "jpeg_huff_sync_intra": J, "jpeg_huff_sync_tail": 0.3 * J,
+    alg = {"jpeg_unstuff_count": J, "jpeg_unstuff_scatter": 2 * J, "jpeg_huff_sync_intra": J, "jpeg_huff_sync_walk1": 0.3 * J, "jpeg_huff_sync_walk2": 0.08 * J,
+           "jpeg_huff_sync_walk3": 0.03 * J,
            "jpeg_huff_write": J + coef_bytes, "jpeg_dc_scan": 2 * coef_bytes / 64, "jpeg_idct": coef_bytes + plane_bytes,
            "jpeg_upsample_color": plane_bytes + ALG_DECODE, "resample_fused": ALG_RESIZE, "resample_stream": ALG_RESIZE, "cmn_hwc2chw": ALG_CMN}
     roofline = None
@@ -341,10 +450,11 @@ def main():
         per_launch = alg.get(dom, 0) * batch
         ach = per_launch / dur / 1e9 if dur > 0 else 0.0
         traffic, traffic_src = None, None
-        try:       # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture (per image)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_dram_traffic_v5.json")))
-            traffic = tj["kernels"][dom]["dram_bytes_per_image"] * batch
-            traffic_src = "profiles/r1_ncu_dram_traffic_v5.json (ncu --set full at batch 64, per image x batch)"
+        try:       # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture at batch 256
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_dram_traffic_batch256.json")))
+            if tj.get("batch") == batch:
+                traffic = tj["kernels"][dom]["dram_bytes_per_launch"]
+                traffic_src = "profiles/r2_ncu_dram_traffic_batch256.json (ncu --set full, --clock-control none, batch 256, per launch)"
         except Exception:
             pass
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
@@ -395,35 +505,13 @@ def main():
            "equals_device_resident_path": api_equal,
            "note": "host header parse + pinned staging + H2D + all kernels + D2H of a checksum scalar, per step"}
 
-    # ---- CPU baseline (rank 0, N == 1 only): bounded sample
-    cpu_baseline = None
-    if rank == 0 and world == 1:
-        sample = min(batch, max(8, 2 * cores))
-        cpu_reference_pipeline(streams[: max(2, min(cores, sample))], cores, mirror)       # warm
-        dt, kind, ref_out = cpu_reference_pipeline(streams[:sample], cores, mirror[:sample])
-        cpu_baseline = {"value": sample / dt, "unit": "images/s", "cores": cores, "kind": kind,
-                        "sample": f"{sample} of the {batch} images; decode = cv2.imdecode (libjpeg-turbo stand-in for nvimgcodec CPU), "
-                                  "resize + CMN = reference CPU kernels" + (" (oracle/_ref)" if kind == "reference" else " restated (oracle port)")}
-        # parity of the timed configuration against the CPU path (reported, not timed)
-        got = pipe.run(streams, mirror)[:sample].cpu().numpy()
-        want = np.stack(ref_out)
+    # ---- parity of the timed configuration against the CPU reference path (reported, not timed)
+    if cpu_baseline is not None:
+        want = np.load(cpu_dump)
+        os.remove(cpu_dump)
+        got = pipe.run(streams, mirror)[:cpu_sample].cpu().numpy()
         cpu_baseline["parity_mismatching_elements"] = int((got.view(np.uint16) != want.view(np.uint16)).sum())
         cpu_baseline["parity_elements"] = int(want.size)
-        if os.environ.get("BENCH_DEBUG_PARITY") and cpu_baseline["parity_mismatching_elements"]:
-            import cv2
-            from oracle import pyoracle as po
-            badi = [i for i in range(sample) if (got[i].view(np.uint16) != want[i].view(np.uint16)).any()]
-            print("parity debug: mismatching images", badi, file=sys.stderr)
-            for i in badi[:4]:
-                dec = cv2.imdecode(streams[i], cv2.IMREAD_COLOR)[..., ::-1]
-                gdec = pipe.decoded(i).cpu().numpy()
-                r1 = po.ref_resample(np.ascontiguousarray(dec), (OUT, OUT)); r2 = po.resample(np.ascontiguousarray(dec), (OUT, OUT))
-                gres = pipe.resized(i).cpu().numpy()
-                print("  img", i, "decode diff", int((gdec != dec).sum()), "resize gpu-vs-ref(1 thread)", int((gres != r1).sum()),
-                      "ref-vs-port", int((r1 != r2).sum()), file=sys.stderr)
-                _, _, again = cpu_reference_pipeline([streams[i]], 1, [mirror[i]])
-                print("  threaded ref vs single-thread ref", int((again[0].view(np.uint16) != want[i].view(np.uint16)).sum()),
-                      "gpu vs single-thread ref", int((again[0].view(np.uint16) != got[i].view(np.uint16)).sum()), file=sys.stderr)
 
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
@@ -452,11 +540,11 @@ def main():
         allgather = {"ms": float(t.item()), "bytes_gathered_per_rank": int(full.numel() * full.element_size()),
                      "bus_GBps": gb * (world - 1) / world / (float(t.item()) / 1e3), "shape": list(full.shape)}
     if rank == 0:
-        line = {"metric": "images/sec decode+resize+CMN (batch 256, 1080p JPEG)", "value": value, "unit": "images/s", "n_gpus": world,
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": dict(config, l2="flushed between timed iterations "
-                                                                                           "(256 MiB write) and working set 1.6 GB > L2",
-                                                                                   mean_jpeg_bytes=J),
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                "l2": "flushed between timed iterations (256 MiB write) and working set 1.6 GB > L2", "mean_jpeg_bytes": J,
+                "ms_per_step_median": ms_median, "value_at_median": world * batch / (ms_median / 1e3),
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "kernels": kernels, "op_boundary_GBps": op_gbs, "op_boundary_frac_of_hbm": op_gbs / hbm_peak,
                 "wall_s_timed_region": t_wall, "checksum": chk, "secondary": secondary, "allgather_fp16_nchw": allgather}

@@ -21,7 +21,7 @@ EXPORTS = [
     "dalib200GetLastError", "dalib200GetVersion", "dalib200GetLaunchCount", "dalib200ProfilingEnable", "dalib200ProfilingCollect",
     "dalib200JpegGetInfo", "dalib200JpegPlanCreate", "dalib200JpegPlanDestroy", "dalib200JpegPlanSetup",
     "dalib200JpegPlanGetInfo", "dalib200JpegPlanStagedBytes", "dalib200JpegUpload", "dalib200JpegLaunch",
-    "dalib200JpegGetStatus", "dalib200JpegDebugGetCoefficients",
+    "dalib200JpegGetStatus", "dalib200JpegDebugGetCoefficients", "dalib200JpegPlanSetupEx", "dalib200JpegPlanGetOutputShape",
     "dalib200ResamplePlanCreate", "dalib200ResamplePlanDestroy", "dalib200ResamplePlanSetup", "dalib200ResampleLaunch",
     "dalib200ResamplePlanGetOrder",
     "dalib200ResamplePlanGetPath",
@@ -38,6 +38,14 @@ EXPORTS = [
 class JpegInfo(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("components", C.c_int32), ("subsampling", C.c_int32),
                 ("restart_interval", C.c_int32), ("orientation", C.c_int32)]
+
+
+class JpegParams(C.Structure):
+    _fields_ = [("output_type", C.c_int32), ("fancy_upsampling", C.c_int32), ("dtype", C.c_int32), ("adjust_orientation", C.c_int32)]
+
+
+class JpegRoi(C.Structure):
+    _fields_ = [("use_roi", C.c_int32), ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32)]
 
 
 class FilterDesc(C.Structure):

@@ -116,8 +116,17 @@ __device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t *p) {
   return v;
 }
 
-// ---- mbarrier + TMA bulk copy (cp.async.bulk, sm_90+ PTX): shared by the resample ring and the warp source tiles
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// ---- shared-memory accesses through 32-bit shared-window addresses.  Hot loops that reach shared memory through generic
+// pointers make the compiler re-derive the shared window base (S2R SR_CgaCtaId / MOV / LEA) next to every access; a plain
+// integer address costs nothing.  The asm is volatile: it must stay behind the barrier that published the data.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory"); }
+
+// ---- mbarrier + TMA bulk copy (cp.async.bulk, sm_90+ PTX): shared by the resample ring and the warp source tiles
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }

@@ -22,13 +22,10 @@
 //
 // Algorithmic bytes per unit: J (encoded bytes) + H*W*3 (decoded image).
 #include "common.cuh"
-#include <cooperative_groups.h>
 #include <algorithm>
 #include <cstring>
 #include <map>
 #include <thread>
-
-namespace cg = cooperative_groups;
 
 namespace dalib200 {
 
@@ -49,7 +46,8 @@ struct HuffSlow {
 };
 
 struct TableSet {             // the 4 tables a baseline scan can reference: DC0, DC1, AC0, AC1
-  uint32_t lut[kLutWords];
+  uint32_t lut[kLutWords];    // 32-bit entries (make_entry): synchronisation passes
+  uint16_t lut16[kLutWords];  // 16-bit entries (make_entry16): write pass (half the shared memory -> 3 x 8 warps more per SM)
   HuffSlow slow[4];
 };
 __host__ __device__ inline int LutOffset(int t) { return t < 2 ? t * kDcLutSize : 2 * kDcLutSize + (t - 2) * kAcLutSize; }
@@ -71,12 +69,31 @@ struct JpegImage {
   int32_t subseq_begin;                    // first global subsequence
   int32_t nsub;                            // upper bound of subsequences (from raw length)
   int32_t block_begin;                     // first sync block
+  int32_t wblock_begin;                    // first block of the write pass (kWriteThreads subsequences each)
   int64_t coef_off;                        // int16 offset into the coefficient arena
   int64_t plane_off[3];                    // byte offsets into the plane arena
   int32_t plane_w[3], plane_h[3];          // padded plane sizes (multiples of the MCU)
   int32_t out_type, fancy;
   int32_t is_rgb;                          // Adobe transform 0 / RGB ids: no YCbCr conversion
   int32_t fast_color;                      // eligible for color_fast_kernel
+  // decode window: the pixels [win_x0, win_x0 + win_w) x [win_y0, win_y0 + win_h) of the (un-oriented) image are produced, `out`
+  // is a tight win_h x win_w x C buffer (the caller's sample, or plan scratch when a post pass follows).  win_x0 % 8 == 0.
+  int32_t win_x0, win_y0, win_w, win_h;
+  int32_t mcu_x0, mcu_y0, mcu_nx, mcu_ny;  // MCUs whose blocks the IDCT transforms (window + chroma upsampling halo)
+};
+
+// Post pass of one sample (decoders.image with output_type / dtype / orientation / unaligned ROI handling): gathers the
+// oriented region of interest from the decoded window and converts colour space and type
+// (dali/operators/imgcodec/util/convert.h:255-316 ApplyOrientation + ConvertPixel, convert_gpu.cu:75-123).
+struct JpegPost {
+  const uint8_t *src; void *dst;
+  int32_t src_w, src_c;                    // window pitch in pixels, channels (1 or 3: GRAY / RGB)
+  int32_t img_w, img_h;                    // un-oriented image size
+  int32_t win_x0, win_y0;
+  int32_t out_x0, out_y0, out_w, out_h;    // region of interest in ORIENTED image coordinates
+  int32_t orientation;                     // EXIF 1..8
+  int32_t out_type, dtype;                 // DALIB200_RGB.. / DALIB200_UINT8 | DALIB200_FLOAT
+  int64_t first_px;
 };
 
 struct JpegUnit {
@@ -130,20 +147,48 @@ __device__ __forceinline__ uint32_t load_raw_word(const uint8_t *p, uint32_t i, 
   return w;
 }
 
+// One chunk = 4096 raw bytes = 4 rounds of 256 words: thread t owns words t, 256 + t, 512 + t, 768 + t, so that the lanes of a warp
+// always touch consecutive words (coalesced loads, conflict-free shared-memory byte stores in the scatter pass).
+constexpr int kChunkRounds = kChunkBytes / (256 * 4);
+
+struct ChunkWords { uint32_t w[kChunkRounds], dm[kChunkRounds]; int nk[kChunkRounds]; };
+
+__device__ __forceinline__ ChunkWords load_chunk(const uint8_t *__restrict__ p, uint32_t c0, uint32_t len) {
+  ChunkWords cw;
+#pragma unroll
+  for (int r = 0; r < kChunkRounds; r++) {
+    const uint32_t i = (uint32_t)r * 1024u + threadIdx.x * 4u;
+    cw.w[r] = 0; cw.dm[r] = 0; cw.nk[r] = 0;
+    if (i < len) {
+      cw.w[r] = load_raw_word(p, i, len);
+      const uint32_t prev = c0 + i > 0 ? p[(int64_t)i - 1] : 0u;      // the chunk is not the first of its unit when c0 > 0
+      cw.dm[r] = dropped_mask(cw.w[r], prev);
+      cw.nk[r] = (int)min(4u, len - i) - (__popc(cw.dm[r]) >> 3);
+    }
+  }
+  return cw;
+}
+
 __global__ void __launch_bounds__(256) unstuff_count_kernel(const uint8_t *__restrict__ raw, const JpegUnit *__restrict__ units,
                                                             int nunits, uint32_t nchunks, uint32_t *__restrict__ chunk_cnt) {
   __shared__ int wsum[8];
-  for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    const int ui = find_unit_by_chunk(units, nunits, chunk);
+  __shared__ int s_ui;
+  // contiguous range of chunks per CTA: the unit is searched once and then only advanced
+  const uint32_t per = (nchunks + gridDim.x - 1) / gridDim.x;
+  const uint32_t ch0 = blockIdx.x * per, ch1 = min(nchunks, ch0 + per);
+  if (ch0 >= ch1) return;
+  if (threadIdx.x == 0) s_ui = find_unit_by_chunk(units, nunits, ch0);
+  __syncthreads();
+  int ui = s_ui;
+  for (uint32_t chunk = ch0; chunk < ch1; chunk++) {
+    while (ui + 1 < nunits && units[ui + 1].first_chunk <= chunk) ui++;
     const JpegUnit &u = units[ui];
     const uint32_t c0 = (chunk - u.first_chunk) * kChunkBytes;
     const uint32_t len = min((uint32_t)kChunkBytes, u.raw_len - c0);
+    const ChunkWords cw = load_chunk(raw + u.raw_off + c0, c0, len);
     int cnt = 0;
-    for (uint32_t i = threadIdx.x * 4; i < len; i += blockDim.x * 4) {
-      const uint32_t w = load_raw_word(raw + u.raw_off + c0, i, len);
-      const uint32_t prev = c0 + i > 0 ? raw[u.raw_off + c0 + i - 1] : 0u;
-      cnt += __popc(dropped_mask(w, prev)) >> 3;
-    }
+#pragma unroll
+    for (int r = 0; r < kChunkRounds; r++) cnt += __popc(cw.dm[r]) >> 3;
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
     __syncthreads();
@@ -152,64 +197,98 @@ __global__ void __launch_bounds__(256) unstuff_count_kernel(const uint8_t *__res
   }
 }
 
-// one thread per unit: exclusive scan of the dropped-byte counts of its chunks (units are short lists)
-__global__ void unstuff_scan_kernel(const JpegUnit *__restrict__ units, int nunits, uint32_t *__restrict__ chunk_cnt,
-                                    uint32_t *__restrict__ unit_clean_len) {
-  for (int ui = blockIdx.x * blockDim.x + threadIdx.x; ui < nunits; ui += gridDim.x * blockDim.x) {
+// one warp per unit: exclusive scan of the dropped-byte counts of its chunks
+__global__ void __launch_bounds__(256) unstuff_scan_kernel(const JpegUnit *__restrict__ units, int nunits, uint32_t *__restrict__ chunk_cnt,
+                                                           uint32_t *__restrict__ unit_clean_len) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  for (int ui = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); ui < nunits; ui += nwarps) {
     const JpegUnit &u = units[ui];
     const uint32_t nch = (u.raw_len + kChunkBytes - 1) / kChunkBytes;
     uint32_t run = 0;
-    for (uint32_t c = 0; c < nch; c++) { uint32_t v = chunk_cnt[u.first_chunk + c]; chunk_cnt[u.first_chunk + c] = run; run += v; }
-    unit_clean_len[ui] = u.raw_len - run;
+    for (uint32_t base = 0; base < nch; base += 32) {
+      const uint32_t c = base + lane;
+      const uint32_t v = c < nch ? chunk_cnt[u.first_chunk + c] : 0u;
+      uint32_t incl = v;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += x; }
+      if (c < nch) chunk_cnt[u.first_chunk + c] = run + incl - v;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) unit_clean_len[ui] = u.raw_len - run;
   }
 }
 
 // Writes the clean stream with every 32-bit word byte-swapped (address ^ 3), so that a plain 32-bit
-// load returns the big-endian bit order the Huffman reader wants.
+// load returns the big-endian bit order the Huffman reader wants.  The kept bytes of a chunk are compacted in shared
+// memory (byte stores, consecutive lanes -> consecutive words) and leave as whole swapped words; only the two words a
+// chunk shares with its neighbours are written byte by byte.
 __global__ void __launch_bounds__(256) unstuff_scatter_kernel(const uint8_t *__restrict__ raw, const JpegUnit *__restrict__ units,
                                                               int nunits, uint32_t nchunks, const uint32_t *__restrict__ chunk_drop,
                                                               uint8_t *__restrict__ clean) {
-  __shared__ int wsum[8];
-  __shared__ int carry_s;
-  for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    const int ui = find_unit_by_chunk(units, nunits, chunk);
+  __shared__ int wsum[8][kChunkRounds];
+  __shared__ uint32_t obuf[kChunkBytes / 4 + 2];
+  __shared__ int s_ui;
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const uint32_t per = (nchunks + gridDim.x - 1) / gridDim.x;
+  const uint32_t ch0 = blockIdx.x * per, ch1 = min(nchunks, ch0 + per);
+  if (ch0 >= ch1) return;
+  if (threadIdx.x == 0) s_ui = find_unit_by_chunk(units, nunits, ch0);
+  __syncthreads();
+  int ui = s_ui;
+  for (uint32_t chunk = ch0; chunk < ch1; chunk++) {
+    while (ui + 1 < nunits && units[ui + 1].first_chunk <= chunk) ui++;
     const JpegUnit &u = units[ui];
     const uint32_t c0 = (chunk - u.first_chunk) * kChunkBytes;
     const uint32_t len = min((uint32_t)kChunkBytes, u.raw_len - c0);
-    uint32_t out_base = u.clean_off + c0 - chunk_drop[chunk];
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < len; base += blockDim.x * 4) {
-      // each thread owns 4 consecutive bytes (one aligned word)
-      const uint32_t i0 = base + threadIdx.x * 4;
-      uint8_t b[4]; bool keep[4]; int nk = 0;
-      {
-        uint32_t w = 0, dm = 0;
-        if (i0 < len) {
-          w = load_raw_word(raw + u.raw_off + c0, i0, len);
-          const uint32_t prev = c0 + i0 > 0 ? raw[u.raw_off + c0 + i0 - 1] : 0u;
-          dm = dropped_mask(w, prev);
-        }
+    const uint32_t out_base = u.clean_off + c0 - chunk_drop[chunk];
+    const ChunkWords cw = load_chunk(raw + u.raw_off + c0, c0, len);
+    int incl[kChunkRounds];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          b[k] = (uint8_t)(w >> (8 * k));
-          keep[k] = i0 + k < len && !((dm >> (8 * k)) & 1u);
-          nk += keep[k];
-        }
-      }
-      int incl = nk;
-      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += v; }
-      if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
-      __syncthreads();
-      int woff = 0, tot = 0;
-      for (int w = 0; w < 8; w++) { if (w < (int)(threadIdx.x >> 5)) woff += wsum[w]; tot += wsum[w]; }
-      uint32_t pos = out_base + carry_s + woff + incl - nk;
+    for (int r = 0; r < kChunkRounds; r++) incl[r] = cw.nk[r];
+    for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) if (keep[k]) { clean[(pos & ~3u) | (3u - (pos & 3u))] = b[k]; pos++; }
-      __syncthreads();
-      if (threadIdx.x == 0) carry_s += tot;
-      __syncthreads();
+      for (int r = 0; r < kChunkRounds; r++) { const int v = __shfl_up_sync(0xffffffffu, incl[r], o); if (lane >= (uint32_t)o) incl[r] += v; }
     }
+    if (lane == 31) {
+#pragma unroll
+      for (int r = 0; r < kChunkRounds; r++) wsum[wid][r] = incl[r];
+    }
+    __syncthreads();
+    const uint32_t head = out_base & 3u;                      // obuf word k <-> clean word (out_base >> 2) + k
+    uint32_t total = 0;
+    uint8_t *ob = reinterpret_cast<uint8_t *>(obuf);
+#pragma unroll
+    for (int r = 0; r < kChunkRounds; r++) {
+      int woff = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) { if (w < (int)wid) woff += wsum[w][r]; tot += wsum[w][r]; }
+      uint32_t pos = head + total + (uint32_t)(woff + incl[r] - cw.nk[r]);
+      const uint32_t i = (uint32_t)r * 1024u + threadIdx.x * 4u;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (i + k < len && !((cw.dm[r] >> (8 * k)) & 1u)) ob[pos++] = (uint8_t)(cw.w[r] >> (8 * k));
+      total += (uint32_t)tot;
+    }
+    __syncthreads();
+    const uint32_t nwords = (head + total + 3u) >> 2, tailb = (head + total) & 3u;
+    uint32_t *cw32 = reinterpret_cast<uint32_t *>(clean) + (out_base >> 2);
+    for (uint32_t wd = threadIdx.x; wd < nwords; wd += blockDim.x) {
+      const uint32_t v = obuf[wd];
+      const bool full = (wd > 0 || head == 0) && (wd + 1 < nwords || tailb == 0);
+      if (full) {
+        cw32[wd] = __byte_perm(v, 0u, 0x0123);
+      } else {
+        const uint32_t lo = wd == 0 ? head : 0u, hi = (wd + 1 == nwords && tailb) ? tailb : 4u;
+        for (uint32_t b = lo; b < hi; b++) reinterpret_cast<uint8_t *>(cw32 + wd)[3u - b] = (uint8_t)(v >> (8 * b));
+      }
+    }
+    if (c0 + kChunkBytes >= u.raw_len) {
+      // last chunk of the unit: zero the pad behind the clean bytes (the bit reader peeks a few bytes past the end); the
+      // clean buffer itself is never memset
+      const uint32_t e0 = out_base + total, e1 = u.clean_off + ((u.raw_len + 32u + 15u) & ~15u);
+      for (uint32_t q = e0 + threadIdx.x; q < e1; q += blockDim.x) clean[(q & ~3u) | (3u - (q & 3u))] = 0;
+    }
+    __syncthreads();
   }
 }
 
@@ -220,9 +299,13 @@ __global__ void __launch_bounds__(256) unstuff_scatter_kernel(const uint8_t *__r
 // subsequences (+ one look-ahead column) into shared memory with coalesced 16-byte loads; word g of the staged run sits at
 // g ^ ((g >> lsw) & 31) so that the 32 lanes of a warp, each inside its own subsequence, always hit 32 different banks.
 struct SmemSrc {
-  const uint32_t *w; int lsw;
-  __device__ __forceinline__ uint32_t load(uint32_t g) const { return w[g ^ ((g >> lsw) & 31u)]; }
+  uint32_t base; int lsw;                  // shared-window address of the staged run
+  __device__ __forceinline__ uint32_t load(uint32_t g) const { return lds_u32(base + ((g ^ ((g >> lsw) & 31u)) << 2)); }
 };
+// table accessors: first-level LUT (32-bit entries) and the per-block (dc | ac << 16) table offsets
+struct SmemLut { uint32_t base; __device__ __forceinline__ uint32_t load(uint32_t i) const { return lds_u32(base + (i << 2)); } };
+struct GlobalLut { const uint32_t *p; __device__ __forceinline__ uint32_t load(uint32_t i) const { return __ldg(p + i); } };
+template <int STRIDE> struct SmemTbl { uint32_t base; __device__ __forceinline__ uint32_t load(int c) const { return lds_u32(base + (uint32_t)c * (STRIDE * 4u)); } };
 struct GlobalSrc {
   const uint32_t *w;
   __device__ __forceinline__ uint32_t load(uint32_t g) const { return __ldg(w + g); }
@@ -255,9 +338,16 @@ struct BitWindow {
   }
 };
 
-__device__ __forceinline__ uint64_t pack_state(uint32_t p, int c, int z) {
-  return (uint64_t)p | ((uint64_t)(uint32_t)c << 32) | ((uint64_t)(uint32_t)z << 40);
+// Per-subsequence record of the synchronisation (one 64-bit word, updated with atomicMax in the chain walk):
+//   [31:0] exit bit position  [35:32] block in MCU (c)  [41:36] zig-zag index (z)  [51:42] blocks completed in the subsequence
+//   [63:52] priority t = distance of the chain that wrote the record from its origin (x - origin): the larger, the further
+//   left the chain started, the better informed it is.  The state proper is the low 42 bits.
+constexpr uint64_t kStateMask = (1ull << 42) - 1;
+constexpr uint32_t kMaxChainLen = 4095;
+__device__ __forceinline__ uint64_t pack_state(uint32_t p, int c, int z, uint32_t cnt = 0, uint32_t t = 0) {
+  return (uint64_t)p | ((uint64_t)(uint32_t)c << 32) | ((uint64_t)(uint32_t)z << 36) | ((uint64_t)min(cnt, 1023u) << 42) | ((uint64_t)t << 52);
 }
+__device__ __forceinline__ uint32_t state_count(uint64_t s) { return (uint32_t)(s >> 42) & 1023u; }
 
 // LUT entry (host: MakeLutEntry): [4:0] bits consumed (code + magnitude, <= 31), [11:8] magnitude size s, [16:12] code
 // length, [26:20] zig-zag advance (run + 1; 16 for ZRL; 64 for EOB; 1 for DC).  0 = code longer than the first-level width.
@@ -269,9 +359,17 @@ __device__ __forceinline__ uint32_t make_entry(uint32_t len, uint32_t sym, bool 
   return (len + s) | (s << 8) | (len << 12) | (adv << 20);
 }
 
+// 16-bit entry of the write pass (host: MakeLutEntry16): [4:0] bits consumed, [8:5] magnitude size s, [15:9] zig-zag advance;
+// code length = consumed - s.  0 = code longer than the first-level width.
+__device__ __forceinline__ uint32_t make_entry16(uint32_t len, uint32_t sym, bool is_dc) {
+  const uint32_t s = sym & 15u, r = sym >> 4;
+  const uint32_t adv = is_dc ? 1u : (s == 0 ? (r == 15u ? 16u : 64u) : r + 1u);
+  return (len + s) | (s << 5) | (adv << 9);
+}
+
 // codes longer than the first-level LUT (std tables: AC codes of 12..16 bits, < 1 % of the symbols): canonical search,
-// T.81 F.2.2.3.  `toff` = LUT word offset of the table, which identifies it.
-__device__ __noinline__ uint32_t slow_symbol(const HuffSlow *__restrict__ slow, uint32_t toff, uint32_t hi, bool is_dc) {
+// T.81 F.2.2.3.  `toff` = LUT word offset of the table, which identifies it.  Returns code length | symbol << 8.
+__device__ __noinline__ uint32_t slow_lookup(const HuffSlow *__restrict__ slow, uint32_t toff, uint32_t hi, bool is_dc) {
   const int tbl = toff < 2u * kDcLutSize ? (int)(toff / kDcLutSize) : 2 + (int)((toff - 2u * kDcLutSize) / kAcLutSize);
   const HuffSlow *sl = slow + tbl;
   const int32_t code16 = (int32_t)(hi >> 16);
@@ -280,41 +378,33 @@ __device__ __noinline__ uint32_t slow_symbol(const HuffSlow *__restrict__ slow, 
   uint32_t sym = 0;
   if (len > 16) len = 16;                                    // corrupt / speculative: keep going deterministically
   else sym = sl->vals[(sl->valoff[len] + (code16 >> (16 - len))) & 0xFF];
-  return make_entry(len, sym, is_dc);
+  return len | (sym << 8);
+}
+__device__ __forceinline__ uint32_t slow_symbol(const HuffSlow *__restrict__ slow, uint32_t toff, uint32_t hi, bool is_dc) {
+  const uint32_t ls = slow_lookup(slow, toff, hi, is_dc);
+  return make_entry(ls & 0xFFu, ls >> 8, is_dc);
+}
+__device__ __forceinline__ uint32_t slow_symbol16(const HuffSlow *__restrict__ slow, uint32_t toff, uint32_t hi, bool is_dc) {
+  const uint32_t ls = slow_lookup(slow, toff, hi, is_dc);
+  return make_entry16(ls & 0xFFu, ls >> 8, is_dc);
 }
 
-// Decodes the symbols that START before `end` (absolute bit positions inside the unit).  State = (pos, c, z); `nb` counts
-// completed blocks.  When WRITE, stores the coefficients of block `blk0 + nb` (natural order; DC terms -- still
-// differential -- into the compact per-block array) and stops at `blk_limit`.  Branch-free apart from the loop, the rare
-// long-code path and the predicated store.
-template <bool WRITE, class Src, int TBL_STRIDE = 1>
-__device__ __forceinline__ void decode_span(const Src &src, BitWindow<Src> &win, const uint32_t *__restrict__ lut,
-                                            const HuffSlow *__restrict__ slow, const uint32_t *__restrict__ s_tbl, int bpm,
-                                            uint32_t &pos, uint32_t end, int &c, int &z, uint32_t &nb,
-                                            int16_t *__restrict__ coef, int16_t *__restrict__ dcv, const uint8_t *__restrict__ s_zig,
-                                            uint32_t blk0, uint32_t blk_limit) {
-  uint32_t tb12 = s_tbl[c * TBL_STRIDE];                      // dc table offset | ac table offset << 16 (in LUT words)
+// Decodes the symbols that START before `end` (absolute bit positions inside the unit) without producing coefficients: the
+// synchronisation only needs the state (pos, c, z) and `nb`, the number of completed blocks.  Branch-free apart from the loop
+// and the rare long-code path.
+template <class Src, class Lut, class Tbl>
+__device__ __forceinline__ void decode_span(const Src &src, BitWindow<Src> &win, const Lut &lut, const HuffSlow *__restrict__ slow,
+                                            const Tbl &tbl, int bpm, uint32_t &pos, uint32_t end, int &c, int &z, uint32_t &nb) {
+  uint32_t tb12 = tbl.load(c);                                // dc table offset | ac table offset << 16 (in LUT words)
   while (pos < end) {
-    if (WRITE && blk0 + nb >= blk_limit) break;
     // the AC entry is fetched before z is known (it is the common case and sits on the loop-carried path); the DC entry only
     // by the lanes that start a block, so that its random-bank lookup costs one shared-memory wavefront instead of three
-    const uint32_t e_ac = lut[(tb12 >> 16) + (win.hi >> (32 - kAcLutBits))];
+    const uint32_t e_ac = lut.load((tb12 >> 16) + (win.hi >> (32 - kAcLutBits)));
     const bool is_dc = z == 0;
     uint32_t e = e_ac;
-    if (is_dc) e = lut[(tb12 & 0xFFFFu) + (win.hi >> (32 - kDcLutBits))];
+    if (is_dc) e = lut.load((tb12 & 0xFFFFu) + (win.hi >> (32 - kDcLutBits)));
     if (__builtin_expect(e == 0, 0)) e = slow_symbol(slow, is_dc ? (tb12 & 0xFFFFu) : (tb12 >> 16), win.hi, is_dc);
     const uint32_t tb = e & 31u, adv = e >> 20;
-    if (WRITE) {
-      const uint32_t s = (e >> 8) & 15u;
-      if (s) {
-        const uint32_t len = (e >> 12) & 31u;
-        const uint32_t bits = ((win.hi << len) >> 1) >> (31u - s);
-        const int v = (int)bits - (((bits >> (s - 1u)) & 1u) ? 0 : (int)((1u << s) - 1u));     // EXTEND, T.81 F.2.2.1
-        const uint32_t blk = blk0 + nb;
-        if (is_dc) dcv[blk] = (int16_t)v;
-        else coef[(size_t)blk * 64 + s_zig[min((uint32_t)z + adv - 1u, 63u)]] = (int16_t)v;
-      }
-    }
     win.consume(src, e);
     pos += tb;
     z += (int)adv;
@@ -323,7 +413,7 @@ __device__ __forceinline__ void decode_span(const Src &src, BitWindow<Src> &win,
     nb += endb ? 1u : 0u;
     c = endb ? c1 : c;
     z = endb ? 0 : z;
-    if (endb) tb12 = s_tbl[c * TBL_STRIDE];
+    if (endb) tb12 = tbl.load(c);
   }
 }
 
@@ -339,18 +429,20 @@ __device__ __forceinline__ int find_unit_by_subseq(const JpegUnit *u, int ub, in
 struct HuffCtx {
   const JpegImage *images; int nimages;
   const int32_t *block_image;           // sync block -> image
+  const int32_t *wblock_image;          // write block -> image
   const JpegUnit *units;
   const uint32_t *unit_clean_len;
   const TableSet *tables;
   const uint8_t *clean;
-  uint64_t *s_state; uint32_t *s_n;     // per subsequence: exit state; completed blocks (after H2b: exclusive prefix per unit)
+  uint64_t *s_state;       // per subsequence: packed record (pack_state)
+  uint32_t *s_n;           // per subsequence: exclusive prefix (per unit) of the completed-block counts (H2b)
   int16_t *coef;
   int16_t *dc;             // compact DC array: one int16 per block, same block order as coef
   int log2_sub;            // log2 of the subsequence size in BITS
   int32_t *status;         // per image: 0 ok, 1 = block count mismatch (corrupt stream)
-  // live chains of the synchronisation (H2a): record = (bit position, c | z << 8, target subsequence, image)
-  uint4 *chains[4];        // [0] = chains that leave their sync block in round 1, [1..3] = rotating lists of rounds >= 2
-  uint32_t *chain_count;   // [4]
+  // live chains of the synchronisation: record = (bit position, c | z << 8 | t << 16, target subsequence, image)
+  uint4 *chains[3];        // [0] filled by H1, [1] survivors of the first walk step, [2] survivors of the second
+  uint32_t *chain_count;   // [3]
 };
 
 __device__ __forceinline__ uint32_t tbl_word(const JpegImage &im, int b) {
@@ -442,15 +534,15 @@ __device__ __forceinline__ SubGeom sync_block_prologue(const HuffCtx &cx, const 
   return sg;
 }
 
-__device__ __forceinline__ void push_chain(const HuffCtx &cx, int list, uint32_t pos, int c, int z, int64_t g, int img) {
+__device__ __forceinline__ void push_chain(const HuffCtx &cx, int list, uint32_t pos, int c, int z, uint32_t t, int64_t g, int img) {
   const uint32_t k = atomicAdd(&cx.chain_count[list], 1u);
-  cx.chains[list][k] = make_uint4(pos, (uint32_t)c | ((uint32_t)z << 8), (uint32_t)g, (uint32_t)img);
+  cx.chains[list][k] = make_uint4(pos, (uint32_t)c | ((uint32_t)z << 8) | (t << 16), (uint32_t)g, (uint32_t)img);
 }
 
 // H1: every thread decodes its own subsequence speculatively from (c, z) = (0, 0) (round 0) and then the following one from
 // its exit state (round 1).  A chain whose exit state does not yet agree with what the owner of that subsequence found is
-// still "live": it is handed to the grid-wide rounds of H2a.  Chain i visits subsequence i + t in round t, so every
-// subsequence is touched by at most one chain per round; rounds are separated by barriers: the result is deterministic.
+// still "live": it is handed to the chain walk (H2a).  Records carry the priority t = (subsequence - origin of the chain that
+// wrote it): 0 for the owner's own speculative decode, 1 for the visit of the left neighbour.
 __global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx cx) {
   extern __shared__ __align__(16) uint32_t hsm[];
   const SyncSmem sm = carve_sync_smem(hsm, cx.log2_sub);
@@ -459,14 +551,16 @@ __global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx c
   const SubGeom sg = sync_block_prologue(cx, im, sm);
   const HuffSlow *slow = sm.slow;
   const int lsw = cx.log2_sub - 5;
-  const SmemSrc src{sm.sw, lsw};
+  const SmemSrc src{smem_u32(sm.sw), lsw};
+  const SmemLut lut{smem_u32(sm.lut)};
+  const SmemTbl<1> tbl{smem_u32(sm.tbl)};
   BitWindow<SmemSrc> win;
   uint32_t pos = sg.jl << cx.log2_sub, nb = 0;
   int c = 0, z = 0;
   // ---- round 0
   if (sg.valid) {
     win.init(src, (uint32_t)threadIdx.x << lsw, 0);
-    decode_span<false>(src, win, sm.lut, slow, sm.tbl, im.bpm, pos, sm.col_end[threadIdx.x], c, z, nb, nullptr, nullptr, nullptr, 0, 0);
+    decode_span(src, win, lut, slow, tbl, im.bpm, pos, sm.col_end[threadIdx.x], c, z, nb);
     sm.exitst[threadIdx.x] = pack_state(pos, c, z);
     sm.cnt[threadIdx.x] = nb;
   }
@@ -474,82 +568,102 @@ __global__ void __launch_bounds__(kSyncThreads) huff_sync_intra_kernel(HuffCtx c
   // ---- round 1: the window simply continues into the next column; the last thread's next column belongs to the next block
   if (sm.col_cont[threadIdx.x]) {
     if (threadIdx.x + 1 == kSyncThreads) {
-      push_chain(cx, 0, pos, c, z, sg.g + 1, img_i);
+      push_chain(cx, 0, pos, c, z, 1u, sg.g + 1, img_i);
     } else {
       const uint32_t x = threadIdx.x + 1;
       nb = 0;
-      decode_span<false>(src, win, sm.lut, slow, sm.tbl, im.bpm, pos, sm.col_end[x], c, z, nb, nullptr, nullptr, nullptr, 0, 0);
+      decode_span(src, win, lut, slow, tbl, im.bpm, pos, sm.col_end[x], c, z, nb);
       const uint64_t ns = pack_state(pos, c, z);
-      // The count is ALWAYS rewritten: a chain that merely converged inside this subsequence entered it in a different
-      // state than the previous visitor; chains started further left arrive later and are the better informed ones.
+      // The record is ALWAYS rewritten: a chain that merely converged inside this subsequence entered it in a different
+      // state than the previous visitor; the chain that started further left is the better informed one.
       const bool same = sm.exitst[x] == ns;
       sm.exitst[x] = ns; sm.cnt[x] = nb;
-      if (!same && sm.col_cont[x]) push_chain(cx, 1, pos, c, z, sg.g + 2, img_i);
+      if (!same && sm.col_cont[x]) push_chain(cx, 0, pos, c, z, 2u, sg.g + 2, img_i);
     }
   }
   __syncthreads();
-  if (sg.valid) { cx.s_state[sg.g] = sm.exitst[threadIdx.x]; cx.s_n[sg.g] = sm.cnt[threadIdx.x]; }
+  if (sg.valid) {
+    const uint32_t t = threadIdx.x > 0 && sm.col_cont[threadIdx.x - 1] ? 1u : 0u;       // visited by the left neighbour above
+    cx.s_state[sg.g] = sm.exitst[threadIdx.x] | ((uint64_t)min(sm.cnt[threadIdx.x], 1023u) << 42) | ((uint64_t)t << 52);
+  }
 }
 
-// H2a: the remaining rounds, grid wide (cooperative launch).  One thread per live chain; a chain decodes ONE subsequence per
-// round, compares with the stored exit state, overwrites it and stays alive while they differ.  Every thread first copies
-// its subsequence (+ look-ahead) into a private shared-memory column ([word][thread]: bank = thread, conflict free), the
-// tables are shared by the CTA.  List 0 (chains that crossed a sync-block boundary in round 1) is processed first so that
-// all chains of a later round are in the same round.
+// H2a: the chain walk.  One thread per live chain; a visit decodes ONE subsequence from the chain's state, publishes the
+// result with atomicMax on the packed record (priority in the top bits) and compares with the record it replaced:
+//   * the old record has a higher priority -> a better informed chain (one that started further left) has already been here;
+//     it covers everything this chain would do: the chain dies without having modified the record;
+//   * equal states -> synchronised: everything to the right was decoded from the right entry state: the chain dies;
+//   * otherwise the chain moves on to the next subsequence with priority + 1.
+// The record of a subsequence therefore always belongs to the best informed visitor so far, whatever the order of arrival:
+// no rounds, no grid-wide barriers (the previous version spent 34 stall cycles per issue in grid.sync()), and the result
+// is deterministic because max() is.  The true chain of a unit (origin = its first subsequence) has the highest priority
+// everywhere, is never overtaken and only stops where the record already equals the true state -- which was then written
+// by a visitor that carries it on.  The walk is issued as three launches over compacted lists: two single-visit steps
+// (30 % / 8 % of the subsequences still carry a live chain) keep the warps full, the last launch follows the few long
+// chains to their end.  Every thread copies its subsequence (+ look-ahead) into a private shared-memory column
+// ([word][thread]: bank = thread, conflict free); the tables are shared by the CTA.
 constexpr int kTailThreads = 256;
 constexpr int kTailColWords = 36;          // 128-byte subsequence + 16 bytes of look-ahead
 struct ColSrc {
-  const uint32_t *w;                       // &column[0][threadIdx.x]
-  __device__ __forceinline__ uint32_t load(uint32_t g) const { return w[g * kTailThreads]; }
+  uint32_t base;                           // shared-window address of column[0][threadIdx.x]
+  __device__ __forceinline__ uint32_t load(uint32_t g) const { return lds_u32(base + g * (kTailThreads * 4u)); }
 };
 
-__device__ __forceinline__ void tail_step(const HuffCtx &cx, const uint4 rec, int out_list, const uint32_t *s_lut, const HuffSlow *s_slow,
-                                          int s_table_set, uint32_t *col, uint32_t *tblcol) {
+__device__ __forceinline__ void walk_chain(const HuffCtx &cx, const uint4 rec, int out_list, int max_visits, const uint32_t *s_lut,
+                                           const HuffSlow *s_slow, int s_table_set, uint32_t *col, uint32_t *tblcol) {
   const int img_i = (int)rec.w;
   const JpegImage &im = cx.images[img_i];
-  const int64_t g = rec.z;
+  int64_t g = rec.z;
   const int j = (int)(g - im.subseq_begin);
   const int ui = im.unit_end - im.unit_begin == 1 ? im.unit_begin : find_unit_by_subseq(cx.units, im.unit_begin, im.unit_end, j);
   const JpegUnit &u = cx.units[ui];
   const uint32_t clean_bits = cx.unit_clean_len[ui] * 8u;
   const uint32_t nsub_eff = (clean_bits + (1u << cx.log2_sub) - 1) >> cx.log2_sub;
-  const uint32_t jl = (uint32_t)(j - u.first_subseq);
+  uint32_t jl = (uint32_t)(j - u.first_subseq);
 #pragma unroll
   for (int b = 0; b < kMaxBlocksPerMcu; b++) tblcol[b * kTailThreads] = tbl_word(im, b);       // private column: bank = thread
   const bool shared_tables = im.table_set == s_table_set;
-  uint32_t pos = rec.x, nb = 0;
+  uint32_t pos = rec.x, t = rec.y >> 16;
   int c = (int)(rec.y & 0xFF), z = (int)((rec.y >> 8) & 0xFF);
-  const uint32_t end = min((jl + 1) << cx.log2_sub, clean_bits);
   const int sub_words = 1 << (cx.log2_sub - 5);
-  if (shared_tables && sub_words + 4 <= kTailColWords) {
-    // private column: words [0, sub_words + 4) of this subsequence
-    const uint4 *p4 = reinterpret_cast<const uint4 *>(cx.clean + u.clean_off + ((size_t)jl << (cx.log2_sub - 3)));
-    for (int q = 0; q < sub_words / 4 + 1; q++) {
-      const uint4 v = __ldg(p4 + q);
-      col[(4 * q + 0) * kTailThreads] = v.x; col[(4 * q + 1) * kTailThreads] = v.y;
-      col[(4 * q + 2) * kTailThreads] = v.z; col[(4 * q + 3) * kTailThreads] = v.w;
+  for (int visit = 0;;) {
+    uint32_t nb = 0;
+    const uint32_t end = min((jl + 1) << cx.log2_sub, clean_bits);
+    if (shared_tables && sub_words + 4 <= kTailColWords) {
+      // private column: words [0, sub_words + 4) of this subsequence
+      const uint4 *p4 = reinterpret_cast<const uint4 *>(cx.clean + u.clean_off + ((size_t)jl << (cx.log2_sub - 3)));
+      for (int q = 0; q < sub_words / 4 + 1; q++) {
+        const uint4 v = __ldg(p4 + q);
+        col[(4 * q + 0) * kTailThreads] = v.x; col[(4 * q + 1) * kTailThreads] = v.y;
+        col[(4 * q + 2) * kTailThreads] = v.z; col[(4 * q + 3) * kTailThreads] = v.w;
+      }
+      const ColSrc src{smem_u32(col)};
+      const uint32_t rel = pos - (jl << cx.log2_sub);
+      BitWindow<ColSrc> win;
+      win.init(src, rel >> 5, rel & 31u);
+      decode_span(src, win, SmemLut{smem_u32(s_lut)}, s_slow, SmemTbl<kTailThreads>{smem_u32(tblcol)}, im.bpm, pos, end, c, z, nb);
+    } else {
+      // another table set than the one this CTA keeps in shared memory (mixed batches), or an oversized subsequence: global path
+      const GlobalSrc src{reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off)};
+      BitWindow<GlobalSrc> win;
+      win.init(src, pos >> 5, pos & 31u);
+      decode_span(src, win, GlobalLut{cx.tables[im.table_set].lut}, cx.tables[im.table_set].slow, SmemTbl<kTailThreads>{smem_u32(tblcol)},
+                  im.bpm, pos, end, c, z, nb);
     }
-    const ColSrc src{col};
-    const uint32_t rel = pos - (jl << cx.log2_sub);
-    BitWindow<ColSrc> win;
-    win.init(src, rel >> 5, rel & 31u);
-    decode_span<false, ColSrc, kTailThreads>(src, win, s_lut, s_slow, tblcol, im.bpm, pos, end, c, z, nb, nullptr, nullptr, nullptr, 0, 0);
-  } else {
-    // another table set than the one this CTA keeps in shared memory (mixed batches), or an oversized subsequence: global path
-    const GlobalSrc src{reinterpret_cast<const uint32_t *>(cx.clean + u.clean_off)};
-    BitWindow<GlobalSrc> win;
-    win.init(src, pos >> 5, pos & 31u);
-    decode_span<false, GlobalSrc, kTailThreads>(src, win, cx.tables[im.table_set].lut, cx.tables[im.table_set].slow, tblcol, im.bpm, pos, end,
-                                                c, z, nb, nullptr, nullptr, nullptr, 0, 0);
+    const uint64_t ns = pack_state(pos, c, z, nb, t);
+    const uint64_t old = atomicMax(reinterpret_cast<unsigned long long *>(cx.s_state + g), (unsigned long long)ns);
+    if ((uint32_t)(old >> 52) >= t) break;                    // overtaken by a better informed chain
+    if (((old ^ ns) & kStateMask) == 0) break;                // synchronised
+    if (jl + 1 >= nsub_eff || t >= kMaxChainLen) break;       // end of the unit (or an absurdly long chain: corrupt data)
+    g++; jl++; t++;
+    if (++visit >= max_visits) { push_chain(cx, out_list, pos, c, z, t, g, img_i); break; }
   }
-  const uint64_t ns = pack_state(pos, c, z);
-  const bool same = cx.s_state[g] == ns;
-  cx.s_state[g] = ns; cx.s_n[g] = nb;                       // always: see huff_sync_intra_kernel
-  if (!same && jl + 1 < nsub_eff) push_chain(cx, out_list, pos, c, z, g + 1, img_i);
 }
 
-__global__ void __launch_bounds__(kTailThreads) huff_sync_tail_kernel(HuffCtx cx) {
+__global__ void __launch_bounds__(kTailThreads) huff_sync_walk_kernel(HuffCtx cx, int in_list, int out_list, int max_visits) {
   extern __shared__ __align__(16) uint32_t tsm[];
+  const uint32_t n = cx.chain_count[in_list];
+  if (blockIdx.x * blockDim.x >= n) return;                  // launched for an upper bound of the list length
   uint32_t *s_lut = tsm;
   HuffSlow *s_slow = reinterpret_cast<HuffSlow *>(s_lut + kLutWords);
   uint32_t *col = reinterpret_cast<uint32_t *>(s_slow + 4) + threadIdx.x;
@@ -564,24 +678,8 @@ __global__ void __launch_bounds__(kTailThreads) huff_sync_tail_kernel(HuffCtx cx
     for (int i = threadIdx.x; i < (int)(4 * sizeof(HuffSlow) / 4); i += blockDim.x) sdst[i] = __ldg(ssrc + i);
   }
   __syncthreads();
-  cg::grid_group grid = cg::this_grid();
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-  // round 1 of the chains that left their sync block: survivors join list 1 (round 2)
-  for (uint32_t i = gtid, n = cx.chain_count[0]; i < n; i += gsize) tail_step(cx, cx.chains[0][i], 1, s_lut, s_slow, s_table_set, col, tblcol);
-  grid.sync();
-  // Three rotating lists: round r reads list `cur`, appends to `nxt`, and the third one -- read in the previous round, appended
-  // to in the next -- is reset meanwhile.  (With two lists the reset of the list just read would race with the appends of
-  // the next round, which start right behind the grid barrier.)
-  int cur = 1;
-  for (;;) {
-    const uint32_t n = cx.chain_count[cur];
-    if (n == 0) break;
-    const int nxt = cur == 3 ? 1 : cur + 1, idle = nxt == 3 ? 1 : nxt + 1;
-    if (gtid == 0) cx.chain_count[idle] = 0;
-    for (uint32_t i = gtid; i < n; i += gsize) tail_step(cx, cx.chains[cur][i], nxt, s_lut, s_slow, s_table_set, col, tblcol);
-    grid.sync();                                             // everybody has read chain_count[cur] and appended its survivors
-    cur = nxt;
-  }
+  for (uint32_t i = gtid; i < n; i += gsize) walk_chain(cx, cx.chains[in_list][i], out_list, max_visits, s_lut, s_slow, s_table_set, col, tblcol);
 }
 
 // H2b: one CTA per image: per-unit exclusive scan of the block counts (in place), status check.
@@ -600,7 +698,7 @@ __global__ void __launch_bounds__(1024) huff_scan_kernel(HuffCtx cx) {
     __syncthreads();
     for (uint32_t base = 0; base < nsub_eff; base += blockDim.x) {
       const uint32_t i = base + threadIdx.x;
-      const uint32_t v = i < nsub_eff ? cx.s_n[g0 + i] : 0u;
+      const uint32_t v = i < nsub_eff ? state_count(cx.s_state[g0 + i]) : 0u;
       uint32_t incl = v;
       for (int o = 1; o < 32; o <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += x; }
       if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
@@ -625,18 +723,89 @@ __global__ void __launch_bounds__(1024) huff_scan_kernel(HuffCtx cx) {
 // (word j of lane l at l * 32 + (j ^ l): conflict free for the per-symbol 16-bit scatter of all lanes to the same j and for the
 // flush) and the warp writes each finished block to HBM as ONE coalesced 128-byte line: no memset of the coefficient arena,
 // no 2-byte read-modify-write traffic, ~12x fewer store wavefronts than a per-symbol scatter.
-__global__ void __launch_bounds__(kSyncThreads) huff_write_kernel(HuffCtx cx) {
+//
+// The loop is a chain of dependent fixed-latency instructions (ncu, round 1: "wait" 2.05 + "short scoreboard" 1.0 cycles per
+// issue at 16 warps/SM, 55 % issue-active): throughput scales with resident warps.  The pass therefore runs its own block
+// shape -- kWriteThreads = 384 subsequences per CTA, 16-bit LUT entries (10 KB instead of 20), prologue scratch aliased with
+// the block buffers: 108 KB per CTA -> 2 CTAs = 24 warps per SM (was 2 x 8).
+constexpr int kWriteThreads = 384;
+struct WriteSmem {
+  uint16_t *lut; uint32_t *sw, *tbl, *blkbuf; uint8_t *zig; HuffSlow *slow; const uint8_t **colptr;
+};
+__host__ __device__ inline size_t write_sw_words(int log2_sub) { return (size_t)(kWriteThreads + look_ahead_cols(log2_sub)) << (log2_sub - 5); }
+__host__ __device__ inline size_t write_smem_bytes(int log2_sub) {
+  return kLutWords * 2 + write_sw_words(log2_sub) * 4 + 16 * 4 /*tbl*/ + 64 /*zig*/ + 4 * sizeof(HuffSlow) + (size_t)kWriteThreads * 128;
+}
+__device__ __forceinline__ WriteSmem carve_write_smem(uint32_t *base, int log2_sub) {
+  WriteSmem s;
+  s.lut = reinterpret_cast<uint16_t *>(base);
+  s.sw = base + kLutWords / 2;
+  s.tbl = s.sw + write_sw_words(log2_sub);
+  s.zig = reinterpret_cast<uint8_t *>(s.tbl + 16);
+  s.slow = reinterpret_cast<HuffSlow *>(s.zig + 64);
+  s.blkbuf = reinterpret_cast<uint32_t *>(s.slow + 4);                       // 16-byte aligned: every size above is a multiple of 16
+  s.colptr = reinterpret_cast<const uint8_t **>(s.blkbuf);                  // prologue only, (kWriteThreads + 8) * 8 bytes
+  return s;
+}
+
+__global__ void __launch_bounds__(kWriteThreads) huff_write_kernel(HuffCtx cx) {
   extern __shared__ __align__(16) uint32_t hsm[];
-  const SyncSmem sm = carve_sync_smem(hsm, cx.log2_sub);
-  const JpegImage &im = cx.images[cx.block_image[blockIdx.x]];
-  const SubGeom sg = sync_block_prologue(cx, im, sm);
+  const WriteSmem sm = carve_write_smem(hsm, cx.log2_sub);
+  const JpegImage &im = cx.images[cx.wblock_image[blockIdx.x]];
+  const int lsw = cx.log2_sub - 5;
+  // ---- prologue: tables, per-thread subsequence geometry, cooperative staging of the stream
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(cx.tables[im.table_set].lut16);
+    uint4 *dst = reinterpret_cast<uint4 *>(sm.lut);
+    for (int i = threadIdx.x; i < kLutWords * 2 / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    if (threadIdx.x < kMaxBlocksPerMcu) sm.tbl[threadIdx.x] = tbl_word(im, threadIdx.x);
+    if (threadIdx.x < 64) sm.zig[threadIdx.x] = c_zigzag[threadIdx.x];
+    const uint32_t *ssrc = reinterpret_cast<const uint32_t *>(cx.tables[im.table_set].slow);
+    uint32_t *sdst = reinterpret_cast<uint32_t *>(sm.slow);
+    for (int i = threadIdx.x; i < (int)(4 * sizeof(HuffSlow) / 4); i += blockDim.x) sdst[i] = __ldg(ssrc + i);
+  }
+  SubGeom sg;
+  {
+    const int j = (blockIdx.x - im.wblock_begin) * kWriteThreads + threadIdx.x;     // image-local subsequence
+    sg.valid = j < im.nsub;
+    sg.ui = 0; sg.jl = 0; sg.nsub_eff = 0; sg.clean_bits = 0;
+    sg.g = (int64_t)im.subseq_begin + j;
+    const uint8_t *ptr = nullptr;
+    if (sg.valid) {
+      sg.ui = im.unit_end - im.unit_begin == 1 ? im.unit_begin : find_unit_by_subseq(cx.units, im.unit_begin, im.unit_end, j);
+      const JpegUnit &u = cx.units[sg.ui];
+      sg.clean_bits = cx.unit_clean_len[sg.ui] * 8u;
+      sg.nsub_eff = (sg.clean_bits + (1u << cx.log2_sub) - 1) >> cx.log2_sub;
+      sg.jl = (uint32_t)(j - u.first_subseq);
+      sg.valid = sg.jl < sg.nsub_eff;
+      if (sg.valid) ptr = cx.clean + u.clean_off + ((size_t)sg.jl << (cx.log2_sub - 3));
+    }
+    sm.colptr[threadIdx.x] = ptr;
+    const int la_cols = look_ahead_cols(cx.log2_sub);
+    if (threadIdx.x == kWriteThreads - 1)
+      for (int q = 1; q <= la_cols; q++) sm.colptr[kWriteThreads - 1 + q] = ptr ? ptr + ((size_t)q << (cx.log2_sub - 3)) : nullptr;
+    __syncthreads();
+    const int cpc = 1 << (cx.log2_sub - 7);                    // 16-byte chunks per column
+    for (int ch = threadIdx.x; ch < (kWriteThreads + la_cols) * cpc; ch += blockDim.x) {
+      const int col = ch / cpc, o = ch - col * cpc;
+      const uint8_t *p = sm.colptr[col];
+      if (p) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p) + o);
+        const uint32_t g = ((uint32_t)col << lsw) + 4u * o, x = (uint32_t)col & 31u;
+        sm.sw[(g + 0) ^ x] = v.x; sm.sw[(g + 1) ^ x] = v.y; sm.sw[(g + 2) ^ x] = v.z; sm.sw[(g + 3) ^ x] = v.w;
+      }
+    }
+    __syncthreads();                                           // colptr (aliased with the block buffers) is dead from here on
+  }
   const HuffSlow *slow = sm.slow;
-  const SmemSrc src{sm.sw, cx.log2_sub - 5};
+  const SmemSrc src{smem_u32(sm.sw), lsw};
   const uint32_t lane = threadIdx.x & 31u;
-  uint32_t *wbuf = sm.blkbuf + (threadIdx.x & ~31u) * 32u;             // this warp's 32 block buffers
-  uint32_t *mybuf = wbuf + lane * 32u;
+  // shared-window addresses (plain integers inside the loop, see lds_u32)
+  const uint32_t a_lut = smem_u32(sm.lut), a_tbl = smem_u32(sm.tbl), a_zig = smem_u32(sm.zig);
+  const uint32_t a_wbuf = smem_u32(sm.blkbuf) + (threadIdx.x & ~31u) * 128u;     // this warp's 32 block buffers (128 bytes each)
+  const uint32_t a_mybuf = a_wbuf + lane * 128u;
 #pragma unroll
-  for (int j = 0; j < 32; j++) mybuf[j] = 0u;
+  for (int j = 0; j < 32; j++) sts_u32(a_mybuf + 4u * j, 0u);
   __syncwarp();
   uint32_t pos = 0, nb = 0, end = 0, hard_end = 0, blk0 = 0, blk_limit = 0;
   int c = 0, z = 0;
@@ -645,7 +814,7 @@ __global__ void __launch_bounds__(kSyncThreads) huff_write_kernel(HuffCtx cx) {
     const JpegUnit &u = cx.units[sg.ui];
     if (sg.jl > 0) {
       const uint64_t prev = cx.s_state[sg.g - 1];
-      pos = (uint32_t)prev; c = (int)((prev >> 32) & 0xFF); z = (int)((prev >> 40) & 0xFF);
+      pos = (uint32_t)prev; c = (int)((prev >> 32) & 15u); z = (int)((prev >> 36) & 63u);
     }
     end = min((sg.jl + 1) << cx.log2_sub, sg.clean_bits);
     hard_end = sg.clean_bits;
@@ -658,33 +827,33 @@ __global__ void __launch_bounds__(kSyncThreads) huff_write_kernel(HuffCtx cx) {
   BitWindow<SmemSrc> win;
   {
     const uint32_t rel = active ? pos - (sg.jl << cx.log2_sub) : 0u;     // 0..31 bits into this thread's column
-    win.init(src, ((uint32_t)threadIdx.x << (cx.log2_sub - 5)) + (rel >> 5), rel & 31u);
+    win.init(src, ((uint32_t)threadIdx.x << lsw) + (rel >> 5), rel & 31u);
   }
   int16_t *coef = cx.coef + im.coef_off;
   int16_t *dcv = cx.dc + im.coef_off / 64;
   const int bpm = im.bpm;
-  uint32_t tb12 = sm.tbl[c];
+  uint32_t tb12 = lds_u32(a_tbl + 4u * c);
   while (__any_sync(0xffffffffu, active)) {
     bool flush = false;
     const uint32_t blk = blk0 + nb;
     if (active) {
-      const uint32_t e_ac = sm.lut[(tb12 >> 16) + (win.hi >> (32 - kAcLutBits))];
+      const uint32_t e_ac = lds_u16(a_lut + 2u * ((tb12 >> 16) + (win.hi >> (32 - kAcLutBits))));
       const bool is_dc = z == 0;
       uint32_t e = e_ac;
-      if (is_dc) e = sm.lut[(tb12 & 0xFFFFu) + (win.hi >> (32 - kDcLutBits))];
-      if (__builtin_expect(e == 0, 0)) e = slow_symbol(slow, is_dc ? (tb12 & 0xFFFFu) : (tb12 >> 16), win.hi, is_dc);
-      const uint32_t tb = e & 31u, adv = e >> 20, s = (e >> 8) & 15u;
+      if (is_dc) e = lds_u16(a_lut + 2u * ((tb12 & 0xFFFFu) + (win.hi >> (32 - kDcLutBits))));
+      if (__builtin_expect(e == 0, 0)) e = slow_symbol16(slow, is_dc ? (tb12 & 0xFFFFu) : (tb12 >> 16), win.hi, is_dc);
+      const uint32_t tb = e & 31u, adv = e >> 9, s = (e >> 5) & 15u;
       {
         // magnitude bits (EXTEND, T.81 F.2.2.1), computed by every lane: s == 0 gives v == 0
-        const uint32_t len = (e >> 12) & 31u;
+        const uint32_t len = tb - s;
         const uint32_t bits = (uint32_t)(((uint64_t)(win.hi << len)) >> (32u - s));      // 64-bit shift: s == 0 -> 0
         const int v = (int)bits - ((s == 0 || ((bits >> (s - 1u)) & 1u)) ? 0 : (int)((1u << s) - 1u));
         if (own) {
           if (is_dc) {
             dcv[blk] = (int16_t)v;                            // every block has a DC term: the compact array needs no memset
           } else if (s) {
-            const uint32_t nat = sm.zig[min((uint32_t)z + adv - 1u, 63u)];
-            reinterpret_cast<int16_t *>(mybuf + ((nat >> 1) ^ lane))[nat & 1u] = (int16_t)v;
+            const uint32_t nat = lds_u8(a_zig + min((uint32_t)z + adv - 1u, 63u));
+            sts_u16(a_mybuf + 4u * ((nat >> 1) ^ lane) + 2u * (nat & 1u), (uint32_t)v);
           }
         }
       }
@@ -698,7 +867,7 @@ __global__ void __launch_bounds__(kSyncThreads) huff_write_kernel(HuffCtx cx) {
       own = own || endb;                                      // the open block of the entry is over: what follows is ours
       c = endb ? c1 : c;
       z = endb ? 0 : z;
-      if (endb) tb12 = sm.tbl[c];
+      if (endb) tb12 = lds_u32(a_tbl + 4u * c);
       // keep going while symbols start inside the subsequence, then until the last own block is complete
       active = blk0 + nb < blk_limit && (pos < end || (z != 0 && pos < hard_end));
     }
@@ -708,9 +877,9 @@ __global__ void __launch_bounds__(kSyncThreads) huff_write_kernel(HuffCtx cx) {
       const uint32_t L = __ffs(m) - 1u;
       m &= m - 1u;
       const uint32_t fb = __shfl_sync(0xffffffffu, blk, L);
-      uint32_t *src_w = wbuf + L * 32u + (lane ^ L);
-      const uint32_t w = *src_w;
-      *src_w = 0u;
+      const uint32_t a_src = a_wbuf + L * 128u + 4u * (lane ^ L);
+      const uint32_t w = lds_u32(a_src);
+      sts_u32(a_src, 0u);
       reinterpret_cast<uint32_t *>(coef + (size_t)fb * 64)[lane] = w;
     }
     __syncwarp();
@@ -722,33 +891,36 @@ __global__ void __launch_bounds__(kSyncThreads) huff_write_kernel(HuffCtx cx) {
 // of each component are visited in scan order; restart intervals reset the predictor.
 __global__ void __launch_bounds__(1024) dc_scan_kernel(const JpegImage *__restrict__ images, int16_t *__restrict__ dc_arena) {
   __shared__ int warp_tot[32];
-  __shared__ int carry;
   const JpegImage &im = images[blockIdx.x];
   int16_t *dc = dc_arena + im.coef_off / 64;
   const int nmcu = im.mcux * im.mcuy;
   const int ri = im.restart_interval > 0 ? im.restart_interval : nmcu;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int comp = 0; comp < im.ncomp; comp++) {
     int nb = 0, bidx[kMaxBlocksPerMcu];
     for (int b = 0; b < im.bpm; b++) if (im.blk_comp[b] == comp) bidx[nb++] = b;
     const int total = nmcu * nb;
     if (ri >= nmcu) {
+      // every warp owns a contiguous run of the component's blocks: pass 1 sums it (coalesced), the 32 run totals are
+      // scanned once, pass 2 re-reads the run and writes the running predictor (two barriers per component)
+      const int per = ((total + 31) / 32 + 31) / 32 * 32;
+      const int i0 = wid * per, i1 = min(total, i0 + per);
+      int sum = 0;
+      for (int i = i0 + lane; i < i1; i += 32) sum += dc[(i / nb) * im.bpm + bidx[i % nb]];
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      __syncthreads();                                        // warp_tot of the previous component has been consumed
+      if (lane == 0) warp_tot[wid] = sum;
       __syncthreads();
-      if (threadIdx.x == 0) carry = 0;
-      __syncthreads();
-      for (int base = 0; base < total; base += blockDim.x) {
-        const int i = base + threadIdx.x;
+      int carry = 0;
+      for (int w = 0; w < wid; w++) carry += warp_tot[w];
+      for (int base = i0; base < i1; base += 32) {
+        const int i = base + lane;
         int idx = 0, v = 0;
-        if (i < total) { idx = (i / nb) * im.bpm + bidx[i % nb]; v = dc[idx]; }
+        if (i < i1) { idx = (i / nb) * im.bpm + bidx[i % nb]; v = dc[idx]; }
         int incl = v;
-        for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += x; }
-        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        int woff = 0, tot = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { if (w < (int)(threadIdx.x >> 5)) woff += warp_tot[w]; tot += warp_tot[w]; }
-        if (i < total) dc[idx] = (int16_t)(carry + woff + incl);
-        __syncthreads();
-        if (threadIdx.x == 0) carry += tot;
-        __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+        if (i < i1) dc[idx] = (int16_t)(carry + incl);
+        carry += __shfl_sync(0xffffffffu, incl, 31);
       }
     } else {
       const int nseg = (nmcu + ri - 1) / ri;
@@ -813,33 +985,37 @@ __device__ __forceinline__ uint32_t range_limit(int x) {     // libjpeg range_li
   return y < 640u ? min(y, 255u) : 0u;
 }
 
-__device__ __forceinline__ int find_image_by_coefblock(const JpegImage *im, int n, int64_t blk) {
+__device__ __forceinline__ int find_by_prefix(const int64_t *first, int n, int64_t v) {
   int lo = 0, hi = n - 1;
   while (lo < hi) {
     int mid = (lo + hi + 1) >> 1;
-    if (im[mid].coef_off / 64 <= blk) lo = mid; else hi = mid - 1;
+    if (first[mid] <= v) lo = mid; else hi = mid - 1;
   }
   return lo;
 }
 
-__global__ void __launch_bounds__(128) idct_kernel(const JpegImage *__restrict__ images, int nimages, int64_t total_blocks,
-                                                   const int16_t *__restrict__ coef_arena, const int16_t *__restrict__ dc_arena,
-                                                   const QuantSet *__restrict__ quants, uint8_t *__restrict__ planes) {
+// Work list: the blocks of the MCUs [mcu_x0, +mcu_nx) x [mcu_y0, +mcu_ny) of every image (all MCUs unless a region of interest
+// was requested); first_work[i] = index of image i's first work block.
+__global__ void __launch_bounds__(128) idct_kernel(const JpegImage *__restrict__ images, const int64_t *__restrict__ first_work, int nimages,
+                                                   int64_t total_work, const int16_t *__restrict__ coef_arena,
+                                                   const int16_t *__restrict__ dc_arena, const QuantSet *__restrict__ quants,
+                                                   uint8_t *__restrict__ planes) {
   // contiguous range of blocks per CTA: the image is searched once and then only advanced
   __shared__ int s_first;
-  const int64_t per_cta = ((total_blocks + gridDim.x - 1) / gridDim.x + 127) / 128 * 128;
-  const int64_t b0 = (int64_t)blockIdx.x * per_cta, b1 = min(total_blocks, b0 + per_cta);
+  const int64_t per_cta = ((total_work + gridDim.x - 1) / gridDim.x + 127) / 128 * 128;
+  const int64_t b0 = (int64_t)blockIdx.x * per_cta, b1 = min(total_work, b0 + per_cta);
   if (b0 >= b1) return;
-  if (threadIdx.x == 0) s_first = find_image_by_coefblock(images, nimages, b0);
+  if (threadIdx.x == 0) s_first = find_by_prefix(first_work, nimages, b0);
   __syncthreads();
   int ii = s_first;
-  for (int64_t gb = b0 + threadIdx.x; gb < b1; gb += blockDim.x) {
-    while (ii + 1 < nimages && images[ii + 1].coef_off / 64 <= gb) ii++;
+  for (int64_t wb = b0 + threadIdx.x; wb < b1; wb += blockDim.x) {
+    while (ii + 1 < nimages && first_work[ii + 1] <= wb) ii++;
     const JpegImage &im = images[ii];
-    const int64_t lb = gb - im.coef_off / 64;          // block index in scan (MCU) order
-    const int mcu = (int)(lb / im.bpm), b = (int)(lb % im.bpm);
+    const int64_t lw = wb - first_work[ii];            // block index inside the window, MCU-row major
+    const int wm = (int)(lw / im.bpm), b = (int)(lw % im.bpm);
+    const int mx = im.mcu_x0 + wm % im.mcu_nx, my = im.mcu_y0 + wm / im.mcu_nx;
+    const int64_t gb = im.coef_off / 64 + ((int64_t)my * im.mcux + mx) * im.bpm + b;     // block index in scan (MCU) order
     const int comp = im.blk_comp[b];
-    const int mx = mcu % im.mcux, my = mcu / im.mcux;
     const int bx = mx * im.hs[comp] + im.blk_x[b], by = my * im.vs[comp] + im.blk_y[b];
     const uint16_t *q = quants[im.quant_set].q[im.tq[comp]];
     const int4 *src = reinterpret_cast<const int4 *>(coef_arena + gb * 64);
@@ -917,12 +1093,12 @@ __global__ void __launch_bounds__(256) color_kernel(const JpegImage *__restrict_
     const JpegImage &im = images[lo];
     if (im.fast_color) continue;
     const int64_t q = gq - first_quad[lo];
-    const int qpr = (im.width + 3) >> 2;
-    const int y = (int)(q / qpr), x0 = (int)(q % qpr) << 2;
+    const int qpr = (im.win_w + 3) >> 2;
+    const int y = im.win_y0 + (int)(q / qpr), x0 = im.win_x0 + ((int)(q % qpr) << 2);
     const int W = im.width, H = im.height;
     const int nout = im.out_type == DALIB200_GRAY ? 1 : 3;
     uint8_t px[12];
-    const int nx = min(4, W - x0);
+    const int nx = min(4, im.win_x0 + im.win_w - x0);
     for (int k = 0; k < nx; k++) {
       const int x = x0 + k;
       int v[3];
@@ -946,7 +1122,7 @@ __global__ void __launch_bounds__(256) color_kernel(const JpegImage *__restrict_
       else if (im.out_type == DALIB200_YCbCr) { px[3 * k] = yy; px[3 * k + 1] = cb; px[3 * k + 2] = cr; }
       else px[k] = (im.ncomp == 1 || !im.is_rgb) ? yy : ((r * 19595 + g * 38470 + b * 7471 + 32768) >> 16);
     }
-    uint8_t *o = im.out + ((int64_t)y * W + x0) * nout;
+    uint8_t *o = im.out + ((int64_t)(y - im.win_y0) * im.win_w + (x0 - im.win_x0)) * nout;
     const int nb = nx * nout;
     if (nb == 12 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
       uint32_t *o4 = reinterpret_cast<uint32_t *>(o);
@@ -1054,8 +1230,8 @@ __device__ __forceinline__ void color_row8(const JpegImage &im, const uint8_t *_
     const int b = clamp255(yy + ((116130 * cbm + 32768) >> 16));
     px[3 * k] = (uint32_t)(bgr ? b : r); px[3 * k + 1] = (uint32_t)g; px[3 * k + 2] = (uint32_t)(bgr ? r : b);
   }
-  uint8_t *o = im.out + ((int64_t)y * W + x0) * 3;
-  const int nx = min(8, W - x0);
+  uint8_t *o = im.out + ((int64_t)(y - im.win_y0) * im.win_w + (x0 - im.win_x0)) * 3;
+  const int nx = min(8, im.win_x0 + im.win_w - x0);
   if (nx == 8 && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
     uint2 *o8 = reinterpret_cast<uint2 *>(o);
 #pragma unroll
@@ -1092,7 +1268,7 @@ __device__ __forceinline__ void ycc_to_rgb_store8(const JpegImage &im, uint2 yw,
     const int b = yy + ((116130 * cbm + 32768) >> 16);
     px[3 * k] = bgr ? b : r; px[3 * k + 1] = g; px[3 * k + 2] = bgr ? r : b;
   }
-  uint2 *o8 = reinterpret_cast<uint2 *>(im.out + ((int64_t)y * im.width + x0) * 3);       // 8-byte aligned (checked by the caller)
+  uint2 *o8 = reinterpret_cast<uint2 *>(im.out + ((int64_t)(y - im.win_y0) * im.win_w + (x0 - im.win_x0)) * 3);   // 8-byte aligned (checked by the caller)
 #pragma unroll
   for (int q = 0; q < 3; q++)
     o8[q] = make_uint2(pack4_sat_u8(px[8 * q], px[8 * q + 1], px[8 * q + 2], px[8 * q + 3]),
@@ -1137,30 +1313,104 @@ __global__ void __launch_bounds__(128) color_fast_kernel(const JpegImage *__rest
     while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (first_item[mid] <= item) lo = mid; else hi = mid - 1; }
     const JpegImage &im = images[lo];
     const int64_t li = item - first_item[lo];
-    const int segs = (im.width + kColorSeg - 1) / kColorSeg;
-    const int x0 = (int)(li % segs) * kColorSeg + threadIdx.x * 8;
-    if (x0 >= im.width) continue;
+    const int segs = (im.win_w + kColorSeg - 1) / kColorSeg;
+    const int x0 = im.win_x0 + (int)(li % segs) * kColorSeg + threadIdx.x * 8;
+    const int wx1 = im.win_x0 + im.win_w, wy1 = im.win_y0 + im.win_h;
+    if (x0 >= wx1) continue;
     const int hexp = im.hmax, vexp = im.vmax;     // chroma is 1x1 (checked on the host)
     if (im.fast_color == 2) {
-      // 4:2:0 fancy: item 0 = row 0, item r >= 1 = rows 2r - 1 and 2r (see color_patch_420)
-      const int r = (int)(li / segs);
-      if (r == 0) { color_row8<2, 2>(im, planes, x0, 0); continue; }
-      const int y = 2 * r - 1;
+      // 4:2:0 fancy: row item r = rows 2r - 1 and 2r (r = 0: row 0 only), see color_patch_420; the window's first item is
+      // r_lo = ceil(win_y0 / 2)
+      const int r = ((im.win_y0 + 1) >> 1) + (int)(li / segs);
+      const int ya = 2 * r - 1, yb = 2 * r;
+      const bool in_a = ya >= im.win_y0 && ya < wy1, in_b = yb >= im.win_y0 && yb < wy1;
       const int dw = (im.width + 1) >> 1, dh = (im.height + 1) >> 1, i0 = x0 >> 1;
-      const bool aligned = (reinterpret_cast<uintptr_t>(im.out) & 7) == 0 && (im.width & 7) == 0;
-      if (aligned && y + 1 < im.height && (y >> 1) + 1 <= dh - 1 && i0 >= 1 && i0 + 4 <= dw - 1 && x0 + 8 <= im.width) {
-        color_patch_420(im, planes, x0, y);
+      const bool aligned = (reinterpret_cast<uintptr_t>(im.out) & 7) == 0 && (im.win_w & 7) == 0;
+      if (aligned && in_a && in_b && (ya >> 1) + 1 <= dh - 1 && i0 >= 1 && i0 + 4 <= dw - 1 && x0 + 8 <= wx1) {
+        color_patch_420(im, planes, x0, ya);
       } else {
-        color_row8<2, 2>(im, planes, x0, y);
-        if (y + 1 < im.height) color_row8<2, 2>(im, planes, x0, y + 1);
+        if (in_a) color_row8<2, 2>(im, planes, x0, ya);
+        if (in_b) color_row8<2, 2>(im, planes, x0, yb);
       }
       continue;
     }
-    const int y = (int)(li / segs);
+    const int y = im.win_y0 + (int)(li / segs);
     if (hexp == 2 && vexp == 2) color_row8<2, 2>(im, planes, x0, y);
     else if (hexp == 1 && vexp == 1) color_row8<1, 1>(im, planes, x0, y);
     else if (hexp == 2 && vexp == 1) color_row8<2, 1>(im, planes, x0, y);
     else color_row8<1, 2>(im, planes, x0, y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Post pass: orientation + region of interest + colour space + data type, one thread per output pixel.
+// Colour formulas: kernels::color::itu_r_bt_601::rgb_to_ycbcr<Out, uint8_t> (color_space_conversion_impl.h:64-103), dtype
+// conversion ConvertSatNorm<float>(uint8_t) = v * (1.0f / 255) (include/dali/core/convert.h:263-275).
+template <typename Out> __device__ __forceinline__ Out post_cvt(uint32_t v);
+template <> __device__ __forceinline__ uint8_t post_cvt<uint8_t>(uint32_t v) { return (uint8_t)v; }
+template <> __device__ __forceinline__ float post_cvt<float>(uint32_t v) { return mul_rn((float)v, 1.0f / 255); }
+
+__device__ __forceinline__ float post_dot3(float c0, float c1, float c2, float a, float b, float c) {
+  return add_rn(add_rn(mul_rn(c0, a), mul_rn(c1, b)), mul_rn(c2, c));
+}
+
+template <typename Out>
+__global__ void __launch_bounds__(256) jpeg_post_kernel(const JpegPost *__restrict__ posts, int n, int64_t total_px) {
+  __shared__ int s_first;
+  const int64_t per_cta = ((total_px + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;
+  const int64_t p0 = (int64_t)blockIdx.x * per_cta, p1 = min(total_px, p0 + per_cta);
+  if (p0 >= p1) return;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (posts[mid].first_px <= p0) lo = mid; else hi = mid - 1; }
+    s_first = lo;
+  }
+  __syncthreads();
+  int ii = s_first;
+  constexpr bool F = sizeof(Out) == 4;
+  // coefficients of rgb_to_ycbcr<Out, uint8_t>: vec3 * scale_factor<uint8_t, Out>() (a float product per coefficient)
+  const float sf = F ? (float)(1.0 / 255.0) : 1.0f;
+  const float ky0 = mul_rn(0.25678823529f, sf), ky1 = mul_rn(0.50412941176f, sf), ky2 = mul_rn(0.09790588235f, sf);
+  const float kb0 = mul_rn(-0.14822289945f, sf), kb1 = mul_rn(-0.29099278682f, sf), kb2 = mul_rn(0.43921568627f, sf);
+  const float kr0 = mul_rn(0.43921568627f, sf), kr1 = mul_rn(-0.36778831435f, sf), kr2 = mul_rn(-0.07142737192f, sf);
+  const float ybias = F ? 0.0625f : 16.0f, cbias = F ? 0.5f : 128.0f;
+  for (int64_t gp = p0 + threadIdx.x; gp < p1; gp += blockDim.x) {
+    while (ii + 1 < n && posts[ii + 1].first_px <= gp) ii++;
+    const JpegPost &d = posts[ii];
+    const int64_t lp = gp - d.first_px;
+    const int oy = (int)(lp / d.out_w), ox = (int)(lp % d.out_w);
+    const int fy = d.out_y0 + oy, fx = d.out_x0 + ox;           // oriented full-image coordinates
+    int sy, sx;
+    switch (d.orientation) {                                   // EXIF: where does the displayed pixel come from?
+      case 2: sy = fy; sx = d.img_w - 1 - fx; break;
+      case 3: sy = d.img_h - 1 - fy; sx = d.img_w - 1 - fx; break;
+      case 4: sy = d.img_h - 1 - fy; sx = fx; break;
+      case 5: sy = fx; sx = fy; break;
+      case 6: sy = d.img_h - 1 - fx; sx = fy; break;
+      case 7: sy = d.img_h - 1 - fx; sx = d.img_w - 1 - fy; break;
+      case 8: sy = fx; sx = d.img_w - 1 - fy; break;
+      default: sy = fy; sx = fx; break;
+    }
+    const uint8_t *sp = d.src + ((int64_t)(sy - d.win_y0) * d.src_w + (sx - d.win_x0)) * d.src_c;
+    if (d.out_type == DALIB200_GRAY) {                         // the decoder produced the Y plane itself (src_c == 1)
+      static_cast<Out *>(d.dst)[lp] = post_cvt<Out>(sp[0]);
+      continue;
+    }
+    uint32_t r, g, b;
+    if (d.src_c == 1) r = g = b = sp[0]; else { r = sp[0]; g = sp[1]; b = sp[2]; }
+    Out *op = static_cast<Out *>(d.dst) + lp * 3;
+    if (d.out_type == DALIB200_YCbCr) {
+      const float fr = (float)r, fg = (float)g, fb = (float)b;
+      const float yv = add_rn(post_dot3(ky0, ky1, ky2, fr, fg, fb), ybias);
+      const float cb = add_rn(post_dot3(kb0, kb1, kb2, fr, fg, fb), cbias);
+      const float cr = add_rn(post_dot3(kr0, kr1, kr2, fr, fg, fb), cbias);
+      if (F) { op[0] = (Out)yv; op[1] = (Out)cb; op[2] = (Out)cr; }
+      else { op[0] = (Out)sat_u8_half_away(yv); op[1] = (Out)sat_u8_half_away(cb); op[2] = (Out)sat_u8_half_away(cr); }
+    } else if (d.out_type == DALIB200_BGR) {
+      op[0] = post_cvt<Out>(b); op[1] = post_cvt<Out>(g); op[2] = post_cvt<Out>(r);
+    } else {
+      op[0] = post_cvt<Out>(r); op[1] = post_cvt<Out>(g); op[2] = post_cvt<Out>(b);
+    }
   }
 }
 
@@ -1201,12 +1451,14 @@ int ParseExifOrientation(const uint8_t *p, int len) {
   auto r16 = [&](unsigned o) { return le ? (p[o] | (p[o + 1] << 8)) : ((p[o] << 8) | p[o + 1]); };
   auto r32 = [&](unsigned o) { return le ? (unsigned)(p[o] | (p[o + 1] << 8) | (p[o + 2] << 16) | ((unsigned)p[o + 3] << 24))
                                          : (((unsigned)p[o] << 24) | (p[o + 1] << 16) | (p[o + 2] << 8) | p[o + 3]); };
-  unsigned ifd = r32(4);
-  if (ifd + 2 > (unsigned)len) return 1;
-  int n = r16(ifd);
+  const uint64_t ulen = (uint64_t)len;                      // 64-bit offsets: a crafted IFD offset must not wrap the bound checks
+  const uint64_t ifd = r32(4);
+  if (ifd + 2 > ulen) return 1;
+  int n = r16((unsigned)ifd);
   for (int i = 0; i < n; i++) {
-    unsigned e = ifd + 2 + 12 * i;
-    if (e + 12 > (unsigned)len) return 1;
+    const uint64_t e64 = ifd + 2 + 12ull * (uint64_t)i;
+    if (e64 + 12 > ulen) return 1;
+    const unsigned e = (unsigned)e64;
     if (r16(e) == 0x0112) { int v = r16(e + 8); return (v >= 1 && v <= 8) ? v : 1; }
   }
   return 1;
@@ -1275,6 +1527,7 @@ int ParseHeaders(const uint8_t *p, size_t n, ParsedJpeg &j, bool need_scan) {
       if (sl >= 12 && !memcmp(s, "Adobe", 5)) j.adobe_transform = s[11];
     } else if (m == 0xDA) {
       if (!got_sof) { SetLastError("JPEG: SOS before SOF"); return DALIB200_ERROR_BAD_DATA; }
+      if (sl < 1) { SetLastError("JPEG: bad SOS"); return DALIB200_ERROR_BAD_DATA; }
       j.scan_ncomp = s[0];
       if (j.scan_ncomp < 1 || j.scan_ncomp > 4 || sl < 1 + 2 * j.scan_ncomp) { SetLastError("JPEG: bad SOS"); return DALIB200_ERROR_BAD_DATA; }
       for (int i = 0; i < j.scan_ncomp; i++) {
@@ -1311,10 +1564,17 @@ uint32_t MakeLutEntry(int len, int sym, bool is_dc) {       // keep in sync with
   return ((uint32_t)len + s) | (s << 8) | ((uint32_t)len << 12) | (adv << 20);
 }
 
-void BuildDeviceTable(const HostHuff &h, uint32_t *lut, HuffSlow &t, bool is_dc) {
+uint16_t MakeLutEntry16(int len, int sym, bool is_dc) {     // keep in sync with make_entry16 (device)
+  const uint32_t s = sym & 15, r = (uint32_t)sym >> 4;
+  const uint32_t adv = is_dc ? 1u : (s == 0 ? (r == 15u ? 16u : 64u) : r + 1u);
+  return (uint16_t)(((uint32_t)len + s) | (s << 5) | (adv << 9));
+}
+
+void BuildDeviceTable(const HostHuff &h, uint32_t *lut, uint16_t *lut16, HuffSlow &t, bool is_dc) {
   const int kLutBits = is_dc ? kDcLutBits : kAcLutBits, kLutSize = 1 << kLutBits;
   memset(&t, 0, sizeof(t));
   memset(lut, 0, sizeof(uint32_t) * kLutSize);
+  memset(lut16, 0, sizeof(uint16_t) * kLutSize);
   int code = 0, k = 0;
   for (int l = 1; l <= 16; l++) {
     const int mincode = code;
@@ -1322,7 +1582,10 @@ void BuildDeviceTable(const HostHuff &h, uint32_t *lut, HuffSlow &t, bool is_dc)
     for (int i = 0; i < h.bits[l]; i++, k++, code++) {
       if (l <= kLutBits) {
         const int lo = code << (kLutBits - l), cnt = 1 << (kLutBits - l);
-        for (int e = 0; e < cnt && lo + e < kLutSize; e++) lut[lo + e] = MakeLutEntry(l, h.vals[k & 255], is_dc);
+        for (int e = 0; e < cnt && lo + e < kLutSize; e++) {
+          lut[lo + e] = MakeLutEntry(l, h.vals[k & 255], is_dc);
+          lut16[lo + e] = MakeLutEntry16(l, h.vals[k & 255], is_dc);
+        }
       }
     }
     // a 16-bit window belongs to length l iff it is < maxcode[l] (exclusive bound, left-aligned) and matched
@@ -1338,7 +1601,16 @@ void BuildDeviceTable(const HostHuff &h, uint32_t *lut, HuffSlow &t, bool is_dc)
 
 struct dalib200JpegPlan {
   int max_batch = 0, n = 0;
-  int output_type = DALIB200_RGB, fancy = 1;
+  int output_type = DALIB200_RGB, fancy = 1, dtype = DALIB200_UINT8, adjust_orientation = 0;
+  std::vector<JpegPost> posts;              // samples that need the post pass (indices in post_sample)
+  std::vector<int> post_sample;
+  std::vector<size_t> post_off;             // byte offset of each post sample's window inside d_post
+  std::vector<int32_t> out_shape;           // n x 3 (H, W, C) of the operator output
+  std::vector<int64_t> first_work;          // IDCT work list prefix
+  int64_t total_work = 0, total_post_px = 0;
+  size_t post_bytes = 0;
+  uint8_t *d_post = nullptr; size_t d_post_cap = 0;
+  JpegPost *d_posts = nullptr; size_t d_posts_cap = 0;
   std::vector<ParsedJpeg> parsed;
   std::vector<JpegImage> images;
   std::vector<JpegUnit> units;
@@ -1346,25 +1618,26 @@ struct dalib200JpegPlan {
   std::vector<QuantSet> quants;
   std::vector<int64_t> first_quad, first_item;
   std::vector<int32_t> block_image;         // sync block -> image
+  std::vector<int32_t> wblock_image;        // write block -> image
   std::vector<const uint8_t *> src_ptr;     // host pointers of the scan data (for staging; borrowed until JpegUpload returns)
   std::vector<size_t> stage_off;            // offset of each sample's scan bytes inside the raw staging area
   size_t raw_bytes = 0, clean_bytes = 0;
   uint32_t nchunks = 0;
   int64_t total_subseq = 0, total_coefs = 0, total_plane_bytes = 0, total_quads = 0, total_items = 0;
-  int total_blocks_sync = 0;
+  int total_blocks_sync = 0, total_blocks_write = 0;
   int log2_sub = 10;
   // staging (pinned) and device buffers -- grow only
   uint8_t *h_stage = nullptr; size_t h_stage_cap = 0;
   uint8_t *d_stage = nullptr; size_t d_stage_cap = 0;
-  size_t desc_bytes = 0, off_images = 0, off_units = 0, off_tables = 0, off_quants = 0, off_quads = 0, off_items = 0, off_blkimg = 0, off_raw = 0;
+  size_t desc_bytes = 0, off_images = 0, off_units = 0, off_tables = 0, off_quants = 0, off_quads = 0, off_items = 0, off_work = 0, off_blkimg = 0, off_wblkimg = 0, off_raw = 0;
   uint8_t *d_clean = nullptr; size_t d_clean_cap = 0;
   uint32_t *d_chunk = nullptr; size_t d_chunk_cap = 0;
   uint32_t *d_unit_len = nullptr; size_t d_unit_cap = 0;
   uint64_t *d_state = nullptr; uint32_t *d_n = nullptr; size_t d_sub_cap = 0;
-  uint4 *d_chain0 = nullptr, *d_chain1 = nullptr, *d_chain2 = nullptr, *d_chain3 = nullptr;
-  size_t d_chain0_cap = 0, d_chain1_cap = 0, d_chain2_cap = 0, d_chain3_cap = 0;
+  uint4 *d_chain1 = nullptr, *d_chain2 = nullptr, *d_chain3 = nullptr;
+  size_t d_chain1_cap = 0, d_chain2_cap = 0, d_chain3_cap = 0;
   uint32_t *d_chain_count = nullptr; size_t d_chain_count_cap = 0;
-  int tail_grid = 0;
+  int walk_max_grid = 0;
   int16_t *d_coef = nullptr; size_t d_coef_cap = 0;
   int16_t *d_dc = nullptr; size_t d_dc_cap = 0;
   uint8_t *d_planes = nullptr; size_t d_planes_cap = 0;
@@ -1421,7 +1694,7 @@ int dalib200JpegPlanDestroy(dalib200JpegPlan *p) {
   if (p->h_stage) cudaFreeHost(p->h_stage);
   if (p->h_images) cudaFreeHost(p->h_images);
   void *bufs[] = { p->d_stage, p->d_clean, p->d_chunk, p->d_unit_len, p->d_state, p->d_n, p->d_coef, p->d_dc, p->d_planes, p->d_status,
-                   p->d_chain0, p->d_chain1, p->d_chain2, p->d_chain3, p->d_chain_count };
+                   p->d_chain1, p->d_chain2, p->d_chain3, p->d_chain_count, p->d_post, p->d_posts };
   for (void *b : bufs) if (b) cudaFree(b);
   delete p;
   return DALIB200_SUCCESS;
@@ -1437,22 +1710,43 @@ size_t dalib200JpegPlanStagedBytes(const dalib200JpegPlan *p) { return p ? p->de
 
 int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *streams, const size_t *lengths, int output_type,
                           int fancy_upsampling) {
-  DB_CHECK_ARG(p && (n == 0 || (streams && lengths)) && n >= 0, "JpegPlanSetup: null argument");
+  dalib200JpegParams prm;
+  prm.output_type = output_type; prm.fancy_upsampling = fancy_upsampling; prm.dtype = DALIB200_UINT8; prm.adjust_orientation = 0;
+  return dalib200JpegPlanSetupEx(p, n, streams, lengths, &prm, nullptr);
+}
+
+int dalib200JpegPlanGetOutputShape(const dalib200JpegPlan *p, int sample, int32_t *hwc) {
+  DB_CHECK_ARG(p && hwc && sample >= 0 && sample < p->n, "JpegPlanGetOutputShape: bad sample index");
+  for (int d = 0; d < 3; d++) hwc[d] = p->out_shape[3 * sample + d];
+  return DALIB200_SUCCESS;
+}
+
+int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *streams, const size_t *lengths,
+                            const dalib200JpegParams *prm, const dalib200JpegRoi *rois) {
+  DB_CHECK_ARG(p && prm && (n == 0 || (streams && lengths)) && n >= 0, "JpegPlanSetup: null argument");
   DB_CHECK_ARG(n <= p->max_batch, "JpegPlanSetup: batch %d exceeds plan capacity %d", n, p->max_batch);
-  DB_CHECK_ARG(output_type == DALIB200_RGB || output_type == DALIB200_BGR || output_type == DALIB200_GRAY,
-               "decoders.image: output_type %d is not supported by the GPU decoder (RGB, BGR, GRAY)", output_type);
+  const int output_type = prm->output_type, fancy_upsampling = prm->fancy_upsampling;
+  DB_CHECK_ARG(output_type == DALIB200_RGB || output_type == DALIB200_BGR || output_type == DALIB200_GRAY || output_type == DALIB200_YCbCr,
+               "decoders.image: output_type %d is not supported (RGB, BGR, GRAY, YCbCr)", output_type);
+  DB_CHECK_ARG(prm->dtype == DALIB200_UINT8 || prm->dtype == DALIB200_FLOAT, "decoders.image: dtype %d is not supported (UINT8, FLOAT)", prm->dtype);
   p->staged = false;
   p->n = n; p->output_type = output_type; p->fancy = fancy_upsampling != 0;
+  p->dtype = prm->dtype; p->adjust_orientation = prm->adjust_orientation != 0;
+  p->posts.clear(); p->post_sample.clear(); p->post_off.clear();
+  p->out_shape.assign((size_t)3 * n, 0);
+  p->first_work.assign(n, 0);
+  int64_t work = 0, post_px = 0;
+  size_t post_bytes = 0;
   p->parsed.assign(n, ParsedJpeg());
   p->images.assign(n, JpegImage());
-  p->units.clear(); p->tables.clear(); p->quants.clear(); p->src_ptr.clear(); p->block_image.clear();
+  p->units.clear(); p->tables.clear(); p->quants.clear(); p->src_ptr.clear(); p->block_image.clear(); p->wblock_image.clear();
   p->first_quad.assign(n, 0);
   p->first_item.assign(n, 0);
   std::map<std::string, int> table_cache, quant_cache;
   size_t raw = 0, clean = 0;
   uint32_t chunks = 0;
   int64_t subseq = 0, coefs = 0, planes = 0, quads = 0, items = 0;
-  int sync_blocks = 0;
+  int sync_blocks = 0, write_blocks = 0;
   // subsequence size: the longer, the fewer re-decodes until the chains lock onto the MCU phase; aim for >= ~200k
   // subsequences per batch (a full B200 holds 300k threads), between 32 and 256 bytes
   size_t total_len = 0;
@@ -1472,7 +1766,6 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
     if (j.precision != 8) return unsupported("only 8-bit baseline JPEG is supported");
     if (j.ncomp != 1 && j.ncomp != 3) return unsupported("only 1- or 3-component JPEG is supported");
     if (j.scan_ncomp != j.ncomp) return unsupported("multi-scan (non-interleaved) baseline JPEG is not supported yet");
-    if (j.orientation != 1) return unsupported("EXIF orientation other than 1 is not applied yet (adjust_orientation)");
     for (int c = 1; c < j.ncomp; c++)
       if (j.hs[c] != 1 || j.vs[c] != 1) return unsupported("chroma sampling factors other than 1x1 are not supported");
     if (j.ncomp == 1) { j.hs[0] = j.vs[0] = 1; j.hmax = j.vmax = 1; }     // a single-component scan is never interleaved
@@ -1511,8 +1804,8 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
       if (it == table_cache.end()) {
         TableSet ts;
         for (int t = 0; t < 2; t++) {
-          BuildDeviceTable(j.dc[t], ts.lut + LutOffset(t), ts.slow[t], true);
-          BuildDeviceTable(j.ac[t], ts.lut + LutOffset(2 + t), ts.slow[2 + t], false);
+          BuildDeviceTable(j.dc[t], ts.lut + LutOffset(t), ts.lut16 + LutOffset(t), ts.slow[t], true);
+          BuildDeviceTable(j.ac[t], ts.lut + LutOffset(2 + t), ts.lut16 + LutOffset(2 + t), ts.slow[2 + t], false);
         }
         p->tables.push_back(ts);
         it = table_cache.emplace(key, (int)p->tables.size() - 1).first;
@@ -1537,6 +1830,7 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
     im.unit_begin = (int)p->units.size();
     im.subseq_begin = (int)subseq;
     im.block_begin = sync_blocks;
+    im.wblock_begin = write_blocks;
     int32_t local_sub = 0;
     auto add_unit = [&](size_t b, size_t e, int64_t mcu0, int64_t mcus) {
       JpegUnit u;
@@ -1582,6 +1876,8 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
     subseq += local_sub;
     sync_blocks += (local_sub + kSyncThreads - 1) / kSyncThreads;
     p->block_image.resize(sync_blocks, i);
+    write_blocks += (local_sub + kWriteThreads - 1) / kWriteThreads;
+    p->wblock_image.resize(write_blocks, i);
     im.coef_off = coefs;
     coefs += nmcu * bpm * 64;
     for (int c = 0; c < j.ncomp; c++) {
@@ -1589,18 +1885,82 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
       im.plane_off[c] = planes;
       planes += Align((size_t)im.plane_w[c] * im.plane_h[c], 16);
     }
-    im.fast_color = j.ncomp == 3 && !im.is_rgb && (output_type == DALIB200_RGB || output_type == DALIB200_BGR) &&
+    // ---- output geometry: orientation, region of interest, decode window, post pass
+    const int orient = p->adjust_orientation ? j.orientation : 1;
+    const int W = j.width, H = j.height;
+    const int OW = orient >= 5 ? H : W, OH = orient >= 5 ? W : H;          // oriented image size
+    int rx0 = 0, ry0 = 0, rx1 = OW, ry1 = OH;                              // region of interest, oriented coordinates
+    if (rois && rois[i].use_roi) {
+      rx0 = rois[i].x0; ry0 = rois[i].y0; rx1 = rois[i].x1; ry1 = rois[i].y1;
+      if (!(0 <= rx0 && rx0 < rx1 && rx1 <= OW && 0 <= ry0 && ry0 < ry1 && ry1 <= OH)) {
+        SetLastError("decoders.image: sample %d: ROI [%d, %d) x [%d, %d) must be non-empty and fit within the image bounds (%d x %d)",
+                     i, rx0, rx1, ry0, ry1, OW, OH);
+        return DALIB200_ERROR_INVALID_ARGUMENT;
+      }
+    }
+    // source rectangle of the region (the EXIF transforms map rectangles to rectangles)
+    int sx0, sx1, sy0, sy1;
+    {
+      auto src_of = [&](int fy, int fx, int &sy, int &sx) {
+        switch (orient) {
+          case 2: sy = fy; sx = W - 1 - fx; break;
+          case 3: sy = H - 1 - fy; sx = W - 1 - fx; break;
+          case 4: sy = H - 1 - fy; sx = fx; break;
+          case 5: sy = fx; sx = fy; break;
+          case 6: sy = H - 1 - fx; sx = fy; break;
+          case 7: sy = H - 1 - fx; sx = W - 1 - fy; break;
+          case 8: sy = fx; sx = W - 1 - fy; break;
+          default: sy = fy; sx = fx; break;
+        }
+      };
+      int ay, ax, by_, bx_;
+      src_of(ry0, rx0, ay, ax); src_of(ry1 - 1, rx1 - 1, by_, bx_);
+      sy0 = std::min(ay, by_); sy1 = std::max(ay, by_) + 1; sx0 = std::min(ax, bx_); sx1 = std::max(ax, bx_) + 1;
+    }
+    const int out_c = output_type == DALIB200_GRAY ? 1 : 3;
+    p->out_shape[3 * i] = ry1 - ry0; p->out_shape[3 * i + 1] = rx1 - rx0; p->out_shape[3 * i + 2] = out_c;
+    im.win_x0 = sx0 & ~7; im.win_y0 = sy0;
+    im.win_w = std::min(W, (sx1 + 7) & ~7) - im.win_x0; im.win_h = sy1 - sy0;
+    const bool direct = orient == 1 && p->dtype == DALIB200_UINT8 && output_type != DALIB200_YCbCr &&
+                        im.win_x0 == sx0 && im.win_x0 + im.win_w == sx1;
+    if (!direct) {
+      // the window is decoded to RGB (or to the Y plane for GRAY) into plan scratch; the post pass gathers / converts it
+      im.out_type = output_type == DALIB200_GRAY ? DALIB200_GRAY : DALIB200_RGB;
+      JpegPost po;
+      memset(&po, 0, sizeof(po));
+      po.src_w = im.win_w; po.src_c = out_c == 1 ? 1 : 3;
+      po.img_w = W; po.img_h = H; po.win_x0 = im.win_x0; po.win_y0 = im.win_y0;
+      po.out_x0 = rx0; po.out_y0 = ry0; po.out_w = rx1 - rx0; po.out_h = ry1 - ry0;
+      po.orientation = orient; po.out_type = output_type; po.dtype = p->dtype;
+      po.first_px = post_px;
+      post_px += (int64_t)po.out_w * po.out_h;
+      p->posts.push_back(po); p->post_sample.push_back(i); p->post_off.push_back(post_bytes);
+      post_bytes += Align((size_t)im.win_w * im.win_h * po.src_c, 256);
+    }
+    // MCUs the IDCT has to produce: the window plus the neighbours the (fancy) chroma upsampling reads
+    {
+      const int mw = 8 * j.hmax, mh = 8 * j.vmax, ex = 2 * j.hmax, ey = 2 * j.vmax;
+      const int mx0 = std::max(0, im.win_x0 - ex) / mw, mx1 = std::min(im.mcux - 1, (im.win_x0 + im.win_w - 1 + ex) / mw);
+      const int my0 = std::max(0, im.win_y0 - ey) / mh, my1 = std::min(im.mcuy - 1, (im.win_y0 + im.win_h - 1 + ey) / mh);
+      im.mcu_x0 = mx0; im.mcu_y0 = my0; im.mcu_nx = mx1 - mx0 + 1; im.mcu_ny = my1 - my0 + 1;
+      p->first_work[i] = work;
+      work += (int64_t)im.mcu_nx * im.mcu_ny * bpm;
+    }
+    im.fast_color = j.ncomp == 3 && !im.is_rgb && (im.out_type == DALIB200_RGB || im.out_type == DALIB200_BGR) &&
                     ((j.hmax == 2 && j.vmax <= 2) || (j.hmax == 1 && j.vmax <= 2));
     p->first_quad[i] = quads;
     p->first_item[i] = items;
     if (im.fast_color && p->fancy && j.hmax == 2 && j.vmax == 2 && (j.width + 1) / 2 > 2) im.fast_color = 2;    // 2-row patches
-    if (im.fast_color) items += (int64_t)((j.width + kColorSeg - 1) / kColorSeg) * (im.fast_color == 2 ? 1 + j.height / 2 : j.height);
-    else quads += (int64_t)((j.width + 3) / 4) * j.height;
+    const int segs = (im.win_w + kColorSeg - 1) / kColorSeg;
+    if (im.fast_color == 2) items += (int64_t)segs * ((im.win_y0 + im.win_h) / 2 - (im.win_y0 + 1) / 2 + 1);
+    else if (im.fast_color) items += (int64_t)segs * im.win_h;
+    else quads += (int64_t)((im.win_w + 3) / 4) * im.win_h;
   }
+  p->total_work = work; p->total_post_px = post_px; p->post_bytes = post_bytes;
   DB_CHECK_ARG(raw < (1ull << 32) && clean < (1ull << 32), "decoders.image: batch of encoded data exceeds 4 GiB");
   p->raw_bytes = raw; p->clean_bytes = clean; p->nchunks = chunks;
   p->total_subseq = subseq; p->total_coefs = coefs; p->total_plane_bytes = planes; p->total_quads = quads; p->total_items = items;
-  p->total_blocks_sync = sync_blocks;
+  p->total_blocks_sync = sync_blocks; p->total_blocks_write = write_blocks;
   // ---- pack descriptors + raw scan bytes into pinned staging
   size_t off = 0;
   p->off_images = off; off += Align(sizeof(JpegImage) * n, 16);
@@ -1609,7 +1969,9 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
   p->off_quants = off; off += Align(sizeof(QuantSet) * p->quants.size(), 16);
   p->off_quads = off; off += Align(sizeof(int64_t) * n, 16);
   p->off_items = off; off += Align(sizeof(int64_t) * n, 16);
+  p->off_work = off; off += Align(sizeof(int64_t) * n, 16);
   p->off_blkimg = off; off += Align(sizeof(int32_t) * p->block_image.size(), 16);
+  p->off_wblkimg = off; off += Align(sizeof(int32_t) * p->wblock_image.size(), 16);
   p->off_raw = off;
   p->desc_bytes = off;
   const size_t total = off + raw + 64;
@@ -1626,7 +1988,9 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
   memcpy(p->h_stage + p->off_quants, p->quants.data(), sizeof(QuantSet) * p->quants.size());
   memcpy(p->h_stage + p->off_quads, p->first_quad.data(), sizeof(int64_t) * n);
   memcpy(p->h_stage + p->off_items, p->first_item.data(), sizeof(int64_t) * n);
+  memcpy(p->h_stage + p->off_work, p->first_work.data(), sizeof(int64_t) * n);
   memcpy(p->h_stage + p->off_blkimg, p->block_image.data(), sizeof(int32_t) * p->block_image.size());
+  memcpy(p->h_stage + p->off_wblkimg, p->wblock_image.data(), sizeof(int32_t) * p->wblock_image.size());
   // the scan bytes themselves are staged by JpegUpload, chunk by chunk, so that the H2D copy starts while later samples
   // are still being copied into the pinned buffer
   p->stage_off.resize(n);
@@ -1729,7 +2093,6 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
     if ((rc = GrowDevice(p->d_state, p->d_sub_cap, (size_t)p->total_subseq + 1))) return rc;
     if ((rc = GrowDevice(p->d_n, cap2, (size_t)p->total_subseq + 1))) return rc;
   }
-  if ((rc = GrowDevice(p->d_chain0, p->d_chain0_cap, (size_t)p->total_blocks_sync + 1))) return rc;
   if ((rc = GrowDevice(p->d_chain1, p->d_chain1_cap, (size_t)p->total_subseq + 1))) return rc;
   if ((rc = GrowDevice(p->d_chain2, p->d_chain2_cap, (size_t)p->total_subseq + 1))) return rc;
   if ((rc = GrowDevice(p->d_chain3, p->d_chain3_cap, (size_t)p->total_subseq + 1))) return rc;
@@ -1738,11 +2101,16 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   if ((rc = GrowDevice(p->d_dc, p->d_dc_cap, (size_t)p->total_coefs / 64 + 64))) return rc;
   if ((rc = GrowDevice(p->d_planes, p->d_planes_cap, (size_t)p->total_plane_bytes + 64))) return rc;
   if ((rc = GrowDevice(p->d_status, p->d_status_cap, (size_t)p->n + 1))) return rc;
+  if (!p->posts.empty()) {
+    if ((rc = GrowDevice(p->d_post, p->d_post_cap, p->post_bytes + 256))) return rc;
+    if ((rc = GrowDevice(p->d_posts, p->d_posts_cap, p->posts.size()))) return rc;
+  }
   // image descriptors carry the output pointers: small separate upload from their own pinned buffer (waiting on the event of
   // the big bit-stream copy here would stall the host for the whole H2D transfer)
   {
     if (p->img_pending) { DB_CUDA(cudaEventSynchronize(p->img_uploaded)); p->img_pending = false; }
-    const size_t need = sizeof(JpegImage) * p->n;
+    const size_t img_bytes = Align(sizeof(JpegImage) * p->n, 16);
+    const size_t need = img_bytes + sizeof(JpegPost) * p->posts.size();
     if (need > p->h_images_cap) {
       if (p->h_images) cudaFreeHost(p->h_images);
       p->h_images = nullptr; p->h_images_cap = 0;
@@ -1751,7 +2119,17 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
     }
     JpegImage *hi = reinterpret_cast<JpegImage *>(p->h_images);
     for (int i = 0; i < p->n; i++) { hi[i] = p->images[i]; hi[i].out = static_cast<uint8_t *>(out_ptrs[i]); }
-    DB_CUDA(cudaMemcpyAsync(p->d_stage + p->off_images, hi, need, cudaMemcpyHostToDevice, stream));
+    JpegPost *hp = reinterpret_cast<JpegPost *>(p->h_images + img_bytes);
+    for (size_t k = 0; k < p->posts.size(); k++) {
+      const int i = p->post_sample[k];
+      hp[k] = p->posts[k];
+      hp[k].src = p->d_post + p->post_off[k];
+      hp[k].dst = out_ptrs[i];
+      hi[i].out = p->d_post + p->post_off[k];              // the decoder writes the window into scratch
+    }
+    DB_CUDA(cudaMemcpyAsync(p->d_stage + p->off_images, hi, sizeof(JpegImage) * p->n, cudaMemcpyHostToDevice, stream));
+    if (!p->posts.empty())
+      DB_CUDA(cudaMemcpyAsync(p->d_posts, hp, sizeof(JpegPost) * p->posts.size(), cudaMemcpyHostToDevice, stream));
     DB_CUDA(cudaEventRecord(p->img_uploaded, stream));
     p->img_pending = true;
   }
@@ -1765,51 +2143,56 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   const int nunits = (int)p->units.size();
   const int sms = NumSMs();
   cudaStream_t s = stream;
-  // the clean stream must be zero-padded behind every unit (the bit reader peeks ahead)
-  DB_CUDA(cudaMemsetAsync(p->d_clean, 0, p->clean_bytes + 1024, s));
+  // (the clean stream is zero-padded behind every unit by the scatter kernel itself: no memset of the 129 MB buffer)
   DB_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * p->n, s));
   DB_CUDA(cudaMemsetAsync(p->d_chain_count, 0, sizeof(uint32_t) * 8, s));
   {
     const int grid = (int)std::min<uint32_t>(p->nchunks, (uint32_t)sms * 16);
     { ProfScope ps_("jpeg_unstuff_count", s); unstuff_count_kernel<<<grid, 256, 0, s>>>(d_raw, d_units, nunits, p->nchunks, p->d_chunk); }
-    { ProfScope ps_("jpeg_unstuff_scan", s); unstuff_scan_kernel<<<(nunits + 127) / 128, 128, 0, s>>>(d_units, nunits, p->d_chunk, p->d_unit_len); }
+    { ProfScope ps_("jpeg_unstuff_scan", s); unstuff_scan_kernel<<<(nunits + 7) / 8, 256, 0, s>>>(d_units, nunits, p->d_chunk, p->d_unit_len); }
     { ProfScope ps_("jpeg_unstuff_scatter", s); unstuff_scatter_kernel<<<grid, 256, 0, s>>>(d_raw, d_units, nunits, p->nchunks, p->d_chunk, p->d_clean); }
     CountLaunch(3);
   }
   HuffCtx cx;
-  cx.images = d_images; cx.nimages = p->n; cx.block_image = reinterpret_cast<const int32_t *>(p->d_stage + p->off_blkimg); cx.units = d_units; cx.unit_clean_len = p->d_unit_len; cx.tables = d_tables;
+  cx.images = d_images; cx.nimages = p->n; cx.block_image = reinterpret_cast<const int32_t *>(p->d_stage + p->off_blkimg);
+  cx.wblock_image = reinterpret_cast<const int32_t *>(p->d_stage + p->off_wblkimg);
+  cx.units = d_units; cx.unit_clean_len = p->d_unit_len; cx.tables = d_tables;
   cx.clean = p->d_clean; cx.s_state = p->d_state; cx.s_n = p->d_n; cx.coef = p->d_coef; cx.dc = p->d_dc; cx.log2_sub = p->log2_sub;
   cx.status = p->d_status;
-  cx.chains[0] = p->d_chain0; cx.chains[1] = p->d_chain1; cx.chains[2] = p->d_chain2; cx.chains[3] = p->d_chain3; cx.chain_count = p->d_chain_count;
-  const size_t hsmem = sync_smem_bytes(p->log2_sub, false), wsmem = sync_smem_bytes(p->log2_sub, true);
+  cx.chains[0] = p->d_chain1; cx.chains[1] = p->d_chain2; cx.chains[2] = p->d_chain3; cx.chain_count = p->d_chain_count;
+  const size_t hsmem = sync_smem_bytes(p->log2_sub, false), wsmem = write_smem_bytes(p->log2_sub);
+  const size_t walk_smem = kLutWords * 4 + 4 * sizeof(HuffSlow) + (size_t)(kTailColWords + kMaxBlocksPerMcu) * kTailThreads * 4;
   if (!p->smem_opted) {
     DB_CUDA(cudaFuncSetAttribute(huff_sync_intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_smem_bytes(kMaxLog2Sub, false)));
-    DB_CUDA(cudaFuncSetAttribute(huff_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_smem_bytes(kMaxLog2Sub, true)));
+    DB_CUDA(cudaFuncSetAttribute(huff_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)write_smem_bytes(kMaxLog2Sub)));
+    DB_CUDA(cudaFuncSetAttribute(huff_sync_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
+    int per_sm = 0;
+    DB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, huff_sync_walk_kernel, kTailThreads, walk_smem));
+    p->walk_max_grid = std::max(1, per_sm) * sms * 4;
     p->smem_opted = true;
   }
   { ProfScope ps_("jpeg_huff_sync_intra", s); huff_sync_intra_kernel<<<p->total_blocks_sync, kSyncThreads, hsmem, s>>>(cx); }
   {
-    const size_t tail_smem = kLutWords * 4 + 4 * sizeof(HuffSlow) + (size_t)(kTailColWords + kMaxBlocksPerMcu) * kTailThreads * 4;
-    if (p->tail_grid == 0) {
-      int per_sm = 0;
-      DB_CUDA(cudaFuncSetAttribute(huff_sync_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem));
-      DB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, huff_sync_tail_kernel, kTailThreads, tail_smem));
-      p->tail_grid = std::max(1, per_sm) * sms;
-    }
-    const int64_t want = (p->total_subseq / 3 + kTailThreads - 1) / kTailThreads;          // ~30 % of the chains are still live after round 1
-    const int tgrid = (int)std::max<int64_t>(1, std::min<int64_t>(p->tail_grid, want));
-    void *args[] = { &cx };
-    ProfScope ps_("jpeg_huff_sync_tail", s);
-    DB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(huff_sync_tail_kernel), dim3(tgrid), dim3(kTailThreads), args, tail_smem, s));
+    // chain walk: grids sized for the expected list lengths (about 30 % / 8 % / 2.5 % of the subsequences carry a live chain
+    // after 1 / 2 / 3 visits); CTAs beyond the actual length return at once, grid-stride loops cover longer lists
+    auto walk_grid = [&](double frac) {
+      const int64_t want = (int64_t)(p->total_subseq * frac) / kTailThreads + p->total_blocks_sync / kTailThreads + 1;
+      return (int)std::max<int64_t>(1, std::min<int64_t>(p->walk_max_grid, want));
+    };
+    { ProfScope ps_("jpeg_huff_sync_walk1", s); huff_sync_walk_kernel<<<walk_grid(0.40), kTailThreads, walk_smem, s>>>(cx, 0, 1, 1); }
+    { ProfScope ps_("jpeg_huff_sync_walk2", s); huff_sync_walk_kernel<<<walk_grid(0.14), kTailThreads, walk_smem, s>>>(cx, 1, 2, 1); }
+    { ProfScope ps_("jpeg_huff_sync_walk3", s); huff_sync_walk_kernel<<<walk_grid(0.06), kTailThreads, walk_smem, s>>>(cx, 2, 0, 1 << 30); }
+    CountLaunch(2);
   }
   { ProfScope ps_("jpeg_huff_scan", s); huff_scan_kernel<<<p->n, 1024, 0, s>>>(cx); }
   CountLaunch();
-  { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_sync, kSyncThreads, wsmem, s>>>(cx); }
+  { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_write, kWriteThreads, wsmem, s>>>(cx); }
   { ProfScope ps_("jpeg_dc_scan", s); dc_scan_kernel<<<p->n, 1024, 0, s>>>(d_images, p->d_dc); }
   {
-    const int64_t total_blocks = p->total_coefs / 64;
+    const int64_t total_blocks = p->total_work;
+    const auto *d_work = reinterpret_cast<const int64_t *>(p->d_stage + p->off_work);
     const int grid = (int)std::min<int64_t>((total_blocks + 127) / 128, (int64_t)sms * 32);
-    { ProfScope ps_("jpeg_idct", s); idct_kernel<<<grid, 128, 0, s>>>(d_images, p->n, total_blocks, p->d_coef, p->d_dc, d_quants, p->d_planes); }
+    { ProfScope ps_("jpeg_idct", s); idct_kernel<<<grid, 128, 0, s>>>(d_images, d_work, p->n, total_blocks, p->d_coef, p->d_dc, d_quants, p->d_planes); }
     if (p->total_quads > 0) {
       const int grid2 = (int)std::min<int64_t>((p->total_quads + 255) / 256, (int64_t)sms * 32);
       { ProfScope ps_("jpeg_upsample_color_generic", s); color_kernel<<<grid2, 256, 0, s>>>(d_images, d_quads, p->n, p->total_quads, p->d_planes); }
@@ -1820,6 +2203,13 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
       { ProfScope ps_("jpeg_upsample_color", s); color_fast_kernel<<<grid3, 128, 0, s>>>(d_images, d_items, p->n, p->total_items, p->d_planes); }
       CountLaunch();
     }
+  }
+  if (!p->posts.empty()) {
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((p->total_post_px + 255) / 256, (int64_t)sms * 16));
+    ProfScope ps_("jpeg_post", s);
+    if (p->dtype == DALIB200_FLOAT) jpeg_post_kernel<float><<<grid, 256, 0, s>>>(p->d_posts, (int)p->posts.size(), p->total_post_px);
+    else jpeg_post_kernel<uint8_t><<<grid, 256, 0, s>>>(p->d_posts, (int)p->posts.size(), p->total_post_px);
+    CountLaunch();
   }
   CountLaunch(5);
   DB_CUDA(cudaGetLastError());

@@ -147,7 +147,7 @@ def _source_group(pipe, source, n, base, layout=None, device="cpu"):
 
 def _readers_file(file_root=None, file_list=None, files=None, labels=None, *, random_shuffle=False, shuffle_after_epoch=False,
                   initial_fill=1024, shard_id=0, num_shards=1, stick_to_shard=False, pad_last_batch=False, seed=-1, name=None,
-                  device="cpu", **_ignored):
+                  device="cpu", shuffle_after_epoch_seed=None, **_ignored):
     """fn.readers.file (dali/operators/reader/file_reader_op.cc, loader/file_label_loader.h): (encoded file bytes, label)."""
     from .readers import FileReader
     pipe = _current()
@@ -158,7 +158,7 @@ def _readers_file(file_root=None, file_list=None, files=None, labels=None, *, ra
     if seed is None or seed < 0:
         seed = pipe.seed if getattr(pipe, "seed", -1) not in (None, -1) else -1
     reader = FileReader(pipe.max_batch_size, file_root, file_list, files, labels, random_shuffle, shuffle_after_epoch, initial_fill,
-                        shard_id, num_shards, stick_to_shard, pad_last_batch, seed)
+                        shard_id, num_shards, stick_to_shard, pad_last_batch, seed, shuffle_after_epoch_seed)
     inst = name or pipe._new_name("readers__File")
     g = _source_group(pipe, reader, 2, inst)
     pipe._readers[inst] = reader

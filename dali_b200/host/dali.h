@@ -286,6 +286,7 @@ inline ArgValue MakeArg(const std::string &v) { ArgValue a; a.kind = ArgValue::S
 inline ArgValue MakeArg(const char *v) { return MakeArg(std::string(v)); }
 inline ArgValue MakeArg(const std::vector<float> &v) { ArgValue a; a.kind = ArgValue::FLOAT_VEC; a.fv = v; return a; }
 inline ArgValue MakeArg(const std::vector<int64_t> &v) { ArgValue a; a.kind = ArgValue::INT_VEC; a.iv = v; return a; }
+inline ArgValue MakeArg(const std::vector<int> &v) { ArgValue a; a.kind = ArgValue::INT_VEC; a.iv.assign(v.begin(), v.end()); return a; }
 inline ArgValue MakeArg(DALIDataType v) { return MakeArg(static_cast<int64_t>(v)); }
 inline ArgValue MakeArg(DALIInterpType v) { return MakeArg(static_cast<int64_t>(v)); }
 inline ArgValue MakeArg(DALIImageType v) { return MakeArg(static_cast<int64_t>(v)); }

@@ -19,6 +19,8 @@
 #include <cmath>
 #include <limits>
 #include "dali.h"
+#include "random_crop.h"
+#include <ctime>
 #include <cstdlib>
 #include "../../include/dali_b200.h"
 
@@ -95,33 +97,53 @@ DALI_SCHEMA(decoders__Image)
     .AddOptionalArg("cache_batch_copy", "ignored", true)
     .AddOptionalArg("cache_type", "ignored", std::string(""));
 
-class ImageDecoderMixed : public Operator<MixedBackend> {
+// Common part of decoders.image / image_crop / image_random_crop / image_slice: header parse, region of interest from the
+// derived class (in OUTPUT = oriented coordinates, imgcodec.h:26-44), plan setup, launch, asynchronous status check.
+class ImageDecoderBase : public Operator<MixedBackend> {
  public:
-  explicit ImageDecoderMixed(const OpSpec &spec) : Operator<MixedBackend>(spec) {
-    output_type_ = spec.GetArgument<DALIImageType>("output_type");
-    DALI_ENFORCE(spec.GetArgument<DALIDataType>("dtype") == DALI_UINT8, "decoders.image: only dtype=UINT8 is supported");
-    fancy_ = spec.GetArgument<bool>("jpeg_fancy_upsampling");
-    CheckStatus(dalib200JpegPlanCreate(&plan_, max_batch_size_), "decoders.image");
+  explicit ImageDecoderBase(const OpSpec &spec, const char *name) : Operator<MixedBackend>(spec), name_(name) {
+    prm_.output_type = spec.GetArgument<DALIImageType>("output_type");
+    const DALIDataType dt = spec.GetArgument<DALIDataType>("dtype");
+    DALI_ENFORCE(dt == DALI_UINT8 || dt == DALI_FLOAT, name_, ": the GPU decoder supports dtype UINT8 and FLOAT");
+    out_type_ = dt;
+    prm_.dtype = dt == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT;
+    prm_.fancy_upsampling = spec.GetArgument<bool>("jpeg_fancy_upsampling");
+    prm_.adjust_orientation = spec.GetArgument<bool>("adjust_orientation");
+    CheckStatus(dalib200JpegPlanCreate(&plan_, max_batch_size_), name_);
   }
-  ~ImageDecoderMixed() override { dalib200JpegPlanDestroy(plan_); }
+  ~ImageDecoderBase() override { dalib200JpegPlanDestroy(plan_); }
 
  protected:
+  // fills rois_[i] (use_roi = 0: whole image) for an image whose ORIENTED size is H x W
+  virtual void SampleRoi(dalib200JpegRoi &roi, const Workspace &ws, int i, int H, int W) { roi.use_roi = 0; }
+  virtual bool HasRoi() const { return false; }
+
   bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
     const auto &in = ws.Input<CPUBackend>(0);
     const int n = in.num_samples();
-    DALI_ENFORCE(in.type() == DALI_UINT8, "decoders.image expects encoded streams as 1-D uint8 tensors");
+    DALI_ENFORCE(in.type() == DALI_UINT8, name_, " expects encoded streams as 1-D uint8 tensors");
     std::vector<const uint8_t *> ptrs(n);
     std::vector<size_t> lens(n);
     for (int i = 0; i < n; i++) { ptrs[i] = in.tensor<uint8_t>(i); lens[i] = static_cast<size_t>(in.shape().tensor_size(i)); }
-    CheckStatus(dalib200JpegPlanSetup(plan_, n, ptrs.data(), lens.data(), output_type_, fancy_), "decoders.image");
+    rois_.assign(n, dalib200JpegRoi{0, 0, 0, 0, 0});
+    if (HasRoi()) {
+      for (int i = 0; i < n; i++) {
+        dalib200JpegInfo info;
+        if (dalib200JpegGetInfo(ptrs[i], lens[i], &info) != DALIB200_SUCCESS)
+          throw DALIException(make_string(name_, ": sample ", i, ": ", dalib200GetLastError()));
+        int H = info.height, W = info.width;
+        if (prm_.adjust_orientation && info.orientation >= 5) std::swap(H, W);      // image_decoder.h:678-681
+        SampleRoi(rois_[i], ws, i, H, W);
+      }
+    }
+    CheckStatus(dalib200JpegPlanSetupEx(plan_, n, ptrs.data(), lens.data(), &prm_, HasRoi() ? rois_.data() : nullptr), name_);
     out.resize(1);
-    out[0].type = DALI_UINT8;
+    out[0].type = out_type_;
     out[0].shape.resize(n, 3);
-    const int ch = output_type_ == DALI_GRAY ? 1 : 3;
     for (int i = 0; i < n; i++) {
-      dalib200JpegInfo info;
-      CheckStatus(dalib200JpegPlanGetInfo(plan_, i, &info), "decoders.image");
-      out[0].shape.set_tensor_shape(i, { info.height, info.width, ch });
+      int32_t hwc[3];
+      CheckStatus(dalib200JpegPlanGetOutputShape(plan_, i, hwc), name_);
+      out[0].shape.set_tensor_shape(i, { hwc[0], hwc[1], hwc[2] });
     }
     return true;
   }
@@ -130,15 +152,235 @@ class ImageDecoderMixed : public Operator<MixedBackend> {
     out.SetLayout("HWC");
     std::vector<void *> optr(out.num_samples());
     for (int i = 0; i < out.num_samples(); i++) optr[i] = out.raw_mutable_tensor(i);
-    CheckStatus(dalib200JpegUpload(plan_, ws.stream()), "decoders.image");
-    CheckStatus(dalib200JpegLaunch(plan_, optr.data(), ws.stream()), "decoders.image");
+    CheckStatus(dalib200JpegUpload(plan_, ws.stream()), name_);
+    CheckStatus(dalib200JpegLaunch(plan_, optr.data(), ws.stream()), name_);
   }
- private:
+
   dalib200JpegPlan *plan_ = nullptr;
-  int output_type_ = DALI_RGB;
-  bool fancy_ = true;
+  dalib200JpegParams prm_{};
+  DALIDataType out_type_ = DALI_UINT8;
+  std::vector<dalib200JpegRoi> rois_;
+  const char *name_;
+};
+
+class ImageDecoderMixed : public ImageDecoderBase {
+ public:
+  explicit ImageDecoderMixed(const OpSpec &spec) : ImageDecoderBase(spec, "decoders.image") {}
 };
 DALI_REGISTER_OPERATOR(decoders__Image, ImageDecoderMixed, Mixed);
+
+#define DALIB200_DECODER_ARGS(schema)                                                                                         \
+  schema.AddOptionalArg("output_type", "Colour space of the output image.", DALI_RGB)                                          \
+      .AddOptionalArg("dtype", "Output data type.", DALI_UINT8)                                                                \
+      .AddOptionalArg("adjust_orientation", "Use EXIF orientation metadata to rectify the images.", true)                      \
+      .AddOptionalArg("use_fast_idct", "ignored (the islow integer IDCT is always used)", false)                               \
+      .AddOptionalArg("jpeg_fancy_upsampling", "Use libjpeg-turbo fancy (triangle) chroma upsampling.", true)                  \
+      .AddOptionalArg("hybrid_huffman_threshold", "ignored", 1000000)                                                          \
+      .AddOptionalArg("hw_decoder_load", "ignored (no hardware engine is used)", 0.9f)                                         \
+      .AddOptionalArg("device_memory_padding", "ignored", 16777216)                                                            \
+      .AddOptionalArg("host_memory_padding", "ignored", 8388608)                                                               \
+      .AddOptionalArg("affine", "ignored", true)                                                                               \
+      .AddOptionalArg("split_stages", "ignored", false)                                                                        \
+      .AddOptionalArg("use_chunk_allocator", "ignored", false)                                                                 \
+      .AddOptionalArg("memory_stats", "ignored", false)
+
+// ----------------------------------------------------------------------------------------------- decoders.image_crop
+// imgcodec decoder_schema.cc:170-196 + CropAttr (crop_attr.cc:21-88,100-239): the window is anchored at
+// round(crop_pos * (image - crop)) -- the same arithmetic as CropMirrorNormalize -- and only its MCUs are transformed.
+struct CropWindowArgs {
+  bool has_crop = false, has_hw = false, truncate = false;
+  void Init(const OpSpec &spec, const char *name) {
+    has_crop = spec.ArgumentDefined("crop");
+    has_hw = spec.ArgumentDefined("crop_h") || spec.ArgumentDefined("crop_w");
+    DALI_ENFORCE(!(has_crop && has_hw), "`crop` argument is not compatible with `crop_h`, `crop_w`, `crop_d`");
+    DALI_ENFORCE(spec.ArgumentDefined("crop_h") == spec.ArgumentDefined("crop_w"), "`crop_h` and `crop_w` arguments must be provided together");
+    const std::string r = spec.GetArgument<std::string>("rounding");
+    DALI_ENFORCE(r == "round" || r == "truncate", "``rounding`` value ", r, " is not supported. Supported values are \"round\", or \"truncate\".");
+    truncate = r == "truncate";
+  }
+  // window [y0, y0 + h) x [x0, x0 + w) for an H x W image
+  void Get(const OpSpec &spec, const Workspace &ws, int i, int64_t H, int64_t W, int64_t &y0, int64_t &x0, int64_t &h, int64_t &w) const {
+    h = H; w = W;
+    float px = 0.5f, py = 0.5f;
+    bool hh = false, hw = false;
+    if (has_crop) {
+      auto c = spec.GetFloatVecArgument("crop", &ws, i);
+      DALI_ENFORCE(c.size() == 2, "`crop` argument should have 2 or 3 elements depending on the input data shape");
+      h = static_cast<int>(c[0]); w = static_cast<int>(c[1]); hh = hw = true;
+    } else if (has_hw) {
+      h = static_cast<int>(spec.GetArgument<float>("crop_h", &ws, i)); w = static_cast<int>(spec.GetArgument<float>("crop_w", &ws, i));
+      hh = hw = true;
+    }
+    if (!(hh && h > 0)) h = H; else py = spec.GetArgument<float>("crop_pos_y", &ws, i);
+    if (!(hw && w > 0)) w = W; else px = spec.GetArgument<float>("crop_pos_x", &ws, i);
+    DALI_ENFORCE(px >= 0.0f && px <= 1.0f && py >= 0.0f && py <= 1.0f, "Anchor for dimension is out of range [0.0, 1.0]");
+    auto rnd = [&](double v) { return truncate ? static_cast<int64_t>(v) : static_cast<int64_t>(std::round(v)); };
+    y0 = rnd(static_cast<double>(py) * (H - h)); x0 = rnd(static_cast<double>(px) * (W - w));
+  }
+};
+
+#define DALIB200_CROP_ARGS(schema)                                                                                             \
+  schema.AddOptionalArgNoDefault("crop", "Shape of the cropped image (H, W).", true)                                           \
+      .AddOptionalArgNoDefault("crop_h", "Cropping window height.", true)                                                      \
+      .AddOptionalArgNoDefault("crop_w", "Cropping window width.", true)                                                       \
+      .AddOptionalArgNoDefault("crop_d", "not supported (2-D images only)", true)                                              \
+      .AddOptionalArg("crop_pos_x", "Normalised horizontal position of the window.", 0.5f, true)                               \
+      .AddOptionalArg("crop_pos_y", "Normalised vertical position of the window.", 0.5f, true)                                 \
+      .AddOptionalArg("crop_pos_z", "unused", 0.5f, true)                                                                      \
+      .AddOptionalArg("rounding", "round | truncate", std::string("round"))
+
+DALI_SCHEMA(decoders__ImageCrop)
+    .DocStr("Decodes JPEG images on the GPU and extracts a fixed crop window; only the blocks under the window are transformed.")
+    .NumInput(1).NumOutput(1)
+    DALIB200_DECODER_ARGS() DALIB200_CROP_ARGS();
+
+class ImageDecoderCropMixed : public ImageDecoderBase {
+ public:
+  explicit ImageDecoderCropMixed(const OpSpec &spec) : ImageDecoderBase(spec, "decoders.image_crop") { crop_.Init(spec, name_); }
+ protected:
+  bool HasRoi() const override { return true; }
+  void SampleRoi(dalib200JpegRoi &roi, const Workspace &ws, int i, int H, int W) override {
+    int64_t y0, x0, h, w;
+    crop_.Get(spec_, ws, i, H, W, y0, x0, h, w);
+    DALI_ENFORCE(y0 >= 0 && x0 >= 0 && y0 + h <= H && x0 + w <= W, "decoders.image_crop: sample ", i, ": the crop window {", y0, ", ", x0,
+                 "} + {", h, ", ", w, "} does not fit the image {", H, ", ", W, "}");
+    roi = { 1, static_cast<int>(x0), static_cast<int>(y0), static_cast<int>(x0 + w), static_cast<int>(y0 + h) };
+  }
+  CropWindowArgs crop_;
+};
+DALI_REGISTER_OPERATOR(decoders__ImageCrop, ImageDecoderCropMixed, Mixed);
+
+// ----------------------------------------------------------------------------------------------- decoders.image_random_crop
+#define DALIB200_RANDOM_CROP_ARGS(schema)                                                                                      \
+  schema.AddOptionalArg("random_aspect_ratio", "Range from which to choose random aspect ratio (width / height).", std::vector<float>{3.f / 4, 4.f / 3}) \
+      .AddOptionalArg("random_area", "Range from which to choose random area fraction A.", std::vector<float>{0.08f, 1.0f})   \
+      .AddOptionalArg("num_attempts", "Maximum number of attempts used to choose random area and aspect ratio.", 10)           \
+      .AddOptionalArg("seed", "Random seed.", -1)
+
+static std::vector<RandomCropGenerator> MakeCropGenerators(const OpSpec &spec, int max_batch) {
+  auto ar = spec.GetRepeatedArgument<float>("random_aspect_ratio");
+  auto area = spec.GetRepeatedArgument<float>("random_area");
+  if (ar.size() == 1) ar.push_back(ar[0]);
+  if (area.size() == 1) area.push_back(area[0]);
+  DALI_ENFORCE(ar.size() == 2 && area.size() == 2, "random_aspect_ratio / random_area expect a scalar or a [min, max] pair");
+  DALI_ENFORCE(ar[0] <= ar[1], "Provided empty range");
+  DALI_ENFORCE(area[0] <= area[1], "Provided empty range");
+  int64_t seed = spec.GetArgument<int>("seed");
+  if (seed < 0) seed = static_cast<int64_t>(time(nullptr));         // random_crop_attr.h:50-52
+  return MakeRandomCropGenerators(max_batch, seed, ar.data(), area.data(), spec.GetArgument<int>("num_attempts"));
+}
+
+DALI_SCHEMA(decoders__ImageRandomCrop)
+    .DocStr("Decodes JPEG images on the GPU and extracts a randomly placed window of random area and aspect ratio.")
+    .NumInput(1).NumOutput(1)
+    DALIB200_DECODER_ARGS() DALIB200_RANDOM_CROP_ARGS();
+
+class ImageDecoderRandomCropMixed : public ImageDecoderBase {
+ public:
+  explicit ImageDecoderRandomCropMixed(const OpSpec &spec)
+      : ImageDecoderBase(spec, "decoders.image_random_crop"), gens_(MakeCropGenerators(spec, max_batch_size_)) {}
+ protected:
+  bool HasRoi() const override { return true; }
+  void SampleRoi(dalib200JpegRoi &roi, const Workspace &, int i, int H, int W) override {
+    const CropWindow2D c = gens_[i].Generate(H, W);
+    roi = { 1, c.anchor[1], c.anchor[0], c.anchor[1] + c.shape[1], c.anchor[0] + c.shape[0] };
+  }
+  std::vector<RandomCropGenerator> gens_;
+};
+DALI_REGISTER_OPERATOR(decoders__ImageRandomCrop, ImageDecoderRandomCropMixed, Mixed);
+
+// ----------------------------------------------------------------------------------------------- decoders.image_slice
+// decoder_schema.cc:198-245 + SliceAttr (dali/operators/generic/slice/slice_attr.h): anchor / shape as positional CPU inputs
+// (normalized by default) or as `start` / `rel_start` / `end` / `rel_end` / `shape` / `rel_shape` arguments, axes (1, 0) =
+// (x, y) by default ("WH").
+DALI_SCHEMA(decoders__ImageSlice)
+    .DocStr("Decodes JPEG images on the GPU and extracts a region of interest given by anchor and shape.")
+    .NumInput(1, 3).NumOutput(1)
+    DALIB200_DECODER_ARGS()
+    .AddOptionalArg("axes", "Order of the dimensions of anchor and shape.", std::vector<int>{1, 0})
+    .AddOptionalArg("axis_names", "Order of the dimensions of anchor and shape, as layout characters.", std::string("WH"))
+    .AddOptionalArg("normalized_anchor", "The anchor input is in normalised coordinates.", true)
+    .AddOptionalArg("normalized_shape", "The shape input is in normalised coordinates.", true)
+    .AddOptionalArgNoDefault("start", "Start of the slice (absolute).", true)
+    .AddOptionalArgNoDefault("rel_start", "Start of the slice (relative).", true)
+    .AddOptionalArgNoDefault("end", "End of the slice (absolute).", true)
+    .AddOptionalArgNoDefault("rel_end", "End of the slice (relative).", true)
+    .AddOptionalArgNoDefault("shape", "Shape of the slice (absolute).", true)
+    .AddOptionalArgNoDefault("rel_shape", "Shape of the slice (relative).", true);
+
+class ImageDecoderSliceMixed : public ImageDecoderBase {
+ public:
+  explicit ImageDecoderSliceMixed(const OpSpec &spec) : ImageDecoderBase(spec, "decoders.image_slice") {
+    const std::string names = spec.GetArgument<std::string>("axis_names");
+    if (spec.ArgumentDefined("axes") || names.empty()) {
+      axes_ = spec.GetRepeatedArgument<int>("axes");
+    } else {
+      for (char c : names) {
+        DALI_ENFORCE(c == 'H' || c == 'W', "decoders.image_slice: axis_names may contain H and W only");
+        axes_.push_back(c == 'H' ? 0 : 1);
+      }
+    }
+    for (int a : axes_) DALI_ENFORCE(a == 0 || a == 1, "decoders.image_slice: only the H (0) and W (1) axes can be sliced");
+    norm_anchor_ = spec.GetArgument<bool>("normalized_anchor"); norm_shape_ = spec.GetArgument<bool>("normalized_shape");
+    positional_ = spec.NumInput() == 3;
+    DALI_ENFORCE(spec.NumInput() == 1 || spec.NumInput() == 3, "decoders.image_slice expects 1 input (and slice arguments) or 3 inputs (data, anchor, shape)");
+    const bool has_start = spec.ArgumentDefined("start") || spec.ArgumentDefined("rel_start");
+    const bool has_end = spec.ArgumentDefined("end") || spec.ArgumentDefined("rel_end");
+    const bool has_shape = spec.ArgumentDefined("shape") || spec.ArgumentDefined("rel_shape");
+    DALI_ENFORCE(!(positional_ && (has_start || has_end || has_shape)), "Named slice arguments cannot be mixed with positional anchor / shape inputs");
+    DALI_ENFORCE(!(has_end && has_shape), "`end`/`rel_end` and `shape`/`rel_shape` are mutually exclusive");
+  }
+ protected:
+  bool HasRoi() const override { return true; }
+  void SampleRoi(dalib200JpegRoi &roi, const Workspace &ws, int i, int H, int W) override {
+    const int64_t dim[2] = { H, W };
+    int64_t b[2] = { 0, 0 }, e[2] = { H, W };
+    const int na = static_cast<int>(axes_.size());
+    for (int k = 0; k < na; k++) {
+      const int ax = axes_[k];
+      double anchor_val = 0, end_val = static_cast<double>(dim[ax]);
+      if (positional_) {
+        // slice_attr.h:282-330 (PositionalSliceAttr)
+        const auto &anc = ws.Input<CPUBackend>(1);
+        const auto &shp = ws.Input<CPUBackend>(2);
+        DALI_ENFORCE(anc.type() == DALI_FLOAT && shp.type() == DALI_FLOAT, "decoders.image_slice: anchor and shape inputs must be float");
+        DALI_ENFORCE(anc.shape().tensor_size(i) == na && shp.shape().tensor_size(i) == na,
+                     "Expected ", na, " elements for slice arguments (start/shape). Got ", anc.shape().tensor_size(i));
+        anchor_val = anc.tensor<float>(i)[k];
+        double shape_val = shp.tensor<float>(i)[k];
+        if (norm_anchor_ && norm_shape_) {        // multiply once, after the sum
+          end_val = (anchor_val + shape_val) * dim[ax];
+          anchor_val *= dim[ax];
+        } else {
+          if (norm_anchor_) anchor_val *= dim[ax];
+          if (norm_shape_) shape_val *= dim[ax];
+          end_val = anchor_val + shape_val;
+        }
+      } else {
+        // slice_attr.h:111-181 (NamedSliceAttr); start / end / shape are integer arguments, rel_* are floats
+        auto arg = [&](const char *name) { return static_cast<double>(spec_.GetFloatVecArgument(name, &ws, i, na)[k]); };
+        const bool has_start = spec_.ArgumentDefined("start"), has_rel_start = spec_.ArgumentDefined("rel_start");
+        if (has_start) anchor_val = static_cast<int>(arg("start"));
+        else if (has_rel_start) anchor_val = static_cast<double>(static_cast<float>(arg("rel_start"))) * dim[ax];
+        if (spec_.ArgumentDefined("end")) end_val = static_cast<int>(arg("end"));
+        else if (spec_.ArgumentDefined("rel_end")) end_val = static_cast<double>(static_cast<float>(arg("rel_end"))) * dim[ax];
+        else if (spec_.ArgumentDefined("shape")) end_val = anchor_val + static_cast<int>(arg("shape"));
+        else if (has_rel_start && !has_start && spec_.ArgumentDefined("rel_shape"))
+          end_val = (static_cast<double>(static_cast<float>(arg("rel_start"))) + static_cast<double>(static_cast<float>(arg("rel_shape")))) * dim[ax];
+        else if (spec_.ArgumentDefined("rel_shape")) end_val = anchor_val + static_cast<double>(static_cast<float>(arg("rel_shape"))) * dim[ax];
+      }
+      DALI_ENFORCE(end_val >= anchor_val, "end coordinates can't be before start coordinates. Got: start=", anchor_val, " end=", end_val);
+      b[ax] = std::llround(anchor_val);
+      e[ax] = std::llround(end_val);
+    }
+    DALI_ENFORCE(b[0] >= 0 && b[1] >= 0 && e[0] <= H && e[1] <= W && b[0] < e[0] && b[1] < e[1],
+                 "decoders.image_slice: sample ", i, ": slice [", b[0], ", ", e[0], ") x [", b[1], ", ", e[1], ") must be non-empty and inside the image {", H, ", ", W, "}");
+    roi = { 1, static_cast<int>(b[1]), static_cast<int>(b[0]), static_cast<int>(e[1]), static_cast<int>(e[0]) };
+  }
+  std::vector<int> axes_;
+  bool norm_anchor_ = true, norm_shape_ = true, positional_ = false;
+};
+DALI_REGISTER_OPERATOR(decoders__ImageSlice, ImageDecoderSliceMixed, Mixed);
 
 // =============================================================================================== Resize
 DALI_SCHEMA(Resize)
@@ -394,6 +636,116 @@ class ResizeGPU : public Operator<GPUBackend> {
   DALIDataType out_type_ = DALI_UINT8;
 };
 DALI_REGISTER_OPERATOR(Resize, ResizeGPU, GPU);
+
+// =============================================================================================== RandomResizedCrop
+// dali/operators/image/resize/random_resized_crop.{h,cc}: a random window (RandomCropAttr) resized to `size`; the window is
+// the ROI of the resampling (the filter support may reach outside it, unlike crop-then-resize).
+DALI_SCHEMA(RandomResizedCrop)
+    .DocStr("Performs a crop with a randomly selected area and aspect ratio and resizes it to the specified size.")
+    .NumInput(1).NumOutput(1).AllowSequences()
+    .AddArg("size", "Size of the resized image (H, W).")
+    DALIB200_RANDOM_CROP_ARGS()
+    .AddOptionalArg("interp_type", "Type of interpolation.", DALI_INTERP_LINEAR, true)
+    .AddOptionalArg("mag_filter", "Filter used when scaling up.", DALI_INTERP_LINEAR, true)
+    .AddOptionalArg("min_filter", "Filter used when scaling down.", DALI_INTERP_LINEAR, true)
+    .AddOptionalArg("antialias", "Apply an antialiasing filter when scaling down.", true)
+    .AddOptionalArgNoDefault("dtype", "Output type: same as input or FLOAT.")
+    .AddOptionalArg("minibatch_size", "ignored (the whole batch is one launch)", 32)
+    .AddOptionalArg("temp_buffer_hint", "ignored (the intermediate lives in shared memory)", 0);
+
+class RandomResizedCropGPU : public Operator<GPUBackend> {
+ public:
+  explicit RandomResizedCropGPU(const OpSpec &spec) : Operator<GPUBackend>(spec), gens_(MakeCropGenerators(spec, max_batch_size_)) {
+    size_ = spec.GetRepeatedArgument<int>("size");
+    if (size_.size() == 1) size_.push_back(size_[0]);
+    DALI_ENFORCE(size_.size() == 2 && size_[0] > 0 && size_[1] > 0, "RandomResizedCrop: `size` must be one or two positive integers");
+    antialias_ = spec.GetArgument<bool>("antialias");
+    CheckStatus(dalib200ResamplePlanCreate(&plan_, max_batch_size_ * 64), "RandomResizedCrop");
+    plan_cap_ = max_batch_size_ * 64;
+  }
+  ~RandomResizedCropGPU() override { dalib200ResamplePlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    const int n = in.num_samples();
+    DALI_ENFORCE(in.type() == DALI_UINT8 || in.type() == DALI_FLOAT, "RandomResizedCrop: the GPU path supports uint8 and float inputs");
+    out_type_ = in.type();
+    if (spec_.ArgumentDefined("dtype")) out_type_ = spec_.GetArgument<DALIDataType>("dtype");
+    DALI_ENFORCE(out_type_ == in.type() || out_type_ == DALI_FLOAT, "RandomResizedCrop: output type must be the same as input or FLOAT");
+    frames_ = ExpandFrames(in.shape(), in.GetLayout(), "RandomResizedCrop");
+    const int nf = frames_.num_frames();
+    if (nf > plan_cap_) { dalib200ResamplePlanDestroy(plan_); plan_ = nullptr; plan_cap_ = nf; CheckStatus(dalib200ResamplePlanCreate(&plan_, nf), "RandomResizedCrop"); }
+    const bool has_interp = spec_.ArgumentDefined("interp_type"), has_min = spec_.ArgumentDefined("min_filter"),
+               has_mag = spec_.ArgumentDefined("mag_filter");
+    samples_.assign(nf, dalib200ResampleSample());
+    crops_.resize(n);
+    int fk = 0;
+    for (int i = 0; i < n; i++) {
+      const int64_t *s = in.shape().tensor_shape_span(i);
+      const int fs = frames_.first_spatial;
+      const int H = static_cast<int>(s[fs]), W = static_cast<int>(s[fs + 1]);
+      crops_[i] = gens_[i].Generate(H, W);
+      int interp = spec_.GetArgument<int>("interp_type", &ws, i);
+      int minf = DALIB200_FILTER_TRIANGULAR, magf = DALIB200_FILTER_LINEAR;
+      auto conv = [](int t, bool aa) {
+        if (aa && t == DALI_INTERP_LINEAR) t = DALI_INTERP_TRIANGULAR; else if (!aa && t == DALI_INTERP_TRIANGULAR) t = DALI_INTERP_LINEAR;
+        return Interp2Filter(t);
+      };
+      if (has_min) minf = conv(spec_.GetArgument<int>("min_filter", &ws, i), antialias_); else if (has_interp) minf = conv(interp, antialias_);
+      if (has_mag) magf = conv(spec_.GetArgument<int>("mag_filter", &ws, i), false); else if (has_interp) magf = conv(interp, false);
+      const int64_t frames = fs ? s[0] : 1;
+      for (int64_t k = 0; k < frames; k++, fk++) {
+        auto &r = samples_[fk];
+        r.in_h = H; r.in_w = W; r.channels = static_cast<int>(s[fs + 2]);
+        r.out_h = size_[0]; r.out_w = size_[1];
+        for (int d = 0; d < 2; d++) {
+          r.use_roi[d] = 1;
+          r.roi_start[d] = static_cast<float>(crops_[i].anchor[d]);
+          r.roi_end[d] = static_cast<float>(crops_[i].anchor[d] + crops_[i].shape[d]);
+          r.min_filter[d] = { minf, antialias_ ? 1 : 0, 0.0f };
+          r.mag_filter[d] = { magf, 0, 0.0f };
+        }
+      }
+    }
+    CheckStatus(dalib200ResamplePlanSetup(plan_, nf, samples_.data(), in.type() == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT,
+                                          out_type_ == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT), "RandomResizedCrop");
+    out.resize(1);
+    out[0].type = out_type_;
+    out[0].shape.resize(n, in.shape().sample_dim());
+    for (int i = 0; i < n; i++) {
+      TensorShape sh = in.shape().tensor_shape(i);
+      sh[frames_.first_spatial] = size_[0]; sh[frames_.first_spatial + 1] = size_[1];
+      out[0].shape.set_tensor_shape(i, sh);
+    }
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout().empty() ? TensorLayout(frames_.first_spatial ? "FHWC" : "HWC") : in.GetLayout());
+    auto ip = FramePtrs(in, frames_, TypeSize(in.type()));
+    std::vector<void *> op(frames_.num_frames());
+    std::vector<int64_t> next(out.num_samples(), 0);
+    for (int k = 0; k < frames_.num_frames(); k++) {
+      const int s = frames_.sample_of_frame[k];
+      op[k] = static_cast<uint8_t *>(out.raw_mutable_tensor(s)) + next[s];
+      next[s] += static_cast<int64_t>(size_[0]) * size_[1] * frames_.c[k] * TypeSize(out_type_);
+    }
+    CheckStatus(dalib200ResampleLaunch(plan_, ip.data(), op.data(), ws.stream()), "RandomResizedCrop");
+  }
+ private:
+  dalib200ResamplePlan *plan_ = nullptr;
+  int plan_cap_ = 0;
+  bool antialias_ = true;
+  std::vector<int> size_;
+  std::vector<RandomCropGenerator> gens_;
+  std::vector<CropWindow2D> crops_;
+  FrameList frames_;
+  std::vector<dalib200ResampleSample> samples_;
+  DALIDataType out_type_ = DALI_UINT8;
+};
+DALI_REGISTER_OPERATOR(RandomResizedCrop, RandomResizedCropGPU, GPU);
 
 // =============================================================================================== CropMirrorNormalize
 DALI_SCHEMA(CropMirrorNormalize)
@@ -932,4 +1284,17 @@ extern "C" int dalihTestResizeParams(int mode, const float *requested_hw, const 
     for (int d = 0; d < 2; d++) { dst_hw[d] = p.dst[d]; lo_hw[d] = p.lo[d]; hi_hw[d] = p.hi[d]; }
     return 0;
   } catch (...) { return 1; }
+}
+
+// Test hook (CPU): the random crop windows of decoders.image_random_crop / random_resized_crop without a pipeline, so that they can be
+// compared with the reference's own generator (oracle/_ref: random_crop_generator_util.cc + philox.cc) where no GPU exists.
+extern "C" int dalihTestRandomCrop(int64_t seed, int sample_idx, int H, int W, float ar_lo, float ar_hi, float area_lo, float area_hi,
+                                   int num_attempts, int ncalls, int *windows) {
+  const uint64_t key = static_cast<uint64_t>(seed) ^ dali::kRandomCropSeedModifier;
+  dali::RandomCropGenerator gen(ar_lo, ar_hi, area_lo, area_hi, key, static_cast<uint64_t>(dali::kSkipaheadPerSample) * sample_idx, num_attempts);
+  for (int k = 0; k < ncalls; k++) {
+    const dali::CropWindow2D w = gen.Generate(H, W);
+    windows[4 * k] = w.anchor[0]; windows[4 * k + 1] = w.anchor[1]; windows[4 * k + 2] = w.shape[0]; windows[4 * k + 3] = w.shape[1];
+  }
+  return 0;
 }

@@ -34,7 +34,7 @@ class DALIGenericIterator:
         for p in self._pipes:
             p.build()
         self.batch_size = self._pipes[0].max_batch_size
-        self._shard_size = None
+        self._last_batch_padded = bool(last_batch_padded)
         if reader_name is not None:
             self._init_from_reader(last_batch_padded)
         self._first = None
@@ -45,7 +45,8 @@ class DALIGenericIterator:
                 self._first = None
 
     def _init_from_reader(self, last_batch_padded):
-        """plugin/base_iterator.py:_extract_from_reader_and_validate: the epoch length comes from the reader's meta data."""
+        """plugin/base_iterator.py:306-371 (_extract_from_reader_and_validate): the epoch length comes from the reader's meta
+        data; per-shard read-ahead counters keep the epochs aligned with the data when shards are uneven."""
         import math
         metas = [p.reader_meta(self._reader_name) for p in self._pipes]
         for k, what in (("epoch_size", "size value"), ("number_of_shards", "`num_shards` argument set"),
@@ -56,21 +57,17 @@ class DALIGenericIterator:
         self._size_no_pad, self._shards_num = n, shards
         self._last_batch_padded = metas[0]["pad_last_batch"]
         self._stick = metas[0]["stick_to_shard"]
-        self._shard_ids = [m["shard_id"] for m in metas]
+        self._shards_id = np.array([m["shard_id"] for m in metas], np.int64)
         if self._policy == LastBatchPolicy.DROP:
             self._size = n // shards
         elif self._last_batch_padded:
             self._size = metas[0]["epoch_size_padded"] // shards
         else:
             self._size = int(math.ceil(math.ceil(n / shards) / self.batch_size)) * self.batch_size
-        self._epoch = 0
-
-    def _shard_sizes_now(self):
-        res = []
-        for sid in self._shard_ids:
-            v = sid if self._stick else (sid + self._epoch) % self._shards_num
-            res.append(self._size_no_pad * (v + 1) // self._shards_num - self._size_no_pad * v // self._shards_num)
-        return res
+        ids = np.arange(shards, dtype=np.int64)
+        self._counter_per_gpu = np.zeros(shards, np.int64)          # where each shard starts inside this epoch (read-ahead)
+        self._shard_sizes_per_gpu = (ids + 1) * n // shards - ids * n // shards
+        self._shard_sizes_initial = self._shard_sizes_per_gpu.copy()
 
     def _fetch(self):
         torch = self._torch
@@ -88,6 +85,11 @@ class DALIGenericIterator:
                         d[name] = t.clone()
                 else:
                     d[name] = torch.from_numpy(np.stack([o.at(i) for i in range(len(o))]))
+            if p.device_id is not None:
+                # The copies above run on torch's current stream; the pipeline refills this slot on its own (non-blocking)
+                # stream at the next run().  Like the reference's feed_ndarray (plugin/pytorch/__init__.py:222-226, which
+                # copies on the torch stream and waits), block until the copies have left the slot before handing it back.
+                torch.cuda.current_stream(dev).synchronize()
             res.append(d)
             p.release_outputs()
         return res
@@ -95,60 +97,115 @@ class DALIGenericIterator:
     def __iter__(self):
         return self
 
-    def __next__(self):
-        if self._size > 0 and self._counter >= self._size:
-            if self._auto_reset:
-                self.reset()
-            raise StopIteration
-        if self._reader_name is not None and self._policy == LastBatchPolicy.DROP and \
-                any(self._counter + self.batch_size > s for s in self._shard_sizes_now()):
-            # the incomplete last batch is dropped: it is the next batch of the stream, so it is fetched and discarded
-            if self._counter < max(self._shard_sizes_now()):
-                try:
-                    if self._first is not None:
-                        self._first = None
-                    else:
-                        self._fetch()
-                except StopIteration:
-                    pass
-            self._counter = self._size if self._size > 0 else self._counter
-            if self._auto_reset:
-                self.reset()
-            raise StopIteration
+    def _end_iteration(self):
+        if self._auto_reset:
+            self.reset()
+        raise StopIteration
+
+    def _advance_and_check_drop_last(self, dry_run=False):
+        """plugin/base_iterator.py:440-466."""
+        counter, should_end = self._counter, False
+        if self._reader_name is not None:
+            counter += self.batch_size                              # per-GPU counter, as in the reference
+            if self._policy == LastBatchPolicy.DROP:
+                should_end = bool(np.any(self._counter_per_gpu + counter > self._shard_sizes_per_gpu))
+        else:
+            counter += self.batch_size * len(self._pipes)
+            if self._policy == LastBatchPolicy.DROP:
+                should_end = self._size > 0 and counter > self._size
+        if not dry_run:
+            self._counter = counter
+        return should_end
+
+    def _get(self):
         if self._first is not None:
             out, self._first = self._first, None
-        else:
-            try:
-                out = self._fetch()
-            except StopIteration:
-                if self._auto_reset:
-                    self.reset()
-                raise
+            return out
+        return self._fetch()
+
+    def __next__(self):
+        if self._size > 0 and self._counter >= self._size:
+            self._end_iteration()
+        try:
+            out = self._get()
+        except StopIteration:
+            if self._size < 0 and self._auto_reset:
+                self.reset()
+            raise
+        if self._advance_and_check_drop_last():
+            self._end_iteration()                                   # the incomplete last batch has been fetched and is dropped
         if self._reader_name is not None:
-            self._counter += self.batch_size                    # per-GPU counter, as in the reference
             if self._policy == LastBatchPolicy.PARTIAL:
-                for d, ssz in zip(out, self._shard_sizes_now()):
-                    left = self.batch_size - (self._counter - ssz)
-                    if left < self.batch_size:                  # the tail of this batch is padding / wrapped-around samples
-                        for k in list(d):
-                            d[k] = d[k][:max(left, 0)]
-        else:
-            self._counter += self.batch_size * len(self._pipes)
+                left = self.batch_size - (self._counter - self._shard_sizes_initial[self._shards_id])
+                if np.any(left < self.batch_size):                  # the tail of this batch is padding / wrapped-around samples
+                    out = [{k: v[:max(int(l), 0)] for k, v in d.items()} for d, l in zip(out, left)]
+        elif self._policy == LastBatchPolicy.PARTIAL and self._size > 0 and self._counter > self._size:
+            diff = len(self._pipes) * self.batch_size - (self._counter - self._size)
+            ngrab = int(np.ceil(diff / self.batch_size))
+            last = diff % self.batch_size or self.batch_size
+            out = out[:ngrab]
+            out[-1] = {k: v[:last] for k, v in out[-1].items()}
         return out
 
     next = __next__
 
     def reset(self):
-        self._counter = 0
+        """plugin/base_iterator.py:489-566: with FILL and a reader that wraps into the next epoch (pad_last_batch=False) every
+        GPU may have read ahead of its next shard; the counters start the next epoch from there and `size` is re-evaluated."""
+        import math
+        if self._policy == LastBatchPolicy.DROP:
+            should_end = self._advance_and_check_drop_last(dry_run=True)
+            already_ended = self._size > 0 and self._counter >= self._size
+            if should_end and not already_ended:
+                try:
+                    self._get()                                     # the incomplete batch still sits in the pipeline: drop it
+                except StopIteration:
+                    pass
+                self._advance_and_check_drop_last()
+        if not (self._counter >= self._size or self._size < 0):
+            import logging
+            logging.warning("DALI iterator does not support resetting while epoch is not finished. Ignoring...")
+            return
+        fill_wrap = self._policy == LastBatchPolicy.FILL and not getattr(self, "_last_batch_padded", False)
+        if fill_wrap:
+            if self._reader_name is not None:
+                self._counter -= int(self._counter_per_gpu.min())
+                self._counter_per_gpu = self._counter_per_gpu + self._counter - self._shard_sizes_per_gpu
+                self._counter = int(self._counter_per_gpu.min())
+            elif self._size > 0:
+                self._counter = self._counter % self._size
+            else:
+                self._counter = 0
+        else:
+            self._counter = 0
         if self._reader_name is not None:
-            self._epoch += 1
+            if not self._stick:
+                self._shards_id = (self._shards_id + 1) % self._shards_num
+            if fill_wrap:
+                if not self._stick:
+                    self._shard_sizes_per_gpu = np.roll(self._shard_sizes_per_gpu, 1)
+                read_next = self._shard_sizes_per_gpu - self._counter_per_gpu
+                self._size = int(math.ceil(int(read_next.max()) / self.batch_size)) * self.batch_size
+                if self._size == 0:                                 # read so far ahead that the next epoch is already done
+                    self._counter_per_gpu = np.zeros(self._shards_num, np.int64)
+                    self._counter = 0
+                    self._shard_sizes_per_gpu = np.roll(self._shard_sizes_per_gpu, 1)
+                    self._size = int(math.ceil(int(self._shard_sizes_per_gpu.max()) / self.batch_size)) * self.batch_size
         for p in self._pipes:
             p.reset()
 
     def __len__(self):
+        """plugin/base_iterator.py:600-616."""
         if self._size < 0:
             raise TypeError("size is unknown (-1)")
-        return (self._size + self.batch_size * len(self._pipes) - 1) // (self.batch_size * len(self._pipes))
+        import math
+        if self._reader_name is not None:
+            if self._policy != LastBatchPolicy.DROP:
+                return int(math.ceil(self._size / self.batch_size))
+            return self._size // self.batch_size
+        if self._policy != LastBatchPolicy.DROP:
+            return int(math.ceil(self._size / (len(self._pipes) * self.batch_size)))
+        return self._size // (len(self._pipes) * self.batch_size)
 
     @property
     def size(self):

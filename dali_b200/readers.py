@@ -78,7 +78,7 @@ class FileReader:
 
     def __init__(self, batch_size, file_root=None, file_list=None, files=None, labels=None, random_shuffle=False,
                  shuffle_after_epoch=False, initial_fill=1024, shard_id=0, num_shards=1, stick_to_shard=False, pad_last_batch=False,
-                 seed=-1):
+                 seed=-1, shuffle_after_epoch_seed=None):
         if not (0 <= shard_id < num_shards):
             raise ValueError("num_shards needs to be greater than shard_id")
         if random_shuffle and shuffle_after_epoch:
@@ -93,7 +93,12 @@ class FileReader:
                                f"number of shards: {num_shards}.")
         self.batch_size, self.shard_id, self.num_shards = batch_size, shard_id, num_shards
         self.random_shuffle, self.shuffle_after_epoch = random_shuffle, shuffle_after_epoch
-        self.stick_to_shard, self.pad_last_batch = stick_to_shard, pad_last_batch
+        # file_label_loader.h:134-138: shuffle_after_epoch implies stick_to_shard (every epoch is a new global permutation, the
+        # shard index stays) and reader_meta reports it; the permutation seed must be the SAME on every rank
+        # (`shuffle_after_epoch_seed`, default kDaliDataloaderSeed = 524287, file_label_loader.h:61-63,236-237) -- never the
+        # per-rank pipeline / operator seed, or the shards would stop partitioning the data set.
+        self.stick_to_shard, self.pad_last_batch = bool(stick_to_shard or shuffle_after_epoch), pad_last_batch
+        self.shuffle_after_epoch_seed = 524287 if shuffle_after_epoch_seed is None else int(shuffle_after_epoch_seed)
         self.initial_fill = max(1, int(initial_fill)) if random_shuffle else 1
         self.seed = 524287 if seed is None or seed < 0 else int(seed)
         self.rng = np.random.default_rng(self.seed)
@@ -119,7 +124,8 @@ class FileReader:
 
     def _reshuffle(self):
         if self.shuffle_after_epoch:
-            self.order = list(np.random.default_rng(self.seed + self.read_epoch).permutation(len(self.entries)))
+            seed = (self.shuffle_after_epoch_seed + ((self.read_epoch + 1) << 32)) & 0xFFFFFFFFFFFFFFFF      # Reset(): ++epoch first
+            self.order = list(np.random.default_rng(seed).permutation(len(self.entries)))
 
     def _shard_bounds(self, shard):
         n = len(self.entries)

@@ -79,12 +79,26 @@ int dalib200JpegPlanDestroy(dalib200JpegPlan *plan);
 int dalib200JpegPlanSetup(dalib200JpegPlan *plan, int n, const uint8_t *const *streams, const size_t *lengths,
                           int output_type /* DALIB200_RGB | BGR | GRAY */, int fancy_upsampling);
 int dalib200JpegPlanGetInfo(const dalib200JpegPlan *plan, int sample, dalib200JpegInfo *info);
+/* Full argument surface of the decoder operators (decoders.image / image_crop / image_random_crop / image_slice):
+ *   output_type          DALIB200_RGB | BGR | GRAY | YCbCr   (decoder_schema.cc:21-60; YCbCr = BT.601 of the decoded RGB,
+ *                        dali/operators/imgcodec/util/convert.h:150-160)
+ *   dtype                DALIB200_UINT8 | DALIB200_FLOAT     (ConvertSatNorm: u8 * (1 / 255), convert.h:118-128)
+ *   adjust_orientation   apply the EXIF orientation (image_decoder.h:211,678-679,806)
+ *   rois[i]              region of interest of sample i in OUTPUT (oriented) pixel coordinates, [x0, x1) x [y0, y1)
+ *                        (imgcodec.h:26-44, image_decoder.h:681-716); only the MCUs under the region are transformed.
+ * The result equals the full decode followed by orientation, crop and conversion, bit for bit. */
+typedef struct { int32_t output_type, fancy_upsampling, dtype, adjust_orientation; } dalib200JpegParams;
+typedef struct { int32_t use_roi, x0, y0, x1, y1; } dalib200JpegRoi;
+int dalib200JpegPlanSetupEx(dalib200JpegPlan *plan, int n, const uint8_t *const *streams, const size_t *lengths,
+                            const dalib200JpegParams *params, const dalib200JpegRoi *rois_or_null);
+/* (H, W, C) of the sample the launch will write (after orientation and region of interest) */
+int dalib200JpegPlanGetOutputShape(const dalib200JpegPlan *plan, int sample, int32_t *hwc);
 /* Bytes of packed entropy-coded data + tables staged for the batch (the H2D payload). */
 size_t dalib200JpegPlanStagedBytes(const dalib200JpegPlan *plan);
 /* Pinned staging + H2D copy of the batch (async on stream, host work overlapped with the transfer).  Split from Launch
  * so that a caller can time the device-resident decode separately from the transfer. */
 int dalib200JpegUpload(dalib200JpegPlan *plan, dalib200Stream_t stream);
-/* Enqueues the decode of the uploaded batch; out_ptrs[i] -> device buffer H*W*C u8 (HWC). */
+/* Enqueues the decode of the uploaded batch; out_ptrs[i] -> device buffer H*W*C of dtype (HWC, see ...GetOutputShape). */
 int dalib200JpegLaunch(dalib200JpegPlan *plan, void *const *out_ptrs, dalib200Stream_t stream);
 /* Per-sample device status after a launch (0 ok, 1 = entropy-coded data ended early).  Synchronises. */
 int dalib200JpegGetStatus(dalib200JpegPlan *plan, int32_t *status_out);

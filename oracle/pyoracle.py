@@ -363,3 +363,56 @@ def mel_weights(nbin, nfilter=128, sample_rate=44100.0, freq_low=0.0, freq_high=
     lib().oracle_mel_weights(_p(W), nbin, nfilter, C.c_float(sample_rate), C.c_float(freq_low), C.c_float(freq_high),
                              int(mel_formula == "htk"), int(bool(normalize)))
     return W
+
+
+# ------------------------------------------------------------------------------------------- decoder post-conversion, random crops
+def exif_transform(img, orientation):
+    """The displayed (upright) image of a stored image with EXIF orientation 1..8 (TIFF/EXIF tag 0x0112)."""
+    o = int(orientation)
+    if o == 2:
+        return img[:, ::-1]
+    if o == 3:
+        return img[::-1, ::-1]
+    if o == 4:
+        return img[::-1]
+    if o == 5:
+        return np.swapaxes(img, 0, 1)
+    if o == 6:
+        return np.swapaxes(img, 0, 1)[:, ::-1]
+    if o == 7:
+        return np.swapaxes(img, 0, 1)[::-1, ::-1]
+    if o == 8:
+        return np.swapaxes(img, 0, 1)[::-1]
+    return img
+
+
+def with_exif_orientation(jpeg_bytes, orientation):
+    """Inserts a minimal APP1 / Exif segment carrying the orientation tag behind SOI."""
+    tiff = b"II*\x00" + (8).to_bytes(4, "little") + (1).to_bytes(2, "little") + \
+        (0x0112).to_bytes(2, "little") + (3).to_bytes(2, "little") + (1).to_bytes(4, "little") + int(orientation).to_bytes(2, "little") + b"\x00\x00" + \
+        (0).to_bytes(4, "little")
+    payload = b"Exif\x00\x00" + tiff
+    seg = b"\xff\xe1" + (len(payload) + 2).to_bytes(2, "big") + payload
+    b = bytes(jpeg_bytes)
+    assert b[:2] == b"\xff\xd8"
+    return b[:2] + seg + b[2:]
+
+
+def ref_decoder_convert(img, out_type, out_float):
+    """The reference's post-decode conversion (dali/operators/imgcodec/util/convert.h ConvertPixel functors) of a decoded RGB / GRAY
+    u8 image: out_type IT_RGB / IT_BGR / IT_GRAY / IT_YCBCR, u8 or f32."""
+    a = np.ascontiguousarray(img)
+    in_c = 1 if a.ndim == 2 or a.shape[2] == 1 else 3
+    npix = a.shape[0] * a.shape[1]
+    oc = 1 if out_type == IT_GRAY else 3
+    out = np.empty((a.shape[0], a.shape[1], oc), np.float32 if out_float else np.uint8)
+    ref().ref_decoder_convert(_p(a), C.c_size_t(npix), in_c, int(out_type), int(bool(out_float)), _p(out))
+    return out
+
+
+def ref_random_crop(seed, sample_idx, H, W, aspect=(3 / 4, 4 / 3), area=(0.08, 1.0), num_attempts=10, ncalls=1):
+    """[(anchor_y, anchor_x, h, w)] from the reference's RandomCropGenerator with RandomCropAttr's per-sample Philox state."""
+    w = (C.c_int * (4 * ncalls))()
+    ref().ref_random_crop(C.c_int64(seed), int(sample_idx), int(H), int(W), C.c_float(aspect[0]), C.c_float(aspect[1]),
+                          C.c_float(area[0]), C.c_float(area[1]), int(num_attempts), int(ncalls), w)
+    return [tuple(w[4 * k:4 * k + 4]) for k in range(ncalls)]

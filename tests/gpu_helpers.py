@@ -117,6 +117,36 @@ def jpeg_decode(streams, output_type=capi.RGB, fancy=True, plan=None, want_coefs
     return res, list(status)
 
 
+def jpeg_decode_ex(streams, output_type=capi.RGB, fancy=True, dtype=capi.UINT8, adjust_orientation=True, rois=None, plan=None):
+    """dalib200JpegPlanSetupEx: rois[i] = None | (x0, y0, x1, y1) in output (oriented) coordinates."""
+    torch = _torch()
+    n = len(streams)
+    bufs = [np.frombuffer(bytes(s), np.uint8) for s in streams]
+    ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    lens = (C.c_size_t * n)(*[b.size for b in bufs])
+    plan = plan or capi.Plan("Jpeg", max(n, 1))
+    prm = capi.JpegParams(output_type, int(fancy), dtype, int(adjust_orientation))
+    cr = None
+    if rois is not None:
+        cr = (capi.JpegRoi * n)()
+        for i, r in enumerate(rois):
+            if r is not None:
+                cr[i].use_roi = 1
+                cr[i].x0, cr[i].y0, cr[i].x1, cr[i].y1 = [int(v) for v in r]
+    capi.check(capi.lib().dalib200JpegPlanSetupEx(plan.handle, n, ptrs, lens, C.byref(prm), cr))
+    outs = []
+    for i in range(n):
+        hwc = (C.c_int32 * 3)()
+        capi.check(capi.lib().dalib200JpegPlanGetOutputShape(plan.handle, i, hwc))
+        outs.append(torch.empty(tuple(hwc), dtype=torch.uint8 if dtype == capi.UINT8 else torch.float32, device="cuda"))
+    capi.check(capi.lib().dalib200JpegUpload(plan.handle, capi.stream_handle()))
+    capi.check(capi.lib().dalib200JpegLaunch(plan.handle, capi.ptr_array(outs), capi.stream_handle()))
+    torch.cuda.synchronize()
+    status = (C.c_int32 * n)()
+    capi.check(capi.lib().dalib200JpegGetStatus(plan.handle, status))
+    return [o.cpu().numpy() for o in outs], list(status)
+
+
 def jpeg_coefs(plan, sample, count):
     out = np.empty(count, np.int16)
     capi.check(capi.lib().dalib200JpegDebugGetCoefficients(plan.handle, sample, out.ctypes.data_as(C.c_void_p), C.c_size_t(count)))

@@ -176,3 +176,91 @@ def test_decode_is_deterministic_over_repeated_batches():
         assert status == [0] * 24
         for i, (o, w) in enumerate(zip(outs, want)):
             assert np.array_equal(o, w), (rep, i)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# decoder variants: region of interest, EXIF orientation, output_type / dtype conversion
+def _variant_streams():
+    import cv2
+    import gpu_helpers as g
+    return [_enc(g.synth_image(203, 310, 11), 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420),
+            _enc(g.synth_image(97, 131, 12), 75, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444),
+            _enc(g.synth_image(160, 96, 13), 85, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422),
+            _enc(g.synth_image(480, 640, 14), 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, rst=8),
+            _enc(g.synth_image(120, 200, 15)[..., 0], 90)]                                        # grayscale JPEG
+
+
+def test_roi_decode_equals_crop_of_full_decode():
+    import gpu_helpers as g
+    streams = _variant_streams()
+    full = [po.jpeg_decode(s) for s in streams]
+    rng = np.random.default_rng(5)
+    for rep in range(6):
+        rois = []
+        for f in full:
+            H, W = f.shape[:2]
+            if rep == 0:
+                rois.append((0, 0, W, H))                                 # whole image through the ROI path
+            elif rep == 1:
+                rois.append((8, 3, min(W, 8 + 64), min(H, 3 + 40)))       # 8-aligned left edge: direct window
+            else:
+                x0, y0 = int(rng.integers(0, W - 1)), int(rng.integers(0, H - 1))
+                rois.append((x0, y0, int(rng.integers(x0 + 1, W + 1)), int(rng.integers(y0 + 1, H + 1))))
+        for ot in (capi.RGB, capi.BGR, capi.GRAY):
+            outs, status = g.jpeg_decode_ex(streams, output_type=ot, rois=rois)
+            assert status == [0] * len(streams)
+            for i, (f, r) in enumerate(zip(full, rois)):
+                want = f[r[1]:r[3], r[0]:r[2]]
+                if ot == capi.BGR:
+                    want = want[..., ::-1]
+                elif ot == capi.GRAY:
+                    want = g.jpeg_decode([streams[i]], output_type=capi.GRAY)[0][0][r[1]:r[3], r[0]:r[2]]
+                assert np.array_equal(outs[i], want), f"rep {rep} type {ot} sample {i} roi {r}"
+
+
+def test_exif_orientation_matches_libjpeg_consumers():
+    import cv2
+    import gpu_helpers as g
+    base = _enc(g.synth_image(123, 200, 21), 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420)
+    dec = po.jpeg_decode(base)
+    streams = [po.with_exif_orientation(base, o) for o in range(1, 9)]
+    outs, status = g.jpeg_decode_ex(streams, adjust_orientation=True)
+    assert status == [0] * 8
+    for o in range(1, 9):
+        want = po.exif_transform(dec, o)
+        assert np.array_equal(outs[o - 1], want), f"orientation {o}"
+        cv = cv2.imdecode(np.frombuffer(streams[o - 1], np.uint8), cv2.IMREAD_COLOR)[..., ::-1]      # cv2 applies the EXIF tag
+        assert np.array_equal(outs[o - 1], cv), f"orientation {o} vs cv2"
+    raw, _ = g.jpeg_decode_ex(streams, adjust_orientation=False)
+    for o in range(8):
+        assert np.array_equal(raw[o], dec)
+    # region of interest in oriented coordinates
+    rois = []
+    for o in range(1, 9):
+        OH, OW = (200, 123) if o >= 5 else (123, 200)
+        rois.append((5, 7, OW - 11, OH - 3))
+    outs, _ = g.jpeg_decode_ex(streams, adjust_orientation=True, rois=rois)
+    for o in range(1, 9):
+        r = rois[o - 1]
+        assert np.array_equal(outs[o - 1], po.exif_transform(dec, o)[r[1]:r[3], r[0]:r[2]]), f"orientation {o} + roi"
+
+
+@pytest.mark.skipif(not po.have_ref(), reason="needs oracle/_ref")
+def test_output_type_and_dtype_conversion_match_reference_convert():
+    import gpu_helpers as g
+    streams = _variant_streams()
+    full = [po.jpeg_decode(s) for s in streams]
+    gray = [g.jpeg_decode([s], output_type=capi.GRAY)[0][0] for s in streams]
+    for ot, it in ((capi.RGB, po.IT_RGB), (capi.BGR, po.IT_BGR), (capi.YCbCr, po.IT_YCBCR), (capi.GRAY, po.IT_GRAY)):
+        for dt, fl in ((capi.UINT8, False), (capi.FLOAT, True)):
+            outs, status = g.jpeg_decode_ex(streams, output_type=ot, dtype=dt)
+            assert status == [0] * len(streams)
+            for i in range(len(streams)):
+                src = gray[i] if ot == capi.GRAY else full[i]           # GRAY is decoded as the Y plane (image_decoder.h:537-540)
+                want = po.ref_decoder_convert(src, it, fl)
+                assert outs[i].dtype == want.dtype and np.array_equal(outs[i], want), f"type {ot} dtype {dt} sample {i}"
+    # everything at once: orientation + ROI + YCbCr float
+    s6 = po.with_exif_orientation(streams[0], 6)
+    out, _ = g.jpeg_decode_ex([s6], output_type=capi.YCbCr, dtype=capi.FLOAT, rois=[(3, 9, 150, 260)])
+    want = po.ref_decoder_convert(np.ascontiguousarray(po.exif_transform(full[0], 6)[9:260, 3:150]), po.IT_YCBCR, True)
+    assert np.array_equal(out[0], want)

@@ -185,3 +185,47 @@ def test_operator_errors_surface_with_operator_name():
     q.build()
     with pytest.raises(backend.BackendError, match="out of bounds"):
         q.run()
+
+
+def test_decoder_crop_family_and_random_resized_crop():
+    """fn.decoders.image_crop / image_random_crop / image_slice decode only the blocks under the window and must equal the crop of
+    the full decode; the random windows are the reference generator's (oracle/_ref RandomCropGenerator, same seed);
+    fn.random_resized_crop = resize with the window as ROI (random_resized_crop.h:112-120)."""
+    from dali_b200 import fn, types, pipeline_def
+    streams = _jpegs(3, 300, 400, 70) + _jpegs(2, 333, 251, 80)
+    n = len(streams)
+    anchors = [np.array([0.1 + 0.05 * i, 0.2], np.float32) for i in range(n)]      # (x, y), normalised ("WH" axes)
+    shapes = [np.array([0.5, 0.6 - 0.05 * i], np.float32) for i in range(n)]
+
+    @pipeline_def(batch_size=n, num_threads=2, device_id=0)
+    def pipe():
+        jpegs = fn.external_source(source=lambda i: streams)
+        anc = fn.external_source(source=lambda i: anchors)
+        shp = fn.external_source(source=lambda i: shapes)
+        a = fn.decoders.image_crop(jpegs, device="mixed", crop=(160, 200), crop_pos_x=0.3, crop_pos_y=0.8)
+        b = fn.decoders.image_random_crop(jpegs, device="mixed", seed=1234, random_area=[0.1, 0.9])
+        c = fn.decoders.image_slice(jpegs, anc, shp, device="mixed")
+        d = fn.decoders.image_slice(jpegs, device="mixed", start=[16, 30], shape=[100, 64], axes=[0, 1])
+        e = fn.random_resized_crop(fn.decoders.image(jpegs, device="mixed"), size=[96, 128], seed=77)
+        return a, b, c, d, e
+    p = pipe()
+    p.build()
+    for it in range(2):
+        a, b, c, d, e = [o.as_cpu() for o in p.run()]
+        for i, s in enumerate(streams):
+            full = po.jpeg_decode(s.tobytes())
+            H, W = full.shape[:2]
+            y0, x0 = po.crop_anchor(0.8, H, 160), po.crop_anchor(0.3, W, 200)
+            assert np.array_equal(a[i], full[y0:y0 + 160, x0:x0 + 200]), (it, i)
+            if po.have_ref():
+                wy, wx, wh, ww = po.ref_random_crop(1234, i, H, W, area=(0.1, 0.9), ncalls=it + 1)[it]
+                assert np.array_equal(b[i], full[wy:wy + wh, wx:wx + ww]), (it, i)
+                ry, rx, rh, rw = po.ref_random_crop(77, i, H, W, ncalls=it + 1)[it]
+                want = po.ref_resample(full, (96, 128), roi=((float(ry), float(rx)), (float(ry + rh), float(rx + rw))))
+                assert np.array_equal(e[i], want), (it, i)
+            ax, ay = float(anchors[i][0]), float(anchors[i][1])
+            sx, sy = float(shapes[i][0]), float(shapes[i][1])
+            bx, ex = int(round(ax * W)), int(round((ax + sx) * W))
+            by, ey = int(round(ay * H)), int(round((ay + sy) * H))
+            assert np.array_equal(c[i], full[by:ey, bx:ex]), (it, i)
+            assert np.array_equal(d[i], full[16:116, 30:94]), (it, i)

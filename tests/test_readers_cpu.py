@@ -120,3 +120,34 @@ def test_pipeline_reader_meta_and_iterator_epochs(tree):
     assert [b[0]["data"][:, 0].tolist() for b in it] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 0, 1]]
     with pytest.raises(ValueError, match="size should not be set"):
         DALIGenericIterator(pipe, ["data", "label"], size=10, reader_name="Reader")
+
+
+def test_iterator_fill_wraparound_keeps_epochs_aligned(tree):
+    """plugin/base_iterator.py reset(): with FILL and pad_last_batch=False the reader runs on into the next epoch; the
+    read-ahead is carried into the next epoch's counter and `size` is re-evaluated, so the epochs do not drift."""
+    @pipeline_def(batch_size=4, num_threads=1, device_id=None, prefetch_queue_depth=2)
+    def p():
+        data, label = fn.readers.file(file_root=tree, name="Reader")
+        return data, label
+    it = DALIGenericIterator(p(), ["data", "label"], reader_name="Reader", last_batch_policy=LastBatchPolicy.FILL, auto_reset=True)
+    e1 = [b[0]["data"][:, 0].tolist() for b in it]
+    assert e1 == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 0, 1]] and len(e1) == 3
+    assert it.size == 8 and len(it) == 2                               # 2 samples of the next epoch were already consumed
+    e2 = [b[0]["data"][:, 0].tolist() for b in it]
+    assert e2 == [[2, 3, 4, 5], [6, 7, 8, 9]]
+    assert it.size == 12
+    e3 = [b[0]["data"][:, 0].tolist() for b in it]
+    assert e3 == e1
+
+
+def test_shuffle_after_epoch_is_rank_independent_and_sticks_to_shard(tree):
+    """file_label_loader.h:61-63,134-138,229-239: one global permutation per epoch, identical on every rank whatever the
+    operator seed; the shard index does not rotate and reader_meta says so."""
+    r0 = FileReader(5, tree, shuffle_after_epoch=True, shard_id=0, num_shards=2, seed=11)
+    r1 = FileReader(5, tree, shuffle_after_epoch=True, shard_id=1, num_shards=2, seed=12)
+    assert r0.meta()["stick_to_shard"] is True and r1.meta()["stick_to_shard"] is True
+    for epoch in range(3):
+        a, b = _ids(r0, 1)[0], _ids(r1, 1)[0]
+        assert sorted(a + b) == list(range(10)), epoch                   # the two shards partition the data set in every epoch
+    other = FileReader(5, tree, shuffle_after_epoch=True, shard_id=0, num_shards=2, shuffle_after_epoch_seed=99)
+    assert _ids(other, 1) != _ids(FileReader(5, tree, shuffle_after_epoch=True, shard_id=0, num_shards=2), 1)

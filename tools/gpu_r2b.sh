@@ -1,16 +1,11 @@
 #!/bin/bash
-# quick GPU check: parity tests then the bench line ($1 = pytest -k filter, optional)
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q ${1:+-k "$1"} 2>&1 | tail -25 | tee gpurun_out/pytest.log
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -5 gpurun_out/bench.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/pytest.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err
 python - <<'PY'
 import json
 d = json.load(open('gpurun_out/bench.json'))
 print('value', round(d['value']), 'ms', round(d['ms_per_step'], 3), 'e2e', round(d['e2e']['value']), round(d['e2e']['ms_per_step'], 3), 'parity_mismatch', (d.get('cpu_baseline') or {}).get('parity_mismatching_elements'))
 print({k: round(v['ms_per_step'], 3) for k, v in d['kernels'].items()})
 print('cpu', {k: v for k, v in (d.get('cpu_baseline') or {}).items() if k in ('value', 'cores', 'workers', 'single_core_value')})
-s = d.get('secondary') or {}
-for k, v in s.items():
-    if isinstance(v, dict): print(k, round(v.get('value', 0)), v.get('kernels_ms'), v.get('parity_mismatching_elements'))
-    else: print(k, v)
 PY

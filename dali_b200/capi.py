@@ -31,6 +31,9 @@ EXPORTS = [
     "dalib200PointwiseLaunch", "dalib200ColorTwistMatrix",
     "dalib200SpectrogramPlanCreate", "dalib200SpectrogramPlanDestroy", "dalib200SpectrogramPlanSetup",
     "dalib200SpectrogramNumWindows", "dalib200SpectrogramLaunch", "dalib200HannWindow",
+    "dalib200SignalPlanCreate", "dalib200SignalPlanDestroy", "dalib200ToDecibelsSetup", "dalib200MfccSetup", "dalib200SignalOutputRows",
+    "dalib200NormalizeSetup", "dalib200SignalLaunch",
+    "dalib200GenericPlanCreate", "dalib200GenericPlanDestroy", "dalib200MultiplyAddSetup", "dalib200WindowCopySetup", "dalib200GenericLaunch",
     "dalib200MelPlanCreate", "dalib200MelPlanDestroy", "dalib200MelPlanSetup", "dalib200MelLaunch", "dalib200MelPlanSetTensorCores",
 ]
 
@@ -81,6 +84,18 @@ class SpectrogramArgs(C.Structure):
 class MelArgs(C.Structure):
     _fields_ = [("nfilter", C.c_int32), ("sample_rate", C.c_float), ("freq_low", C.c_float), ("freq_high", C.c_float),
                 ("htk", C.c_int32), ("normalize", C.c_int32)]
+
+
+class ToDecibelsArgs(C.Structure):
+    _fields_ = [("multiplier", C.c_float), ("reference", C.c_float), ("cutoff_db", C.c_float), ("ref_max", C.c_int32)]
+
+
+class MfccArgs(C.Structure):
+    _fields_ = [("n_mfcc", C.c_int32), ("dct_type", C.c_int32), ("normalize", C.c_int32), ("lifter", C.c_float)]
+
+
+class NormalizeArgs(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("ddof", C.c_int32), ("scale", C.c_float), ("shift", C.c_float), ("epsilon", C.c_float)]
 
 
 class DaliB200Error(RuntimeError):

@@ -1,0 +1,360 @@
+// dali_b200/csrc/audio_tail.cu -- the audio tail behind Spectrogram / MelFilterBank: ToDecibels, MFCC
+// (DCT + liftering) and Normalize for sm_100a.
+//
+//   ToDecibels   dali/kernels/signal/decibel/to_decibels_cpu.cc:47-72 + decibel_calculator.h:25-56:
+//                out = (mul * log10(2)) * log2(max(min_ratio, in * (1 / s_ref))), s_ref = per-sample maximum when no
+//                `reference` is given (0 -> 1).  log2f on the device vs glibc's on the host: <= 2 ulp of the logarithm
+//                (stated tolerance of the tests: 1e-5 dB absolute + 1e-6 relative).
+//   MFCC         dali/kernels/signal/dct/dct_cpu.cc:76-115 (out[k] = sum_n in[n] * table[k][n], n ascending, mul and add rounded
+//                separately), cosine tables table.h:27-112 (double on the host), liftering mfcc.h:36-41, mfcc.cc:52-72.
+//                Same order, same tables -> bit-exact.
+//   Normalize    dali/operators/math/normalize/normalize.cc: out = (in - mean) * scale / sqrt(var + eps) + shift over the reduced
+//                axes of a 2-D sample; the mean / variance sums are tree reductions here (tolerance: 1e-5 relative).
+// Every op is one launch per batch over a per-sample descriptor list (one H2D descriptor copy per launch).
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace dalib200 {
+
+enum { SIG_NONE = 0, SIG_TODB = 1, SIG_MFCC = 2, SIG_NORMALIZE = 3 };
+
+struct SigDesc {
+  const float *in; float *out;
+  int64_t n;                 // elements
+  int64_t rows, cols;        // 2-D view (MFCC: rows = nfeat, cols = frames; Normalize)
+  int64_t first_item;
+};
+
+__device__ __forceinline__ int find_sig(const SigDesc *d, int n, int64_t v) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (d[mid].first_item <= v) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+
+// ---- ToDecibels
+constexpr int kDbItem = 4096;       // elements per work item
+
+__global__ void __launch_bounds__(256) todb_max_kernel(const SigDesc *__restrict__ descs, int n, int64_t total_items, uint32_t *__restrict__ smax) {
+  __shared__ float wmax[8];
+  for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const int s = find_sig(descs, n, item);
+    const SigDesc &d = descs[s];
+    const int64_t e0 = (item - d.first_item) * kDbItem, e1 = min(d.n, e0 + kDbItem);
+    float m = 0.0f;                                    // s_ref starts at 0: only values above it count
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) { const float v = __ldg(d.in + e); if (v > m) m = v; }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; w++) m = fmaxf(m, wmax[w]);
+      atomicMax(smax + s, __float_as_uint(m));          // m >= 0: the integer order of the bit patterns is the float order
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) todb_kernel(const SigDesc *__restrict__ descs, int n, int64_t total_items, float mul_log2, float s_ref,
+                                                   float min_ratio, const uint32_t *__restrict__ smax) {
+  for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const int s = find_sig(descs, n, item);
+    const SigDesc &d = descs[s];
+    float ref = s_ref;
+    if (smax) { ref = __uint_as_float(smax[s]); if (ref == 0.0f) ref = 1.0f; }
+    const float inv = ref == 1.0f ? 1.0f : __fdiv_rn(1.0f, ref);
+    const int64_t e0 = (item - d.first_item) * kDbItem, e1 = min(d.n, e0 + kDbItem);
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x)
+      d.out[e] = mul_rn(mul_log2, log2f(fmaxf(min_ratio, mul_rn(__ldg(d.in + e), inv))));
+  }
+}
+
+// ---- MFCC: one thread = one frame (column) x up to 32 coefficients; the table row of a coefficient is read from shared memory
+constexpr int kMfccK = 32;
+__global__ void __launch_bounds__(128) mfcc_kernel(const SigDesc *__restrict__ descs, int n, int64_t total_items, int nfeat, int ndct,
+                                                   const float *__restrict__ table, const float *__restrict__ lifter) {
+  extern __shared__ float s_tab[];                      // [ndct][nfeat]
+  for (int i = threadIdx.x; i < ndct * nfeat; i += blockDim.x) s_tab[i] = table[i];
+  __syncthreads();
+  for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const int s = find_sig(descs, n, item);
+    const SigDesc &d = descs[s];
+    const int64_t t = (item - d.first_item) * blockDim.x + threadIdx.x;
+    if (t >= d.cols) continue;
+    for (int k0 = 0; k0 < ndct; k0 += kMfccK) {
+      float acc[kMfccK];
+#pragma unroll
+      for (int k = 0; k < kMfccK; k++) acc[k] = 0.0f;
+      for (int f = 0; f < nfeat; f++) {
+        const float v = __ldg(d.in + (int64_t)f * d.cols + t);
+#pragma unroll
+        for (int k = 0; k < kMfccK; k++)
+          if (k0 + k < ndct) acc[k] = add_rn(acc[k], mul_rn(v, s_tab[(k0 + k) * nfeat + f]));
+      }
+#pragma unroll
+      for (int k = 0; k < kMfccK; k++)
+        if (k0 + k < ndct) d.out[(int64_t)(k0 + k) * d.cols + t] = lifter ? mul_rn(lifter[k0 + k], acc[k]) : acc[k];
+    }
+  }
+}
+
+// ---- Normalize (2-D samples): mode 0 = over both axes (one mean / stddev per sample), 1 = over axis 1 (per row), 2 = over axis 0
+// (per column).  One CTA per (sample, group).
+__device__ __forceinline__ float block_sum(float v, float *sh) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.0f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) r += sh[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(256) normalize_kernel(const SigDesc *__restrict__ descs, int n, int64_t total_items, int mode, float scale,
+                                                        float shift, float eps, int ddof) {
+  __shared__ float sh[8];
+  for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const int s = find_sig(descs, n, item);
+    const SigDesc &d = descs[s];
+    const int64_t g = item - d.first_item;               // group inside the sample
+    int64_t cnt, stride, base;
+    if (mode == 0) { cnt = d.rows * d.cols; stride = 1; base = 0; }
+    else if (mode == 1) { cnt = d.cols; stride = 1; base = g * d.cols; }
+    else { cnt = d.rows; stride = d.cols; base = g; }
+    float sum = 0.0f;
+    for (int64_t e = threadIdx.x; e < cnt; e += blockDim.x) sum += __ldg(d.in + base + e * stride);
+    const float mean = block_sum(sum, sh) / (float)cnt;
+    float sq = 0.0f;
+    for (int64_t e = threadIdx.x; e < cnt; e += blockDim.x) { const float x = __ldg(d.in + base + e * stride) - mean; sq += x * x; }
+    const float var = block_sum(sq, sh) / (float)max((int64_t)1, cnt - ddof);
+    const float sd = sqrtf(var + eps);
+    const float mul = sd != 0.0f ? scale / sd : 0.0f;
+    for (int64_t e = threadIdx.x; e < cnt; e += blockDim.x) {
+      const int64_t i = base + e * stride;
+      d.out[i] = (__ldg(d.in + i) - mean) * mul + shift;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace dalib200
+
+using namespace dalib200;  // NOLINT
+
+struct dalib200SignalPlan {
+  int max_batch = 0, n = 0, kind = SIG_NONE;
+  std::vector<SigDesc> descs;
+  int64_t total_items = 0;
+  DescArena arena;
+  cudaEvent_t uploaded = nullptr;
+  bool pending = false;
+  // ToDecibels
+  float mul_log2 = 0, s_ref = 1, min_ratio = 1e-8f; bool ref_max = false;
+  uint32_t *d_max = nullptr; size_t d_max_cap = 0;
+  // MFCC
+  int nfeat = 0, ndct = 0; bool has_lifter = false;
+  float *d_table = nullptr; size_t d_table_cap = 0;     // [ndct * nfeat] + [ndct] lifter
+  std::vector<float> h_table;
+  bool table_dirty = true;
+  // Normalize
+  int mode = 0, ddof = 0; float scale = 1, shift = 0, eps = 0;
+};
+
+namespace {
+int GrowF(float *&p, size_t &cap, size_t need) {
+  if (need <= cap) return DALIB200_SUCCESS;
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+  DB_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), need * sizeof(float)));
+  cap = need;
+  return DALIB200_SUCCESS;
+}
+
+// dali/kernels/signal/dct/table.h:27-112
+void FillCosineTable(float *table, int64_t n, int ndct, int type, bool normalize) {
+  int64_t idx = 0;
+  if (type == 1) {
+    const double phase_mul = M_PI / (n - 1);
+    for (int64_t k = 0; k < ndct; k++) {
+      table[idx++] = 0.5f;
+      for (int64_t i = 1; i < n - 1; i++) table[idx++] = static_cast<float>(std::cos(phase_mul * k * i));
+      table[idx++] = k % 2 == 0 ? 0.5f : -0.5f;
+    }
+  } else if (type == 2) {
+    const double phase_mul = M_PI / n;
+    double f0 = 1, fi = 1;
+    if (normalize) { fi = std::sqrt(2.0 / n); f0 = 1.0 / std::sqrt(static_cast<double>(n)); }
+    for (int64_t k = 0; k < ndct; k++) {
+      const double nf = k == 0 ? f0 : fi;
+      for (int64_t i = 0; i < n; i++) table[idx++] = static_cast<float>(nf * std::cos(phase_mul * (i + 0.5) * k));
+    }
+  } else if (type == 3) {
+    const double phase_mul = M_PI / n;
+    double f0 = 0.5, fi = 1;
+    if (normalize) { fi = std::sqrt(2.0 / n); f0 = 1.0 / std::sqrt(static_cast<double>(n)); }
+    for (int64_t k = 0; k < ndct; k++) {
+      table[idx++] = static_cast<float>(f0);
+      for (int64_t i = 1; i < n; i++) table[idx++] = static_cast<float>(fi * std::cos(phase_mul * i * (k + 0.5)));
+    }
+  } else {
+    const double phase_mul = M_PI / n;
+    const double f = normalize ? std::sqrt(2.0 / n) : 1.0;
+    for (int64_t k = 0; k < ndct; k++)
+      for (int64_t i = 0; i < n; i++) table[idx++] = static_cast<float>(f * std::cos(phase_mul * (i + 0.5) * (k + 0.5)));
+  }
+}
+
+int UploadDescs(dalib200SignalPlan *p) {
+  if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
+  int rc = p->arena.Reserve(sizeof(SigDesc) * std::max(1, p->n));
+  return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int dalib200SignalPlanCreate(dalib200SignalPlan **plan, int max_batch) {
+  DB_CHECK_ARG(plan && max_batch > 0, "SignalPlanCreate: bad arguments");
+  auto *p = new dalib200SignalPlan();
+  p->max_batch = max_batch;
+  if (cudaEventCreateWithFlags(&p->uploaded, cudaEventDisableTiming) != cudaSuccess) {
+    SetLastError("SignalPlanCreate: cudaEventCreate failed"); delete p; return DALIB200_ERROR_CUDA;
+  }
+  *plan = p;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200SignalPlanDestroy(dalib200SignalPlan *p) {
+  if (!p) return DALIB200_SUCCESS;
+  if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
+  p->arena.Free();
+  if (p->d_max) cudaFree(p->d_max);
+  if (p->d_table) cudaFree(p->d_table);
+  delete p;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200ToDecibelsSetup(dalib200SignalPlan *p, const dalib200ToDecibelsArgs *a, int n, const int64_t *volumes) {
+  DB_CHECK_ARG(p && a && (n == 0 || volumes) && n >= 0 && n <= p->max_batch, "ToDecibelsSetup: bad arguments");
+  DB_CHECK_ARG(a->ref_max || a->reference != 0.0f, "`reference` argument can't be zero");
+  p->kind = SIG_TODB; p->n = n;
+  // to_decibels_op.h:41-50 and decibel_calculator.h:29-33 (float arithmetic throughout)
+  p->mul_log2 = a->multiplier * 0.3010299956639812f;
+  p->ref_max = a->ref_max != 0;
+  p->s_ref = a->ref_max ? 1.0f : a->reference;
+  p->min_ratio = std::pow(10.0f, a->cutoff_db / a->multiplier);
+  if (p->min_ratio == 0) p->min_ratio = std::nextafter(0.0f, 1.0f);
+  p->descs.assign(n, SigDesc());
+  int64_t items = 0;
+  for (int i = 0; i < n; i++) {
+    DB_CHECK_ARG(volumes[i] >= 0, "ToDecibelsSetup: negative volume");
+    p->descs[i].n = volumes[i]; p->descs[i].first_item = items;
+    items += (volumes[i] + kDbItem - 1) / kDbItem;
+  }
+  p->total_items = items;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200MfccSetup(dalib200SignalPlan *p, const dalib200MfccArgs *a, int n, const int64_t *shapes) {
+  DB_CHECK_ARG(p && a && (n == 0 || shapes) && n >= 0 && n <= p->max_batch, "MfccSetup: bad arguments");
+  DB_CHECK_ARG(a->n_mfcc > 0, "number of MFCCs should be > 0");
+  DB_CHECK_ARG(a->dct_type >= 1 && a->dct_type <= 4, "Unsupported DCT type: %d. Supported types are: 1, 2, 3, 4.", a->dct_type);
+  DB_CHECK_ARG(!(a->normalize && a->dct_type == 1), "Ortho-normalization is not supported for DCT type I.");
+  p->kind = SIG_MFCC; p->n = n;
+  const int nfeat = n ? (int)shapes[0] : 1;
+  int ndct = a->n_mfcc;
+  if (ndct > nfeat) ndct = nfeat;                                 // dct_cpu.cc:56-58
+  DB_CHECK_ARG(a->dct_type != 1 || nfeat > 1, "DCT type I requires an input length > 1");
+  p->descs.assign(n, SigDesc());
+  int64_t items = 0;
+  for (int i = 0; i < n; i++) {
+    DB_CHECK_ARG(shapes[2 * i] == nfeat, "MFCC: all samples of a batch must have the same extent along the transformed axis");
+    p->descs[i].rows = nfeat; p->descs[i].cols = shapes[2 * i + 1]; p->descs[i].n = nfeat * shapes[2 * i + 1];
+    p->descs[i].first_item = items;
+    items += (shapes[2 * i + 1] + 127) / 128;
+  }
+  p->total_items = items;
+  std::vector<float> tab((size_t)ndct * nfeat + ndct);
+  FillCosineTable(tab.data(), nfeat, ndct, a->dct_type, a->normalize != 0);
+  p->has_lifter = a->lifter != 0.0f;
+  if (p->has_lifter) {                                            // mfcc.h:36-41
+    const float ampl_mult = a->lifter / 2, phase_mult = static_cast<float>(M_PI) / a->lifter;
+    // all-float arithmetic (the reference's unqualified sin() resolves to sinf there: checked on the compiled header)
+    for (int64_t i = 0; i < ndct; i++) tab[(size_t)ndct * nfeat + i] = 1.f + ampl_mult * sinf(phase_mult * (i + 1));
+  }
+  if (tab != p->h_table || nfeat != p->nfeat || ndct != p->ndct) { p->h_table = tab; p->table_dirty = true; }
+  p->nfeat = nfeat; p->ndct = ndct;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200SignalOutputRows(const dalib200SignalPlan *p) { return p ? p->ndct : 0; }
+
+int dalib200NormalizeSetup(dalib200SignalPlan *p, const dalib200NormalizeArgs *a, int n, const int64_t *shapes) {
+  DB_CHECK_ARG(p && a && (n == 0 || shapes) && n >= 0 && n <= p->max_batch, "NormalizeSetup: bad arguments");
+  DB_CHECK_ARG(a->mode >= 0 && a->mode <= 2, "NormalizeSetup: mode must be 0 (all axes), 1 (axis 1) or 2 (axis 0)");
+  DB_CHECK_ARG(a->ddof >= 0, "Normalize: ddof must be non-negative");
+  p->kind = SIG_NORMALIZE; p->n = n;
+  p->mode = a->mode; p->ddof = a->ddof; p->scale = a->scale; p->shift = a->shift; p->eps = a->epsilon;
+  p->descs.assign(n, SigDesc());
+  int64_t items = 0;
+  for (int i = 0; i < n; i++) {
+    p->descs[i].rows = shapes[2 * i]; p->descs[i].cols = shapes[2 * i + 1]; p->descs[i].n = shapes[2 * i] * shapes[2 * i + 1];
+    p->descs[i].first_item = items;
+    items += p->descs[i].n == 0 ? 0 : a->mode == 0 ? 1 : a->mode == 1 ? shapes[2 * i] : shapes[2 * i + 1];
+  }
+  p->total_items = items;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200SignalLaunch(dalib200SignalPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+  DB_CHECK_ARG(p && p->kind != SIG_NONE && (p->n == 0 || (in_ptrs && out_ptrs)), "SignalLaunch: call a ...Setup function first");
+  if (p->n == 0 || p->total_items == 0) return DALIB200_SUCCESS;
+  int rc = UploadDescs(p);
+  if (rc) return rc;
+  SigDesc *h = reinterpret_cast<SigDesc *>(p->arena.host);
+  for (int i = 0; i < p->n; i++) { h[i] = p->descs[i]; h[i].in = static_cast<const float *>(in_ptrs[i]); h[i].out = static_cast<float *>(out_ptrs[i]); }
+  if ((rc = p->arena.Upload(sizeof(SigDesc) * p->n, stream))) return rc;
+  DB_CUDA(cudaEventRecord(p->uploaded, stream));
+  p->pending = true;
+  const SigDesc *d = reinterpret_cast<const SigDesc *>(p->arena.dev);
+  const int grid = (int)std::min<int64_t>(p->total_items, (int64_t)NumSMs() * 16);
+  if (p->kind == SIG_TODB) {
+    const uint32_t *smax = nullptr;
+    if (p->ref_max) {
+      if ((size_t)p->n > p->d_max_cap) {
+        if (p->d_max) cudaFree(p->d_max);
+        p->d_max = nullptr; p->d_max_cap = 0;
+        DB_CUDA(cudaMalloc(reinterpret_cast<void **>(&p->d_max), sizeof(uint32_t) * p->max_batch));
+        p->d_max_cap = p->max_batch;
+      }
+      DB_CUDA(cudaMemsetAsync(p->d_max, 0, sizeof(uint32_t) * p->n, stream));
+      { ProfScope ps_("to_decibels_max", stream); todb_max_kernel<<<grid, 256, 0, stream>>>(d, p->n, p->total_items, p->d_max); }
+      CountLaunch();
+      smax = p->d_max;
+    }
+    { ProfScope ps_("to_decibels", stream); todb_kernel<<<grid, 256, 0, stream>>>(d, p->n, p->total_items, p->mul_log2, p->s_ref, p->min_ratio, smax); }
+    CountLaunch();
+  } else if (p->kind == SIG_MFCC) {
+    if ((rc = GrowF(p->d_table, p->d_table_cap, p->h_table.size()))) return rc;
+    if (p->table_dirty) {
+      // pageable source: the copy is staged by the runtime before the call returns
+      DB_CUDA(cudaMemcpyAsync(p->d_table, p->h_table.data(), p->h_table.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+      p->table_dirty = false;
+    }
+    const size_t smem = (size_t)p->ndct * p->nfeat * sizeof(float);
+    DB_CHECK_ARG(smem <= 200 * 1024, "MFCC: the cosine table (%d x %d) does not fit shared memory", p->ndct, p->nfeat);
+    if (smem > 48 * 1024) DB_CUDA(cudaFuncSetAttribute(mfcc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps_("mfcc_dct", stream);
+    mfcc_kernel<<<grid, 128, smem, stream>>>(d, p->n, p->total_items, p->nfeat, p->ndct, p->d_table,
+                                             p->has_lifter ? p->d_table + (size_t)p->ndct * p->nfeat : nullptr);
+    CountLaunch();
+  } else {
+    ProfScope ps_("normalize", stream);
+    normalize_kernel<<<grid, 256, 0, stream>>>(d, p->n, p->total_items, p->mode, p->scale, p->shift, p->eps, p->ddof);
+    CountLaunch();
+  }
+  DB_CUDA(cudaGetLastError());
+  return DALIB200_SUCCESS;
+}
+
+}  // extern "C"

@@ -257,7 +257,24 @@ DALI_REGISTER_OPERATOR(decoders__ImageCrop, ImageDecoderCropMixed, Mixed);
       .AddOptionalArg("num_attempts", "Maximum number of attempts used to choose random area and aspect ratio.", 10)           \
       .AddOptionalArg("seed", "Random seed.", -1)
 
-static std::vector<RandomCropGenerator> MakeCropGenerators(const OpSpec &spec, int max_batch) {
+// The prefetch slots of a pipeline instantiate every operator once per slot, but a random operator is ONE stream of numbers in the
+// reference (one instance serves all iterations).  Instances created from the same graph node (same `_state_key`, set by the
+// pipeline) therefore share their generators; the slots run their Setup in iteration order on the pipeline's host thread.
+using CropGenerators = std::shared_ptr<std::vector<RandomCropGenerator>>;
+static std::vector<RandomCropGenerator> MakeCropGeneratorsImpl(const OpSpec &spec, int max_batch);
+static CropGenerators MakeCropGenerators(const OpSpec &spec, int max_batch) {
+  static std::map<std::string, std::weak_ptr<std::vector<RandomCropGenerator>>> shared;
+  std::string key;
+  if (spec.ArgumentDefined("_state_key")) key = spec.GetArgument<std::string>("_state_key");
+  if (!key.empty()) {
+    auto it = shared.find(key);
+    if (it != shared.end()) if (auto sp = it->second.lock()) return sp;
+  }
+  auto sp = std::make_shared<std::vector<RandomCropGenerator>>(MakeCropGeneratorsImpl(spec, max_batch));
+  if (!key.empty()) shared[key] = sp;
+  return sp;
+}
+static std::vector<RandomCropGenerator> MakeCropGeneratorsImpl(const OpSpec &spec, int max_batch) {
   auto ar = spec.GetRepeatedArgument<float>("random_aspect_ratio");
   auto area = spec.GetRepeatedArgument<float>("random_area");
   if (ar.size() == 1) ar.push_back(ar[0]);
@@ -282,10 +299,10 @@ class ImageDecoderRandomCropMixed : public ImageDecoderBase {
  protected:
   bool HasRoi() const override { return true; }
   void SampleRoi(dalib200JpegRoi &roi, const Workspace &, int i, int H, int W) override {
-    const CropWindow2D c = gens_[i].Generate(H, W);
+    const CropWindow2D c = (*gens_)[i].Generate(H, W);
     roi = { 1, c.anchor[1], c.anchor[0], c.anchor[1] + c.shape[1], c.anchor[0] + c.shape[0] };
   }
-  std::vector<RandomCropGenerator> gens_;
+  CropGenerators gens_;
 };
 DALI_REGISTER_OPERATOR(decoders__ImageRandomCrop, ImageDecoderRandomCropMixed, Mixed);
 
@@ -308,52 +325,53 @@ DALI_SCHEMA(decoders__ImageSlice)
     .AddOptionalArgNoDefault("shape", "Shape of the slice (absolute).", true)
     .AddOptionalArgNoDefault("rel_shape", "Shape of the slice (relative).", true);
 
-class ImageDecoderSliceMixed : public ImageDecoderBase {
- public:
-  explicit ImageDecoderSliceMixed(const OpSpec &spec) : ImageDecoderBase(spec, "decoders.image_slice") {
+// slice_attr.h:36-345 (NamedSliceAttr / PositionalSliceAttr) for the H and W axes of an image
+struct SliceArgs {
+  std::vector<int> axes;
+  bool norm_anchor = true, norm_shape = true, positional = false;
+  void Init(const OpSpec &spec, const char *name) {
     const std::string names = spec.GetArgument<std::string>("axis_names");
     if (spec.ArgumentDefined("axes") || names.empty()) {
-      axes_ = spec.GetRepeatedArgument<int>("axes");
+      axes = spec.GetRepeatedArgument<int>("axes");
     } else {
       for (char c : names) {
-        DALI_ENFORCE(c == 'H' || c == 'W', "decoders.image_slice: axis_names may contain H and W only");
-        axes_.push_back(c == 'H' ? 0 : 1);
+        DALI_ENFORCE(c == 'H' || c == 'W', name, ": axis_names may contain H and W only");
+        axes.push_back(c == 'H' ? 0 : 1);
       }
     }
-    for (int a : axes_) DALI_ENFORCE(a == 0 || a == 1, "decoders.image_slice: only the H (0) and W (1) axes can be sliced");
-    norm_anchor_ = spec.GetArgument<bool>("normalized_anchor"); norm_shape_ = spec.GetArgument<bool>("normalized_shape");
-    positional_ = spec.NumInput() == 3;
-    DALI_ENFORCE(spec.NumInput() == 1 || spec.NumInput() == 3, "decoders.image_slice expects 1 input (and slice arguments) or 3 inputs (data, anchor, shape)");
+    for (int a : axes) DALI_ENFORCE(a == 0 || a == 1, name, ": only the H (0) and W (1) axes can be sliced");
+    norm_anchor = spec.GetArgument<bool>("normalized_anchor"); norm_shape = spec.GetArgument<bool>("normalized_shape");
+    positional = spec.NumInput() == 3;
+    DALI_ENFORCE(spec.NumInput() == 1 || spec.NumInput() == 3, name, " expects 1 input (and slice arguments) or 3 inputs (data, anchor, shape)");
     const bool has_start = spec.ArgumentDefined("start") || spec.ArgumentDefined("rel_start");
     const bool has_end = spec.ArgumentDefined("end") || spec.ArgumentDefined("rel_end");
     const bool has_shape = spec.ArgumentDefined("shape") || spec.ArgumentDefined("rel_shape");
-    DALI_ENFORCE(!(positional_ && (has_start || has_end || has_shape)), "Named slice arguments cannot be mixed with positional anchor / shape inputs");
+    DALI_ENFORCE(!(positional && (has_start || has_end || has_shape)), "Named slice arguments cannot be mixed with positional anchor / shape inputs");
     DALI_ENFORCE(!(has_end && has_shape), "`end`/`rel_end` and `shape`/`rel_shape` are mutually exclusive");
   }
- protected:
-  bool HasRoi() const override { return true; }
-  void SampleRoi(dalib200JpegRoi &roi, const Workspace &ws, int i, int H, int W) override {
+  // [b, e) per axis (0 = H, 1 = W) for an H x W image; not clamped
+  void Get(const OpSpec &spec_, const Workspace &ws, int i, int64_t H, int64_t W, int64_t b[2], int64_t e[2]) const {
     const int64_t dim[2] = { H, W };
-    int64_t b[2] = { 0, 0 }, e[2] = { H, W };
-    const int na = static_cast<int>(axes_.size());
+    b[0] = b[1] = 0; e[0] = H; e[1] = W;
+    const int na = static_cast<int>(axes.size());
     for (int k = 0; k < na; k++) {
-      const int ax = axes_[k];
+      const int ax = axes[k];
       double anchor_val = 0, end_val = static_cast<double>(dim[ax]);
-      if (positional_) {
+      if (positional) {
         // slice_attr.h:282-330 (PositionalSliceAttr)
         const auto &anc = ws.Input<CPUBackend>(1);
         const auto &shp = ws.Input<CPUBackend>(2);
-        DALI_ENFORCE(anc.type() == DALI_FLOAT && shp.type() == DALI_FLOAT, "decoders.image_slice: anchor and shape inputs must be float");
+        DALI_ENFORCE(anc.type() == DALI_FLOAT && shp.type() == DALI_FLOAT, "slice: anchor and shape inputs must be float");
         DALI_ENFORCE(anc.shape().tensor_size(i) == na && shp.shape().tensor_size(i) == na,
                      "Expected ", na, " elements for slice arguments (start/shape). Got ", anc.shape().tensor_size(i));
         anchor_val = anc.tensor<float>(i)[k];
         double shape_val = shp.tensor<float>(i)[k];
-        if (norm_anchor_ && norm_shape_) {        // multiply once, after the sum
+        if (norm_anchor && norm_shape) {          // multiply once, after the sum
           end_val = (anchor_val + shape_val) * dim[ax];
           anchor_val *= dim[ax];
         } else {
-          if (norm_anchor_) anchor_val *= dim[ax];
-          if (norm_shape_) shape_val *= dim[ax];
+          if (norm_anchor) anchor_val *= dim[ax];
+          if (norm_shape) shape_val *= dim[ax];
           end_val = anchor_val + shape_val;
         }
       } else {
@@ -373,12 +391,34 @@ class ImageDecoderSliceMixed : public ImageDecoderBase {
       b[ax] = std::llround(anchor_val);
       e[ax] = std::llround(end_val);
     }
+  }
+};
+
+#define DALIB200_SLICE_ARGS(schema)                                                                                            \
+  schema.AddOptionalArg("axes", "Order of the dimensions of anchor and shape.", std::vector<int>{1, 0})                        \
+      .AddOptionalArg("axis_names", "Order of the dimensions of anchor and shape, as layout characters.", std::string("WH"))   \
+      .AddOptionalArg("normalized_anchor", "The anchor input is in normalised coordinates.", true)                             \
+      .AddOptionalArg("normalized_shape", "The shape input is in normalised coordinates.", true)                               \
+      .AddOptionalArgNoDefault("start", "Start of the slice (absolute).", true)                                                \
+      .AddOptionalArgNoDefault("rel_start", "Start of the slice (relative).", true)                                            \
+      .AddOptionalArgNoDefault("end", "End of the slice (absolute).", true)                                                    \
+      .AddOptionalArgNoDefault("rel_end", "End of the slice (relative).", true)                                                \
+      .AddOptionalArgNoDefault("shape", "Shape of the slice (absolute).", true)                                                \
+      .AddOptionalArgNoDefault("rel_shape", "Shape of the slice (relative).", true)
+
+class ImageDecoderSliceMixed : public ImageDecoderBase {
+ public:
+  explicit ImageDecoderSliceMixed(const OpSpec &spec) : ImageDecoderBase(spec, "decoders.image_slice") { slice_.Init(spec, name_); }
+ protected:
+  bool HasRoi() const override { return true; }
+  void SampleRoi(dalib200JpegRoi &roi, const Workspace &ws, int i, int H, int W) override {
+    int64_t b[2], e[2];
+    slice_.Get(spec_, ws, i, H, W, b, e);
     DALI_ENFORCE(b[0] >= 0 && b[1] >= 0 && e[0] <= H && e[1] <= W && b[0] < e[0] && b[1] < e[1],
                  "decoders.image_slice: sample ", i, ": slice [", b[0], ", ", e[0], ") x [", b[1], ", ", e[1], ") must be non-empty and inside the image {", H, ", ", W, "}");
     roi = { 1, static_cast<int>(b[1]), static_cast<int>(b[0]), static_cast<int>(e[1]), static_cast<int>(e[0]) };
   }
-  std::vector<int> axes_;
-  bool norm_anchor_ = true, norm_shape_ = true, positional_ = false;
+  SliceArgs slice_;
 };
 DALI_REGISTER_OPERATOR(decoders__ImageSlice, ImageDecoderSliceMixed, Mixed);
 
@@ -685,7 +725,7 @@ class RandomResizedCropGPU : public Operator<GPUBackend> {
       const int64_t *s = in.shape().tensor_shape_span(i);
       const int fs = frames_.first_spatial;
       const int H = static_cast<int>(s[fs]), W = static_cast<int>(s[fs + 1]);
-      crops_[i] = gens_[i].Generate(H, W);
+      crops_[i] = (*gens_)[i].Generate(H, W);
       int interp = spec_.GetArgument<int>("interp_type", &ws, i);
       int minf = DALIB200_FILTER_TRIANGULAR, magf = DALIB200_FILTER_LINEAR;
       auto conv = [](int t, bool aa) {
@@ -739,7 +779,7 @@ class RandomResizedCropGPU : public Operator<GPUBackend> {
   int plan_cap_ = 0;
   bool antialias_ = true;
   std::vector<int> size_;
-  std::vector<RandomCropGenerator> gens_;
+  CropGenerators gens_;
   std::vector<CropWindow2D> crops_;
   FrameList frames_;
   std::vector<dalib200ResampleSample> samples_;
@@ -1268,6 +1308,576 @@ class MelFilterBankGPU : public Operator<GPUBackend> {
   dalib200MelArgs args_{};
 };
 DALI_REGISTER_OPERATOR(MelFilterBank, MelFilterBankGPU, GPU);
+
+// =============================================================================================== BrightnessContrast / ColorTwist
+DALI_SCHEMA(BrightnessContrast)
+    .DocStr("Adjusts the brightness and contrast of the images: out = brightness_shift * range + brightness * (center + contrast * (in - center)).")
+    .NumInput(1).NumOutput(1).AllowSequences()
+    .AddOptionalArg("brightness", "Brightness multiplier.", 1.0f, true)
+    .AddOptionalArg("brightness_shift", "The brightness shift (in units of the full range of the output type).", 0.0f, true)
+    .AddOptionalArg("contrast", "The contrast multiplier.", 1.0f, true)
+    .AddOptionalArgNoDefault("contrast_center", "The intensity level that is unaffected by contrast (default: half the input range).", true)
+    .AddOptionalArgNoDefault("dtype", "Output data type (default: the input type).");
+
+class GenericOpBase : public Operator<GPUBackend> {
+ public:
+  explicit GenericOpBase(const OpSpec &spec, const char *name) : Operator<GPUBackend>(spec), name_(name) {
+    CheckStatus(dalib200GenericPlanCreate(&plan_, max_batch_size_ * 64), name_);
+    plan_cap_ = max_batch_size_ * 64;
+  }
+  ~GenericOpBase() override { dalib200GenericPlanDestroy(plan_); }
+ protected:
+  void EnsureCap(int n) {
+    if (n > plan_cap_) { dalib200GenericPlanDestroy(plan_); plan_ = nullptr; plan_cap_ = n; CheckStatus(dalib200GenericPlanCreate(&plan_, n), name_); }
+  }
+  dalib200GenericPlan *plan_ = nullptr;
+  int plan_cap_ = 0;
+  const char *name_;
+};
+
+class BrightnessContrastGPU : public GenericOpBase {
+ public:
+  explicit BrightnessContrastGPU(const OpSpec &spec) : GenericOpBase(spec, "BrightnessContrast") {}
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_UINT8, "BrightnessContrast: the GPU path expects uint8 input");
+    out_type_ = spec_.ArgumentDefined("dtype") ? spec_.GetArgument<DALIDataType>("dtype") : DALI_UINT8;
+    DALI_ENFORCE(out_type_ == DALI_UINT8 || out_type_ == DALI_FLOAT, "BrightnessContrast: the GPU path supports dtype UINT8 and FLOAT");
+    const int n = in.num_samples();
+    EnsureCap(n);
+    std::vector<int64_t> vol(n);
+    std::vector<float> mul(n), add(n);
+    // brightness_contrast.h:84-103: FullRange<Out> = 255 (u8) or 1 (float); HalfRange<uint8_t> = 128
+    const float range = out_type_ == DALI_UINT8 ? 255.0f : 1.0f;
+    for (int i = 0; i < n; i++) {
+      vol[i] = in.shape().tensor_size(i);
+      const float brightness = spec_.GetArgument<float>("brightness", &ws, i), shift = spec_.GetArgument<float>("brightness_shift", &ws, i);
+      const float contrast = spec_.GetArgument<float>("contrast", &ws, i);
+      const float center = spec_.ArgumentDefined("contrast_center") ? spec_.GetArgument<float>("contrast_center", &ws, i) : 128.0f;
+      volatile float t0 = contrast * center;            // every product / sum rounded to float, in the reference's order
+      volatile float t1 = center - t0;
+      volatile float t2 = brightness * t1;
+      volatile float t3 = shift * range;
+      add[i] = t3 + t2;
+      mul[i] = brightness * contrast;
+    }
+    CheckStatus(dalib200MultiplyAddSetup(plan_, n, vol.data(), mul.data(), add.data(), out_type_ == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT), name_);
+    out.resize(1);
+    out[0].shape = in.shape(); out[0].type = out_type_;
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    std::vector<const void *> ip(in.num_samples());
+    std::vector<void *> op(in.num_samples());
+    for (int i = 0; i < in.num_samples(); i++) { ip[i] = in.raw_tensor(i); op[i] = out.raw_mutable_tensor(i); }
+    CheckStatus(dalib200GenericLaunch(plan_, ip.data(), op.data(), ws.stream()), name_);
+  }
+  DALIDataType out_type_ = DALI_UINT8;
+};
+DALI_REGISTER_OPERATOR(BrightnessContrast, BrightnessContrastGPU, GPU);
+
+DALI_SCHEMA(ColorTwist)
+    .DocStr("Adjusts hue, saturation, brightness and contrast of the image.")
+    .NumInput(1).NumOutput(1).AllowSequences()
+    .AddOptionalArg("hue", "Hue change, in degrees.", 0.0f, true)
+    .AddOptionalArg("saturation", "Saturation change factor.", 1.0f, true)
+    .AddOptionalArg("contrast", "Contrast change factor.", 1.0f, true)
+    .AddOptionalArg("brightness", "Brightness change factor.", 1.0f, true)
+    .AddOptionalArg("image_type", "The color space of the input and the output image.", DALI_RGB)
+    .AddOptionalArgNoDefault("dtype", "Output data type (default: the input type).");
+
+class ColorTwistGPU : public PointwiseBase {
+ public:
+  explicit ColorTwistGPU(const OpSpec &spec) : PointwiseBase(spec, "ColorTwist") {
+    out_type_ = spec.ArgumentDefined("dtype") ? spec.GetArgument<DALIDataType>("dtype") : DALI_UINT8;
+    DALI_ENFORCE(out_type_ == DALI_UINT8 || out_type_ == DALI_FLOAT, "ColorTwist: the GPU path supports dtype UINT8 and FLOAT");
+  }
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_UINT8, "ColorTwist: the GPU path expects uint8 input");
+    const int n = in.num_samples();
+    EnsureCap(n);
+    std::vector<dalib200ColorSample> cs(n);
+    for (int i = 0; i < n; i++) {
+      const int nd = in.shape().sample_dim();
+      DALI_ENFORCE(in.shape().tensor_shape_span(i)[nd - 1] == 3, "ColorTwist expects 3-channel (channel-last) images");
+      cs[i].num_pixels = in.shape().tensor_size(i) / 3;
+      // color_twist.h:156-170: value = 1; half_range = 128 for integer inputs
+      dalib200ColorTwistMatrix(spec_.GetArgument<float>("hue", &ws, i), spec_.GetArgument<float>("saturation", &ws, i), 1.0f,
+                               spec_.GetArgument<float>("brightness", &ws, i), spec_.GetArgument<float>("contrast", &ws, i), 128.0f,
+                               cs[i].matrix, cs[i].offset);
+    }
+    CheckStatus(dalib200LinearTransformSetup(plan_, n, cs.data(), out_type_ == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT), "ColorTwist");
+    out.resize(1);
+    out[0].shape = in.shape(); out[0].type = out_type_;
+    return true;
+  }
+  void RunImpl(Workspace &ws) override { Launch(ws); }
+ private:
+  DALIDataType out_type_ = DALI_UINT8;
+};
+DALI_REGISTER_OPERATOR(ColorTwist, ColorTwistGPU, GPU);
+
+// =============================================================================================== Flip / Crop / Slice
+// Window copies of interleaved u8 images (dali/operators/generic/flip.{h,cc}, image/crop/crop.{h,cc}, generic/slice/slice.{h,cc}).
+class WindowOpBase : public GenericOpBase {
+ public:
+  explicit WindowOpBase(const OpSpec &spec, const char *name) : GenericOpBase(spec, name) {}
+ protected:
+  // fills w (anchor / out size / flips / fill) for frame-independent sample i of size H x W x C
+  virtual void SampleWindow(dalib200WindowSample &w, const Workspace &ws, int i, int H, int W, int C) = 0;
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_UINT8, name_, ": the GPU path expects uint8 input");
+    const int n = in.num_samples();
+    frames_ = ExpandFrames(in.shape(), in.GetLayout(), name_);
+    const int nf = frames_.num_frames();
+    EnsureCap(nf);
+    samples_.assign(nf, dalib200WindowSample());
+    out_hw_.assign(n, {0, 0});
+    int fk = 0;
+    for (int i = 0; i < n; i++) {
+      const int64_t *s = in.shape().tensor_shape_span(i);
+      const int fs = frames_.first_spatial;
+      dalib200WindowSample w{};
+      w.in_h = static_cast<int>(s[fs]); w.in_w = static_cast<int>(s[fs + 1]); w.channels = static_cast<int>(s[fs + 2]);
+      DALI_ENFORCE(w.channels >= 1, name_, ": empty channel dimension");
+      SampleWindow(w, ws, i, w.in_h, w.in_w, w.channels);
+      out_hw_[i] = { w.out_h, w.out_w };
+      const int64_t frames = fs ? s[0] : 1;
+      for (int64_t k = 0; k < frames; k++) samples_[fk++] = w;
+    }
+    CheckStatus(dalib200WindowCopySetup(plan_, nf, samples_.data()), name_);
+    out.resize(1);
+    out[0].type = DALI_UINT8;
+    out[0].shape.resize(n, in.shape().sample_dim());
+    for (int i = 0; i < n; i++) {
+      TensorShape sh = in.shape().tensor_shape(i);
+      sh[frames_.first_spatial] = out_hw_[i].first; sh[frames_.first_spatial + 1] = out_hw_[i].second;
+      out[0].shape.set_tensor_shape(i, sh);
+    }
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout().empty() ? TensorLayout(frames_.first_spatial ? "FHWC" : "HWC") : in.GetLayout());
+    auto ip = FramePtrs(in, frames_, 1);
+    std::vector<void *> op(frames_.num_frames());
+    std::vector<int64_t> next(out.num_samples(), 0);
+    for (int k = 0; k < frames_.num_frames(); k++) {
+      const int s = frames_.sample_of_frame[k];
+      op[k] = static_cast<uint8_t *>(out.raw_mutable_tensor(s)) + next[s];
+      next[s] += static_cast<int64_t>(out_hw_[s].first) * out_hw_[s].second * frames_.c[k];
+    }
+    CheckStatus(dalib200GenericLaunch(plan_, ip.data(), op.data(), ws.stream()), name_);
+  }
+  // out_of_bounds_policy handling shared by crop and slice (generic/slice/out_of_bounds_policy.h)
+  void ApplyOob(dalib200WindowSample &w, const std::string &policy, const std::vector<float> &fill, int64_t ay, int64_t ax, int64_t h, int64_t wd) {
+    const int64_t H = w.in_h, W = w.in_w;
+    const bool oob = ay < 0 || ax < 0 || ay + h > H || ax + wd > W;
+    if (oob) {
+      if (policy == "error") {
+        DALI_FAIL(make_string("Slice can't be placed out of bounds with current policy. Got: input_shape={", H, ", ", W, ", ", w.channels,
+                              "}, slice_anchor={", ay, ", ", ax, ", 0}, slice_shape={", h, ", ", wd, ", ", w.channels, "}"));
+      } else if (policy == "trim_to_shape") {
+        const int64_t y0 = std::min(std::max<int64_t>(ay, 0), H), x0 = std::min(std::max<int64_t>(ax, 0), W);
+        const int64_t y1 = std::min(std::max<int64_t>(ay + h, 0), H), x1 = std::min(std::max<int64_t>(ax + wd, 0), W);
+        ay = y0; ax = x0; h = y1 - y0; wd = x1 - x0;
+      }
+    }
+    w.anchor_y = static_cast<int>(ay); w.anchor_x = static_cast<int>(ax); w.out_h = static_cast<int>(h); w.out_w = static_cast<int>(wd);
+    for (int k = 0; k < 4; k++) {
+      const float f = fill.empty() ? 0.0f : fill.size() == 1 ? fill[0] : (k < static_cast<int>(fill.size()) ? fill[k] : 0.0f);
+      w.fill[k] = static_cast<uint8_t>(std::min(255.0f, std::max(0.0f, std::round(f))));      // ConvertSat<uint8_t>
+    }
+  }
+  FrameList frames_;
+  std::vector<dalib200WindowSample> samples_;
+  std::vector<std::pair<int, int>> out_hw_;
+};
+
+DALI_SCHEMA(Flip)
+    .DocStr("Flips the images in selected dimensions (horizontal, vertical).")
+    .NumInput(1).NumOutput(1).AllowSequences()
+    .AddOptionalArg("horizontal", "Flip the horizontal dimension.", 1, true)
+    .AddOptionalArg("vertical", "Flip the vertical dimension.", 0, true)
+    .AddOptionalArg("depthwise", "not supported (2-D images only)", 0, true);
+
+class FlipGPU : public WindowOpBase {
+ public:
+  explicit FlipGPU(const OpSpec &spec) : WindowOpBase(spec, "Flip") {}
+ protected:
+  void SampleWindow(dalib200WindowSample &w, const Workspace &ws, int i, int H, int W, int) override {
+    DALI_ENFORCE(spec_.GetArgument<int>("depthwise", &ws, i) == 0, "Flip: depthwise flips need volumetric data, which the GPU path does not support");
+    w.anchor_y = w.anchor_x = 0; w.out_h = H; w.out_w = W;
+    w.flip_x = spec_.GetArgument<int>("horizontal", &ws, i) != 0;
+    w.flip_y = spec_.GetArgument<int>("vertical", &ws, i) != 0;
+  }
+};
+DALI_REGISTER_OPERATOR(Flip, FlipGPU, GPU);
+
+DALI_SCHEMA(Crop)
+    .DocStr("Crops the images with the specified window dimensions and window position (upper left corner).")
+    .NumInput(1).NumOutput(1).AllowSequences()
+    DALIB200_CROP_ARGS()
+    .AddOptionalArg("out_of_bounds_policy", "error | pad | trim_to_shape", std::string("error"))
+    .AddOptionalArg("fill_values", "Fill values for padding.", std::vector<float>{0.0f})
+    .AddOptionalArgNoDefault("dtype", "Output data type (UINT8 only on the GPU path).");
+
+class CropGPU : public WindowOpBase {
+ public:
+  explicit CropGPU(const OpSpec &spec) : WindowOpBase(spec, "Crop") {
+    crop_.Init(spec, name_);
+    oob_ = spec.GetArgument<std::string>("out_of_bounds_policy");
+    DALI_ENFORCE(oob_ == "error" || oob_ == "pad" || oob_ == "trim_to_shape", "Unsupported out_of_bounds_policy: ", oob_);
+    fill_ = spec.GetRepeatedArgument<float>("fill_values");
+    if (spec.ArgumentDefined("dtype")) DALI_ENFORCE(spec.GetArgument<DALIDataType>("dtype") == DALI_UINT8, "Crop: the GPU path keeps the uint8 input type");
+  }
+ protected:
+  void SampleWindow(dalib200WindowSample &w, const Workspace &ws, int i, int H, int W, int) override {
+    int64_t y0, x0, h, wd;
+    crop_.Get(spec_, ws, i, H, W, y0, x0, h, wd);
+    ApplyOob(w, oob_, fill_, y0, x0, h, wd);
+  }
+  CropWindowArgs crop_;
+  std::string oob_;
+  std::vector<float> fill_;
+};
+DALI_REGISTER_OPERATOR(Crop, CropGPU, GPU);
+
+DALI_SCHEMA(Slice)
+    .DocStr("Extracts a subtensor, or slice (H / W axes of interleaved images on the GPU path).")
+    .NumInput(1, 3).NumOutput(1).AllowSequences()
+    DALIB200_SLICE_ARGS()
+    .AddOptionalArg("out_of_bounds_policy", "error | pad | trim_to_shape", std::string("error"))
+    .AddOptionalArg("fill_values", "Fill values for padding.", std::vector<float>{0.0f})
+    .AddOptionalArgNoDefault("dtype", "Output data type (UINT8 only on the GPU path).");
+
+class SliceGPU : public WindowOpBase {
+ public:
+  explicit SliceGPU(const OpSpec &spec) : WindowOpBase(spec, "Slice") {
+    slice_.Init(spec, name_);
+    oob_ = spec.GetArgument<std::string>("out_of_bounds_policy");
+    DALI_ENFORCE(oob_ == "error" || oob_ == "pad" || oob_ == "trim_to_shape", "Unsupported out_of_bounds_policy: ", oob_);
+    fill_ = spec.GetRepeatedArgument<float>("fill_values");
+  }
+ protected:
+  void SampleWindow(dalib200WindowSample &w, const Workspace &ws, int i, int H, int W, int) override {
+    int64_t b[2], e[2];
+    slice_.Get(spec_, ws, i, H, W, b, e);
+    ApplyOob(w, oob_, fill_, b[0], b[1], e[0] - b[0], e[1] - b[1]);
+  }
+  SliceArgs slice_;
+  std::string oob_;
+  std::vector<float> fill_;
+};
+DALI_REGISTER_OPERATOR(Slice, SliceGPU, GPU);
+
+// =============================================================================================== Rotate
+// dali/operators/image/remap/rotate.cc + rotate_params.h: a WarpAffine whose matrix is
+// translation(in / 2) * rotation2D(-a) * translation(-out / 2) with a = deg2rad(-angle) (counter-clockwise for a top-left origin)
+// and whose canvas is the bounding box of the rotated image (parity kept, rotate_params.h:36-55,279-297) unless `size` / `keep_size`.
+DALI_SCHEMA(Rotate)
+    .DocStr("Rotates the images by the specified angle.")
+    .NumInput(1).NumOutput(1).AllowSequences()
+    .AddArg("angle", "Angle, in degrees, by which the image is rotated (counter-clockwise).", true)
+    .AddOptionalArg("keep_size", "If True, original canvas size is kept.", false)
+    .AddOptionalArgNoDefault("axis", "3-D rotation axis: not supported (2-D images only).", true)
+    .AddOptionalArgNoDefault("size", "Output size (H, W).", true)
+    .AddOptionalArgNoDefault("fill_value", "Value used outside the source image; absent = clamp to border.")
+    .AddOptionalArgNoDefault("dtype", "Output type (same as input or FLOAT).")
+    .AddOptionalArg("interp_type", "NN or LINEAR.", DALI_INTERP_LINEAR);
+
+namespace rotate_detail {
+// geom/mat.h operator* for 3x3 floats: every element is a left-to-right sum of three separately rounded products
+inline void Mul3(const float a[9], const float b[9], float r[9]) {
+  float t[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      volatile float s = a[i * 3] * b[j];
+      volatile float p = a[i * 3 + 1] * b[3 + j];
+      s = s + p;
+      p = a[i * 3 + 2] * b[6 + j];
+      s = s + p;
+      t[i * 3 + j] = s;
+    }
+  std::copy(t, t + 9, r);
+}
+inline void CanvasSize(int h, int w, double angle, int &h_out, int &w_out, int &par_w, int &par_h) {     // rotate_params.h:36-55
+  const double eps = 1e-2;
+  const double abs_cos = std::abs(std::cos(angle)), abs_sin = std::abs(std::sin(angle));
+  w_out = static_cast<int>(std::ceil(abs_cos * w + abs_sin * h - eps));
+  h_out = static_cast<int>(std::ceil(abs_cos * h + abs_sin * w - eps));
+  if (abs_sin <= abs_cos) { par_w = w % 2; par_h = h % 2; } else { par_w = h % 2; par_h = w % 2; }
+}
+inline void Params(float angle_deg, int in_h, int in_w, bool keep_size, const float *size_hw, int &out_h, int &out_w, float M[6]) {
+  const float d2r = M_PI / 180;
+  const float neg = -angle_deg;                         // SetParams(): 2-D angles are negated
+  volatile float a = neg * d2r;                         // deg2rad(float)
+  if (size_hw) {                                        // warp_param_provider.h:234-314: explicit size, rounded
+    out_h = std::max<int>(static_cast<int>(std::roundf(size_hw[0])), 1); out_w = std::max<int>(static_cast<int>(std::roundf(size_hw[1])), 1);
+  } else if (keep_size) {
+    out_h = in_h; out_w = in_w;
+  } else {
+    int pw, ph;
+    CanvasSize(in_h, in_w, static_cast<double>(a), out_h, out_w, pw, ph);
+    out_w += (out_w % 2) ^ (2 * pw > 1);                 // one frame: the majority vote is the frame's own parity
+    out_h += (out_h % 2) ^ (2 * ph > 1);
+  }
+  const float ra = -a;
+  const float c = std::cos(ra), sn = std::sin(ra);
+  const float T1[9] = { 1, 0, in_w * 0.5f, 0, 1, in_h * 0.5f, 0, 0, 1 };
+  const float R[9] = { c, -sn, 0, sn, c, 0, 0, 0, 1 };
+  const float T2[9] = { 1, 0, -(out_w * 0.5f), 0, 1, -(out_h * 0.5f), 0, 0, 1 };
+  float A[9], B[9];
+  Mul3(T1, R, A);
+  Mul3(A, T2, B);
+  std::copy(B, B + 6, M);
+}
+}  // namespace rotate_detail
+
+class RotateGPU : public Operator<GPUBackend> {
+ public:
+  explicit RotateGPU(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    const int it = spec.GetArgument<int>("interp_type");
+    DALI_ENFORCE(it == DALI_INTERP_NN || it == DALI_INTERP_LINEAR, "Unsupported interpolation type");
+    interp_ = it == DALI_INTERP_LINEAR;
+    keep_size_ = spec.GetArgument<bool>("keep_size");
+    DALI_ENFORCE(!spec.ArgumentDefined("axis"), "Rotate: `axis` (3-D rotation) is not supported by the GPU path");
+    use_fill_ = spec.ArgumentDefined("fill_value");
+    if (use_fill_) fill_ = spec.GetArgument<float>("fill_value");
+    CheckStatus(dalib200WarpPlanCreate(&plan_, max_batch_size_ * 64), "Rotate");
+    plan_cap_ = max_batch_size_ * 64;
+  }
+  ~RotateGPU() override { dalib200WarpPlanDestroy(plan_); }
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_UINT8, "Rotate: the GPU path expects uint8 input");
+    out_type_ = spec_.ArgumentDefined("dtype") ? spec_.GetArgument<DALIDataType>("dtype") : DALI_UINT8;
+    DALI_ENFORCE(out_type_ == DALI_UINT8 || out_type_ == DALI_FLOAT, "Rotate: output type must be UINT8 or FLOAT");
+    const int n = in.num_samples();
+    frames_ = ExpandFrames(in.shape(), in.GetLayout(), "Rotate");
+    const int nf = frames_.num_frames();
+    if (nf > plan_cap_) { dalib200WarpPlanDestroy(plan_); plan_ = nullptr; plan_cap_ = nf; CheckStatus(dalib200WarpPlanCreate(&plan_, nf), "Rotate"); }
+    samples_.assign(nf, dalib200WarpSample());
+    out_hw_.assign(n, {0, 0});
+    int fk = 0;
+    for (int i = 0; i < n; i++) {
+      const int64_t *s = in.shape().tensor_shape_span(i);
+      const int fs = frames_.first_spatial;
+      const int H = static_cast<int>(s[fs]), W = static_cast<int>(s[fs + 1]);
+      const float angle = spec_.GetArgument<float>("angle", &ws, i);
+      std::vector<float> sz;
+      if (spec_.ArgumentDefined("size")) {
+        sz = spec_.GetFloatVecArgument("size", &ws, i);
+        DALI_ENFORCE(sz.size() == 2, "output_size must specify same number of dimensions as the input (excluding channels)");
+        DALI_ENFORCE(sz[0] > 0 && sz[1] > 0, "Output size must be positive");
+      }
+      int oh, ow; float M[6];
+      rotate_detail::Params(angle, H, W, keep_size_, sz.empty() ? nullptr : sz.data(), oh, ow, M);
+      out_hw_[i] = { oh, ow };
+      const int64_t frames = fs ? s[0] : 1;
+      for (int64_t k = 0; k < frames; k++, fk++) {
+        auto &w = samples_[fk];
+        w.in_h = H; w.in_w = W; w.channels = static_cast<int>(s[fs + 2]);
+        w.out_h = oh; w.out_w = ow;
+        std::copy(M, M + 6, w.matrix);
+      }
+    }
+    CheckStatus(dalib200WarpPlanSetup(plan_, nf, samples_.data(), interp_, use_fill_, fill_, out_type_ == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT), "Rotate");
+    out.resize(1);
+    out[0].type = out_type_;
+    out[0].shape.resize(n, in.shape().sample_dim());
+    for (int i = 0; i < n; i++) {
+      TensorShape sh = in.shape().tensor_shape(i);
+      sh[frames_.first_spatial] = out_hw_[i].first; sh[frames_.first_spatial + 1] = out_hw_[i].second;
+      out[0].shape.set_tensor_shape(i, sh);
+    }
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout().empty() ? TensorLayout(frames_.first_spatial ? "FHWC" : "HWC") : in.GetLayout());
+    auto ip = FramePtrs(in, frames_, 1);
+    std::vector<void *> op(frames_.num_frames());
+    std::vector<int64_t> next(out.num_samples(), 0);
+    for (int k = 0; k < frames_.num_frames(); k++) {
+      const int s = frames_.sample_of_frame[k];
+      op[k] = static_cast<uint8_t *>(out.raw_mutable_tensor(s)) + next[s];
+      next[s] += static_cast<int64_t>(out_hw_[s].first) * out_hw_[s].second * frames_.c[k] * TypeSize(out_type_);
+    }
+    CheckStatus(dalib200WarpLaunch(plan_, ip.data(), op.data(), ws.stream()), "Rotate");
+  }
+ private:
+  dalib200WarpPlan *plan_ = nullptr;
+  int plan_cap_ = 0;
+  bool interp_ = true, keep_size_ = false, use_fill_ = false;
+  float fill_ = 0;
+  DALIDataType out_type_ = DALI_UINT8;
+  FrameList frames_;
+  std::vector<dalib200WarpSample> samples_;
+  std::vector<std::pair<int, int>> out_hw_;
+};
+DALI_REGISTER_OPERATOR(Rotate, RotateGPU, GPU);
+
+// =============================================================================================== ToDecibels / MFCC / Normalize
+class SignalOpBase : public Operator<GPUBackend> {
+ public:
+  explicit SignalOpBase(const OpSpec &spec, const char *name) : Operator<GPUBackend>(spec), name_(name) {
+    CheckStatus(dalib200SignalPlanCreate(&plan_, max_batch_size_), name_);
+  }
+  ~SignalOpBase() override { dalib200SignalPlanDestroy(plan_); }
+ protected:
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    std::vector<const void *> ip(in.num_samples());
+    std::vector<void *> op(in.num_samples());
+    for (int i = 0; i < in.num_samples(); i++) { ip[i] = in.raw_tensor(i); op[i] = out.raw_mutable_tensor(i); }
+    CheckStatus(dalib200SignalLaunch(plan_, ip.data(), op.data(), ws.stream()), name_);
+  }
+  dalib200SignalPlan *plan_ = nullptr;
+  const char *name_;
+};
+
+DALI_SCHEMA(ToDecibels)
+    .DocStr("Converts a magnitude (real, positive) to the decibel scale.")
+    .NumInput(1).NumOutput(1)
+    .AddOptionalArg("multiplier", "Factor by which the logarithm is multiplied (10 or 20).", 10.0f)
+    .AddOptionalArgNoDefault("reference", "Reference magnitude; when absent the per-sample maximum is used.")
+    .AddOptionalArg("cutoff_db", "Minimum or cut-off ratio in dB.", -200.0f);
+
+class ToDecibelsGPU : public SignalOpBase {
+ public:
+  explicit ToDecibelsGPU(const OpSpec &spec) : SignalOpBase(spec, "ToDecibels") {
+    args_.multiplier = spec.GetArgument<float>("multiplier");
+    args_.ref_max = !spec.ArgumentDefined("reference");
+    args_.reference = args_.ref_max ? 1.0f : spec.GetArgument<float>("reference");
+    DALI_ENFORCE(args_.ref_max || args_.reference != 0, "`reference` argument can't be zero");
+    args_.cutoff_db = spec.GetArgument<float>("cutoff_db");
+  }
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_FLOAT, "Unsupported data type: ", static_cast<int>(in.type()));
+    const int n = in.num_samples();
+    std::vector<int64_t> vol(n);
+    for (int i = 0; i < n; i++) vol[i] = in.shape().tensor_size(i);
+    CheckStatus(dalib200ToDecibelsSetup(plan_, &args_, n, vol.data()), name_);
+    out.resize(1);
+    out[0].shape = in.shape(); out[0].type = DALI_FLOAT;
+    return true;
+  }
+  dalib200ToDecibelsArgs args_{};
+};
+DALI_REGISTER_OPERATOR(ToDecibels, ToDecibelsGPU, GPU);
+
+DALI_SCHEMA(MFCC)
+    .DocStr("Computes Mel Frequency Cepstral Coefficients (MFCC) from a mel spectrogram.")
+    .NumInput(1).NumOutput(1)
+    .AddOptionalArg("n_mfcc", "Number of MFCC coefficients.", 20)
+    .AddOptionalArg("dct_type", "Discrete Cosine Transform type (1, 2, 3, 4).", 2)
+    .AddOptionalArg("normalize", "If set to True, the DCT uses an ortho-normal basis.", false)
+    .AddOptionalArg("axis", "Axis over which the transform is applied.", 0)
+    .AddOptionalArg("lifter", "Cepstral filtering (liftering) coefficient; 0 = none.", 0.0f);
+
+class MfccGPU : public SignalOpBase {
+ public:
+  explicit MfccGPU(const OpSpec &spec) : SignalOpBase(spec, "MFCC") {
+    args_.n_mfcc = spec.GetArgument<int>("n_mfcc");
+    DALI_ENFORCE(args_.n_mfcc > 0, "number of MFCCs should be > 0");
+    args_.dct_type = spec.GetArgument<int>("dct_type");
+    DALI_ENFORCE(args_.dct_type >= 1 && args_.dct_type <= 4, "Unsupported DCT type: ", args_.dct_type, ". Supported types are: 1, 2, 3, 4.");
+    args_.normalize = spec.GetArgument<bool>("normalize");
+    DALI_ENFORCE(!(args_.normalize && args_.dct_type == 1), "Ortho-normalization is not supported for DCT type I.");
+    axis_ = spec.GetArgument<int>("axis");
+    DALI_ENFORCE(axis_ >= 0, "Provided axis cannot be negative.");
+    args_.lifter = spec.GetArgument<float>("lifter");
+  }
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_FLOAT, "MFCC: unsupported data type");
+    const int nd = in.shape().sample_dim();
+    DALI_ENFORCE(axis_ < nd, "Axis ", axis_, " is out of bounds [0,", nd, ")");
+    DALI_ENFORCE(nd == 2 && axis_ == 0, "MFCC: the GPU path transforms axis 0 of 2-D (frequency, time) inputs");
+    const int n = in.num_samples();
+    std::vector<int64_t> shp(2 * n);
+    for (int i = 0; i < n; i++) { shp[2 * i] = in.shape().tensor_shape_span(i)[0]; shp[2 * i + 1] = in.shape().tensor_shape_span(i)[1]; }
+    CheckStatus(dalib200MfccSetup(plan_, &args_, n, shp.data()), name_);
+    out.resize(1);
+    out[0].type = DALI_FLOAT;
+    out[0].shape.resize(n, 2);
+    for (int i = 0; i < n; i++) out[0].shape.set_tensor_shape(i, { dalib200SignalOutputRows(plan_), shp[2 * i + 1] });
+    return true;
+  }
+  dalib200MfccArgs args_{};
+  int axis_ = 0;
+};
+DALI_REGISTER_OPERATOR(MFCC, MfccGPU, GPU);
+
+DALI_SCHEMA(Normalize)
+    .DocStr("Normalizes the input by removing the mean and dividing by the standard deviation (per sample, 2-D float inputs).")
+    .NumInput(1).NumOutput(1)
+    .AddOptionalArg("batch", "not supported by the GPU path (per-sample statistics only)", false)
+    .AddOptionalArgNoDefault("axes", "Indices of dimensions along which the input is normalized (default: all).")
+    .AddOptionalArgNoDefault("axis_names", "Names of the reduced axes in the input layout.")
+    .AddOptionalArg("shift", "The value to which the mean will map in the output.", 0.0f)
+    .AddOptionalArg("scale", "The scaling factor applied to the output.", 1.0f)
+    .AddOptionalArg("epsilon", "A value that is added to the variance.", 0.0f)
+    .AddOptionalArg("ddof", "Delta Degrees of Freedom for Bessel's correction.", 0)
+    .AddOptionalArg("dtype", "Output data type (FLOAT).", DALI_FLOAT);
+
+class NormalizeGPU : public SignalOpBase {
+ public:
+  explicit NormalizeGPU(const OpSpec &spec) : SignalOpBase(spec, "Normalize") {
+    DALI_ENFORCE(!spec.GetArgument<bool>("batch"), "Normalize: batch=True is not supported by the GPU path");
+    DALI_ENFORCE(spec.GetArgument<DALIDataType>("dtype") == DALI_FLOAT, "Normalize: the GPU path produces FLOAT output");
+    DALI_ENFORCE(!(spec.ArgumentDefined("axes") && spec.ArgumentDefined("axis_names")), "Arguments `axes` and `axis_names` are mutually exclusive");
+    args_.scale = spec.GetArgument<float>("scale"); args_.shift = spec.GetArgument<float>("shift");
+    args_.epsilon = spec.GetArgument<float>("epsilon"); args_.ddof = spec.GetArgument<int>("ddof");
+  }
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_FLOAT, "Normalize: the GPU path expects float input");
+    const int nd = in.shape().sample_dim();
+    DALI_ENFORCE(nd == 1 || nd == 2, "Normalize: the GPU path supports 1-D and 2-D inputs");
+    bool red[2] = { true, true };
+    if (spec_.ArgumentDefined("axes")) {
+      red[0] = red[1] = false;
+      for (int a : spec_.GetRepeatedArgument<int>("axes")) { DALI_ENFORCE(a >= 0 && a < nd, "Axis index out of range: ", a); red[nd == 1 ? 1 : a] = true; }
+    } else if (spec_.ArgumentDefined("axis_names")) {
+      red[0] = red[1] = false;
+      const std::string names = spec_.GetArgument<std::string>("axis_names"), lay = in.GetLayout().str();
+      for (char c : names) { const auto p = lay.find(c); DALI_ENFORCE(p != std::string::npos, "Axis '", std::string(1, c), "' not found in the input layout"); red[nd == 1 ? 1 : p] = true; }
+    }
+    if (nd == 1) red[0] = true;
+    DALI_ENFORCE(red[0] || red[1], "Normalize: at least one axis must be reduced");
+    args_.mode = red[0] && red[1] ? 0 : red[1] ? 1 : 2;
+    const int n = in.num_samples();
+    std::vector<int64_t> shp(2 * n);
+    for (int i = 0; i < n; i++) {
+      const int64_t *s = in.shape().tensor_shape_span(i);
+      shp[2 * i] = nd == 1 ? 1 : s[0]; shp[2 * i + 1] = nd == 1 ? s[0] : s[1];
+    }
+    CheckStatus(dalib200NormalizeSetup(plan_, &args_, n, shp.data()), name_);
+    out.resize(1);
+    out[0].shape = in.shape(); out[0].type = DALI_FLOAT;
+    return true;
+  }
+  dalib200NormalizeArgs args_{};
+};
+DALI_REGISTER_OPERATOR(Normalize, NormalizeGPU, GPU);
 
 }  // namespace dali
 

@@ -190,6 +190,8 @@ class Pipeline:
                 raise TypeError(f"Pipeline outputs must be DataNodes, got {type(o).__name__}")
         # prefetch_queue_depth independent executor slots (the reference's queue depth, exec2.h:66-131): while the GPU works on
         # batch i, the host parses / stages / uploads batch i+1 into the other slot.
+        for schema, inst, spec in self._nodes:
+            spec.add_arg("_state_key", f"{id(self)}:{inst}")       # operator instances of one node share their random state
         for _ in range(self._depth):
             be = backend.Pipeline(self.max_batch_size, self.num_threads, self.device_id)
             for g in self._externals:

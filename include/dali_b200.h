@@ -240,6 +240,54 @@ int dalib200MelPlanSetup(dalib200MelPlan *plan, const dalib200MelArgs *args, int
 int dalib200MelPlanSetTensorCores(dalib200MelPlan *plan, int enable);
 int dalib200MelLaunch(dalib200MelPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Audio tail behind Spectrogram / MelFilterBank: ToDecibels, MFCC (DCT + liftering), Normalize.
+ * Replaces kernels::signal::ToDecibelsGpu (dali/kernels/signal/decibel/to_decibels_gpu.cu), kernels::signal::dct::Dct1DGpu
+ * (dali/kernels/signal/dct/dct_gpu.cu) + the liftering of dali/operators/audio/mfcc/mfcc.cu, and the 2-D float case of
+ * kernels::NormalizeGPU (dali/kernels/normalize/normalize_gpu.cu); numerics follow the CPU kernels
+ * (to_decibels_cpu.cc:47-72, dct_cpu.cc:76-115, mfcc.cc:52-72). */
+typedef struct dalib200SignalPlan dalib200SignalPlan;
+typedef struct {
+  float multiplier, reference, cutoff_db;   /* dali/operators/signal/decibel/to_decibels_op.h:38-50 */
+  int32_t ref_max;                          /* no `reference` given: the per-sample maximum is the reference */
+} dalib200ToDecibelsArgs;
+typedef struct { int32_t n_mfcc, dct_type, normalize; float lifter; } dalib200MfccArgs;
+typedef struct {
+  int32_t mode;                             /* 0: reduce both axes, 1: reduce axis 1 (per row), 2: reduce axis 0 (per column) */
+  int32_t ddof;
+  float scale, shift, epsilon;
+} dalib200NormalizeArgs;
+
+int dalib200SignalPlanCreate(dalib200SignalPlan **plan, int max_batch);
+int dalib200SignalPlanDestroy(dalib200SignalPlan *plan);
+int dalib200ToDecibelsSetup(dalib200SignalPlan *plan, const dalib200ToDecibelsArgs *args, int n, const int64_t *volumes);
+/* shapes: n x 2 = (features, frames); the transform runs along axis 0; outputs are [min(n_mfcc, features)][frames] */
+int dalib200MfccSetup(dalib200SignalPlan *plan, const dalib200MfccArgs *args, int n, const int64_t *shapes);
+int dalib200SignalOutputRows(const dalib200SignalPlan *plan);
+int dalib200NormalizeSetup(dalib200SignalPlan *plan, const dalib200NormalizeArgs *args, int n, const int64_t *shapes);
+/* in_ptrs[i] / out_ptrs[i]: device f32 */
+int dalib200SignalLaunch(dalib200SignalPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small per-pixel / geometry helpers for interleaved u8 images:
+ *   multiply-add   out = ConvertSat<Out>(in * multiplier + addend)   -- brightness_contrast
+ *                  (kernels::MultiplyAddGpu, dali/kernels/imgproc/pointwise/multiply_add_gpu.h; CPU numerics multiply_add.h:47-60)
+ *   window copy    crop / slice / flip with out-of-bounds fill        -- fn.crop, fn.slice, fn.flip
+ *                  (kernels::SliceGPU / SliceFlipNormalizePermutePadGpu, dali/kernels/slice/) */
+typedef struct dalib200GenericPlan dalib200GenericPlan;
+typedef struct {
+  int32_t in_h, in_w, channels;
+  int32_t anchor_y, anchor_x, out_h, out_w;   /* window in input coordinates; may leave the image (filled) */
+  int32_t flip_x, flip_y;                     /* mirror the window horizontally / vertically */
+  uint8_t fill[4];                            /* per channel */
+} dalib200WindowSample;
+int dalib200GenericPlanCreate(dalib200GenericPlan **plan, int max_batch);
+int dalib200GenericPlanDestroy(dalib200GenericPlan *plan);
+int dalib200MultiplyAddSetup(dalib200GenericPlan *plan, int n, const int64_t *volumes, const float *multipliers,
+                             const float *addends, int out_dtype /* UINT8 | FLOAT */);
+int dalib200WindowCopySetup(dalib200GenericPlan *plan, int n, const dalib200WindowSample *samples);
+int dalib200GenericLaunch(dalib200GenericPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -416,3 +416,24 @@ def ref_random_crop(seed, sample_idx, H, W, aspect=(3 / 4, 4 / 3), area=(0.08, 1
     ref().ref_random_crop(C.c_int64(seed), int(sample_idx), int(H), int(W), C.c_float(aspect[0]), C.c_float(aspect[1]),
                           C.c_float(area[0]), C.c_float(area[1]), int(num_attempts), int(ncalls), w)
     return [tuple(w[4 * k:4 * k + 4]) for k in range(ncalls)]
+
+
+# ------------------------------------------------------------------------------------------- audio tail
+def ref_to_decibels(x, multiplier=10.0, reference=None, cutoff_db=-200.0):
+    """dali/kernels/signal/decibel/to_decibels_cpu.cc (compiled reference); reference=None -> per-sample maximum."""
+    a = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(a)
+    rc = ref().ref_to_decibels(_p(a), C.c_int64(a.size), _p(out), C.c_float(multiplier), C.c_float(reference if reference is not None else 1.0),
+                               C.c_float(cutoff_db), int(reference is None))
+    assert rc == 0
+    return out
+
+
+def ref_mfcc(mel, n_mfcc=20, dct_type=2, normalize=False, lifter=0.0):
+    """dali/kernels/signal/dct/dct_cpu.cc along axis 0 of [nfeat, ncols] + the liftering of dali/operators/audio/mfcc."""
+    a = np.ascontiguousarray(mel, np.float32)
+    nfeat, ncols = a.shape
+    out = np.empty((min(n_mfcc, nfeat), ncols), np.float32)
+    rows = ref().ref_mfcc(_p(a), nfeat, C.c_int64(ncols), _p(out), int(n_mfcc), int(dct_type), int(bool(normalize)), C.c_float(lifter))
+    assert rows == out.shape[0], rows
+    return out

@@ -60,3 +60,54 @@ int ref_mel_filter_bank_ft(const float *in, int nbin, int64_t nwin, float *out, 
 }
 
 }  // extern "C"
+
+// ---- audio tail (round 2): ToDecibelsCpu, Dct1DCpu, MFCC liftering coefficients
+#include "dali/kernels/signal/decibel/to_decibels_cpu.cc"   // NOLINT
+#include "dali/kernels/signal/dct/dct_cpu.cc"               // NOLINT
+#include "dali/operators/audio/mfcc/mfcc.h"                 // LifterCoeffs::CalculateCoeffs (private; built with -fno-access-control)
+
+extern "C" {
+
+int ref_to_decibels(const float *in, int64_t n, float *out, float multiplier, float reference, float cutoff_db, int ref_max) {
+  try {
+    signal::ToDecibelsCpu<float> k;
+    signal::ToDecibelsArgs<float> args;
+    args.multiplier = multiplier;
+    args.ref_max = ref_max != 0;
+    if (!args.ref_max) args.s_ref = reference;
+    args.min_ratio = std::pow(10.0f, cutoff_db / args.multiplier);          // to_decibels_op.h:47-50
+    if (args.min_ratio == 0) args.min_ratio = std::nextafter(0.0f, 1.0f);
+    KernelContext ctx;
+    InTensorCPU<float, DynamicDimensions> tin(in, TensorShape<>(n));
+    OutTensorCPU<float, DynamicDimensions> tout(out, TensorShape<>(n));
+    k.Setup(ctx, tin, args);
+    k.Run(ctx, tout, tin, args);
+    return 0;
+  } catch (...) { return -1; }
+}
+
+// in [nfeat][ncols] -> out [ndct][ncols] (axis 0), optional liftering (mfcc.cc:52-72)
+int ref_mfcc(const float *in, int nfeat, int64_t ncols, float *out, int n_mfcc, int dct_type, int normalize, float lifter) {
+  try {
+    signal::dct::Dct1DCpu<float, float, 2> k;
+    signal::dct::DctArgs args;
+    args.ndct = n_mfcc; args.dct_type = dct_type; args.normalize = normalize != 0;
+    KernelContext ctx;
+    InTensorCPU<float, 2> tin(in, TensorShape<2>(nfeat, ncols));
+    auto req = k.Setup(ctx, tin, args, 0);
+    auto sh = req.output_shapes[0][0];
+    OutTensorCPU<float, 2> tout(out, TensorShape<2>(sh[0], sh[1]));
+    k.Run(ctx, tout, tin, args, 0);
+    if (lifter != 0.0f) {
+      dali::detail::LifterCoeffs<dali::CPUBackend> lc;
+      lc.lifter_ = lifter;
+      std::vector<float> c(sh[0]);
+      lc.CalculateCoeffs(c.data(), 0, sh[0]);
+      for (int64_t r = 0; r < sh[0]; r++)
+        for (int64_t t = 0; t < sh[1]; t++) out[r * sh[1] + t] = c[r] * out[r * sh[1] + t];
+    }
+    return static_cast<int>(sh[0]);
+  } catch (...) { return -1; }
+}
+
+}  // extern "C"

@@ -179,3 +179,55 @@ def test_audio_golden(golden_dir):
     assert np.array_equal(bits(m), bits(gz["mel_128_16k_slaney_norm"]))
     (m2,) = g.mel_filter_bank([s32], 40, 16000.0, 20.0, 7600.0, "htk", False)
     assert np.array_equal(bits(m2), bits(gz["mel_40_16k_htk_nonorm"]))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# audio tail: to_decibels, mfcc, normalize through the public API
+def _audio_pipe(batch, source, build):
+    from dali_b200 import fn, pipeline_def
+
+    @pipeline_def(batch_size=batch, num_threads=1, device_id=0)
+    def pipe():
+        x = fn.external_source(source=lambda i: source, device="gpu", layout="ft")
+        return build(fn, x)
+    p = pipe()
+    p.build()
+    return [o.as_cpu() for o in p.run()]
+
+
+@pytest.mark.skipif(not po.have_ref(), reason="needs oracle/_ref")
+def test_to_decibels_and_mfcc_match_reference_cpu_kernels():
+    rng = np.random.default_rng(9)
+    mels = [np.abs(rng.normal(0, 1, (80, 37 + 50 * i))).astype(np.float32) ** 2 + 1e-9 for i in range(3)]
+    mels[1][3, 5] = 0.0                                                  # below the cut-off
+    a, b, c, d, e = _audio_pipe(3, mels, lambda fn, x: (
+        fn.to_decibels(x), fn.to_decibels(x, multiplier=20.0, reference=0.5, cutoff_db=-60.0),
+        fn.mfcc(fn.to_decibels(x, reference=1.0, cutoff_db=-80.0), n_mfcc=13, dct_type=2, normalize=True, lifter=22.0),
+        fn.mfcc(x, n_mfcc=40, dct_type=3), fn.mfcc(x, n_mfcc=7, dct_type=1)))
+    for i, m in enumerate(mels):
+        # stated tolerance of ToDecibels: device log2f vs glibc log2f, 1e-5 dB absolute + 1e-6 relative
+        assert np.allclose(a[i], po.ref_to_decibels(m), rtol=1e-6, atol=1e-5), i
+        assert np.allclose(b[i], po.ref_to_decibels(m, 20.0, 0.5, -60.0), rtol=1e-6, atol=1e-5), i
+        db = po.ref_to_decibels(m, 10.0, 1.0, -80.0)
+        want = po.ref_mfcc(db, 13, 2, True, 22.0)
+        assert c[i].shape == want.shape and np.allclose(c[i], want, rtol=0, atol=2e-4 * np.abs(want).max()), i     # inherits the dB tolerance
+        assert np.array_equal(d[i], po.ref_mfcc(m, 40, 3)), i           # the DCT itself is bit-exact (same order, same tables)
+        assert np.array_equal(e[i], po.ref_mfcc(m, 7, 1)), i
+    # the DCT on identical inputs, with liftering: bit-exact
+    (f,) = _audio_pipe(3, mels, lambda fn, x: (fn.mfcc(x, n_mfcc=20, lifter=10.0),))
+    for i, m in enumerate(mels):
+        assert np.array_equal(f[i], po.ref_mfcc(m, 20, 2, False, 10.0)), i
+
+
+def test_normalize_axes_ddof_epsilon():
+    rng = np.random.default_rng(10)
+    xs = [rng.normal(3.0, 2.0, (40, 25 + 9 * i)).astype(np.float32) for i in range(3)]
+    a, b, c = _audio_pipe(3, xs, lambda fn, x: (fn.normalize(x), fn.normalize(x, axes=[1], ddof=1, epsilon=1e-3),
+                                                fn.normalize(x, axis_names="f", scale=2.0, shift=0.5)))
+    for i, x in enumerate(xs):
+        x64 = x.astype(np.float64)
+        assert np.allclose(a[i], (x64 - x64.mean()) / x64.std(), rtol=1e-5, atol=1e-5), i
+        m, v = x64.mean(1, keepdims=True), x64.var(1, ddof=1, keepdims=True)
+        assert np.allclose(b[i], (x64 - m) / np.sqrt(v + 1e-3), rtol=1e-5, atol=1e-5), i
+        m, sd = x64.mean(0, keepdims=True), x64.std(0, keepdims=True)
+        assert np.allclose(c[i], 2.0 * (x64 - m) / sd + 0.5, rtol=1e-5, atol=1e-5), i

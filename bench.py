@@ -443,7 +443,9 @@ def main():
     alg = {"jpeg_unstuff_count": J, "jpeg_unstuff_scatter": 2 * J, "jpeg_huff_sync_intra": J, "jpeg_huff_sync_walk1": 0.3 * J, "jpeg_huff_sync_walk2": 0.08 * J,
            "jpeg_huff_sync_walk3": 0.03 * J,
            "jpeg_huff_write": J + coef_bytes, "jpeg_dc_scan": 2 * coef_bytes / 64, "jpeg_idct": coef_bytes + plane_bytes,
-           "jpeg_upsample_color": plane_bytes + ALG_DECODE, "resample_fused": ALG_RESIZE, "resample_stream": ALG_RESIZE, "cmn_hwc2chw": ALG_CMN}
+           "jpeg_upsample_color": plane_bytes + ALG_DECODE, "resample_fused": ALG_RESIZE, "resample_stream": ALG_RESIZE, "cmn_hwc2chw": ALG_CMN,
+           # decode -> resize without the RGB image: the 4:2:0 planes in (1.5 bytes per pixel), the resized image out
+           "resample_planar": plane_bytes + OUT * OUT * 3}
     roofline = None
     if dom is not None:
         dur = kernels[dom]["ms_per_step"] / max(1.0, kernels[dom]["launches_per_step"]) / 1e3

@@ -22,6 +22,8 @@ EXPORTS = [
     "dalib200JpegGetInfo", "dalib200JpegPlanCreate", "dalib200JpegPlanDestroy", "dalib200JpegPlanSetup",
     "dalib200JpegPlanGetInfo", "dalib200JpegPlanStagedBytes", "dalib200JpegUpload", "dalib200JpegLaunch",
     "dalib200JpegGetStatus", "dalib200JpegDebugGetCoefficients", "dalib200JpegPlanSetupEx", "dalib200JpegPlanGetOutputShape",
+    "dalib200JpegStatusAsync", "dalib200JpegStatusFetch", "dalib200JpegPlanGetPlanes", "dalib200JpegPlanSetPlanesOnly",
+    "dalib200ResamplePlanSetupPlanar", "dalib200ResampleLaunchPlanar",
     "dalib200ResamplePlanCreate", "dalib200ResamplePlanDestroy", "dalib200ResamplePlanSetup", "dalib200ResampleLaunch",
     "dalib200ResamplePlanGetOrder",
     "dalib200ResamplePlanGetPath",
@@ -48,7 +50,12 @@ class JpegParams(C.Structure):
 
 
 class JpegRoi(C.Structure):
-    _fields_ = [("use_roi", C.c_int32), ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32)]
+    _fields_ = [("use_roi", C.c_int32), ("x0", C.c_int32), ("y0", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32), ("planes_only", C.c_int32)]
+
+
+class PlanarImage(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("cb", C.c_void_p), ("cr", C.c_void_p), ("pitch_y", C.c_int32), ("pitch_c", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32), ("crop_x", C.c_int32), ("crop_y", C.c_int32)]
 
 
 class FilterDesc(C.Structure):

@@ -1,5 +1,6 @@
 // dali_b200/csrc/common.cu -- error state, descriptor arena, launch accounting.
 #include "common.cuh"
+#include <nvtx3/nvToolsExt.h>
 #include <cstring>
 
 namespace dalib200 {
@@ -65,13 +66,18 @@ static cudaEvent_t ProfEvent() {
   cudaEventCreate(&e);
   return e;
 }
+// NVTX range around every kernel launch (header-only nvtx3: a no-op unless a tool such as nsys / ncu injects the library), like the
+// reference's DomainTimeRange around operator Setup / Run (dali/pipeline/executor/executor2/exec_node_task.cc:291,314,
+// include/dali/core/nvtx.h:37-100).
 void ProfBegin(const char *name, cudaStream_t s) {
+  nvtxRangePushA(name);
   if (!g_prof_on) return;
   ProfRec r{name, ProfEvent(), ProfEvent()};
   cudaEventRecord(r.a, s);
   g_prof.push_back(r);
 }
 void ProfEnd(cudaStream_t s) {
+  nvtxRangePop();
   if (!g_prof_on || g_prof.empty()) return;
   cudaEventRecord(g_prof.back().b, s);
 }

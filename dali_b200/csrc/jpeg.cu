@@ -440,6 +440,7 @@ struct HuffCtx {
   int16_t *dc;             // compact DC array: one int16 per block, same block order as coef
   int log2_sub;            // log2 of the subsequence size in BITS
   int32_t *status;         // per image: 0 ok, 1 = block count mismatch (corrupt stream)
+  uint32_t *unit_nblk;     // per unit: blocks actually decoded (H2b), <= the unit's block count
   // live chains of the synchronisation: record = (bit position, c | z << 8 | t << 16, target subsequence, image)
   uint4 *chains[3];        // [0] filled by H1, [1] survivors of the first walk step, [2] survivors of the second
   uint32_t *chain_count;   // [3]
@@ -711,7 +712,10 @@ __global__ void __launch_bounds__(1024) huff_scan_kernel(HuffCtx cx) {
       __syncthreads();
     }
     // trailing pad bits may decode into a few extra symbols, so only a SHORT count is an error
-    if (threadIdx.x == 0 && (int64_t)carry * 64 < u.nslots) cx.status[blockIdx.x] = 1;
+    if (threadIdx.x == 0) {
+      if ((int64_t)carry * 64 < u.nslots) cx.status[blockIdx.x] = 1;
+      cx.unit_nblk[ui] = (uint32_t)min((int64_t)carry, u.nslots >> 6);
+    }
   }
 }
 
@@ -935,6 +939,23 @@ __global__ void __launch_bounds__(1024) dc_scan_kernel(const JpegImage *__restri
           }
       }
     }
+  }
+}
+
+// Truncated / corrupt entropy-coded data: libjpeg stops decoding when the data runs out and leaves the remaining MCUs as all-zero
+// coefficient blocks (jdhuff.c: insufficient_data -> the blocks keep the zeros of jzero_far, DC included), which decode to mid-gray.
+// The blocks behind the last decoded one of every short unit get exactly that: zero coefficients and an ABSOLUTE DC of zero (this
+// runs after the DC prediction).  One CTA per image; returns at once for intact images.
+__global__ void __launch_bounds__(256) truncation_fixup_kernel(HuffCtx cx) {
+  if (cx.status[blockIdx.x] == 0) return;
+  const JpegImage &im = cx.images[blockIdx.x];
+  uint4 *coef4 = reinterpret_cast<uint4 *>(cx.coef + im.coef_off);
+  int16_t *dcv = cx.dc + im.coef_off / 64;
+  for (int ui = im.unit_begin; ui < im.unit_end; ui++) {
+    const JpegUnit &u = cx.units[ui];
+    const int64_t b0 = (u.slot_base >> 6) + cx.unit_nblk[ui], b1 = (u.slot_base + u.nslots) >> 6;
+    for (int64_t q = b0 * 8 + threadIdx.x; q < b1 * 8; q += blockDim.x) coef4[q] = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t b = b0 + threadIdx.x; b < b1; b += blockDim.x) dcv[b] = 0;
   }
 }
 
@@ -1599,6 +1620,8 @@ void BuildDeviceTable(const HostHuff &h, uint32_t *lut, uint16_t *lut16, HuffSlo
 
 }  // namespace
 
+struct JpegGeo { int orient = 1, rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0, out_c = 3; bool direct = true, planar_ok = false; };
+
 struct dalib200JpegPlan {
   int max_batch = 0, n = 0;
   int output_type = DALIB200_RGB, fancy = 1, dtype = DALIB200_UINT8, adjust_orientation = 0;
@@ -1606,6 +1629,8 @@ struct dalib200JpegPlan {
   std::vector<int> post_sample;
   std::vector<size_t> post_off;             // byte offset of each post sample's window inside d_post
   std::vector<int32_t> out_shape;           // n x 3 (H, W, C) of the operator output
+  std::vector<uint8_t> planes_only;         // the sample's colour stage is skipped (the caller reads the planes)
+  std::vector<JpegGeo> geo;                 // per-sample output geometry (orientation, region of interest, eligibility)
   std::vector<int64_t> first_work;          // IDCT work list prefix
   int64_t total_work = 0, total_post_px = 0;
   size_t post_bytes = 0;
@@ -1642,6 +1667,8 @@ struct dalib200JpegPlan {
   int16_t *d_dc = nullptr; size_t d_dc_cap = 0;
   uint8_t *d_planes = nullptr; size_t d_planes_cap = 0;
   int32_t *d_status = nullptr; size_t d_status_cap = 0;
+  uint32_t *d_unit_nblk = nullptr; size_t d_unit_nblk_cap = 0;
+  int32_t *h_status = nullptr; size_t h_status_cap = 0;        // pinned copy of d_status (JpegStatusAsync / JpegStatusFetch)
   cudaEvent_t uploaded = nullptr, img_uploaded = nullptr;
   uint8_t *h_images = nullptr; size_t h_images_cap = 0;
   bool pending = false, img_pending = false, staged = false, smem_opted = false;
@@ -1662,6 +1689,51 @@ int GrowDevice(T *&ptr, size_t &cap, size_t need) {
 
 inline size_t Align(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+}  // namespace
+
+namespace {
+// Work lists that depend on the per-sample colour decision: post pass descriptors, colour work items, IDCT block ranges.  Run by
+// PlanSetupEx and again by JpegPlanSetPlanesOnly (cheap: O(batch)).
+void BuildWorkLists(dalib200JpegPlan *p) {
+  const int n = p->n;
+  p->posts.clear(); p->post_sample.clear(); p->post_off.clear();
+  int64_t work = 0, post_px = 0, quads = 0, items = 0;
+  size_t post_bytes = 0;
+  for (int i = 0; i < n; i++) {
+    JpegImage &im = p->images[i];
+    const ParsedJpeg &j = p->parsed[i];
+    const JpegGeo &ge = p->geo[i];
+    const bool planes_only = p->planes_only[i] != 0;
+    im.out_type = p->output_type;
+    if (!ge.direct && !planes_only) {
+      // the window is decoded to RGB (or to the Y plane for GRAY) into plan scratch; the post pass gathers / converts it
+      im.out_type = p->output_type == DALIB200_GRAY ? DALIB200_GRAY : DALIB200_RGB;
+      JpegPost po;
+      memset(&po, 0, sizeof(po));
+      po.src_w = im.win_w; po.src_c = ge.out_c == 1 ? 1 : 3;
+      po.img_w = j.width; po.img_h = j.height; po.win_x0 = im.win_x0; po.win_y0 = im.win_y0;
+      po.out_x0 = ge.rx0; po.out_y0 = ge.ry0; po.out_w = ge.rx1 - ge.rx0; po.out_h = ge.ry1 - ge.ry0;
+      po.orientation = ge.orient; po.out_type = p->output_type; po.dtype = p->dtype;
+      po.first_px = post_px;
+      post_px += (int64_t)po.out_w * po.out_h;
+      p->posts.push_back(po); p->post_sample.push_back(i); p->post_off.push_back(post_bytes);
+      post_bytes += Align((size_t)im.win_w * im.win_h * po.src_c, 256);
+    }
+    p->first_work[i] = work;
+    work += (int64_t)im.mcu_nx * im.mcu_ny * im.bpm;
+    im.fast_color = j.ncomp == 3 && !im.is_rgb && (im.out_type == DALIB200_RGB || im.out_type == DALIB200_BGR) &&
+                    ((j.hmax == 2 && j.vmax <= 2) || (j.hmax == 1 && j.vmax <= 2));
+    p->first_quad[i] = quads;
+    p->first_item[i] = items;
+    if (im.fast_color && p->fancy && j.hmax == 2 && j.vmax == 2 && (j.width + 1) / 2 > 2) im.fast_color = 2;    // 2-row patches
+    const int segs = (im.win_w + kColorSeg - 1) / kColorSeg;
+    if (planes_only) { im.fast_color = 1; }                               // owns no colour work items (fast path, zero items)
+    else if (im.fast_color == 2) items += (int64_t)segs * ((im.win_y0 + im.win_h) / 2 - (im.win_y0 + 1) / 2 + 1);
+    else if (im.fast_color) items += (int64_t)segs * im.win_h;
+    else quads += (int64_t)((im.win_w + 3) / 4) * im.win_h;
+  }
+  p->total_work = work; p->total_post_px = post_px; p->post_bytes = post_bytes; p->total_quads = quads; p->total_items = items;
+}
 }  // namespace
 
 extern "C" {
@@ -1693,8 +1765,9 @@ int dalib200JpegPlanDestroy(dalib200JpegPlan *p) {
   if (p->img_uploaded) { cudaEventSynchronize(p->img_uploaded); cudaEventDestroy(p->img_uploaded); }
   if (p->h_stage) cudaFreeHost(p->h_stage);
   if (p->h_images) cudaFreeHost(p->h_images);
+  if (p->h_status) cudaFreeHost(p->h_status);
   void *bufs[] = { p->d_stage, p->d_clean, p->d_chunk, p->d_unit_len, p->d_state, p->d_n, p->d_coef, p->d_dc, p->d_planes, p->d_status,
-                   p->d_chain1, p->d_chain2, p->d_chain3, p->d_chain_count, p->d_post, p->d_posts };
+                   p->d_chain1, p->d_chain2, p->d_chain3, p->d_chain_count, p->d_post, p->d_posts, p->d_unit_nblk };
   for (void *b : bufs) if (b) cudaFree(b);
   delete p;
   return DALIB200_SUCCESS;
@@ -1713,6 +1786,27 @@ int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *stre
   dalib200JpegParams prm;
   prm.output_type = output_type; prm.fancy_upsampling = fancy_upsampling; prm.dtype = DALIB200_UINT8; prm.adjust_orientation = 0;
   return dalib200JpegPlanSetupEx(p, n, streams, lengths, &prm, nullptr);
+}
+
+int dalib200JpegPlanSetPlanesOnly(dalib200JpegPlan *p, const uint8_t *want, uint8_t *granted) {
+  DB_CHECK_ARG(p && p->staged && want && granted, "JpegPlanSetPlanesOnly: call JpegPlanSetupEx first");
+  for (int i = 0; i < p->n; i++) { granted[i] = want[i] && p->geo[i].planar_ok; p->planes_only[i] = granted[i]; }
+  BuildWorkLists(p);
+  memcpy(p->h_stage + p->off_quads, p->first_quad.data(), sizeof(int64_t) * p->n);
+  memcpy(p->h_stage + p->off_items, p->first_item.data(), sizeof(int64_t) * p->n);
+  memcpy(p->h_stage + p->off_work, p->first_work.data(), sizeof(int64_t) * p->n);
+  return DALIB200_SUCCESS;
+}
+
+int dalib200JpegPlanGetPlanes(const dalib200JpegPlan *p, int sample, dalib200PlanarImage *out) {
+  DB_CHECK_ARG(p && out && sample >= 0 && sample < p->n && p->d_planes, "JpegPlanGetPlanes: call JpegLaunch first");
+  const JpegImage &im = p->images[sample];
+  DB_CHECK_ARG(im.ncomp == 3, "JpegPlanGetPlanes: sample %d has %d components", sample, im.ncomp);
+  out->y = p->d_planes + im.plane_off[0]; out->cb = p->d_planes + im.plane_off[1]; out->cr = p->d_planes + im.plane_off[2];
+  out->pitch_y = im.plane_w[0]; out->pitch_c = im.plane_w[1];
+  out->width = im.width; out->height = im.height;
+  out->crop_x = 0; out->crop_y = 0;
+  return DALIB200_SUCCESS;
 }
 
 int dalib200JpegPlanGetOutputShape(const dalib200JpegPlan *p, int sample, int32_t *hwc) {
@@ -1734,9 +1828,10 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
   p->dtype = prm->dtype; p->adjust_orientation = prm->adjust_orientation != 0;
   p->posts.clear(); p->post_sample.clear(); p->post_off.clear();
   p->out_shape.assign((size_t)3 * n, 0);
+  p->planes_only.assign(n, 0);
+  p->geo.assign(n, JpegGeo());
   p->first_work.assign(n, 0);
-  int64_t work = 0, post_px = 0;
-  size_t post_bytes = 0;
+
   p->parsed.assign(n, ParsedJpeg());
   p->images.assign(n, JpegImage());
   p->units.clear(); p->tables.clear(); p->quants.clear(); p->src_ptr.clear(); p->block_image.clear(); p->wblock_image.clear();
@@ -1745,7 +1840,7 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
   std::map<std::string, int> table_cache, quant_cache;
   size_t raw = 0, clean = 0;
   uint32_t chunks = 0;
-  int64_t subseq = 0, coefs = 0, planes = 0, quads = 0, items = 0;
+  int64_t subseq = 0, coefs = 0, planes = 0;
   int sync_blocks = 0, write_blocks = 0;
   // subsequence size: the longer, the fewer re-decodes until the chains lock onto the MCU phase; aim for >= ~200k
   // subsequences per batch (a full B200 holds 300k threads), between 32 and 256 bytes
@@ -1881,7 +1976,8 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
     im.coef_off = coefs;
     coefs += nmcu * bpm * 64;
     for (int c = 0; c < j.ncomp; c++) {
-      im.plane_w[c] = im.mcux * j.hs[c] * 8; im.plane_h[c] = im.mcuy * j.vs[c] * 8;
+      // pitch: a multiple of 16 bytes, so that every plane row can be the source of a TMA bulk copy (resample_planar_kernel)
+      im.plane_w[c] = (int)Align((size_t)im.mcux * j.hs[c] * 8, 16); im.plane_h[c] = im.mcuy * j.vs[c] * 8;
       im.plane_off[c] = planes;
       planes += Align((size_t)im.plane_w[c] * im.plane_h[c], 16);
     }
@@ -1921,45 +2017,30 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
     p->out_shape[3 * i] = ry1 - ry0; p->out_shape[3 * i + 1] = rx1 - rx0; p->out_shape[3 * i + 2] = out_c;
     im.win_x0 = sx0 & ~7; im.win_y0 = sy0;
     im.win_w = std::min(W, (sx1 + 7) & ~7) - im.win_x0; im.win_h = sy1 - sy0;
-    const bool direct = orient == 1 && p->dtype == DALIB200_UINT8 && output_type != DALIB200_YCbCr &&
-                        im.win_x0 == sx0 && im.win_x0 + im.win_w == sx1;
-    if (!direct) {
-      // the window is decoded to RGB (or to the Y plane for GRAY) into plan scratch; the post pass gathers / converts it
-      im.out_type = output_type == DALIB200_GRAY ? DALIB200_GRAY : DALIB200_RGB;
-      JpegPost po;
-      memset(&po, 0, sizeof(po));
-      po.src_w = im.win_w; po.src_c = out_c == 1 ? 1 : 3;
-      po.img_w = W; po.img_h = H; po.win_x0 = im.win_x0; po.win_y0 = im.win_y0;
-      po.out_x0 = rx0; po.out_y0 = ry0; po.out_w = rx1 - rx0; po.out_h = ry1 - ry0;
-      po.orientation = orient; po.out_type = output_type; po.dtype = p->dtype;
-      po.first_px = post_px;
-      post_px += (int64_t)po.out_w * po.out_h;
-      p->posts.push_back(po); p->post_sample.push_back(i); p->post_off.push_back(post_bytes);
-      post_bytes += Align((size_t)im.win_w * im.win_h * po.src_c, 256);
+    JpegGeo &ge = p->geo[i];
+    ge.orient = orient; ge.rx0 = rx0; ge.ry0 = ry0; ge.rx1 = rx1; ge.ry1 = ry1; ge.out_c = out_c;
+    ge.direct = orient == 1 && p->dtype == DALIB200_UINT8 && output_type != DALIB200_YCbCr && im.win_x0 == sx0 && im.win_x0 + im.win_w == sx1;
+    // decode -> resize without the RGB image (the caller consumes the planes): 4:2:0 YCbCr, fancy upsampling, plain RGB u8 request
+    ge.planar_ok = j.ncomp == 3 && !im.is_rgb && j.hmax == 2 && j.vmax == 2 && p->fancy && orient == 1 && j.width > 4 &&
+                   output_type == DALIB200_RGB && p->dtype == DALIB200_UINT8;
+    const bool planes_only = rois && rois[i].planes_only;
+    if (planes_only && !ge.planar_ok) {
+      SetLastError("decoders.image: sample %d: planes_only needs a 3-component 4:2:0 YCbCr stream without orientation, RGB u8 output", i);
+      return DALIB200_ERROR_UNSUPPORTED;
     }
+    p->planes_only[i] = planes_only;
     // MCUs the IDCT has to produce: the window plus the neighbours the (fancy) chroma upsampling reads
     {
       const int mw = 8 * j.hmax, mh = 8 * j.vmax, ex = 2 * j.hmax, ey = 2 * j.vmax;
       const int mx0 = std::max(0, im.win_x0 - ex) / mw, mx1 = std::min(im.mcux - 1, (im.win_x0 + im.win_w - 1 + ex) / mw);
       const int my0 = std::max(0, im.win_y0 - ey) / mh, my1 = std::min(im.mcuy - 1, (im.win_y0 + im.win_h - 1 + ey) / mh);
       im.mcu_x0 = mx0; im.mcu_y0 = my0; im.mcu_nx = mx1 - mx0 + 1; im.mcu_ny = my1 - my0 + 1;
-      p->first_work[i] = work;
-      work += (int64_t)im.mcu_nx * im.mcu_ny * bpm;
     }
-    im.fast_color = j.ncomp == 3 && !im.is_rgb && (im.out_type == DALIB200_RGB || im.out_type == DALIB200_BGR) &&
-                    ((j.hmax == 2 && j.vmax <= 2) || (j.hmax == 1 && j.vmax <= 2));
-    p->first_quad[i] = quads;
-    p->first_item[i] = items;
-    if (im.fast_color && p->fancy && j.hmax == 2 && j.vmax == 2 && (j.width + 1) / 2 > 2) im.fast_color = 2;    // 2-row patches
-    const int segs = (im.win_w + kColorSeg - 1) / kColorSeg;
-    if (im.fast_color == 2) items += (int64_t)segs * ((im.win_y0 + im.win_h) / 2 - (im.win_y0 + 1) / 2 + 1);
-    else if (im.fast_color) items += (int64_t)segs * im.win_h;
-    else quads += (int64_t)((im.win_w + 3) / 4) * im.win_h;
   }
-  p->total_work = work; p->total_post_px = post_px; p->post_bytes = post_bytes;
+  BuildWorkLists(p);
   DB_CHECK_ARG(raw < (1ull << 32) && clean < (1ull << 32), "decoders.image: batch of encoded data exceeds 4 GiB");
   p->raw_bytes = raw; p->clean_bytes = clean; p->nchunks = chunks;
-  p->total_subseq = subseq; p->total_coefs = coefs; p->total_plane_bytes = planes; p->total_quads = quads; p->total_items = items;
+  p->total_subseq = subseq; p->total_coefs = coefs; p->total_plane_bytes = planes;
   p->total_blocks_sync = sync_blocks; p->total_blocks_write = write_blocks;
   // ---- pack descriptors + raw scan bytes into pinned staging
   size_t off = 0;
@@ -2023,6 +2104,26 @@ int dalib200JpegGetStatus(dalib200JpegPlan *p, int32_t *status_out) {
   DB_CHECK_ARG(p && status_out && p->d_status, "JpegGetStatus: bad arguments");
   DB_CUDA(cudaDeviceSynchronize());
   DB_CUDA(cudaMemcpy(status_out, p->d_status, sizeof(int32_t) * p->n, cudaMemcpyDeviceToHost));
+  return DALIB200_SUCCESS;
+}
+
+// Asynchronous variant: enqueues the copy of the per-sample status words into a pinned buffer of the plan; JpegStatusFetch reads
+// that buffer without synchronising (valid once the stream has been synchronised by the caller, e.g. at Pipeline outputs()).
+int dalib200JpegStatusAsync(dalib200JpegPlan *p, dalib200Stream_t stream) {
+  DB_CHECK_ARG(p && p->d_status, "JpegStatusAsync: nothing has been launched");
+  if ((size_t)p->n > p->h_status_cap) {
+    if (p->h_status) cudaFreeHost(p->h_status);
+    p->h_status = nullptr; p->h_status_cap = 0;
+    DB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p->h_status), sizeof(int32_t) * p->max_batch));
+    p->h_status_cap = p->max_batch;
+  }
+  DB_CUDA(cudaMemcpyAsync(p->h_status, p->d_status, sizeof(int32_t) * p->n, cudaMemcpyDeviceToHost, stream));
+  return DALIB200_SUCCESS;
+}
+
+int dalib200JpegStatusFetch(const dalib200JpegPlan *p, int32_t *status_out, int n) {
+  DB_CHECK_ARG(p && status_out && p->h_status && n <= (int)p->h_status_cap, "JpegStatusFetch: call JpegStatusAsync first");
+  for (int i = 0; i < n; i++) status_out[i] = p->h_status[i];
   return DALIB200_SUCCESS;
 }
 
@@ -2101,6 +2202,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   if ((rc = GrowDevice(p->d_dc, p->d_dc_cap, (size_t)p->total_coefs / 64 + 64))) return rc;
   if ((rc = GrowDevice(p->d_planes, p->d_planes_cap, (size_t)p->total_plane_bytes + 64))) return rc;
   if ((rc = GrowDevice(p->d_status, p->d_status_cap, (size_t)p->n + 1))) return rc;
+  if ((rc = GrowDevice(p->d_unit_nblk, p->d_unit_nblk_cap, p->units.size() + 1))) return rc;
   if (!p->posts.empty()) {
     if ((rc = GrowDevice(p->d_post, p->d_post_cap, p->post_bytes + 256))) return rc;
     if ((rc = GrowDevice(p->d_posts, p->d_posts_cap, p->posts.size()))) return rc;
@@ -2158,7 +2260,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   cx.wblock_image = reinterpret_cast<const int32_t *>(p->d_stage + p->off_wblkimg);
   cx.units = d_units; cx.unit_clean_len = p->d_unit_len; cx.tables = d_tables;
   cx.clean = p->d_clean; cx.s_state = p->d_state; cx.s_n = p->d_n; cx.coef = p->d_coef; cx.dc = p->d_dc; cx.log2_sub = p->log2_sub;
-  cx.status = p->d_status;
+  cx.status = p->d_status; cx.unit_nblk = p->d_unit_nblk;
   cx.chains[0] = p->d_chain1; cx.chains[1] = p->d_chain2; cx.chains[2] = p->d_chain3; cx.chain_count = p->d_chain_count;
   const size_t hsmem = sync_smem_bytes(p->log2_sub, false), wsmem = write_smem_bytes(p->log2_sub);
   const size_t walk_smem = kLutWords * 4 + 4 * sizeof(HuffSlow) + (size_t)(kTailColWords + kMaxBlocksPerMcu) * kTailThreads * 4;
@@ -2188,6 +2290,8 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   CountLaunch();
   { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_write, kWriteThreads, wsmem, s>>>(cx); }
   { ProfScope ps_("jpeg_dc_scan", s); dc_scan_kernel<<<p->n, 1024, 0, s>>>(d_images, p->d_dc); }
+  { ProfScope ps_("jpeg_truncation_fixup", s); truncation_fixup_kernel<<<p->n, 256, 0, s>>>(cx); }
+  CountLaunch();
   {
     const int64_t total_blocks = p->total_work;
     const auto *d_work = reinterpret_cast<const int64_t *>(p->d_stage + p->off_work);

@@ -131,6 +131,10 @@ struct RsDesc {
   int32_t tile_walk;         // the tile kernel may use the row walk (tile step count fits)
   int32_t walk_slots;        // > 0: vertical pass by the row walk with this many accumulator slots (see walk_vertical_u8)
   int64_t first_tile;
+  // planar 4:2:0 YCbCr source (decoder planes, see resample_planar_kernel): the sample is the window [crop_y, +in_h) x [crop_x, +in_w)
+  // of an img_h x img_w image
+  const uint8_t *pl[3];
+  int32_t pitch_y, pitch_c, img_w, img_h, crop_x, crop_y;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -682,6 +686,243 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
   }
 }
 
+// =============================================================================================
+// PLANAR variant of the streaming kernel: decode -> resize without the RGB image.
+//
+// The source is the decoder's planar 4:2:0 output (Y at full, Cb / Cr at half resolution); the strip's rows are streamed through the
+// ring as [Y row | Cb near | Cb far | Cr near | Cr far] (five bulk copies per row, near / far = the two chroma rows libjpeg's h2v2
+// fancy upsampling blends for that luma row).  A consumer thread owns two neighbouring pixels (one chroma column): it forms the
+// vertically blended chroma of its column and the two next to it, the horizontally blended values of its two pixels, converts to RGB
+// with libjpeg's fixed-point coefficients (jdcolor.c, SCALEBITS 16), and feeds the six bytes straight into the row walk as
+// 2^23 + b floats -- the decoded RGB image (6.2 MB per 1080p sample, written and read back by the two-kernel path) never exists.
+// Everything behind that point (slots, parking, horizontal pass, rounding flags) is the streaming kernel's.
+// Bit-exact with decode-then-resize: the per-pixel arithmetic is the colour kernel's, the filter arithmetic the streaming kernel's.
+constexpr int kPlPx = 512;                 // strip width in pixels (2 per consumer thread)
+constexpr int kPlChroma = kPlPx / 2 + 32;  // chroma samples per slot row (16 of halo on each side, 16-byte granules)
+constexpr int kPlSlot = kPlPx + 4 * kPlChroma;
+constexpr int kPlStages = 16;
+constexpr int kPlSmemBytes = kStTH * kPlPx * 3 * 4 + kPlStages * kPlSlot + kWalkMax * kWalkSlots * 16 + kWalkMax * 4 + 2 * kPlStages * 8;
+
+struct PlanarGeom { int px0, npx, c0, e0; };
+__device__ __forceinline__ PlanarGeom planar_geom(const RsDesc &d, const int32_t *idx_x, int ox0, int tw) {
+  const int ia = idx_x[ox0], ib = idx_x[ox0 + tw - 1];
+  const int bx = d.base[0], ex = d.extent[0], Sx = d.support[0];
+  const int cmin = d.crop_x + bx + min(max(min(ia, ib), 0), ex - 1);
+  const int cmax = d.crop_x + bx + min(max(max(ia, ib) + Sx - 1, 0), ex - 1);
+  PlanarGeom g;
+  g.px0 = cmin & ~31;
+  g.npx = ((cmax + 1 - g.px0) + 31) & ~31;
+  g.c0 = max((g.px0 >> 1) - 16, 0);
+  g.e0 = (g.px0 - d.crop_x) * 3;
+  return g;
+}
+
+template <int WMAX>
+__global__ void __launch_bounds__(kStThreads, 2) resample_planar_kernel(const RsDesc *__restrict__ descs, const int32_t *__restrict__ tab,
+                                                                        const RsItem *__restrict__ items, int nitems) {
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  float *tmp2 = reinterpret_cast<float *>(st_smem);                               // [4 row pairs][RE][2]
+  uint8_t *ring = st_smem + kStTH * kPlPx * 3 * 4;
+  float2 (*ent)[kWalkSlots] = reinterpret_cast<float2 (*)[kWalkSlots]>(ring + kPlStages * kPlSlot);
+  uint32_t *fin = reinterpret_cast<uint32_t *>(ring + kPlStages * kPlSlot + kWalkMax * kWalkSlots * 16);
+  uint64_t *full = reinterpret_cast<uint64_t *>(fin + kWalkMax);
+  uint64_t *empty = full + kPlStages;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < kPlStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kStConsumers / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid >= kStConsumers) {
+    // ------------------------------------------------------------------ producer warp: one lane issues the bulk copies
+    if (tid == kStConsumers) {
+      uint32_t stage = 0, par = 1;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const RsItem it = items[item];
+        const RsDesc &d = descs[it.sample];
+        const int32_t *idx_x = tab + d.idx_off[0], *idx_y = tab + d.idx_off[1];
+        const int Sy = d.support[1], by = d.base[1], ey = d.extent[1];
+        const PlanarGeom g = planar_geom(d, idx_x, it.ox0, it.tw);
+        const int dh = (d.img_h + 1) >> 1;
+        const uint32_t ybytes = (uint32_t)min(g.npx, d.pitch_y - g.px0);
+        const uint32_t cbytes = (uint32_t)min(g.npx / 2 + 32, d.pitch_c - g.c0);
+        const int ustart = idx_y[it.oy0], uend = idx_y[it.oy1 - 1] + Sy - 1;
+        for (int u = ustart; u <= uend; u++) {
+          mbar_wait(&empty[stage], par);
+          mbar_expect_tx(&full[stage], ybytes + 4u * cbytes);
+          const int fy = d.crop_y + by + min(max(u, 0), ey - 1);
+          const int rn = fy >> 1;
+          const int rf = min(max((fy & 1) ? rn + 1 : rn - 1, 0), dh - 1);
+          uint8_t *slot = ring + stage * kPlSlot;
+          bulk_g2s(slot, d.pl[0] + (int64_t)fy * d.pitch_y + g.px0, ybytes, &full[stage]);
+          bulk_g2s(slot + kPlPx, d.pl[1] + (int64_t)rn * d.pitch_c + g.c0, cbytes, &full[stage]);
+          bulk_g2s(slot + kPlPx + kPlChroma, d.pl[1] + (int64_t)rf * d.pitch_c + g.c0, cbytes, &full[stage]);
+          bulk_g2s(slot + kPlPx + 2 * kPlChroma, d.pl[2] + (int64_t)rn * d.pitch_c + g.c0, cbytes, &full[stage]);
+          bulk_g2s(slot + kPlPx + 3 * kPlChroma, d.pl[2] + (int64_t)rf * d.pitch_c + g.c0, cbytes, &full[stage]);
+          if (++stage == kPlStages) { stage = 0; par ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- consumers
+  const int lane = tid & 31;
+  const uint32_t a_ring = smem_u32(ring);
+  uint32_t stage = 0, par = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const RsItem it = items[item];
+    const RsDesc &d = descs[it.sample];
+    const int C = 3, Sx = d.support[0], Sy = d.support[1], W = d.walk_slots;
+    const int32_t *idx_x = tab + d.idx_off[0], *idx_y = tab + d.idx_off[1];
+    const float *coef_x = reinterpret_cast<const float *>(tab + d.coef_off[0]);
+    const float *coef_y = reinterpret_cast<const float *>(tab + d.coef_off[1]);
+    const int bx = d.base[0], ex = d.extent[0];
+    const PlanarGeom g = planar_geom(d, idx_x, it.ox0, it.tw);
+    const int RE = g.npx * 3;
+    const uint8_t *flags = d.flags_off >= 0 ? reinterpret_cast<const uint8_t *>(tab + d.flags_off) : nullptr;
+    uint8_t *out = static_cast<uint8_t *>(d.out);
+    const int ustart = idx_y[it.oy0];
+    const bool okw = 2 * tid < g.npx;
+    // chroma column of this thread and the edge rules of h2v2 fancy upsampling (jdsample.c)
+    const int ci = (g.px0 >> 1) + tid, dw = (d.img_w + 1) >> 1;
+    const bool first_col = ci == 0, last_col = ci >= dw - 1;
+    const uint32_t coff = (uint32_t)(ci - g.c0);                    // position inside the chroma slot rows
+    const uint32_t o_prev = first_col ? coff : coff - 1u, o_next = coff + 1u;
+    float2 acc[WMAX][3];
+#pragma unroll
+    for (int s = 0; s < WMAX; s++)
+#pragma unroll
+      for (int q = 0; q < 3; q++) acc[s][q] = make_float2(0.f, 0.f);
+
+    for (int cy0 = it.oy0; cy0 < it.oy1; cy0 += kStTH) {
+      const int th = min(kStTH, it.oy1 - cy0);
+      const int cs = cy0 == it.oy0 ? ustart : idx_y[cy0 - 1] + Sy;
+      const int J = idx_y[cy0 + th - 1] + Sy - cs;
+      // ---- chunk tables
+      for (int e = tid; e < J * kWalkSlots; e += kStConsumers) (&ent[0][0])[e] = make_float2(0.f, 0.f);
+      for (int j = tid; j < J; j += kStConsumers) fin[j] = 0xFFFFFFFFu;
+      consumer_bar();
+      for (int e = tid; e < (th + kWalkSlots) * Sy; e += kStConsumers) {
+        const int tl = e / Sy, k = e - tl * Sy, t = cy0 + tl;
+        if (t < it.oy1) {
+          const int j = idx_y[t] + k - cs;
+          if (j >= 0 && j < J) {
+            const float c = coef_y[(int64_t)t * Sy + k];
+            ent[j][t % W] = make_float2(c, mul_rn(c, -8388608.0f));
+            if (k == Sy - 1) reinterpret_cast<uint8_t *>(&fin[j])[t % W] = (uint8_t)tl;
+          }
+        }
+      }
+      consumer_bar();
+      // ---- stage A: row walk over the ring, pixels produced on the fly
+      for (int j = 0; j < J; j++) {
+        mbar_wait(&full[stage], par);
+        const uint32_t a_slot = a_ring + stage * kPlSlot;
+        const uint32_t yw = lds_u16(a_slot + 2u * tid);
+        uint32_t cbn[3], cbf[3], crn[3], crf[3];
+        {
+          const uint32_t a_c = a_slot + kPlPx;
+          cbn[0] = lds_u8(a_c + o_prev); cbn[1] = lds_u8(a_c + coff); cbn[2] = lds_u8(a_c + o_next);
+          cbf[0] = lds_u8(a_c + kPlChroma + o_prev); cbf[1] = lds_u8(a_c + kPlChroma + coff); cbf[2] = lds_u8(a_c + kPlChroma + o_next);
+          crn[0] = lds_u8(a_c + 2 * kPlChroma + o_prev); crn[1] = lds_u8(a_c + 2 * kPlChroma + coff); crn[2] = lds_u8(a_c + 2 * kPlChroma + o_next);
+          crf[0] = lds_u8(a_c + 3 * kPlChroma + o_prev); crf[1] = lds_u8(a_c + 3 * kPlChroma + coff); crf[2] = lds_u8(a_c + 3 * kPlChroma + o_next);
+        }
+        // release the slot once the values have ARRIVED in registers (see resample_stream_kernel)
+        asm volatile("fence.proxy.async.shared::cta;" :: "r"(yw), "r"(crf[2]) : "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == kPlStages) { stage = 0; par ^= 1u; }
+        float2 cd[kWalkSlots];
+        {
+          const float4 e01 = *reinterpret_cast<const float4 *>(&ent[j][0]);
+          cd[0] = make_float2(e01.x, e01.y); cd[1] = make_float2(e01.z, e01.w);
+          if (WMAX > 2) {
+            const float4 e23 = *reinterpret_cast<const float4 *>(&ent[j][2]);
+            cd[2] = make_float2(e23.x, e23.y); cd[3] = make_float2(e23.z, e23.w);
+          }
+        }
+        // chroma: vertical blend 3 * near + far of the three columns, then the horizontal blend of the two pixels
+        int cb[2], cr[2];
+        {
+          const int b0 = 3 * (int)cbn[0] + (int)cbf[0], b1 = 3 * (int)cbn[1] + (int)cbf[1], b2 = 3 * (int)cbn[2] + (int)cbf[2];
+          const int r0 = 3 * (int)crn[0] + (int)crf[0], r1 = 3 * (int)crn[1] + (int)crf[1], r2 = 3 * (int)crn[2] + (int)crf[2];
+          cb[0] = first_col ? (b1 * 4 + 8) >> 4 : (b1 * 3 + b0 + 8) >> 4;
+          cb[1] = last_col ? (b1 * 4 + 7) >> 4 : (b1 * 3 + b2 + 7) >> 4;
+          cr[0] = first_col ? (r1 * 4 + 8) >> 4 : (r1 * 3 + r0 + 8) >> 4;
+          cr[1] = last_col ? (r1 * 4 + 7) >> 4 : (r1 * 3 + r2 + 7) >> 4;
+        }
+        uint32_t m[6];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const int yy = (int)((yw >> (8 * k)) & 0xFFu);
+          const int cbm = cb[k] - 128, crm = cr[k] - 128;
+          const int r = yy + ((91881 * crm + 32768) >> 16);
+          const int gq = yy + ((-22554 * cbm + 32768 - 46802 * crm) >> 16);
+          const int b = yy + ((116130 * cbm + 32768) >> 16);
+          m[3 * k] = 0x4B000000u | (uint32_t)min(max(r, 0), 255);
+          m[3 * k + 1] = 0x4B000000u | (uint32_t)min(max(gq, 0), 255);
+          m[3 * k + 2] = 0x4B000000u | (uint32_t)min(max(b, 0), 255);
+        }
+        const float2 m01 = make_float2(__uint_as_float(m[0]), __uint_as_float(m[1]));
+        const float2 m23 = make_float2(__uint_as_float(m[2]), __uint_as_float(m[3]));
+        const float2 m45 = make_float2(__uint_as_float(m[4]), __uint_as_float(m[5]));
+#pragma unroll
+        for (int s = 0; s < WMAX; s++) {
+          const float2 c2 = make_float2(cd[s].x, cd[s].x), d2 = make_float2(cd[s].y, cd[s].y);
+          acc[s][0] = add2_rn(acc[s][0], fma2_rn(m01, c2, d2));
+          acc[s][1] = add2_rn(acc[s][1], fma2_rn(m23, c2, d2));
+          acc[s][2] = add2_rn(acc[s][2], fma2_rn(m45, c2, d2));
+        }
+        const uint32_t f = fin[j];
+        if (f != 0xFFFFFFFFu) {
+#pragma unroll
+          for (int s = 0; s < WMAX; s++) {
+            const uint32_t tl = (f >> (8 * s)) & 0xFFu;
+            if (tl != 0xFFu) {
+              if (okw) {
+                float *p6 = tmp2 + ((size_t)(tl >> 1) * RE) * 2 + (tl & 1u) + 12 * tid;
+                p6[0] = acc[s][0].x; p6[2] = acc[s][0].y; p6[4] = acc[s][1].x; p6[6] = acc[s][1].y; p6[8] = acc[s][2].x; p6[10] = acc[s][2].y;
+              }
+              acc[s][0] = acc[s][1] = acc[s][2] = make_float2(0.f, 0.f);
+            }
+          }
+        }
+      }
+      consumer_bar();
+      // ---- stage B: horizontal pass of the chunk's th rows, two rows per packed operation (as in resample_stream_kernel)
+      const int npair = (th + 1) >> 1;
+      for (int e = tid; e < it.tw * C; e += kStConsumers) {
+        const int x = e / C, c = e - x * C;
+        const int ox = it.ox0 + x;
+        const int i0 = idx_x[ox];
+        const float *cx = coef_x + (int64_t)ox * Sx;
+        const bool he = flags ? flags[ox] != 0 : false;
+        float2 a[kStTH / 2];
+#pragma unroll
+        for (int p = 0; p < kStTH / 2; p++) a[p] = make_float2(0.f, 0.f);
+        const float2 nz = make_float2(d.neg_zero, d.neg_zero);
+        const bool interior = i0 >= 0 && i0 + Sx <= ex;
+        const int col0 = (bx + i0) * C + c - g.e0;
+        for (int k = 0; k < Sx; k++) {
+          const int col = interior ? col0 + k * C : (bx + min(max(i0 + k, 0), ex - 1)) * C + c - g.e0;
+          const float ck = cx[k];
+          const float2 c2 = make_float2(ck, ck);
+          const float2 *src = reinterpret_cast<const float2 *>(tmp2) + col;
+#pragma unroll
+          for (int p = 0; p < kStTH / 2; p++)
+            if (p < npair) a[p] = add2_rn(a[p], fma2_rn(src[(size_t)p * RE], c2, nz));
+        }
+#pragma unroll
+        for (int p = 0; p < kStTH / 2; p++) {
+          const int t0 = 2 * p;
+          if (t0 < th) out[((int64_t)(cy0 + t0) * d.out_w + ox) * C + c] = rs_store_cvt<uint8_t>(a[p].x, he);
+          if (t0 + 1 < th) out[((int64_t)(cy0 + t0 + 1) * d.out_w + ox) * C + c] = rs_store_cvt<uint8_t>(a[p].y, he);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace dalib200
 
 using namespace dalib200;  // NOLINT
@@ -719,7 +960,8 @@ struct dalib200ResamplePlan {
   bool tables_dirty = true;
   cudaEvent_t uploaded = nullptr;
   bool pending = false;
-  bool smem_opted[10] = { false, false, false, false, false, false, false, false, false, false };
+  bool smem_opted[13] = { false, false, false, false, false, false, false, false, false, false, false, false, false };
+  bool planar_mode = false;                    // strips sized for resample_planar_kernel (set by ...SetupPlanar)
 };
 
 namespace {
@@ -1001,6 +1243,9 @@ int dalib200ResamplePlanSetup(dalib200ResamplePlan *p, int n, const dalib200Resa
           int a = ix[o0], b = ix[o0 + cnt - 1];
           int cmin = d.base[0] + std::min(std::max(std::min(a, b), 0), d.extent[0] - 1);
           int cmax = d.base[0] + std::min(std::max(std::max(a, b) + Sx - 1, 0), d.extent[0] - 1);
+          // planar source: the strip is at most kPlPx pixels wide after aligning its start down and its width up to 32 pixels
+          // (the crop offset is only known at launch: worst-case slack), expressed on the kStRowBytes scale
+          if (p->planar_mode) return (cmax - cmin + 1 + 62 <= kPlPx) ? kStRowBytes : kStRowBytes + 1;
           return (((cmax + 1) * C + 15) & ~15) - ((cmin * C) & ~15);
         };
         int stw = 0;
@@ -1034,6 +1279,91 @@ int dalib200ResamplePlanSetup(dalib200ResamplePlan *p, int n, const dalib200Resa
   p->n = n; p->in_dtype = in_dtype; p->out_dtype = out_dtype; p->total_tiles = tiles;
   // identical tables (the common fixed-size case) are not uploaded again
   p->tables_dirty = p->tables != p->uploaded_tables;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200ResamplePlanSetupPlanar(dalib200ResamplePlan *p, int n, const dalib200ResampleSample *samples, uint8_t *planar_ok) {
+  DB_CHECK_ARG(p && samples && planar_ok, "ResamplePlanSetupPlanar: null argument");
+  p->planar_mode = true;
+  const int rc = dalib200ResamplePlanSetup(p, n, samples, DALIB200_UINT8, DALIB200_UINT8);
+  p->planar_mode = false;
+  if (rc) return rc;
+  // eligible = what the streaming kernel takes (vertical pass first, strictly increasing source rows, strips that fit), 3 channels;
+  // items exist for exactly those samples
+  for (int i = 0; i < n; i++) planar_ok[i] = p->stream_ok[i] && samples[i].channels == 3 && samples[i].in_w > 4;
+  std::vector<RsItem> keep;
+  for (const RsItem &it : p->items) if (planar_ok[it.sample]) keep.push_back(it);
+  p->items.swap(keep);
+  for (int i = 0; i < n; i++) p->stream_ok[i] = planar_ok[i];
+  return DALIB200_SUCCESS;
+}
+
+int dalib200ResampleLaunchPlanar(dalib200ResamplePlan *p, const dalib200PlanarImage *srcs, void *const *out_ptrs, dalib200Stream_t stream) {
+  DB_CHECK_ARG(p && srcs && out_ptrs, "ResampleLaunchPlanar: null argument");
+  if (p->n == 0 || p->items.empty()) return DALIB200_SUCCESS;
+  if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
+  int rc = p->desc_arena.Reserve(sizeof(RsDesc) * p->n);
+  if (rc) return rc;
+  auto *hd = reinterpret_cast<RsDesc *>(p->desc_arena.host);
+  int wmax = 1;
+  for (int i = 0; i < p->n; i++) {
+    hd[i] = p->descs[i];
+    hd[i].in = nullptr;
+    hd[i].out = out_ptrs[i];
+    hd[i].neg_zero = -0.0f;
+    hd[i].use_stream = p->stream_ok[i];
+    p->path[i] = p->stream_ok[i] ? 2 : 0;
+    if (!p->stream_ok[i]) continue;
+    const dalib200PlanarImage &s = srcs[i];
+    DB_CHECK_ARG(s.y && s.cb && s.cr && s.pitch_y % 16 == 0 && s.pitch_c % 16 == 0 &&
+                 (reinterpret_cast<uintptr_t>(s.y) | reinterpret_cast<uintptr_t>(s.cb) | reinterpret_cast<uintptr_t>(s.cr)) % 16 == 0,
+                 "ResampleLaunchPlanar: sample %d: planes must be 16-byte aligned with a pitch that is a multiple of 16", i);
+    DB_CHECK_ARG(s.crop_x >= 0 && s.crop_y >= 0 && s.crop_x + hd[i].in_w <= s.width && s.crop_y + hd[i].in_h <= s.height,
+                 "ResampleLaunchPlanar: sample %d: the window does not fit the image", i);
+    hd[i].pl[0] = s.y; hd[i].pl[1] = s.cb; hd[i].pl[2] = s.cr;
+    hd[i].pitch_y = s.pitch_y; hd[i].pitch_c = s.pitch_c; hd[i].img_w = s.width; hd[i].img_h = s.height;
+    hd[i].crop_x = s.crop_x; hd[i].crop_y = s.crop_y;
+    wmax = std::max(wmax, (int)hd[i].walk_slots);
+  }
+  rc = p->desc_arena.Upload(sizeof(RsDesc) * p->n, stream);
+  if (rc) return rc;
+  if (p->tables_dirty) {
+    size_t bytes = p->tables.size() * sizeof(int32_t);
+    rc = p->table_arena.Reserve(bytes);
+    if (rc) return rc;
+    memcpy(p->table_arena.host, p->tables.data(), bytes);
+    rc = p->table_arena.Upload(bytes, stream);
+    if (rc) return rc;
+    p->uploaded_tables = p->tables;
+    p->tables_dirty = false;
+  }
+  const size_t ib = p->items.size() * sizeof(RsItem);
+  rc = p->item_arena.Reserve(ib);
+  if (rc) return rc;
+  memcpy(p->item_arena.host, p->items.data(), ib);
+  rc = p->item_arena.Upload(ib, stream);
+  if (rc) return rc;
+  DB_CUDA(cudaEventRecord(p->uploaded, stream));
+  p->pending = true;
+  const auto *dd = reinterpret_cast<const RsDesc *>(p->desc_arena.dev);
+  const auto *tb = reinterpret_cast<const int32_t *>(p->table_arena.dev);
+  const auto *di = reinterpret_cast<const RsItem *>(p->item_arena.dev);
+  const int nitems = (int)p->items.size();
+  const int sgrid = std::min(nitems, NumSMs() * 2);
+  auto slaunch = [&](auto kern, int slot) -> int {
+    if (!p->smem_opted[slot]) {
+      DB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlSmemBytes));
+      p->smem_opted[slot] = true;
+    }
+    { ProfScope ps_("resample_planar", stream); kern<<<sgrid, kStThreads, kPlSmemBytes, stream>>>(dd, tb, di, nitems); }
+    return DALIB200_SUCCESS;
+  };
+  if (wmax <= 2)      rc = slaunch(resample_planar_kernel<2>, 10);
+  else if (wmax == 3) rc = slaunch(resample_planar_kernel<3>, 11);
+  else                rc = slaunch(resample_planar_kernel<4>, 12);
+  if (rc) return rc;
+  CountLaunch();
+  DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
 }
 

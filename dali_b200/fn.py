@@ -54,13 +54,15 @@ def _make_wrapper(schema):
         spec = backend.OpSpec(schema)
         spec.add_arg("device", device)
         in_dev = _INPUT_DEVICE[device]
-        for i in inputs:
+        for idx, i in enumerate(inputs):
             if i.device != in_dev:
-                if i.device == "cpu" and in_dev == "gpu":
+                if i.device == "cpu" and in_dev == "gpu" and idx == 0:
                     i = i.gpu()
+                elif i.device == "cpu" and in_dev == "gpu":
+                    pass            # auxiliary inputs of GPU operators (slice anchor / shape) may stay on the CPU, as in the reference
                 else:
                     raise ValueError(f"Operator {schema} on device '{device}' expects {in_dev} inputs, got a {i.device} input")
-            if in_dev == "cpu":
+            if i.device == "cpu":
                 i._consumed_cpu = True
             spec.add_input(i.name, i.device)
         for k, v in kwargs.items():

@@ -352,6 +352,9 @@ class OperatorBase {
   bool Setup(std::vector<OutputDesc> &output_desc, const Workspace &ws) { return SetupImpl(output_desc, ws); }
   void Run(Workspace &ws) { RunImpl(ws); }
   virtual bool HasContiguousOutputs() const { return true; }
+  // called by the executor once the iteration's stream has been synchronised (where the reference's executor rethrows the
+  // errors captured during the run, exec_node_task.cc): operators with device-side status words check them here
+  virtual void CheckCompletion() {}
   const OpSpec &GetSpec() const { return spec_; }
  protected:
   virtual bool SetupImpl(std::vector<OutputDesc> &output_desc, const Workspace &ws) = 0;
@@ -359,6 +362,27 @@ class OperatorBase {
   const OpSpec spec_;
   int num_threads_;
   int max_batch_size_;
+};
+
+// Executor-level fusion of an image decoder with the Resize that consumes it: when the decoded image has no
+// other consumer the pipeline links the two operators; the decoder then defers its launch to the Resize, which asks it for the
+// component planes of the samples its planar kernel can take and resizes them without the RGB image ever being written.
+struct PlanarSource {            // mirrors dalib200PlanarImage (include/dali_b200.h)
+  const uint8_t *y, *cb, *cr;
+  int32_t pitch_y, pitch_c, width, height, crop_x, crop_y;
+};
+class PlanarProducer {
+ public:
+  virtual ~PlanarProducer() = default;
+  virtual void EnableDeferredRun() = 0;                                      // build time: a fused consumer exists
+  virtual void SelectPlanar(const std::vector<uint8_t> &want, std::vector<uint8_t> &granted) = 0;   // per iteration, from the consumer's Setup
+  virtual void RunDeferred(cudaStream_t stream) = 0;                          // upload + decode (planes only where granted)
+  virtual void GetPlanarSource(int sample, PlanarSource *out) = 0;            // after RunDeferred
+};
+class PlanarConsumer {
+ public:
+  virtual ~PlanarConsumer() = default;
+  virtual void AttachProducer(PlanarProducer *p) = 0;
 };
 
 template <typename Backend>

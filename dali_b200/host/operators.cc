@@ -17,6 +17,7 @@
 // There is no CPU implementation: the ops are registered for GPU / Mixed only.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <limits>
 #include "dali.h"
 #include "random_crop.h"
@@ -99,8 +100,29 @@ DALI_SCHEMA(decoders__Image)
 
 // Common part of decoders.image / image_crop / image_random_crop / image_slice: header parse, region of interest from the
 // derived class (in OUTPUT = oriented coordinates, imgcodec.h:26-44), plan setup, launch, asynchronous status check.
-class ImageDecoderBase : public Operator<MixedBackend> {
+class ImageDecoderBase : public Operator<MixedBackend>, public PlanarProducer {
  public:
+  // ---- PlanarProducer: decode -> resize fusion (the launch is deferred to the consuming Resize)
+  void EnableDeferredRun() override { deferred_ = true; }
+  void SelectPlanar(const std::vector<uint8_t> &want, std::vector<uint8_t> &granted) override {
+    granted.assign(want.size(), 0);
+    CheckStatus(dalib200JpegPlanSetPlanesOnly(plan_, want.data(), granted.data()), name_);
+  }
+  void RunDeferred(cudaStream_t stream) override {
+    CheckStatus(dalib200JpegUpload(plan_, stream), name_);
+    CheckStatus(dalib200JpegLaunch(plan_, optr_.data(), stream), name_);
+    CheckStatus(dalib200JpegStatusAsync(plan_, stream), name_);
+    launched_ = static_cast<int>(optr_.size());
+  }
+  void GetPlanarSource(int sample, PlanarSource *out) override {
+    dalib200PlanarImage pi;
+    CheckStatus(dalib200JpegPlanGetPlanes(plan_, sample, &pi), name_);
+    out->y = pi.y; out->cb = pi.cb; out->cr = pi.cr; out->pitch_y = pi.pitch_y; out->pitch_c = pi.pitch_c;
+    out->width = pi.width; out->height = pi.height;
+    out->crop_x = rois_[sample].use_roi ? rois_[sample].x0 : 0;
+    out->crop_y = rois_[sample].use_roi ? rois_[sample].y0 : 0;
+  }
+
   explicit ImageDecoderBase(const OpSpec &spec, const char *name) : Operator<MixedBackend>(spec), name_(name) {
     prm_.output_type = spec.GetArgument<DALIImageType>("output_type");
     const DALIDataType dt = spec.GetArgument<DALIDataType>("dtype");
@@ -150,11 +172,24 @@ class ImageDecoderBase : public Operator<MixedBackend> {
   void RunImpl(Workspace &ws) override {
     auto &out = ws.Output<GPUBackend>(0);
     out.SetLayout("HWC");
-    std::vector<void *> optr(out.num_samples());
-    for (int i = 0; i < out.num_samples(); i++) optr[i] = out.raw_mutable_tensor(i);
-    CheckStatus(dalib200JpegUpload(plan_, ws.stream()), name_);
-    CheckStatus(dalib200JpegLaunch(plan_, optr.data(), ws.stream()), name_);
+    optr_.resize(out.num_samples());
+    for (int i = 0; i < out.num_samples(); i++) optr_[i] = out.raw_mutable_tensor(i);
+    if (deferred_) return;                  // the consuming Resize launches the decode (RunDeferred) once it has chosen the planar samples
+    RunDeferred(ws.stream());
   }
+  void CheckCompletion() override {
+    if (launched_ <= 0) return;
+    std::vector<int32_t> st(launched_);
+    const int n = launched_;
+    launched_ = 0;
+    CheckStatus(dalib200JpegStatusFetch(plan_, st.data(), n), name_);
+    for (int i = 0; i < n; i++)
+      if (st[i] != 0)       // image_decoder.h:826-831: "Failed to decode sample #i"
+        throw DALIException(make_string("Failed to decode sample #", i, ": the entropy-coded data ends early or is corrupt"));
+  }
+  int launched_ = 0;
+  bool deferred_ = false;
+  std::vector<void *> optr_;
 
   dalib200JpegPlan *plan_ = nullptr;
   dalib200JpegParams prm_{};
@@ -533,9 +568,16 @@ static int Interp2Filter(int interp) {      // resampling_attr.cc:60-74
   }
 }
 
-class ResizeGPU : public Operator<GPUBackend> {
+class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
  public:
-  explicit ResizeGPU(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+  void AttachProducer(PlanarProducer *p) override {
+    producer_ = p;
+    CheckStatus(dalib200ResamplePlanCreate(&plan_planar_, plan_cap_), "Resize");
+    planar_cap_ = plan_cap_;
+  }
+  // hook of ResizeCropMirror: crop window and mirror applied to the per-sample parameters
+  virtual void AdjustSampleParams(resize_detail::Params &, const Workspace &, int) {}
+  explicit ResizeGPU(const OpSpec &spec, const char *name = "Resize") : Operator<GPUBackend>(spec) {
     using resize_detail::Mode;
     has_shorter_ = spec.ArgumentDefined("resize_shorter"); has_longer_ = spec.ArgumentDefined("resize_longer");
     has_x_ = spec.ArgumentDefined("resize_x"); has_y_ = spec.ArgumentDefined("resize_y");
@@ -563,7 +605,7 @@ class ResizeGPU : public Operator<GPUBackend> {
     CheckStatus(dalib200ResamplePlanCreate(&plan_, max_batch_size_ * 64), "Resize");
     plan_cap_ = max_batch_size_ * 64;
   }
-  ~ResizeGPU() override { dalib200ResamplePlanDestroy(plan_); }
+  ~ResizeGPU() override { dalib200ResamplePlanDestroy(plan_); if (plan_planar_) dalib200ResamplePlanDestroy(plan_planar_); }
 
  protected:
   bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
@@ -611,6 +653,7 @@ class ResizeGPU : public Operator<GPUBackend> {
       resize_detail::Params p;
       const bool empty_input = in.shape().tensor_size(i) == 0;
       resize_detail::CalculateSampleParams(p, req, lo, hi, subpixel_scale_, empty_input, mode_, has_max_ ? max_size.data() : nullptr);
+      AdjustSampleParams(p, ws, i);
       // filters (resampling_attr.cc:76-133)
       int interp = spec_.GetArgument<int>("interp_type", &ws, i);
       int minf = DALIB200_FILTER_TRIANGULAR, magf = DALIB200_FILTER_LINEAR;
@@ -634,8 +677,33 @@ class ResizeGPU : public Operator<GPUBackend> {
         }
       }
     }
-    CheckStatus(dalib200ResamplePlanSetup(plan_, nf, samples_.data(), in.type() == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT,
-                                          out_type == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT), "Resize");
+    // ---- fused with the decoder that produces the input: the samples the planar kernel can take never exist as RGB images
+    planar_.assign(nf, 0);
+    rest_.clear();
+    if (producer_ && frames_.first_spatial == 0 && nf == n && in.type() == DALI_UINT8 && out_type == DALI_UINT8) {
+      if (nf > planar_cap_) { dalib200ResamplePlanDestroy(plan_planar_); plan_planar_ = nullptr; planar_cap_ = nf; CheckStatus(dalib200ResamplePlanCreate(&plan_planar_, nf), "Resize"); }
+      std::vector<uint8_t> ok(nf, 0), granted;
+      CheckStatus(dalib200ResamplePlanSetupPlanar(plan_planar_, nf, samples_.data(), ok.data()), "Resize");
+      producer_->SelectPlanar(ok, granted);
+      if (ok != granted) {       // the resampler's item list must cover exactly the granted samples
+        std::vector<dalib200ResampleSample> tmp(samples_);
+        for (int i = 0; i < nf; i++) if (!granted[i]) tmp[i].channels = 1;      // 1-channel samples are never planar-eligible
+        CheckStatus(dalib200ResamplePlanSetupPlanar(plan_planar_, nf, tmp.data(), ok.data()), "Resize");
+      }
+      planar_ = granted;
+    } else if (producer_) {
+      std::vector<uint8_t> none(n, 0), granted;
+      producer_->SelectPlanar(none, granted);
+    }
+    for (int k = 0; k < nf; k++) if (!planar_[k]) rest_.push_back(k);
+    if (static_cast<int>(rest_.size()) == nf) {
+      CheckStatus(dalib200ResamplePlanSetup(plan_, nf, samples_.data(), in.type() == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT,
+                                            out_type == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT), "Resize");
+    } else if (!rest_.empty()) {
+      std::vector<dalib200ResampleSample> sub(rest_.size());
+      for (size_t q = 0; q < rest_.size(); q++) sub[q] = samples_[rest_[q]];
+      CheckStatus(dalib200ResamplePlanSetup(plan_, static_cast<int>(sub.size()), sub.data(), DALIB200_UINT8, DALIB200_UINT8), "Resize");
+    }
     out.resize(1);
     out[0].type = out_type;
     out[0].shape.resize(n, in.shape().sample_dim());
@@ -661,12 +729,37 @@ class ResizeGPU : public Operator<GPUBackend> {
       op[k] = static_cast<uint8_t *>(out.raw_mutable_tensor(s)) + next[s];
       next[s] += fr;
     }
-    CheckStatus(dalib200ResampleLaunch(plan_, ip.data(), op.data(), ws.stream()), "Resize");
+    if (producer_) {
+      producer_->RunDeferred(ws.stream());
+      if (rest_.size() != op.size()) {
+        std::vector<dalib200PlanarImage> srcs(op.size());
+        for (size_t k = 0; k < op.size(); k++) {
+          memset(&srcs[k], 0, sizeof(srcs[k]));
+          if (!planar_[k]) continue;
+          PlanarSource ps;
+          producer_->GetPlanarSource(static_cast<int>(k), &ps);
+          srcs[k].y = ps.y; srcs[k].cb = ps.cb; srcs[k].cr = ps.cr; srcs[k].pitch_y = ps.pitch_y; srcs[k].pitch_c = ps.pitch_c;
+          srcs[k].width = ps.width; srcs[k].height = ps.height; srcs[k].crop_x = ps.crop_x; srcs[k].crop_y = ps.crop_y;
+        }
+        CheckStatus(dalib200ResampleLaunchPlanar(plan_planar_, srcs.data(), op.data(), ws.stream()), "Resize");
+      }
+    }
+    if (rest_.size() == op.size()) {
+      CheckStatus(dalib200ResampleLaunch(plan_, ip.data(), op.data(), ws.stream()), "Resize");
+    } else if (!rest_.empty()) {
+      std::vector<const void *> ip2(rest_.size());
+      std::vector<void *> op2(rest_.size());
+      for (size_t q = 0; q < rest_.size(); q++) { ip2[q] = ip[rest_[q]]; op2[q] = op[rest_[q]]; }
+      CheckStatus(dalib200ResampleLaunch(plan_, ip2.data(), op2.data(), ws.stream()), "Resize");
+    }
   }
 
  private:
-  dalib200ResamplePlan *plan_ = nullptr;
-  int plan_cap_ = 0;
+  dalib200ResamplePlan *plan_ = nullptr, *plan_planar_ = nullptr;
+  int plan_cap_ = 0, planar_cap_ = 0;
+  PlanarProducer *producer_ = nullptr;
+  std::vector<uint8_t> planar_;
+  std::vector<int> rest_;
   bool has_shorter_ = false, has_longer_ = false, has_x_ = false, has_y_ = false, has_size_ = false, has_max_ = false, has_roi_ = false;
   bool roi_relative_ = false, subpixel_scale_ = true, antialias_ = true;
   resize_detail::Mode mode_ = resize_detail::Mode::Default;
@@ -676,6 +769,61 @@ class ResizeGPU : public Operator<GPUBackend> {
   DALIDataType out_type_ = DALI_UINT8;
 };
 DALI_REGISTER_OPERATOR(Resize, ResizeGPU, GPU);
+
+class ResizeCropMirrorGPU : public ResizeGPU {
+ public:
+  explicit ResizeCropMirrorGPU(const OpSpec &spec) : ResizeGPU(spec, "ResizeCropMirror") { crop_.Init(spec, "ResizeCropMirror"); }
+  void AdjustSampleParams(resize_detail::Params &p, const Workspace &ws, int i) override {
+    // resize_crop_mirror.cc:84-108; the crop window is computed on the RESIZED shape
+    int64_t y0, x0, h, w;
+    crop_.Get(spec_, ws, i, p.dst[0], p.dst[1], y0, x0, h, w);
+    const int64_t anchor[2] = { y0, x0 }, shape[2] = { h, w };
+    const int mirror = spec_.GetArgument<int>("mirror", &ws, i);
+    for (int d = 0; d < 2; d++) {
+      const double src_extent = p.hi[d] - p.lo[d];
+      const double resize_ratio = src_extent / p.dst[d];
+      const double resize_offset = p.lo[d];
+      const double crop_lo = static_cast<double>(anchor[d]), crop_hi = static_cast<double>(anchor[d] + shape[d]);
+      p.lo[d] = static_cast<float>(crop_lo * resize_ratio + resize_offset);
+      p.hi[d] = static_cast<float>(crop_hi * resize_ratio + resize_offset);
+      if (mirror & (1 << (2 - 1 - d))) std::swap(p.lo[d], p.hi[d]);
+      p.dst[d] = static_cast<int>(shape[d]);
+    }
+  }
+ private:
+  CropWindowArgs crop_;
+};
+DALI_REGISTER_OPERATOR(ResizeCropMirror, ResizeCropMirrorGPU, GPU);
+
+// =============================================================================================== ResizeCropMirror
+// dali/operators/image/resize/resize_crop_mirror.{h,cc}: resize, then crop, then flip -- executed as ONE resampling whose ROI is the
+// crop window projected back into the input (resize_crop_mirror.cc:73-110).
+class ResizeCropMirrorGPU;
+DALI_SCHEMA(ResizeCropMirror)
+    .DocStr("Performs a fused resize, crop, mirror operation.")
+    .NumInput(1).NumOutput(1).AllowSequences()
+    .AddOptionalArgNoDefault("resize_x", "Length of the X dimension of the resized image (0 = keep aspect).", true)
+    .AddOptionalArgNoDefault("resize_y", "Length of the Y dimension of the resized image (0 = keep aspect).", true)
+    .AddOptionalArgNoDefault("resize_z", "not supported by the GPU path (2-D images only)", true)
+    .AddOptionalArgNoDefault("size", "Desired output size (H, W).", true)
+    .AddOptionalArgNoDefault("resize_shorter", "Length of the shorter dimension of the resized image.", true)
+    .AddOptionalArgNoDefault("resize_longer", "Length of the longer dimension of the resized image.", true)
+    .AddOptionalArgNoDefault("mode", "default | stretch | not_larger | not_smaller")
+    .AddOptionalArgNoDefault("max_size", "Limit of the output size.")
+    .AddOptionalArg("subpixel_scale", "Adjust the ROI so that fractional sizes keep the scale.", true)
+    .AddOptionalArgNoDefault("roi_start", "Origin of the input region of interest.", true)
+    .AddOptionalArgNoDefault("roi_end", "End of the input region of interest.", true)
+    .AddOptionalArg("roi_relative", "ROI given in relative coordinates.", false)
+    .AddOptionalArg("interp_type", "Type of interpolation.", DALI_INTERP_LINEAR, true)
+    .AddOptionalArg("mag_filter", "Filter used when scaling up.", DALI_INTERP_LINEAR, true)
+    .AddOptionalArg("min_filter", "Filter used when scaling down.", DALI_INTERP_LINEAR, true)
+    .AddOptionalArg("antialias", "Apply an antialiasing filter when scaling down.", true)
+    .AddOptionalArgNoDefault("dtype", "Output type: same as input or FLOAT.")
+    .AddOptionalArg("minibatch_size", "ignored (the whole batch is one launch)", 32)
+    .AddOptionalArg("temp_buffer_hint", "ignored (the intermediate lives in shared memory)", 0)
+    .AddOptionalArg("save_attrs", "not supported", false)
+    .AddOptionalArg("mirror", "Mask for flipping: 1 = horizontal, 2 = vertical.", 0, true)
+    DALIB200_CROP_ARGS();
 
 // =============================================================================================== RandomResizedCrop
 // dali/operators/image/resize/random_resized_crop.{h,cc}: a random window (RandomCropAttr) resized to `size`; the window is
@@ -1906,5 +2054,12 @@ extern "C" int dalihTestRandomCrop(int64_t seed, int sample_idx, int H, int W, f
     const dali::CropWindow2D w = gen.Generate(H, W);
     windows[4 * k] = w.anchor[0]; windows[4 * k + 1] = w.anchor[1]; windows[4 * k + 2] = w.shape[0]; windows[4 * k + 3] = w.shape[1];
   }
+  return 0;
+}
+
+// Test hooks (CPU): Rotate's canvas size / matrix and BrightnessContrast's kernel arguments, for comparison with the reference's own
+// code (oracle/_ref: rotate_params.h + geom/transform.h, brightness_contrast.h) where no GPU exists.
+extern "C" int dalihTestRotateParams(float angle_deg, int in_h, int in_w, int keep_size, const float *size_hw_or_null, int *out_hw, float *m2x3) {
+  dali::rotate_detail::Params(angle_deg, in_h, in_w, keep_size != 0, size_hw_or_null, out_hw[0], out_hw[1], m2x3);
   return 0;
 }

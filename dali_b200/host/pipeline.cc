@@ -9,6 +9,7 @@
 // The reference's prefetch queues, stream assignment and thread-pool scheduling (exec2) are out of scope
 // (SURVEY.md 2.1 row 5): the hot-path ops are GPU-only and enqueue on one stream without host syncs.
 #include "dali.h"
+#include <nvtx3/nvToolsExt.h>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +17,11 @@
 #include <mutex>
 
 namespace dali {
+
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---------------------------------------------------------------------------------------------- TensorList storage
 template <>
@@ -328,6 +334,25 @@ void Pipeline::Build() {
   for (auto &o : output_names_) GetEdge(o.first, o.second);
   if (device_id_ >= 0) CUDA_CALL(cudaSetDevice(device_id_));
   for (auto &n : nodes_) n.op = InstantiateOperator(n.spec);
+  // decoder -> Resize fusion: the decoded image must have exactly one consumer and must not be a pipeline output
+  if (!getenv("DALIB200_NO_FUSION")) {
+    for (auto &c : nodes_) {
+      auto *cons = dynamic_cast<PlanarConsumer *>(c.op.get());
+      if (!cons || c.spec.NumInput() < 1) continue;
+      const auto edge = c.spec.Input(0);
+      int uses = 0;
+      for (auto &o : nodes_) {
+        for (int i = 0; i < o.spec.NumInput(); i++) uses += o.spec.Input(i) == edge;
+      }
+      for (auto &o : output_names_) uses += o == edge;
+      if (uses != 1) continue;
+      for (auto &pn : nodes_) {
+        if (pn.spec.NumOutput() == 1 && pn.spec.Output(0) == edge) {
+          if (auto *prod = dynamic_cast<PlanarProducer *>(pn.op.get())) { prod->EnableDeferredRun(); cons->AttachProducer(prod); }
+        }
+      }
+    }
+  }
   built_ = true;
 }
 
@@ -380,6 +405,7 @@ void Pipeline::Run() {
     static const bool timing = getenv("DALIB200_HOST_TIMING") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
     try {
+      NvtxRange op_range(n.name.c_str());                  // like DomainTimeRange around Setup / Run (exec_node_task.cc:291,314)
       if (n.op->Setup(descs, ws)) {
         DALI_ENFORCE(descs.size() == outs.size(), "Operator returned ", descs.size(), " output descriptors for ", outs.size(), " outputs");
         for (size_t i = 0; i < outs.size(); i++) {
@@ -411,6 +437,14 @@ const TensorList<GPUBackend> *Pipeline::OutputGPU(int i) const {
 }
 void Pipeline::WaitOutputs() {
   if (stream_) CUDA_CALL(cudaStreamSynchronize(stream_));
+  for (auto &n : nodes_) {
+    try {
+      n.op->CheckCompletion();
+    } catch (const std::exception &ex) {
+      throw DALIException(make_string("Error in ", n.spec.GetArgument<std::string>("device"), " operator `", n.spec.SchemaName(),
+                                      "` (", n.name, "): ", ex.what()));
+    }
+  }
 }
 
 }  // namespace dali

@@ -32,15 +32,20 @@ def cmn_norm_args(mean, std, scale=1.0, shift=0.0):
 class ImagePipelineC2:
     """decode (mixed) -> resize(out_h, out_w) -> crop_mirror_normalize(fp16/fp32, CHW) for one batch."""
 
-    def __init__(self, max_batch, out_hw=(224, 224), out_dtype="float16", mean=IMAGENET_MEAN, std=IMAGENET_STD, device=None):
+    def __init__(self, max_batch, out_hw=(224, 224), out_dtype="float16", mean=IMAGENET_MEAN, std=IMAGENET_STD, device=None, fused=True):
         import torch
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.max_batch = max_batch
         self.out_hw = tuple(out_hw)
         self.out_dtype = torch.float16 if out_dtype in ("float16", torch.float16) else torch.float32
+        # fused: samples that qualify (4:2:0 YCbCr streams, stream-eligible resize) are resized straight from the decoder's planes
+        # (dalib200ResampleLaunchPlanar); the decoded RGB image is then never written.  The others take the two-kernel path.
+        self.fused = bool(fused)
         self.jpeg = capi.Plan("Jpeg", max_batch)
         self.resample = capi.Plan("Resample", max_batch)
+        self.resample_planar = capi.Plan("Resample", max_batch) if self.fused else None
+        self.planar = []
         self.cmn = capi.Plan("Cmn", max_batch)
         self.mean, self.inv_std = cmn_norm_args(mean, std)
         self._decoded = None
@@ -83,7 +88,25 @@ class ImagePipelineC2:
             for k in range(3):
                 c.mean[k] = float(self.mean[k]); c.inv_std[k] = float(self.inv_std[k]); c.fill[k] = 0.0
             c.mean[3] = 0.0; c.inv_std[3] = 1.0; c.fill[3] = 0.0
-        capi.check(lib.dalib200ResamplePlanSetup(self.resample.handle, n, rs, capi.UINT8, capi.UINT8))
+        self.planar = [0] * n
+        if self.fused:
+            ok = (C.c_uint8 * n)()
+            capi.check(lib.dalib200ResamplePlanSetupPlanar(self.resample_planar.handle, n, rs, ok))
+            granted = (C.c_uint8 * n)()
+            capi.check(lib.dalib200JpegPlanSetPlanesOnly(self.jpeg.handle, ok, granted))
+            self.planar = list(granted)
+            if any(o and not g for o, g in zip(ok, granted)):
+                # the resampler's item list covers the samples IT found eligible: re-run its setup with the decoder's verdict
+                for i in range(n):
+                    if not granted[i]:
+                        rs[i].channels = 1          # 1-channel samples are never planar-eligible
+                capi.check(lib.dalib200ResamplePlanSetupPlanar(self.resample_planar.handle, n, rs, ok))
+                for i in range(n):
+                    rs[i].channels = 3
+        self._rest = [i for i in range(n) if not self.planar[i]]
+        if self._rest:
+            rs_b = (capi.ResampleSample * len(self._rest))(*[rs[i] for i in self._rest])
+            capi.check(lib.dalib200ResamplePlanSetup(self.resample.handle, len(self._rest), rs_b, capi.UINT8, capi.UINT8))
         capi.check(lib.dalib200CmnPlanSetup(self.cmn.handle, n, cm, capi.FLOAT16 if self.out_dtype == torch.float16 else capi.FLOAT,
                                             capi.LAYOUT_CHW, 3))
         # inter-stage buffers (grow only; one allocation per stage, samples packed back to back)
@@ -111,7 +134,16 @@ class ImagePipelineC2:
     def launch(self, stream=None):
         lib, s = capi.lib(), capi.stream_handle(stream)
         capi.check(lib.dalib200JpegLaunch(self.jpeg.handle, self._dec_ptrs, s))
-        capi.check(lib.dalib200ResampleLaunch(self.resample.handle, self._dec_ptrs, self._res_ptrs, s))
+        if any(self.planar):
+            srcs = (capi.PlanarImage * self.n)()
+            for i in range(self.n):
+                if self.planar[i]:
+                    capi.check(lib.dalib200JpegPlanGetPlanes(self.jpeg.handle, i, C.byref(srcs[i])))
+            capi.check(lib.dalib200ResampleLaunchPlanar(self.resample_planar.handle, srcs, self._res_ptrs, s))
+        if self._rest:
+            dec = capi.ptr_array([self._dec_ptrs[i] for i in self._rest])
+            res = capi.ptr_array([self._res_ptrs[i] for i in self._rest])
+            capi.check(lib.dalib200ResampleLaunch(self.resample.handle, dec, res, s))
         capi.check(lib.dalib200CmnLaunch(self.cmn.handle, self._res_ptrs, self._out_ptrs, s))
         return self.output[: self.n]
 

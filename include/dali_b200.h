@@ -88,7 +88,26 @@ int dalib200JpegPlanGetInfo(const dalib200JpegPlan *plan, int sample, dalib200Jp
  *                        (imgcodec.h:26-44, image_decoder.h:681-716); only the MCUs under the region are transformed.
  * The result equals the full decode followed by orientation, crop and conversion, bit for bit. */
 typedef struct { int32_t output_type, fancy_upsampling, dtype, adjust_orientation; } dalib200JpegParams;
-typedef struct { int32_t use_roi, x0, y0, x1, y1; } dalib200JpegRoi;
+typedef struct {
+  int32_t use_roi, x0, y0, x1, y1;
+  int32_t planes_only;        /* skip upsampling + colour conversion for this sample: the caller reads the component planes
+                                 (dalib200JpegPlanGetPlanes -> dalib200ResampleLaunchPlanar); 4:2:0 YCbCr streams only */
+} dalib200JpegRoi;
+/* The decoder's planar output of a sample: 8-bit planes, Cb / Cr at half resolution (4:2:0), rows padded to a multiple of 16 bytes.
+ * Only the MCUs under the sample's region of interest hold data.  crop_x / crop_y: filled by the caller (window the resampler treats
+ * as its input image). */
+typedef struct {
+  const uint8_t *y, *cb, *cr;
+  int32_t pitch_y, pitch_c;
+  int32_t width, height;
+  int32_t crop_x, crop_y;
+} dalib200PlanarImage;
+/* Alternative to the planes_only flags of SetupEx, for callers that learn only after the setup which samples they can consume as
+ * planes: want[i] != 0 asks for sample i, granted[i] tells whether the stream qualifies (3 components, 4:2:0, YCbCr, fancy upsampling,
+ * no orientation, RGB u8 request).  Call between JpegPlanSetupEx and JpegUpload. */
+int dalib200JpegPlanSetPlanesOnly(dalib200JpegPlan *plan, const uint8_t *want, uint8_t *granted);
+/* valid after dalib200JpegLaunch of the batch (the plane arena may grow there) until the next launch */
+int dalib200JpegPlanGetPlanes(const dalib200JpegPlan *plan, int sample, dalib200PlanarImage *out);
 int dalib200JpegPlanSetupEx(dalib200JpegPlan *plan, int n, const uint8_t *const *streams, const size_t *lengths,
                             const dalib200JpegParams *params, const dalib200JpegRoi *rois_or_null);
 /* (H, W, C) of the sample the launch will write (after orientation and region of interest) */
@@ -102,6 +121,11 @@ int dalib200JpegUpload(dalib200JpegPlan *plan, dalib200Stream_t stream);
 int dalib200JpegLaunch(dalib200JpegPlan *plan, void *const *out_ptrs, dalib200Stream_t stream);
 /* Per-sample device status after a launch (0 ok, 1 = entropy-coded data ended early).  Synchronises. */
 int dalib200JpegGetStatus(dalib200JpegPlan *plan, int32_t *status_out);
+/* Non-blocking status: ...Async enqueues the D2H copy of the status words on `stream` into the plan's pinned buffer, ...Fetch reads
+ * them once the caller has synchronised the stream (the operator does it where the executor waits for the outputs, so a truncated
+ * stream raises from Pipeline.run() without an extra synchronisation). */
+int dalib200JpegStatusAsync(dalib200JpegPlan *plan, dalib200Stream_t stream);
+int dalib200JpegStatusFetch(const dalib200JpegPlan *plan, int32_t *status_out, int n);
 /* Test accessor: quantised coefficients of one sample (MCU order, natural order per block).  Synchronises. */
 int dalib200JpegDebugGetCoefficients(dalib200JpegPlan *plan, int sample, int16_t *out, size_t count);
 
@@ -130,6 +154,13 @@ int dalib200ResamplePlanSetup(dalib200ResamplePlan *plan, int n, const dalib200R
 /* in_ptrs[i]: device HWC in_dtype; out_ptrs[i]: device HWC out_dtype [out_h][out_w][channels] */
 int dalib200ResampleLaunch(dalib200ResamplePlan *plan, const void *const *in_ptrs, void *const *out_ptrs,
                            dalib200Stream_t stream);
+/* Decode -> resize without the RGB image (the reference's fused ROI decode + resize path,
+ * image_decoder.h:699-716 + resize.cc): samples whose `planar_ok` is 1 after ...SetupPlanar are resampled straight from the decoder's
+ * planes (fancy chroma upsampling + YCbCr->RGB happen inside the resampling kernel, bit-exact with decode-then-resize); sample i of
+ * ...LaunchPlanar reads srcs[i] (window crop_x, crop_y, in_w x in_h of the setup) and is skipped when planar_ok[i] == 0. */
+int dalib200ResamplePlanSetupPlanar(dalib200ResamplePlan *plan, int n, const dalib200ResampleSample *samples, uint8_t *planar_ok);
+int dalib200ResampleLaunchPlanar(dalib200ResamplePlan *plan, const dalib200PlanarImage *srcs, void *const *out_ptrs,
+                                 dalib200Stream_t stream);
 /* introspection used by the tests: processing order chosen for a sample (0 = horizontal pass first) */
 int dalib200ResamplePlanGetOrder(const dalib200ResamplePlan *plan, int sample);
 /* 1 when the sample went through the streaming (TMA ring) kernel in the last launch, 0 = tile kernel, -1 = bad index. */

@@ -1,0 +1,438 @@
+// integration/b200_ops.cc -- the operator plugin a DALI maintainer adds to run the hot path on libdali_b200.so.
+//
+// Written against the REFERENCE's own headers (dali/pipeline/operator/operator.h, crop_attr.h, resize_attr.h, resampling_attr.h, ...):
+// the argument handling is the reference's (CropAttr, ResizeAttr, ResamplingFilterAttr, OpSpec::GetArgument), only the kernel call
+// changes -- to the C-ABI of include/dali_b200.h.  Built as a normal DALI plugin and loaded with
+// nvidia.dali.plugin_manager.load_library; the operators register under the `b200` prefix (fn.b200.resize, ...), because the stock
+// names are taken in a stock build (operator_factory.h:55-58).
+// tests/test_integration_cpu.py compiles this file with `g++ -std=c++20 -fsyntax-only` against /root/reference where it exists.
+#include <string>
+#include <vector>
+
+#include "dali/core/static_switch.h"
+#include "dali/kernels/imgproc/resample/params.h"
+#include "dali/operators/image/crop/crop_attr.h"
+#include "dali/operators/image/resize/resampling_attr.h"
+#include "dali/operators/image/resize/resize_attr.h"
+#include "dali/pipeline/operator/operator.h"
+
+#include "dali_b200.h"
+
+namespace b200 {
+using namespace dali;  // NOLINT
+
+inline void Check(int rc, const char *what) {
+  if (rc != DALIB200_SUCCESS) DALI_FAIL(make_string(what, ": ", dalib200GetLastError()));
+}
+
+template <typename TL>
+inline std::vector<const void *> InPtrs(const TL &tl) {
+  std::vector<const void *> p(tl.num_samples());
+  for (int i = 0; i < tl.num_samples(); i++) p[i] = tl.raw_tensor(i);
+  return p;
+}
+template <typename TL>
+inline std::vector<void *> OutPtrs(TL &tl) {
+  std::vector<void *> p(tl.num_samples());
+  for (int i = 0; i < tl.num_samples(); i++) p[i] = tl.raw_mutable_tensor(i);
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------ decoders.image (mixed)
+class ImageDecoder : public Operator<MixedBackend> {
+ public:
+  explicit ImageDecoder(const OpSpec &spec) : Operator<MixedBackend>(spec) {
+    prm_.output_type = static_cast<int>(spec.GetArgument<DALIImageType>("output_type"));
+    prm_.dtype = spec.GetArgument<DALIDataType>("dtype") == DALI_FLOAT ? DALIB200_FLOAT : DALIB200_UINT8;
+    prm_.fancy_upsampling = spec.GetArgument<bool>("jpeg_fancy_upsampling");
+    prm_.adjust_orientation = spec.GetArgument<bool>("adjust_orientation");
+    Check(dalib200JpegPlanCreate(&plan_, max_batch_size_), "decoders.image");
+  }
+  ~ImageDecoder() override { dalib200JpegPlanDestroy(plan_); }
+  bool HasContiguousOutputs() const override { return true; }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<CPUBackend>(0);
+    const int n = in.num_samples();
+    std::vector<const uint8_t *> ptrs(n);
+    std::vector<size_t> lens(n);
+    for (int i = 0; i < n; i++) {
+      ptrs[i] = static_cast<const uint8_t *>(in.raw_tensor(i));
+      lens[i] = static_cast<size_t>(in.tensor_shape(i).num_elements());
+    }
+    Check(dalib200JpegPlanSetupEx(plan_, n, ptrs.data(), lens.data(), &prm_, nullptr), "decoders.image");
+    out.resize(1);
+    out[0].type = prm_.dtype == DALIB200_FLOAT ? DALI_FLOAT : DALI_UINT8;
+    out[0].shape.resize(n, 3);
+    for (int i = 0; i < n; i++) {
+      int32_t hwc[3];
+      Check(dalib200JpegPlanGetOutputShape(plan_, i, hwc), "decoders.image");
+      out[0].shape.set_tensor_shape(i, TensorShape<>{hwc[0], hwc[1], hwc[2]});
+    }
+    return true;                                     // the executor allocates the output (exec_node_task.cc:296-307)
+  }
+  void RunImpl(Workspace &ws) override {
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout("HWC");
+    auto op = OutPtrs(out);
+    Check(dalib200JpegUpload(plan_, ws.stream()), "decoders.image");
+    Check(dalib200JpegLaunch(plan_, op.data(), ws.stream()), "decoders.image");      // enqueue only, no host sync
+  }
+
+ private:
+  dalib200JpegPlan *plan_ = nullptr;
+  dalib200JpegParams prm_{};
+};
+
+// ------------------------------------------------------------------------------------------------ Resize
+class Resize : public Operator<GPUBackend> {
+ public:
+  explicit Resize(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    Check(dalib200ResamplePlanCreate(&plan_, max_batch_size_), "Resize");
+  }
+  ~Resize() override { dalib200ResamplePlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    const int n = in.num_samples();
+    const auto &shape = in.shape();
+    resize_attr_.PrepareResizeParams(spec_, ws, shape, in.GetLayout());            // resize_attr.cc:178-259 (reference code)
+    resampling_attr_.PrepareFilterParams(spec_, ws, n);                             // resampling_attr.cc:76-133
+    std::vector<kernels::ResamplingParams> rp(static_cast<size_t>(n) * 2);
+    resampling_attr_.GetResamplingParams(make_span(rp), make_cspan(resize_attr_.params_));
+    samples_.resize(n);
+    out.resize(1);
+    out[0].type = resampling_attr_.GetOutputType(in.type());
+    resize_attr_.GetResizedShape(out[0].shape, shape);
+    const int fs = resize_attr_.first_spatial_dim_;
+    for (int i = 0; i < n; i++) {
+      auto sh = shape.tensor_shape_span(i);
+      auto &s = samples_[i];
+      s.in_h = static_cast<int>(sh[fs]); s.in_w = static_cast<int>(sh[fs + 1]); s.channels = static_cast<int>(sh[fs + 2]);
+      s.out_h = rp[2 * i].output_size; s.out_w = rp[2 * i + 1].output_size;
+      for (int d = 0; d < 2; d++) {
+        const auto &p = rp[2 * i + d];
+        s.use_roi[d] = p.roi.use_roi; s.roi_start[d] = p.roi.start; s.roi_end[d] = p.roi.end;
+        s.min_filter[d] = { static_cast<int>(p.min_filter.type), p.min_filter.antialias, p.min_filter.radius };
+        s.mag_filter[d] = { static_cast<int>(p.mag_filter.type), p.mag_filter.antialias, p.mag_filter.radius };
+      }
+    }
+    Check(dalib200ResamplePlanSetup(plan_, n, samples_.data(), in.type() == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT,
+                                    out[0].type == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT), "Resize");
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200ResampleLaunch(plan_, ip.data(), op.data(), ws.stream()), "Resize");
+  }
+
+ private:
+  ResizeAttr resize_attr_;
+  ResamplingFilterAttr resampling_attr_;
+  dalib200ResamplePlan *plan_ = nullptr;
+  std::vector<dalib200ResampleSample> samples_;
+};
+
+// ------------------------------------------------------------------------------------------------ CropMirrorNormalize
+class CropMirrorNormalize : public Operator<GPUBackend> {
+ public:
+  explicit CropMirrorNormalize(const OpSpec &spec) : Operator<GPUBackend>(spec), crop_attr_(spec) {
+    out_type_ = spec.GetArgument<DALIDataType>("dtype");
+    pad_output_ = spec.GetArgument<bool>("pad_output");
+    mean_ = spec.GetRepeatedArgument<float>("mean");
+    std_ = spec.GetRepeatedArgument<float>("std");
+    scale_ = spec.GetArgument<float>("scale"); shift_ = spec.GetArgument<float>("shift");
+    Check(dalib200CmnPlanCreate(&plan_, max_batch_size_), "CropMirrorNormalize");
+  }
+  ~CropMirrorNormalize() override { dalib200CmnPlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    const int n = in.num_samples();
+    crop_attr_.ProcessArguments(spec_, ws);                                        // crop_attr.cc:100-245 (reference code)
+    samples_.resize(n);
+    out.resize(1);
+    out[0].type = out_type_;
+    out[0].shape.resize(n, 3);
+    int out_c = 3;
+    for (int i = 0; i < n; i++) {
+      auto sh = in.tensor_shape(i);                                                // HWC
+      auto win = crop_attr_.GetCropWindowGenerator(i)(sh, "HWC");
+      auto &s = samples_[i];
+      s.in_h = static_cast<int>(sh[0]); s.in_w = static_cast<int>(sh[1]); s.channels = static_cast<int>(sh[2]);
+      s.anchor_y = static_cast<int>(win.anchor[0]); s.anchor_x = static_cast<int>(win.anchor[1]);
+      s.crop_h = static_cast<int>(win.shape[0]); s.crop_w = static_cast<int>(win.shape[1]);
+      s.mirror = spec_.GetArgument<int>("mirror", &ws, i);
+      out_c = s.channels;
+      if (pad_output_) { out_c = 1; while (out_c < s.channels) out_c *= 2; }       // crop_mirror_normalize.h:69-77
+      for (int d = 0; d < 4; d++) {
+        if (d < s.channels) {                                                      // crop_mirror_normalize.h:135-141
+          const double mean_val = mean_[d % mean_.size()], std_val = std_[d % std_.size()];
+          s.mean[d] = static_cast<float>(std::fma(-static_cast<double>(shift_), std_val / scale_, mean_val));
+          s.inv_std[d] = static_cast<float>(scale_ / std_val);
+        } else { s.mean[d] = 0.0f; s.inv_std[d] = 1.0f; }
+        s.fill[d] = 0.0f;
+      }
+      out[0].shape.set_tensor_shape(i, TensorShape<>{out_c, win.shape[0], win.shape[1]});
+    }
+    Check(dalib200CmnPlanSetup(plan_, n, samples_.data(), out_type_ == DALI_FLOAT16 ? DALIB200_FLOAT16 : DALIB200_FLOAT,
+                               DALIB200_LAYOUT_CHW, out_c), "CropMirrorNormalize");
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout("CHW");
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200CmnLaunch(plan_, ip.data(), op.data(), ws.stream()), "CropMirrorNormalize");
+  }
+
+ private:
+  CropAttr crop_attr_;
+  dalib200CmnPlan *plan_ = nullptr;
+  std::vector<dalib200CmnSample> samples_;
+  std::vector<float> mean_, std_;
+  float scale_ = 1, shift_ = 0;
+  DALIDataType out_type_ = DALI_FLOAT;
+  bool pad_output_ = false;
+};
+
+// ------------------------------------------------------------------------------------------------ WarpAffine
+class WarpAffine : public Operator<GPUBackend> {
+ public:
+  explicit WarpAffine(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    interp_ = spec.GetArgument<DALIInterpType>("interp_type") == DALI_INTERP_LINEAR;
+    invert_ = !spec.GetArgument<bool>("inverse_map");
+    use_fill_ = spec.TryGetArgument(fill_, "fill_value");
+    Check(dalib200WarpPlanCreate(&plan_, max_batch_size_), "WarpAffine");
+  }
+  ~WarpAffine() override { dalib200WarpPlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    const int n = in.num_samples();
+    samples_.resize(n);
+    out.resize(1);
+    out[0].type = DALI_UINT8;
+    out[0].shape = in.shape();
+    for (int i = 0; i < n; i++) {
+      auto sh = in.tensor_shape(i);
+      std::vector<float> m;
+      GetGeneralizedArg<float>(make_span(m = std::vector<float>(6)), "matrix", i, spec_, ws);
+      auto &s = samples_[i];
+      s.in_h = s.out_h = static_cast<int>(sh[0]); s.in_w = s.out_w = static_cast<int>(sh[1]); s.channels = static_cast<int>(sh[2]);
+      if (invert_) dalib200AffineInverse(m.data(), s.matrix);                      // warp_affine_params.h:50-83
+      else for (int k = 0; k < 6; k++) s.matrix[k] = m[k];
+    }
+    Check(dalib200WarpPlanSetup(plan_, n, samples_.data(), interp_, use_fill_, fill_, DALIB200_UINT8), "WarpAffine");
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200WarpLaunch(plan_, ip.data(), op.data(), ws.stream()), "WarpAffine");
+  }
+
+ private:
+  dalib200WarpPlan *plan_ = nullptr;
+  std::vector<dalib200WarpSample> samples_;
+  bool interp_ = true, invert_ = false, use_fill_ = false;
+  float fill_ = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ Hsv / ColorSpaceConversion
+class PointwiseBase : public Operator<GPUBackend> {
+ public:
+  explicit PointwiseBase(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    Check(dalib200PointwisePlanCreate(&plan_, max_batch_size_), "pointwise");
+  }
+  ~PointwiseBase() override { dalib200PointwisePlanDestroy(plan_); }
+
+ protected:
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200PointwiseLaunch(plan_, ip.data(), op.data(), ws.stream()), "pointwise");
+  }
+  dalib200PointwisePlan *plan_ = nullptr;
+};
+
+class Hsv : public PointwiseBase {
+ public:
+  explicit Hsv(const OpSpec &spec) : PointwiseBase(spec) {}
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    const int n = in.num_samples();
+    std::vector<dalib200ColorSample> cs(n);
+    for (int i = 0; i < n; i++) {
+      cs[i].num_pixels = in.tensor_shape(i).num_elements() / 3;
+      dalib200ColorTwistMatrix(spec_.GetArgument<float>("hue", &ws, i), spec_.GetArgument<float>("saturation", &ws, i),
+                               spec_.GetArgument<float>("value", &ws, i), 1.0f, 1.0f, 128.0f, cs[i].matrix, cs[i].offset);
+    }
+    Check(dalib200LinearTransformSetup(plan_, n, cs.data(), DALIB200_UINT8), "Hsv");
+    out.resize(1);
+    out[0].shape = in.shape(); out[0].type = DALI_UINT8;
+    return true;
+  }
+};
+
+class ColorSpaceConversion : public PointwiseBase {
+ public:
+  explicit ColorSpaceConversion(const OpSpec &spec) : PointwiseBase(spec) {
+    in_t_ = static_cast<int>(spec.GetArgument<DALIImageType>("image_type"));
+    out_t_ = static_cast<int>(spec.GetArgument<DALIImageType>("output_type"));
+  }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    const int n = in.num_samples(), nd = in.shape().sample_dim();
+    const int ic = in_t_ == DALI_GRAY ? 1 : 3, oc = out_t_ == DALI_GRAY ? 1 : 3;
+    std::vector<int64_t> npx(n);
+    out.resize(1);
+    out[0].type = DALI_UINT8;
+    out[0].shape = in.shape();
+    for (int i = 0; i < n; i++) {
+      npx[i] = in.tensor_shape(i).num_elements() / ic;
+      auto sh = in.tensor_shape(i);
+      sh[nd - 1] = oc;
+      out[0].shape.set_tensor_shape(i, sh);
+    }
+    Check(dalib200ColorSpaceSetup(plan_, n, npx.data(), in_t_, out_t_), "ColorSpaceConversion");
+    return true;
+  }
+
+ private:
+  int in_t_ = 0, out_t_ = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ Spectrogram / MelFilterBank
+class Spectrogram : public Operator<GPUBackend> {
+ public:
+  explicit Spectrogram(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    args_.window_length = spec.GetArgument<int>("window_length");
+    args_.window_step = spec.GetArgument<int>("window_step");
+    args_.power = spec.GetArgument<int>("power");
+    args_.nfft = spec.HasArgument("nfft") ? spec.GetArgument<int>("nfft") : args_.window_length;
+    args_.center = spec.GetArgument<bool>("center_windows");
+    args_.reflect = spec.GetArgument<bool>("reflect_padding");
+    args_.layout_ft = spec.GetArgument<TensorLayout>("layout") == TensorLayout("ft");
+    if (spec.HasArgument("window_fn")) window_ = spec.GetRepeatedArgument<float>("window_fn");
+    Check(dalib200SpectrogramPlanCreate(&plan_, max_batch_size_), "Spectrogram");
+  }
+  ~Spectrogram() override { dalib200SpectrogramPlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    const int n = in.num_samples();
+    std::vector<int64_t> lens(n);
+    for (int i = 0; i < n; i++) lens[i] = in.tensor_shape(i).num_elements();
+    Check(dalib200SpectrogramPlanSetup(plan_, &args_, window_.empty() ? nullptr : window_.data(), n, lens.data()), "Spectrogram");
+    out.resize(1);
+    out[0].type = DALI_FLOAT;
+    out[0].shape.resize(n, 2);
+    const int64_t nbin = args_.nfft / 2 + 1;
+    for (int i = 0; i < n; i++) {
+      const int64_t nw = dalib200SpectrogramNumWindows(plan_, i);
+      out[0].shape.set_tensor_shape(i, args_.layout_ft ? TensorShape<>{nbin, nw} : TensorShape<>{nw, nbin});
+    }
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(args_.layout_ft ? "ft" : "tf");
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200SpectrogramLaunch(plan_, ip.data(), op.data(), ws.stream()), "Spectrogram");
+  }
+
+ private:
+  dalib200SpectrogramPlan *plan_ = nullptr;
+  dalib200SpectrogramArgs args_{};
+  std::vector<float> window_;
+};
+
+class MelFilterBank : public Operator<GPUBackend> {
+ public:
+  explicit MelFilterBank(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    args_.nfilter = spec.GetArgument<int>("nfilter");
+    args_.sample_rate = spec.GetArgument<float>("sample_rate");
+    args_.freq_low = spec.GetArgument<float>("freq_low"); args_.freq_high = spec.GetArgument<float>("freq_high");
+    args_.normalize = spec.GetArgument<bool>("normalize");
+    args_.htk = spec.GetArgument<std::string>("mel_formula") == "htk";
+    Check(dalib200MelPlanCreate(&plan_, max_batch_size_), "MelFilterBank");
+  }
+  ~MelFilterBank() override { dalib200MelPlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    const int n = in.num_samples();
+    std::vector<int64_t> nwin(n);
+    const int nbin = n ? static_cast<int>(in.tensor_shape(0)[0]) : 2;
+    out.resize(1);
+    out[0].type = DALI_FLOAT;
+    out[0].shape.resize(n, 2);
+    for (int i = 0; i < n; i++) {
+      nwin[i] = in.tensor_shape(i)[1];
+      out[0].shape.set_tensor_shape(i, TensorShape<>{args_.nfilter, nwin[i]});
+    }
+    Check(dalib200MelPlanSetup(plan_, &args_, nbin, n, nwin.data()), "MelFilterBank");
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout("ft");
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200MelLaunch(plan_, ip.data(), op.data(), ws.stream()), "MelFilterBank");
+  }
+
+ private:
+  dalib200MelPlan *plan_ = nullptr;
+  dalib200MelArgs args_{};
+};
+
+}  // namespace b200
+
+namespace dali {       // the registration macros expect the dali namespace (operator.h:327-333)
+
+DALI_SCHEMA(b200__decoders__Image).NumInput(1).NumOutput(1).AddParent("decoders__Image");
+DALI_SCHEMA(b200__Resize).NumInput(1).NumOutput(1).AddParent("Resize");
+DALI_SCHEMA(b200__CropMirrorNormalize).NumInput(1).NumOutput(1).AddParent("CropMirrorNormalize");
+DALI_SCHEMA(b200__WarpAffine).NumInput(1).NumOutput(1).AddParent("WarpAffine");
+DALI_SCHEMA(b200__Hsv).NumInput(1).NumOutput(1).AddParent("Hsv");
+DALI_SCHEMA(b200__ColorSpaceConversion).NumInput(1).NumOutput(1).AddParent("ColorSpaceConversion");
+DALI_SCHEMA(b200__Spectrogram).NumInput(1).NumOutput(1).AddParent("Spectrogram");
+DALI_SCHEMA(b200__MelFilterBank).NumInput(1).NumOutput(1).AddParent("MelFilterBank");
+
+DALI_REGISTER_OPERATOR(b200__decoders__Image, b200::ImageDecoder, Mixed);
+DALI_REGISTER_OPERATOR(b200__Resize, b200::Resize, GPU);
+DALI_REGISTER_OPERATOR(b200__CropMirrorNormalize, b200::CropMirrorNormalize, GPU);
+DALI_REGISTER_OPERATOR(b200__WarpAffine, b200::WarpAffine, GPU);
+DALI_REGISTER_OPERATOR(b200__Hsv, b200::Hsv, GPU);
+DALI_REGISTER_OPERATOR(b200__ColorSpaceConversion, b200::ColorSpaceConversion, GPU);
+DALI_REGISTER_OPERATOR(b200__Spectrogram, b200::Spectrogram, GPU);
+DALI_REGISTER_OPERATOR(b200__MelFilterBank, b200::MelFilterBank, GPU);
+
+}  // namespace dali

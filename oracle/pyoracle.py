@@ -437,3 +437,21 @@ def ref_mfcc(mel, n_mfcc=20, dct_type=2, normalize=False, lifter=0.0):
     rows = ref().ref_mfcc(_p(a), nfeat, C.c_int64(ncols), _p(out), int(n_mfcc), int(dct_type), int(bool(normalize)), C.c_float(lifter))
     assert rows == out.shape[0], rows
     return out
+
+
+# ------------------------------------------------------------------------------------------- f4 operators
+def ref_rotate_params(angle_deg, in_h, in_w, keep_size=False, size=None):
+    """(out_h, out_w), 2x3 destination->source matrix of fn.rotate (rotate_params.h, built from the reference's transform.h)."""
+    hw = (C.c_int * 2)()
+    M = np.empty(6, np.float32)
+    sz = None if size is None else (C.c_float * 2)(float(size[0]), float(size[1]))
+    ref().ref_rotate_params(C.c_float(angle_deg), int(in_h), int(in_w), int(bool(keep_size)), sz, hw, _p(M))
+    return (hw[0], hw[1]), M.reshape(2, 3)
+
+
+def ref_brightness_contrast(img, brightness=1.0, brightness_shift=0.0, contrast=1.0, contrast_center=128.0, out_float=False):
+    a = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(a.shape, np.float32 if out_float else np.uint8)
+    ref().ref_brightness_contrast(_p(a), C.c_size_t(a.size), int(bool(out_float)), C.c_float(brightness), C.c_float(brightness_shift),
+                                  C.c_float(contrast), C.c_float(contrast_center), _p(out))
+    return out

@@ -16,6 +16,10 @@
 #include "dali/core/random/philox.h"
 #include "dali/kernels/imgproc/color_manipulation/color_space_conversion_impl.h"
 #include "dali/operators/image/crop/random_crop_generator_util.h"
+#include "dali/core/geom/transform.h"
+#include "dali/core/math_util.h"
+#include "dali/operators/image/remap/rotate_params.h"
+#include "dali/operators/image/color/brightness_contrast.h"
 
 using namespace dali;  // NOLINT
 
@@ -58,6 +62,48 @@ int ref_random_crop(int64_t seed, int sample_idx, int H, int W, float ar_lo, flo
 int ref_decoder_convert(const uint8_t *in, size_t npix, int in_c, int out_type, int out_float, void *out) {
   if (out_float) ConvertPixels<float>(in, npix, in_c, out_type, static_cast<float *>(out));
   else ConvertPixels<uint8_t>(in, npix, in_c, out_type, static_cast<uint8_t *>(out));
+  return 0;
+}
+
+
+// Rotate: output canvas (rotate_params.h:36-55 RotatedCanvasSize + the parity vote of InferSize :279-297 for one frame) and the
+// destination -> source matrix of AdjustParams (:222-236), built from the reference's own geom/transform.h functions.
+int ref_rotate_params(float angle_deg, int in_h, int in_w, int keep_size, const float *size_hw, int *out_hw, float *M) {
+  float neg = -angle_deg;                                  // SetParams(): 2-D angles are negated
+  int oh, ow;
+  if (size_hw) { oh = std::max<int>(static_cast<int>(std::roundf(size_hw[0])), 1); ow = std::max<int>(static_cast<int>(std::roundf(size_hw[1])), 1); }
+  else if (keep_size) { oh = in_h; ow = in_w; }
+  else {
+    ivec2 shape, parity;
+    std::tie(shape, parity) = RotatedCanvasSize(TensorShape<2>(in_h, in_w), deg2rad(neg));
+    ivec2 acc_shape = shape, acc_parity = parity;
+    const int num_frames = 1;
+    acc_shape += (acc_shape % 2) ^ (2 * acc_parity > num_frames);
+    ow = acc_shape[0]; oh = acc_shape[1];
+  }
+  ivec2 in_size(in_w, in_h), out_size(ow, oh);
+  float a = deg2rad(neg);
+  mat3 T = translation(in_size * 0.5f) * rotation2D(-a) * translation(-out_size * 0.5f);
+  auto P = sub<2, 3>(T);
+  for (int r = 0; r < 2; r++) for (int c = 0; c < 3; c++) M[r * 3 + c] = P(r, c);
+  out_hw[0] = oh; out_hw[1] = ow;
+  return 0;
+}
+
+// BrightnessContrast: OpArgsToKernelArgs<Out, uint8_t> (brightness_contrast.h:84-103; protected member, built with
+// -fno-access-control) and the element functor of the CPU kernel (multiply_add.h:47-60)
+struct BcProbe : BrightnessContrastOp<CPUBackend> {
+  using BrightnessContrastOp<CPUBackend>::OpArgsToKernelArgs;
+};
+int ref_brightness_contrast(const uint8_t *in, size_t n, int out_float, float brightness, float shift, float contrast, float center, void *out) {
+  float addend, multiplier;
+  BcProbe *probe = nullptr;                                // OpArgsToKernelArgs touches no member
+  if (out_float) probe->OpArgsToKernelArgs<float, uint8_t>(addend, multiplier, brightness, shift, contrast, center);
+  else probe->OpArgsToKernelArgs<uint8_t, uint8_t>(addend, multiplier, brightness, shift, contrast, center);
+  for (size_t i = 0; i < n; i++) {
+    if (out_float) static_cast<float *>(out)[i] = ConvertSat<float>(in[i] * multiplier + addend);
+    else static_cast<uint8_t *>(out)[i] = ConvertSat<uint8_t>(in[i] * multiplier + addend);
+  }
   return 0;
 }
 

@@ -264,3 +264,29 @@ def test_output_type_and_dtype_conversion_match_reference_convert():
     out, _ = g.jpeg_decode_ex([s6], output_type=capi.YCbCr, dtype=capi.FLOAT, rois=[(3, 9, 150, 260)])
     want = po.ref_decoder_convert(np.ascontiguousarray(po.exif_transform(full[0], 6)[9:260, 3:150]), po.IT_YCBCR, True)
     assert np.array_equal(out[0], want)
+
+
+def test_truncated_stream_status_gray_tail_and_pipeline_error():
+    """A stream cut in the middle of the scan: status 1, everything decoded before the damage is intact, the MCU rows well behind it
+    are mid-gray (libjpeg leaves all-zero blocks there: jdhuff.c insufficient_data), and a pipeline raises at run() -- the status
+    words travel with the outputs (no extra synchronisation)."""
+    import cv2
+    import gpu_helpers as g
+    from dali_b200 import fn, pipeline_def
+    good = _enc(g.synth_image(240, 320, 31), 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420)
+    full = po.jpeg_decode(good)
+    cut = good[: len(good) * 6 // 10]
+    outs, status = g.jpeg_decode([cut, good])
+    assert status == [1, 0]
+    assert np.array_equal(outs[1], full)
+    assert np.array_equal(outs[0][:96], full[:96])                        # 60 % of the bytes cover more than 40 % of the rows
+    assert (outs[0][-48:] == 128).all()                                   # zero coefficients, DC 0 -> Y = Cb = Cr = 128 -> RGB gray
+    streams = [np.frombuffer(cut, np.uint8), np.frombuffer(good, np.uint8)]
+
+    @pipeline_def(batch_size=2, num_threads=1, device_id=0, prefetch_queue_depth=1)
+    def pipe():
+        return fn.decoders.image(fn.external_source(source=lambda i: streams), device="mixed")
+    p = pipe()
+    p.build()
+    with pytest.raises(RuntimeError, match="Failed to decode sample #0"):
+        p.run()

@@ -225,7 +225,51 @@ def test_decoder_crop_family_and_random_resized_crop():
                 assert np.array_equal(e[i], want), (it, i)
             ax, ay = float(anchors[i][0]), float(anchors[i][1])
             sx, sy = float(shapes[i][0]), float(shapes[i][1])
-            bx, ex = int(round(ax * W)), int(round((ax + sx) * W))
-            by, ey = int(round(ay * H)), int(round((ay + sy) * H))
+            rnd = lambda v: int(np.floor(v + 0.5))                   # std::llround: half away from zero (slice_attr.h:330-331)
+            bx, ex = rnd(ax * W), rnd((ax + sx) * W)
+            by, ey = rnd(ay * H), rnd((ay + sy) * H)
             assert np.array_equal(c[i], full[by:ey, bx:ex]), (it, i)
             assert np.array_equal(d[i], full[16:116, 30:94]), (it, i)
+
+
+def test_decoder_resize_fusion_in_the_executor():
+    """decoders.image* -> resize with no other consumer of the decoded image: the executor links the two operators, the Resize reads
+    the decoder's planes (kernel `resample_planar`) for the samples that qualify and the usual path for the rest (grayscale, 4:4:4);
+    results equal decode-then-resize / crop-then-resize on the oracle, and the unfused pipeline (image also returned) bit for bit."""
+    import cv2
+    import gpu_helpers as g
+    from dali_b200 import capi, fn, pipeline_def
+    streams = _jpegs(3, 480, 640, 90)
+    ok, enc = cv2.imencode(".jpg", g.synth_image(300, 400, 95), [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])
+    streams.append(np.ascontiguousarray(enc.ravel()))
+    ok, enc = cv2.imencode(".jpg", g.synth_image(300, 400, 96)[..., 0], [cv2.IMWRITE_JPEG_QUALITY, 90])
+    streams.append(np.ascontiguousarray(enc.ravel()))
+    n = len(streams)
+
+    def build(keep_image):
+        @pipeline_def(batch_size=n, num_threads=2, device_id=0)
+        def pipe():
+            jpegs = fn.external_source(source=lambda i: streams)
+            img = fn.decoders.image(jpegs, device="mixed")
+            a = fn.resize(img, resize_x=160, resize_y=120)
+            crop = fn.decoders.image_random_crop(jpegs, device="mixed", seed=5)
+            b = fn.resize(crop, size=[64, 64])
+            return (a, b, img) if keep_image else (a, b)
+        p = pipe()
+        p.build()
+        return p
+    capi.profiling(True); capi.profiling_collect()
+    fused = [o.as_cpu() for o in build(False).run()]
+    names = {k for k, _ in capi.profiling_collect()}
+    plain = [o.as_cpu() for o in build(True).run()]          # `img` is a pipeline output there: the first pair is not fused
+    capi.profiling(False)
+    assert "resample_planar" in names
+    for i, s in enumerate(streams):
+        full = po.jpeg_decode(s.tobytes())
+        assert np.array_equal(fused[0][i], po.resample(full, (120, 160))), i
+        assert np.array_equal(fused[0][i], plain[0][i]) and np.array_equal(fused[1][i], plain[1][i]), i
+        assert np.array_equal(plain[2][i], full), i
+        if po.have_ref():
+            H, W = full.shape[:2]
+            wy, wx, wh, ww = po.ref_random_crop(5, i, H, W)[0]
+            assert np.array_equal(fused[1][i], po.resample(np.ascontiguousarray(full[wy:wy + wh, wx:wx + ww]), (64, 64))), i

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from dali_b200 import backend, fn, types, pipeline_def, Pipeline
+from oracle import pyoracle as po
 
 
 def test_schema_registry_and_fn_names():
@@ -128,3 +129,43 @@ def test_external_source_feeding_modes():
     assert calls[4] == (4, 0, 1)
     with pytest.raises(StopIteration):
         p.run()
+
+
+@pytest.mark.skipif(not po.have_ref(), reason="needs oracle/_ref")
+def test_rotate_params_match_reference_transform_code():
+    """fn.rotate: canvas size (RotatedCanvasSize + parity vote) and the 2x3 matrix equal the reference's own
+    translation * rotation2D * translation (rotate_params.h:36-55,222-236,279-297), bit for bit."""
+    import ctypes as C
+    from dali_b200 import backend
+    h = backend.lib()
+    rng = np.random.default_rng(3)
+    for t in range(400):
+        ang = float(rng.uniform(-400, 400)) if t > 8 else [0.0, 90.0, -90.0, 180.0, 45.0, -45.0, 30.0, 270.0, 360.0][t]
+        H, W = int(rng.integers(1, 900)), int(rng.integers(1, 900))
+        mode = t % 3
+        size = (float(rng.uniform(1, 500)), float(rng.uniform(1, 500))) if mode == 1 else None
+        hw = (C.c_int * 2)()
+        M = np.empty(6, np.float32)
+        sz = None if size is None else (C.c_float * 2)(*size)
+        h.dalihTestRotateParams(C.c_float(ang), H, W, int(mode == 2), sz, hw, M.ctypes.data_as(C.c_void_p))
+        want_hw, want_M = po.ref_rotate_params(ang, H, W, keep_size=mode == 2, size=size)
+        assert (hw[0], hw[1]) == want_hw, (ang, H, W, mode)
+        assert np.array_equal(M.view(np.uint32), want_M.reshape(-1).view(np.uint32)), (ang, H, W, mode)
+
+
+@pytest.mark.skipif(not po.have_ref(), reason="needs oracle/_ref")
+def test_random_crop_generator_matches_reference():
+    """decoders.image_random_crop / random_resized_crop draw the reference's windows: Philox4x32-10 with RandomCropAttr's per-sample
+    states feeding the same libstdc++ distributions (random_crop_generator_util.cc, random_crop_attr.h:36-72)."""
+    import ctypes as C
+    from dali_b200 import backend
+    h = backend.lib()
+    rng = np.random.default_rng(1)
+    for t in range(200):
+        seed, si = int(rng.integers(0, 2 ** 31)), int(rng.integers(0, 300))
+        H, W = int(rng.integers(1, 2000)), int(rng.integers(1, 2000))
+        ar, area, na = sorted(rng.uniform(0.2, 3.0, 2)), sorted(rng.uniform(0.01, 1.0, 2)), int(rng.integers(1, 12))
+        a = (C.c_int * 40)()
+        h.dalihTestRandomCrop(C.c_int64(seed), si, H, W, C.c_float(ar[0]), C.c_float(ar[1]), C.c_float(area[0]), C.c_float(area[1]), na, 10, a)
+        want = po.ref_random_crop(seed, si, H, W, ar, area, na, 10)
+        assert [tuple(a[4 * k:4 * k + 4]) for k in range(10)] == want, (seed, si, H, W)

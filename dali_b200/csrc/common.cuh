@@ -145,6 +145,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// TMA tiled load through a tensor map (cuTensorMapEncodeTiled): a boxDim[0] x boxDim[1] x 1 tile of a rank-3 tensor at element
+// coordinates (c0, c1, c2) into shared memory; out-of-range parts of the box are zero filled by the unit.  SASS: UTMALDG.3D.
+__device__ __forceinline__ void tma_load_3d(void *dst, const void *tmap, int c0, int c1, int c2, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               :: "r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
 #endif  // __CUDACC__
 
 }  // namespace dalib200

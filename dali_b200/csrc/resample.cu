@@ -601,7 +601,11 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
         for (int q = 0; q < NW; q++) w[q] = rw[tid + q * kStConsumers];       // the slot is kStRowBytes long: always in bounds
         // release the slot only once the words have ARRIVED in registers (the asm consumes them): the LDS of a warp completes
         // for all lanes together, and the slot is rewritten by the async proxy as soon as all 8 warps have arrived
+#ifndef DALIB200_NO_RING_FENCE
         asm volatile("fence.proxy.async.shared::cta;" :: "r"(w[0]), "r"(w[NW - 1]) : "memory");
+#else
+        asm volatile("" :: "r"(w[0]), "r"(w[NW - 1]) : "memory");
+#endif
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == kStStages) { stage = 0; par ^= 1u; }
@@ -828,7 +832,11 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_planar_kernel(const Rs
           crf[0] = lds_u8(a_c + 3 * kPlChroma + o_prev); crf[1] = lds_u8(a_c + 3 * kPlChroma + coff); crf[2] = lds_u8(a_c + 3 * kPlChroma + o_next);
         }
         // release the slot once the values have ARRIVED in registers (see resample_stream_kernel)
+#ifndef DALIB200_NO_RING_FENCE
         asm volatile("fence.proxy.async.shared::cta;" :: "r"(yw), "r"(crf[2]) : "memory");
+#else
+        asm volatile("" :: "r"(yw), "r"(crf[2]), "r"(cbn[0]), "r"(cbf[1]), "r"(crn[2]) : "memory");
+#endif
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == kPlStages) { stage = 0; par ^= 1u; }

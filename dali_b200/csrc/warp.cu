@@ -13,6 +13,7 @@
 //
 // Algorithmic bytes per unit: in_h*in_w*C + out_h*out_w*C*sizeof(Out).
 #include "common.cuh"
+#include <cuda.h>            // CUtensorMap (the encoder is resolved through cudaGetDriverEntryPoint: no libcuda link dependency)
 #include <algorithm>
 #include <cstring>
 
@@ -180,6 +181,132 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const WarpDesc *__rest
   }
 }
 
+// =============================================================================================
+// Tensor-map TMA variant (uniform batches of 3-channel u8 frames, bilinear): the source box of a 16 x 128 output tile is staged in
+// shared memory by ONE tiled TMA load (cp.async.bulk.tensor.3d through a CUtensorMap over the whole batch viewed as
+// [frame][row][32-bit word]; SASS UTMALDG.3D) and the four taps of every pixel come from there instead of six word loads per pixel
+// through L1.  The box is sized from the tile's replayed corner coordinates: 448 bytes x 48 rows covers rotations of about +-12
+// degrees at unit scale; tiles whose footprint is larger or touches the image border take the generic path of
+// warp_affine_kernel.  Coordinates are still replayed (bit-exact with the reference CPU kernel).
+constexpr int kTmaTileW = 128, kTmaTileH = 16;
+constexpr int kTmaBoxBytes = 448, kTmaBoxRows = 48;
+
+template <bool CLAMP>
+__global__ void __launch_bounds__(256) warp_affine_tma_kernel(const WarpDesc *__restrict__ descs, int n, int64_t total_tiles, float border,
+                                                              const __grid_constant__ CUtensorMap tmap) {
+  __shared__ __align__(128) uint8_t box[kTmaBoxRows * kTmaBoxBytes];
+  __shared__ float2 coords[kTmaTileH][kTmaTileW];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_first, s_use, s_bx, s_by;
+  const int64_t per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * per_cta, t1 = min(total_tiles, t0 + per_cta);
+  if (t0 >= t1) return;
+  if (threadIdx.x == 0) {
+    s_first = find_warp_sample(descs, n, t0);
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int s = s_first;
+  uint32_t phase = 0;
+  for (int64_t tile = t0; tile < t1; tile++) {
+    while (s + 1 < n && descs[s + 1].first_tile <= tile) s++;
+    const WarpDesc &d = descs[s];
+    const int64_t tl = tile - d.first_tile;
+    const int ty = (int)(tl / d.tiles_x), tx = (int)(tl % d.tiles_x);
+    const int y0 = ty * kTmaTileH, x0 = tx * kTmaTileW;
+    const int th = min(kTmaTileH, d.out_h - y0), tw = min(kTmaTileW, d.out_w - x0);
+    // ---- stage 1: replay the reference's coordinate accumulation (re-anchored every 256 pixels), one thread per row
+    if (threadIdx.x < th) {
+      const int y = y0 + threadIdx.x;
+      const float vx = 0.5f, vy = (float)y + 0.5f;
+      float sx = add_rn(add_rn(d.m[2], mul_rn(d.m[0], vx)), mul_rn(d.m[1], vy));
+      float sy = add_rn(add_rn(d.m[5], mul_rn(d.m[3], vx)), mul_rn(d.m[4], vy));
+      const float dx = d.m[0], dy = d.m[3];
+      const float tdx = mul_rn(256.0f, dx), tdy = mul_rn(256.0f, dy);
+      for (int t = 0; t < x0 / kWarpTileW; t++) { sx = add_rn(sx, tdx); sy = add_rn(sy, tdy); }
+      for (int j = 0; j < x0 % kWarpTileW; j++) { sx = add_rn(sx, dx); sy = add_rn(sy, dy); }
+      for (int j = 0; j < tw; j++) {
+        coords[threadIdx.x][j] = make_float2(sx, sy);
+        sx = add_rn(sx, dx); sy = add_rn(sy, dy);
+      }
+    }
+    __syncthreads();
+    // ---- source box of the tile (the map is affine: the extremes sit at the corners; one pixel of margin covers the rounding of the
+    //      replayed coordinates) and the TMA load
+    if (threadIdx.x == 0) {
+      const float2 c00 = coords[0][0], c01 = coords[0][tw - 1], c10 = coords[th - 1][0], c11 = coords[th - 1][tw - 1];
+      const float minx = fminf(fminf(c00.x, c01.x), fminf(c10.x, c11.x)), maxx = fmaxf(fmaxf(c00.x, c01.x), fmaxf(c10.x, c11.x));
+      const float miny = fminf(fminf(c00.y, c01.y), fminf(c10.y, c11.y)), maxy = fmaxf(fmaxf(c00.y, c01.y), fmaxf(c10.y, c11.y));
+      const int ix0 = (int)floorf(minx - 0.5f) - 1, ix1 = (int)floorf(maxx - 0.5f) + 2;      // taps ix .. ix + 1, margin 1
+      const int iy0 = (int)floorf(miny - 0.5f) - 1, iy1 = (int)floorf(maxy - 0.5f) + 2;
+      const int bx = (ix0 * 3) & ~3;                                     // byte column of the box, 32-bit aligned
+      const bool fits = (ix1 + 1) * 3 - bx <= kTmaBoxBytes && iy1 - iy0 + 1 <= kTmaBoxRows;
+      // the 12-byte windows read per tap pair must stay inside the image rows: two pixels of slack on the right
+      const bool inside = ix0 >= 0 && iy0 >= 0 && ix1 + 2 < d.in_w && iy1 < d.in_h;
+      s_use = fits && inside;
+      s_bx = bx; s_by = iy0;
+      if (s_use) {
+        mbar_expect_tx(&bar, kTmaBoxRows * kTmaBoxBytes);
+        tma_load_3d(box, &tmap, bx >> 2, iy0, s, &bar);
+      }
+    }
+    __syncthreads();
+    const bool use_box = s_use != 0;
+    const int bxb = s_bx, by0 = s_by;
+    if (use_box) { mbar_wait(&bar, phase); phase ^= 1u; }
+    // ---- stage 2: sample; one thread = 4 consecutive pixels of a row
+    uint8_t *out = static_cast<uint8_t *>(d.out);
+    const int gpr = (tw + 3) >> 2;
+    const uint32_t a_box = smem_u32(box);
+    for (int e = threadIdx.x; e < th * gpr; e += blockDim.x) {
+      const int r = e / gpr, j0 = (e - r * gpr) << 2;
+      const int np = min(4, tw - j0);
+      uint8_t *o = out + ((int64_t)(y0 + r) * d.out_w + x0 + j0) * 3;
+      uint32_t b[12];
+      for (int k = 0; k < np; k++) {
+        float res[3];
+        const float2 src = coords[r][j0 + k];
+        if (use_box) {
+          const float fx = sub_rn(src.x, 0.5f), fy = sub_rn(src.y, 0.5f);
+          const float flx = floorf(fx), fly = floorf(fy);
+          const int ix = (int)flx, iy = (int)fly;
+          const float qx = sub_rn(fx, flx), px = sub_rn(1.0f, qx), qy = sub_rn(fy, fly);
+          float t[2][6];
+#pragma unroll
+          for (int rr = 0; rr < 2; rr++) {
+            const uint32_t off = (uint32_t)((iy + rr - by0) * kTmaBoxBytes + ix * 3 - bxb);
+            const uint32_t sh = off & 3u, a = a_box + (off & ~3u);
+            const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 4), w2 = lds_u32(a + 8);
+            const uint32_t lo = __funnelshift_r(w0, w1, sh * 8u), hi = __funnelshift_r(w1, w2, sh * 8u);
+            t[rr][0] = u8_to_float(lo & 0xFFu); t[rr][1] = u8_to_float((lo >> 8) & 0xFFu); t[rr][2] = u8_to_float((lo >> 16) & 0xFFu);
+            t[rr][3] = u8_to_float(lo >> 24); t[rr][4] = u8_to_float(hi & 0xFFu); t[rr][5] = u8_to_float((hi >> 8) & 0xFFu);
+          }
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const float s0 = add_rn(mul_rn(t[0][c], px), mul_rn(t[0][3 + c], qx));
+            const float s1 = add_rn(mul_rn(t[1][c], px), mul_rn(t[1][3 + c], qx));
+            res[c] = add_rn(s0, mul_rn(sub_rn(s1, s0), qy));
+          }
+        } else {
+          warp_pixel<uint8_t, true, CLAMP, 3>(d, src, border, 3, res);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) b[3 * k + c] = (uint32_t)sat_u8_half_away(res[c]);
+      }
+      if (np == 4 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+        uint32_t *o4 = reinterpret_cast<uint32_t *>(o);
+        o4[0] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        o4[1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+        o4[2] = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+      } else {
+        for (int k = 0; k < np * 3; k++) o[k] = (uint8_t)b[k];
+      }
+    }
+    __syncthreads();           // the box and the coordinates are rewritten by the next tile
+  }
+}
+
 }  // namespace dalib200
 
 using namespace dalib200;  // NOLINT
@@ -192,9 +319,31 @@ struct dalib200WarpPlan {
   DescArena arena;
   cudaEvent_t uploaded = nullptr;
   bool pending = false;
+  // tensor-map path (uniform batches): descriptors re-tiled to 16 x 128, map cached per (base, stride, shape)
+  std::vector<dalib200WarpSample> samples;
+  CUtensorMap tmap;
+  const void *tmap_base = nullptr; size_t tmap_stride = 0; int tmap_h = 0, tmap_w = 0, tmap_n = 0;
+  int path = 0;                  // 1 = the last launch used the tensor-map kernel
 };
 
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn GetEncodeTiled() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+}  // namespace
+
 extern "C" {
+
+int dalib200WarpPlanGetPath(const dalib200WarpPlan *p) { return p ? p->path : -1; }
 
 void dalib200AffineInverse(const float *M, float *out) {
   // include/dali/core/geom/transform.h:166-174 + mat.h:611-623: m = adj(2x2)/det ; t = (-m) * t
@@ -237,6 +386,7 @@ int dalib200WarpPlanSetup(dalib200WarpPlan *p, int n, const dalib200WarpSample *
   DB_CHECK_ARG(out_dtype == DALIB200_UINT8 || out_dtype == DALIB200_FLOAT, "WarpAffine: output type %d not supported", out_dtype);
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
   auto *descs = reinterpret_cast<WarpDesc *>(p->arena.host);
+  p->samples.assign(samples, samples + n);
   int64_t tiles = 0;
   for (int i = 0; i < n; i++) {
     const auto &s = samples[i];
@@ -264,15 +414,73 @@ int dalib200WarpLaunch(dalib200WarpPlan *p, const void *const *in_ptrs, void *co
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
   auto *descs = reinterpret_cast<WarpDesc *>(p->arena.host);
   for (int i = 0; i < p->n; i++) { descs[i].in = static_cast<const uint8_t *>(in_ptrs[i]); descs[i].out = out_ptrs[i]; }
+  // ---- tensor-map path: bilinear u8 -> u8 over a uniform batch of 3-channel frames laid out at a constant stride
+  bool tma = p->interp == 1 && p->out_dtype == DALIB200_UINT8 && p->n >= 1 && !getenv("DALIB200_WARP_NO_TMA") && GetEncodeTiled() != nullptr;
+  const auto &s0 = p->samples[0];
+  size_t stride = 0;
+  if (tma) {
+    tma = s0.channels == 3 && (s0.in_w * 3) % 16 == 0 && reinterpret_cast<uintptr_t>(in_ptrs[0]) % 16 == 0 && s0.in_w * 3 / 4 >= kTmaBoxBytes / 4 &&
+          s0.in_h >= 1;
+    if (tma && p->n > 1) {
+      stride = static_cast<const uint8_t *>(in_ptrs[1]) - static_cast<const uint8_t *>(in_ptrs[0]);
+      tma = static_cast<const uint8_t *>(in_ptrs[1]) > static_cast<const uint8_t *>(in_ptrs[0]) && stride % 16 == 0 &&
+            stride >= (size_t)s0.in_h * s0.in_w * 3;
+    } else if (tma) {
+      stride = (size_t)s0.in_h * s0.in_w * 3;
+    }
+    for (int i = 0; i < p->n && tma; i++) {
+      const auto &s = p->samples[i];
+      tma = s.in_h == s0.in_h && s.in_w == s0.in_w && s.channels == 3 &&
+            static_cast<const uint8_t *>(in_ptrs[i]) == static_cast<const uint8_t *>(in_ptrs[0]) + (size_t)i * stride;
+    }
+  }
+  if (tma && (p->tmap_base != in_ptrs[0] || p->tmap_stride != stride || p->tmap_h != s0.in_h || p->tmap_w != s0.in_w || p->tmap_n != p->n)) {
+    // the batch as a rank-3 tensor of 32-bit words: [frame][row][word]; box = 112 words x 48 rows x 1 frame
+    const cuuint64_t dims[3] = { (cuuint64_t)s0.in_w * 3 / 4, (cuuint64_t)s0.in_h, (cuuint64_t)p->n };
+    const cuuint64_t strides[2] = { (cuuint64_t)s0.in_w * 3, (cuuint64_t)stride };
+    const cuuint32_t box[3] = { kTmaBoxBytes / 4, kTmaBoxRows, 1 }, estr[3] = { 1, 1, 1 };
+    const CUresult r = GetEncodeTiled()(&p->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(in_ptrs[0]), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) tma = false;
+    else { p->tmap_base = in_ptrs[0]; p->tmap_stride = stride; p->tmap_h = s0.in_h; p->tmap_w = s0.in_w; p->tmap_n = p->n; }
+  }
+  p->path = tma ? 1 : 0;
+  int64_t total_tiles = p->total_tiles;
+  if (tma) {                     // 16 x 128 tiles
+    total_tiles = 0;
+    for (int i = 0; i < p->n; i++) {
+      descs[i].tiles_x = (descs[i].out_w + kTmaTileW - 1) / kTmaTileW;
+      descs[i].tiles_y = (descs[i].out_h + kTmaTileH - 1) / kTmaTileH;
+      descs[i].first_tile = total_tiles;
+      total_tiles += (int64_t)descs[i].tiles_x * descs[i].tiles_y;
+    }
+  } else {
+    int64_t t = 0;
+    for (int i = 0; i < p->n; i++) {
+      descs[i].tiles_x = (descs[i].out_w + kWarpTileW - 1) / kWarpTileW;
+      descs[i].tiles_y = (descs[i].out_h + kWarpTileH - 1) / kWarpTileH;
+      descs[i].first_tile = t;
+      t += (int64_t)descs[i].tiles_x * descs[i].tiles_y;
+    }
+  }
   int rc = p->arena.Upload(sizeof(WarpDesc) * p->n, stream);
   if (rc) return rc;
   DB_CUDA(cudaEventRecord(p->uploaded, stream));
   p->pending = true;
   const auto *dd = reinterpret_cast<const WarpDesc *>(p->arena.dev);
-  const int grid = (int)std::min<int64_t>(p->total_tiles, (int64_t)NumSMs() * 16);
-  ProfScope ps_("warp_affine", stream);
+  const int grid = (int)std::min<int64_t>(total_tiles, (int64_t)NumSMs() * 16);
   const bool lin = p->interp == 1, clampb = !p->use_fill, u8 = p->out_dtype == DALIB200_UINT8;
-#define LAUNCH(O, L, Cc) warp_affine_kernel<O, L, Cc><<<grid, 256, 0, stream>>>(dd, p->n, p->total_tiles, p->border)
+  if (tma) {
+    ProfScope ps_("warp_affine_tma", stream);
+    if (clampb) warp_affine_tma_kernel<true><<<grid, 256, 0, stream>>>(dd, p->n, total_tiles, p->border, p->tmap);
+    else warp_affine_tma_kernel<false><<<grid, 256, 0, stream>>>(dd, p->n, total_tiles, p->border, p->tmap);
+    CountLaunch();
+    DB_CUDA(cudaGetLastError());
+    return DALIB200_SUCCESS;
+  }
+  ProfScope ps_("warp_affine", stream);
+#define LAUNCH(O, L, Cc) warp_affine_kernel<O, L, Cc><<<grid, 256, 0, stream>>>(dd, p->n, total_tiles, p->border)
   if (u8) {
     if (lin) { if (clampb) LAUNCH(uint8_t, true, true); else LAUNCH(uint8_t, true, false); }
     else     { if (clampb) LAUNCH(uint8_t, false, true); else LAUNCH(uint8_t, false, false); }

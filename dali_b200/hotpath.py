@@ -32,7 +32,7 @@ def cmn_norm_args(mean, std, scale=1.0, shift=0.0):
 class ImagePipelineC2:
     """decode (mixed) -> resize(out_h, out_w) -> crop_mirror_normalize(fp16/fp32, CHW) for one batch."""
 
-    def __init__(self, max_batch, out_hw=(224, 224), out_dtype="float16", mean=IMAGENET_MEAN, std=IMAGENET_STD, device=None, fused=True):
+    def __init__(self, max_batch, out_hw=(224, 224), out_dtype="float16", mean=IMAGENET_MEAN, std=IMAGENET_STD, device=None, fused=False):
         import torch
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -41,6 +41,7 @@ class ImagePipelineC2:
         self.out_dtype = torch.float16 if out_dtype in ("float16", torch.float16) else torch.float32
         # fused: samples that qualify (4:2:0 YCbCr streams, stream-eligible resize) are resized straight from the decoder's planes
         # (dalib200ResampleLaunchPlanar); the decoded RGB image is then never written.  The others take the two-kernel path.
+        # Off by default: less DRAM traffic but ~4 % more time per batch at 1080p (both variants are issue-bound).
         self.fused = bool(fused)
         self.jpeg = capi.Plan("Jpeg", max_batch)
         self.resample = capi.Plan("Resample", max_batch)

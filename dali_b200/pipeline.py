@@ -40,8 +40,9 @@ class DataNode:
 class TensorListGPU:
     """Output batch living in device memory.  Uniform batches expose __cuda_array_interface__ (zero copy into torch)."""
 
-    def __init__(self, dtype, layout, contiguous, shapes, ptrs, stream):
+    def __init__(self, dtype, layout, contiguous, shapes, ptrs, stream, owner=None):
         self._dtype, self._layout, self._contig, self._shapes, self._ptrs, self._stream = dtype, layout, contiguous, shapes, ptrs, stream
+        self._owner = owner          # the pipeline that owns the device buffers stays alive as long as its outputs are referenced
 
     def __len__(self):
         return len(self._ptrs)
@@ -323,7 +324,7 @@ class Pipeline:
         for i in range(be.num_outputs()):
             gpu, dt, lay, cont, shapes, ptrs = be.output(i)
             if gpu:
-                outs.append(TensorListGPU(dt, lay, cont, shapes, ptrs, stream))
+                outs.append(TensorListGPU(dt, lay, cont, shapes, ptrs, stream, owner=self))
             else:
                 import ctypes as C
                 npdt = types.to_numpy_type(dt)

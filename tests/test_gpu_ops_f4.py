@@ -104,8 +104,17 @@ def test_rotate_and_resize_crop_mirror():
         scale = 50.0 / min(H, W)
         rh, rw = max(1, int(np.round(np.float32(H * scale)))), max(1, int(np.round(np.float32(W * scale))))
         y0, x0 = po.crop_anchor(0.5, rh, 40), po.crop_anchor(0.3, rw, 44)
-        lo = [np.float32(y0 * (H / rh)), np.float32(x0 * (W / rw))]
-        hi = [np.float32((y0 + 40) * (H / rh)), np.float32((x0 + 44) * (W / rw))]
+        # subpixel_scale (default): the resize ROI is first adjusted for the rounded size (resize_attr_base.h:97-113) ...
+        rlo, rhi = [0.0, 0.0], [float(H), float(W)]
+        for dd, (real, frac) in enumerate(((rh, H * scale), (rw, W * scale))):
+            if real != np.float32(frac):
+                adj = real / float(np.float32(abs(np.float32(frac))))
+                cc = 0.5 * rlo[dd] + 0.5 * rhi[dd]
+                rlo[dd], rhi[dd] = float(np.float32(cc + (rlo[dd] - cc) * adj)), float(np.float32(cc + (rhi[dd] - cc) * adj))
+        # ... then the crop window is projected back through it in double precision
+        ry, rx = (rhi[0] - rlo[0]) / rh, (rhi[1] - rlo[1]) / rw
+        lo = [np.float32(y0 * ry + rlo[0]), np.float32(x0 * rx + rlo[1])]
+        hi = [np.float32((y0 + 40) * ry + rlo[0]), np.float32((x0 + 44) * rx + rlo[1])]
         m = int(mir[i])
         if m & 2:
             lo[0], hi[0] = hi[0], lo[0]

@@ -232,13 +232,15 @@ def test_decoder_crop_family_and_random_resized_crop():
             assert np.array_equal(d[i], full[16:116, 30:94]), (it, i)
 
 
-def test_decoder_resize_fusion_in_the_executor():
-    """decoders.image* -> resize with no other consumer of the decoded image: the executor links the two operators, the Resize reads
+def test_decoder_resize_fusion_in_the_executor(monkeypatch):
+    """decoders.image* -> resize with no other consumer of the decoded image (opt-in, DALIB200_FUSE_DECODE_RESIZE=1): the executor
+    links the two operators, the Resize reads
     the decoder's planes (kernel `resample_planar`) for the samples that qualify and the usual path for the rest (grayscale, 4:4:4);
     results equal decode-then-resize / crop-then-resize on the oracle, and the unfused pipeline (image also returned) bit for bit."""
     import cv2
     import gpu_helpers as g
     from dali_b200 import capi, fn, pipeline_def
+    monkeypatch.setenv("DALIB200_FUSE_DECODE_RESIZE", "1")
     streams = _jpegs(3, 480, 640, 90)
     ok, enc = cv2.imencode(".jpg", g.synth_image(300, 400, 95), [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])
     streams.append(np.ascontiguousarray(enc.ravel()))

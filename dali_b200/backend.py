@@ -135,12 +135,13 @@ class Pipeline:
     def build(self):
         check(lib().dalihPipelineBuild(self.h))
 
-    def feed_input(self, name, ptrs, shapes, ndim, dtype, layout=""):
+    def feed_input(self, name, ptrs, shapes, ndim, dtype, layout="", no_copy=False):
         import numpy as np
         n = len(ptrs)
         p = (C.c_void_p * n)(*ptrs)
         sh = np.ascontiguousarray(shapes, dtype=np.int64).reshape(-1)
-        check(lib().dalihPipelineFeedInput(self.h, _b(name), n, p, sh.ctypes.data_as(C.c_void_p), int(ndim), int(dtype), _b(layout or "")))
+        check(lib().dalihPipelineFeedInputEx(self.h, _b(name), n, p, sh.ctypes.data_as(C.c_void_p), int(ndim), int(dtype), _b(layout or ""),
+                                             int(bool(no_copy))))
 
     def run(self):
         check(lib().dalihPipelineRun(self.h))

@@ -23,12 +23,13 @@ EXPORTS = [
     "dalib200JpegPlanGetInfo", "dalib200JpegPlanStagedBytes", "dalib200JpegUpload", "dalib200JpegLaunch",
     "dalib200JpegGetStatus", "dalib200JpegDebugGetCoefficients", "dalib200JpegPlanSetupEx", "dalib200JpegPlanGetOutputShape",
     "dalib200JpegStatusAsync", "dalib200JpegStatusFetch", "dalib200JpegPlanGetPlanes", "dalib200JpegPlanSetPlanesOnly",
+    "dalib200JpegPlanSetSourceStable", "dalib200JpegPlanLastUploadDirect", "dalib200HostAlloc", "dalib200HostFree",
     "dalib200ResamplePlanSetupPlanar", "dalib200ResampleLaunchPlanar",
     "dalib200ResamplePlanCreate", "dalib200ResamplePlanDestroy", "dalib200ResamplePlanSetup", "dalib200ResampleLaunch",
     "dalib200ResamplePlanGetOrder",
     "dalib200ResamplePlanGetPath",
     "dalib200CmnPlanCreate", "dalib200CmnPlanDestroy", "dalib200CmnPlanSetup", "dalib200CmnLaunch",
-    "dalib200WarpPlanCreate", "dalib200WarpPlanDestroy", "dalib200WarpPlanSetup", "dalib200WarpLaunch", "dalib200AffineInverse",
+    "dalib200WarpPlanCreate", "dalib200WarpPlanDestroy", "dalib200WarpPlanSetup", "dalib200WarpLaunch", "dalib200WarpPlanGetPath", "dalib200AffineInverse",
     "dalib200PointwisePlanCreate", "dalib200PointwisePlanDestroy", "dalib200LinearTransformSetup", "dalib200ColorSpaceSetup",
     "dalib200PointwiseLaunch", "dalib200ColorTwistMatrix",
     "dalib200SpectrogramPlanCreate", "dalib200SpectrogramPlanDestroy", "dalib200SpectrogramPlanSetup",
@@ -124,6 +125,30 @@ def lib():
         _lib.dalib200JpegPlanStagedBytes.restype = C.c_size_t
         _lib.dalib200SpectrogramNumWindows.restype = C.c_int64
     return _lib
+
+
+class _PinnedBlock:
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        check(lib().dalib200HostAlloc(C.byref(p), C.c_size_t(nbytes)))
+        self.ptr, self.nbytes = p.value, nbytes
+
+    def __del__(self):
+        try:
+            lib().dalib200HostFree(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(nbytes):
+    """uint8 numpy array over page-locked host memory (freed with the last view).  Encoded streams held in such memory and fed
+    with external_source(no_copy=True) reach the decoder by DMA straight from here (dalib200JpegPlanSetSourceStable)."""
+    import numpy as np
+    nbytes = max(1, int(nbytes))
+    blk = _PinnedBlock(nbytes)
+    buf = (C.c_uint8 * nbytes).from_address(blk.ptr)
+    buf._blk = blk                      # the numpy array keeps `buf` (its base) alive, `buf` keeps the allocation
+    return np.frombuffer(buf, dtype=np.uint8)
 
 
 def check(rc):

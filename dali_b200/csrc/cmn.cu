@@ -63,6 +63,106 @@ __device__ __forceinline__ void store4<uint16_t>(uint16_t *p, uint16_t a, uint16
 
 // ------------------------------------------------------------------------------------------
 // Fast path: u8 HWC (3 ch) -> planar CHW Out, window inside the image.
+// A unit = 128 pixels of one row (384 source bytes); a warp works on TWO units per iteration -- all six coalesced word loads are
+// issued before the first is consumed, which doubles the bytes each warp keeps in flight (the kernel is latency-bound otherwise).
+struct CmnUnit {
+  const CmnDesc *d;
+  const uint32_t *aw;
+  int y, xb, npx, nwords;
+  uint32_t sh;
+  uint32_t w[3], extra;
+};
+
+__device__ __forceinline__ void cmn_unit_open(CmnUnit &c, const CmnDesc &d, int64_t u, int lane) {
+  c.d = &d;
+  const int upr = (d.cw + 127) >> 7;
+  c.y = (int)(u / upr);
+  c.xb = (int)(u % upr) << 7;
+  c.npx = min(128, d.cw - c.xb);
+  const int src_px0 = d.mirror ? d.ax + d.cw - c.xb - c.npx : d.ax + c.xb;
+  const uint8_t *a = d.in + ((int64_t)(d.ay + c.y) * d.in_w + src_px0) * 3;
+  c.sh = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 3);
+  c.aw = reinterpret_cast<const uint32_t *>(a - c.sh);
+  c.nwords = (int)((c.sh + c.npx * 3 + 3) >> 2);       // aligned words covering the segment
+  // coalesced loads: word index = lane + 32 t
+#pragma unroll
+  for (int t = 0; t < 3; t++) {
+    const int i = lane + 32 * t;
+    c.w[t] = i < c.nwords ? ld_nc_u32(c.aw + i) : 0u;
+  }
+  // word 96 for the funnel shift of the last word when the segment is misaligned
+  c.extra = (c.sh != 0 && lane == 0 && 96 < c.nwords) ? ld_nc_u32(c.aw + 96) : 0u;
+}
+
+template <typename Out>
+__device__ __forceinline__ void cmn_unit_finish(const CmnUnit &c, int lane, int out_c) {
+  const CmnDesc &d = *c.d;
+  const uint32_t extra = __shfl_sync(0xffffffffu, c.extra, 0);
+  uint32_t wn[3];
+  {
+    const uint32_t n0 = __shfl_down_sync(0xffffffffu, c.w[0], 1), n1 = __shfl_down_sync(0xffffffffu, c.w[1], 1),
+                   n2 = __shfl_down_sync(0xffffffffu, c.w[2], 1);
+    const uint32_t f1 = __shfl_sync(0xffffffffu, c.w[1], 0), f2 = __shfl_sync(0xffffffffu, c.w[2], 0);
+    wn[0] = lane == 31 ? f1 : n0;
+    wn[1] = lane == 31 ? f2 : n1;
+    wn[2] = lane == 31 ? extra : n2;
+  }
+  uint32_t r[3];
+#pragma unroll
+  for (int t = 0; t < 3; t++) r[t] = __funnelshift_r(c.w[t], wn[t], c.sh * 8);   // realigned word (lane + 32 t)
+  // register transpose: lane l needs realigned words 3l, 3l+1, 3l+2
+  uint32_t q[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int j = 3 * lane + k;
+    const int src = j & 31, reg = j >> 5;
+    const uint32_t v0 = __shfl_sync(0xffffffffu, r[0], src);
+    const uint32_t v1 = __shfl_sync(0xffffffffu, r[1], src);
+    const uint32_t v2 = __shfl_sync(0xffffffffu, r[2], src);
+    q[k] = reg == 0 ? v0 : reg == 1 ? v1 : v2;
+  }
+  // 12 bytes = 4 pixels x 3 channels
+  const int p0 = lane * 4, npx = c.npx, xb = c.xb;
+  if (p0 >= npx) return;
+  Out *obase = static_cast<Out *>(d.out);
+  const int64_t plane = (int64_t)d.ch * d.cw;
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    Out v[4];
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      const int bi = 3 * p + ch;
+      const uint32_t byte = (q[bi >> 2] >> ((bi & 3) * 8)) & 0xFFu;
+      const float f = mul_rn(sub_rn(u8_to_float(byte), d.mean[ch]), d.inv_std[ch]);
+      v[p] = OutConv<Out>::cvt(f);
+    }
+    Out *orow = obase + ch * plane + (int64_t)c.y * d.cw;
+    const int valid = min(4, npx - p0);
+    if (!d.mirror) {
+      Out *o = orow + xb + p0;
+      if (valid == 4 && (reinterpret_cast<uintptr_t>(o) & (4 * sizeof(Out) - 1)) == 0) {
+        store4<Out>(o, v[0], v[1], v[2], v[3]);
+      } else {
+        for (int p = 0; p < valid; p++) o[p] = v[p];
+      }
+    } else {
+      // source pixel (src_px0 + p0 + p) lands at output x = xb + npx - 1 - (p0 + p)
+      Out *o = orow + xb + npx - 1 - p0 - 3;      // address of the p = 3 pixel
+      if (valid == 4 && (reinterpret_cast<uintptr_t>(o) & (4 * sizeof(Out) - 1)) == 0) {
+        store4<Out>(o, v[3], v[2], v[1], v[0]);
+      } else {
+        for (int p = 0; p < valid; p++) orow[xb + npx - 1 - p0 - p] = v[p];
+      }
+    }
+  }
+  // padding planes (pad_output): constant fill
+  for (int ch = 3; ch < out_c; ch++) {
+    const Out fv = OutConv<Out>::cvt(d.fill[ch]);
+    Out *orow = obase + ch * plane + (int64_t)c.y * d.cw + xb;
+    for (int p = p0; p < min(p0 + 4, npx); p++) orow[p] = fv;
+  }
+}
+
 template <typename Out>
 __global__ void __launch_bounds__(256) cmn_hwc2chw_kernel(const CmnDesc *__restrict__ descs, int n, int64_t total_units,
                                                           int out_c) {
@@ -71,101 +171,25 @@ __global__ void __launch_bounds__(256) cmn_hwc2chw_kernel(const CmnDesc *__restr
   // advanced -- a binary search over thousands of frame descriptors per 384-byte unit used to dominate this kernel
   __shared__ int s_first;
   const int wpc = blockDim.x >> 5;
-  const int64_t per_cta = ((total_units + gridDim.x - 1) / gridDim.x + wpc - 1) / wpc * wpc;
+  const int64_t per_cta = ((total_units + gridDim.x - 1) / gridDim.x + 2 * wpc - 1) / (2 * wpc) * (2 * wpc);
   const int64_t u0 = (int64_t)blockIdx.x * per_cta, u1 = min(total_units, u0 + per_cta);
   if (u0 >= u1) return;
   if (threadIdx.x == 0) s_first = find_sample_units(descs, n, u0);
   __syncthreads();
   int s = s_first;
-  for (int64_t unit = u0 + (threadIdx.x >> 5); unit < u1; unit += wpc) {
+  for (int64_t unit = u0 + (threadIdx.x >> 5); unit < u1; unit += 2 * wpc) {
     while (s + 1 < n && descs[s + 1].first_unit <= unit) s++;
-    const CmnDesc &d = descs[s];
-    if (!d.fast) continue;                       // generic samples own zero units, defensive
-    const int64_t u = unit - d.first_unit;
-    const int upr = (d.cw + 127) >> 7;
-    const int y = (int)(u / upr);
-    const int xb = (int)(u % upr) << 7;
-    const int npx = min(128, d.cw - xb);
-    const int src_px0 = d.mirror ? d.ax + d.cw - xb - npx : d.ax + xb;
-    const uint8_t *a = d.in + ((int64_t)(d.ay + y) * d.in_w + src_px0) * 3;
-    const int nbytes = npx * 3;
-    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 3);
-    const uint32_t *aw = reinterpret_cast<const uint32_t *>(a - sh);
-    const int nwords = (int)((sh + nbytes + 3) >> 2);     // aligned words covering the segment
-
-    // coalesced loads: word index = lane + 32 t
-    uint32_t w[3], wn[3];
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-      int i = lane + 32 * t;
-      w[t] = i < nwords ? ld_nc_u32(aw + i) : 0u;
-    }
-    // word i+1 for the funnel shift: neighbour lane, or lane 0 of the next register, or one more load
-    uint32_t extra = (sh != 0 && lane == 0 && 96 < nwords) ? ld_nc_u32(aw + 96) : 0u;
-    extra = __shfl_sync(0xffffffffu, extra, 0);
-    {
-      const uint32_t n0 = __shfl_down_sync(0xffffffffu, w[0], 1), n1 = __shfl_down_sync(0xffffffffu, w[1], 1),
-                     n2 = __shfl_down_sync(0xffffffffu, w[2], 1);
-      const uint32_t f1 = __shfl_sync(0xffffffffu, w[1], 0), f2 = __shfl_sync(0xffffffffu, w[2], 0);
-      wn[0] = lane == 31 ? f1 : n0;
-      wn[1] = lane == 31 ? f2 : n1;
-      wn[2] = lane == 31 ? extra : n2;
-    }
-    uint32_t r[3];
-#pragma unroll
-    for (int t = 0; t < 3; t++) r[t] = __funnelshift_r(w[t], wn[t], sh * 8);   // realigned word (lane + 32 t)
-
-    // register transpose: lane l needs realigned words 3l, 3l+1, 3l+2
-    uint32_t q[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const int j = 3 * lane + k;
-      const int src = j & 31, reg = j >> 5;
-      uint32_t v0 = __shfl_sync(0xffffffffu, r[0], src);
-      uint32_t v1 = __shfl_sync(0xffffffffu, r[1], src);
-      uint32_t v2 = __shfl_sync(0xffffffffu, r[2], src);
-      q[k] = reg == 0 ? v0 : reg == 1 ? v1 : v2;
-    }
-    // 12 bytes = 4 pixels x 3 channels
-    const int p0 = lane * 4;
-    if (p0 >= npx) continue;
-    Out *obase = static_cast<Out *>(d.out);
-    const int64_t plane = (int64_t)d.ch * d.cw;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      Out v[4];
-#pragma unroll
-      for (int p = 0; p < 4; p++) {
-        const int bi = 3 * p + c;
-        const uint32_t byte = (q[bi >> 2] >> ((bi & 3) * 8)) & 0xFFu;
-        const float f = mul_rn(sub_rn(u8_to_float(byte), d.mean[c]), d.inv_std[c]);
-        v[p] = OutConv<Out>::cvt(f);
-      }
-      Out *orow = obase + c * plane + (int64_t)y * d.cw;
-      const int valid = min(4, npx - p0);
-      if (!d.mirror) {
-        Out *o = orow + xb + p0;
-        if (valid == 4 && (reinterpret_cast<uintptr_t>(o) & (4 * sizeof(Out) - 1)) == 0) {
-          store4<Out>(o, v[0], v[1], v[2], v[3]);
-        } else {
-          for (int p = 0; p < valid; p++) o[p] = v[p];
-        }
-      } else {
-        // source pixel (src_px0 + p0 + p) lands at output x = xb + npx - 1 - (p0 + p)
-        Out *o = orow + xb + npx - 1 - p0 - 3;      // address of the p = 3 pixel
-        if (valid == 4 && (reinterpret_cast<uintptr_t>(o) & (4 * sizeof(Out) - 1)) == 0) {
-          store4<Out>(o, v[3], v[2], v[1], v[0]);
-        } else {
-          for (int p = 0; p < valid; p++) orow[xb + npx - 1 - p0 - p] = v[p];
-        }
-      }
-    }
-    // padding planes (pad_output): constant fill
-    for (int c = 3; c < out_c; c++) {
-      const Out fv = OutConv<Out>::cvt(d.fill[c]);
-      Out *orow = obase + c * plane + (int64_t)y * d.cw + xb;
-      for (int p = p0; p < min(p0 + 4, npx); p++) orow[p] = fv;
-    }
+    const int64_t unit2 = unit + wpc;
+    int s2 = s;
+    const bool two = unit2 < u1;
+    if (two) while (s2 + 1 < n && descs[s2 + 1].first_unit <= unit2) s2++;
+    const bool go1 = descs[s].fast != 0, go2 = two && descs[s2].fast != 0;       // generic samples own zero units, defensive
+    CmnUnit a, b;
+    if (go1) cmn_unit_open(a, descs[s], unit - descs[s].first_unit, lane);
+    if (go2) cmn_unit_open(b, descs[s2], unit2 - descs[s2].first_unit, lane);
+    if (go1) cmn_unit_finish<Out>(a, lane, out_c);
+    if (go2) cmn_unit_finish<Out>(b, lane, out_c);
+    s = s2;
   }
 }
 

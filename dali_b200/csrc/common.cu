@@ -85,6 +85,20 @@ void ProfEnd(cudaStream_t s) {
 }  // namespace dalib200
 
 extern "C" {
+
+int dalib200HostAlloc(void **ptr, size_t bytes) {
+  DB_CHECK_ARG(ptr, "HostAlloc: null pointer");
+  *ptr = nullptr;
+  if (bytes == 0) return DALIB200_SUCCESS;
+  DB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return DALIB200_SUCCESS;
+}
+
+int dalib200HostFree(void *ptr) {
+  if (ptr) DB_CUDA(cudaFreeHost(ptr));
+  return DALIB200_SUCCESS;
+}
+
 int dalib200ProfilingEnable(int on) { dalib200::g_prof_on = on != 0; return DALIB200_SUCCESS; }
 // Synchronises, writes up to `max` records (names: `name_stride` bytes each, NUL terminated) and clears the log.
 int dalib200ProfilingCollect(char *names, int name_stride, float *ms, int max, int *count) {

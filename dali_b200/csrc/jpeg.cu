@@ -1645,6 +1645,8 @@ struct dalib200JpegPlan {
   std::vector<int32_t> block_image;         // sync block -> image
   std::vector<int32_t> wblock_image;        // write block -> image
   std::vector<const uint8_t *> src_ptr;     // host pointers of the scan data (for staging; borrowed until JpegUpload returns)
+  bool source_stable = false;               // JpegPlanSetSourceStable: page-locked sources are copied by the DMA engine directly
+  int last_upload_direct = 0;
   std::vector<size_t> stage_off;            // offset of each sample's scan bytes inside the raw staging area
   size_t raw_bytes = 0, clean_bytes = 0;
   uint32_t nchunks = 0;
@@ -2127,6 +2129,14 @@ int dalib200JpegStatusFetch(const dalib200JpegPlan *p, int32_t *status_out, int 
   return DALIB200_SUCCESS;
 }
 
+int dalib200JpegPlanSetSourceStable(dalib200JpegPlan *p, int stable) {
+  DB_CHECK_ARG(p, "JpegPlanSetSourceStable: null plan");
+  p->source_stable = stable != 0;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200JpegPlanLastUploadDirect(const dalib200JpegPlan *p) { return p ? p->last_upload_direct : -1; }
+
 int dalib200JpegUpload(dalib200JpegPlan *p, dalib200Stream_t stream) {
   DB_CHECK_ARG(p && p->staged, "JpegUpload: call JpegPlanSetup first");
   if (p->n == 0) return DALIB200_SUCCESS;
@@ -2135,6 +2145,37 @@ int dalib200JpegUpload(dalib200JpegPlan *p, dalib200Stream_t stream) {
   if (rc) return rc;
   // output pointers are patched at launch: images are uploaded there.  Descriptors and tables go first ...
   DB_CUDA(cudaMemcpyAsync(p->d_stage + p->off_units, p->h_stage + p->off_units, p->off_raw - p->off_units, cudaMemcpyHostToDevice, stream));
+  // Sources the caller declared stable (JpegPlanSetSourceStable) AND that are page-locked go to the device without the host
+  // repack: one DMA per sample straight from the caller's buffer (no CPU memcpy, no bounce buffer -- with N ranks on one host
+  // the repack of N x 100 MB per batch would otherwise saturate the host's memory system).  The kernels never read the padding
+  // behind a sample (load_raw_word is bounded by raw_len), so it is left as it is.
+  p->last_upload_direct = 0;
+  if (p->source_stable) {
+    bool pinned = true;
+    for (int i = 0; i < p->n && pinned; i++) {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, p->src_ptr[i]) != cudaSuccess) { cudaGetLastError(); pinned = false; }
+      else pinned = a.type == cudaMemoryTypeHost;
+    }
+    if (pinned) {
+      for (int i = 0; i < p->n; i++) {
+        const size_t len = p->parsed[i].scan_end - p->parsed[i].scan_begin;
+        // neighbours in one arena (sample i + 1 starts where the device layout expects it): merged into one copy
+        int j = i;
+        size_t run = len;
+        while (j + 1 < p->n && p->src_ptr[j + 1] == p->src_ptr[i] + (p->stage_off[j + 1] - p->stage_off[i])) {
+          j++;
+          run = (p->stage_off[j] - p->stage_off[i]) + (p->parsed[j].scan_end - p->parsed[j].scan_begin);
+        }
+        DB_CUDA(cudaMemcpyAsync(p->d_stage + p->off_raw + p->stage_off[i], p->src_ptr[i], run, cudaMemcpyHostToDevice, stream));
+        i = j;
+      }
+      p->last_upload_direct = 1;
+      DB_CUDA(cudaEventRecord(p->uploaded, stream));
+      p->pending = true;
+      return DALIB200_SUCCESS;
+    }
+  }
   // ... then the scan bytes in groups of ~8 MB: worker threads copy the samples into the pinned buffer in index order, the
   // calling thread issues the H2D copy of a group as soon as its last sample has landed (staging and PCIe transfer overlap).
   {

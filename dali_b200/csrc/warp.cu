@@ -188,12 +188,15 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const WarpDesc *__rest
 // through L1.  The box is sized from the tile's replayed corner coordinates: 448 bytes x 48 rows covers rotations of about +-12
 // degrees at unit scale; tiles whose footprint is larger or touches the image border take the generic path of
 // warp_affine_kernel.  Coordinates are still replayed (bit-exact with the reference CPU kernel).
+// The descriptor is read from GLOBAL memory (a 128-byte device copy owned by the plan): with this image's toolchain / driver pair
+// (nvcc 12.9 code on a CUDA 13.0 driver) a descriptor passed as a __grid_constant__ kernel parameter faults with
+// "illegal instruction" at the UTMALDG (tools/probe/tma_probe.cu reproduces it), the global-memory form works.
 constexpr int kTmaTileW = 128, kTmaTileH = 16;
 constexpr int kTmaBoxBytes = 448, kTmaBoxRows = 48;
 
 template <bool CLAMP>
 __global__ void __launch_bounds__(256) warp_affine_tma_kernel(const WarpDesc *__restrict__ descs, int n, int64_t total_tiles, float border,
-                                                              const __grid_constant__ CUtensorMap tmap) {
+                                                              const CUtensorMap *__restrict__ tmap) {
   __shared__ __align__(128) uint8_t box[kTmaBoxRows * kTmaBoxBytes];
   __shared__ float2 coords[kTmaTileH][kTmaTileW];
   __shared__ __align__(8) uint64_t bar;
@@ -241,14 +244,14 @@ __global__ void __launch_bounds__(256) warp_affine_tma_kernel(const WarpDesc *__
       const int ix0 = (int)floorf(minx - 0.5f) - 1, ix1 = (int)floorf(maxx - 0.5f) + 2;      // taps ix .. ix + 1, margin 1
       const int iy0 = (int)floorf(miny - 0.5f) - 1, iy1 = (int)floorf(maxy - 0.5f) + 2;
       const int bx = (ix0 * 3) & ~3;                                     // byte column of the box, 32-bit aligned
-      const bool fits = (ix1 + 1) * 3 - bx <= kTmaBoxBytes && iy1 - iy0 + 1 <= kTmaBoxRows;
+      const bool fits = (ix1 + 2) * 3 - bx <= kTmaBoxBytes && iy1 - iy0 + 1 <= kTmaBoxRows;
       // the 12-byte windows read per tap pair must stay inside the image rows: two pixels of slack on the right
       const bool inside = ix0 >= 0 && iy0 >= 0 && ix1 + 2 < d.in_w && iy1 < d.in_h;
       s_use = fits && inside;
       s_bx = bx; s_by = iy0;
       if (s_use) {
         mbar_expect_tx(&bar, kTmaBoxRows * kTmaBoxBytes);
-        tma_load_3d(box, &tmap, bx >> 2, iy0, s, &bar);
+        tma_load_3d(box, tmap, bx >> 2, iy0, s, &bar);
       }
     }
     __syncthreads();
@@ -322,6 +325,7 @@ struct dalib200WarpPlan {
   // tensor-map path (uniform batches): descriptors re-tiled to 16 x 128, map cached per (base, stride, shape)
   std::vector<dalib200WarpSample> samples;
   CUtensorMap tmap;
+  CUtensorMap *d_tmap = nullptr;            // device copy read by the kernel
   const void *tmap_base = nullptr; size_t tmap_stride = 0; int tmap_h = 0, tmap_w = 0, tmap_n = 0;
   int path = 0;                  // 1 = the last launch used the tensor-map kernel
 };
@@ -374,6 +378,7 @@ int dalib200WarpPlanDestroy(dalib200WarpPlan *p) {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   p->arena.Free();
+  if (p->d_tmap) cudaFree(p->d_tmap);
   delete p;
   return DALIB200_SUCCESS;
 }
@@ -442,8 +447,15 @@ int dalib200WarpLaunch(dalib200WarpPlan *p, const void *const *in_ptrs, void *co
     const CUresult r = GetEncodeTiled()(&p->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(in_ptrs[0]), dims, strides, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) tma = false;
-    else { p->tmap_base = in_ptrs[0]; p->tmap_stride = stride; p->tmap_h = s0.in_h; p->tmap_w = s0.in_w; p->tmap_n = p->n; }
+    if (r == CUDA_SUCCESS && !p->d_tmap && cudaMalloc(reinterpret_cast<void **>(&p->d_tmap), sizeof(CUtensorMap)) != cudaSuccess) {
+      cudaGetLastError(); p->d_tmap = nullptr;
+    }
+    if (r != CUDA_SUCCESS || !p->d_tmap ||
+        cudaMemcpyAsync(p->d_tmap, &p->tmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice, stream) != cudaSuccess) {
+      tma = false; p->tmap_base = nullptr;
+    } else {
+      p->tmap_base = in_ptrs[0]; p->tmap_stride = stride; p->tmap_h = s0.in_h; p->tmap_w = s0.in_w; p->tmap_n = p->n;
+    }
   }
   p->path = tma ? 1 : 0;
   int64_t total_tiles = p->total_tiles;
@@ -473,8 +485,8 @@ int dalib200WarpLaunch(dalib200WarpPlan *p, const void *const *in_ptrs, void *co
   const bool lin = p->interp == 1, clampb = !p->use_fill, u8 = p->out_dtype == DALIB200_UINT8;
   if (tma) {
     ProfScope ps_("warp_affine_tma", stream);
-    if (clampb) warp_affine_tma_kernel<true><<<grid, 256, 0, stream>>>(dd, p->n, total_tiles, p->border, p->tmap);
-    else warp_affine_tma_kernel<false><<<grid, 256, 0, stream>>>(dd, p->n, total_tiles, p->border, p->tmap);
+    if (clampb) warp_affine_tma_kernel<true><<<grid, 256, 0, stream>>>(dd, p->n, total_tiles, p->border, p->d_tmap);
+    else warp_affine_tma_kernel<false><<<grid, 256, 0, stream>>>(dd, p->n, total_tiles, p->border, p->d_tmap);
     CountLaunch();
     DB_CUDA(cudaGetLastError());
     return DALIB200_SUCCESS;

@@ -108,8 +108,10 @@ def external_source(source=None, num_outputs=None, *, cycle=None, name=None, dev
         raise ValueError("external_source device must be 'cpu' or 'gpu'")
     n = num_outputs or 1
     base = name or pipe._new_name("ExternalSource")
+    # no_copy=True (external_source.py `no_copy`): the caller keeps the buffers alive and unmodified until the iteration that uses
+    # them has completed; page-locked encoded streams then reach the GPU decoder by DMA straight from the caller's memory
     g = _ExternalSourceGroup(source, [], batch, cycle, layout if isinstance(layout, str) or layout is None else layout[0], dtype, device,
-                             batch_info)
+                             batch_info, bool(no_copy))
     for k in range(n):
         node = DataNode(base if n == 1 else f"{base}[{k}]", device, source=g)
         g.outputs.append(node)
@@ -163,6 +165,10 @@ def _readers_file(file_root=None, file_list=None, files=None, labels=None, *, ra
                         shard_id, num_shards, stick_to_shard, pad_last_batch, seed, shuffle_after_epoch_seed)
     inst = name or pipe._new_name("readers__File")
     g = _source_group(pipe, reader, 2, inst)
+    if pipe.device_id is not None:
+        # GPU pipeline: page-locked reader buffers, borrowed by the decoder until the iteration completes (no_copy semantics)
+        reader.enable_pinned(pipe._depth + 1)
+        g.no_copy = True
     pipe._readers[inst] = reader
     return g.outputs[0], g.outputs[1]
 

@@ -107,6 +107,16 @@ int dalihPipelineFeedInput(void *p, const char *name, int n, const void *const *
                                                layout ? layout : "");
   API_END
 }
+// no_copy != 0: the caller keeps the buffers valid AND unmodified until the iteration has completed (external_source(no_copy=True))
+int dalihPipelineFeedInputEx(void *p, const char *name, int n, const void *const *ptrs, const int64_t *shapes, int ndim, int dtype,
+                             const char *layout, int no_copy) {
+  API_BEGIN
+  TensorListShape sh(n, ndim);
+  for (int i = 0; i < n; i++) sh.set_tensor_shape(i, TensorShape(shapes + static_cast<size_t>(i) * ndim, shapes + static_cast<size_t>(i + 1) * ndim));
+  static_cast<Pipeline *>(p)->SetExternalInput(name, std::vector<const void *>(ptrs, ptrs + n), sh, static_cast<DALIDataType>(dtype),
+                                               layout ? layout : "", no_copy != 0);
+  API_END
+}
 int dalihPipelineRun(void *p) { API_BEGIN static_cast<Pipeline *>(p)->Run(); API_END }
 int dalihPipelineWait(void *p) { API_BEGIN static_cast<Pipeline *>(p)->WaitOutputs(); API_END }
 int dalihPipelineNumOutputs(void *p) { return static_cast<Pipeline *>(p)->NumOutputs(); }

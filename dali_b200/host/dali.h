@@ -144,8 +144,12 @@ class TensorList {
   void Resize(const TensorListShape &shape, DALIDataType type);
   // borrow external per-sample memory (ExternalSource no_copy, decoder input)
   void ShareData(const std::vector<void *> &ptrs, const TensorListShape &shape, DALIDataType type) {
-    shape_ = shape; type_ = type; ptrs_ = ptrs; owned_ = false;
+    shape_ = shape; type_ = type; ptrs_ = ptrs; owned_ = false; stable_ = false;
   }
+  // borrowed memory the producer promised to keep valid and unmodified until the iteration has completed
+  // (external_source(no_copy=True), reader-owned buffers): consumers may read it asynchronously
+  void set_stable(bool v) { stable_ = v; }
+  bool stable() const { return stable_; }
 
  private:
   void Free();
@@ -155,7 +159,7 @@ class TensorList {
   std::vector<void *> ptrs_;
   void *data_ = nullptr;
   size_t capacity_ = 0;
-  bool owned_ = false;
+  bool owned_ = false, stable_ = false;
 };
 
 // ---------------------------------------------------------------------------------------------- OpSpec
@@ -432,7 +436,7 @@ class Pipeline {
   void Build();
   // External data: host pointers, one per sample.  For device == "gpu" the samples are copied H2D on the pipeline stream.
   void SetExternalInput(const std::string &name, const std::vector<const void *> &ptrs, const TensorListShape &shape,
-                        DALIDataType type, const std::string &layout);
+                        DALIDataType type, const std::string &layout, bool no_copy = false);
   void Run();
   // Synchronises the pipeline stream.  Returned pointers stay valid until the next Run().
   int NumOutputs() const { return static_cast<int>(output_names_.size()); }

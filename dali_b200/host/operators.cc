@@ -158,6 +158,7 @@ class ImageDecoderBase : public Operator<MixedBackend>, public PlanarProducer {
         SampleRoi(rois_[i], ws, i, H, W);
       }
     }
+    CheckStatus(dalib200JpegPlanSetSourceStable(plan_, in.stable() ? 1 : 0), name_);
     CheckStatus(dalib200JpegPlanSetupEx(plan_, n, ptrs.data(), lens.data(), &prm_, HasRoi() ? rois_.data() : nullptr), name_);
     out.resize(1);
     out[0].type = out_type_;

@@ -360,7 +360,7 @@ void Pipeline::Build() {
 }
 
 void Pipeline::SetExternalInput(const std::string &name, const std::vector<const void *> &ptrs, const TensorListShape &shape,
-                                DALIDataType type, const std::string &layout) {
+                                DALIDataType type, const std::string &layout, bool no_copy) {
   DALI_ENFORCE(static_cast<int>(ptrs.size()) == shape.num_samples(), "SetExternalInput: pointer / shape count mismatch");
   DALI_ENFORCE(shape.num_samples() <= max_batch_size_, "External source batch (", shape.num_samples(), ") exceeds max_batch_size (",
                max_batch_size_, ")");
@@ -375,6 +375,7 @@ void Pipeline::SetExternalInput(const std::string &name, const std::vector<const
     std::vector<void *> p(ptrs.size());
     for (size_t i = 0; i < ptrs.size(); i++) p[i] = const_cast<void *>(ptrs[i]);
     e->cpu->ShareData(p, shape, type);
+    e->cpu->set_stable(no_copy);
     e->cpu->SetLayout(lay);
   } else {
     e->gpu->Resize(shape, type);

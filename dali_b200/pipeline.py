@@ -107,8 +107,9 @@ class TensorListCPU:
 
 
 class _ExternalSourceGroup:
-    def __init__(self, source, outputs, batch, cycle, layout, dtype, device, batch_info):
+    def __init__(self, source, outputs, batch, cycle, layout, dtype, device, batch_info, no_copy=False):
         self.source, self.outputs, self.batch, self.cycle = source, outputs, batch, cycle
+        self.no_copy = bool(no_copy)
         self.layout, self.dtype, self.device, self.batch_info = layout, dtype, device, batch_info
         self.iterator = None
         self.is_callable = callable(source) and not hasattr(source, "__iter__")
@@ -238,7 +239,7 @@ class Pipeline:
         self._cur_slot = self._next_slot
         self._feed(name, data, layout or "")
 
-    def _feed(self, name, data, layout):
+    def _feed(self, name, data, layout, no_copy=False):
         if hasattr(data, "cpu") and hasattr(data, "numpy") and not isinstance(data, np.ndarray):     # torch tensor batch
             data = data.cpu().numpy()
         if isinstance(data, np.ndarray):
@@ -258,7 +259,8 @@ class Pipeline:
             arrs.append(np.ascontiguousarray(s))
         self._pending.append(arrs)          # kept alive until the slot that consumes them is reused (the backend borrows the pointers)
         shapes = np.array([a.shape for a in arrs], np.int64).reshape(len(arrs), nd) if nd else np.zeros((len(arrs), 0), np.int64)
-        self._slots[self._cur_slot].feed_input(name, [a.ctypes.data for a in arrs], shapes, nd, int(types.from_numpy_type(dt)), layout)
+        self._slots[self._cur_slot].feed_input(name, [a.ctypes.data for a in arrs], shapes, nd, int(types.from_numpy_type(dt)), layout,
+                                               no_copy)
 
     def _run_input_callbacks(self, slot):
         self._cur_slot = slot
@@ -269,7 +271,7 @@ class Pipeline:
             if len(g.outputs) == 1:
                 batch = (batch,)
             for o, b in zip(g.outputs, batch):
-                self._feed(o.name, b, g.layout or "")
+                self._feed(o.name, b, g.layout or "", g.no_copy)
         # everything fed for this iteration (feed_input() calls and source callbacks) replaces what the slot held before
         self._keep[slot] = self._pending
         self._pending = []

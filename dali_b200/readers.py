@@ -166,13 +166,41 @@ class FileReader:
         self.last = idx
         return idx
 
+    def enable_pinned(self, num_buffers):
+        """Read the files into a ring of page-locked arenas (one per batch in flight, `num_buffers` = prefetch depth + 1): the
+        mixed decoder then copies the streams to the GPU by DMA straight from the reader's buffers, as the reference's readers
+        feed its mixed operators from their own pinned buffers."""
+        self._pin_ring = [None] * max(2, int(num_buffers))
+        self._pin_next = 0
+
+    def _arena(self, nbytes):
+        from . import capi
+        k = self._pin_next
+        self._pin_next = (k + 1) % len(self._pin_ring)
+        if self._pin_ring[k] is None or self._pin_ring[k].size < nbytes:
+            self._pin_ring[k] = capi.pinned_empty(max(nbytes + nbytes // 4, 1 << 20))
+        return self._pin_ring[k]
+
     def __call__(self, _iteration=None):
-        data, labels = [], []
+        paths, labels = [], []
         for i in range(self.batch_size):
             idx = self._next_sample(i == 0)
             path, lab = self.entries[idx]
-            data.append(np.fromfile(path, dtype=np.uint8))
+            paths.append(path)
             labels.append(np.array([lab], np.int32))
+        if getattr(self, "_pin_ring", None) is None:
+            return [np.fromfile(p, dtype=np.uint8) for p in paths], labels
+        sizes = [os.path.getsize(p) for p in paths]
+        offs = np.concatenate([[0], np.cumsum([(s + 63) & ~63 for s in sizes])])
+        arena = self._arena(int(offs[-1]))
+        data = []
+        for p, s, o in zip(paths, sizes, offs[:-1]):
+            view = arena[int(o):int(o) + s]
+            with open(p, "rb") as f:
+                got = f.readinto(memoryview(view))
+            if got != s:
+                raise IOError(f"short read from {p}: {got} of {s} bytes")
+            data.append(view)
         return data, labels
 
 

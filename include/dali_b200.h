@@ -117,6 +117,16 @@ size_t dalib200JpegPlanStagedBytes(const dalib200JpegPlan *plan);
 /* Pinned staging + H2D copy of the batch (async on stream, host work overlapped with the transfer).  Split from Launch
  * so that a caller can time the device-resident decode separately from the transfer. */
 int dalib200JpegUpload(dalib200JpegPlan *plan, dalib200Stream_t stream);
+/* stable != 0: the caller guarantees that the encoded streams passed to the next JpegPlanSetup calls stay valid and unmodified
+ * until the launch that consumes them has completed -- the contract of the reference's external_source(no_copy=True)
+ * (dali/python/nvidia/dali/external_source.py, `no_copy`) and of its readers' own buffers.  JpegUpload then copies samples that
+ * live in page-locked memory straight from the caller's buffers (one DMA per sample, no host repack); anything else still goes
+ * through the pinned staging buffer.  JpegPlanLastUploadDirect: 1 when the last upload took the direct path. */
+int dalib200JpegPlanSetSourceStable(dalib200JpegPlan *plan, int stable);
+int dalib200JpegPlanLastUploadDirect(const dalib200JpegPlan *plan);
+/* Page-locked host memory for callers that want the direct path (cudaHostAlloc / cudaFreeHost behind the C ABI). */
+int dalib200HostAlloc(void **ptr, size_t bytes);
+int dalib200HostFree(void *ptr);
 /* Enqueues the decode of the uploaded batch; out_ptrs[i] -> device buffer H*W*C of dtype (HWC, see ...GetOutputShape). */
 int dalib200JpegLaunch(dalib200JpegPlan *plan, void *const *out_ptrs, dalib200Stream_t stream);
 /* Per-sample device status after a launch (0 ok, 1 = entropy-coded data ended early).  Synchronises. */
@@ -203,6 +213,9 @@ int dalib200WarpPlanSetup(dalib200WarpPlan *plan, int n, const dalib200WarpSampl
                           int interp /* NN | LINEAR */, int use_fill, float fill_value,
                           int out_dtype /* UINT8 | FLOAT */);
 int dalib200WarpLaunch(dalib200WarpPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
+/* 1 when the last launch staged source tiles with tiled TMA loads through a tensor map (bilinear u8 -> u8 over 3-channel frames of
+ * one shape laid out at a constant 16-byte-aligned stride, e.g. the frames of an FHWC batch); 0 for the generic kernel. */
+int dalib200WarpPlanGetPath(const dalib200WarpPlan *plan);
 /* host helper: include/dali/core/geom/transform.h:166-174 */
 void dalib200AffineInverse(const float *m2x3, float *out2x3);
 

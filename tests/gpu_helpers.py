@@ -153,7 +153,9 @@ def jpeg_coefs(plan, sample, count):
     return out
 
 
-def warp_affine(imgs, mats, out_hws=None, interp=1, fill=None, out_dtype=np.uint8):
+def warp_affine(imgs, mats, out_hws=None, interp=1, fill=None, out_dtype=np.uint8, contiguous=False, want_path=False):
+    """contiguous=True: the inputs are slices of ONE device allocation (like the frames of an FHWC batch) -> the tensor-map TMA
+    kernel can take them; want_path=True also returns dalib200WarpPlanGetPath."""
     torch = _torch()
     n = len(imgs)
     samples = (capi.WarpSample * n)()
@@ -165,12 +167,17 @@ def warp_affine(imgs, mats, out_hws=None, interp=1, fill=None, out_dtype=np.uint
     plan = capi.Plan("Warp", max(n, 1))
     odt = capi.UINT8 if np.dtype(out_dtype) == np.uint8 else capi.FLOAT
     capi.check(capi.lib().dalib200WarpPlanSetup(plan.handle, n, samples, int(interp), int(fill is not None), C.c_float(fill or 0.0), odt))
-    din = to_dev(imgs)
+    if contiguous:
+        whole = torch.from_numpy(np.stack(imgs)).cuda()
+        din = [whole[i] for i in range(n)]
+    else:
+        din = to_dev(imgs)
     outs = [torch.empty((samples[i].out_h, samples[i].out_w, imgs[i].shape[2]), dtype=torch.uint8 if odt == capi.UINT8 else torch.float32,
                         device="cuda") for i in range(n)]
     capi.check(capi.lib().dalib200WarpLaunch(plan.handle, capi.ptr_array(din), capi.ptr_array(outs), capi.stream_handle()))
     torch.cuda.synchronize()
-    return [o.cpu().numpy() for o in outs]
+    res = [o.cpu().numpy() for o in outs]
+    return (res, capi.lib().dalib200WarpPlanGetPath(plan.handle)) if want_path else res
 
 
 def color_twist_matrix(hue=0.0, saturation=1.0, value=1.0, brightness=1.0, contrast=1.0, half_range=128.0):

@@ -61,6 +61,41 @@ def test_warp_c3_frame():
     assert np.array_equal(o, po.warp_affine(img, M, None, 1, 0.0))
 
 
+def test_warp_tensor_map_tma_path():
+    """Uniform batches of 3-channel frames at a constant stride take the tensor-map TMA kernel (tile boxes staged in shared memory by
+    cp.async.bulk.tensor); tiles at the border, or whose footprint exceeds the box (large angles, down-scaling maps), fall back per
+    tile.  Everything stays bit-exact, for both border modes and for output sizes that are not tile multiples."""
+    import gpu_helpers as g
+    rng = np.random.default_rng(57)
+    for (H, W), out_hw in (((360, 640), None), ((200, 448), (173, 301)), ((96, 1280), (96, 1277))):
+        n = 5
+        imgs = [rng.integers(0, 256, (H, W, 3)).astype(np.uint8) for _ in range(n)]
+        mats = []
+        for k, (deg, sc) in enumerate(((3.0, 1.0), (-9.0, 1.04), (40.0, 1.0), (1.0, 2.2), (0.0, 1.0))):
+            a = np.deg2rad(deg)
+            c, si = np.cos(a) * sc, np.sin(a) * sc
+            cx, cy = W / 2, H / 2
+            mats.append(np.float32([[c, -si, cx - c * cx + si * cy + 0.37 * k], [si, c, cy - si * cx - c * cy - 0.21 * k]]))
+        outs = [out_hw] * n if out_hw else None
+        for fill in (None, 17.0):
+            got, path = g.warp_affine(imgs, mats, outs, 1, fill, np.uint8, contiguous=True, want_path=True)
+            assert path == 1
+            for im, M, o in zip(imgs, mats, got):
+                assert np.array_equal(o, po.warp_affine(im, M, out_hw, 1, fill, np.uint8)), ((H, W), out_hw, fill)
+        # nearest-neighbour and float outputs keep the generic kernel
+        got, path = g.warp_affine(imgs, mats, outs, 0, None, np.uint8, contiguous=True, want_path=True)
+        assert path == 0
+        for im, M, o in zip(imgs, mats, got):
+            assert np.array_equal(o, po.warp_affine(im, M, out_hw, 0, None, np.uint8))
+    # rows that are not a multiple of 16 bytes cannot be described by a tensor map
+    imgs = [rng.integers(0, 256, (64, 301, 3)).astype(np.uint8) for _ in range(2)]
+    mats = [np.float32([[1, 0.02, 0.5], [-0.02, 1, 0.25]])] * 2
+    got, path = g.warp_affine(imgs, mats, None, 1, None, np.uint8, contiguous=True, want_path=True)
+    assert path == 0
+    for im, M, o in zip(imgs, mats, got):
+        assert np.array_equal(o, po.warp_affine(im, M, None, 1, None, np.uint8))
+
+
 def test_hsv_and_linear_transform():
     import gpu_helpers as g
     rng = np.random.default_rng(53)

@@ -38,6 +38,7 @@ EXPORTS = [
     "dalib200NormalizeSetup", "dalib200SignalLaunch",
     "dalib200GenericPlanCreate", "dalib200GenericPlanDestroy", "dalib200MultiplyAddSetup", "dalib200WindowCopySetup", "dalib200GenericLaunch",
     "dalib200MelPlanCreate", "dalib200MelPlanDestroy", "dalib200MelPlanSetup", "dalib200MelLaunch", "dalib200MelPlanSetTensorCores",
+    "dalib200SpectrogramMelSupported", "dalib200SpectrogramMelLaunch",
 ]
 
 

@@ -174,6 +174,167 @@ __device__ __forceinline__ int find_mel_sample(const MelDesc *d, int n, int64_t 
   return lo;
 }
 
+// ---------------------------------------------------------------------------------------------
+// nfft = 1024: the FFT lives in REGISTERS.  One warp transforms one pair of frames (frame 2p = real part, 2p + 1 = imaginary part)
+// as 1024 = 32 x 32 (Cooley-Tukey, n = 32 n1 + n2, k = k1 + 32 k2):
+//   step 1  lane = n2 holds x[32 n1 + n2], n1 = 0..31 (every load is one coalesced 128-byte row of the frame) and runs a
+//           32-point DFT over n1 in registers (5 fully unrolled radix-2 DIF stages, constant twiddles);
+//   step 2  multiplies Y[k1] by W_1024^(n2 k1) (32 x 32 table in shared memory, row k1 read conflict-free);
+//   step 3  transposes through a warp-private 32 x 33 tile (the only shared-memory round trip, __syncwarp only) so that lane = k1
+//           holds Y[k1][n2], and runs the second 32-point DFT over n2: X[k1 + 32 k2].
+// The two real spectra are separated with one shuffle per bin (the partner bin N - k sits in lane 32 - k1, register 31 - k2).
+// Against the shared-memory radix-2 kernel above: 1 shared round trip instead of 5, no block-wide barrier, ~64 independent values
+// per thread in flight.  With `mel` the power spectrum of the pair never leaves the SM: it is parked in the (now free) tile and
+// the mel filters are applied there, in the summation order of mel_kernel below -- STFT -> mel in ONE kernel, 128 x T written once.
+__device__ __forceinline__ float w32c(int j) {      // cos(2 pi j / 32)
+  switch (j) {
+    case 0: return 1.0f; case 1: return 0.98078528040323043f; case 2: return 0.92387953251128674f; case 3: return 0.83146961230254524f;
+    case 4: return 0.70710678118654757f; case 5: return 0.55557023301960229f; case 6: return 0.38268343236508984f;
+    case 7: return 0.19509032201612833f; case 8: return 0.0f; case 9: return -0.19509032201612819f; case 10: return -0.38268343236508973f;
+    case 11: return -0.55557023301960196f; case 12: return -0.70710678118654746f; case 13: return -0.83146961230254535f;
+    case 14: return -0.92387953251128674f; default: return -0.98078528040323043f;
+  }
+}
+
+template <int HALF>
+__device__ __forceinline__ void fft32_stage(float (&re)[32], float (&im)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2 * HALF) {
+#pragma unroll
+    for (int j = 0; j < HALF; j++) {
+      const int a = i + j, b = a + HALF;
+      const float ar = re[a], ai = im[a], br = re[b], bi = im[b];
+      re[a] = ar + br; im[a] = ai + bi;
+      float tr = ar - br, ti = ai - bi;
+      const int tw = j * (16 / HALF);                  // times W_32^tw = exp(-2 pi i tw / 32)
+      if (tw == 8) { const float t = tr; tr = ti; ti = -t; }
+      else if (tw != 0) {
+        const float c = w32c(tw), sn = w32c(tw <= 8 ? 8 - tw : tw - 8);      // sin(2 pi tw / 32) = cos(2 pi (8 - tw) / 32)
+        const float r2 = tr * c + ti * sn, i2 = ti * c - tr * sn;
+        tr = r2; ti = i2;
+      }
+      re[b] = tr; im[b] = ti;
+    }
+  }
+}
+// natural order in, bit-reversed order out: X[k] = v[brev5(k)]
+__device__ __forceinline__ void fft32(float (&re)[32], float (&im)[32]) {
+  fft32_stage<16>(re, im); fft32_stage<8>(re, im); fft32_stage<4>(re, im); fft32_stage<2>(re, im); fft32_stage<1>(re, im);
+}
+__device__ __forceinline__ constexpr int brev5(int k) { return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4); }
+
+constexpr int kF1024Warps = 8;                       // 16 frames per CTA, like the radix-2 kernel's grouping at nfft = 1024
+constexpr int kF1024Tile = 32 * 33;                  // float2 per warp
+constexpr size_t kF1024Smem = sizeof(float2) * (1024 + (size_t)kF1024Warps * kF1024Tile);
+
+struct MelTables { const int32_t *ends; const float *w_up, *w_down; int nfilter; };
+
+template <bool MEL>
+__global__ void __launch_bounds__(kF1024Warps * 32, 2) spectrogram1024_kernel(const SpecDesc *__restrict__ descs, int n, int64_t total_groups,
+                                                                              SpecParams P, const float *__restrict__ window,
+                                                                              const float2 *__restrict__ twiddle1024, MelTables mt,
+                                                                              const MelDesc *__restrict__ mdescs, int write_spec) {
+  extern __shared__ float2 fbuf[];
+  float2 *tw = fbuf;                                 // [k1][n2] = W_1024^(k1 n2)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2 *tile = fbuf + 1024 + warp * kF1024Tile;
+  for (int e = threadIdx.x; e < 1024; e += blockDim.x) {
+    const int idx = (e >> 5) * (e & 31);             // < 1024; W^(idx) from the half table: W^(idx) = -W^(idx - 512)
+    const float2 t = twiddle1024[idx & 511];
+    tw[e] = idx < 512 ? t : make_float2(-t.x, -t.y);
+  }
+  __syncthreads();
+  for (int64_t grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+    const int s = find_spec_sample(descs, n, grp);
+    const SpecDesc &d = descs[s];
+    const int64_t w0 = (grp - d.first_group) * (2 * kF1024Warps) + 2 * warp;
+    if (w0 >= d.nwin) continue;
+    const bool two = w0 + 1 < d.nwin;
+    float re[32], im[32];
+    // ---- framing (window applied here); interior pairs skip the per-sample bounds logic
+    {
+      const int64_t start = w0 * (int64_t)P.step - P.center_off - P.in_win_start;      // signal index of FFT sample 0 of frame w0
+      const bool interior = two && P.in_win_start == 0 && P.win_len == 1024 && start >= 0 && start + P.step + 1024 <= d.len;
+      if (interior) {
+        const float *pa = d.in + start + lane, *pb = pa + P.step;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; n1++) {
+          const float wv = __ldg(window + 32 * n1 + lane);
+          re[n1] = mul_rn(wv, __ldg(pa + 32 * n1));
+          im[n1] = mul_rn(wv, __ldg(pb + 32 * n1));
+        }
+      } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 32; n1++) {
+          const int t = 32 * n1 + lane - P.in_win_start;
+          float va = 0.0f, vb = 0.0f;
+          if (t >= 0 && t < P.win_len) {
+            va = spec_sample(d, P, window, w0, t);
+            if (two) vb = spec_sample(d, P, window, w0 + 1, t);
+          }
+          re[n1] = va; im[n1] = vb;
+        }
+      }
+    }
+    fft32(re, im);                                   // Y[k1] (for this lane's n2) = v[brev5(k1)]
+    __syncwarp();                                    // the tile may still be read as the previous pair's power spectrum
+#pragma unroll
+    for (int k1 = 0; k1 < 32; k1++) {
+      const float2 w = tw[k1 * 32 + lane];
+      const float yr = re[brev5(k1)], yi = im[brev5(k1)];
+      tile[k1 * 33 + lane] = make_float2(yr * w.x + yi * w.y, yi * w.x - yr * w.y);     // * (cos - i sin)
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; n2++) {
+      const float2 v = tile[lane * 33 + n2];
+      re[n2] = v.x; im[n2] = v.y;
+    }
+    fft32(re, im);                                   // Z[lane + 32 k2] = v[brev5(k2)]
+    __syncwarp();
+    // ---- separate the two real spectra, power / magnitude.  Bins k = lane + 32 k2, k2 = 0..15, and k = 512 (lane 0, k2 = 16).
+    float *pw = reinterpret_cast<float *>(tile);     // [2][520] floats: the pair's spectra, parked for the mel filters
+    const int src = (32 - lane) & 31;
+#pragma unroll
+    for (int k2 = 0; k2 <= 16; k2++) {
+      // partner bin N - k: lane (32 - k1) % 32, k2' = 31 - k2 -- for k1 = 0 it stays in lane 0 with k2' = (32 - k2) % 32
+      const float zr = re[brev5(k2)], zi = im[brev5(k2)];
+      float pr = __shfl_sync(0xffffffffu, re[brev5(31 - k2)], src);
+      float pi = __shfl_sync(0xffffffffu, im[brev5(31 - k2)], src);
+      if (lane == 0) { pr = re[brev5((32 - k2) & 31)]; pi = im[brev5((32 - k2) & 31)]; }
+      if (k2 == 16 && lane != 0) continue;
+      const float ax = 0.5f * (zr + pr), ay = 0.5f * (zi - pi);       // frame 2p
+      const float bx = 0.5f * (zi + pi), by = 0.5f * (pr - zr);       // frame 2p + 1
+      float va = ax * ax + ay * ay, vb = bx * bx + by * by;
+      if (P.power != 2) { va = sqrtf(va); vb = sqrtf(vb); }
+      const int k = lane + 32 * k2;
+      if (write_spec) {
+        if (P.layout_ft) {
+          float *o = d.out + (int64_t)k * d.nwin + w0;
+          o[0] = va;
+          if (two) o[1] = vb;
+        } else {
+          d.out[w0 * (int64_t)P.nbin + k] = va;
+          if (two) d.out[(w0 + 1) * (int64_t)P.nbin + k] = vb;
+        }
+      }
+      if (MEL) { pw[k] = va; pw[520 + k] = vb; }
+    }
+    if (MEL) {
+      __syncwarp();
+      float *mo = mdescs[s].out;
+      for (int m = lane; m < mt.nfilter; m += 32) {
+        const int b0 = mt.ends[m], b1 = mt.ends[m + 1], b2 = mt.ends[m + 2];
+        float acca = 0.0f, accb = 0.0f;
+        for (int b = b0; b < b1; b++) { const float w = __ldg(mt.w_up + b); acca = add_rn(acca, mul_rn(w, pw[b])); accb = add_rn(accb, mul_rn(w, pw[520 + b])); }
+        for (int b = b1; b < b2; b++) { const float w = __ldg(mt.w_down + b); acca = add_rn(acca, mul_rn(w, pw[b])); accb = add_rn(accb, mul_rn(w, pw[520 + b])); }
+        mo[(int64_t)m * d.nwin + w0] = acca;
+        if (two) mo[(int64_t)m * d.nwin + w0 + 1] = accb;
+      }
+    }
+  }
+}
+
 // tables: ends[nfilter+2] (int, interval boundaries in bins), w_up[nbin], w_down[nbin] (already normalised)
 __global__ void __launch_bounds__(128) mel_kernel(const MelDesc *__restrict__ descs, int n, int64_t total_items, int nfilter,
                                                   const int32_t *__restrict__ ends, const float *__restrict__ w_up,
@@ -473,8 +634,11 @@ int64_t dalib200SpectrogramNumWindows(const dalib200SpectrogramPlan *p, int samp
   return p->descs[sample].nwin;
 }
 
-int dalib200SpectrogramLaunch(dalib200SpectrogramPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
-  DB_CHECK_ARG(p && in_ptrs && out_ptrs, "SpectrogramLaunch: null argument");
+static int MelUploadTables(dalib200MelPlan *p, dalib200Stream_t stream, size_t *o_up_out, size_t *o_down_out);
+
+// mel != nullptr: STFT -> mel in one kernel (nfft = 1024 only); out_ptrs may then be null (the spectrogram is not written)
+static int SpectrogramLaunchImpl(dalib200SpectrogramPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200MelPlan *mel,
+                                 void *const *mel_out_ptrs, dalib200Stream_t stream) {
   if (p->n == 0 || p->total_groups == 0) return DALIB200_SUCCESS;
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
   const SpecParams &P = p->P;
@@ -503,15 +667,51 @@ int dalib200SpectrogramLaunch(dalib200SpectrogramPlan *p, const void *const *in_
     p->window_dirty = false;
   }
   auto *hd = reinterpret_cast<SpecDesc *>(p->arena.host);
-  for (int i = 0; i < p->n; i++) { hd[i] = p->descs[i]; hd[i].in = static_cast<const float *>(in_ptrs[i]); hd[i].out = static_cast<float *>(out_ptrs[i]); }
+  for (int i = 0; i < p->n; i++) {
+    hd[i] = p->descs[i]; hd[i].in = static_cast<const float *>(in_ptrs[i]);
+    hd[i].out = out_ptrs ? static_cast<float *>(out_ptrs[i]) : nullptr;
+  }
   int rc = p->arena.Upload(sizeof(SpecDesc) * p->n, stream);
   if (rc) return rc;
   DB_CUDA(cudaEventRecord(p->uploaded, stream));
   p->pending = true;
-  if (!p->smem_set || true) {
-    DB_CUDA(cudaFuncSetAttribute(spectrogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(p->smem, 96 * 1024)));
-    p->smem_set = true;
+  static const bool radix2_only = getenv("DALIB200_STFT_RADIX2") != nullptr;
+  if (P.nfft == 1024 && (!radix2_only || mel)) {
+    // register-resident 32 x 32 FFT, one warp per pair of frames (16 frames per CTA = the grouping the descriptors were built with)
+    static bool attr_set = false;
+    if (!attr_set) {
+      DB_CUDA(cudaFuncSetAttribute(spectrogram1024_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF1024Smem));
+      DB_CUDA(cudaFuncSetAttribute(spectrogram1024_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kF1024Smem));
+      attr_set = true;
+    }
+    const int grid = (int)std::min<int64_t>(p->total_groups, (int64_t)NumSMs() * 2);
+    MelTables mt{};
+    if (mel) {
+      if (mel->pending) { DB_CUDA(cudaEventSynchronize(mel->uploaded)); mel->pending = false; }
+      size_t o_up = 0, o_down = 0;
+      if ((rc = MelUploadTables(mel, stream, &o_up, &o_down))) return rc;
+      auto *md = reinterpret_cast<MelDesc *>(mel->arena.host);
+      for (int i = 0; i < mel->n; i++) { md[i] = mel->descs[i]; md[i].in = nullptr; md[i].out = static_cast<float *>(mel_out_ptrs[i]); }
+      if ((rc = mel->arena.Upload(sizeof(MelDesc) * mel->n, stream))) return rc;
+      DB_CUDA(cudaEventRecord(mel->uploaded, stream));
+      mel->pending = true;
+      mt.ends = reinterpret_cast<const int32_t *>(mel->tables.dev);
+      mt.w_up = reinterpret_cast<const float *>(mel->tables.dev + o_up);
+      mt.w_down = reinterpret_cast<const float *>(mel->tables.dev + o_down);
+      mt.nfilter = mel->nfilter;
+      ProfScope ps_("spectrogram_mel_fused", stream);
+      spectrogram1024_kernel<true><<<grid, kF1024Warps * 32, kF1024Smem, stream>>>(reinterpret_cast<const SpecDesc *>(p->arena.dev), p->n,
+          p->total_groups, P, p->d_window, p->d_twiddle, mt, reinterpret_cast<const MelDesc *>(mel->arena.dev), out_ptrs ? 1 : 0);
+    } else {
+      ProfScope ps_("spectrogram_stft", stream);
+      spectrogram1024_kernel<false><<<grid, kF1024Warps * 32, kF1024Smem, stream>>>(reinterpret_cast<const SpecDesc *>(p->arena.dev), p->n,
+          p->total_groups, P, p->d_window, p->d_twiddle, mt, nullptr, 1);
+    }
+    CountLaunch();
+    DB_CUDA(cudaGetLastError());
+    return DALIB200_SUCCESS;
   }
+  DB_CUDA(cudaFuncSetAttribute(spectrogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(p->smem, 96 * 1024)));
   const int grid = (int)std::min<int64_t>(p->total_groups, (int64_t)NumSMs() * 8);
   ProfScope ps_("spectrogram_stft", stream);
   spectrogram_kernel<<<grid, 256, p->smem, stream>>>(reinterpret_cast<const SpecDesc *>(p->arena.dev), p->n, p->total_groups, P,
@@ -519,6 +719,25 @@ int dalib200SpectrogramLaunch(dalib200SpectrogramPlan *p, const void *const *in_
   CountLaunch();
   DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
+}
+
+int dalib200SpectrogramLaunch(dalib200SpectrogramPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+  DB_CHECK_ARG(p && in_ptrs && out_ptrs, "SpectrogramLaunch: null argument");
+  return SpectrogramLaunchImpl(p, in_ptrs, out_ptrs, nullptr, nullptr, stream);
+}
+
+int dalib200SpectrogramMelSupported(const dalib200SpectrogramPlan *p, const dalib200MelPlan *m) {
+  if (!p || !m || p->P.nfft != 1024 || !p->P.layout_ft || m->nbin != p->P.nbin || m->n != p->n || m->tensor_cores) return 0;
+  for (int i = 0; i < p->n; i++) if (m->descs[i].nwin != p->descs[i].nwin) return 0;
+  return 1;
+}
+
+int dalib200SpectrogramMelLaunch(dalib200SpectrogramPlan *p, dalib200MelPlan *m, const void *const *in_ptrs, void *const *spec_out_ptrs,
+                                 void *const *mel_out_ptrs, dalib200Stream_t stream) {
+  DB_CHECK_ARG(p && m && in_ptrs && mel_out_ptrs, "SpectrogramMelLaunch: null argument");
+  DB_CHECK_ARG(dalib200SpectrogramMelSupported(p, m), "SpectrogramMelLaunch: the fused kernel needs nfft = 1024, the (f, t) layout and a mel "
+               "plan set up for the same batch (check dalib200SpectrogramMelSupported)");
+  return SpectrogramLaunchImpl(p, in_ptrs, spec_out_ptrs, m, mel_out_ptrs, stream);
 }
 
 int dalib200MelPlanCreate(dalib200MelPlan **plan, int max_batch) {
@@ -583,12 +802,10 @@ int dalib200MelPlanSetup(dalib200MelPlan *p, const dalib200MelArgs *args, int nb
   return DALIB200_SUCCESS;
 }
 
-int dalib200MelLaunch(dalib200MelPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
-  DB_CHECK_ARG(p && in_ptrs && out_ptrs, "MelLaunch: null argument");
-  if (p->n == 0 || p->total_items == 0) return DALIB200_SUCCESS;
-  if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
+static int MelUploadTables(dalib200MelPlan *p, dalib200Stream_t stream, size_t *o_up_out, size_t *o_down_out) {
   const size_t o_up = (p->h_ends.size() * 4 + 15) / 16 * 16, o_down = o_up + (p->h_up.size() * 4 + 15) / 16 * 16;
   const size_t tbytes = o_down + p->h_down.size() * 4;
+  *o_up_out = o_up; *o_down_out = o_down;
   if (p->tables_dirty) {
     int rc = p->tables.Reserve(tbytes);
     if (rc) return rc;
@@ -598,6 +815,18 @@ int dalib200MelLaunch(dalib200MelPlan *p, const void *const *in_ptrs, void *cons
     rc = p->tables.Upload(tbytes, stream);
     if (rc) return rc;
     p->tables_dirty = false;
+  }
+  return DALIB200_SUCCESS;
+}
+
+int dalib200MelLaunch(dalib200MelPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+  DB_CHECK_ARG(p && in_ptrs && out_ptrs, "MelLaunch: null argument");
+  if (p->n == 0 || p->total_items == 0) return DALIB200_SUCCESS;
+  if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
+  size_t o_up = 0, o_down = 0;
+  {
+    const int rc = MelUploadTables(p, stream, &o_up, &o_down);
+    if (rc) return rc;
   }
   auto *hd = reinterpret_cast<MelDesc *>(p->arena.host);
   for (int i = 0; i < p->n; i++) {

@@ -389,6 +389,21 @@ class PlanarConsumer {
   virtual void AttachProducer(PlanarProducer *p) = 0;
 };
 
+// Spectrogram -> MelFilterBank fusion (one kernel, the spectrogram is not materialised): same linking scheme
+class SpectrumProducer {
+ public:
+  virtual ~SpectrumProducer() = default;
+  virtual void EnableDeferredRun() = 0;                            // build time: the only consumer is a MelFilterBank
+  virtual bool Deferred() const = 0;                               // this iteration's launch was left to the consumer
+  virtual void *SpectrogramPlan() = 0;                             // dalib200SpectrogramPlan *
+  virtual const std::vector<const void *> &DeferredInputs() const = 0;
+};
+class SpectrumConsumer {
+ public:
+  virtual ~SpectrumConsumer() = default;
+  virtual void AttachProducer(SpectrumProducer *p) = 0;
+};
+
 template <typename Backend>
 class Operator : public OperatorBase {
  public:

@@ -1334,8 +1334,14 @@ DALI_SCHEMA(Spectrogram)
     .AddOptionalArg("reflect_padding", "Reflect (True) or zero (False) padding.", true)
     .AddOptionalArg("layout", "Output layout: \"ft\" or \"tf\".", std::string("ft"));
 
-class SpectrogramGPU : public Operator<GPUBackend> {
+class SpectrogramGPU : public Operator<GPUBackend>, public SpectrumProducer {
  public:
+  // ---- SpectrumProducer
+  void EnableDeferredRun() override { fuse_ = true; }
+  bool Deferred() const override { return deferred_now_; }
+  void *SpectrogramPlan() override { return plan_; }
+  const std::vector<const void *> &DeferredInputs() const override { return deferred_in_; }
+
   explicit SpectrogramGPU(const OpSpec &spec) : Operator<GPUBackend>(spec) {
     args_.window_length = spec.GetArgument<int>("window_length");
     args_.window_step = spec.GetArgument<int>("window_step");
@@ -1386,9 +1392,15 @@ class SpectrogramGPU : public Operator<GPUBackend> {
     std::vector<const void *> ip(in.num_samples());
     std::vector<void *> op(in.num_samples());
     for (int i = 0; i < in.num_samples(); i++) { ip[i] = in.raw_tensor(i); op[i] = out.raw_mutable_tensor(i); }
+    // fused with the MelFilterBank that consumes this output: it launches STFT -> mel as one kernel and the spectrogram is never
+    // written (the fused kernel exists for nfft = 1024, (f, t) layout)
+    deferred_now_ = fuse_ && args_.nfft == 1024 && args_.layout_ft;
+    if (deferred_now_) { deferred_in_ = ip; return; }
     CheckStatus(dalib200SpectrogramLaunch(plan_, ip.data(), op.data(), ws.stream()), "Spectrogram");
   }
  private:
+  bool fuse_ = false, deferred_now_ = false;
+  std::vector<const void *> deferred_in_;
   dalib200SpectrogramPlan *plan_ = nullptr;
   dalib200SpectrogramArgs args_{};
   std::vector<float> window_;
@@ -1407,8 +1419,9 @@ DALI_SCHEMA(MelFilterBank)
     .AddOptionalArg("normalize", "Normalise the triangular filter weights by the width of their bands.", true)
     .AddOptionalArg("mel_formula", "slaney | htk", std::string("slaney"));
 
-class MelFilterBankGPU : public Operator<GPUBackend> {
+class MelFilterBankGPU : public Operator<GPUBackend>, public SpectrumConsumer {
  public:
+  void AttachProducer(SpectrumProducer *p) override { producer_ = p; }
   explicit MelFilterBankGPU(const OpSpec &spec) : Operator<GPUBackend>(spec) {
     args_.nfilter = spec.GetArgument<int>("nfilter");
     args_.sample_rate = spec.GetArgument<float>("sample_rate");
@@ -1450,9 +1463,22 @@ class MelFilterBankGPU : public Operator<GPUBackend> {
     std::vector<const void *> ip(in.num_samples());
     std::vector<void *> op(in.num_samples());
     for (int i = 0; i < in.num_samples(); i++) { ip[i] = in.raw_tensor(i); op[i] = out.raw_mutable_tensor(i); }
+    if (producer_ && producer_->Deferred()) {
+      auto *sp = static_cast<dalib200SpectrogramPlan *>(producer_->SpectrogramPlan());
+      const auto &sin = producer_->DeferredInputs();
+      if (dalib200SpectrogramMelSupported(sp, plan_)) {
+        CheckStatus(dalib200SpectrogramMelLaunch(sp, plan_, sin.data(), nullptr, op.data(), ws.stream()), "MelFilterBank");
+        return;
+      }
+      // not fusable after all (e.g. the tensor-core mel path was requested): materialise the spectrogram, then filter it
+      std::vector<void *> sp_out(in.num_samples());
+      for (int i = 0; i < in.num_samples(); i++) sp_out[i] = const_cast<void *>(in.raw_tensor(i));
+      CheckStatus(dalib200SpectrogramLaunch(sp, sin.data(), sp_out.data(), ws.stream()), "Spectrogram");
+    }
     CheckStatus(dalib200MelLaunch(plan_, ip.data(), op.data(), ws.stream()), "MelFilterBank");
   }
  private:
+  SpectrumProducer *producer_ = nullptr;
   dalib200MelPlan *plan_ = nullptr;
   dalib200MelArgs args_{};
 };

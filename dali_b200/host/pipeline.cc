@@ -356,6 +356,25 @@ void Pipeline::Build() {
       }
     }
   }
+  // Spectrogram -> MelFilterBank: one kernel when the spectrogram has no other consumer (the kernel pair is measurably slower and
+  // writes + re-reads the spectrogram); DALIB200_NO_FUSION=1 keeps the operators separate
+  if (!getenv("DALIB200_NO_FUSION")) {
+    for (auto &c : nodes_) {
+      auto *cons = dynamic_cast<SpectrumConsumer *>(c.op.get());
+      if (!cons || c.spec.NumInput() < 1) continue;
+      const auto edge = c.spec.Input(0);
+      int uses = 0;
+      for (auto &o : nodes_)
+        for (int i = 0; i < o.spec.NumInput(); i++) uses += o.spec.Input(i) == edge;
+      for (auto &o : output_names_) uses += o == edge;
+      if (uses != 1) continue;
+      for (auto &pn : nodes_) {
+        if (pn.spec.NumOutput() == 1 && pn.spec.Output(0) == edge) {
+          if (auto *prod = dynamic_cast<SpectrumProducer *>(pn.op.get())) { prod->EnableDeferredRun(); cons->AttachProducer(prod); }
+        }
+      }
+    }
+  }
   built_ = true;
 }
 

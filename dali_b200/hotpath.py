@@ -52,6 +52,7 @@ class ImagePipelineC2:
         self._decoded = None
         self._resized = None
         self.output = None
+        self._bound = False
         self.n = 0
         self.shapes = []
         self.staged_bytes = 0
@@ -116,7 +117,10 @@ class ImagePipelineC2:
             self._decoded = torch.empty(dec_bytes, dtype=torch.uint8, device=self.device)
         if self._resized is None or self._resized.shape[0] < n:
             self._resized = torch.empty((max(n, self.max_batch), oh, ow, 3), dtype=torch.uint8, device=self.device)
-        if self.output is None or self.output.shape[0] < n:
+        if self._bound:
+            if tuple(self.output.shape[1:]) != (3, oh, ow) or self.output.shape[0] < n or self.output.dtype != self.out_dtype:
+                raise ValueError("bind_output: the bound tensor does not fit this batch")
+        elif self.output is None or self.output.shape[0] < n:
             self.output = torch.empty((max(n, self.max_batch), 3, oh, ow), dtype=self.out_dtype, device=self.device)
         base = self._decoded.data_ptr()
         offs, o = [], 0
@@ -128,6 +132,13 @@ class ImagePipelineC2:
         self._res_ptrs = capi.ptr_array([rbase + i * rstride for i in range(n)])
         obase, ostride = self.output.data_ptr(), 3 * oh * ow * self.output.element_size()
         self._out_ptrs = capi.ptr_array([obase + i * ostride for i in range(n)])
+
+    def bind_output(self, tensor):
+        """CropMirrorNormalize writes into `tensor` ([>= batch, 3, H, W], contiguous) from the next setup() on -- e.g. this rank's
+        slice of a sharding.GatherBuffer, so that a following all-gather needs no copy."""
+        if not tensor.is_contiguous():
+            raise ValueError("bind_output: the tensor must be contiguous")
+        self.output, self._bound = tensor, True
 
     def upload(self, stream=None):
         capi.check(capi.lib().dalib200JpegUpload(self.jpeg.handle, capi.stream_handle(stream)))
@@ -236,8 +247,11 @@ class AudioPipelineC4:
     """spectrogram(nfft, window_length, window_step, power 2, centred, reflect) -> mel_filter_bank (BASELINE configs[3])."""
 
     def __init__(self, nclips, clip_len, nfft=1024, window_length=1024, window_step=256, nfilter=128, sample_rate=16000.0,
-                 freq_high=8000.0, device=None):
+                 freq_high=8000.0, device=None, fused=False, keep_spectrogram=True):
         import torch
+        # fused: STFT -> mel in one kernel (dalib200SpectrogramMelLaunch); with keep_spectrogram=False the spectrogram is never
+        # written to HBM (it is an intermediate of the chain), which is what the executor does when nothing else consumes it
+        self.fused, self.keep_spectrogram = bool(fused), bool(keep_spectrogram)
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         lib = capi.lib()
@@ -262,6 +276,12 @@ class AudioPipelineC4:
         """clips: float32 CUDA tensor [n, clip_len]."""
         lib, s = capi.lib(), capi.stream_handle(stream)
         in_ptrs = capi.ptr_array([clips.data_ptr() + i * self.clip_len * 4 for i in range(self.n)])
+        if self.fused:
+            if not lib.dalib200SpectrogramMelSupported(self.spec.handle, self.mel.handle):
+                raise capi.DaliB200Error("the fused STFT -> mel kernel needs nfft = 1024 and the (f, t) layout")
+            capi.check(lib.dalib200SpectrogramMelLaunch(self.spec.handle, self.mel.handle, in_ptrs,
+                                                        self._s_ptrs if self.keep_spectrogram else None, self._o_ptrs, s))
+            return self.output
         capi.check(lib.dalib200SpectrogramLaunch(self.spec.handle, in_ptrs, self._s_ptrs, s))
         capi.check(lib.dalib200MelLaunch(self.mel.handle, self._s_ptrs, self._o_ptrs, s))
         return self.output

@@ -30,6 +30,27 @@ def sharded_source(items, batch_size, shard_id, num_shards):
     return source
 
 
+class GatherBuffer:
+    """One persistent [world * B_local, ...] tensor per rank.  `local` is this rank's slice of it: bind it as the output of the
+    last operator (ImagePipelineC2.bind_output) so that CropMirrorNormalize writes its batch where the collective expects it;
+    `all_gather()` is then ONE in-place NCCL all-gather (sendbuf == recvbuf + rank * count), no staging copy, no allocation."""
+
+    def __init__(self, local_shape, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.b = int(local_shape[0])
+        self.full = torch.empty((self.world * self.b,) + tuple(local_shape[1:]), dtype=dtype, device=device)
+        self.local = self.full[self.rank * self.b:(self.rank + 1) * self.b]
+        self._cpu = self.full.device.type == "cpu"
+
+    def all_gather(self, async_op=False):
+        import torch.distributed as dist
+        # gloo (CPU tests) has no in-place form: it gets a copy of the slice
+        return dist.all_gather_into_tensor(self.full, self.local.clone() if self._cpu else self.local, group=self.group, async_op=async_op)
+
+
 def all_gather_output(local, group=None):
     """[B_local, ...] on every rank -> [world * B_local, ...] on every rank, in place (sendbuf = recvbuf + rank*count).
     Requires torch.distributed to be initialised with the nccl (GPU) or gloo (CPU tests) backend."""

@@ -283,6 +283,13 @@ int dalib200MelPlanSetup(dalib200MelPlan *plan, const dalib200MelArgs *args, int
  * banded kernel. */
 int dalib200MelPlanSetTensorCores(dalib200MelPlan *plan, int enable);
 int dalib200MelLaunch(dalib200MelPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
+/* Spectrogram -> MelFilterBank in ONE kernel (audio/mel_scale/mel_filter_bank.cc consuming signal/fft/spectrogram.cc): the
+ * power spectrum of a frame pair stays in shared memory and only the nfilter x nwin mel output is written.  Available for
+ * nfft = 1024 with the (f, t) layout and a mel plan set up for the same batch (dalib200SpectrogramMelSupported returns 1).
+ * spec_out_ptrs may be NULL: the spectrogram is then not materialised at all. */
+int dalib200SpectrogramMelSupported(const dalib200SpectrogramPlan *plan, const dalib200MelPlan *mel);
+int dalib200SpectrogramMelLaunch(dalib200SpectrogramPlan *plan, dalib200MelPlan *mel, const void *const *in_ptrs,
+                                 void *const *spec_out_ptrs, void *const *mel_out_ptrs, dalib200Stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Audio tail behind Spectrogram / MelFilterBank: ToDecibels, MFCC (DCT + liftering), Normalize.

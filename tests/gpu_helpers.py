@@ -256,3 +256,29 @@ def mel_filter_bank(specs, nfilter=128, sample_rate=44100.0, freq_low=0.0, freq_
     capi.check(capi.lib().dalib200MelLaunch(plan.handle, capi.ptr_array(din), capi.ptr_array(outs), capi.stream_handle()))
     torch.cuda.synchronize()
     return [o.cpu().numpy() for o in outs]
+
+
+def spectrogram_mel_fused(sigs, nfilter=128, sample_rate=16000.0, freq_high=8000.0, keep_spectrogram=True, **spec_kw):
+    """dalib200SpectrogramMelLaunch: (spectrograms or None, mel outputs); the spectrogram arguments are those of `spectrogram`."""
+    torch = _torch()
+    n = len(sigs)
+    wl = spec_kw.get("window_length", 512)
+    nfft = spec_kw.get("nfft") or wl
+    args = capi.SpectrogramArgs(nfft, wl, spec_kw.get("window_step", 256), spec_kw.get("power", 2), int(spec_kw.get("center", True)),
+                                int(spec_kw.get("reflect", True)), 1)
+    lens = (C.c_int64 * n)(*[int(s.size) for s in sigs])
+    sp = capi.Plan("Spectrogram", max(n, 1))
+    capi.check(capi.lib().dalib200SpectrogramPlanSetup(sp.handle, C.byref(args), None, n, lens))
+    nbin = nfft // 2 + 1
+    nws = [int(capi.lib().dalib200SpectrogramNumWindows(sp.handle, i)) for i in range(n)]
+    margs = capi.MelArgs(nfilter, sample_rate, 0.0, freq_high, 0, 1)
+    mp = capi.Plan("Mel", max(n, 1))
+    capi.check(capi.lib().dalib200MelPlanSetup(mp.handle, C.byref(margs), nbin, n, (C.c_int64 * n)(*nws)))
+    assert capi.lib().dalib200SpectrogramMelSupported(sp.handle, mp.handle) == 1
+    din = to_dev([np.ascontiguousarray(s, np.float32) for s in sigs])
+    specs = [torch.zeros((nbin, nw), dtype=torch.float32, device="cuda") for nw in nws]
+    mels = [torch.empty((nfilter, nw), dtype=torch.float32, device="cuda") for nw in nws]
+    capi.check(capi.lib().dalib200SpectrogramMelLaunch(sp.handle, mp.handle, capi.ptr_array(din), capi.ptr_array(specs) if keep_spectrogram else None,
+                                                       capi.ptr_array(mels), capi.stream_handle()))
+    torch.cuda.synchronize()
+    return ([o.cpu().numpy() for o in specs] if keep_spectrogram else None), [o.cpu().numpy() for o in mels]

@@ -167,6 +167,29 @@ def test_spectrogram_vs_oracle(cfg):
         assert np.abs(o - want).max() <= 5e-6 * want.max()
 
 
+@pytest.mark.parametrize("cfg", [dict(nfft=1024, window_length=1024, window_step=256), dict(nfft=1024, window_length=800, window_step=200, reflect=False),
+                                 dict(nfft=1024, window_length=1024, window_step=512, center=False), dict(nfft=1024, window_length=1024, window_step=160, power=1)])
+def test_spectrogram_mel_fused_kernel(cfg):
+    """STFT -> mel in one kernel (nfft = 1024: register-resident 32 x 32 FFT, power spectrum parked in shared memory): the
+    spectrogram it can optionally write equals the stand-alone spectrogram launch bit for bit, the mel output equals the stand-alone
+    mel kernel applied to that spectrogram bit for bit (same summation order), with and without materialising the spectrogram; odd
+    window counts, clips shorter than a window (reflect padding) and several clips per batch included."""
+    import gpu_helpers as g
+    rng = np.random.default_rng(77)
+    lens = (16000, 5000, 40001, 1500) if cfg.get("center", True) else (16000, 5000, 40001, 2049)
+    sigs = [_clip(rng, n) for n in lens]
+    spec = g.spectrogram(sigs, **cfg)
+    mel = g.mel_filter_bank(spec, 128, 16000.0, 0.0, 8000.0)
+    fs, fm = g.spectrogram_mel_fused(sigs, **cfg)
+    _, fm2 = g.spectrogram_mel_fused(sigs, keep_spectrogram=False, **cfg)
+    for a, b, c, d, e in zip(spec, mel, fs, fm, fm2):
+        assert np.array_equal(bits(a), bits(c))
+        assert np.array_equal(bits(b), bits(d)) and np.array_equal(bits(b), bits(e))
+    for s_, got in zip(sigs, spec):                       # and the new FFT against the oracle, at the stated tolerance
+        want = po.spectrogram(s_, **cfg)
+        assert np.abs(got - want).max() <= 2e-4 * max(1e-30, np.abs(want).max())
+
+
 def test_spectrogram_c4_shape_and_unsupported():
     import gpu_helpers as g
     rng = np.random.default_rng(62)

@@ -31,6 +31,11 @@ local = torch.arange(lo, hi, dtype=torch.float32).reshape(-1, 1, 1, 1).expand(-1
 full = all_gather_output(local)
 assert full.shape == (8, 3, 2, 2) and full.dtype == torch.float16
 assert torch.equal(full[:, 0, 0, 0].float(), torch.arange(8, dtype=torch.float32)), full[:, 0, 0, 0]
+from dali_b200.sharding import GatherBuffer
+gb = GatherBuffer((hi - lo, 3, 2, 2), torch.float16, torch.device("cpu"))
+gb.local.copy_(local)                                   # on the GPU the last operator writes here directly
+gb.all_gather()
+assert torch.equal(gb.full, full)
 dist.barrier()
 if r == 0:
     print("GLOO_OK")

@@ -23,7 +23,7 @@ EXPORTS = [
     "dalib200JpegPlanGetInfo", "dalib200JpegPlanStagedBytes", "dalib200JpegUpload", "dalib200JpegLaunch",
     "dalib200JpegGetStatus", "dalib200JpegDebugGetCoefficients", "dalib200JpegPlanSetupEx", "dalib200JpegPlanGetOutputShape",
     "dalib200JpegStatusAsync", "dalib200JpegStatusFetch", "dalib200JpegPlanGetPlanes", "dalib200JpegPlanSetPlanesOnly",
-    "dalib200JpegPlanSetSourceStable", "dalib200JpegPlanLastUploadDirect", "dalib200HostAlloc", "dalib200HostFree",
+    "dalib200JpegPlanSetSourceStable", "dalib200JpegPlanLastUploadDirect", "dalib200HostAlloc", "dalib200HostFree", "dalib200DebugCheckHalfConversion",
     "dalib200ResamplePlanSetupPlanar", "dalib200ResampleLaunchPlanar",
     "dalib200ResamplePlanCreate", "dalib200ResamplePlanDestroy", "dalib200ResamplePlanSetup", "dalib200ResampleLaunch",
     "dalib200ResamplePlanGetOrder",

@@ -76,8 +76,8 @@ struct CmnUnit {
 __device__ __forceinline__ void cmn_unit_open(CmnUnit &c, const CmnDesc &d, int64_t u, int lane) {
   c.d = &d;
   const int upr = (d.cw + 127) >> 7;
-  c.y = (int)(u / upr);
-  c.xb = (int)(u % upr) << 7;
+  c.y = (int)((uint32_t)u / (uint32_t)upr);            // units of one sample fit 32 bits; a 64-bit division costs ~100 instructions
+  c.xb = (int)((uint32_t)u - (uint32_t)c.y * (uint32_t)upr) << 7;
   c.npx = min(128, d.cw - c.xb);
   const int src_px0 = d.mirror ? d.ax + d.cw - c.xb - c.npx : d.ax + c.xb;
   const uint8_t *a = d.in + ((int64_t)(d.ay + c.y) * d.in_w + src_px0) * 3;

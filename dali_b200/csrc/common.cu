@@ -84,7 +84,34 @@ void ProfEnd(cudaStream_t s) {
 
 }  // namespace dalib200
 
+namespace dalib200 {
+__global__ void half_cvt_check_kernel(unsigned long long *mismatches) {
+  unsigned long long bad = 0;
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < (1ull << 32); v += (uint64_t)gridDim.x * blockDim.x) {
+    const float f = __uint_as_float((uint32_t)v);
+    bad += float2half_ties_away(f) != float2half_ties_away_ref(f);
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace dalib200
+
 extern "C" {
+
+// Test hook: compares the hardware-assisted float -> half (ties away) conversion of the kernels with the integer restatement of
+// include/dali/util/half.hpp on ALL 2^32 float bit patterns; *mismatches must come back 0.
+int dalib200DebugCheckHalfConversion(uint64_t *mismatches) {
+  DB_CHECK_ARG(mismatches, "DebugCheckHalfConversion: null pointer");
+  unsigned long long *d = nullptr;
+  DB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d), 8));
+  DB_CUDA(cudaMemset(d, 0, 8));
+  dalib200::half_cvt_check_kernel<<<dalib200::NumSMs() * 8, 256>>>(d);
+  unsigned long long h = 0;
+  const cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  DB_CUDA(e);
+  *mismatches = h;
+  return DALIB200_SUCCESS;
+}
 
 int dalib200HostAlloc(void **ptr, size_t bytes) {
   DB_CHECK_ARG(ptr, "HostAlloc: null pointer");

@@ -69,10 +69,10 @@ __global__ void __launch_bounds__(256) window_copy_kernel(const GenDesc *__restr
     const GenDesc &d = descs[s];
     const int64_t e0 = (item - d.first_item) * kGenItem, e1 = min(d.n, e0 + kGenItem);
     uint8_t *out = static_cast<uint8_t *>(d.out);
-    const int64_t row = (int64_t)d.out_w * d.c;
+    const uint32_t row = (uint32_t)d.out_w * (uint32_t)d.c;          // WindowCopySetup rejects samples of 2^31 elements or more
     for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-      const int oy = (int)(e / row);
-      const int r = (int)(e - (int64_t)oy * row);
+      const int oy = (int)((uint32_t)e / row);
+      const int r = (int)((uint32_t)e - (uint32_t)oy * row);
       const int ox = r / d.c, ch = r - ox * d.c;
       const int sy = d.anchor_y + (d.flip_y ? d.out_h - 1 - oy : oy), sx = d.anchor_x + (d.flip_x ? d.out_w - 1 - ox : ox);
       uint8_t v = d.fill[min(ch, 3)];
@@ -148,6 +148,7 @@ int dalib200WindowCopySetup(dalib200GenericPlan *p, int n, const dalib200WindowS
     d.flip_x = w.flip_x != 0; d.flip_y = w.flip_y != 0;
     for (int k = 0; k < 4; k++) d.fill[k] = w.fill[k];
     d.n = (int64_t)w.out_h * w.out_w * w.channels;
+    DB_CHECK_ARG(d.n < (1ll << 31), "WindowCopySetup: sample %d: outputs of 2^31 elements or more are not supported", i);
     d.first_item = items;
     items += (d.n + kGenItem - 1) / kGenItem;
   }

@@ -1033,7 +1033,8 @@ __global__ void __launch_bounds__(128) idct_kernel(const JpegImage *__restrict__
     while (ii + 1 < nimages && first_work[ii + 1] <= wb) ii++;
     const JpegImage &im = images[ii];
     const int64_t lw = wb - first_work[ii];            // block index inside the window, MCU-row major
-    const int wm = (int)(lw / im.bpm), b = (int)(lw % im.bpm);
+    // per-image counts fit 32 bits (the plan rejects images above 2^31 pixels): 32-bit divisions, a 64-bit one costs ~100 instructions
+    const int wm = (int)((uint32_t)lw / (uint32_t)im.bpm), b = (int)((uint32_t)lw - (uint32_t)wm * (uint32_t)im.bpm);
     const int mx = im.mcu_x0 + wm % im.mcu_nx, my = im.mcu_y0 + wm / im.mcu_nx;
     const int64_t gb = im.coef_off / 64 + ((int64_t)my * im.mcux + mx) * im.bpm + b;     // block index in scan (MCU) order
     const int comp = im.blk_comp[b];
@@ -1115,7 +1116,8 @@ __global__ void __launch_bounds__(256) color_kernel(const JpegImage *__restrict_
     if (im.fast_color) continue;
     const int64_t q = gq - first_quad[lo];
     const int qpr = (im.win_w + 3) >> 2;
-    const int y = im.win_y0 + (int)(q / qpr), x0 = im.win_x0 + ((int)(q % qpr) << 2);
+    const uint32_t qy = (uint32_t)q / (uint32_t)qpr;
+    const int y = im.win_y0 + (int)qy, x0 = im.win_x0 + ((int)((uint32_t)q - qy * (uint32_t)qpr) << 2);
     const int W = im.width, H = im.height;
     const int nout = im.out_type == DALIB200_GRAY ? 1 : 3;
     uint8_t px[12];
@@ -1335,14 +1337,15 @@ __global__ void __launch_bounds__(128) color_fast_kernel(const JpegImage *__rest
     const JpegImage &im = images[lo];
     const int64_t li = item - first_item[lo];
     const int segs = (im.win_w + kColorSeg - 1) / kColorSeg;
-    const int x0 = im.win_x0 + (int)(li % segs) * kColorSeg + threadIdx.x * 8;
+    const uint32_t lrow = (uint32_t)li / (uint32_t)segs, lseg = (uint32_t)li - lrow * (uint32_t)segs;     // 32-bit: see idct_kernel
+    const int x0 = im.win_x0 + (int)lseg * kColorSeg + threadIdx.x * 8;
     const int wx1 = im.win_x0 + im.win_w, wy1 = im.win_y0 + im.win_h;
     if (x0 >= wx1) continue;
     const int hexp = im.hmax, vexp = im.vmax;     // chroma is 1x1 (checked on the host)
     if (im.fast_color == 2) {
       // 4:2:0 fancy: row item r = rows 2r - 1 and 2r (r = 0: row 0 only), see color_patch_420; the window's first item is
       // r_lo = ceil(win_y0 / 2)
-      const int r = ((im.win_y0 + 1) >> 1) + (int)(li / segs);
+      const int r = ((im.win_y0 + 1) >> 1) + (int)lrow;
       const int ya = 2 * r - 1, yb = 2 * r;
       const bool in_a = ya >= im.win_y0 && ya < wy1, in_b = yb >= im.win_y0 && yb < wy1;
       const int dw = (im.width + 1) >> 1, dh = (im.height + 1) >> 1, i0 = x0 >> 1;
@@ -1355,7 +1358,7 @@ __global__ void __launch_bounds__(128) color_fast_kernel(const JpegImage *__rest
       }
       continue;
     }
-    const int y = im.win_y0 + (int)(li / segs);
+    const int y = im.win_y0 + (int)lrow;
     if (hexp == 2 && vexp == 2) color_row8<2, 2>(im, planes, x0, y);
     else if (hexp == 1 && vexp == 1) color_row8<1, 1>(im, planes, x0, y);
     else if (hexp == 2 && vexp == 1) color_row8<2, 1>(im, planes, x0, y);
@@ -1399,7 +1402,7 @@ __global__ void __launch_bounds__(256) jpeg_post_kernel(const JpegPost *__restri
     while (ii + 1 < n && posts[ii + 1].first_px <= gp) ii++;
     const JpegPost &d = posts[ii];
     const int64_t lp = gp - d.first_px;
-    const int oy = (int)(lp / d.out_w), ox = (int)(lp % d.out_w);
+    const int oy = (int)((uint32_t)lp / (uint32_t)d.out_w), ox = (int)((uint32_t)lp - (uint32_t)oy * (uint32_t)d.out_w);
     const int fy = d.out_y0 + oy, fx = d.out_x0 + ox;           // oriented full-image coordinates
     int sy, sx;
     switch (d.orientation) {                                   // EXIF: where does the displayed pixel come from?
@@ -1860,6 +1863,7 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
     if (rc) { std::string m = dalib200GetLastError(); SetLastError("decoders.image: sample %d: %s", i, m.c_str()); return rc; }
     auto unsupported = [&](const char *what) { SetLastError("decoders.image: sample %d: %s", i, what); return DALIB200_ERROR_UNSUPPORTED; };
     if (j.progressive) return unsupported("progressive JPEG is not supported by the GPU decoder yet");
+    if ((int64_t)j.width * j.height >= (1ll << 31)) return unsupported("images of 2^31 pixels or more are not supported");
     if (j.precision != 8) return unsupported("only 8-bit baseline JPEG is supported");
     if (j.ncomp != 1 && j.ncomp != 3) return unsupported("only 1- or 3-component JPEG is supported");
     if (j.scan_ncomp != j.ncomp) return unsupported("multi-scan (non-interleaved) baseline JPEG is not supported yet");

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const WarpDesc *__rest
     while (s + 1 < n && descs[s + 1].first_tile <= tile) s++;
     const WarpDesc &d = descs[s];
     const int64_t tl = tile - d.first_tile;
-    const int ty = (int)(tl / d.tiles_x), tx = (int)(tl % d.tiles_x);
+    const int ty = (int)((uint32_t)tl / (uint32_t)d.tiles_x), tx = (int)((uint32_t)tl - (uint32_t)ty * (uint32_t)d.tiles_x);
     const int y0 = ty * kWarpTileH, x0 = tx * kWarpTileW;
     const int th = min(kWarpTileH, d.out_h - y0), tw = min(kWarpTileW, d.out_w - x0);
     // ---- stage 1: replay the reference's coordinate accumulation, one thread per row
@@ -182,131 +182,185 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const WarpDesc *__rest
 }
 
 // =============================================================================================
-// Tensor-map TMA variant (uniform batches of 3-channel u8 frames, bilinear): the source box of a 16 x 128 output tile is staged in
-// shared memory by ONE tiled TMA load (cp.async.bulk.tensor.3d through a CUtensorMap over the whole batch viewed as
-// [frame][row][32-bit word]; SASS UTMALDG.3D) and the four taps of every pixel come from there instead of six word loads per pixel
-// through L1.  The box is sized from the tile's replayed corner coordinates: 448 bytes x 48 rows covers rotations of about +-12
-// degrees at unit scale; tiles whose footprint is larger or touches the image border take the generic path of
-// warp_affine_kernel.  Coordinates are still replayed (bit-exact with the reference CPU kernel).
-// The descriptor is read from GLOBAL memory (a 128-byte device copy owned by the plan): with this image's toolchain / driver pair
-// (nvcc 12.9 code on a CUDA 13.0 driver) a descriptor passed as a __grid_constant__ kernel parameter faults with
-// "illegal instruction" at the UTMALDG (tools/probe/tma_probe.cu reproduces it), the global-memory form works.
-constexpr int kTmaTileW = 128, kTmaTileH = 16;
-constexpr int kTmaBoxBytes = 448, kTmaBoxRows = 48;
+// Band kernel: bilinear, 3-channel u8 -> u8 (the C3 hot case).
+//
+// The reference's coordinate accumulation is a serial recurrence per (row, 256-pixel block); with one thread per row of a 16-row
+// tile only half a warp works on it while the other warps wait, and it then costs more than the sampling.  Here a CTA owns a BAND
+// of 32 output rows x up to 2048 columns:
+//   phase 1  one thread per (row, 256-block) -- 256 independent chains, all lanes busy -- replays the recurrence and keeps every
+//            16th coordinate (an ANCHOR) in shared memory (32 x 129 float2);
+//   phase 2  the band is walked in 32 x 128 tiles; a thread owns one 16-pixel run of a row: it restarts the recurrence at the run's
+//            anchor (15 more adds -- the very same additions the reference performs) and samples as it goes, so the coordinates
+//            of the other 15 pixels never touch memory; it writes its 48 output bytes as three 16-byte stores.
+// With a tensor map (uniform batches: frames of one shape at a constant stride) the source box of tile t + 2 is fetched by ONE
+// tiled TMA load (cp.async.bulk.tensor.3d, SASS UTMALDG.3D) into a two-deep shared-memory ring while tile t is sampled, and the
+// taps come from shared memory; the box (448 bytes x 64 rows) covers rotations of about +-12 degrees at unit scale.  A pixel whose
+// footprint is not inside the loaded box (large angles, down-scaling maps, image borders, no tensor map at all) takes the generic
+// tap path of warp_pixel -- decided per pixel from its replayed coordinate, so a wrong box estimate can cost time, not correctness.
+// The box must START on a 16-byte boundary of the innermost dimension: a tile coordinate with (c0 * 4) % 16 != 0 faults with
+// "illegal instruction" at the UTMALDG (measured, tools/probe/tma_probe.cu), so the byte column of the box is aligned down to 16.
+constexpr int kBandH = 32, kBandW = 2048, kBandTileW = 128, kRun = 16;
+constexpr int kAnchorPitch = kBandW / kRun + 1;                       // float2 per row (+1: conflict-free column accesses)
+constexpr int kTmaBoxBytes = 448, kTmaBoxRows = 64;
+constexpr size_t kBandSmem = sizeof(float2) * kBandH * kAnchorPitch + 2 * (size_t)kTmaBoxRows * kTmaBoxBytes + 128;
+
+struct BoxInfo { int use, bx, by; };
 
 template <bool CLAMP>
-__global__ void __launch_bounds__(256) warp_affine_tma_kernel(const WarpDesc *__restrict__ descs, int n, int64_t total_tiles, float border,
-                                                              const CUtensorMap *__restrict__ tmap) {
-  __shared__ __align__(128) uint8_t box[kTmaBoxRows * kTmaBoxBytes];
-  __shared__ float2 coords[kTmaTileH][kTmaTileW];
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ int s_first, s_use, s_bx, s_by;
-  const int64_t per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
-  const int64_t t0 = (int64_t)blockIdx.x * per_cta, t1 = min(total_tiles, t0 + per_cta);
-  if (t0 >= t1) return;
-  if (threadIdx.x == 0) {
-    s_first = find_warp_sample(descs, n, t0);
-    mbar_init(&bar, 1);
+__global__ void __launch_bounds__(256, 2) warp_affine_band_kernel(const WarpDesc *__restrict__ descs, int n, int64_t total_items, float border,
+                                                                  const __grid_constant__ CUtensorMap tmap, int use_tma) {
+  extern __shared__ __align__(128) uint8_t band_smem[];
+  uint8_t *box0 = band_smem;                                                       // 2 boxes, 128-byte aligned
+  float2 *anchors = reinterpret_cast<float2 *>(band_smem + 2 * kTmaBoxRows * kTmaBoxBytes);
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ BoxInfo binfo[2];
+  __shared__ int s_first;
+  const int tid = threadIdx.x;
+  const int64_t per_cta = (total_items + gridDim.x - 1) / gridDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * per_cta, i1 = min(total_items, i0 + per_cta);
+  if (i0 >= i1) return;
+  if (tid == 0) {
+    s_first = find_warp_sample(descs, n, i0);
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   int s = s_first;
-  uint32_t phase = 0;
-  for (int64_t tile = t0; tile < t1; tile++) {
-    while (s + 1 < n && descs[s + 1].first_tile <= tile) s++;
+  uint32_t phase[2] = {0u, 0u};
+  for (int64_t item = i0; item < i1; item++) {
+    while (s + 1 < n && descs[s + 1].first_tile <= item) s++;
     const WarpDesc &d = descs[s];
-    const int64_t tl = tile - d.first_tile;
-    const int ty = (int)(tl / d.tiles_x), tx = (int)(tl % d.tiles_x);
-    const int y0 = ty * kTmaTileH, x0 = tx * kTmaTileW;
-    const int th = min(kTmaTileH, d.out_h - y0), tw = min(kTmaTileW, d.out_w - x0);
-    // ---- stage 1: replay the reference's coordinate accumulation (re-anchored every 256 pixels), one thread per row
-    if (threadIdx.x < th) {
-      const int y = y0 + threadIdx.x;
-      const float vx = 0.5f, vy = (float)y + 0.5f;
-      float sx = add_rn(add_rn(d.m[2], mul_rn(d.m[0], vx)), mul_rn(d.m[1], vy));
-      float sy = add_rn(add_rn(d.m[5], mul_rn(d.m[3], vx)), mul_rn(d.m[4], vy));
-      const float dx = d.m[0], dy = d.m[3];
-      const float tdx = mul_rn(256.0f, dx), tdy = mul_rn(256.0f, dy);
-      for (int t = 0; t < x0 / kWarpTileW; t++) { sx = add_rn(sx, tdx); sy = add_rn(sy, tdy); }
-      for (int j = 0; j < x0 % kWarpTileW; j++) { sx = add_rn(sx, dx); sy = add_rn(sy, dy); }
-      for (int j = 0; j < tw; j++) {
-        coords[threadIdx.x][j] = make_float2(sx, sy);
-        sx = add_rn(sx, dx); sy = add_rn(sy, dy);
-      }
-    }
-    __syncthreads();
-    // ---- source box of the tile (the map is affine: the extremes sit at the corners; one pixel of margin covers the rounding of the
-    //      replayed coordinates) and the TMA load
-    if (threadIdx.x == 0) {
-      const float2 c00 = coords[0][0], c01 = coords[0][tw - 1], c10 = coords[th - 1][0], c11 = coords[th - 1][tw - 1];
-      const float minx = fminf(fminf(c00.x, c01.x), fminf(c10.x, c11.x)), maxx = fmaxf(fmaxf(c00.x, c01.x), fmaxf(c10.x, c11.x));
-      const float miny = fminf(fminf(c00.y, c01.y), fminf(c10.y, c11.y)), maxy = fmaxf(fmaxf(c00.y, c01.y), fmaxf(c10.y, c11.y));
-      const int ix0 = (int)floorf(minx - 0.5f) - 1, ix1 = (int)floorf(maxx - 0.5f) + 2;      // taps ix .. ix + 1, margin 1
-      const int iy0 = (int)floorf(miny - 0.5f) - 1, iy1 = (int)floorf(maxy - 0.5f) + 2;
-      const int bx = (ix0 * 3) & ~3;                                     // byte column of the box, 32-bit aligned
-      const bool fits = (ix1 + 2) * 3 - bx <= kTmaBoxBytes && iy1 - iy0 + 1 <= kTmaBoxRows;
-      // the 12-byte windows read per tap pair must stay inside the image rows: two pixels of slack on the right
-      const bool inside = ix0 >= 0 && iy0 >= 0 && ix1 + 2 < d.in_w && iy1 < d.in_h;
-      s_use = fits && inside;
-      s_bx = bx; s_by = iy0;
-      if (s_use) {
-        mbar_expect_tx(&bar, kTmaBoxRows * kTmaBoxBytes);
-        tma_load_3d(box, tmap, bx >> 2, iy0, s, &bar);
-      }
-    }
-    __syncthreads();
-    const bool use_box = s_use != 0;
-    const int bxb = s_bx, by0 = s_by;
-    if (use_box) { mbar_wait(&bar, phase); phase ^= 1u; }
-    // ---- stage 2: sample; one thread = 4 consecutive pixels of a row
-    uint8_t *out = static_cast<uint8_t *>(d.out);
-    const int gpr = (tw + 3) >> 2;
-    const uint32_t a_box = smem_u32(box);
-    for (int e = threadIdx.x; e < th * gpr; e += blockDim.x) {
-      const int r = e / gpr, j0 = (e - r * gpr) << 2;
-      const int np = min(4, tw - j0);
-      uint8_t *o = out + ((int64_t)(y0 + r) * d.out_w + x0 + j0) * 3;
-      uint32_t b[12];
-      for (int k = 0; k < np; k++) {
-        float res[3];
-        const float2 src = coords[r][j0 + k];
-        if (use_box) {
-          const float fx = sub_rn(src.x, 0.5f), fy = sub_rn(src.y, 0.5f);
-          const float flx = floorf(fx), fly = floorf(fy);
-          const int ix = (int)flx, iy = (int)fly;
-          const float qx = sub_rn(fx, flx), px = sub_rn(1.0f, qx), qy = sub_rn(fy, fly);
-          float t[2][6];
+    const int64_t li = item - d.first_tile;
+    const int by_ = (int)((uint32_t)li / (uint32_t)d.tiles_x), gx = (int)((uint32_t)li - (uint32_t)by_ * (uint32_t)d.tiles_x);
+    const int y0 = by_ * kBandH, X0 = gx * kBandW;
+    const int bh = min(kBandH, d.out_h - y0), bw = min(kBandW, d.out_w - X0);
+    const float dx = d.m[0], dy = d.m[3];
+    // ---- phase 1: anchors.  thread = (row, 256-block of the band)
+    {
+      const int r = tid & 31, k = tid >> 5;                       // 8 blocks of 256 columns
+      if (r < bh && k * 256 < bw) {
+        const float vy = (float)(y0 + r) + 0.5f;
+        float sx = add_rn(add_rn(d.m[2], mul_rn(d.m[0], 0.5f)), mul_rn(d.m[1], vy));
+        float sy = add_rn(add_rn(d.m[5], mul_rn(d.m[3], 0.5f)), mul_rn(d.m[4], vy));
+        const float tdx = mul_rn(256.0f, dx), tdy = mul_rn(256.0f, dy);
+        for (int t = 0; t < (X0 >> 8) + k; t++) { sx = add_rn(sx, tdx); sy = add_rn(sy, tdy); }
+        const int steps = min(256, bw - k * 256);
+        float2 *arow = anchors + r * kAnchorPitch + k * (256 / kRun);
+        for (int j = 0; j < steps; j += kRun) {
+          arow[j / kRun] = make_float2(sx, sy);
 #pragma unroll
-          for (int rr = 0; rr < 2; rr++) {
-            const uint32_t off = (uint32_t)((iy + rr - by0) * kTmaBoxBytes + ix * 3 - bxb);
-            const uint32_t sh = off & 3u, a = a_box + (off & ~3u);
-            const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 4), w2 = lds_u32(a + 8);
-            const uint32_t lo = __funnelshift_r(w0, w1, sh * 8u), hi = __funnelshift_r(w1, w2, sh * 8u);
-            t[rr][0] = u8_to_float(lo & 0xFFu); t[rr][1] = u8_to_float((lo >> 8) & 0xFFu); t[rr][2] = u8_to_float((lo >> 16) & 0xFFu);
-            t[rr][3] = u8_to_float(lo >> 24); t[rr][4] = u8_to_float(hi & 0xFFu); t[rr][5] = u8_to_float((hi >> 8) & 0xFFu);
-          }
-#pragma unroll
-          for (int c = 0; c < 3; c++) {
-            const float s0 = add_rn(mul_rn(t[0][c], px), mul_rn(t[0][3 + c], qx));
-            const float s1 = add_rn(mul_rn(t[1][c], px), mul_rn(t[1][3 + c], qx));
-            res[c] = add_rn(s0, mul_rn(sub_rn(s1, s0), qy));
-          }
-        } else {
-          warp_pixel<uint8_t, true, CLAMP, 3>(d, src, border, 3, res);
+          for (int q = 0; q < kRun; q++) { sx = add_rn(sx, dx); sy = add_rn(sy, dy); }
         }
-#pragma unroll
-        for (int c = 0; c < 3; c++) b[3 * k + c] = (uint32_t)sat_u8_half_away(res[c]);
-      }
-      if (np == 4 && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
-        uint32_t *o4 = reinterpret_cast<uint32_t *>(o);
-        o4[0] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-        o4[1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-        o4[2] = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
-      } else {
-        for (int k = 0; k < np * 3; k++) o[k] = (uint8_t)b[k];
       }
     }
-    __syncthreads();           // the box and the coordinates are rewritten by the next tile
+    __syncthreads();
+    // ---- phase 2: 32 x 128 tiles, two boxes in flight
+    const int ntiles = (bw + kBandTileW - 1) / kBandTileW;
+    auto issue = [&](int t) {                                     // thread 0 only: source box of tile t -> ring slot t & 1
+      const int slot = t & 1;
+      BoxInfo bi; bi.use = 0; bi.bx = 0; bi.by = 0;
+      if (use_tma) {
+        const int tx0 = X0 + t * kBandTileW, tw = min(kBandTileW, bw - t * kBandTileW);
+        // the map is affine: the extremes of the tile's footprint sit at its corners (exact map here; the replayed coordinates
+        // drift from it by far less than the one-pixel margin, and a pixel outside the box falls back to the generic taps anyway)
+        float minx = 3.0e38f, maxx = -3.0e38f, miny = 3.0e38f, maxy = -3.0e38f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const float ux = (float)(tx0 + ((c & 1) ? tw - 1 : 0)) + 0.5f, uy = (float)(y0 + ((c & 2) ? bh - 1 : 0)) + 0.5f;
+          const float px = d.m[2] + d.m[0] * ux + d.m[1] * uy, py = d.m[5] + d.m[3] * ux + d.m[4] * uy;
+          minx = fminf(minx, px); maxx = fmaxf(maxx, px); miny = fminf(miny, py); maxy = fmaxf(maxy, py);
+        }
+        if (fabsf(minx) < 1.0e6f && fabsf(maxx) < 1.0e6f && fabsf(miny) < 1.0e6f && fabsf(maxy) < 1.0e6f) {
+          const int ix0 = (int)floorf(minx - 0.5f) - 1, iy0 = (int)floorf(miny - 0.5f) - 1;
+          const int iy1 = (int)floorf(maxy - 0.5f) + 2;
+          bi.bx = (ix0 * 3) & ~15;                                  // 16-byte aligned start (TMA requirement)
+          bi.by = iy0;
+          // worth fetching only if the box can hold most of the footprint; each pixel re-checks its own taps
+          bi.use = ((int)floorf(maxx - 0.5f) + 4) * 3 - bi.bx <= kTmaBoxBytes + 96 && iy1 - iy0 + 1 <= kTmaBoxRows + 8 &&
+                   bi.bx + kTmaBoxBytes > 0 && bi.bx < d.in_w * 3 && iy0 + kTmaBoxRows > 0 && iy0 < d.in_h;
+        }
+      }
+      binfo[slot] = bi;
+      if (bi.use) {
+        mbar_expect_tx(&bars[slot], kTmaBoxRows * kTmaBoxBytes);
+        tma_load_3d(box0 + slot * kTmaBoxRows * kTmaBoxBytes, &tmap, bi.bx >> 2, bi.by, s, &bars[slot]);
+      }
+    };
+    if (tid == 0) { issue(0); if (ntiles > 1) issue(1); }
+    __syncthreads();
+    const int row = tid >> 3, seg = tid & 7;
+    uint8_t *out = static_cast<uint8_t *>(d.out);
+    for (int t = 0; t < ntiles; t++) {
+      const int slot = t & 1;
+      const BoxInfo bi = binfo[slot];
+      if (bi.use) { mbar_wait(&bars[slot], phase[slot]); phase[slot] ^= 1u; }
+      const int lx = t * kBandTileW + seg * kRun;                  // column of the run inside the band
+      if (row < bh && lx < bw) {
+        const int np = min(kRun, bw - lx);
+        const float2 a = anchors[row * kAnchorPitch + lx / kRun];
+        float sx = a.x, sy = a.y;
+        const uint32_t a_box = smem_u32(box0 + slot * kTmaBoxRows * kTmaBoxBytes);
+        uint32_t w[12];
+#pragma unroll
+        for (int q = 0; q < 12; q++) w[q] = 0u;
+#pragma unroll
+        for (int k = 0; k < kRun; k++) {
+          if (k < np) {
+            float res[3];
+            const float fx = sub_rn(sx, 0.5f), fy = sub_rn(sy, 0.5f);
+            const float flx = floorf(fx), fly = floorf(fy);
+            const int ix = (int)flx, iy = (int)fly;
+            const int col = ix * 3 - bi.bx, rr0 = iy - bi.by;
+            // taps (ix, ix + 1) x (iy, iy + 1) inside the image AND their 12-byte windows inside the loaded box
+            const bool in_box = bi.use && col >= 0 && col + 12 <= kTmaBoxBytes && rr0 >= 0 && rr0 + 1 < kTmaBoxRows &&
+                                ix >= 0 && ix + 1 < d.in_w && iy >= 0 && iy + 1 < d.in_h;
+            if (in_box) {
+              const float qx = sub_rn(fx, flx), px = sub_rn(1.0f, qx), qy = sub_rn(fy, fly);
+              float tp[2][6];
+#pragma unroll
+              for (int rr = 0; rr < 2; rr++) {
+                const uint32_t off = (uint32_t)((rr0 + rr) * kTmaBoxBytes + col);
+                const uint32_t sh = off & 3u, ad = a_box + (off & ~3u);
+                const uint32_t w0 = lds_u32(ad), w1 = lds_u32(ad + 4), w2 = lds_u32(ad + 8);
+                const uint32_t lo = __funnelshift_r(w0, w1, sh * 8u), hi = __funnelshift_r(w1, w2, sh * 8u);
+                tp[rr][0] = u8_to_float(lo & 0xFFu); tp[rr][1] = u8_to_float((lo >> 8) & 0xFFu); tp[rr][2] = u8_to_float((lo >> 16) & 0xFFu);
+                tp[rr][3] = u8_to_float(lo >> 24); tp[rr][4] = u8_to_float(hi & 0xFFu); tp[rr][5] = u8_to_float((hi >> 8) & 0xFFu);
+              }
+#pragma unroll
+              for (int c = 0; c < 3; c++) {
+                const float s0 = add_rn(mul_rn(tp[0][c], px), mul_rn(tp[0][3 + c], qx));
+                const float s1 = add_rn(mul_rn(tp[1][c], px), mul_rn(tp[1][3 + c], qx));
+                res[c] = add_rn(s0, mul_rn(sub_rn(s1, s0), qy));
+              }
+            } else {
+              warp_pixel<uint8_t, true, CLAMP, 3>(d, make_float2(sx, sy), border, 3, res);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              const int bidx = 3 * k + c;
+              w[bidx >> 2] |= (uint32_t)sat_u8_half_away(res[c]) << (8 * (bidx & 3));
+            }
+            sx = add_rn(sx, dx); sy = add_rn(sy, dy);
+          }
+        }
+        uint8_t *o = out + ((int64_t)(y0 + row) * d.out_w + X0 + lx) * 3;
+        if (np == kRun && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+          uint4 *o16 = reinterpret_cast<uint4 *>(o);
+          o16[0] = make_uint4(w[0], w[1], w[2], w[3]); o16[1] = make_uint4(w[4], w[5], w[6], w[7]); o16[2] = make_uint4(w[8], w[9], w[10], w[11]);
+        } else if (np == kRun && (reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+          uint32_t *o4 = reinterpret_cast<uint32_t *>(o);
+#pragma unroll
+          for (int q = 0; q < 12; q++) o4[q] = w[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < kRun * 3; q++)
+            if (q < np * 3) o[q] = (uint8_t)(w[q >> 2] >> (8 * (q & 3)));
+        }
+      }
+      __syncthreads();                                             // every reader of ring slot `slot` is done
+      if (tid == 0 && t + 2 < ntiles) issue(t + 2);
+    }
+    __syncthreads();                                               // anchors and binfo are rewritten by the next item
   }
 }
 
@@ -322,12 +376,11 @@ struct dalib200WarpPlan {
   DescArena arena;
   cudaEvent_t uploaded = nullptr;
   bool pending = false;
-  // tensor-map path (uniform batches): descriptors re-tiled to 16 x 128, map cached per (base, stride, shape)
+  // band kernel / tensor-map path: the map is cached per (base, stride, shape)
   std::vector<dalib200WarpSample> samples;
   CUtensorMap tmap;
-  CUtensorMap *d_tmap = nullptr;            // device copy read by the kernel
   const void *tmap_base = nullptr; size_t tmap_stride = 0; int tmap_h = 0, tmap_w = 0, tmap_n = 0;
-  int path = 0;                  // 1 = the last launch used the tensor-map kernel
+  int path = 0;                  // last launch: 0 generic kernel, 1 band kernel with tensor-map TMA boxes, 2 band kernel without
 };
 
 namespace {
@@ -378,7 +431,6 @@ int dalib200WarpPlanDestroy(dalib200WarpPlan *p) {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   p->arena.Free();
-  if (p->d_tmap) cudaFree(p->d_tmap);
   delete p;
   return DALIB200_SUCCESS;
 }
@@ -419,13 +471,15 @@ int dalib200WarpLaunch(dalib200WarpPlan *p, const void *const *in_ptrs, void *co
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
   auto *descs = reinterpret_cast<WarpDesc *>(p->arena.host);
   for (int i = 0; i < p->n; i++) { descs[i].in = static_cast<const uint8_t *>(in_ptrs[i]); descs[i].out = out_ptrs[i]; }
-  // ---- tensor-map path: bilinear u8 -> u8 over a uniform batch of 3-channel frames laid out at a constant stride
-  bool tma = p->interp == 1 && p->out_dtype == DALIB200_UINT8 && p->n >= 1 && !getenv("DALIB200_WARP_NO_TMA") && GetEncodeTiled() != nullptr;
+  // ---- band kernel: bilinear u8 -> u8, every sample 3-channel (DALIB200_WARP_GENERIC=1 forces the generic kernel: A/B runs)
+  bool band = p->interp == 1 && p->out_dtype == DALIB200_UINT8 && !getenv("DALIB200_WARP_GENERIC");
+  for (int i = 0; i < p->n && band; i++) band = p->samples[i].channels == 3;
+  // ---- ... with tensor-map TMA source boxes when the batch is uniform: frames of one shape laid out at a constant stride
+  bool tma = band && !getenv("DALIB200_WARP_NO_TMA") && GetEncodeTiled() != nullptr;
   const auto &s0 = p->samples[0];
   size_t stride = 0;
   if (tma) {
-    tma = s0.channels == 3 && (s0.in_w * 3) % 16 == 0 && reinterpret_cast<uintptr_t>(in_ptrs[0]) % 16 == 0 && s0.in_w * 3 / 4 >= kTmaBoxBytes / 4 &&
-          s0.in_h >= 1;
+    tma = (s0.in_w * 3) % 16 == 0 && reinterpret_cast<uintptr_t>(in_ptrs[0]) % 16 == 0 && s0.in_w * 3 >= kTmaBoxBytes;
     if (tma && p->n > 1) {
       stride = static_cast<const uint8_t *>(in_ptrs[1]) - static_cast<const uint8_t *>(in_ptrs[0]);
       tma = static_cast<const uint8_t *>(in_ptrs[1]) > static_cast<const uint8_t *>(in_ptrs[0]) && stride % 16 == 0 &&
@@ -435,62 +489,54 @@ int dalib200WarpLaunch(dalib200WarpPlan *p, const void *const *in_ptrs, void *co
     }
     for (int i = 0; i < p->n && tma; i++) {
       const auto &s = p->samples[i];
-      tma = s.in_h == s0.in_h && s.in_w == s0.in_w && s.channels == 3 &&
+      tma = s.in_h == s0.in_h && s.in_w == s0.in_w &&
             static_cast<const uint8_t *>(in_ptrs[i]) == static_cast<const uint8_t *>(in_ptrs[0]) + (size_t)i * stride;
     }
   }
   if (tma && (p->tmap_base != in_ptrs[0] || p->tmap_stride != stride || p->tmap_h != s0.in_h || p->tmap_w != s0.in_w || p->tmap_n != p->n)) {
-    // the batch as a rank-3 tensor of 32-bit words: [frame][row][word]; box = 112 words x 48 rows x 1 frame
+    // the batch as a rank-3 tensor of 32-bit words: [frame][row][word]; box = 112 words x 64 rows x 1 frame
     const cuuint64_t dims[3] = { (cuuint64_t)s0.in_w * 3 / 4, (cuuint64_t)s0.in_h, (cuuint64_t)p->n };
     const cuuint64_t strides[2] = { (cuuint64_t)s0.in_w * 3, (cuuint64_t)stride };
     const cuuint32_t box[3] = { kTmaBoxBytes / 4, kTmaBoxRows, 1 }, estr[3] = { 1, 1, 1 };
     const CUresult r = GetEncodeTiled()(&p->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(in_ptrs[0]), dims, strides, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r == CUDA_SUCCESS && !p->d_tmap && cudaMalloc(reinterpret_cast<void **>(&p->d_tmap), sizeof(CUtensorMap)) != cudaSuccess) {
-      cudaGetLastError(); p->d_tmap = nullptr;
-    }
-    if (r != CUDA_SUCCESS || !p->d_tmap ||
-        cudaMemcpyAsync(p->d_tmap, &p->tmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice, stream) != cudaSuccess) {
+    if (r != CUDA_SUCCESS) {
       tma = false; p->tmap_base = nullptr;
     } else {
       p->tmap_base = in_ptrs[0]; p->tmap_stride = stride; p->tmap_h = s0.in_h; p->tmap_w = s0.in_w; p->tmap_n = p->n;
     }
   }
-  p->path = tma ? 1 : 0;
-  int64_t total_tiles = p->total_tiles;
-  if (tma) {                     // 16 x 128 tiles
-    total_tiles = 0;
-    for (int i = 0; i < p->n; i++) {
-      descs[i].tiles_x = (descs[i].out_w + kTmaTileW - 1) / kTmaTileW;
-      descs[i].tiles_y = (descs[i].out_h + kTmaTileH - 1) / kTmaTileH;
-      descs[i].first_tile = total_tiles;
-      total_tiles += (int64_t)descs[i].tiles_x * descs[i].tiles_y;
-    }
-  } else {
-    int64_t t = 0;
-    for (int i = 0; i < p->n; i++) {
-      descs[i].tiles_x = (descs[i].out_w + kWarpTileW - 1) / kWarpTileW;
-      descs[i].tiles_y = (descs[i].out_h + kWarpTileH - 1) / kWarpTileH;
-      descs[i].first_tile = t;
-      t += (int64_t)descs[i].tiles_x * descs[i].tiles_y;
-    }
+  p->path = !band ? 0 : tma ? 1 : 2;
+  int64_t total_tiles = 0;
+  for (int i = 0; i < p->n; i++) {        // work items: 32-row bands x 2048-column groups, or the generic kernel's 16 x 256 tiles
+    descs[i].tiles_x = band ? (descs[i].out_w + kBandW - 1) / kBandW : (descs[i].out_w + kWarpTileW - 1) / kWarpTileW;
+    descs[i].tiles_y = band ? (descs[i].out_h + kBandH - 1) / kBandH : (descs[i].out_h + kWarpTileH - 1) / kWarpTileH;
+    descs[i].first_tile = total_tiles;
+    total_tiles += (int64_t)descs[i].tiles_x * descs[i].tiles_y;
   }
   int rc = p->arena.Upload(sizeof(WarpDesc) * p->n, stream);
   if (rc) return rc;
   DB_CUDA(cudaEventRecord(p->uploaded, stream));
   p->pending = true;
   const auto *dd = reinterpret_cast<const WarpDesc *>(p->arena.dev);
-  const int grid = (int)std::min<int64_t>(total_tiles, (int64_t)NumSMs() * 16);
   const bool lin = p->interp == 1, clampb = !p->use_fill, u8 = p->out_dtype == DALIB200_UINT8;
-  if (tma) {
-    ProfScope ps_("warp_affine_tma", stream);
-    if (clampb) warp_affine_tma_kernel<true><<<grid, 256, 0, stream>>>(dd, p->n, total_tiles, p->border, p->d_tmap);
-    else warp_affine_tma_kernel<false><<<grid, 256, 0, stream>>>(dd, p->n, total_tiles, p->border, p->d_tmap);
+  if (band) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DB_CUDA(cudaFuncSetAttribute(warp_affine_band_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandSmem));
+      DB_CUDA(cudaFuncSetAttribute(warp_affine_band_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandSmem));
+      attr_set = true;
+    }
+    const int grid = (int)std::min<int64_t>(total_tiles, (int64_t)NumSMs() * 2);
+    ProfScope ps_(tma ? "warp_affine_tma" : "warp_affine_band", stream);
+    if (clampb) warp_affine_band_kernel<true><<<grid, 256, kBandSmem, stream>>>(dd, p->n, total_tiles, p->border, p->tmap, tma ? 1 : 0);
+    else warp_affine_band_kernel<false><<<grid, 256, kBandSmem, stream>>>(dd, p->n, total_tiles, p->border, p->tmap, tma ? 1 : 0);
     CountLaunch();
     DB_CUDA(cudaGetLastError());
     return DALIB200_SUCCESS;
   }
+  const int grid = (int)std::min<int64_t>(total_tiles, (int64_t)NumSMs() * 16);
   ProfScope ps_("warp_affine", stream);
 #define LAUNCH(O, L, Cc) warp_affine_kernel<O, L, Cc><<<grid, 256, 0, stream>>>(dd, p->n, total_tiles, p->border)
   if (u8) {

@@ -124,6 +124,9 @@ int dalib200JpegUpload(dalib200JpegPlan *plan, dalib200Stream_t stream);
  * through the pinned staging buffer.  JpegPlanLastUploadDirect: 1 when the last upload took the direct path. */
 int dalib200JpegPlanSetSourceStable(dalib200JpegPlan *plan, int stable);
 int dalib200JpegPlanLastUploadDirect(const dalib200JpegPlan *plan);
+/* Test hook: exhaustive (2^32 inputs) check of the kernels' float -> float16 conversion against the integer restatement of the
+ * reference's half_float rounding (include/dali/util/half.hpp, ties away from zero).  *mismatches == 0 on success. */
+int dalib200DebugCheckHalfConversion(uint64_t *mismatches);
 /* Page-locked host memory for callers that want the direct path (cudaHostAlloc / cudaFreeHost behind the C ABI). */
 int dalib200HostAlloc(void **ptr, size_t bytes);
 int dalib200HostFree(void *ptr);
@@ -213,8 +216,10 @@ int dalib200WarpPlanSetup(dalib200WarpPlan *plan, int n, const dalib200WarpSampl
                           int interp /* NN | LINEAR */, int use_fill, float fill_value,
                           int out_dtype /* UINT8 | FLOAT */);
 int dalib200WarpLaunch(dalib200WarpPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
-/* 1 when the last launch staged source tiles with tiled TMA loads through a tensor map (bilinear u8 -> u8 over 3-channel frames of
- * one shape laid out at a constant 16-byte-aligned stride, e.g. the frames of an FHWC batch); 0 for the generic kernel. */
+/* Kernel taken by the last launch: 1 = band kernel with the source boxes staged by tiled TMA loads through a tensor map (bilinear
+ * u8 -> u8 over 3-channel frames of one shape laid out at a constant 16-byte-aligned stride, e.g. the frames of an FHWC batch);
+ * 2 = band kernel without a tensor map (bilinear u8 -> u8, 3 channels, any shapes); 0 = generic kernel (NN, float output, other
+ * channel counts). */
 int dalib200WarpPlanGetPath(const dalib200WarpPlan *plan);
 /* host helper: include/dali/core/geom/transform.h:166-174 */
 void dalib200AffineInverse(const float *m2x3, float *out2x3);

@@ -45,6 +45,16 @@ def test_cmn_reference_shape_matrix():
                         assert np.array_equal(bits(o), bits(want)), (img.shape, a, c, dt, pad, mirror, layout)
 
 
+def test_half_conversion_exhaustive():
+    """The kernels convert float -> float16 with ONE hardware conversion (round to nearest even of `bits | 1`); it must equal the
+    integer restatement of the reference's half_float rounding (ties away from zero, after the +-65504 clamp) for all 2^32 floats."""
+    import ctypes as C
+    from dali_b200 import capi
+    bad = C.c_uint64(123)
+    capi.check(capi.lib().dalib200DebugCheckHalfConversion(C.byref(bad)))
+    assert bad.value == 0
+
+
 def test_cmn_random_windows_and_padding():
     import gpu_helpers as g
     rng = np.random.default_rng(21)

@@ -62,9 +62,10 @@ def test_warp_c3_frame():
 
 
 def test_warp_tensor_map_tma_path():
-    """Uniform batches of 3-channel frames at a constant stride take the tensor-map TMA kernel (tile boxes staged in shared memory by
-    cp.async.bulk.tensor); tiles at the border, or whose footprint exceeds the box (large angles, down-scaling maps), fall back per
-    tile.  Everything stays bit-exact, for both border modes and for output sizes that are not tile multiples."""
+    """Bilinear u8 3-channel batches take the band kernel (anchored coordinate replay); uniform batches at a constant stride
+    additionally get their source boxes staged in shared memory by tiled TMA loads through a tensor map (cp.async.bulk.tensor);
+    pixels at the border, or whose footprint is not inside the box (large angles, down-scaling maps), fall back per pixel.
+    Everything stays bit-exact, for both border modes and for output sizes that are not tile multiples."""
     import gpu_helpers as g
     rng = np.random.default_rng(57)
     for (H, W), out_hw in (((360, 640), None), ((200, 448), (173, 301)), ((96, 1280), (96, 1277))):
@@ -87,11 +88,11 @@ def test_warp_tensor_map_tma_path():
         assert path == 0
         for im, M, o in zip(imgs, mats, got):
             assert np.array_equal(o, po.warp_affine(im, M, out_hw, 0, None, np.uint8))
-    # rows that are not a multiple of 16 bytes cannot be described by a tensor map
+    # rows that are not a multiple of 16 bytes cannot be described by a tensor map: band kernel without the TMA boxes
     imgs = [rng.integers(0, 256, (64, 301, 3)).astype(np.uint8) for _ in range(2)]
     mats = [np.float32([[1, 0.02, 0.5], [-0.02, 1, 0.25]])] * 2
     got, path = g.warp_affine(imgs, mats, None, 1, None, np.uint8, contiguous=True, want_path=True)
-    assert path == 0
+    assert path == 2
     for im, M, o in zip(imgs, mats, got):
         assert np.array_equal(o, po.warp_affine(im, M, None, 1, None, np.uint8))
 

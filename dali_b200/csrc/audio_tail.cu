@@ -10,6 +10,12 @@
 //                Same order, same tables -> bit-exact.
 //   Normalize    dali/operators/math/normalize/normalize.cc: out = (in - mean) * scale / sqrt(var + eps) + shift over the reduced
 //                axes of a 2-D sample; the mean / variance sums are tree reductions here (tolerance: 1e-5 relative).
+//   NonsilentRegion  dali/operators/audio/nonsilence_op.h:60-130 + dali/kernels/signal/moving_mean_square.cc:55-77: moving mean
+//                square with a RUNNING float sum (add the new square, emit, subtract the oldest), restarted every `reset_interval`
+//                samples; threshold = reference * 10^(cutoff_db / 10) with reference = the maximum of the moving mean square by
+//                default; first / last sample at or above it; the start is moved back by window_length - 1.  The running sum
+//                is a serial float recurrence: one thread replays one reset interval (bit-exact), intervals and samples in
+//                parallel; the reductions behind it are exact (max / min / max index).
 // Every op is one launch per batch over a per-sample descriptor list (one H2D descriptor copy per launch).
 #include "common.cuh"
 #include <algorithm>
@@ -18,7 +24,7 @@
 
 namespace dalib200 {
 
-enum { SIG_NONE = 0, SIG_TODB = 1, SIG_MFCC = 2, SIG_NORMALIZE = 3 };
+enum { SIG_NONE = 0, SIG_TODB = 1, SIG_MFCC = 2, SIG_NORMALIZE = 3, SIG_NONSILENT = 4 };
 
 struct SigDesc {
   const float *in; float *out;
@@ -31,6 +37,76 @@ __device__ __forceinline__ int find_sig(const SigDesc *d, int n, int64_t v) {
   int lo = 0, hi = n - 1;
   while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (d[mid].first_item <= v) lo = mid; else hi = mid - 1; }
   return lo;
+}
+
+// ---- NonsilentRegion
+struct NsDesc {
+  const float *in; float *mms;          // mms: scratch, one float per input sample
+  int32_t *begin, *length;
+  int64_t n, first_item;                // items = reset intervals
+  float factor, reference;              // threshold = ref * factor, ref = reference > 0 ? reference : max(mms)
+  int32_t window, interval;
+};
+
+__device__ __forceinline__ int find_ns(const NsDesc *d, int n, int64_t v) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (d[mid].first_item <= v) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+
+// thread = one reset interval of one sample (moving_mean_square.cc:55-77)
+__global__ void __launch_bounds__(128) nonsilent_mms_kernel(const NsDesc *__restrict__ descs, int n, int64_t total_items) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= total_items) return;
+  const NsDesc &d = descs[find_ns(descs, n, item)];
+  const int64_t out0 = (item - d.first_item) * d.interval, out1 = min(d.n, out0 + d.interval);
+  const float mean_factor = 1.0f / (float)d.window;
+  int64_t win_begin = out0 - d.window + 1;
+  float sumsq = 0.0f;
+  for (int64_t pos = max(win_begin, (int64_t)0); pos < out0; pos++) { const float v = __ldg(d.in + pos); sumsq = add_rn(sumsq, mul_rn(v, v)); }
+  for (int64_t pos = out0; pos < out1; pos++, win_begin++) {
+    const float v = __ldg(d.in + pos);
+    sumsq = add_rn(sumsq, mul_rn(v, v));
+    d.mms[pos] = mul_rn(sumsq, mean_factor);
+    if (win_begin >= 0) { const float o = __ldg(d.in + win_begin); sumsq = sub_rn(sumsq, mul_rn(o, o)); }
+  }
+}
+
+// CTA = one sample: maximum of the moving mean square, threshold, first / last index at or above it (nonsilence_op.h:60-130)
+__global__ void __launch_bounds__(256) nonsilent_region_kernel(const NsDesc *__restrict__ descs) {
+  const NsDesc &d = descs[blockIdx.x];
+  __shared__ float s_f[8];
+  __shared__ long long s_lo[8], s_hi[8];
+  __shared__ float s_ref;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ref = d.reference;
+  if (!(ref > 0.0f)) {
+    float m = -INFINITY;                                  // std::max chain over finite values = exact maximum
+    for (int64_t i = threadIdx.x; i < d.n; i += blockDim.x) m = fmaxf(m, d.mms[i]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) s_f[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = s_f[0]; for (int w = 1; w < 8; w++) t = fmaxf(t, s_f[w]); s_ref = t; }
+    __syncthreads();
+    ref = s_ref;
+  }
+  const float cutoff = mul_rn(ref, d.factor);             // s_ref * pow(10, cutoff_db / 10): the power is taken on the host
+  long long lo = d.n, hi = -1;
+  for (int64_t i = threadIdx.x; i < d.n; i += blockDim.x)
+    if (d.mms[i] >= cutoff) { lo = min(lo, (long long)i); hi = max(hi, (long long)i); }
+  for (int o = 16; o; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) { lo = min(lo, s_lo[w]); hi = max(hi, s_hi[w]); }
+    long long begin = 0, len = 0;
+    if (hi >= 0) { begin = lo; len = hi - lo + 1; }
+    if (begin != 0 && len != 0) {                         // the non-silent sample sits somewhere inside the window that reported it
+      const long long nb = max(begin - (d.window - 1), 0ll);
+      len += begin - nb; begin = nb;
+    }
+    *d.begin = (int32_t)begin; *d.length = (int32_t)len;
+  }
 }
 
 // ---- ToDecibels
@@ -158,6 +234,10 @@ struct dalib200SignalPlan {
   bool table_dirty = true;
   // Normalize
   int mode = 0, ddof = 0; float scale = 1, shift = 0, eps = 0;
+  // NonsilentRegion
+  std::vector<NsDesc> ns;
+  float *d_mms = nullptr; size_t d_mms_cap = 0;
+  int64_t mms_total = 0;
 };
 
 namespace {
@@ -230,6 +310,7 @@ int dalib200SignalPlanDestroy(dalib200SignalPlan *p) {
   p->arena.Free();
   if (p->d_max) cudaFree(p->d_max);
   if (p->d_table) cudaFree(p->d_table);
+  if (p->d_mms) cudaFree(p->d_mms);
   delete p;
   return DALIB200_SUCCESS;
 }
@@ -303,6 +384,65 @@ int dalib200NormalizeSetup(dalib200SignalPlan *p, const dalib200NormalizeArgs *a
     items += p->descs[i].n == 0 ? 0 : a->mode == 0 ? 1 : a->mode == 1 ? shapes[2 * i] : shapes[2 * i + 1];
   }
   p->total_items = items;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200NonsilentSetup(dalib200SignalPlan *p, int n, const int64_t *lengths, const dalib200NonsilentSample *args, int window_length,
+                           int reset_interval) {
+  DB_CHECK_ARG(p && n >= 0 && n <= p->max_batch && (n == 0 || (lengths && args)), "NonsilentSetup: bad arguments");
+  DB_CHECK_ARG(window_length > 0, "NonsilentRegion: window_length must be positive, got %d", window_length);
+  DB_CHECK_ARG(reset_interval == -1 || (reset_interval > 0 && reset_interval % window_length == 0),
+               "`reset_interval` shall be a multiple of `window_length`. Got: reset_interval: %d vs window_length: %d", reset_interval, window_length);
+  p->kind = SIG_NONSILENT; p->n = n;
+  p->ns.assign(n, NsDesc());
+  int64_t items = 0, total = 0;
+  for (int i = 0; i < n; i++) {
+    DB_CHECK_ARG(lengths[i] > 0, "NonsilentRegion: sample %d is empty", i);
+    DB_CHECK_ARG(lengths[i] < (1ll << 31), "NonsilentRegion: sample %d is too long for the int32 outputs", i);
+    NsDesc &d = p->ns[i];
+    memset(&d, 0, sizeof(d));
+    d.n = lengths[i];
+    d.window = (int32_t)std::min<int64_t>(window_length, lengths[i]);          // nonsilence_op.cc: min(window_length, num_elements)
+    d.interval = reset_interval == -1 ? (int32_t)lengths[i] : reset_interval;
+    // DecibelToMagnitude<float>(10.f, ref)(cutoff_db) = ref * pow(10.f, cutoff_db * (1.f / 10.f))   (decibel_calculator.h:60-73)
+    d.factor = std::pow(10.0f, args[i].cutoff_db * (1.0f / 10.0f));
+    d.reference = args[i].reference_power;
+    DB_CHECK_ARG(!(args[i].use_reference_power) || args[i].reference_power > 0, "`reference_power` has to be positive. Got: %g",
+                 (double)args[i].reference_power);
+    if (!args[i].use_reference_power) d.reference = 0.0f;
+    d.first_item = items;
+    items += (d.n + d.interval - 1) / d.interval;
+    total += d.n;
+  }
+  p->total_items = items; p->mms_total = total;
+  return DALIB200_SUCCESS;
+}
+
+int dalib200NonsilentLaunch(dalib200SignalPlan *p, const void *const *in_ptrs, void *const *begin_ptrs, void *const *length_ptrs,
+                            dalib200Stream_t stream) {
+  DB_CHECK_ARG(p && p->kind == SIG_NONSILENT && (p->n == 0 || (in_ptrs && begin_ptrs && length_ptrs)), "NonsilentLaunch: call NonsilentSetup first");
+  if (p->n == 0) return DALIB200_SUCCESS;
+  int rc = GrowF(p->d_mms, p->d_mms_cap, (size_t)p->mms_total);
+  if (rc) return rc;
+  if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
+  if ((rc = p->arena.Reserve(sizeof(NsDesc) * p->n))) return rc;
+  NsDesc *h = reinterpret_cast<NsDesc *>(p->arena.host);
+  int64_t off = 0;
+  for (int i = 0; i < p->n; i++) {
+    h[i] = p->ns[i];
+    h[i].in = static_cast<const float *>(in_ptrs[i]); h[i].mms = p->d_mms + off;
+    h[i].begin = static_cast<int32_t *>(begin_ptrs[i]); h[i].length = static_cast<int32_t *>(length_ptrs[i]);
+    off += p->ns[i].n;
+  }
+  if ((rc = p->arena.Upload(sizeof(NsDesc) * p->n, stream))) return rc;
+  DB_CUDA(cudaEventRecord(p->uploaded, stream));
+  p->pending = true;
+  const NsDesc *d = reinterpret_cast<const NsDesc *>(p->arena.dev);
+  { ProfScope ps_("nonsilent_mms", stream); nonsilent_mms_kernel<<<(unsigned)((p->total_items + 127) / 128), 128, 0, stream>>>(d, p->n, p->total_items); }
+  CountLaunch();
+  { ProfScope ps_("nonsilent_region", stream); nonsilent_region_kernel<<<p->n, 256, 0, stream>>>(d); }
+  CountLaunch();
+  DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
 }
 

@@ -90,6 +90,8 @@ __global__ void half_cvt_check_kernel(unsigned long long *mismatches) {
   for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < (1ull << 32); v += (uint64_t)gridDim.x * blockDim.x) {
     const float f = __uint_as_float((uint32_t)v);
     bad += float2half_ties_away(f) != float2half_ties_away_ref(f);
+    // round_u8_bits is used for values in (-0.5, 255.5) only
+    if (f > -0.4999f && f < 255.4999f) bad += (round_u8_bits(f) & 0xFFu) != (uint32_t)sat_u8_half_away(f);
   }
   if (bad) atomicAdd(mismatches, bad);
 }

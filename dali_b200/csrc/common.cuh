@@ -66,6 +66,13 @@ __device__ __forceinline__ uint8_t sat_u8_half_away(float x) {
   int i = __float_as_int(y) - 0x4B400000 + (d == 0.5f ? 1 : 0);
   return (uint8_t)min(max(i, 0), 255);
 }
+// The same conversion for values already known to lie in (-0.5, 255.5) (e.g. bilinear blends of bytes): setting the lowest mantissa
+// bit moves exactly the ties (x.5, whose lowest bit is clear) just above the midpoint, so one round-to-nearest-EVEN addition of
+// 1.5 * 2^23 leaves round-half-AWAY(x) in the low byte of the sum.  2 instructions; checked against sat_u8_half_away over the whole
+// range by dalib200DebugCheckHalfConversion.  Returns the sum's bits: the caller takes byte 0 (e.g. with a PRMT while packing).
+__device__ __forceinline__ uint32_t round_u8_bits(float x) {
+  return __float_as_uint(__fadd_rn(__uint_as_float(__float_as_uint(x) | 1u), 12582912.0f));
+}
 // dali/kernels/common/simd.h:233-263: the SSE2 store path rounds half to EVEN (cvtps2dq) then saturates.
 __device__ __forceinline__ uint8_t sat_u8_half_even(float x) {
   x = fminf(fmaxf(x, 0.0f), 255.0f);

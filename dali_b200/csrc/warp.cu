@@ -206,6 +206,13 @@ constexpr size_t kBandSmem = sizeof(float2) * kBandH * kAnchorPitch + 2 * (size_
 
 struct BoxInfo { int use, bx, by; };
 
+// the rare path of the band kernel (borders, pixels outside the loaded box), kept OUT of line: inlined into the 16-times unrolled
+// pixel loop it grew the kernel to 4 096 instructions and the warps stalled on instruction fetch (ncu: no_instruction top stall)
+template <bool CLAMP>
+__device__ __noinline__ void warp_pixel_outline(const WarpDesc &d, float sx, float sy, float border, float *res) {
+  warp_pixel<uint8_t, true, CLAMP, 3>(d, make_float2(sx, sy), border, 3, res);
+}
+
 template <bool CLAMP>
 __global__ void __launch_bounds__(256, 2) warp_affine_band_kernel(const WarpDesc *__restrict__ descs, int n, int64_t total_items, float border,
                                                                   const __grid_constant__ CUtensorMap tmap, int use_tma) {
@@ -312,33 +319,36 @@ __global__ void __launch_bounds__(256, 2) warp_affine_band_kernel(const WarpDesc
             const int ix = (int)flx, iy = (int)fly;
             const int col = ix * 3 - bi.bx, rr0 = iy - bi.by;
             // taps (ix, ix + 1) x (iy, iy + 1) inside the image AND their 12-byte windows inside the loaded box
-            const bool in_box = bi.use && col >= 0 && col + 12 <= kTmaBoxBytes && rr0 >= 0 && rr0 + 1 < kTmaBoxRows &&
-                                ix >= 0 && ix + 1 < d.in_w && iy >= 0 && iy + 1 < d.in_h;
+            const bool in_box = bi.use && (unsigned)col <= (unsigned)(kTmaBoxBytes - 12) && (unsigned)rr0 < (unsigned)(kTmaBoxRows - 1) &&
+                                (unsigned)ix < (unsigned)(d.in_w - 1) && (unsigned)iy < (unsigned)(d.in_h - 1);
             if (in_box) {
               const float qx = sub_rn(fx, flx), px = sub_rn(1.0f, qx), qy = sub_rn(fy, fly);
-              float tp[2][6];
+              // products without converting the bytes: 0x4B0000bb is the float 2^23 + b, and fma(2^23 + b, p, -2^23 p) = RN(b p)
+              // exactly (2^23 p is exact) -- one PRMT per byte instead of extract + bias subtract, the product is one FFMA
+              const float npx = mul_rn(px, -8388608.0f), nqx = mul_rn(qx, -8388608.0f);
+              float s[2][3];
 #pragma unroll
               for (int rr = 0; rr < 2; rr++) {
                 const uint32_t off = (uint32_t)((rr0 + rr) * kTmaBoxBytes + col);
                 const uint32_t sh = off & 3u, ad = a_box + (off & ~3u);
                 const uint32_t w0 = lds_u32(ad), w1 = lds_u32(ad + 4), w2 = lds_u32(ad + 8);
                 const uint32_t lo = __funnelshift_r(w0, w1, sh * 8u), hi = __funnelshift_r(w1, w2, sh * 8u);
-                tp[rr][0] = u8_to_float(lo & 0xFFu); tp[rr][1] = u8_to_float((lo >> 8) & 0xFFu); tp[rr][2] = u8_to_float((lo >> 16) & 0xFFu);
-                tp[rr][3] = u8_to_float(lo >> 24); tp[rr][4] = u8_to_float(hi & 0xFFu); tp[rr][5] = u8_to_float((hi >> 8) & 0xFFu);
+                const float b0 = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7440)), b1 = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7441));
+                const float b2 = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7442)), b3 = __uint_as_float(__byte_perm(lo, 0x4B000000u, 0x7443));
+                const float b4 = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7440)), b5 = __uint_as_float(__byte_perm(hi, 0x4B000000u, 0x7441));
+                s[rr][0] = add_rn(__fmaf_rn(b0, px, npx), __fmaf_rn(b3, qx, nqx));
+                s[rr][1] = add_rn(__fmaf_rn(b1, px, npx), __fmaf_rn(b4, qx, nqx));
+                s[rr][2] = add_rn(__fmaf_rn(b2, px, npx), __fmaf_rn(b5, qx, nqx));
               }
 #pragma unroll
-              for (int c = 0; c < 3; c++) {
-                const float s0 = add_rn(mul_rn(tp[0][c], px), mul_rn(tp[0][3 + c], qx));
-                const float s1 = add_rn(mul_rn(tp[1][c], px), mul_rn(tp[1][3 + c], qx));
-                res[c] = add_rn(s0, mul_rn(sub_rn(s1, s0), qy));
-              }
+              for (int c = 0; c < 3; c++) res[c] = add_rn(s[0][c], mul_rn(sub_rn(s[1][c], s[0][c]), qy));
             } else {
-              warp_pixel<uint8_t, true, CLAMP, 3>(d, make_float2(sx, sy), border, 3, res);
+              warp_pixel_outline<CLAMP>(d, sx, sy, border, res);
             }
 #pragma unroll
             for (int c = 0; c < 3; c++) {
               const int bidx = 3 * k + c;
-              w[bidx >> 2] |= (uint32_t)sat_u8_half_away(res[c]) << (8 * (bidx & 3));
+              w[bidx >> 2] = __byte_perm(w[bidx >> 2], round_u8_bits(res[c]), (bidx & 3) == 0 ? 0x3214 : (bidx & 3) == 1 ? 0x3240 : (bidx & 3) == 2 ? 0x3410 : 0x4210);
             }
             sx = add_rn(sx, dx); sy = add_rn(sy, dy);
           }
@@ -471,10 +481,12 @@ int dalib200WarpLaunch(dalib200WarpPlan *p, const void *const *in_ptrs, void *co
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
   auto *descs = reinterpret_cast<WarpDesc *>(p->arena.host);
   for (int i = 0; i < p->n; i++) { descs[i].in = static_cast<const uint8_t *>(in_ptrs[i]); descs[i].out = out_ptrs[i]; }
-  // ---- band kernel: bilinear u8 -> u8, every sample 3-channel (DALIB200_WARP_GENERIC=1 forces the generic kernel: A/B runs)
+  // ---- band kernel: bilinear u8 -> u8, every sample 3-channel (DALIB200_WARP_GENERIC=1 forces the generic kernel: A/B runs) ...
   bool band = p->interp == 1 && p->out_dtype == DALIB200_UINT8 && !getenv("DALIB200_WARP_GENERIC");
   for (int i = 0; i < p->n && band; i++) band = p->samples[i].channels == 3;
-  // ---- ... with tensor-map TMA source boxes when the batch is uniform: frames of one shape laid out at a constant stride
+  // ---- ... with tensor-map TMA source boxes: the batch must be uniform (frames of one shape laid out at a constant stride).
+  // Without the boxes the band kernel measures slower than the generic kernel (every pixel takes the out-of-line tap path), so it
+  // is only used together with them unless DALIB200_WARP_BAND=1 asks for it.
   bool tma = band && !getenv("DALIB200_WARP_NO_TMA") && GetEncodeTiled() != nullptr;
   const auto &s0 = p->samples[0];
   size_t stride = 0;
@@ -507,6 +519,7 @@ int dalib200WarpLaunch(dalib200WarpPlan *p, const void *const *in_ptrs, void *co
       p->tmap_base = in_ptrs[0]; p->tmap_stride = stride; p->tmap_h = s0.in_h; p->tmap_w = s0.in_w; p->tmap_n = p->n;
     }
   }
+  if (!tma && !getenv("DALIB200_WARP_BAND")) band = false;
   p->path = !band ? 0 : tma ? 1 : 2;
   int64_t total_tiles = 0;
   for (int i = 0; i < p->n; i++) {        // work items: 32-row bands x 2048-column groups, or the generic kernel's 16 x 256 tiles

@@ -1924,6 +1924,59 @@ class SignalOpBase : public Operator<GPUBackend> {
   const char *name_;
 };
 
+// dali/operators/audio/nonsilence_op.{h,cc}: leading / trailing silence detection; outputs (begin, length) as int32 scalars
+DALI_SCHEMA(NonsilentRegion)
+    .DocStr("Performs leading and trailing silence detection in an audio buffer.")
+    .NumInput(1).NumOutput(2)
+    .AddOptionalArg("cutoff_db", "The threshold, in dB, below which the signal is considered silent.", -60.0f, true)
+    .AddOptionalArg("window_length", "Size of the sliding window used to calculate the short-term power of the signal.", 2048)
+    .AddOptionalArgNoDefault("reference_power", "The reference power; when absent the maximum power of the signal is used.", true)
+    .AddOptionalArg("reset_interval", "Number of samples after which the moving mean average is recalculated (-1: never).", 8192);
+
+class NonsilentRegionGPU : public SignalOpBase {
+ public:
+  explicit NonsilentRegionGPU(const OpSpec &spec) : SignalOpBase(spec, "NonsilentRegion") {
+    window_ = spec.GetArgument<int>("window_length");
+    reset_ = spec.GetArgument<int>("reset_interval");
+    has_ref_ = spec.ArgumentDefined("reference_power");
+  }
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_FLOAT, "NonsilentRegion: the GPU path supports float input; got type ", static_cast<int>(in.type()));
+    const int n = in.num_samples();
+    std::vector<int64_t> len(n);
+    std::vector<dalib200NonsilentSample> args(n);
+    for (int i = 0; i < n; i++) {
+      len[i] = in.shape().tensor_size(i);
+      args[i].cutoff_db = spec_.GetArgument<float>("cutoff_db", &ws, i);
+      args[i].use_reference_power = has_ref_ ? 1 : 0;
+      args[i].reference_power = has_ref_ ? spec_.GetArgument<float>("reference_power", &ws, i) : 0.0f;
+      DALI_ENFORCE(!has_ref_ || args[i].reference_power > 0, "`reference_power` has to be positive. Got: ", args[i].reference_power);
+    }
+    CheckStatus(dalib200NonsilentSetup(plan_, n, len.data(), args.data(), window_, reset_), name_);
+    out.resize(2);
+    for (int o = 0; o < 2; o++) {
+      out[o].type = DALI_INT32;
+      out[o].shape.resize(n, 0);
+    }
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &begin = ws.Output<GPUBackend>(0);
+    auto &length = ws.Output<GPUBackend>(1);
+    const int n = in.num_samples();
+    std::vector<const void *> ip(n);
+    std::vector<void *> bp(n), lp(n);
+    for (int i = 0; i < n; i++) { ip[i] = in.raw_tensor(i); bp[i] = begin.raw_mutable_tensor(i); lp[i] = length.raw_mutable_tensor(i); }
+    CheckStatus(dalib200NonsilentLaunch(plan_, ip.data(), bp.data(), lp.data(), ws.stream()), name_);
+  }
+  int window_ = 2048, reset_ = 8192;
+  bool has_ref_ = false;
+};
+DALI_REGISTER_OPERATOR(NonsilentRegion, NonsilentRegionGPU, GPU);
+
 DALI_SCHEMA(ToDecibels)
     .DocStr("Converts a magnitude (real, positive) to the decibel scale.")
     .NumInput(1).NumOutput(1)

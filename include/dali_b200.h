@@ -324,6 +324,19 @@ int dalib200NormalizeSetup(dalib200SignalPlan *plan, const dalib200NormalizeArgs
 /* in_ptrs[i] / out_ptrs[i]: device f32 */
 int dalib200SignalLaunch(dalib200SignalPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
 
+/* NonsilentRegion (dali/operators/audio/nonsilence_op.{h,cc}; moving mean square: dali/kernels/signal/moving_mean_square.cc):
+ * float input, two int32 scalars per sample (begin, length).  use_reference_power == 0: the reference is the maximum of the
+ * moving mean square (the operator's default).  reset_interval: -1 or a multiple of window_length (float inputs: 8192). */
+typedef struct {
+  float cutoff_db;
+  float reference_power;
+  int32_t use_reference_power;
+} dalib200NonsilentSample;
+int dalib200NonsilentSetup(dalib200SignalPlan *plan, int n, const int64_t *lengths, const dalib200NonsilentSample *args,
+                           int window_length, int reset_interval);
+int dalib200NonsilentLaunch(dalib200SignalPlan *plan, const void *const *in_ptrs, void *const *begin_ptrs,
+                            void *const *length_ptrs, dalib200Stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Small per-pixel / geometry helpers for interleaved u8 images:
  *   multiply-add   out = ConvertSat<Out>(in * multiplier + addend)   -- brightness_contrast

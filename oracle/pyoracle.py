@@ -429,6 +429,16 @@ def ref_to_decibels(x, multiplier=10.0, reference=None, cutoff_db=-200.0):
     return out
 
 
+def ref_nonsilent_region(x, cutoff_db=-60.0, window_length=2048, reference_power=None, reset_interval=8192):
+    """dali/operators/audio/nonsilence_op.h over the compiled reference kernels (moving mean square, dB -> magnitude): (begin, length)."""
+    a = np.ascontiguousarray(x, np.float32)
+    b, l = C.c_int32(-1), C.c_int32(-1)
+    rc = ref().ref_nonsilent_region(_p(a), C.c_int64(a.size), C.c_float(cutoff_db), C.c_float(reference_power or 0.0), int(reference_power is not None),
+                                    int(window_length), int(reset_interval), C.byref(b), C.byref(l))
+    assert rc == 0
+    return b.value, l.value
+
+
 def ref_mfcc(mel, n_mfcc=20, dct_type=2, normalize=False, lifter=0.0):
     """dali/kernels/signal/dct/dct_cpu.cc along axis 0 of [nfeat, ncols] + the liftering of dali/operators/audio/mfcc."""
     a = np.ascontiguousarray(mel, np.float32)

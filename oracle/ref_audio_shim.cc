@@ -66,7 +66,44 @@ int ref_mel_filter_bank_ft(const float *in, int nbin, int64_t nwin, float *out, 
 #include "dali/kernels/signal/dct/dct_cpu.cc"               // NOLINT
 #include "dali/operators/audio/mfcc/mfcc.h"                 // LifterCoeffs::CalculateCoeffs (private; built with -fno-access-control)
 
+#include "dali/kernels/signal/moving_mean_square.cc"       // NOLINT
+#include "dali/kernels/signal/decibel/decibel_calculator.h"
+
 extern "C" {
+
+// NonsilentRegion for one float sample: the reference's MovingMeanSquareCpu and DecibelToMagnitude, with the thresholding and
+// window adjustment of dali/operators/audio/nonsilence_op.h:60-130 (that header pulls in the whole operator framework, so its
+// 25 lines of index logic are restated here around the reference kernels).
+int ref_nonsilent_region(const float *in, int64_t n, float cutoff_db, float reference_power, int use_reference_power, int window_length,
+                         int reset_interval, int32_t *begin, int32_t *length) {
+  try {
+    signal::MovingMeanSquareCpu<float> mms;
+    signal::MovingMeanSquareArgs args{std::min<int>(window_length, (int)n), reset_interval};
+    KernelContext ctx;
+    InTensorCPU<float, 1> tin(in, TensorShape<1>(n));
+    std::vector<float> buf(n);
+    OutTensorCPU<float, 1> tout(buf.data(), TensorShape<1>(n));
+    mms.Setup(ctx, tin, args);
+    mms.Run(ctx, tout, tin, args);
+    float ref = reference_power;
+    if (!use_reference_power) { ref = buf[0]; for (int64_t i = 1; i < n; i++) ref = std::max(ref, buf[i]); }
+    signal::DecibelToMagnitude<float> db2mag(10.f, ref);
+    const float cutoff = db2mag(cutoff_db);
+    int64_t end = n, b = n;
+    for (int64_t i = 0; i < end; i++) if (buf[i] >= cutoff) { b = i; break; }
+    int64_t first = 0, second = 0;
+    if (b != end) {
+      for (int64_t i = end - 1; i >= b; i--) if (buf[i] >= cutoff) { end = i; break; }
+      first = b; second = end - b + 1;
+    }
+    if (first != 0 && second != 0) {
+      const int new_start = std::max<int>((int)first - (args.window_size - 1), 0);
+      second += first - new_start; first = new_start;
+    }
+    *begin = (int32_t)first; *length = (int32_t)second;
+    return 0;
+  } catch (...) { return -1; }
+}
 
 int ref_to_decibels(const float *in, int64_t n, float *out, float multiplier, float reference, float cutoff_db, int ref_max) {
   try {

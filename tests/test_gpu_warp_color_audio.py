@@ -88,11 +88,11 @@ def test_warp_tensor_map_tma_path():
         assert path == 0
         for im, M, o in zip(imgs, mats, got):
             assert np.array_equal(o, po.warp_affine(im, M, out_hw, 0, None, np.uint8))
-    # rows that are not a multiple of 16 bytes cannot be described by a tensor map: band kernel without the TMA boxes
+    # rows that are not a multiple of 16 bytes cannot be described by a tensor map: generic kernel
     imgs = [rng.integers(0, 256, (64, 301, 3)).astype(np.uint8) for _ in range(2)]
     mats = [np.float32([[1, 0.02, 0.5], [-0.02, 1, 0.25]])] * 2
     got, path = g.warp_affine(imgs, mats, None, 1, None, np.uint8, contiguous=True, want_path=True)
-    assert path == 2
+    assert path == 0
     for im, M, o in zip(imgs, mats, got):
         assert np.array_equal(o, po.warp_affine(im, M, None, 1, None, np.uint8))
 
@@ -290,3 +290,43 @@ def test_normalize_axes_ddof_epsilon():
         assert np.allclose(b[i], (x64 - m) / np.sqrt(v + 1e-3), rtol=1e-5, atol=1e-5), i
         m, sd = x64.mean(0, keepdims=True), x64.std(0, keepdims=True)
         assert np.allclose(c[i], 2.0 * (x64 - m) / sd + 0.5, rtol=1e-5, atol=1e-5), i
+
+
+@pytest.mark.skipif(not po.have_ref(), reason="needs oracle/_ref")
+def test_nonsilent_region_matches_reference():
+    """fn.nonsilent_region: the moving mean square is a running float sum restarted every `reset_interval` samples -- replayed as the
+    same serial recurrence per interval (bit-exact), so (begin, length) equal the reference's for every sample, including all-silent
+    clips, clips shorter than the window, a fixed reference power and per-sample cut-offs."""
+    from dali_b200 import fn, pipeline_def
+    rng = np.random.default_rng(12)
+    clips = []
+    for n, lead, trail in ((40000, 6000, 9000), (16000, 0, 3000), (30000, 12345, 0), (5000, 0, 0), (1000, 300, 200), (20000, 0, 0)):
+        x = (0.4 * np.sin(np.arange(n) * 0.05) + 0.05 * rng.normal(0, 1, n)).astype(np.float32)
+        x[:lead] = (1e-5 * rng.normal(0, 1, lead)).astype(np.float32)
+        if trail:
+            x[n - trail:] = (1e-5 * rng.normal(0, 1, trail)).astype(np.float32)
+        clips.append(x)
+    clips[3][:] = 0.0                                                   # rest is silence
+    cut = [np.float32(v) for v in (-60, -40, -50, -60, -30, -80)]
+    n = len(clips)
+
+    @pipeline_def(batch_size=n, num_threads=1, device_id=0)
+    def pipe():
+        x = fn.external_source(source=lambda i: clips, device="gpu")
+        c = fn.external_source(source=lambda i: cut)
+        b0, l0 = fn.nonsilent_region(x)
+        b1, l1 = fn.nonsilent_region(x, cutoff_db=c, window_length=512, reset_interval=2048)
+        b2, l2 = fn.nonsilent_region(x, cutoff_db=-45.0, window_length=3000, reference_power=0.02, reset_interval=-1)
+        return b0, l0, b1, l1, b2, l2
+    p = pipe()
+    p.build()
+    outs = [o.as_cpu() for o in p.run()]
+    for i, x in enumerate(clips):
+        got = [(int(np.asarray(outs[2 * k][i]).reshape(-1)[0]), int(np.asarray(outs[2 * k + 1][i]).reshape(-1)[0])) for k in range(3)]
+        want = [po.ref_nonsilent_region(x), po.ref_nonsilent_region(x, float(cut[i]), 512, None, 2048),
+                po.ref_nonsilent_region(x, -45.0, 3000, 0.02, -1)]
+        for k in range(3):
+            if want[k][1] == 0:
+                assert got[k][1] == 0, (i, k, got[k], want[k])           # begin is undefined for an all-silent clip
+            else:
+                assert got[k] == want[k], (i, k, got[k], want[k])

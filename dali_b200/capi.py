@@ -35,7 +35,7 @@ EXPORTS = [
     "dalib200SpectrogramPlanCreate", "dalib200SpectrogramPlanDestroy", "dalib200SpectrogramPlanSetup",
     "dalib200SpectrogramNumWindows", "dalib200SpectrogramLaunch", "dalib200HannWindow",
     "dalib200SignalPlanCreate", "dalib200SignalPlanDestroy", "dalib200ToDecibelsSetup", "dalib200MfccSetup", "dalib200SignalOutputRows",
-    "dalib200NormalizeSetup", "dalib200SignalLaunch", "dalib200NonsilentSetup", "dalib200NonsilentLaunch",
+    "dalib200NormalizeSetup", "dalib200SignalLaunch", "dalib200NonsilentSetup", "dalib200NonsilentLaunch", "dalib200AudioResampleSetup",
     "dalib200GenericPlanCreate", "dalib200GenericPlanDestroy", "dalib200MultiplyAddSetup", "dalib200WindowCopySetup", "dalib200GenericLaunch",
     "dalib200MelPlanCreate", "dalib200MelPlanDestroy", "dalib200MelPlanSetup", "dalib200MelLaunch", "dalib200MelPlanSetTensorCores",
     "dalib200SpectrogramMelSupported", "dalib200SpectrogramMelLaunch",

@@ -16,6 +16,12 @@
 //                default; first / last sample at or above it; the start is moved back by window_length - 1.  The running sum
 //                is a serial float recurrence: one thread replays one reset interval (bit-exact), intervals and samples in
 //                parallel; the reductions behind it are exact (max / min / max index).
+//   AudioResample  dali/kernels/signal/resampling_cpu.cc:120-165 (single channel: the SSE2 path, four partial sums over taps
+//                i0 + l + 4k, combined as (f0 + f2) + (f1 + f3), then the scalar tail) and :186-230 (multi-channel: scalar, taps in
+//                order), window = Hann-windowed sinc looked up with linear interpolation (resampling.h:36-92, built on the host with
+//                the same float / double expressions).  The source position is accumulated in float inside blocks of 256 outputs
+//                (in_pos += fscale): a serial recurrence, replayed by one thread per block into shared memory; everything else is
+//                one thread per output sample with the reference's operation order -> bit-exact.
 // Every op is one launch per batch over a per-sample descriptor list (one H2D descriptor copy per launch).
 #include "common.cuh"
 #include <algorithm>
@@ -24,7 +30,7 @@
 
 namespace dalib200 {
 
-enum { SIG_NONE = 0, SIG_TODB = 1, SIG_MFCC = 2, SIG_NORMALIZE = 3, SIG_NONSILENT = 4 };
+enum { SIG_NONE = 0, SIG_TODB = 1, SIG_MFCC = 2, SIG_NORMALIZE = 3, SIG_NONSILENT = 4, SIG_RESAMPLE = 5 };
 
 struct SigDesc {
   const float *in; float *out;
@@ -37,6 +43,100 @@ __device__ __forceinline__ int find_sig(const SigDesc *d, int n, int64_t v) {
   int lo = 0, hi = n - 1;
   while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (d[mid].first_item <= v) lo = mid; else hi = mid - 1; }
   return lo;
+}
+
+// ---- AudioResample
+struct ArDesc {
+  const float *in; float *out;
+  int64_t n_in, n_out, first_item;      // items = groups of 4 blocks of 256 outputs
+  double scale;                         // in_rate / out_rate
+  int32_t channels;
+};
+struct ArWindow { float scale, center; int lobes; const float *lookup; };
+
+__device__ __forceinline__ float ar_window(const ArWindow &w, float x) {           // resampling.h:59-66 / resampling_cpu.cc:86-99
+  const float fi = add_rn(mul_rn(x, w.scale), w.center);
+  const float fl = floorf(fi);
+  const float di = sub_rn(fi, fl);
+  const int i = (int)fl;
+  const float c = __ldg(w.lookup + i), nx = __ldg(w.lookup + i + 1);
+  return add_rn(c, mul_rn(di, sub_rn(nx, c)));
+}
+
+constexpr int kArBlock = 256, kArBlocksPerCta = 4;
+
+__global__ void __launch_bounds__(256) audio_resample_kernel(const ArDesc *__restrict__ descs, int n, int64_t total_items, ArWindow win) {
+  __shared__ float s_pos[kArBlocksPerCta][kArBlock];
+  __shared__ long long s_blk[kArBlocksPerCta];
+  for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (descs[mid].first_item <= item) lo = mid; else hi = mid - 1; }
+    const ArDesc &d = descs[lo];
+    const int64_t out0 = (item - d.first_item) * (kArBlock * kArBlocksPerCta);
+    const float fscale = (float)d.scale;
+    // ---- the float source position of every output of the group: one thread replays one block of 256 (resampling_cpu.cc:131-136)
+    if (threadIdx.x < kArBlocksPerCta) {
+      const int64_t ob = out0 + (int64_t)threadIdx.x * kArBlock;
+      if (ob < d.n_out) {
+        const double in_block_f = (double)ob * d.scale;
+        const long long in_block_i = (long long)floor(in_block_f);
+        float in_pos = (float)(in_block_f - (double)in_block_i);
+        s_blk[threadIdx.x] = in_block_i;
+        const int cnt = (int)min((int64_t)kArBlock, d.n_out - ob);
+        for (int j = 0; j < cnt; j++) { s_pos[threadIdx.x][j] = in_pos; in_pos = add_rn(in_pos, fscale); }
+      }
+    }
+    __syncthreads();
+    for (int b = 0; b < kArBlocksPerCta; b++) {
+      const int64_t op = out0 + (int64_t)b * kArBlock + threadIdx.x;
+      if (op >= d.n_out) continue;
+      const float in_pos = s_pos[b][threadIdx.x];
+      const long long in_block_i = s_blk[b];
+      const int xc = (int)ceilf(in_pos);
+      int i0 = xc - win.lobes, i1 = xc + win.lobes;
+      if (i0 + in_block_i < 0) i0 = (int)(-in_block_i);
+      if (i1 + in_block_i > d.n_in) i1 = (int)(d.n_in - in_block_i);
+      if (d.channels == 1) {
+        const float *__restrict__ inb = d.in + in_block_i;
+        int i = i0;
+        float f4[4] = {0.f, 0.f, 0.f, 0.f}, x4[4];
+#pragma unroll
+        for (int l = 0; l < 4; l++) x4[l] = sub_rn((float)(i + l), in_pos);
+        for (; i + 3 < i1; i += 4) {
+#pragma unroll
+          for (int l = 0; l < 4; l++) {
+            // evaluate(): truncation instead of floor (cvttps) -- the argument is positive inside the window
+            const float fi = add_rn(mul_rn(x4[l], win.scale), win.center);
+            const int idx = (int)fi;
+            const float di = sub_rn(fi, (float)idx);
+            const float c = __ldg(win.lookup + idx), nx = __ldg(win.lookup + idx + 1);
+            const float w = add_rn(c, mul_rn(di, sub_rn(nx, c)));
+            f4[l] = add_rn(f4[l], mul_rn(__ldg(inb + i + l), w));
+            x4[l] = add_rn(x4[l], 4.0f);
+          }
+        }
+        float f = add_rn(add_rn(f4[0], f4[2]), add_rn(f4[1], f4[3]));
+        float x = sub_rn((float)i, in_pos);
+        for (; i < i1; i++, x = add_rn(x, 1.0f)) f = add_rn(f, mul_rn(__ldg(inb + i), ar_window(win, x)));
+        d.out[op] = f;
+      } else {
+        const int C = d.channels;
+        const float *__restrict__ inb = d.in + in_block_i * C;
+        float tmp[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) tmp[c] = 0.f;
+        float x = sub_rn((float)i0, in_pos);
+        for (int i = i0; i < i1; i++, x = add_rn(x, 1.0f)) {
+          const float w = ar_window(win, x);
+#pragma unroll
+          for (int c = 0; c < 8; c++) if (c < C) tmp[c] = add_rn(tmp[c], mul_rn(__ldg(inb + (int64_t)i * C + c), w));
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) if (c < C) d.out[op * C + c] = tmp[c];
+      }
+    }
+    __syncthreads();
+  }
 }
 
 // ---- NonsilentRegion
@@ -234,6 +334,10 @@ struct dalib200SignalPlan {
   bool table_dirty = true;
   // Normalize
   int mode = 0, ddof = 0; float scale = 1, shift = 0, eps = 0;
+  // AudioResample
+  std::vector<ArDesc> ar;
+  std::vector<float> ar_lookup; float *d_lookup = nullptr; size_t d_lookup_cap = 0; bool lookup_dirty = true;
+  float ar_scale = 1, ar_center = 1; int ar_lobes = 0; float ar_quality = -1;
   // NonsilentRegion
   std::vector<NsDesc> ns;
   float *d_mms = nullptr; size_t d_mms_cap = 0;
@@ -311,6 +415,7 @@ int dalib200SignalPlanDestroy(dalib200SignalPlan *p) {
   if (p->d_max) cudaFree(p->d_max);
   if (p->d_table) cudaFree(p->d_table);
   if (p->d_mms) cudaFree(p->d_mms);
+  if (p->d_lookup) cudaFree(p->d_lookup);
   delete p;
   return DALIB200_SUCCESS;
 }
@@ -387,6 +492,52 @@ int dalib200NormalizeSetup(dalib200SignalPlan *p, const dalib200NormalizeArgs *a
   return DALIB200_SUCCESS;
 }
 
+int dalib200AudioResampleSetup(dalib200SignalPlan *p, int n, const dalib200AudioResampleSample *samples, float quality) {
+  DB_CHECK_ARG(p && n >= 0 && n <= p->max_batch && (n == 0 || samples), "AudioResampleSetup: bad arguments");
+  DB_CHECK_ARG(quality >= 0 && quality <= 100, "``quality`` out of range: %g\nValid range is [0..100].", (double)quality);
+  p->kind = SIG_RESAMPLE; p->n = n;
+  if (quality != p->ar_quality) {
+    // ResamplingParams::FromQuality (resampling_params.h:27-30) + windowed_sinc (resampling.h:73-96), same float / double expressions
+    const double q = quality;
+    const int lobes = (int)std::round(0.007 * q * q - 0.09 * q + 3);
+    const int coeffs = lobes * 64 + 1;
+    const float scale = 2.0f * lobes / (coeffs - 1);
+    const float scale_envelope = 2.0f / coeffs;
+    const int center = (int)((coeffs - 1) * 0.5f);
+    p->ar_lookup.assign((size_t)coeffs + 5, 0.0f);
+    for (int i = 0; i < coeffs; i++) {
+      const float x = (i - center) * scale;
+      const float y = (i - center) * scale_envelope;
+      float sx = x; sx *= M_PI;                                                   // math_util.h:188-193 (float overload)
+      const float sinc = std::abs(sx) < 1e-5f ? 1.0f - sx * sx * (1.0f / 6) : std::sin(sx) / sx;
+      const double hann = 0.5 * (1 + std::cos((double)y * M_PI));
+      const float w = sinc * hann;
+      p->ar_lookup[i + 1] = w;
+    }
+    p->ar_center = (float)(center + 1);
+    p->ar_scale = 1 / scale;
+    p->ar_lobes = lobes;
+    p->ar_quality = quality;
+    p->lookup_dirty = true;
+  }
+  p->ar.assign(n, ArDesc());
+  int64_t items = 0;
+  for (int i = 0; i < n; i++) {
+    const auto &s = samples[i];
+    DB_CHECK_ARG(s.in_rate > 0 && s.out_rate > 0, "AudioResample: sample %d: sampling rates must be positive", i);
+    DB_CHECK_ARG(s.in_length >= 0 && s.out_length >= 0 && s.channels >= 1 && s.channels <= 8, "AudioResample: sample %d: unsupported shape", i);
+    DB_CHECK_ARG(s.in_length < (1ll << 31) && s.out_length < (1ll << 31), "AudioResample: sample %d is too long", i);
+    ArDesc &d = p->ar[i];
+    memset(&d, 0, sizeof(d));
+    d.n_in = s.in_length; d.n_out = s.out_length; d.channels = s.channels;
+    d.scale = s.in_rate / s.out_rate;
+    d.first_item = items;
+    items += (d.n_out + kArBlock * kArBlocksPerCta - 1) / (kArBlock * kArBlocksPerCta);
+  }
+  p->total_items = items;
+  return DALIB200_SUCCESS;
+}
+
 int dalib200NonsilentSetup(dalib200SignalPlan *p, int n, const int64_t *lengths, const dalib200NonsilentSample *args, int window_length,
                            int reset_interval) {
   DB_CHECK_ARG(p && n >= 0 && n <= p->max_batch && (n == 0 || (lengths && args)), "NonsilentSetup: bad arguments");
@@ -446,9 +597,34 @@ int dalib200NonsilentLaunch(dalib200SignalPlan *p, const void *const *in_ptrs, v
   return DALIB200_SUCCESS;
 }
 
+static int AudioResampleLaunch(dalib200SignalPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+  int rc = GrowF(p->d_lookup, p->d_lookup_cap, p->ar_lookup.size());
+  if (rc) return rc;
+  if (p->lookup_dirty) {
+    DB_CUDA(cudaMemcpyAsync(p->d_lookup, p->ar_lookup.data(), p->ar_lookup.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    p->lookup_dirty = false;
+  }
+  if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
+  if ((rc = p->arena.Reserve(sizeof(ArDesc) * p->n))) return rc;
+  ArDesc *h = reinterpret_cast<ArDesc *>(p->arena.host);
+  for (int i = 0; i < p->n; i++) { h[i] = p->ar[i]; h[i].in = static_cast<const float *>(in_ptrs[i]); h[i].out = static_cast<float *>(out_ptrs[i]); }
+  if ((rc = p->arena.Upload(sizeof(ArDesc) * p->n, stream))) return rc;
+  DB_CUDA(cudaEventRecord(p->uploaded, stream));
+  p->pending = true;
+  ArWindow w{ p->ar_scale, p->ar_center, p->ar_lobes, p->d_lookup };
+  const int grid = (int)std::min<int64_t>(p->total_items, (int64_t)NumSMs() * 8);
+  ProfScope ps_("audio_resample", stream);
+  audio_resample_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const ArDesc *>(p->arena.dev), p->n, p->total_items, w);
+  CountLaunch();
+  DB_CUDA(cudaGetLastError());
+  return DALIB200_SUCCESS;
+}
+
 int dalib200SignalLaunch(dalib200SignalPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
-  DB_CHECK_ARG(p && p->kind != SIG_NONE && (p->n == 0 || (in_ptrs && out_ptrs)), "SignalLaunch: call a ...Setup function first");
+  DB_CHECK_ARG(p && p->kind != SIG_NONE && p->kind != SIG_NONSILENT && (p->n == 0 || (in_ptrs && out_ptrs)),
+               "SignalLaunch: call a ...Setup function first (NonsilentRegion has its own launch)");
   if (p->n == 0 || p->total_items == 0) return DALIB200_SUCCESS;
+  if (p->kind == SIG_RESAMPLE) return AudioResampleLaunch(p, in_ptrs, out_ptrs, stream);
   int rc = UploadDescs(p);
   if (rc) return rc;
   SigDesc *h = reinterpret_cast<SigDesc *>(p->arena.host);

@@ -1924,6 +1924,76 @@ class SignalOpBase : public Operator<GPUBackend> {
   const char *name_;
 };
 
+// dali/operators/audio/resample.{h,cc}: windowed-sinc resampling of [time] or [time, channels] float signals
+DALI_SCHEMA(AudioResample)
+    .DocStr("Resamples an audio signal (windowed sinc).")
+    .NumInput(1).NumOutput(1)
+    .AddOptionalArgNoDefault("in_rate", "Input sampling rate.", true)
+    .AddOptionalArgNoDefault("out_rate", "Output sampling rate.", true)
+    .AddOptionalArgNoDefault("scale", "The scaling factor (out_rate / in_rate).", true)
+    .AddOptionalArgNoDefault("out_length", "The requested output length, in samples.", true)
+    .AddOptionalArg("quality", "Resampling quality, 0 (lowest) .. 100 (highest); 50 = 16 lobes of the sinc.", 50.0f)
+    .AddOptionalArgNoDefault("dtype", "Output type; the GPU path supports FLOAT.");
+
+class AudioResampleGPU : public SignalOpBase {
+ public:
+  explicit AudioResampleGPU(const OpSpec &spec) : SignalOpBase(spec, "AudioResample") {
+    has_rates_ = spec.ArgumentDefined("in_rate");
+    DALI_ENFORCE(has_rates_ == spec.ArgumentDefined("out_rate"), "The parameters ``in_rate`` and ``out_rate`` must be specified together.");
+    has_scale_ = spec.ArgumentDefined("scale"); has_len_ = spec.ArgumentDefined("out_length");
+    DALI_ENFORCE(static_cast<int>(has_rates_) + has_scale_ + has_len_ <= 1, "The sampling rates, ``scale`` and ``out_length`` cannot be used together.");
+    DALI_ENFORCE(has_rates_ || has_scale_ || has_len_, "No resampling factor specified! Please supply either the scale, the output length or "
+                 "the input and output sampling rates.");
+    quality_ = spec.GetArgument<float>("quality");
+    DALI_ENFORCE(quality_ >= 0 && quality_ <= 100, "``quality`` out of range: ", quality_, "\nValid range is [0..100].");
+    if (spec.ArgumentDefined("dtype"))
+      DALI_ENFORCE(spec.GetArgument<int>("dtype") == DALI_FLOAT, "AudioResample: the GPU path produces FLOAT output only");
+  }
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_FLOAT, "AudioResample: the GPU path supports float input; got type ", static_cast<int>(in.type()));
+    const int nd = in.shape().sample_dim();
+    DALI_ENFORCE(nd == 1 || nd == 2, "Audio resampling supports only time series data, with an optional innermost channel dimension.");
+    const int n = in.num_samples();
+    std::vector<dalib200AudioResampleSample> s(n);
+    out.resize(1);
+    out[0].type = DALI_FLOAT;
+    out[0].shape.resize(n, nd);
+    for (int i = 0; i < n; i++) {
+      const int64_t *sh = in.shape().tensor_shape_span(i);
+      const int64_t in_len = sh[0];
+      s[i].channels = nd == 2 ? static_cast<int>(sh[1]) : 1;
+      s[i].in_length = in_len;
+      if (has_rates_) {                                   // resample.h:73-101
+        const double ir = spec_.GetArgument<float>("in_rate", &ws, i), orate = spec_.GetArgument<float>("out_rate", &ws, i);
+        DALI_ENFORCE(ir > 0, "Input sampling rates must be positive. Got in_rate == ", ir);
+        DALI_ENFORCE(orate > 0, "Output sampling rates must be positive on the GPU path. Got out_rate == ", orate);
+        s[i].in_rate = ir; s[i].out_rate = orate;
+        s[i].out_length = static_cast<int64_t>(std::ceil(in_len * orate / ir));
+      } else if (has_scale_) {
+        const double sc = spec_.GetArgument<float>("scale", &ws, i);
+        DALI_ENFORCE(sc > 0, "The scaling factor must be positive on the GPU path. Got scale == ", sc);
+        s[i].in_rate = 1.0; s[i].out_rate = sc;
+        s[i].out_length = static_cast<int64_t>(std::ceil(in_len * sc / 1));
+      } else {
+        const int64_t ol = spec_.GetArgument<int64_t>("out_length", &ws, i);
+        DALI_ENFORCE(!(in_len == 0 && ol != 0), "Cannot produce a non-empty signal from an empty input.\nError at sample ", i);
+        s[i].in_rate = in_len ? static_cast<double>(in_len) : 1.0;
+        s[i].out_rate = ol ? static_cast<double>(ol) : 1.0;
+        s[i].out_length = ol;
+      }
+      if (nd == 2) out[0].shape.set_tensor_shape(i, { s[i].out_length, sh[1] });
+      else out[0].shape.set_tensor_shape(i, { s[i].out_length });
+    }
+    CheckStatus(dalib200AudioResampleSetup(plan_, n, s.data(), quality_), name_);
+    return true;
+  }
+  bool has_rates_ = false, has_scale_ = false, has_len_ = false;
+  float quality_ = 50;
+};
+DALI_REGISTER_OPERATOR(AudioResample, AudioResampleGPU, GPU);
+
 // dali/operators/audio/nonsilence_op.{h,cc}: leading / trailing silence detection; outputs (begin, length) as int32 scalars
 DALI_SCHEMA(NonsilentRegion)
     .DocStr("Performs leading and trailing silence detection in an audio buffer.")

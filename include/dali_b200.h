@@ -324,6 +324,17 @@ int dalib200NormalizeSetup(dalib200SignalPlan *plan, const dalib200NormalizeArgs
 /* in_ptrs[i] / out_ptrs[i]: device f32 */
 int dalib200SignalLaunch(dalib200SignalPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
 
+/* AudioResample (dali/operators/audio/resample.{h,cc}, kernel dali/kernels/signal/resampling_cpu.cc): float in, float out, 1..8
+ * interleaved channels; in_rate / out_rate as the operator derives them (scale: 1 / scale; out_length: in_length / out_length);
+ * out_length = resampled_length() = ceil(in_length * out_rate / in_rate) unless given.  quality 0..100 selects the windowed-sinc
+ * width (resampling_params.h).  Launched with dalib200SignalLaunch. */
+typedef struct {
+  double in_rate, out_rate;
+  int64_t in_length, out_length;
+  int32_t channels;
+} dalib200AudioResampleSample;
+int dalib200AudioResampleSetup(dalib200SignalPlan *plan, int n, const dalib200AudioResampleSample *samples, float quality);
+
 /* NonsilentRegion (dali/operators/audio/nonsilence_op.{h,cc}; moving mean square: dali/kernels/signal/moving_mean_square.cc):
  * float input, two int32 scalars per sample (begin, length).  use_reference_power == 0: the reference is the maximum of the
  * moving mean square (the operator's default).  reset_interval: -1 or a multiple of window_length (float inputs: 8192). */

@@ -429,6 +429,19 @@ def ref_to_decibels(x, multiplier=10.0, reference=None, cutoff_db=-200.0):
     return out
 
 
+def ref_audio_resample(x, in_rate, out_rate, quality=50.0, out_length=None):
+    """dali/kernels/signal/resampling_cpu.cc through ResamplerCPU (compiled reference); x: [n] or [n, channels] float32."""
+    a = np.ascontiguousarray(x, np.float32)
+    n_in, ch = a.shape[0], (a.shape[1] if a.ndim == 2 else 1)
+    lib = ref()
+    lib.ref_resampled_length.restype = C.c_int64
+    n_out = int(out_length) if out_length is not None else int(lib.ref_resampled_length(C.c_int64(n_in), C.c_double(in_rate), C.c_double(out_rate)))
+    out = np.empty((n_out,) + a.shape[1:], np.float32)
+    rc = lib.ref_audio_resample(_p(a), C.c_int64(n_in), ch, C.c_double(in_rate), C.c_double(out_rate), C.c_int64(n_out), C.c_float(quality), _p(out))
+    assert rc == 0
+    return out
+
+
 def ref_nonsilent_region(x, cutoff_db=-60.0, window_length=2048, reference_power=None, reset_interval=8192):
     """dali/operators/audio/nonsilence_op.h over the compiled reference kernels (moving mean square, dB -> magnitude): (begin, length)."""
     a = np.ascontiguousarray(x, np.float32)

@@ -67,6 +67,9 @@ int ref_mel_filter_bank_ft(const float *in, int nbin, int64_t nwin, float *out, 
 #include "dali/operators/audio/mfcc/mfcc.h"                 // LifterCoeffs::CalculateCoeffs (private; built with -fno-access-control)
 
 #include "dali/kernels/signal/moving_mean_square.cc"       // NOLINT
+#include "dali/kernels/signal/resampling_cpu.h"
+#include "dali/kernels/signal/resampling_cpu.cc"            // NOLINT
+#include "dali/operators/audio/resampling_params.h"
 #include "dali/kernels/signal/decibel/decibel_calculator.h"
 
 extern "C" {
@@ -103,6 +106,21 @@ int ref_nonsilent_region(const float *in, int64_t n, float cutoff_db, float refe
     *begin = (int32_t)first; *length = (int32_t)second;
     return 0;
   } catch (...) { return -1; }
+}
+
+// AudioResample, float -> float: ResamplerCPU (windowed sinc from ResamplingParams::FromQuality) over [n_in][channels]
+int ref_audio_resample(const float *in, int64_t n_in, int channels, double in_rate, double out_rate, int64_t n_out, float quality, float *out) {
+  try {
+    auto params = dali::audio::ResamplingParams::FromQuality(quality);
+    signal::resampling::ResamplerCPU R;
+    R.Initialize(params.lobes, params.lookup_size);
+    R.Resample(out, 0, n_out, out_rate, in, n_in, in_rate, channels);
+    return 0;
+  } catch (...) { return -1; }
+}
+
+int64_t ref_resampled_length(int64_t in_length, double in_rate, double out_rate) {
+  return signal::resampling::resampled_length(in_length, in_rate, out_rate);
 }
 
 int ref_to_decibels(const float *in, int64_t n, float *out, float multiplier, float reference, float cutoff_db, int ref_max) {

@@ -330,3 +330,39 @@ def test_nonsilent_region_matches_reference():
                 assert got[k][1] == 0, (i, k, got[k], want[k])           # begin is undefined for an all-silent clip
             else:
                 assert got[k] == want[k], (i, k, got[k], want[k])
+
+
+@pytest.mark.skipif(not po.have_ref(), reason="needs oracle/_ref")
+def test_audio_resample_matches_reference():
+    """fn.audio_resample: windowed-sinc resampling with the reference's operation order (four partial sums + scalar tail for one
+    channel, in-order taps for several; float source position accumulated per block of 256 outputs) -> bit-exact against the
+    compiled reference kernel for up- and down-sampling, `scale`, `out_length`, several qualities, mono and interleaved stereo."""
+    from dali_b200 import fn, pipeline_def
+    rng = np.random.default_rng(13)
+    mono = [_clip(rng, n) for n in (16000, 4001, 700, 25000)]
+    stereo = [np.stack([_clip(rng, n), _clip(rng, n)], axis=1) for n in (3000, 9000, 512, 12345)]
+    n = len(mono)
+    in_r = [np.float32(v) for v in (16000, 44100, 8000, 22050)]
+    out_r = [np.float32(v) for v in (44100, 16000, 16000, 8000)]
+    lens = [np.int64(v) for v in (12000, 1234, 3000, 5)]
+
+    @pipeline_def(batch_size=n, num_threads=1, device_id=0)
+    def pipe():
+        x = fn.external_source(source=lambda i: mono, device="gpu")
+        s = fn.external_source(source=lambda i: stereo, device="gpu")
+        ir = fn.external_source(source=lambda i: in_r)
+        orr = fn.external_source(source=lambda i: out_r)
+        ol = fn.external_source(source=lambda i: lens)
+        return (fn.audio_resample(x, in_rate=ir, out_rate=orr), fn.audio_resample(x, scale=0.37, quality=90.0),
+                fn.audio_resample(x, out_length=ol, quality=10.0), fn.audio_resample(s, in_rate=ir, out_rate=orr),
+                fn.audio_resample(s, scale=2.5, quality=0.0))
+    p = pipe()
+    p.build()
+    a, b, c, d, e = [o.as_cpu() for o in p.run()]
+    for i in range(n):
+        assert np.array_equal(bits(a[i]), bits(po.ref_audio_resample(mono[i], float(in_r[i]), float(out_r[i])))), i
+        assert np.array_equal(bits(b[i]), bits(po.ref_audio_resample(mono[i], 1.0, float(np.float32(0.37)), 90.0))), i
+        L = int(lens[i])
+        assert np.array_equal(bits(c[i]), bits(po.ref_audio_resample(mono[i], float(mono[i].shape[0]), float(L), 10.0, out_length=L))), i
+        assert np.array_equal(bits(d[i]), bits(po.ref_audio_resample(stereo[i], float(in_r[i]), float(out_r[i])))), i
+        assert np.array_equal(bits(e[i]), bits(po.ref_audio_resample(stereo[i], 1.0, 2.5, 0.0))), i

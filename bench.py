@@ -82,12 +82,53 @@ def make_batch(n, seed0, threads):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  NVML in-process (a sample every ~2 ms: the
+    timed region of the default run is only ~70 ms, shorter than the start-up of an `nvidia-smi -lms` child); nvidia-smi as fallback."""
+    HW_SLOWDOWN, SW_THERMAL, HW_THERMAL, SW_POWER_CAP = 0x8, 0x20, 0x40, 0x4
 
     def __init__(self, index):
-        self.lines, self.proc, self.index = [], None, index
+        self.index, self.samples, self.mx, self.reasons = index, [], None, set()
+        self.stop_flag, self.thr, self.nvml, self.handle, self.proc, self.lines = False, None, None, None, None, []
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.handle = pynvml, h
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n, h = self.nvml, self.handle
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+        try:
+            r = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        for bit, nm in ((self.HW_SLOWDOWN, "hw_slowdown"), (self.HW_THERMAL, "hw_thermal_slowdown"), (self.SW_THERMAL, "sw_thermal_slowdown"),
+                        (self.SW_POWER_CAP, "sw_power_cap")):
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.thr = threading.Thread(target=self._loop, daemon=True)
+            self.thr.start()
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -103,6 +144,12 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            if self.thr is not None:
+                self.thr.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(self.samples), "source": "nvml, sampled during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -123,7 +170,8 @@ class ClockSampler:
             for k, nm in enumerate(names):
                 if f[3 + k].lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 100"}
 
 
 _CPU_STREAMS = None      # set before the worker processes are forked: they inherit the encoded batch

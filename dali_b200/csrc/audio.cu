@@ -158,6 +158,51 @@ __global__ void __launch_bounds__(256) spectrogram_kernel(const SpecDesc *__rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// nfft NOT a power of two (the reference hands those to FFTS' complex transform, fft_cpu_impl_ffts.cc:38-86): a direct DFT from shared
+// memory -- O(nfft^2 / 2) per frame, meant for the occasional odd nfft (400, 600, 1000 ...), not for the hot configurations.  One thread
+// = one (frame, bin); the twiddle e^(-2 pi i k t / n) is read from a full-period table with an incrementally wrapped index (no
+// trigonometry in the loop), sums are accumulated in double so that the result stays inside the stated STFT tolerance for any nfft.
+__global__ void __launch_bounds__(256) spectrogram_dft_kernel(const SpecDesc *__restrict__ descs, int n, int64_t total_groups, SpecParams P,
+                                                              const float *__restrict__ window, const float2 *__restrict__ twiddle_full) {
+  extern __shared__ float2 dbuf[];
+  const int N = P.nfft, F = P.frames_per_cta;
+  float2 *tw = dbuf;                                   // [N] (cos, sin)(2 pi j / N)
+  float *fr = reinterpret_cast<float *>(dbuf + N);     // [F][N]
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = twiddle_full[i];
+  for (int64_t grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+    const int s = find_spec_sample(descs, n, grp);
+    const SpecDesc &d = descs[s];
+    const int64_t w0 = (grp - d.first_group) * F;
+    const int nf = (int)min((int64_t)F, d.nwin - w0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nf * N; e += blockDim.x) {
+      const int f = e / N, i = e - f * N;
+      const int t = i - P.in_win_start;
+      fr[f * N + i] = (t >= 0 && t < P.win_len) ? spec_sample(d, P, window, w0 + f, t) : 0.0f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nf * P.nbin; e += blockDim.x) {
+      int f, k;
+      if (P.layout_ft) { k = e / nf; f = e - k * nf; } else { f = e / P.nbin; k = e - f * P.nbin; }
+      const float *x = fr + f * N;
+      double re = 0.0, im = 0.0;
+      int idx = 0;
+      for (int t = 0; t < N; t++) {
+        const float2 w = tw[idx];
+        const double xv = (double)x[t];
+        re += xv * (double)w.x; im -= xv * (double)w.y;
+        idx += k; if (idx >= N) idx -= N;
+      }
+      const float fre = (float)re, fim = (float)im;
+      const float pw = fre * fre + fim * fim;
+      const float v = P.power == 2 ? pw : sqrtf(pw);
+      if (P.layout_ft) d.out[(int64_t)k * d.nwin + w0 + f] = v;
+      else d.out[(w0 + f) * (int64_t)P.nbin + k] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 struct MelDesc {
   const float *in;
   float *out;
@@ -594,8 +639,9 @@ int dalib200SpectrogramPlanSetup(dalib200SpectrogramPlan *p, const dalib200Spect
   DB_CHECK_ARG(a->power == 1 || a->power == 2, "Spectrogram: power must be 1 or 2, got %d", a->power);
   const int nfft = a->nfft > 0 ? a->nfft : a->window_length;
   DB_CHECK_ARG(nfft >= a->window_length, "Spectrogram: nfft (%d) must not be smaller than window_length (%d)", nfft, a->window_length);
-  if ((nfft & (nfft - 1)) != 0 || nfft > 8192 || nfft < 2) {
-    SetLastError("Spectrogram: nfft=%d -- the GPU path supports powers of two up to 8192", nfft);
+  const bool pow2 = (nfft & (nfft - 1)) == 0;
+  if (nfft < 2 || (pow2 && nfft > 8192) || (!pow2 && nfft > 4096)) {
+    SetLastError("Spectrogram: nfft=%d -- the GPU path supports powers of two up to 8192 and other sizes up to 4096", nfft);
     return DALIB200_ERROR_UNSUPPORTED;
   }
   SpecParams &P = p->P;
@@ -609,6 +655,10 @@ int dalib200SpectrogramPlanSetup(dalib200SpectrogramPlan *p, const dalib200Spect
   // two frames share one complex buffer: 16 frames (8 buffers of nfft + nfft/32 float2) per CTA at nfft = 1024 -> 3 CTAs / SM
   P.frames_per_cta = 2 * std::max(1, std::min(8, (64 * 1024) / (nfft * 8)));
   p->smem = (size_t)(P.frames_per_cta / 2) * (nfft + nfft / 32) * sizeof(float2) + (size_t)(nfft / 2) * sizeof(float2);
+  if (!pow2) {                       // direct DFT: full twiddle period + F windowed frames in shared memory
+    P.frames_per_cta = std::max(1, std::min(8, (int)((160 * 1024 - (size_t)nfft * 8) / ((size_t)nfft * 4))));
+    p->smem = (size_t)nfft * sizeof(float2) + (size_t)P.frames_per_cta * nfft * sizeof(float);
+  }
   std::vector<float> w(a->window_length);
   if (window_fn) memcpy(w.data(), window_fn, sizeof(float) * a->window_length);
   else dalib200HannWindow(w.data(), a->window_length);
@@ -642,12 +692,14 @@ static int SpectrogramLaunchImpl(dalib200SpectrogramPlan *p, const void *const *
   if (p->n == 0 || p->total_groups == 0) return DALIB200_SUCCESS;
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
   const SpecParams &P = p->P;
+  const bool pow2 = (P.nfft & (P.nfft - 1)) == 0;
   if (p->tw_nfft != P.nfft) {
     if (p->d_twiddle) cudaFree(p->d_twiddle);
     p->d_twiddle = nullptr;
-    DB_CUDA(cudaMalloc(reinterpret_cast<void **>(&p->d_twiddle), sizeof(float2) * (P.nfft / 2)));
-    std::vector<float2> tw(P.nfft / 2);
-    for (int k = 0; k < P.nfft / 2; k++) {
+    const int ntw = pow2 ? P.nfft / 2 : P.nfft;          // half period for the FFT kernels, the full one for the direct DFT
+    DB_CUDA(cudaMalloc(reinterpret_cast<void **>(&p->d_twiddle), sizeof(float2) * ntw));
+    std::vector<float2> tw(ntw);
+    for (int k = 0; k < ntw; k++) {
       const double ang = 2.0 * M_PI * k / P.nfft;
       tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     }
@@ -707,6 +759,16 @@ static int SpectrogramLaunchImpl(dalib200SpectrogramPlan *p, const void *const *
       spectrogram1024_kernel<false><<<grid, kF1024Warps * 32, kF1024Smem, stream>>>(reinterpret_cast<const SpecDesc *>(p->arena.dev), p->n,
           p->total_groups, P, p->d_window, p->d_twiddle, mt, nullptr, 1);
     }
+    CountLaunch();
+    DB_CUDA(cudaGetLastError());
+    return DALIB200_SUCCESS;
+  }
+  if (!pow2) {
+    DB_CUDA(cudaFuncSetAttribute(spectrogram_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(p->smem, 48 * 1024)));
+    const int gridd = (int)std::min<int64_t>(p->total_groups, (int64_t)NumSMs() * 4);
+    ProfScope ps_("spectrogram_dft", stream);
+    spectrogram_dft_kernel<<<gridd, 256, p->smem, stream>>>(reinterpret_cast<const SpecDesc *>(p->arena.dev), p->n, p->total_groups, P,
+                                                           p->d_window, p->d_twiddle);
     CountLaunch();
     DB_CUDA(cudaGetLastError());
     return DALIB200_SUCCESS;

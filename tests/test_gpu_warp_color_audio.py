@@ -197,7 +197,21 @@ def test_spectrogram_c4_shape_and_unsupported():
     (o,) = g.spectrogram([_clip(rng, 160000)], nfft=1024, window_length=1024, window_step=256)
     assert o.shape == (513, 626)
     with pytest.raises(capi.DaliB200Error, match="powers of two"):
-        g.spectrogram([_clip(rng, 4000)], nfft=400, window_length=400, window_step=160)
+        g.spectrogram([_clip(rng, 20000)], nfft=5000, window_length=5000, window_step=160)
+
+
+@pytest.mark.parametrize("cfg", [dict(nfft=400, window_length=400, window_step=160), dict(nfft=600, window_length=500, window_step=200, center=False),
+                                 dict(nfft=1000, window_length=1000, window_step=250, power=1, layout="tf", reflect=False)])
+def test_spectrogram_non_power_of_two_nfft(cfg):
+    """nfft that is not a power of two (the reference's FFTS complex path): direct DFT kernel, same stated tolerance."""
+    import gpu_helpers as g
+    rng = np.random.default_rng(64)
+    sigs = [_clip(rng, n) for n in (16000, 4000, 1003)]
+    got = g.spectrogram(sigs, **cfg)
+    for s, o in zip(sigs, got):
+        want = po.spectrogram(s, **cfg)
+        assert o.shape == want.shape
+        assert np.abs(o - want).max() <= 5e-6 * want.max()
 
 
 def test_mel_filter_bank_bit_exact():

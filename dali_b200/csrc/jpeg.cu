@@ -39,10 +39,17 @@ constexpr int kMaxLog2Sub = 10;              // largest subsequence: 2^10 bits =
 
 // Huffman tables as the device sees them.  The first-level LUTs (one 32-bit entry per 10-bit prefix, see make_entry) are
 // copied to shared memory by every sync block; the canonical tables for longer codes stay in global memory.
+constexpr int kLongLut = 512;
 struct HuffSlow {
   int32_t maxcode[18];        // T.81 F.2.2.3: maxcode[l] left-aligned to 16 bits (+1)
   int32_t valoff[18];         // valptr[l] - mincode[l]
   uint8_t vals[256];
+  // canonical codes grow with their length, so the codes longer than the first-level LUT occupy the top [long_base, 65536) of the
+  // left-aligned 16-bit code space -- 192 values for the standard tables.  When that range fits, ONE lookup indexed by
+  // (window - long_base) replaces the length search (which ran on a single lane while the warp waited: ~5 % of the warp-instructions
+  // of the Huffman kernels at quality 90).  Entry = code length | symbol << 8, 0 = not a code.  long_n == 0: use the search.
+  int32_t long_base, long_n;
+  uint16_t long_lut[kLongLut];
 };
 
 struct TableSet {             // the 4 tables a baseline scan can reference: DC0, DC1, AC0, AC1
@@ -373,6 +380,11 @@ __device__ __noinline__ uint32_t slow_lookup(const HuffSlow *__restrict__ slow, 
   const int tbl = toff < 2u * kDcLutSize ? (int)(toff / kDcLutSize) : 2 + (int)((toff - 2u * kDcLutSize) / kAcLutSize);
   const HuffSlow *sl = slow + tbl;
   const int32_t code16 = (int32_t)(hi >> 16);
+  if (sl->long_n > 0) {
+    const int idx = min(max(code16 - sl->long_base, 0), sl->long_n - 1);
+    const uint32_t e = sl->long_lut[idx];
+    return e ? e : 16u;                                      // corrupt / speculative: keep going deterministically (length 16, symbol 0)
+  }
   uint32_t len = (is_dc ? kDcLutBits : kAcLutBits) + 1;
   while (len <= 16 && code16 >= sl->maxcode[len]) len++;
   uint32_t sym = 0;
@@ -1298,11 +1310,17 @@ __device__ __forceinline__ void ycc_to_rgb_store8(const JpegImage &im, uint2 yw,
                        pack4_sat_u8(px[8 * q + 4], px[8 * q + 5], px[8 * q + 6], px[8 * q + 7]));
 }
 
-__device__ __forceinline__ void chroma_patch_420(const uint8_t *__restrict__ pl, int pw, int i0, int k, int *near_out, int *far_out) {
+// left / right: the patch touches the first / last chroma column -- libjpeg's edge rule (jdsample.c h2v2_fancy_upsample: the first
+// output is (4 * this + 8) >> 4, the last (4 * this + 7) >> 4) is the interior formula with the missing neighbour replaced by
+// the column itself, so the edge patches take this path too (they used to fall to the one-lane generic path, which cost a third
+// of the kernel at 1080p: two of every 240 threads of a row ran ~600 instructions alone).
+__device__ __forceinline__ void chroma_patch_420(const uint8_t *__restrict__ pl, int pw, int i0, int k, bool left, bool right,
+                                                 int *near_out, int *far_out) {
   const uint8_t *ra = pl + (int64_t)k * pw + i0, *rb = ra + pw;
   const uint32_t wa = *reinterpret_cast<const uint32_t *>(ra), wb = *reinterpret_cast<const uint32_t *>(rb);
   int a[6], b[6];
-  a[0] = ra[-1]; b[0] = rb[-1]; a[5] = ra[4]; b[5] = rb[4];
+  a[0] = left ? (int)(wa & 0xFFu) : (int)ra[-1]; b[0] = left ? (int)(wb & 0xFFu) : (int)rb[-1];
+  a[5] = right ? (int)(wa >> 24) : (int)ra[4]; b[5] = right ? (int)(wb >> 24) : (int)rb[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) { a[1 + j] = (int)((wa >> (8 * j)) & 0xFFu); b[1 + j] = (int)((wb >> (8 * j)) & 0xFFu); }
   int cn[6], cf[6];
@@ -1319,9 +1337,11 @@ __device__ __forceinline__ void chroma_patch_420(const uint8_t *__restrict__ pl,
 
 __device__ __forceinline__ void color_patch_420(const JpegImage &im, const uint8_t *__restrict__ planes, int x0, int y) {
   const int i0 = x0 >> 1, k = y >> 1;
+  const int dw = (im.width + 1) >> 1;
+  const bool left = i0 == 0, right = i0 + 4 == dw;
   int cb0[8], cb1[8], cr0[8], cr1[8];
-  chroma_patch_420(planes + im.plane_off[1], im.plane_w[1], i0, k, cb0, cb1);
-  chroma_patch_420(planes + im.plane_off[2], im.plane_w[2], i0, k, cr0, cr1);
+  chroma_patch_420(planes + im.plane_off[1], im.plane_w[1], i0, k, left, right, cb0, cb1);
+  chroma_patch_420(planes + im.plane_off[2], im.plane_w[2], i0, k, left, right, cr0, cr1);
   const uint8_t *yp = planes + im.plane_off[0] + (int64_t)y * im.plane_w[0] + x0;
   const uint2 y0 = *reinterpret_cast<const uint2 *>(yp), y1 = *reinterpret_cast<const uint2 *>(yp + im.plane_w[0]);
   ycc_to_rgb_store8(im, y0, cb0, cr0, x0, y);
@@ -1331,9 +1351,17 @@ __device__ __forceinline__ void color_patch_420(const JpegImage &im, const uint8
 // items: per image height * ceil(width / kColorSeg); images not eligible for the fast path own zero items
 __global__ void __launch_bounds__(128) color_fast_kernel(const JpegImage *__restrict__ images, const int64_t *__restrict__ first_item,
                                                          int nimages, int64_t total_items, const uint8_t *__restrict__ planes) {
-  for (int64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
-    int lo = 0, hi = nimages - 1;
-    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (first_item[mid] <= item) lo = mid; else hi = mid - 1; }
+  // every CTA owns a contiguous range of items: the image is searched once (by one thread) and then only advanced -- the per-item,
+  // per-thread binary search with its dependent global loads was a quarter of this kernel's stall samples
+  __shared__ int s_first;
+  const int64_t per_cta = (total_items + gridDim.x - 1) / gridDim.x;
+  const int64_t it0 = (int64_t)blockIdx.x * per_cta, it1 = min(total_items, it0 + per_cta);
+  if (it0 >= it1) return;
+  if (threadIdx.x == 0) s_first = find_by_prefix(first_item, nimages, it0);
+  __syncthreads();
+  int lo = s_first;
+  for (int64_t item = it0; item < it1; item++) {
+    while (lo + 1 < nimages && first_item[lo + 1] <= item) lo++;
     const JpegImage &im = images[lo];
     const int64_t li = item - first_item[lo];
     const int segs = (im.win_w + kColorSeg - 1) / kColorSeg;
@@ -1350,7 +1378,7 @@ __global__ void __launch_bounds__(128) color_fast_kernel(const JpegImage *__rest
       const bool in_a = ya >= im.win_y0 && ya < wy1, in_b = yb >= im.win_y0 && yb < wy1;
       const int dw = (im.width + 1) >> 1, dh = (im.height + 1) >> 1, i0 = x0 >> 1;
       const bool aligned = (reinterpret_cast<uintptr_t>(im.out) & 7) == 0 && (im.win_w & 7) == 0;
-      if (aligned && in_a && in_b && (ya >> 1) + 1 <= dh - 1 && i0 >= 1 && i0 + 4 <= dw - 1 && x0 + 8 <= wx1) {
+      if (aligned && in_a && in_b && (ya >> 1) + 1 <= dh - 1 && i0 + 4 <= dw && x0 + 8 <= wx1) {
         color_patch_420(im, planes, x0, ya);
       } else {
         if (in_a) color_row8<2, 2>(im, planes, x0, ya);
@@ -1619,6 +1647,24 @@ void BuildDeviceTable(const HostHuff &h, uint32_t *lut, uint16_t *lut16, HuffSlo
   }
   t.maxcode[17] = 0x7fffffff;
   memcpy(t.vals, h.vals, 256);
+  // direct table for the codes behind the first level (see HuffSlow)
+  t.long_base = t.maxcode[kLutBits];
+  const int range = 65536 - t.long_base;
+  t.long_n = 0;
+  if (range > 0 && range <= kLongLut) {
+    t.long_n = range;
+    int c2 = 0, k2 = 0;
+    for (int l = 1; l <= 16; l++) {
+      for (int i = 0; i < h.bits[l]; i++, k2++, c2++) {
+        if (l > kLutBits) {
+          const int lo = (c2 << (16 - l)) - t.long_base, cnt = 1 << (16 - l);
+          for (int e = 0; e < cnt; e++)
+            if (lo + e >= 0 && lo + e < range) t.long_lut[lo + e] = (uint16_t)(l | (h.vals[k2 & 255] << 8));
+        }
+      }
+      c2 <<= 1;
+    }
+  }
 }
 
 }  // namespace

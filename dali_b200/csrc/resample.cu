@@ -479,12 +479,15 @@ __global__ void __launch_bounds__(256) resample_fused_kernel(const RsDesc *__res
 // rows (so there is no vertical overlap between chunks: every source byte is loaded and converted once per strip), park each
 // finished output row in shared memory and, every 8 rows, run the horizontal pass from there.  The producer runs ahead
 // across chunk and item boundaries, so HBM latency is hidden by the ring, not by occupancy.
-constexpr int kStRowBytes = 2048;         // ring slot = one source row segment
-constexpr int kStStages = 16;
+constexpr int kStRowBytes = 2048;         // one source row segment
+constexpr int kStSlotRows = 2;            // ring slot = TWO consecutive source rows of a chunk: one mbarrier wait / proxy fence / arrive
+                                          // per two rows (the per-row synchronisation was ~20 % of the walk's stall samples)
+constexpr int kStStages = 8;
 constexpr int kStTH = 8;                  // output rows per chunk
 constexpr int kStConsumers = 256;
 constexpr int kStThreads = kStConsumers + 32;
-constexpr int kStSmemBytes = kStTH * kStRowBytes * 4 + kStStages * kStRowBytes + kWalkMax * kWalkSlots * 16 + kWalkMax * 4 +
+constexpr int kStSlotBytes = kStSlotRows * kStRowBytes;
+constexpr int kStSmemBytes = kStTH * kStRowBytes * 4 + kStStages * kStSlotBytes + kWalkMax * kWalkSlots * 16 + kWalkMax * 4 +
                              2 * kStStages * 8;
 
 struct RsItem { int32_t sample, ox0, tw, oy0, oy1; };
@@ -509,8 +512,8 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
   extern __shared__ __align__(128) uint8_t st_smem[];
   float *tmp2 = reinterpret_cast<float *>(st_smem);                               // [4 row pairs][RE][2]
   uint8_t *ring = st_smem + kStTH * kStRowBytes * 4;
-  float2 (*ent)[kWalkSlots] = reinterpret_cast<float2 (*)[kWalkSlots]>(ring + kStStages * kStRowBytes);   // (c, -2^23 c) per step, slot
-  uint32_t *fin = reinterpret_cast<uint32_t *>(ring + kStStages * kStRowBytes + kWalkMax * kWalkSlots * 16);
+  float2 (*ent)[kWalkSlots] = reinterpret_cast<float2 (*)[kWalkSlots]>(ring + kStStages * kStSlotBytes);   // (c, -2^23 c) per step, slot
+  uint32_t *fin = reinterpret_cast<uint32_t *>(ring + kStStages * kStSlotBytes + kWalkMax * kWalkSlots * 16);
   uint64_t *full = reinterpret_cast<uint64_t *>(fin + kWalkMax);
   uint64_t *empty = full + kStStages;
   const int tid = threadIdx.x;
@@ -532,13 +535,22 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
         const StripGeom g = strip_geom(d, idx_x, it.ox0, it.tw);
         const int64_t pitch = (int64_t)d.in_w * d.C;
         const uint8_t *src0 = static_cast<const uint8_t *>(d.in) + g.e0;
-        const int ustart = idx_y[it.oy0], uend = idx_y[it.oy1 - 1] + Sy - 1;
-        for (int u = ustart; u <= uend; u++) {
-          mbar_wait(&empty[stage], par);
-          mbar_expect_tx(&full[stage], (uint32_t)g.bytes);
-          const int row = by + min(max(u, 0), ey - 1);
-          bulk_g2s(ring + stage * kStRowBytes, src0 + row * pitch, (uint32_t)g.bytes, &full[stage]);
-          if (++stage == kStStages) { stage = 0; par ^= 1u; }
+        const int ustart = idx_y[it.oy0];
+        // the same chunking as the consumers: slots pair the rows of ONE chunk (a chunk with an odd row count ends with a half slot)
+        for (int cy0 = it.oy0; cy0 < it.oy1; cy0 += kStTH) {
+          const int th = min(kStTH, it.oy1 - cy0);
+          const int cs = cy0 == it.oy0 ? ustart : idx_y[cy0 - 1] + Sy;
+          const int J = idx_y[cy0 + th - 1] + Sy - cs;
+          for (int j = 0; j < J; j += kStSlotRows) {
+            const int nr = min(kStSlotRows, J - j);
+            mbar_wait(&empty[stage], par);
+            mbar_expect_tx(&full[stage], (uint32_t)(g.bytes * nr));
+            for (int q = 0; q < nr; q++) {
+              const int row = by + min(max(cs + j + q, 0), ey - 1);
+              bulk_g2s(ring + stage * kStSlotBytes + q * kStRowBytes, src0 + row * pitch, (uint32_t)g.bytes, &full[stage]);
+            }
+            if (++stage == kStStages) { stage = 0; par ^= 1u; }
+          }
         }
       }
     }
@@ -593,22 +605,31 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
       consumer_bar();
       // ---- stage A: row walk over the ring.  All WMAX slots are updated unconditionally (a closed slot has c = d = 0 and
       //      adds +0, which is exact); the only data-dependent branch is the rare "row finished" one.
-      for (int j = 0; j < J; j++) {
+      for (int j2 = 0; j2 < J; j2 += kStSlotRows) {
         mbar_wait(&full[stage], par);
-        const uint32_t *rw = reinterpret_cast<const uint32_t *>(ring + stage * kStRowBytes);
-        uint32_t w[NW];
+        const uint32_t *rw = reinterpret_cast<const uint32_t *>(ring + stage * kStSlotBytes);
+        uint32_t wr[kStSlotRows][NW];
 #pragma unroll
-        for (int q = 0; q < NW; q++) w[q] = rw[tid + q * kStConsumers];       // the slot is kStRowBytes long: always in bounds
+        for (int r2 = 0; r2 < kStSlotRows; r2++)
+#pragma unroll
+          for (int q = 0; q < NW; q++) wr[r2][q] = rw[r2 * (kStRowBytes / 4) + tid + q * kStConsumers];   // always inside the slot
         // release the slot only once the words have ARRIVED in registers (the asm consumes them): the LDS of a warp completes
         // for all lanes together, and the slot is rewritten by the async proxy as soon as all 8 warps have arrived
 #ifndef DALIB200_NO_RING_FENCE
-        asm volatile("fence.proxy.async.shared::cta;" :: "r"(w[0]), "r"(w[NW - 1]) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" :: "r"(wr[0][0]), "r"(wr[0][NW - 1]), "r"(wr[kStSlotRows - 1][0]), "r"(wr[kStSlotRows - 1][NW - 1]) : "memory");
 #else
-        asm volatile("" :: "r"(w[0]), "r"(w[NW - 1]) : "memory");
+        asm volatile("" :: "r"(wr[0][0]), "r"(wr[kStSlotRows - 1][NW - 1]) : "memory");
 #endif
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == kStStages) { stage = 0; par ^= 1u; }
+#pragma unroll
+        for (int r2 = 0; r2 < kStSlotRows; r2++) {
+        const int j = j2 + r2;
+        if (j >= J) continue;
+        uint32_t w[NW];
+#pragma unroll
+        for (int q = 0; q < NW; q++) w[q] = wr[r2][q];
         float2 cd[kWalkSlots];
         {
           const float4 e01 = *reinterpret_cast<const float4 *>(&ent[j][0]);
@@ -652,6 +673,7 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
             }
           }
         }
+        }            // rows of the slot
       }
       consumer_bar();
       // ---- stage B: horizontal pass of the chunk's th rows, two rows per packed operation

@@ -1056,17 +1056,22 @@ __global__ void __launch_bounds__(128) idct_kernel(const JpegImage *__restrict__
     int ws[64];
     {
       int in[64];
+      const uint4 *q4 = reinterpret_cast<const uint4 *>(q);      // 8 x u16 per row in ONE 16-byte load (the table is 16-byte aligned)
+      uint32_t q00 = 0;
 #pragma unroll
       for (int r = 0; r < 8; r++) {
         const int4 v = __ldg(src + r);
+        const uint4 qv = __ldg(q4 + r);
         const int w[4] = { v.x, v.y, v.z, v.w };
+        const uint32_t qw[4] = { qv.x, qv.y, qv.z, qv.w };
+        if (r == 0) q00 = qv.x & 0xFFFFu;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          in[r * 8 + 2 * k] = (int)(int16_t)(w[k] & 0xFFFF) * (int)q[r * 8 + 2 * k];
-          in[r * 8 + 2 * k + 1] = (w[k] >> 16) * (int)q[r * 8 + 2 * k + 1];
+          in[r * 8 + 2 * k] = (int)(int16_t)(w[k] & 0xFFFF) * (int)(qw[k] & 0xFFFFu);
+          in[r * 8 + 2 * k + 1] = (w[k] >> 16) * (int)(qw[k] >> 16);
         }
       }
-      in[0] = (int)__ldg(dc_arena + gb) * (int)q[0];        // DC lives in the compact array (after prediction)
+      in[0] = (int)__ldg(dc_arena + gb) * (int)q00;         // DC lives in the compact array (after prediction)
 #pragma unroll
       for (int x = 0; x < 8; x++) {       // pass 1: columns
         int o[8];

@@ -480,9 +480,9 @@ __global__ void __launch_bounds__(256) resample_fused_kernel(const RsDesc *__res
 // finished output row in shared memory and, every 8 rows, run the horizontal pass from there.  The producer runs ahead
 // across chunk and item boundaries, so HBM latency is hidden by the ring, not by occupancy.
 constexpr int kStRowBytes = 2048;         // one source row segment
-constexpr int kStSlotRows = 4;            // ring slot = TWO consecutive source rows of a chunk: one mbarrier wait / proxy fence / arrive
+constexpr int kStSlotRows = 8;            // ring slot = TWO consecutive source rows of a chunk: one mbarrier wait / proxy fence / arrive
                                           // per two rows (the per-row synchronisation was ~20 % of the walk's stall samples)
-constexpr int kStStages = 5;
+constexpr int kStStages = 2;
 constexpr int kStTH = 8;                  // output rows per chunk
 constexpr int kStConsumers = 256;
 constexpr int kStThreads = kStConsumers + 32;

@@ -750,7 +750,7 @@ struct WriteSmem {
 };
 __host__ __device__ inline size_t write_sw_words(int log2_sub) { return (size_t)(kWriteThreads + look_ahead_cols(log2_sub)) << (log2_sub - 5); }
 __host__ __device__ inline size_t write_smem_bytes(int log2_sub) {
-  return kLutWords * 2 + write_sw_words(log2_sub) * 4 + 16 * 4 /*tbl*/ + 64 /*zig*/ + 4 * sizeof(HuffSlow) + (size_t)kWriteThreads * 128;
+  return kLutWords * 2 + write_sw_words(log2_sub) * 4 + 16 * 4 /*tbl*/ + 64 /*zig*/ + (size_t)kWriteThreads * 128;
 }
 __device__ __forceinline__ WriteSmem carve_write_smem(uint32_t *base, int log2_sub) {
   WriteSmem s;
@@ -758,8 +758,8 @@ __device__ __forceinline__ WriteSmem carve_write_smem(uint32_t *base, int log2_s
   s.sw = base + kLutWords / 2;
   s.tbl = s.sw + write_sw_words(log2_sub);
   s.zig = reinterpret_cast<uint8_t *>(s.tbl + 16);
-  s.slow = reinterpret_cast<HuffSlow *>(s.zig + 64);
-  s.blkbuf = reinterpret_cast<uint32_t *>(s.slow + 4);                       // 16-byte aligned: every size above is a multiple of 16
+  s.slow = nullptr;                                                          // the long-code tables stay in global memory (see below)
+  s.blkbuf = reinterpret_cast<uint32_t *>(s.zig + 64);                       // 16-byte aligned: every size above is a multiple of 16
   s.colptr = reinterpret_cast<const uint8_t **>(s.blkbuf);                  // prologue only, (kWriteThreads + 8) * 8 bytes
   return s;
 }
@@ -776,9 +776,6 @@ __global__ void __launch_bounds__(kWriteThreads) huff_write_kernel(HuffCtx cx) {
     for (int i = threadIdx.x; i < kLutWords * 2 / 16; i += blockDim.x) dst[i] = __ldg(src + i);
     if (threadIdx.x < kMaxBlocksPerMcu) sm.tbl[threadIdx.x] = tbl_word(im, threadIdx.x);
     if (threadIdx.x < 64) sm.zig[threadIdx.x] = c_zigzag[threadIdx.x];
-    const uint32_t *ssrc = reinterpret_cast<const uint32_t *>(cx.tables[im.table_set].slow);
-    uint32_t *sdst = reinterpret_cast<uint32_t *>(sm.slow);
-    for (int i = threadIdx.x; i < (int)(4 * sizeof(HuffSlow) / 4); i += blockDim.x) sdst[i] = __ldg(ssrc + i);
   }
   SubGeom sg;
   {
@@ -813,7 +810,9 @@ __global__ void __launch_bounds__(kWriteThreads) huff_write_kernel(HuffCtx cx) {
     }
     __syncthreads();                                           // colptr (aliased with the block buffers) is dead from here on
   }
-  const HuffSlow *slow = sm.slow;
+  // long codes (~1 % of the symbols) are looked up in global memory (L1-resident, one load with the direct table): a shared-memory
+  // copy cost 5.7 KB per CTA and made the compiler rebuild the generic address of the copy inside the symbol loop
+  const HuffSlow *slow = cx.tables[im.table_set].slow;
   const SmemSrc src{smem_u32(sm.sw), lsw};
   const uint32_t lane = threadIdx.x & 31u;
   // shared-window addresses (plain integers inside the loop, see lds_u32)

@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
           const int J = idx_y[cy0 + th - 1] + Sy - cs;
           for (int j = 0; j < J; j += kStSlotRows) {
             const int nr = min(kStSlotRows, J - j);
-            mbar_wait(&empty[stage], par);
+            mbar_wait_backoff(&empty[stage], par);
             mbar_expect_tx(&full[stage], (uint32_t)(g.bytes * nr));
             for (int q = 0; q < nr; q++) {
               const int row = by + min(max(cs + j + q, 0), ey - 1);
@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_planar_kernel(const Rs
         const uint32_t cbytes = (uint32_t)min(g.npx / 2 + 32, d.pitch_c - g.c0);
         const int ustart = idx_y[it.oy0], uend = idx_y[it.oy1 - 1] + Sy - 1;
         for (int u = ustart; u <= uend; u++) {
-          mbar_wait(&empty[stage], par);
+          mbar_wait_backoff(&empty[stage], par);
           mbar_expect_tx(&full[stage], ybytes + 4u * cbytes);
           const int fy = d.crop_y + by + min(max(u, 0), ey - 1);
           const int rn = fy >> 1;

@@ -14,5 +14,6 @@ tail -2 gpurun_out/prof_c34.log
 python tools/ncu_traffic.py /tmp/r2_full_c34.ncu-rep 0 gpurun_out/r2_ncu_c34.json gpurun_out/r2_ncu_full_c34.txt > /dev/null
 ncu -i /tmp/r2_full_c34.ncu-rep --page raw --csv | gzip -9 > gpurun_out/r2_ncu_full_c34.raw.csv.gz
 ncu --set full --clock-control none --import-source on -k regex:'huff_write' -s 1 -c 1 -f -o gpurun_out/r2_huff_write_batch256 python tools/prof_c2.py 256 2 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'resample_stream' -s 1 -c 1 -f -o gpurun_out/r2_resample_stream_batch256 python tools/prof_c2.py 256 2 > /dev/null 2>&1
 ls -la gpurun_out/ | head -40
 du -sh gpurun_out

@@ -121,7 +121,8 @@ int dalib200JpegUpload(dalib200JpegPlan *plan, dalib200Stream_t stream);
  * until the launch that consumes them has completed -- the contract of the reference's external_source(no_copy=True)
  * (dali/python/nvidia/dali/external_source.py, `no_copy`) and of its readers' own buffers.  JpegUpload then copies samples that
  * live in page-locked memory straight from the caller's buffers (one DMA per sample, no host repack); anything else still goes
- * through the pinned staging buffer.  JpegPlanLastUploadDirect: 1 when the last upload took the direct path. */
+ * through the pinned staging buffer.  JpegPlanLastUploadDirect: 0 = staged, 1 = direct (one cudaMemcpyAsync per
+ * sample), 2 = direct as one cudaMemcpyBatchAsync submission. */
 int dalib200JpegPlanSetSourceStable(dalib200JpegPlan *plan, int stable);
 int dalib200JpegPlanLastUploadDirect(const dalib200JpegPlan *plan);
 /* Test hook: exhaustive (2^32 inputs) check of the kernels' float -> float16 conversion against the integer restatement of the

@@ -117,15 +117,27 @@ def jpeg_decode(streams, output_type=capi.RGB, fancy=True, plan=None, want_coefs
     return res, list(status)
 
 
-def jpeg_decode_ex(streams, output_type=capi.RGB, fancy=True, dtype=capi.UINT8, adjust_orientation=True, rois=None, plan=None):
-    """dalib200JpegPlanSetupEx: rois[i] = None | (x0, y0, x1, y1) in output (oriented) coordinates."""
+def jpeg_decode_ex(streams, output_type=capi.RGB, fancy=True, dtype=capi.UINT8, adjust_orientation=True, rois=None, plan=None, pinned=False,
+                   want_upload_path=False):
+    """dalib200JpegPlanSetupEx: rois[i] = None | (x0, y0, x1, y1) in output (oriented) coordinates.  pinned=True: the streams live in
+    page-locked memory and are declared stable (dalib200JpegPlanSetSourceStable) -> no host repack."""
     torch = _torch()
     n = len(streams)
     bufs = [np.frombuffer(bytes(s), np.uint8) for s in streams]
+    if pinned:
+        arena = capi.pinned_empty(sum((b.size + 63) & ~63 for b in bufs) + 64)
+        off, pb = 0, []
+        for b in bufs:
+            v = arena[off:off + b.size]
+            v[:] = b
+            pb.append(v)
+            off += (b.size + 63) & ~63
+        bufs = pb
     ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
     lens = (C.c_size_t * n)(*[b.size for b in bufs])
     plan = plan or capi.Plan("Jpeg", max(n, 1))
     prm = capi.JpegParams(output_type, int(fancy), dtype, int(adjust_orientation))
+    capi.check(capi.lib().dalib200JpegPlanSetSourceStable(plan.handle, int(pinned)))
     cr = None
     if rois is not None:
         cr = (capi.JpegRoi * n)()
@@ -144,6 +156,8 @@ def jpeg_decode_ex(streams, output_type=capi.RGB, fancy=True, dtype=capi.UINT8, 
     torch.cuda.synchronize()
     status = (C.c_int32 * n)()
     capi.check(capi.lib().dalib200JpegGetStatus(plan.handle, status))
+    if want_upload_path:
+        return [o.cpu().numpy() for o in outs], list(status), int(capi.lib().dalib200JpegPlanLastUploadDirect(plan.handle))
     return [o.cpu().numpy() for o in outs], list(status)
 
 

@@ -290,3 +290,20 @@ def test_truncated_stream_status_gray_tail_and_pipeline_error():
     p.build()
     with pytest.raises(RuntimeError, match="Failed to decode sample #0"):
         p.run()
+
+
+def test_direct_upload_from_page_locked_sources():
+    """Streams in page-locked memory that the caller declares stable are copied by DMA straight from the caller's buffers (one
+    batched submission, or one copy per sample when the driver lacks the batch call); pageable or undeclared sources go through
+    the pinned staging buffer.  All three routes decode to the same bytes."""
+    import cv2
+    import gpu_helpers as g
+    streams = []
+    for i, (h, w) in enumerate(((300, 420), (64, 64), (481, 641), (200, 333))):
+        ok, enc = cv2.imencode(".jpg", g.synth_image(h, w, 70 + i), [cv2.IMWRITE_JPEG_QUALITY, 85])
+        streams.append(np.ascontiguousarray(enc.ravel()))
+    a, sa, pa = g.jpeg_decode_ex(streams, want_upload_path=True)
+    b, sb, pb = g.jpeg_decode_ex(streams, pinned=True, want_upload_path=True)
+    assert pa == 0 and pb in (1, 2) and sa == sb == [0] * len(streams)
+    for x, y, s in zip(a, b, streams):
+        assert np.array_equal(x, y) and np.array_equal(x, po.jpeg_decode(s.tobytes()))

@@ -572,8 +572,9 @@ def main():
            "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / args.steps, "api": "dali_b200.pipeline_def + fn.external_source / "
            "fn.decoders.image(mixed) / fn.resize / fn.crop_mirror_normalize, Pipeline.run()", "prefetch_queue_depth": e2e_depth,
            "equals_device_resident_path": api_equal,
-           "host_buffers": "page-locked host arena, fn.external_source(no_copy=True): one H2D DMA per sample from the caller's memory",
-           "note": "host header parse + pinned staging + H2D + all kernels + D2H of a checksum scalar, per step"}
+           "host_buffers": "page-locked host arena, fn.external_source(no_copy=True): the samples are copied by DMA from the caller's memory "
+                           "(one cudaMemcpyBatchAsync submission per batch, no host repack)",
+           "note": "host header parse + H2D + all kernels + D2H of a checksum scalar, per step"}
 
     # ---- parity of the timed configuration against the CPU reference path (reported, not timed)
     if cpu_baseline is not None:

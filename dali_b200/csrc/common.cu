@@ -1,5 +1,6 @@
 // dali_b200/csrc/common.cu -- error state, descriptor arena, launch accounting.
 #include "common.cuh"
+#include <mutex>
 #include <nvtx3/nvToolsExt.h>
 #include <cstring>
 
@@ -60,6 +61,8 @@ static bool g_prof_on = false;
 struct ProfRec { const char *name; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_prof_pool;
+static std::mutex g_prof_mutex;                        // several pipelines (one host thread each) may launch concurrently
+static thread_local std::vector<size_t> tls_prof_open;  // indices of this thread's open records
 static cudaEvent_t ProfEvent() {
   if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
   cudaEvent_t e = nullptr;
@@ -72,14 +75,19 @@ static cudaEvent_t ProfEvent() {
 void ProfBegin(const char *name, cudaStream_t s) {
   nvtxRangePushA(name);
   if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   ProfRec r{name, ProfEvent(), ProfEvent()};
   cudaEventRecord(r.a, s);
+  tls_prof_open.push_back(g_prof.size());
   g_prof.push_back(r);
 }
 void ProfEnd(cudaStream_t s) {
   nvtxRangePop();
-  if (!g_prof_on || g_prof.empty()) return;
-  cudaEventRecord(g_prof.back().b, s);
+  if (!g_prof_on || tls_prof_open.empty()) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  const size_t i = tls_prof_open.back();
+  tls_prof_open.pop_back();
+  if (i < g_prof.size()) cudaEventRecord(g_prof[i].b, s);
 }
 
 }  // namespace dalib200
@@ -132,6 +140,7 @@ int dalib200ProfilingEnable(int on) { dalib200::g_prof_on = on != 0; return DALI
 // Synchronises, writes up to `max` records (names: `name_stride` bytes each, NUL terminated) and clears the log.
 int dalib200ProfilingCollect(char *names, int name_stride, float *ms, int max, int *count) {
   using namespace dalib200;  // NOLINT
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   int n = 0;
   for (auto &r : g_prof) {
     cudaEventSynchronize(r.b);

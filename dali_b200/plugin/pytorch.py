@@ -38,6 +38,7 @@ class DALIGenericIterator:
         if reader_name is not None:
             self._init_from_reader(last_batch_padded)
         self._first = None
+        self._pool = None
         if prepare_first_batch:
             try:
                 self._first = self._fetch()
@@ -69,11 +70,22 @@ class DALIGenericIterator:
         self._shard_sizes_per_gpu = (ids + 1) * n // shards - ids * n // shards
         self._shard_sizes_initial = self._shard_sizes_per_gpu.copy()
 
+    def _run_all(self):
+        """One iteration of every pipeline.  With several pipelines (one per GPU in one process, the layout of the reference's
+        multi-GPU examples) the host work of an iteration -- feeding, header parsing, H2D submission, the wait for the oldest
+        batch -- runs concurrently, one thread per pipeline (the native calls release the GIL)."""
+        if len(self._pipes) == 1:
+            return [self._pipes[0].run()]
+        if self._pool is None:
+            import concurrent.futures as cf
+            self._pool = cf.ThreadPoolExecutor(max_workers=len(self._pipes), thread_name_prefix="dali_b200_iter")
+        futs = [self._pool.submit(p.run) for p in self._pipes]
+        return [f.result() for f in futs]          # a StopIteration / error of any pipeline propagates
+
     def _fetch(self):
         torch = self._torch
         res = []
-        for p in self._pipes:
-            outs = p.run()          # keeps `prefetch_queue_depth` batches in flight and returns the oldest
+        for p, outs in zip(self._pipes, self._run_all()):
             if len(outs) != len(self.output_map):
                 raise RuntimeError(f"The pipeline has {len(outs)} outputs but output_map has {len(self.output_map)} names")
             d = {}

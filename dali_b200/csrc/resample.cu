@@ -661,12 +661,16 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
           for (int s = 0; s < WMAX; s++) {
             const uint32_t tl = (f >> (8 * s)) & 0xFFu;
             if (tl != 0xFFu) {
+              // parked rows are laid out by BYTE LANE: byte k of source word w of a row pair sits at float2 index k * words + w
+              // (x = even row of the pair, y = odd row).  A warp's store of one byte lane then covers 32 consecutive float2 --
+              // 2-way bank conflicts instead of the 8-way conflicts of the natural [byte][pair] order, which were three quarters
+              // of this kernel's shared-memory wavefronts (ncu: 101 M conflicts of 178 M wavefronts)
               float *dst = tmp2 + ((size_t)(tl >> 1) * RE) * 2 + (tl & 1u);
 #pragma unroll
               for (int q = 0; q < NW; q++) {
                 if (okw[q]) {
-                  float *p4 = dst + 8 * (tid + q * kStConsumers);
-                  p4[0] = acc[s][q][0].x; p4[2] = acc[s][q][0].y; p4[4] = acc[s][q][1].x; p4[6] = acc[s][q][1].y;
+                  float *p4 = dst + 2 * (tid + q * kStConsumers);
+                  p4[0] = acc[s][q][0].x; p4[2 * words] = acc[s][q][0].y; p4[4 * words] = acc[s][q][1].x; p4[6 * words] = acc[s][q][1].y;
                 }
                 acc[s][q][0] = acc[s][q][1] = make_float2(0.f, 0.f);
               }
@@ -696,7 +700,7 @@ __global__ void __launch_bounds__(kStThreads, 2) resample_stream_kernel(const Rs
           const int col = interior ? col0 + k * C : (bx + min(max(i0 + k, 0), ex - 1)) * C + c - g.e0;
           const float ck = cx[k];
           const float2 c2 = make_float2(ck, ck);
-          const float2 *src = reinterpret_cast<const float2 *>(tmp2) + col;
+          const float2 *src = reinterpret_cast<const float2 *>(tmp2) + (col & 3) * words + (col >> 2);      // byte-lane layout, see stage A
 #pragma unroll
           for (int p = 0; p < kStTH / 2; p++)
             if (p < npair) a[p] = add2_rn(a[p], fma2_rn(src[(size_t)p * RE], c2, nz));

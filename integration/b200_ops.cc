@@ -14,6 +14,8 @@
 #include "dali/operators/image/crop/crop_attr.h"
 #include "dali/operators/image/resize/resampling_attr.h"
 #include "dali/operators/image/resize/resize_attr.h"
+#include "dali/operators/audio/nonsilence_op.h"
+#include "dali/operators/audio/resample.h"
 #include "dali/pipeline/operator/operator.h"
 
 #include "dali_b200.h"
@@ -413,6 +415,72 @@ class MelFilterBank : public Operator<GPUBackend> {
   dalib200MelArgs args_{};
 };
 
+// ------------------------------------------------------------------------------------------------ AudioResample / NonsilentRegion
+// These two derive from the reference's OWN operator bases: argument handling, shape inference and error messages are the reference's
+// code (audio::ResampleBase::SetupImpl / CalculateShapeAndArgs, NonsilenceOperator::SetupImpl / AcquireArgs); only RunImpl changes.
+class AudioResample : public audio::ResampleBase<GPUBackend> {
+ public:
+  using Base = audio::ResampleBase<GPUBackend>;
+  explicit AudioResample(const OpSpec &spec) : Base(spec) { Check(dalib200SignalPlanCreate(&plan_, max_batch_size_), "AudioResample"); }
+  ~AudioResample() override { dalib200SignalPlanDestroy(plan_); }
+
+ protected:
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_FLOAT && out.type() == DALI_FLOAT, "b200 AudioResample: float input and output only");
+    out.SetLayout(in.GetLayout());
+    const int n = in.num_samples();
+    std::vector<dalib200AudioResampleSample> s(n);
+    for (int i = 0; i < n; i++) {
+      const auto ish = in.tensor_shape(i), osh = out.tensor_shape(i);
+      s[i].in_rate = args_[i].in_rate; s[i].out_rate = args_[i].out_rate;          // filled by ResampleBase::CalculateShapeAndArgs
+      s[i].in_length = ish[0]; s[i].out_length = osh[0];
+      s[i].channels = ish.sample_dim() > 1 ? static_cast<int>(ish[1]) : 1;
+    }
+    Check(dalib200AudioResampleSetup(plan_, n, s.data(), quality_), "AudioResample");
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200SignalLaunch(plan_, ip.data(), op.data(), ws.stream()), "AudioResample");
+  }
+
+ private:
+  dalib200SignalPlan *plan_ = nullptr;
+};
+
+class NonsilentRegion : public NonsilenceOperator<GPUBackend> {
+ public:
+  explicit NonsilentRegion(const OpSpec &spec) : NonsilenceOperator<GPUBackend>(spec) {
+    Check(dalib200SignalPlanCreate(&plan_, max_batch_size_), "NonsilentRegion");
+  }
+  ~NonsilentRegion() override { dalib200SignalPlanDestroy(plan_); }
+
+ protected:
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &begin = ws.Output<GPUBackend>(0);
+    auto &length = ws.Output<GPUBackend>(1);
+    DALI_ENFORCE(in.type() == DALI_FLOAT, "b200 NonsilentRegion: float input only");
+    const int n = in.num_samples();
+    std::vector<int64_t> len(n);
+    std::vector<dalib200NonsilentSample> a(n);
+    for (int i = 0; i < n; i++) {
+      len[i] = in.tensor_shape(i).num_elements();
+      a[i].cutoff_db = cutoff_db_[i];                                                // filled by NonsilenceOperator::AcquireArgs
+      a[i].use_reference_power = reference_max_ ? 0 : 1;
+      a[i].reference_power = reference_max_ ? 0.0f : reference_power_[i];
+    }
+    Check(dalib200NonsilentSetup(plan_, n, len.data(), a.data(), window_length_, reset_interval_), "NonsilentRegion");
+    auto ip = InPtrs(in);
+    auto bp = OutPtrs(begin);
+    auto lp = OutPtrs(length);
+    Check(dalib200NonsilentLaunch(plan_, ip.data(), bp.data(), lp.data(), ws.stream()), "NonsilentRegion");
+  }
+
+ private:
+  dalib200SignalPlan *plan_ = nullptr;
+};
+
 }  // namespace b200
 
 namespace dali {       // the registration macros expect the dali namespace (operator.h:327-333)
@@ -434,5 +502,9 @@ DALI_REGISTER_OPERATOR(b200__Hsv, b200::Hsv, GPU);
 DALI_REGISTER_OPERATOR(b200__ColorSpaceConversion, b200::ColorSpaceConversion, GPU);
 DALI_REGISTER_OPERATOR(b200__Spectrogram, b200::Spectrogram, GPU);
 DALI_REGISTER_OPERATOR(b200__MelFilterBank, b200::MelFilterBank, GPU);
+DALI_SCHEMA(b200__AudioResample).NumInput(1).NumOutput(1).AddParent("AudioResample");
+DALI_SCHEMA(b200__NonsilentRegion).NumInput(1).NumOutput(2).AddParent("NonsilentRegion");
+DALI_REGISTER_OPERATOR(b200__AudioResample, b200::AudioResample, GPU);
+DALI_REGISTER_OPERATOR(b200__NonsilentRegion, b200::NonsilentRegion, GPU);
 
 }  // namespace dali

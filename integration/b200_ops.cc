@@ -12,6 +12,7 @@
 #include "dali/core/static_switch.h"
 #include "dali/kernels/imgproc/resample/params.h"
 #include "dali/operators/image/crop/crop_attr.h"
+#include "dali/operators/image/crop/random_crop_attr.h"
 #include "dali/operators/image/resize/resampling_attr.h"
 #include "dali/operators/image/resize/resize_attr.h"
 #include "dali/operators/audio/nonsilence_op.h"
@@ -86,6 +87,75 @@ class ImageDecoder : public Operator<MixedBackend> {
   dalib200JpegPlan *plan_ = nullptr;
   dalib200JpegParams prm_{};
 };
+
+// ------------------------------------------------------------------------------------------------ decoders.image_crop / image_random_crop
+// Region-of-interest decode: the window comes from the reference's OWN attribute classes (CropAttr: crop / crop_pos_x / crop_pos_y ...;
+// RandomCropAttr: the Philox-based RandomCropGenerator, so a given seed yields the reference's windows), in the coordinates of the
+// oriented image (imgcodec.h:26-44); the library decodes only the MCUs the window and the upsampling taps touch.
+template <typename WindowAttr>
+class ImageDecoderRoi : public Operator<MixedBackend> {
+ public:
+  explicit ImageDecoderRoi(const OpSpec &spec) : Operator<MixedBackend>(spec), attr_(spec) {
+    prm_.output_type = static_cast<int>(spec.GetArgument<DALIImageType>("output_type"));
+    prm_.dtype = spec.GetArgument<DALIDataType>("dtype") == DALI_FLOAT ? DALIB200_FLOAT : DALIB200_UINT8;
+    prm_.fancy_upsampling = spec.GetArgument<bool>("jpeg_fancy_upsampling");
+    prm_.adjust_orientation = spec.GetArgument<bool>("adjust_orientation");
+    Check(dalib200JpegPlanCreate(&plan_, max_batch_size_), "decoders.image_crop");
+  }
+  ~ImageDecoderRoi() override { dalib200JpegPlanDestroy(plan_); }
+  bool HasContiguousOutputs() const override { return true; }
+
+ protected:
+  virtual void AcquireWindowArgs(const Workspace &ws) {}
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<CPUBackend>(0);
+    const int n = in.num_samples();
+    AcquireWindowArgs(ws);
+    std::vector<const uint8_t *> ptrs(n);
+    std::vector<size_t> lens(n);
+    std::vector<dalib200JpegRoi> rois(n);
+    for (int i = 0; i < n; i++) {
+      ptrs[i] = static_cast<const uint8_t *>(in.raw_tensor(i));
+      lens[i] = static_cast<size_t>(in.tensor_shape(i).num_elements());
+      dalib200JpegInfo info;
+      Check(dalib200JpegGetInfo(ptrs[i], lens[i], &info), "decoders.image_crop");
+      int64_t H = info.height, W = info.width;
+      if (prm_.adjust_orientation && info.orientation >= 5) std::swap(H, W);       // image_decoder.h:678-681
+      const CropWindow win = attr_.GetCropWindowGenerator(i)(TensorShape<>{H, W}, "HW");
+      rois[i] = { 1, static_cast<int32_t>(win.anchor[1]), static_cast<int32_t>(win.anchor[0]),
+                  static_cast<int32_t>(win.anchor[1] + win.shape[1]), static_cast<int32_t>(win.anchor[0] + win.shape[0]), 0 };
+    }
+    Check(dalib200JpegPlanSetupEx(plan_, n, ptrs.data(), lens.data(), &prm_, rois.data()), "decoders.image_crop");
+    out.resize(1);
+    out[0].type = prm_.dtype == DALIB200_FLOAT ? DALI_FLOAT : DALI_UINT8;
+    out[0].shape.resize(n, 3);
+    for (int i = 0; i < n; i++) {
+      int32_t hwc[3];
+      Check(dalib200JpegPlanGetOutputShape(plan_, i, hwc), "decoders.image_crop");
+      out[0].shape.set_tensor_shape(i, TensorShape<>{hwc[0], hwc[1], hwc[2]});
+    }
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout("HWC");
+    auto op = OutPtrs(out);
+    Check(dalib200JpegUpload(plan_, ws.stream()), "decoders.image_crop");
+    Check(dalib200JpegLaunch(plan_, op.data(), ws.stream()), "decoders.image_crop");
+  }
+
+  WindowAttr attr_;
+  dalib200JpegPlan *plan_ = nullptr;
+  dalib200JpegParams prm_{};
+};
+
+class ImageDecoderCrop : public ImageDecoderRoi<CropAttr> {
+ public:
+  using ImageDecoderRoi<CropAttr>::ImageDecoderRoi;
+ protected:
+  void AcquireWindowArgs(const Workspace &ws) override { attr_.ProcessArguments(spec_, ws); }      // crop_attr.cc:100-245
+};
+using ImageDecoderRandomCrop = ImageDecoderRoi<RandomCropAttr>;
 
 // ------------------------------------------------------------------------------------------------ Resize
 class Resize : public Operator<GPUBackend> {
@@ -502,6 +572,10 @@ DALI_REGISTER_OPERATOR(b200__Hsv, b200::Hsv, GPU);
 DALI_REGISTER_OPERATOR(b200__ColorSpaceConversion, b200::ColorSpaceConversion, GPU);
 DALI_REGISTER_OPERATOR(b200__Spectrogram, b200::Spectrogram, GPU);
 DALI_REGISTER_OPERATOR(b200__MelFilterBank, b200::MelFilterBank, GPU);
+DALI_SCHEMA(b200__decoders__ImageCrop).NumInput(1).NumOutput(1).AddParent("decoders__ImageCrop");
+DALI_SCHEMA(b200__decoders__ImageRandomCrop).NumInput(1).NumOutput(1).AddParent("decoders__ImageRandomCrop");
+DALI_REGISTER_OPERATOR(b200__decoders__ImageCrop, b200::ImageDecoderCrop, Mixed);
+DALI_REGISTER_OPERATOR(b200__decoders__ImageRandomCrop, b200::ImageDecoderRandomCrop, Mixed);
 DALI_SCHEMA(b200__AudioResample).NumInput(1).NumOutput(1).AddParent("AudioResample");
 DALI_SCHEMA(b200__NonsilentRegion).NumInput(1).NumOutput(2).AddParent("NonsilentRegion");
 DALI_REGISTER_OPERATOR(b200__AudioResample, b200::AudioResample, GPU);

@@ -21,7 +21,7 @@ def test_plugin_compiles_against_reference_headers():
     assert r.returncode == 0, r.stderr[-4000:]
     src = open(os.path.join(ROOT, "integration", "b200_ops.cc")).read()
     for op in ("decoders__Image", "Resize", "CropMirrorNormalize", "WarpAffine", "Hsv", "ColorSpaceConversion", "Spectrogram", "MelFilterBank",
-               "AudioResample", "NonsilentRegion"):
+               "AudioResample", "NonsilentRegion", "decoders__ImageCrop", "decoders__ImageRandomCrop"):
         assert f"DALI_REGISTER_OPERATOR(b200__{op}," in src, op
 
 

@@ -228,3 +228,207 @@ int oracle_mel_weights(float *W, int nbin, int nfilter, float sample_rate, float
   free(m.weights_down); free(m.norm_factors); free(m.intervals);
   return 0;
 }
+
+/* ================================================================================================================================
+ * Audio tail: plain-C restatements, pinned bit for bit against the compiled reference kernels (oracle/_ref) by
+ * tests/test_audio_tail_ref_cpu.py.
+ * ================================================================================================================================ */
+
+/* ToDecibels: dali/kernels/signal/decibel/to_decibels_cpu.cc:47-72 + decibel_calculator.h:25-56
+ *   out = (mul * log10(2)) * log2(max(min_ratio, in * (1 / s_ref))),  s_ref = max over the sample when ref_max (0 -> 1) */
+void oracle_to_decibels(const float *in, int64_t n, float *out, float multiplier, float reference, float cutoff_db, int ref_max) {
+  float min_ratio = powf(10.0f, cutoff_db / multiplier);              /* to_decibels_op.h:47-50 */
+  if (min_ratio == 0) min_ratio = nextafterf(0.0f, 1.0f);
+  float s_ref = reference;
+  if (ref_max) {
+    s_ref = 0.0f;
+    for (int64_t i = 0; i < n; i++) if (in[i] > s_ref) s_ref = in[i];
+    if (s_ref == 0.0f) s_ref = 1.0f;                                   /* avoid division by 0 */
+  }
+  const float kLog2Factor = 0.3010299956639812f;                      /* std::log10(2.0) */
+  const float mul_log2 = multiplier * kLog2Factor;
+  const float inv_s_ref = 1.0f / s_ref;
+  for (int64_t i = 0; i < n; i++) {
+    float r = in[i] * inv_s_ref;
+    if (r < min_ratio) r = min_ratio;
+    out[i] = mul_log2 * log2f(r);
+  }
+}
+
+/* DCT along axis 0 of [nfeat][ncols]: dali/kernels/signal/dct/table.h:27-112 (cosine tables in double, stored as float) and
+ * dct_cpu.cc:76-115 (out[k] = sum_n in[n] * table[k][n], n ascending, float mul + add); liftering mfcc.h:36-41, mfcc.cc:52-72. */
+static void dct_table(float *table, int64_t n, int ndct, int type, int normalize) {
+  int64_t idx = 0;
+  if (type == 1) {
+    const double phase_mul = M_PI / (n - 1);
+    for (int64_t k = 0; k < ndct; k++) {
+      table[idx++] = 0.5f;
+      for (int64_t i = 1; i < n - 1; i++) table[idx++] = (float)cos(phase_mul * k * i);
+      table[idx++] = k % 2 == 0 ? 0.5f : -0.5f;
+    }
+  } else if (type == 2) {
+    const double phase_mul = M_PI / n;
+    double f0 = 1, fi = 1;
+    if (normalize) { fi = sqrt(2.0 / n); f0 = 1.0 / sqrt((double)n); }
+    for (int64_t k = 0; k < ndct; k++) {
+      const double nf = k == 0 ? f0 : fi;
+      for (int64_t i = 0; i < n; i++) table[idx++] = (float)(nf * cos(phase_mul * (i + 0.5) * k));
+    }
+  } else if (type == 3) {
+    const double phase_mul = M_PI / n;
+    double f0 = 0.5, fi = 1;
+    if (normalize) { fi = sqrt(2.0 / n); f0 = 1.0 / sqrt((double)n); }
+    for (int64_t k = 0; k < ndct; k++) {
+      table[idx++] = (float)f0;
+      for (int64_t i = 1; i < n; i++) table[idx++] = (float)(fi * cos(phase_mul * i * (k + 0.5)));
+    }
+  } else {
+    const double phase_mul = M_PI / n;
+    const double f = normalize ? sqrt(2.0 / n) : 1.0;
+    for (int64_t k = 0; k < ndct; k++)
+      for (int64_t i = 0; i < n; i++) table[idx++] = (float)(f * cos(phase_mul * (i + 0.5) * (k + 0.5)));
+  }
+}
+
+int oracle_mfcc(const float *in, int nfeat, int64_t ncols, float *out, int n_mfcc, int dct_type, int normalize, float lifter) {
+  const int ndct = n_mfcc < nfeat ? n_mfcc : nfeat;
+  float *table = (float *)malloc(sizeof(float) * (size_t)ndct * nfeat);
+  if (!table) return -1;
+  dct_table(table, nfeat, ndct, dct_type, normalize);
+  for (int k = 0; k < ndct; k++) {
+    float coeff = 1.0f;
+    if (lifter != 0.0f) coeff = 1.0f + lifter / 2 * sinf((float)M_PI / lifter * (k + 1));   /* all-float, see audio_tail.cu */
+    for (int64_t c = 0; c < ncols; c++) {
+      float acc = 0.0f;
+      for (int nn = 0; nn < nfeat; nn++) acc += table[(size_t)k * nfeat + nn] * in[(size_t)nn * ncols + c];
+      out[(size_t)k * ncols + c] = lifter != 0.0f ? acc * coeff : acc;
+    }
+  }
+  free(table);
+  return ndct;
+}
+
+/* NonsilentRegion: moving mean square with a running float sum (dali/kernels/signal/moving_mean_square.cc:55-77), threshold
+ * s_ref * pow(10, cutoff_db / 10) (decibel_calculator.h:60-73), first / last sample at or above it and the window adjustment
+ * (dali/operators/audio/nonsilence_op.h:60-130). */
+void oracle_nonsilent_region(const float *in, int64_t n, float cutoff_db, float reference_power, int use_reference_power, int window_length,
+                             int reset_interval, int32_t *begin, int32_t *length) {
+  const int win = window_length < n ? window_length : (int)n;
+  const int64_t interval = reset_interval == -1 ? n : reset_interval;
+  float *mms = (float *)malloc(sizeof(float) * (size_t)n);
+  const float mean_factor = 1.0f / win;
+  int64_t win_begin = -(int64_t)win + 1;
+  for (int64_t out_pos = 0; out_pos < n;) {
+    float sumsq = 0;
+    for (int64_t pos = win_begin > 0 ? win_begin : 0; pos < out_pos; pos++) sumsq += in[pos] * in[pos];
+    const int64_t interval_end = out_pos + interval < n ? out_pos + interval : n;
+    for (; out_pos < interval_end; out_pos++, win_begin++) {
+      sumsq += in[out_pos] * in[out_pos];
+      mms[out_pos] = sumsq * mean_factor;
+      if (win_begin >= 0) sumsq -= in[win_begin] * in[win_begin];
+    }
+  }
+  float ref = reference_power;
+  if (!use_reference_power) { ref = mms[0]; for (int64_t i = 1; i < n; i++) if (mms[i] > ref) ref = mms[i]; }
+  const float cutoff = ref * powf(10.0f, cutoff_db * (1.0f / 10.0f));
+  int64_t end = n, b = n, first = 0, second = 0;
+  for (int64_t i = 0; i < end; i++) if (mms[i] >= cutoff) { b = i; break; }
+  if (b != end) {
+    for (int64_t i = end - 1; i >= b; i--) if (mms[i] >= cutoff) { end = i; break; }
+    first = b; second = end - b + 1;
+  }
+  if (first != 0 && second != 0) {
+    int64_t ns = first - (win - 1); if (ns < 0) ns = 0;
+    second += first - ns; first = ns;
+  }
+  *begin = (int32_t)first; *length = (int32_t)second;
+  free(mms);
+}
+
+/* AudioResample, float -> float: dali/kernels/signal/resampling.h:36-100 (Hann-windowed sinc, linearly interpolated lookup) and
+ * resampling_cpu.cc:120-230 (one channel: four SSE partial sums over taps i0 + l + 4k combined as (f0 + f2) + (f1 + f3), then the
+ * scalar tail; several channels: taps in order).  quality -> lobes: dali/operators/audio/resampling_params.h:27-30. */
+typedef struct { float scale, center; int lobes, size; float *lookup; } rs_window;
+
+static float rs_sincf(float x) {                                       /* math_util.h:188-193 */
+  x *= M_PI;
+  if (fabsf(x) < 1e-5f) return 1.0f - x * x * (1.0f / 6);
+  return sinf(x) / x;
+}
+static float rs_eval(const rs_window *w, float x) {                    /* resampling.h:59-66 */
+  float fi = x * w->scale + w->center;
+  float floori = floorf(fi);
+  float di = fi - floori;
+  int i = (int)floori;
+  return w->lookup[i] + di * (w->lookup[i + 1] - w->lookup[i]);
+}
+static float rs_eval_trunc(const rs_window *w, float x) {              /* resampling_cpu.cc:86-99 (cvttps: truncation) */
+  float fi = x * w->scale + w->center;
+  int i = (int)fi;
+  float di = fi - (float)i;
+  return w->lookup[i] + di * (w->lookup[i + 1] - w->lookup[i]);
+}
+
+int oracle_audio_resample(const float *in, int64_t n_in, int channels, double in_rate, double out_rate, int64_t n_out, float quality,
+                          float *out) {
+  rs_window w;
+  {
+    const double q = quality;
+    w.lobes = (int)round(0.007 * q * q - 0.09 * q + 3);
+    const int coeffs = w.lobes * 64 + 1;
+    const float scale = 2.0f * w.lobes / (coeffs - 1);
+    const float scale_envelope = 2.0f / coeffs;
+    const int center = (int)((coeffs - 1) * 0.5f);
+    w.size = coeffs + 5;
+    w.lookup = (float *)calloc((size_t)w.size, sizeof(float));
+    if (!w.lookup) return -1;
+    for (int i = 0; i < coeffs; i++) {
+      const float x = (i - center) * scale, y = (i - center) * scale_envelope;
+      w.lookup[i + 1] = (float)(rs_sincf(x) * (0.5 * (1 + cos((double)y * M_PI))));
+    }
+    w.center = (float)(center + 1);
+    w.scale = 1 / scale;
+  }
+  const int64_t block = 1 << 8;
+  const double scale = in_rate / out_rate;
+  const float fscale = (float)scale;
+  for (int64_t out_block = 0; out_block < n_out; out_block += block) {
+    const int64_t block_end = out_block + block < n_out ? out_block + block : n_out;
+    const double in_block_f = out_block * scale;
+    const int64_t in_block_i = (int64_t)floor(in_block_f);
+    float in_pos = (float)(in_block_f - in_block_i);
+    const float *inb = in + in_block_i * channels;
+    for (int64_t out_pos = out_block; out_pos < block_end; out_pos++, in_pos += fscale) {
+      const int xc = (int)ceilf(in_pos);
+      int i0 = xc - w.lobes, i1 = xc + w.lobes;
+      if (i0 + in_block_i < 0) i0 = (int)-in_block_i;
+      if (i1 + in_block_i > n_in) i1 = (int)(n_in - in_block_i);
+      if (channels == 1) {
+        int i = i0;
+        float f4[4] = {0, 0, 0, 0}, x4[4];
+        for (int l = 0; l < 4; l++) x4[l] = (float)(i + l) - in_pos;
+        for (; i + 3 < i1; i += 4)
+          for (int l = 0; l < 4; l++) {
+            const float wv = rs_eval_trunc(&w, x4[l]);
+            f4[l] = f4[l] + inb[i + l] * wv;
+            x4[l] = x4[l] + 4;
+          }
+        float f = (f4[0] + f4[2]) + (f4[1] + f4[3]);
+        float x = (float)i - in_pos;
+        for (; i < i1; i++, x++) f += inb[i] * rs_eval(&w, x);
+        out[out_pos] = f;
+      } else {
+        float tmp[16];
+        for (int c = 0; c < channels; c++) tmp[c] = 0;
+        float x = (float)i0 - in_pos;
+        for (int i = i0; i < i1; i++, x++) {
+          const float wv = rs_eval(&w, x);
+          for (int c = 0; c < channels; c++) tmp[c] += inb[(int64_t)i * channels + c] * wv;
+        }
+        for (int c = 0; c < channels; c++) out[out_pos * channels + c] = tmp[c];
+      }
+    }
+  }
+  free(w.lookup);
+  return 0;
+}

@@ -429,6 +429,46 @@ def ref_to_decibels(x, multiplier=10.0, reference=None, cutoff_db=-200.0):
     return out
 
 
+def to_decibels(x, multiplier=10.0, reference=None, cutoff_db=-200.0):
+    """oracle/audio_oracle.c restatement of ToDecibels; reference=None -> per-sample maximum."""
+    a = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(a)
+    lib().oracle_to_decibels(_p(a), C.c_int64(a.size), _p(out), C.c_float(multiplier), C.c_float(reference if reference is not None else 1.0),
+                             C.c_float(cutoff_db), int(reference is None))
+    return out
+
+
+def mfcc(mel, n_mfcc=20, dct_type=2, normalize=False, lifter=0.0):
+    """oracle/audio_oracle.c restatement of the DCT + liftering along axis 0 of [nfeat, ncols]."""
+    a = np.ascontiguousarray(mel, np.float32)
+    nfeat, ncols = a.shape
+    out = np.empty((min(n_mfcc, nfeat), ncols), np.float32)
+    rows = lib().oracle_mfcc(_p(a), nfeat, C.c_int64(ncols), _p(out), int(n_mfcc), int(dct_type), int(bool(normalize)), C.c_float(lifter))
+    assert rows == out.shape[0], rows
+    return out
+
+
+def nonsilent_region(x, cutoff_db=-60.0, window_length=2048, reference_power=None, reset_interval=8192):
+    """oracle/audio_oracle.c restatement of NonsilentRegion: (begin, length)."""
+    a = np.ascontiguousarray(x, np.float32)
+    b, l = C.c_int32(-1), C.c_int32(-1)
+    lib().oracle_nonsilent_region(_p(a), C.c_int64(a.size), C.c_float(cutoff_db), C.c_float(reference_power or 0.0), int(reference_power is not None),
+                                  int(window_length), int(reset_interval), C.byref(b), C.byref(l))
+    return b.value, l.value
+
+
+def audio_resample(x, in_rate, out_rate, quality=50.0, out_length=None):
+    """oracle/audio_oracle.c restatement of AudioResample (float -> float); x: [n] or [n, channels]."""
+    import math
+    a = np.ascontiguousarray(x, np.float32)
+    n_in, ch = a.shape[0], (a.shape[1] if a.ndim == 2 else 1)
+    n_out = int(out_length) if out_length is not None else int(math.ceil(n_in * float(out_rate) / float(in_rate)))
+    out = np.empty((n_out,) + a.shape[1:], np.float32)
+    rc = lib().oracle_audio_resample(_p(a), C.c_int64(n_in), ch, C.c_double(in_rate), C.c_double(out_rate), C.c_int64(n_out), C.c_float(quality), _p(out))
+    assert rc == 0
+    return out
+
+
 def ref_audio_resample(x, in_rate, out_rate, quality=50.0, out_length=None):
     """dali/kernels/signal/resampling_cpu.cc through ResamplerCPU (compiled reference); x: [n] or [n, channels] float32."""
     a = np.ascontiguousarray(x, np.float32)

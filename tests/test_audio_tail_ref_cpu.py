@@ -60,3 +60,32 @@ def test_to_decibels_and_mfcc_known_answers():
     m = np.full((8, 3), 2.0, np.float32)
     c = po.ref_mfcc(m, n_mfcc=4, dct_type=2, normalize=False)
     assert c.shape == (4, 3) and np.allclose(c[0], 8 * 2.0) and np.abs(c[1:]).max() < 1e-4
+
+
+def test_plain_c_restatements_equal_the_compiled_reference():
+    """oracle/audio_oracle.c (to_decibels, mfcc, nonsilent_region, audio_resample) against oracle/_ref, bit for bit, on random sweeps."""
+    rng = np.random.default_rng(21)
+    for it in range(6):
+        m = (np.abs(rng.normal(0, 1, (int(rng.integers(8, 90)), int(rng.integers(1, 70))))).astype(np.float32) ** 2) + 1e-12
+        for args in ((10.0, None, -200.0), (20.0, 0.5, -60.0), (10.0, 1.0, -80.0)):
+            assert np.array_equal(po.to_decibels(m, *args).view(np.uint32), po.ref_to_decibels(m, *args).view(np.uint32)), (it, args)
+        for n_mfcc, t, norm, lift in ((13, 2, True, 22.0), (40, 3, False, 0.0), (7, 1, False, 0.0), (20, 4, True, 5.0), (20, 2, False, 10.0)):
+            if t == 1 and m.shape[0] < 3:
+                continue
+            assert np.array_equal(po.mfcc(m, n_mfcc, t, norm, lift).view(np.uint32), po.ref_mfcc(m, n_mfcc, t, norm, lift).view(np.uint32)), (it, n_mfcc, t)
+    for n, lead, trail in ((40000, 6000, 9000), (16000, 0, 3000), (1000, 300, 200), (5000, 0, 0)):
+        x = (0.4 * np.sin(np.arange(n) * 0.05) + 0.05 * rng.normal(0, 1, n)).astype(np.float32)
+        x[:lead] = (1e-5 * rng.normal(0, 1, lead)).astype(np.float32)
+        if trail:
+            x[n - trail:] = (1e-5 * rng.normal(0, 1, trail)).astype(np.float32)
+        for kw in (dict(), dict(cutoff_db=-40.0, window_length=512, reset_interval=2048), dict(cutoff_db=-45.0, window_length=3000, reference_power=0.02,
+                                                                                              reset_interval=-1)):
+            assert po.nonsilent_region(x, **kw) == po.ref_nonsilent_region(x, **kw), (n, kw)
+    for n, ir, orr, q in ((16000, 16000.0, 44100.0, 50.0), (4001, 44100.0, 16000.0, 50.0), (700, 8000.0, 16000.0, 90.0), (25000, 22050.0, 8000.0, 10.0),
+                          (3000, 1.0, 0.37, 0.0)):
+        x = rng.uniform(-1, 1, n).astype(np.float32)
+        assert np.array_equal(po.audio_resample(x, ir, orr, q).view(np.uint32), po.ref_audio_resample(x, ir, orr, q).view(np.uint32)), (n, ir, orr, q)
+        st = rng.uniform(-1, 1, (n // 3, 2)).astype(np.float32)
+        assert np.array_equal(po.audio_resample(st, ir, orr, q).view(np.uint32), po.ref_audio_resample(st, ir, orr, q).view(np.uint32)), (n, "stereo")
+    x = rng.uniform(-1, 1, 5000).astype(np.float32)
+    assert np.array_equal(po.audio_resample(x, 5000.0, 1234.0, 50.0, out_length=1234), po.ref_audio_resample(x, 5000.0, 1234.0, 50.0, out_length=1234))

@@ -2213,3 +2213,48 @@ extern "C" int dalihTestRotateParams(float angle_deg, int in_h, int in_w, int ke
   dali::rotate_detail::Params(angle_deg, in_h, in_w, keep_size != 0, size_hw_or_null, out_hw[0], out_hw[1], m2x3);
   return 0;
 }
+
+// Test hooks (CPU): the crop-window and slice-window arithmetic of decoders.image_crop / crop / slice without a pipeline (no device
+// calls), for known answers of the reference's rules: CropAttr::CalculateAnchor (crop_attr.cc:224-239: anchor = round(pos * (in - crop)),
+// half away from zero, or truncation with rounding="truncate") and the slice attributes (slice_attr.h: std::llround of start / end).
+extern "C" int dalihTestCropWindow(float crop_h, float crop_w, float pos_y, float pos_x, int truncate, int H, int W, int64_t *yxhw) {
+  try {
+    dali::OpSpec spec("Crop");
+    spec.AddArg("crop_h", dali::MakeArg(crop_h)).AddArg("crop_w", dali::MakeArg(crop_w));
+    spec.AddArg("crop_pos_y", dali::MakeArg(pos_y)).AddArg("crop_pos_x", dali::MakeArg(pos_x));
+    spec.AddArg("rounding", dali::MakeArg(std::string(truncate ? "truncate" : "round")));
+    dali::CropWindowArgs c;
+    c.Init(spec, "Crop");
+    dali::Workspace ws;
+    c.Get(spec, ws, 0, H, W, yxhw[0], yxhw[1], yxhw[2], yxhw[3]);
+    return 0;
+  } catch (...) { return 1; }
+}
+
+// anchor / shape given per axis in (W, H) order like the operator's default `axis_names="WH"`; mode 0: absolute start + shape,
+// 1: relative start + relative shape, 2: absolute start + end, 3: relative start + relative end.  out = {y0, y1, x0, x1}.
+extern "C" int dalihTestSliceWindow(int mode, const float *a_wh, const float *b_wh, int H, int W, int64_t *out) {
+  try {
+    dali::OpSpec spec("Slice");
+    spec.AddArg("axis_names", dali::MakeArg(std::string("WH")));
+    spec.AddArg("normalized_anchor", dali::MakeArg(true)).AddArg("normalized_shape", dali::MakeArg(true));
+    const std::vector<float> a(a_wh, a_wh + 2), b(b_wh, b_wh + 2);
+    const char *an = (mode == 0 || mode == 2) ? "start" : "rel_start";
+    const char *bn = mode == 0 ? "shape" : mode == 1 ? "rel_shape" : mode == 2 ? "end" : "rel_end";
+    if (mode == 0 || mode == 2) {
+      spec.AddArg(an, dali::MakeArg(std::vector<int>{ static_cast<int>(a[0]), static_cast<int>(a[1]) }));
+      spec.AddArg(bn, dali::MakeArg(std::vector<int>{ static_cast<int>(b[0]), static_cast<int>(b[1]) }));
+    } else {
+      spec.AddArg(an, dali::MakeArg(a)).AddArg(bn, dali::MakeArg(b));
+    }
+    // one data input only: named arguments
+    spec.AddInput("data", "gpu");
+    dali::SliceArgs sl;
+    sl.Init(spec, "Slice");
+    dali::Workspace ws;
+    int64_t bgn[2], end[2];
+    sl.Get(spec, ws, 0, H, W, bgn, end);
+    out[0] = bgn[0]; out[1] = end[0]; out[2] = bgn[1]; out[3] = end[1];
+    return 0;
+  } catch (...) { return 1; }
+}

@@ -169,3 +169,43 @@ def test_random_crop_generator_matches_reference():
         h.dalihTestRandomCrop(C.c_int64(seed), si, H, W, C.c_float(ar[0]), C.c_float(ar[1]), C.c_float(area[0]), C.c_float(area[1]), na, 10, a)
         want = po.ref_random_crop(seed, si, H, W, ar, area, na, 10)
         assert [tuple(a[4 * k:4 * k + 4]) for k in range(10)] == want, (seed, si, H, W)
+
+
+def _host():
+    import ctypes as C
+    from dali_b200 import backend
+    return backend.lib(), C
+
+
+def test_crop_window_known_answers():
+    """CropAttr::CalculateAnchor (crop_attr.cc:224-239): anchor = round(pos * (in - crop)) with halves away from zero, or truncated
+    with rounding="truncate"; a zero crop extent keeps the whole axis."""
+    lib, C = _host()
+
+    def win(ch, cw, py, px, H, W, trunc=False):
+        out = (C.c_int64 * 4)()
+        assert lib.dalihTestCropWindow(C.c_float(ch), C.c_float(cw), C.c_float(py), C.c_float(px), int(trunc), H, W, out) == 0
+        return tuple(out)
+    assert win(224, 224, 0.5, 0.5, 256, 341) == (16, 59, 224, 224)           # 0.5 * 117 = 58.5 -> 59 (half away from zero)
+    assert win(224, 224, 0.5, 0.5, 256, 341, trunc=True) == (16, 58, 224, 224)
+    assert win(0, 100, 0.3, 1.0, 50, 200) == (0, 100, 50, 100)                # crop_h = 0: the whole axis, anchor 0
+    assert win(10, 10, 0.0, 0.25, 11, 13) == (0, 1, 10, 10)                   # round(0.25 * 3) = 1
+    assert win(3, 5, 1.0, 0.0, 3, 5) == (0, 0, 3, 5)
+
+
+def test_slice_window_known_answers():
+    """slice_attr.h (NamedSliceAttr): start / end from absolute or relative arguments in `axis_names` order ("WH"), rounded with
+    std::llround; rel_start + rel_shape are summed BEFORE the multiplication by the extent."""
+    lib, C = _host()
+
+    def sl(mode, a, b, H, W):
+        out = (C.c_int64 * 4)()
+        assert lib.dalihTestSliceWindow(mode, (C.c_float * 2)(*a), (C.c_float * 2)(*b), H, W, out) == 0
+        return tuple(out)                                                     # (y0, y1, x0, x1)
+    assert sl(0, (10, 20), (30, 40), 100, 200) == (20, 60, 10, 40)            # start + shape
+    assert sl(1, (0.1, 0.25), (0.5, 0.5), 100, 200) == (25, 75, 20, 120)      # rel_start, rel_shape
+    assert sl(2, (10, 20), (60, 70), 100, 200) == (20, 70, 10, 60)            # start, end
+    # float32(0.255) * 100 = 25.4999995 -> 25 and float32(0.755) * 100 = 75.4999995 -> 75 (the products are formed in double from the
+    # float arguments, as the reference does); 0.105f * 200 = 21.00000016 -> 21
+    assert sl(3, (0.105, 0.255), (0.6, 0.755), 100, 200) == (25, 75, 21, 120)
+    assert sl(1, (0.5, 0.5), (0.5, 0.5), 7, 9) == (4, 7, 5, 9)                # llround(3.5) = 4, llround(4.5) = 5: halves away from zero

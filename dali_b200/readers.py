@@ -188,20 +188,34 @@ class FileReader:
             path, lab = self.entries[idx]
             paths.append(path)
             labels.append(np.array([lab], np.int32))
+        pool = self._read_pool()
         if getattr(self, "_pin_ring", None) is None:
-            return [np.fromfile(p, dtype=np.uint8) for p in paths], labels
-        sizes = [os.path.getsize(p) for p in paths]
+            return list(pool.map(lambda p: np.fromfile(p, dtype=np.uint8), paths)), labels
+        sizes = list(pool.map(os.path.getsize, paths))
         offs = np.concatenate([[0], np.cumsum([(s + 63) & ~63 for s in sizes])])
         arena = self._arena(int(offs[-1]))
-        data = []
-        for p, s, o in zip(paths, sizes, offs[:-1]):
-            view = arena[int(o):int(o) + s]
+        views = [arena[int(o):int(o) + s] for s, o in zip(sizes, offs[:-1])]
+
+        def read(job):
+            p, s, view = job
             with open(p, "rb") as f:
-                got = f.readinto(memoryview(view))
+                got = f.readinto(memoryview(view))          # releases the GIL: the files of a batch are read concurrently
             if got != s:
                 raise IOError(f"short read from {p}: {got} of {s} bytes")
-            data.append(view)
-        return data, labels
+        list(pool.map(read, zip(paths, sizes, views)))
+        return views, labels
+
+    def _read_pool(self):
+        """File reads of a batch run on a small thread pool (the reference's loader reads ahead on its own thread; at 256 x 0.5 MB per
+        batch a sequential Python loop would cap the pipeline at ~10 k images/s)."""
+        if getattr(self, "_pool", None) is None:
+            import concurrent.futures as cf
+            try:
+                ncpu = len(os.sched_getaffinity(0))
+            except AttributeError:
+                ncpu = os.cpu_count() or 4
+            self._pool = cf.ThreadPoolExecutor(max_workers=max(2, min(16, ncpu)), thread_name_prefix="dali_b200_reader")
+        return self._pool
 
 
 class CoinFlip:

@@ -151,3 +151,23 @@ def test_shuffle_after_epoch_is_rank_independent_and_sticks_to_shard(tree):
         assert sorted(a + b) == list(range(10)), epoch                   # the two shards partition the data set in every epoch
     other = FileReader(5, tree, shuffle_after_epoch=True, shard_id=0, num_shards=2, shuffle_after_epoch_seed=99)
     assert _ids(other, 1) != _ids(FileReader(5, tree, shuffle_after_epoch=True, shard_id=0, num_shards=2), 1)
+
+
+def test_reader_arena_ring_keeps_batches_in_flight_intact(tree, monkeypatch):
+    """GPU pipelines read the files of a batch into a ring of page-locked arenas (one per batch in flight) that the mixed decoder copies
+    from by DMA; here the arena allocator is replaced by plain numpy memory to check the bookkeeping on the CPU: every sample is a view
+    of the batch's arena with the file's bytes, and the arenas of the last `num_buffers - 1` batches are not overwritten."""
+    from dali_b200 import capi
+    monkeypatch.setattr(capi, "pinned_empty", lambda n: np.zeros(max(1, int(n)), np.uint8))
+    r = FileReader(4, tree)
+    r.enable_pinned(3)
+    batches = [r() for _ in range(5)]
+    want = [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 0, 1], [2, 3, 4, 5], [6, 7, 8, 9]]
+    for b, (data, labels) in enumerate(batches):
+        assert len({d.base is None for d in data}) == 1 and all(d.base is not None for d in data)     # views of one arena
+    # the two most recent batches still hold their own bytes (ring of 3: the arena of batch 2 was reused by batch 5 - 3 = 2 ... only older ones)
+    for b in (3, 4):
+        assert [int(d[0]) for d in batches[b][0]] == want[b] and all(d.size == 4 for d in batches[b][0])
+    # batch 1's arena was recycled for batch 4 (1 + 3): its views now show batch 4's data -- which is why the ring must be as deep as the
+    # number of batches in flight + 1 (prefetch_queue_depth + 1 in fn.readers.file)
+    assert [int(d[0]) for d in batches[1][0]] == want[4]

@@ -165,10 +165,13 @@ def _readers_file(file_root=None, file_list=None, files=None, labels=None, *, ra
                         shard_id, num_shards, stick_to_shard, pad_last_batch, seed, shuffle_after_epoch_seed)
     inst = name or pipe._new_name("readers__File")
     g = _source_group(pipe, reader, 2, inst)
+    ahead = 2                                # batches read ahead of the pipeline on the reader's own thread
     if pipe.device_id is not None:
-        # GPU pipeline: page-locked reader buffers, borrowed by the decoder until the iteration completes (no_copy semantics)
-        reader.enable_pinned(pipe._depth + 1)
+        # GPU pipeline: page-locked reader buffers, borrowed by the decoder until the iteration completes (no_copy semantics); the
+        # ring covers the batches in flight in the pipeline, the ones queued by the read-ahead thread and the one being read
+        reader.enable_pinned(pipe._depth + 1 + ahead + 1)
         g.no_copy = True
+    reader.enable_prefetch(ahead)
     pipe._readers[inst] = reader
     return g.outputs[0], g.outputs[1]
 

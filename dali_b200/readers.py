@@ -181,7 +181,51 @@ class FileReader:
             self._pin_ring[k] = capi.pinned_empty(max(nbytes + nbytes // 4, 1 << 20))
         return self._pin_ring[k]
 
+    def enable_prefetch(self, ahead=2):
+        """Read `ahead` batches ahead of the consumer on a background thread (the reference's loader fills its queue on a thread of
+        its own, loader.h PrefetchWorker): file I/O then overlaps the GPU work instead of sitting on the thread that schedules the
+        pipeline.  The sequence of batches is unchanged -- the reader's state is only advanced by that one thread.  With page-locked
+        arenas the ring must hold the batches in flight in the pipeline, the `ahead` queued ones and the one being read."""
+        import queue
+        import threading
+        if getattr(self, "_q", None) is not None:
+            return
+        self._ahead = max(1, int(ahead))
+        self._q = queue.Queue(maxsize=self._ahead)
+        self._stop = False
+
+        def producer():
+            while not self._stop:
+                try:
+                    item = self._produce()
+                except BaseException as ex:          # surfaced on the consumer's thread
+                    item = ex
+                while not self._stop:
+                    try:
+                        self._q.put(item, timeout=0.2)
+                        break
+                    except queue.Full:
+                        continue
+                if isinstance(item, BaseException):
+                    return
+        self._thr = threading.Thread(target=producer, name="dali_b200_reader_prefetch", daemon=True)
+        self._thr.start()
+
+    def close(self):
+        self._stop = True
+
     def __call__(self, _iteration=None):
+        if getattr(self, "_q", None) is not None:
+            if getattr(self, "_dead", None) is not None:        # the read-ahead thread stopped at an error: keep reporting it
+                raise self._dead
+            item = self._q.get()
+            if isinstance(item, BaseException):
+                self._dead = item
+                raise item
+            return item
+        return self._produce()
+
+    def _produce(self):
         paths, labels = [], []
         for i in range(self.batch_size):
             idx = self._next_sample(i == 0)

@@ -171,3 +171,36 @@ def test_reader_arena_ring_keeps_batches_in_flight_intact(tree, monkeypatch):
     # batch 1's arena was recycled for batch 4 (1 + 3): its views now show batch 4's data -- which is why the ring must be as deep as the
     # number of batches in flight + 1 (prefetch_queue_depth + 1 in fn.readers.file)
     assert [int(d[0]) for d in batches[1][0]] == want[4]
+
+
+def test_reader_read_ahead_thread_with_arena_ring(tree, monkeypatch):
+    """The read-ahead thread may run `ahead` batches (+ the one it is reading) in front of the consumer; with the ring sized as
+    fn.readers.file does (depth + 1 + ahead + 1 arenas) a consumer that keeps `depth` batches in flight never sees an arena overwritten,
+    and the sequence of batches is the one of the synchronous reader."""
+    import time
+    from dali_b200 import capi
+    monkeypatch.setattr(capi, "pinned_empty", lambda n: np.zeros(max(1, int(n)), np.uint8))
+    depth, ahead = 2, 2
+    ref = FileReader(3, tree, random_shuffle=True, initial_fill=5, seed=4)
+    want = [[int(d[0]) for d in ref()[0]] for _ in range(12)]
+    r = FileReader(3, tree, random_shuffle=True, initial_fill=5, seed=4)
+    r.enable_pinned(depth + 1 + ahead + 1)
+    r.enable_prefetch(ahead)
+    inflight = []
+    for k in range(12):
+        inflight.append((k, r()[0]))
+        time.sleep(0.01)                                         # let the producer run as far ahead as it is allowed to
+        for kk, data in inflight[-depth:]:                       # the batches a pipeline of this depth still reads from
+            assert [int(d[0]) for d in data] == want[kk], (k, kk)
+    r.close()
+
+
+def test_reader_read_ahead_reports_io_errors_on_the_consumer(tree):
+    import os
+    r = FileReader(4, tree)
+    os.remove(os.path.join(tree, "b_dog", "img1.jpg"))            # file 5 disappears after discovery
+    r.enable_prefetch(2)
+    assert [int(d[0]) for d in r()[0]] == [0, 1, 2, 3]
+    for _ in range(2):                                            # the error is raised where the batch is consumed, and stays
+        with pytest.raises((FileNotFoundError, OSError)):
+            r()

@@ -23,7 +23,7 @@ EXPORTS = [
     "dalib200JpegPlanGetInfo", "dalib200JpegPlanStagedBytes", "dalib200JpegUpload", "dalib200JpegLaunch",
     "dalib200JpegGetStatus", "dalib200JpegDebugGetCoefficients", "dalib200JpegPlanSetupEx", "dalib200JpegPlanGetOutputShape",
     "dalib200JpegStatusAsync", "dalib200JpegStatusFetch", "dalib200JpegPlanGetPlanes", "dalib200JpegPlanSetPlanesOnly",
-    "dalib200JpegPlanSetSourceStable", "dalib200JpegPlanLastUploadDirect", "dalib200HostAlloc", "dalib200HostFree", "dalib200DebugCheckHalfConversion",
+    "dalib200JpegPlanSetSourceStable", "dalib200JpegPlanLastUploadDirect", "dalib200HostAlloc", "dalib200HostAllocOnDevice", "dalib200HostFree", "dalib200DebugCheckHalfConversion",
     "dalib200ResamplePlanSetupPlanar", "dalib200ResampleLaunchPlanar",
     "dalib200ResamplePlanCreate", "dalib200ResamplePlanDestroy", "dalib200ResamplePlanSetup", "dalib200ResampleLaunch",
     "dalib200ResamplePlanGetOrder",
@@ -129,9 +129,12 @@ def lib():
 
 
 class _PinnedBlock:
-    def __init__(self, nbytes):
+    def __init__(self, nbytes, device=None):
         p = C.c_void_p()
-        check(lib().dalib200HostAlloc(C.byref(p), C.c_size_t(nbytes)))
+        if device is None:
+            check(lib().dalib200HostAlloc(C.byref(p), C.c_size_t(nbytes)))
+        else:
+            check(lib().dalib200HostAllocOnDevice(C.byref(p), C.c_size_t(nbytes), int(device)))
         self.ptr, self.nbytes = p.value, nbytes
 
     def __del__(self):
@@ -141,12 +144,13 @@ class _PinnedBlock:
             pass
 
 
-def pinned_empty(nbytes):
+def pinned_empty(nbytes, device=None):
     """uint8 numpy array over page-locked host memory (freed with the last view).  Encoded streams held in such memory and fed
-    with external_source(no_copy=True) reach the decoder by DMA straight from here (dalib200JpegPlanSetSourceStable)."""
+    with external_source(no_copy=True) reach the decoder by DMA straight from here (dalib200JpegPlanSetSourceStable).
+    device: allocate with that GPU current (for threads whose current device differs, e.g. a reader's read-ahead thread)."""
     import numpy as np
     nbytes = max(1, int(nbytes))
-    blk = _PinnedBlock(nbytes)
+    blk = _PinnedBlock(nbytes, device)
     buf = (C.c_uint8 * nbytes).from_address(blk.ptr)
     buf._blk = blk                      # the numpy array keeps `buf` (its base) alive, `buf` keeps the allocation
     return np.frombuffer(buf, dtype=np.uint8)

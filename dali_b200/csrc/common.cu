@@ -131,6 +131,22 @@ int dalib200HostAlloc(void **ptr, size_t bytes) {
   return DALIB200_SUCCESS;
 }
 
+// The same for a caller thread whose current device is not the consumer's (e.g. a reader's read-ahead thread, whose thread-local
+// current device is still 0): the allocation is made with `device` current -- no context is created on another GPU as a side effect
+// -- and is portable (page-locked for every context).  The thread's current device is restored.
+int dalib200HostAllocOnDevice(void **ptr, size_t bytes, int device) {
+  DB_CHECK_ARG(ptr && device >= 0, "HostAllocOnDevice: bad arguments");
+  *ptr = nullptr;
+  if (bytes == 0) return DALIB200_SUCCESS;
+  int prev = -1;
+  const bool have_prev = cudaGetDevice(&prev) == cudaSuccess;
+  DB_CUDA(cudaSetDevice(device));
+  const cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+  if (have_prev && prev != device) cudaSetDevice(prev);
+  DB_CUDA(e);
+  return DALIB200_SUCCESS;
+}
+
 int dalib200HostFree(void *ptr) {
   if (ptr) DB_CUDA(cudaFreeHost(ptr));
   return DALIB200_SUCCESS;

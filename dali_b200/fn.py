@@ -169,7 +169,7 @@ def _readers_file(file_root=None, file_list=None, files=None, labels=None, *, ra
     if pipe.device_id is not None:
         # GPU pipeline: page-locked reader buffers, borrowed by the decoder until the iteration completes (no_copy semantics); the
         # ring covers the batches in flight in the pipeline, the ones queued by the read-ahead thread and the one being read
-        reader.enable_pinned(pipe._depth + 1 + ahead + 1)
+        reader.enable_pinned(pipe._depth + 1 + ahead + 1, pipe.device_id)
         g.no_copy = True
     reader.enable_prefetch(ahead)
     pipe._readers[inst] = reader

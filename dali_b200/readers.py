@@ -166,19 +166,22 @@ class FileReader:
         self.last = idx
         return idx
 
-    def enable_pinned(self, num_buffers):
+    def enable_pinned(self, num_buffers, device=None):
         """Read the files into a ring of page-locked arenas (one per batch in flight, `num_buffers` = prefetch depth + 1): the
         mixed decoder then copies the streams to the GPU by DMA straight from the reader's buffers, as the reference's readers
         feed its mixed operators from their own pinned buffers."""
         self._pin_ring = [None] * max(2, int(num_buffers))
         self._pin_next = 0
+        self._pin_device = device            # the arenas are allocated on the read-ahead thread: with THIS GPU current, not device 0
 
     def _arena(self, nbytes):
         from . import capi
         k = self._pin_next
         self._pin_next = (k + 1) % len(self._pin_ring)
         if self._pin_ring[k] is None or self._pin_ring[k].size < nbytes:
-            self._pin_ring[k] = capi.pinned_empty(max(nbytes + nbytes // 4, 1 << 20))
+            size = max(nbytes + nbytes // 4, 1 << 20)
+            dev = getattr(self, "_pin_device", None)
+            self._pin_ring[k] = capi.pinned_empty(size) if dev is None else capi.pinned_empty(size, dev)
         return self._pin_ring[k]
 
     def enable_prefetch(self, ahead=2):

@@ -130,6 +130,9 @@ int dalib200JpegPlanLastUploadDirect(const dalib200JpegPlan *plan);
 int dalib200DebugCheckHalfConversion(uint64_t *mismatches);
 /* Page-locked host memory for callers that want the direct path (cudaHostAlloc / cudaFreeHost behind the C ABI). */
 int dalib200HostAlloc(void **ptr, size_t bytes);
+/* The same from a thread whose current device is not the consumer's: allocated with `device` current (no context appears on another
+ * GPU as a side effect), page-locked for every context (cudaHostAllocPortable); the thread's current device is restored. */
+int dalib200HostAllocOnDevice(void **ptr, size_t bytes, int device);
 int dalib200HostFree(void *ptr);
 /* Enqueues the decode of the uploaded batch; out_ptrs[i] -> device buffer H*W*C of dtype (HWC, see ...GetOutputShape). */
 int dalib200JpegLaunch(dalib200JpegPlan *plan, void *const *out_ptrs, dalib200Stream_t stream);

@@ -197,15 +197,27 @@ class FileReader:
         self._q = queue.Queue(maxsize=self._ahead)
         self._stop = False
 
+        import weakref
+        ref, q = weakref.ref(self), self._q
+
         def producer():
-            while not self._stop:
+            # holds the reader only while a batch is being read: a reader dropped with its pipeline ends the thread (and frees its arenas)
+            while True:
+                r = ref()
+                if r is None or r._stop:
+                    return
                 try:
-                    item = self._produce()
+                    item = r._produce()
                 except BaseException as ex:          # surfaced on the consumer's thread
                     item = ex
-                while not self._stop:
+                del r
+                while True:
+                    r = ref()
+                    if r is None or r._stop:
+                        return
+                    del r
                     try:
-                        self._q.put(item, timeout=0.2)
+                        q.put(item, timeout=0.2)
                         break
                     except queue.Full:
                         continue

@@ -204,3 +204,24 @@ def test_reader_read_ahead_reports_io_errors_on_the_consumer(tree):
     for _ in range(2):                                            # the error is raised where the batch is consumed, and stays
         with pytest.raises((FileNotFoundError, OSError)):
             r()
+
+
+def test_reader_read_ahead_thread_ends_with_the_reader(tmp_path):
+    """The read-ahead thread holds the reader only while it reads a batch: dropping the reader (with its pipeline) ends the thread."""
+    import gc
+    import time
+    from dali_b200.readers import FileReader
+    (tmp_path / "a").mkdir()
+    for i in range(4):
+        (tmp_path / "a" / f"{i}.jpg").write_bytes(bytes([i]) * 10)
+    r = FileReader(2, file_root=str(tmp_path))
+    r.enable_prefetch(2)
+    r()
+    thr = r._thr
+    assert thr.is_alive()
+    del r
+    gc.collect()
+    t0 = time.time()
+    while thr.is_alive() and time.time() - t0 < 5:
+        time.sleep(0.05)
+    assert not thr.is_alive()

@@ -28,6 +28,8 @@ def _to_snake_case(name):
 
 
 _INPUT_DEVICE = {"mixed": "cpu", "cpu": "cpu", "gpu": "gpu"}
+# operators whose reference schema has a random seed argument (random_crop_attr.cc:34): unseeded ones draw from the pipeline's table
+_SEEDED_SCHEMAS = ("decoders__ImageRandomCrop", "RandomResizedCrop")
 
 
 def _make_wrapper(schema):
@@ -89,6 +91,12 @@ def _make_wrapper(schema):
         for o in outs:
             spec.add_output(o.name, o.device)
         pipe._nodes.append((schema, inst, spec))
+        # graph bookkeeping for the seed assignment (Pipeline._assign_seeds): inputs in the reference's order -- positional, then
+        # argument inputs sorted by name (ops/__init__.py:400-403) -- and whether the user left the seed open
+        arg_in = {k: v for k, v in kwargs.items() if isinstance(v, DataNode)}
+        user_seed = kwargs.get("seed")
+        pipe._op_graph[inst] = ([i.name for i in inputs] + [arg_in[k].name for k in sorted(arg_in)], [o.name for o in outs],
+                                schema in _SEEDED_SCHEMAS, not (isinstance(user_seed, int) and user_seed >= 0))
         return outs[0] if num_out == 1 else tuple(outs)
 
     op.__name__ = _to_snake_case(schema.split("__")[-1])
@@ -159,8 +167,6 @@ def _readers_file(file_root=None, file_list=None, files=None, labels=None, *, ra
         raise RuntimeError("fn.readers.file must be called inside a pipeline definition")
     if device != "cpu":
         raise ValueError("readers.file produces CPU batches")
-    if seed is None or seed < 0:
-        seed = pipe.seed if getattr(pipe, "seed", -1) not in (None, -1) else -1
     reader = FileReader(pipe.max_batch_size, file_root, file_list, files, labels, random_shuffle, shuffle_after_epoch, initial_fill,
                         shard_id, num_shards, stick_to_shard, pad_last_batch, seed, shuffle_after_epoch_seed)
     inst = name or pipe._new_name("readers__File")

@@ -318,7 +318,7 @@ static std::vector<RandomCropGenerator> MakeCropGeneratorsImpl(const OpSpec &spe
   DALI_ENFORCE(ar.size() == 2 && area.size() == 2, "random_aspect_ratio / random_area expect a scalar or a [min, max] pair");
   DALI_ENFORCE(ar[0] <= ar[1], "Provided empty range");
   DALI_ENFORCE(area[0] <= area[1], "Provided empty range");
-  int64_t seed = spec.GetArgument<int>("seed");
+  int64_t seed = spec.GetArgument<int64_t>("seed");
   if (seed < 0) seed = static_cast<int64_t>(time(nullptr));         // random_crop_attr.h:50-52
   return MakeRandomCropGenerators(max_batch, seed, ar.data(), area.data(), spec.GetArgument<int>("num_attempts"));
 }

@@ -144,6 +144,7 @@ class Pipeline:
         self._cur_slot = 0
         self._pending = []
         self._readers = {}          # reader instance name -> dali_b200.readers.FileReader
+        self._op_graph = {}         # operator instance -> (input names, output names, has a seed argument, seed left open)
 
     # ---- context management (with pipe: ...)
     def __enter__(self):
@@ -192,6 +193,7 @@ class Pipeline:
                 raise TypeError(f"Pipeline outputs must be DataNodes, got {type(o).__name__}")
         # prefetch_queue_depth independent executor slots (the reference's queue depth, exec2.h:66-131): while the GPU works on
         # batch i, the host parses / stages / uploads batch i+1 into the other slot.
+        self._assign_seeds()
         for schema, inst, spec in self._nodes:
             spec.add_arg("_state_key", f"{id(self)}:{inst}")       # operator instances of one node share their random state
         for _ in range(self._depth):
@@ -208,6 +210,56 @@ class Pipeline:
         self._keep = [[] for _ in self._slots]
         self._built = True
         return self
+
+    def _assign_seeds(self):
+        """Seeds of the operators the user did not seed, as the reference derives them: a table of 1024 values generated from the
+        pipeline seed (pipeline.cc:303-308; the clock when there is none), handed out in the order Pipeline::AddOperator sees the
+        operators that take a seed (pipeline.cc:823-831) -- the depth-first, inputs-first order from the outputs of
+        pipeline.py:2423-2463 _collect_ops; unreachable operators are pruned and take no seed."""
+        from . import readers
+        producers = {}
+        for schema, inst, spec in self._nodes:
+            for name in self._op_graph.get(inst, ((), (), False, False))[1]:
+                producers[name] = inst
+        for g in self._externals:
+            for o in g.outputs:
+                producers[o.name] = g
+        order, visited = [], set()
+
+        def visit(name):
+            prod = producers.get(name)
+            if prod is None:
+                return
+            key = prod if isinstance(prod, str) else id(prod)
+            if key in visited:
+                return
+            visited.add(key)
+            if isinstance(prod, str):
+                for n in self._op_graph[prod][0]:
+                    visit(n)
+            order.append(prod)
+        for o in self._outputs:
+            visit(o.name)
+        specs = {inst: spec for _, inst, spec in self._nodes}
+        table, k = None, 0
+        for prod in order:
+            if isinstance(prod, str):
+                _, _, seeded, open_seed = self._op_graph[prod]
+                if not (seeded and open_seed):
+                    continue
+            else:
+                src = prod.source
+                if not hasattr(src, "set_seed") or getattr(src, "seed", 0) >= 0:
+                    continue
+            if table is None:
+                base = self.seed if self.seed is not None and self.seed >= 0 else readers._clock_seed()
+                table = readers.seed_table(base)
+            if isinstance(prod, str):
+                specs[prod].add_arg("seed", int(table[k]))
+            else:
+                prod.source.set_seed(int(table[k]))
+            k = (k + 1) % len(table)
+        self._seed_order = [p if isinstance(p, str) else p.outputs[0].name for p in order]
 
     # ---- external source feeding (external_source.py:312-1150, _run_input_callbacks)
     def _next_batch(self, g):

@@ -13,18 +13,51 @@ Reference behaviour mirrored here:
                         `pad_last_batch` repeats the last sample until every shard has returned ceil(N / num_shards) samples
                         and the batch is full (loader.h:206-216, 262-283); without it batches simply run on into the next
                         epoch's samples.  `reader_meta()` has the reference's keys (pipeline.py reader_meta).
-  * shuffling           `random_shuffle`: a buffer of `initial_fill` samples from which a random one is returned and replaced
-                        by the next one read (loader.h:218-330); `shuffle_after_epoch`: the whole file list is re-shuffled
-                        with the seed + epoch before every epoch and sharding is by stick_to_shard (file_label_loader.h).
-                        The random ORDER is not the reference's (std::mt19937 streams cannot be reproduced from numpy); the
-                        distribution and the epoch / shard structure are.
-  * random.coin_flip / random.uniform   dali/operators/random/{coin_flip,uniform_distribution}_cpu.cc: one value (or `shape`)
-                        per sample, int32 for coin_flip, float32 for uniform (`range` continuous, `values` discrete).
+  * shuffling           `random_shuffle`: one global shuffle with the fixed data-loader seed, then a buffer of `initial_fill`
+                        samples from which a random one is returned and replaced by the next one read (loader.h:225-342);
+                        `shuffle_after_epoch`: the whole file list is re-shuffled with the seed + epoch before every epoch and
+                        sharding is by stick_to_shard (file_label_loader.h:198-241).  The ORDER is the reference's: the loader's
+                        state machine is restated in dali_b200/host/host_random.cc on the same C++ standard library engines and
+                        distributions the reference instantiates (dalihSampleOrder*).
+  * random.coin_flip / random.uniform   dali/operators/random/{coin_flip,uniform_distribution}.h, rng_base{,_cpu}.h, random_dist.h:
+                        Philox4x32-10 addressed by (seed, samples generated so far + 65537 * sample, 257 * element); int32 for
+                        coin_flip, float32 for uniform (`range` continuous, `values` discrete) -- the reference's numbers, bit
+                        for bit (dalihRandomCoinFlip / dalihRandomUniform; pinned by tests/test_random_ref_cpu.py).
+  * seeds               operators without a `seed` get theirs from the pipeline's seed table in the order the reference's
+                        Pipeline::AddOperator would see them (dali_b200/pipeline.py _assign_seeds; pipeline.cc:303-308,823-831).
 """
+import ctypes as C
 import math
 import os
+import time
 
 import numpy as np
+
+
+def _host():
+    """libdali_b200_host.so entry points of host_random.cc."""
+    from . import backend
+    L = backend.lib()
+    if not getattr(L, "_random_ready", False):
+        L.dalihRandomLastError.restype = C.c_char_p
+        L._random_ready = True
+    return L
+
+
+def _hcheck(rc):
+    if rc != 0:
+        raise RuntimeError(_host().dalihRandomLastError().decode("utf-8", "replace"))
+
+
+def seed_table(seed, n=1024):
+    """The per-operator seeds the reference's pipeline derives from its `seed` (pipeline.cc:303-308)."""
+    out = (C.c_int64 * n)()
+    _hcheck(_host().dalihSeedTable(C.c_int64(int(seed)), out, n))
+    return list(out)
+
+
+def _clock_seed():
+    return time.time_ns() & 0x7FFFFFFFFFFFFFFF
 
 KNOWN_EXTENSIONS = (".jpg", ".jpeg", ".png", ".bmp", ".tif", ".tiff", ".pnm", ".ppm", ".pgm", ".pbm", ".jp2", ".webp",
                     ".flac", ".ogg", ".wav")
@@ -100,20 +133,34 @@ class FileReader:
         self.stick_to_shard, self.pad_last_batch = bool(stick_to_shard or shuffle_after_epoch), pad_last_batch
         self.shuffle_after_epoch_seed = 524287 if shuffle_after_epoch_seed is None else int(shuffle_after_epoch_seed)
         self.initial_fill = max(1, int(initial_fill)) if random_shuffle else 1
-        self.seed = 524287 if seed is None or seed < 0 else int(seed)
-        self.rng = np.random.default_rng(self.seed)
-        self.order = list(range(len(self.entries)))
-        # read side: sequential position inside the (virtual) shard of the epoch being READ
-        self.read_epoch = 0
-        self.virtual_shard = shard_id
-        self._reshuffle()
-        self.cursor = start_index(self.virtual_shard, num_shards, len(self.entries))
-        self.read_in_shard = 0
-        # return side: the epoch whose samples are being RETURNED (the shuffle buffer lets the reads run ahead)
-        self.cur_epoch = 0
-        self.returned_in_epoch = 0
-        self.buffer = []                # (epoch tag, sample index), in read order
+        # the operator seed: the user's, else the pipeline's seed table (Pipeline.build -> set_seed), else the data-loader constant
+        self.seed = -1 if seed is None or seed < 0 else int(seed)
+        self._order = None              # dalihSampleOrder handle, created at the first read (the seed may be assigned until then)
         self.last = None
+
+    def set_seed(self, seed):
+        if self._order is not None:
+            raise RuntimeError("the reader has already started reading")
+        self.seed = int(seed)
+
+    def _order_handle(self):
+        if self._order is None:
+            h = C.c_void_p()
+            seed = 524287 if self.seed < 0 else self.seed
+            _hcheck(_host().dalihSampleOrderCreate(C.byref(h), C.c_int64(len(self.entries)), int(self.random_shuffle), int(self.initial_fill),
+                                                   C.c_int64(seed), int(self.shard_id), int(self.num_shards), int(self.stick_to_shard),
+                                                   int(bool(self.pad_last_batch)), int(self.shuffle_after_epoch),
+                                                   C.c_int64(self.shuffle_after_epoch_seed)))
+            self._order = h
+        return self._order
+
+    def __del__(self):
+        try:
+            if self._order is not None:
+                _host().dalihSampleOrderDestroy(self._order)
+                self._order = None
+        except Exception:
+            pass
 
     # ---- reference: reader_meta keys
     def meta(self):
@@ -122,49 +169,12 @@ class FileReader:
                 "number_of_shards": self.num_shards, "shard_id": self.shard_id, "pad_last_batch": self.pad_last_batch,
                 "stick_to_shard": self.stick_to_shard}
 
-    def _reshuffle(self):
-        if self.shuffle_after_epoch:
-            seed = (self.shuffle_after_epoch_seed + ((self.read_epoch + 1) << 32)) & 0xFFFFFFFFFFFFFFFF      # Reset(): ++epoch first
-            self.order = list(np.random.default_rng(seed).permutation(len(self.entries)))
-
-    def _shard_bounds(self, shard):
-        n = len(self.entries)
-        return start_index(shard, self.num_shards, n), start_index(shard + 1, self.num_shards, n)
-
-    def _read_one(self):
-        """Sequential read with the shard switch of loader.h (IncreaseReadSampleCounter / MoveToNextShard / Reset)."""
-        item = (self.read_epoch, self.order[self.cursor])
-        self.cursor += 1
-        self.read_in_shard += 1
-        lo, hi = self._shard_bounds(self.virtual_shard)
-        if self.read_in_shard >= hi - lo:                    # the shard has been read completely: next epoch
-            self.read_in_shard = 0
-            self.read_epoch += 1
-            if not self.stick_to_shard:
-                self.virtual_shard = (self.virtual_shard + 1) % self.num_shards
-            self._reshuffle()
-            self.cursor = self._shard_bounds(self.virtual_shard)[0]
-        return item
-
     def _next_sample(self, first_in_batch):
-        while len(self.buffer) < self.initial_fill:
-            self.buffer.append(self._read_one())
-        cand = [k for k, (t, _) in enumerate(self.buffer) if t == self.cur_epoch]
-        if not cand:
-            # the epoch's samples are exhausted.  pad_last_batch (loader.h ShouldPadBatch): repeat the last sample until every
-            # shard has returned ceil(N / num_shards) samples AND the batch is complete
-            target = int(math.ceil(len(self.entries) / self.num_shards))
-            if self.pad_last_batch and (self.returned_in_epoch < target or not first_in_batch):
-                self.returned_in_epoch += 1
-                return self.last
-            self.cur_epoch += 1
-            self.returned_in_epoch = 0
-            cand = [k for k, (t, _) in enumerate(self.buffer) if t == self.cur_epoch]
-        k = cand[int(self.rng.integers(0, len(cand)))] if self.random_shuffle else cand[0]
-        idx = self.buffer.pop(k)[1]
-        self.returned_in_epoch += 1
-        self.last = idx
-        return idx
+        """Index (in discovery order) of the next returned sample: Loader<>::ReadOne, restated in host_random.cc."""
+        idx = C.c_int64()
+        _hcheck(_host().dalihSampleOrderNext(self._order_handle(), int(bool(first_in_batch)), C.byref(idx)))
+        self.last = int(idx.value)
+        return self.last
 
     def enable_pinned(self, num_buffers, device=None):
         """Read the files into a ring of page-locked arenas (one per batch in flight, `num_buffers` = prefetch depth + 1): the
@@ -189,15 +199,15 @@ class FileReader:
         its own, loader.h PrefetchWorker): file I/O then overlaps the GPU work instead of sitting on the thread that schedules the
         pipeline.  The sequence of batches is unchanged -- the reader's state is only advanced by that one thread.  With page-locked
         arenas the ring must hold the batches in flight in the pipeline, the `ahead` queued ones and the one being read."""
+        if getattr(self, "_ahead", None) is None:
+            self._ahead = max(1, int(ahead))            # the thread starts with the first batch request (the seed may still be assigned)
+
+    def _start_prefetch(self):
         import queue
         import threading
-        if getattr(self, "_q", None) is not None:
-            return
-        self._ahead = max(1, int(ahead))
+        import weakref
         self._q = queue.Queue(maxsize=self._ahead)
         self._stop = False
-
-        import weakref
         ref, q = weakref.ref(self), self._q
 
         def producer():
@@ -230,6 +240,8 @@ class FileReader:
         self._stop = True
 
     def __call__(self, _iteration=None):
+        if getattr(self, "_ahead", None) is not None and getattr(self, "_q", None) is None:
+            self._start_prefetch()
         if getattr(self, "_q", None) is not None:
             if getattr(self, "_dead", None) is not None:        # the read-ahead thread stopped at an error: keep reporting it
                 raise self._dead
@@ -277,27 +289,67 @@ class FileReader:
         return self._pool
 
 
-class CoinFlip:
+class _RandomSource:
+    """Common part of the random number generators (rng_base.h OperatorWithRng): a master Philox state keyed by the operator seed whose
+    sequence counter advances by the batch size after every iteration (:143-145)."""
+
+    def __init__(self, batch_size, shape, seed, dtype):
+        self.batch_size, self.shape, self.dtype = int(batch_size), shape, np.dtype(dtype)
+        self.seed = -1 if seed is None or seed < 0 else int(seed)
+        self._sequence = 0
+        self._started = False
+
+    def set_seed(self, seed):
+        if self._started:
+            raise RuntimeError("the generator has already produced numbers")
+        self.seed = int(seed)
+
+    def _begin(self):
+        if not self._started:
+            if self.seed < 0:
+                self.seed = _clock_seed()               # the reference seeds an unseeded pipeline from the clock (pipeline.cc:303)
+            self._started = True
+        shp = tuple(int(v) for v in self.shape) if self.shape is not None else ()
+        outs = [np.empty(shp, self.dtype) for _ in range(self.batch_size)]
+        vols = (C.c_int64 * self.batch_size)(*[o.size for o in outs])
+        ptrs = (C.c_void_p * self.batch_size)(*[o.ctypes.data for o in outs])
+        return outs, vols, ptrs
+
+    def _end(self):
+        self._sequence += self.batch_size
+
+
+class CoinFlip(_RandomSource):
     def __init__(self, batch_size, probability=0.5, shape=None, seed=-1, dtype=np.int32):
-        self.batch_size, self.p, self.shape, self.dtype = batch_size, float(probability), shape, dtype
-        self.rng = np.random.default_rng(None if seed is None or seed < 0 else seed)
+        super().__init__(batch_size, shape, seed, dtype)
+        self.p = float(probability)
 
     def __call__(self, _iteration=None):
-        shp = tuple(self.shape) if self.shape is not None else ()
-        return [np.asarray(self.rng.random(shp) < self.p, self.dtype) for _ in range(self.batch_size)]
+        from . import types
+        outs, vols, ptrs = self._begin()
+        prob = (C.c_float * self.batch_size)(*([self.p] * self.batch_size))
+        _hcheck(_host().dalihRandomCoinFlip(C.c_int64(self.seed), C.c_uint64(self._sequence), self.batch_size, vols, prob,
+                                            int(types.from_numpy_type(self.dtype)), ptrs))
+        self._end()
+        return outs
 
 
-class Uniform:
+class Uniform(_RandomSource):
     def __init__(self, batch_size, range=(-1.0, 1.0), values=None, shape=None, seed=-1, dtype=np.float32):
-        self.batch_size, self.shape, self.dtype = batch_size, shape, dtype
-        self.values = None if values is None else np.asarray(values, dtype)
+        super().__init__(batch_size, shape, seed, dtype)
+        self.values = None if values is None else np.ascontiguousarray(np.asarray(values, np.float32).ravel())
         self.lo, self.hi = float(range[0]), float(range[1])
         if self.values is None and not self.lo < self.hi:
-            raise ValueError(f"Invalid range. It shall be left-closed [a, b), where a < b. Got: [{self.lo}, {self.hi})")
-        self.rng = np.random.default_rng(None if seed is None or seed < 0 else seed)
+            raise ValueError(f"Invalid range [{self.lo}, {self.hi}).")
 
     def __call__(self, _iteration=None):
-        shp = tuple(self.shape) if self.shape is not None else ()
+        from . import types
+        outs, vols, ptrs = self._begin()
         if self.values is not None:
-            return [np.asarray(self.values[self.rng.integers(0, len(self.values), shp)], self.dtype) for _ in range(self.batch_size)]
-        return [np.asarray(self.rng.uniform(self.lo, self.hi, shp), self.dtype) for _ in range(self.batch_size)]
+            rng, vals, nvals = None, self.values.ctypes.data_as(C.POINTER(C.c_float)), int(self.values.size)
+        else:
+            rng, vals, nvals = (C.c_float * (2 * self.batch_size))(*([self.lo, self.hi] * self.batch_size)), None, 0
+        _hcheck(_host().dalihRandomUniform(C.c_int64(self.seed), C.c_uint64(self._sequence), self.batch_size, vols, rng, vals,
+                                           C.c_int64(nvals), int(types.from_numpy_type(self.dtype)), ptrs))
+        self._end()
+        return outs

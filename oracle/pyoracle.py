@@ -518,3 +518,31 @@ def ref_brightness_contrast(img, brightness=1.0, brightness_shift=0.0, contrast=
     ref().ref_brightness_contrast(_p(a), C.c_size_t(a.size), int(bool(out_float)), C.c_float(brightness), C.c_float(brightness_shift),
                                   C.c_float(contrast), C.c_float(contrast_center), _p(out))
     return out
+
+
+# ---- reference random number operators (oracle/ref_random_shim.cc); only with oracle/_ref
+def ref_random_coin_flip(seed, iterations, batch, volume, probability, dtype=np.int32):
+    code = {np.dtype(np.int32): 6, np.dtype(np.uint8): 0}[np.dtype(dtype)]
+    out = np.empty((iterations, batch, volume), dtype)
+    rc = ref().ref_random_coin_flip(C.c_int64(seed), iterations, batch, C.c_int64(volume), C.c_float(probability), code,
+                                        out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out
+
+
+def ref_random_uniform(seed, iterations, batch, volume, rng=(-1.0, 1.0), values=None, dtype=np.float32):
+    code = {np.dtype(np.uint8): 0, np.dtype(np.int16): 5, np.dtype(np.int32): 6, np.dtype(np.int64): 7, np.dtype(np.float32): 9,
+            np.dtype(np.float64): 10}[np.dtype(dtype)]
+    out = np.empty((iterations, batch, volume), dtype)
+    vals = None if values is None else np.ascontiguousarray(values, np.float32)
+    rc = ref().ref_random_uniform(C.c_int64(seed), iterations, batch, C.c_int64(volume), C.c_float(rng[0]), C.c_float(rng[1]),
+                                      None if vals is None else vals.ctypes.data_as(C.c_void_p), C.c_int64(0 if vals is None else vals.size),
+                                      code, out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out
+
+
+def ref_philox(key, sequence, offset, n):
+    out = np.empty(n, np.uint32)
+    ref().ref_philox(C.c_uint64(key), C.c_uint64(sequence), C.c_uint64(offset), n, out.ctypes.data_as(C.c_void_p))
+    return out

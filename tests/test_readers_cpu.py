@@ -72,8 +72,15 @@ def test_shuffling_is_a_permutation_per_epoch(tree):
         assert a[0] + a[1] != list(range(10)) and a[0] + a[1] != a[2] + a[3]
         b = _ids(FileReader(5, tree, **kw), 6)
         assert a == b                                                    # deterministic for a given seed
-    sh = _ids(FileReader(3, tree, shard_id=1, num_shards=2, stick_to_shard=True, random_shuffle=True, initial_fill=100, seed=1, pad_last_batch=True), 4)
-    assert sorted(sh[0] + sh[1][:2]) == [5, 6, 7, 8, 9] and sh[1][2] == sh[1][1]      # shard [5, 10) once, then the pad
+    # random_shuffle shuffles the file list once with a seed every rank shares (file_label_loader.h:200-205): the shards are ranges
+    # [5 k, 5 k + 5) of THAT list, so they still partition the data set whatever the per-rank seeds are
+    kw = dict(num_shards=2, stick_to_shard=True, random_shuffle=True, initial_fill=100, pad_last_batch=True)
+    sh = [_ids(FileReader(3, tree, shard_id=k, seed=1 + k, **kw), 4) for k in range(2)]
+    parts = [sorted(x[0] + x[1][:2]) for x in sh]
+    assert sorted(parts[0] + parts[1]) == list(range(10)) and parts[0] != [0, 1, 2, 3, 4]
+    for x in sh:
+        assert x[1][2] == x[1][1]                                            # each shard once, then the pad
+        assert sorted(x[2] + x[3][:2]) == sorted(x[0] + x[1][:2])            # stick_to_shard: the same files in the next epoch
 
 
 def test_random_generators():
@@ -225,3 +232,43 @@ def test_reader_read_ahead_thread_ends_with_the_reader(tmp_path):
     while thr.is_alive() and time.time() - t0 < 5:
         time.sleep(0.05)
     assert not thr.is_alive()
+
+
+def test_shuffle_orders_are_the_standard_library_shuffles_the_reference_calls(tree, tmp_path):
+    """random_shuffle = std::shuffle(entries, std::mt19937(524287)) once (file_label_loader.h:200-205); with initial_fill = 1 the
+    buffer holds one sample, so the reader returns exactly that order.  shuffle_after_epoch = std::shuffle with
+    std::mt19937_64(seed + (epoch << 32)), epoch counted from 1, applied to the order the previous epoch left (:229-240)."""
+    import shutil
+    import subprocess
+    cxx = shutil.which(os.environ.get("CXX", "g++"))
+    if cxx is None:
+        pytest.skip("no C++ compiler")
+    src = tmp_path / "s.cc"
+    src.write_text(r"""
+#include <algorithm>
+#include <cstdio>
+#include <numeric>
+#include <random>
+#include <vector>
+int main() {
+  std::vector<int> v(10);
+  std::iota(v.begin(), v.end(), 0);
+  std::mt19937 g(524287);
+  std::shuffle(v.begin(), v.end(), g);
+  for (int x : v) std::printf("%d ", x);
+  std::printf("\n");
+  std::iota(v.begin(), v.end(), 0);
+  for (unsigned long long epoch = 1; epoch <= 3; epoch++) {
+    std::mt19937_64 g64(77ull + (epoch << 32));
+    std::shuffle(v.begin(), v.end(), g64);
+    for (int x : v) std::printf("%d ", x);
+    std::printf("\n");
+  }
+}
+""")
+    subprocess.run([cxx, "-std=c++17", "-O1", str(src), "-o", str(tmp_path / "s")], check=True)
+    lines = [[int(t) for t in ln.split()] for ln in subprocess.run([str(tmp_path / "s")], check=True, capture_output=True, text=True).stdout.splitlines()]
+    got = _ids(FileReader(5, tree, random_shuffle=True, initial_fill=1, seed=5), 4)
+    assert got[0] + got[1] == lines[0] and got[2] + got[3] == lines[0]           # the same global order in every epoch
+    got = _ids(FileReader(5, tree, shuffle_after_epoch=True, shuffle_after_epoch_seed=77), 6)
+    assert [got[0] + got[1], got[2] + got[3], got[4] + got[5]] == lines[1:4]

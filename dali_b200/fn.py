@@ -159,7 +159,8 @@ def _source_group(pipe, source, n, base, layout=None, device="cpu"):
 
 def _readers_file(file_root=None, file_list=None, files=None, labels=None, *, random_shuffle=False, shuffle_after_epoch=False,
                   initial_fill=1024, shard_id=0, num_shards=1, stick_to_shard=False, pad_last_batch=False, seed=-1, name=None,
-                  device="cpu", shuffle_after_epoch_seed=None, **_ignored):
+                  device="cpu", shuffle_after_epoch_seed=None, file_filters=None, dir_filters=None, case_sensitive_filter=False,
+                  **_ignored):
     """fn.readers.file (dali/operators/reader/file_reader_op.cc, loader/file_label_loader.h): (encoded file bytes, label)."""
     from .readers import FileReader
     pipe = _current()
@@ -168,7 +169,8 @@ def _readers_file(file_root=None, file_list=None, files=None, labels=None, *, ra
     if device != "cpu":
         raise ValueError("readers.file produces CPU batches")
     reader = FileReader(pipe.max_batch_size, file_root, file_list, files, labels, random_shuffle, shuffle_after_epoch, initial_fill,
-                        shard_id, num_shards, stick_to_shard, pad_last_batch, seed, shuffle_after_epoch_seed)
+                        shard_id, num_shards, stick_to_shard, pad_last_batch, seed, shuffle_after_epoch_seed, file_filters, dir_filters,
+                        case_sensitive_filter)
     inst = name or pipe._new_name("readers__File")
     g = _source_group(pipe, reader, 2, inst)
     ahead = 2                                # batches read ahead of the pipeline on the reader's own thread

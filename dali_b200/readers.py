@@ -68,8 +68,21 @@ def start_index(shard_id, num_shards, size):
     return size * shard_id // num_shards
 
 
-def discover_files(file_root=None, file_list=None, files=None, labels=None):
-    """[(path, label)] in the reference's order."""
+KNOWN_EXTENSIONS_GLOB = tuple("*" + e for e in KNOWN_EXTENSIONS)          # utils.h:34-36 kKnownExtensionsGlob
+
+
+def _glob_match(name, filters, case_sensitive):
+    """fnmatch(3) of discover_files.cc:64-67,100-105 (FNM_CASEFOLD unless case_sensitive_filter)."""
+    import fnmatch
+    if not case_sensitive:
+        name = name.lower()
+    return any(fnmatch.fnmatchcase(name, f if case_sensitive else f.lower()) for f in filters)
+
+
+def discover_files(file_root=None, file_list=None, files=None, labels=None, file_filters=None, dir_filters=None,
+                   case_sensitive_filter=False):
+    """[(path, label)] in the reference's order (discover_files.cc:124-157: sub-directories sorted -> label, files sorted inside a
+    directory, `file_filters` / `dir_filters` globs; the filters are ignored with `file_list` / `files`, file_reader_op.cc:128-138)."""
     if files is not None:
         if file_list is not None:
             raise ValueError("`files` and `file_list` are mutually exclusive")
@@ -97,11 +110,17 @@ def discover_files(file_root=None, file_list=None, files=None, labels=None):
     if file_root is None:
         raise ValueError("One of `file_root`, `file_list` or `files` is required")
     out = []
-    classes = sorted(d for d in os.listdir(file_root) if os.path.isdir(os.path.join(file_root, d)))
+    if isinstance(file_filters, str):
+        file_filters = [file_filters]
+    if isinstance(dir_filters, str):
+        dir_filters = [dir_filters]
+    file_filters = list(file_filters) if file_filters else list(KNOWN_EXTENSIONS_GLOB)
+    classes = sorted(d for d in os.listdir(file_root) if os.path.isdir(os.path.join(file_root, d))
+                     and (not dir_filters or _glob_match(d, dir_filters, case_sensitive_filter)))
     for label, d in enumerate(classes):
         for f in sorted(os.listdir(os.path.join(file_root, d))):
             p = os.path.join(file_root, d, f)
-            if os.path.isfile(p) and f.lower().endswith(KNOWN_EXTENSIONS):
+            if os.path.isfile(p) and _glob_match(f, file_filters, case_sensitive_filter):
                 out.append((p, label))
     return out
 
@@ -111,14 +130,14 @@ class FileReader:
 
     def __init__(self, batch_size, file_root=None, file_list=None, files=None, labels=None, random_shuffle=False,
                  shuffle_after_epoch=False, initial_fill=1024, shard_id=0, num_shards=1, stick_to_shard=False, pad_last_batch=False,
-                 seed=-1, shuffle_after_epoch_seed=None):
+                 seed=-1, shuffle_after_epoch_seed=None, file_filters=None, dir_filters=None, case_sensitive_filter=False):
         if not (0 <= shard_id < num_shards):
             raise ValueError("num_shards needs to be greater than shard_id")
         if random_shuffle and shuffle_after_epoch:
             raise ValueError("shuffle_after_epoch and random_shuffle cannot be both true")
         if shuffle_after_epoch and stick_to_shard:
             raise ValueError("shuffle_after_epoch and stick_to_shard cannot be both true")
-        self.entries = discover_files(file_root, file_list, files, labels)
+        self.entries = discover_files(file_root, file_list, files, labels, file_filters, dir_filters, case_sensitive_filter)
         if not self.entries:
             raise RuntimeError("No files found.")
         if num_shards > len(self.entries):

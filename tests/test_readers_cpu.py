@@ -48,6 +48,18 @@ def test_discovery_order_labels_and_lists(tree, tmp_path):
     assert discover_files(files=["a.jpg"], labels=[5], file_root="/r") == [("/r/a.jpg", 5)]
     with pytest.raises(ValueError):
         discover_files(files=["a"], labels=[1, 2])
+    # file_filters / dir_filters / case_sensitive_filter (file_reader_op.cc:128-138, discover_files.cc:40-110): globs, matched
+    # case-insensitively by default; labels are the indices of the directories that PASSED the filter
+    os.rename(os.path.join(tree, "b_dog", "img1.jpg"), os.path.join(tree, "b_dog", "IMG1.JPG"))
+    rel = lambda es: [(os.path.relpath(p, tree), l) for p, l in es]
+    assert ("b_dog/IMG1.JPG", 1) in rel(discover_files(tree))
+    assert ("b_dog/IMG1.JPG", 1) not in rel(discover_files(tree, case_sensitive_filter=True))
+    assert rel(discover_files(tree, file_filters=["*.txt"])) == [("a_cat/notes.txt", 0)]
+    assert rel(discover_files(tree, file_filters=["img0.*", "*2.jpg"], dir_filters=["?_[cd]*"])) == [
+        ("a_cat/img0.jpg", 0), ("a_cat/img2.jpg", 0), ("b_dog/img0.jpg", 1), ("b_dog/img2.jpg", 1)]
+    assert rel(discover_files(tree, dir_filters=["C_*"])) == [("c_eel/img0.jpg", 0), ("c_eel/img1.jpg", 0), ("c_eel/img2.jpg", 0)]
+    assert discover_files(tree, dir_filters=["C_*"], case_sensitive_filter=True) == []
+    os.rename(os.path.join(tree, "b_dog", "IMG1.JPG"), os.path.join(tree, "b_dog", "img1.jpg"))
 
 
 def test_sharding_rotation_and_padding(tree):

@@ -12,7 +12,7 @@ __version__ = "0.1.0"
 def __getattr__(name):
     # lazy: importing the package must not require the native libraries (build() imports it before they exist)
     import importlib
-    if name in ("fn", "types", "pipeline", "backend", "capi", "hotpath", "plugin", "sharding", "plugin_manager", "readers"):
+    if name in ("fn", "types", "pipeline", "backend", "capi", "hotpath", "plugin", "sharding", "plugin_manager", "readers", "ops"):
         return importlib.import_module(f"{__name__}.{name}")
     if name in ("Pipeline", "pipeline_def", "DataNode"):
         return getattr(importlib.import_module(f"{__name__}.pipeline"), name)

@@ -180,9 +180,12 @@ class Pipeline:
     def build(self):
         if self._built:
             return self
-        if self._definition is not None and not self._outputs:
+        definition = self._definition
+        if definition is None and not self._outputs and callable(getattr(self, "define_graph", None)):
+            definition = self.define_graph              # legacy subclass style (pipeline.py: Pipeline.define_graph)
+        if definition is not None and not self._outputs:
             with self:
-                outs = self._definition()
+                outs = definition()
             if isinstance(outs, DataNode):
                 outs = (outs,)
             self._outputs = list(outs)
@@ -316,6 +319,8 @@ class Pipeline:
 
     def _run_input_callbacks(self, slot):
         self._cur_slot = slot
+        if callable(getattr(self, "iter_setup", None)):
+            self.iter_setup()                           # legacy hook: the subclass calls feed_input() here, once per iteration
         for g in self._externals:
             if g.source is None:
                 continue

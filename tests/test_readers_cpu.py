@@ -284,3 +284,43 @@ int main() {
     assert got[0] + got[1] == lines[0] and got[2] + got[3] == lines[0]           # the same global order in every epoch
     got = _ids(FileReader(5, tree, shuffle_after_epoch=True, shuffle_after_epoch_seed=77), 6)
     assert [got[0] + got[1], got[2] + got[3], got[4] + got[5]] == lines[1:4]
+
+
+def test_legacy_ops_api_define_graph_and_iter_setup(tree):
+    """nvidia.dali.ops object API + Pipeline subclass with define_graph() / iter_setup() (the style of the reference's older examples):
+    the classes forward to the same functional wrappers, so the graph -- and the numbers for a given seed -- are those of fn.*."""
+    from dali_b200 import Pipeline, ops
+    import nvidia.dali.ops as nv_ops
+    assert nv_ops is ops and ops.decoders.Image is not None and ops.ImageDecoder._fn_name == "decoders.image"
+    assert {"Resize", "CropMirrorNormalize", "WarpAffine", "Hsv", "Spectrogram", "MelFilterBank", "FileReader", "ExternalSource"} <= set(dir(ops))
+
+    class Legacy(Pipeline):
+        def __init__(self):
+            super().__init__(batch_size=4, num_threads=1, device_id=None, seed=21)
+            self.reader = ops.readers.File(file_root=tree, name="Reader")
+            self.flip = ops.random.CoinFlip(probability=0.3)
+            self.src = ops.ExternalSource()
+            self.fed = 0
+
+        def define_graph(self):
+            data, label = self.reader()
+            self.extra = self.src()
+            return data, label, self.flip(), self.extra
+
+        def iter_setup(self):
+            self.feed_input(self.extra, [np.full((2,), self.fed, np.int32)] * 4)
+            self.fed += 1
+
+    @pipeline_def(batch_size=4, num_threads=1, device_id=None, seed=21)
+    def functional():
+        data, label = fn.readers.file(file_root=tree, name="Reader")
+        return data, label, fn.random.coin_flip(probability=0.3)
+    a, b = Legacy(), functional()
+    a.build()
+    assert a.reader_meta("Reader")["epoch_size"] == 10
+    for it in range(3):
+        oa, ob = a.run(), b.run()
+        for k in range(3):
+            for i in range(4):
+                assert np.array_equal(np.asarray(oa[k].at(i)), np.asarray(ob[k].at(i))), (it, k, i)
+        assert all(int(np.asarray(oa[3].at(i))[0]) == it for i in range(4))

@@ -210,7 +210,12 @@ class FileReader:
         if self._pin_ring[k] is None or self._pin_ring[k].size < nbytes:
             size = max(nbytes + nbytes // 4, 1 << 20)
             dev = getattr(self, "_pin_device", None)
-            self._pin_ring[k] = capi.pinned_empty(size) if dev is None else capi.pinned_empty(size, dev)
+            try:
+                self._pin_ring[k] = capi.pinned_empty(size) if dev is None else capi.pinned_empty(size, dev)
+            except capi.DaliB200Error:
+                if dev is None:
+                    raise
+                self._pin_ring[k] = capi.pinned_empty(size)         # still page-locked, allocated under the thread's current device
         return self._pin_ring[k]
 
     def enable_prefetch(self, ahead=2):

@@ -15,8 +15,13 @@
 #include "dali/operators/image/crop/random_crop_attr.h"
 #include "dali/operators/image/resize/resampling_attr.h"
 #include "dali/operators/image/resize/resize_attr.h"
+#include "dali/operators/audio/mfcc/mfcc.h"
 #include "dali/operators/audio/nonsilence_op.h"
 #include "dali/operators/audio/resample.h"
+#include "dali/operators/generic/flip.h"
+#include "dali/operators/image/color/brightness_contrast.h"
+#include "dali/operators/image/color/color_twist.h"
+#include "dali/operators/signal/decibel/to_decibels_op.h"
 #include "dali/pipeline/operator/operator.h"
 
 #include "dali_b200.h"
@@ -551,6 +556,300 @@ class NonsilentRegion : public NonsilenceOperator<GPUBackend> {
   dalib200SignalPlan *plan_ = nullptr;
 };
 
+// ------------------------------------------------------------------------------------------------ ColorTwist / BrightnessContrast
+// Both sit on the reference's OWN operator bases: ColorTwistBase composes the 3x3 matrix and offset per sample (color_twist.h:128-170),
+// BrightnessContrastOp acquires the arguments and folds them into multiplier / addend (brightness_contrast.h:78-131); only RunImpl
+// -- the kernel call -- is replaced.
+class ColorTwist : public ColorTwistBase<GPUBackend> {
+ public:
+  explicit ColorTwist(const OpSpec &spec) : ColorTwistBase<GPUBackend>(spec) {
+    Check(dalib200PointwisePlanCreate(&plan_, max_batch_size_), "ColorTwist");
+  }
+  ~ColorTwist() override { dalib200PointwisePlanDestroy(plan_); }
+
+ protected:
+  using SequenceOperator<GPUBackend, StatelessOperator>::RunImpl;
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    DALI_ENFORCE(in.type() == DALI_UINT8 && (output_type_ == DALI_UINT8 || output_type_ == DALI_FLOAT),
+                 "b200.color_twist: uint8 input, uint8 or float output");
+    const int n = in.num_samples();
+    std::vector<dalib200ColorSample> cs(n);
+    for (int i = 0; i < n; i++) {
+      cs[i].num_pixels = in.tensor_shape(i).num_elements() / 3;
+      for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) cs[i].matrix[3 * r + c] = tmatrices_[i](r, c);
+        cs[i].offset[r] = toffsets_[i][r];
+      }
+    }
+    Check(dalib200LinearTransformSetup(plan_, n, cs.data(), output_type_ == DALI_FLOAT ? DALIB200_FLOAT : DALIB200_UINT8), "ColorTwist");
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200PointwiseLaunch(plan_, ip.data(), op.data(), ws.stream()), "ColorTwist");
+  }
+
+ private:
+  dalib200PointwisePlan *plan_ = nullptr;
+};
+
+class BrightnessContrast : public BrightnessContrastOp<GPUBackend> {
+ public:
+  explicit BrightnessContrast(const OpSpec &spec) : BrightnessContrastOp<GPUBackend>(spec) {
+    Check(dalib200GenericPlanCreate(&plan_, max_batch_size_), "BrightnessContrast");
+  }
+  ~BrightnessContrast() override { dalib200GenericPlanDestroy(plan_); }
+
+ protected:
+  using Base::RunImpl;
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    DALI_ENFORCE(input_type_ == DALI_UINT8 && (output_type_ == DALI_UINT8 || output_type_ == DALI_FLOAT),
+                 "b200.brightness_contrast: uint8 input, uint8 or float output");
+    const int n = in.num_samples();
+    const auto &center = GetContrastCenter<uint8_t>(ws, n);
+    std::vector<int64_t> vol(n);
+    std::vector<float> mul(n), add(n);
+    for (int i = 0; i < n; i++) {
+      vol[i] = in.tensor_shape(i).num_elements();
+      if (output_type_ == DALI_FLOAT) OpArgsToKernelArgs<float, uint8_t>(add[i], mul[i], brightness_[i], brightness_shift_[i], contrast_[i], center[i]);
+      else OpArgsToKernelArgs<uint8_t, uint8_t>(add[i], mul[i], brightness_[i], brightness_shift_[i], contrast_[i], center[i]);
+    }
+    Check(dalib200MultiplyAddSetup(plan_, n, vol.data(), mul.data(), add.data(), output_type_ == DALI_FLOAT ? DALIB200_FLOAT : DALIB200_UINT8),
+          "BrightnessContrast");
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200GenericLaunch(plan_, ip.data(), op.data(), ws.stream()), "BrightnessContrast");
+  }
+
+ private:
+  dalib200GenericPlan *plan_ = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------ Flip / Crop (window copy)
+class WindowCopyBase : public Operator<GPUBackend> {
+ public:
+  explicit WindowCopyBase(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    Check(dalib200GenericPlanCreate(&plan_, max_batch_size_), "window copy");
+  }
+  ~WindowCopyBase() override { dalib200GenericPlanDestroy(plan_); }
+
+ protected:
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200GenericLaunch(plan_, ip.data(), op.data(), ws.stream()), "window copy");
+  }
+  dalib200GenericPlan *plan_ = nullptr;
+  std::vector<dalib200WindowSample> win_;
+};
+
+class Flip : public WindowCopyBase {
+ public:
+  using WindowCopyBase::WindowCopyBase;
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_UINT8 && in.shape().sample_dim() == 3, "b200.flip: uint8 HWC images");
+    const int n = in.num_samples();
+    win_.assign(n, dalib200WindowSample{});
+    for (int i = 0; i < n; i++) {
+      auto sh = in.shape().tensor_shape_span(i);
+      auto &w = win_[i];
+      w.in_h = w.out_h = static_cast<int>(sh[0]); w.in_w = w.out_w = static_cast<int>(sh[1]); w.channels = static_cast<int>(sh[2]);
+      w.flip_x = spec_.GetArgument<int>("horizontal", &ws, i) != 0;              // flip.h:43-49
+      w.flip_y = spec_.GetArgument<int>("vertical", &ws, i) != 0;
+    }
+    Check(dalib200WindowCopySetup(plan_, n, win_.data()), "Flip");
+    out.resize(1);
+    out[0].shape = in.shape(); out[0].type = DALI_UINT8;
+    return true;
+  }
+};
+
+class Crop : public WindowCopyBase {
+ public:
+  explicit Crop(const OpSpec &spec) : WindowCopyBase(spec), crop_attr_(spec) {}
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_UINT8 && in.shape().sample_dim() == 3, "b200.crop: uint8 HWC images");
+    const int n = in.num_samples();
+    crop_attr_.ProcessArguments(spec_, ws);                                         // crop_attr.cc:100-245 (reference code)
+    win_.assign(n, dalib200WindowSample{});
+    out.resize(1);
+    out[0].type = DALI_UINT8;
+    out[0].shape.resize(n, 3);
+    for (int i = 0; i < n; i++) {
+      auto sh = in.shape().tensor_shape_span(i);
+      const CropWindow cw = crop_attr_.GetCropWindowGenerator(i)(TensorShape<>{sh[0], sh[1]}, "HW");
+      auto &w = win_[i];
+      w.in_h = static_cast<int>(sh[0]); w.in_w = static_cast<int>(sh[1]); w.channels = static_cast<int>(sh[2]);
+      w.anchor_y = static_cast<int>(cw.anchor[0]); w.anchor_x = static_cast<int>(cw.anchor[1]);
+      w.out_h = static_cast<int>(cw.shape[0]); w.out_w = static_cast<int>(cw.shape[1]);
+      out[0].shape.set_tensor_shape(i, TensorShape<>{cw.shape[0], cw.shape[1], sh[2]});
+    }
+    Check(dalib200WindowCopySetup(plan_, n, win_.data()), "Crop");
+    return true;
+  }
+
+ private:
+  CropAttr crop_attr_;
+};
+
+// ------------------------------------------------------------------------------------------------ RandomResizedCrop
+// Window from the reference's RandomCropAttr (Philox generator, random_crop_attr.h:36-72), filters from ResamplingFilterAttr; the
+// window becomes the resampling ROI exactly as in random_resized_crop.h:105-112.
+class RandomResizedCrop : public OperatorWithRandomCrop<Operator<GPUBackend>> {
+ public:
+  explicit RandomResizedCrop(const OpSpec &spec) : OperatorWithRandomCrop<Operator<GPUBackend>>(spec) {
+    GetSingleOrRepeatedArg(spec, size_, "size", 2);
+    Check(dalib200ResamplePlanCreate(&plan_, max_batch_size_), "RandomResizedCrop");
+  }
+  ~RandomResizedCrop() override { dalib200ResamplePlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.shape().sample_dim() == 3, "b200.random_resized_crop: HWC images");
+    const int n = in.num_samples();
+    resampling_attr_.PrepareFilterParams(spec_, ws, n);
+    std::vector<kernels::ResamplingParams2D> rp(n);
+    for (int i = 0; i < n; i++) {
+      auto sh = in.shape().tensor_shape_span(i);
+      const CropWindow wnd = this->GetCropWindowGenerator(i)(TensorShape<>{sh[0], sh[1]}, "HW");
+      for (int d = 0; d < 2; d++) {
+        rp[i][d].output_size = size_[d];
+        rp[i][d].roi = kernels::ResamplingParams::ROI(wnd.anchor[d], wnd.anchor[d] + wnd.shape[d]);
+      }
+    }
+    resampling_attr_.ApplyFilterParams(make_span(rp));
+    samples_.resize(n);
+    out.resize(1);
+    out[0].type = resampling_attr_.GetOutputType(in.type());
+    out[0].shape.resize(n, 3);
+    for (int i = 0; i < n; i++) {
+      auto sh = in.shape().tensor_shape_span(i);
+      auto &s = samples_[i];
+      s.in_h = static_cast<int>(sh[0]); s.in_w = static_cast<int>(sh[1]); s.channels = static_cast<int>(sh[2]);
+      s.out_h = size_[0]; s.out_w = size_[1];
+      for (int d = 0; d < 2; d++) {
+        const auto &p = rp[i][d];
+        s.use_roi[d] = p.roi.use_roi; s.roi_start[d] = p.roi.start; s.roi_end[d] = p.roi.end;
+        s.min_filter[d] = { static_cast<int>(p.min_filter.type), p.min_filter.antialias, p.min_filter.radius };
+        s.mag_filter[d] = { static_cast<int>(p.mag_filter.type), p.mag_filter.antialias, p.mag_filter.radius };
+      }
+      out[0].shape.set_tensor_shape(i, TensorShape<>{size_[0], size_[1], sh[2]});
+    }
+    Check(dalib200ResamplePlanSetup(plan_, n, samples_.data(), in.type() == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT,
+                                    out[0].type == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT), "RandomResizedCrop");
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200ResampleLaunch(plan_, ip.data(), op.data(), ws.stream()), "RandomResizedCrop");
+  }
+
+ private:
+  std::vector<int> size_;
+  ResamplingFilterAttr resampling_attr_;
+  dalib200ResamplePlan *plan_ = nullptr;
+  std::vector<dalib200ResampleSample> samples_;
+};
+
+// ------------------------------------------------------------------------------------------------ ToDecibels / MFCC
+// On the reference's operator classes: their constructors / GetArguments read and validate the arguments
+// (to_decibels_op.h:38-50, mfcc.h:95-118); Setup and Run go to the signal plan of the library.
+class ToDecibels : public ::dali::ToDecibels<GPUBackend> {
+ public:
+  explicit ToDecibels(const OpSpec &spec) : ::dali::ToDecibels<GPUBackend>(spec) {
+    db_.multiplier = args_.multiplier;
+    db_.ref_max = args_.ref_max;
+    db_.reference = args_.ref_max ? 1.0f : args_.s_ref;
+    db_.cutoff_db = spec.GetArgument<float>("cutoff_db");
+    Check(dalib200SignalPlanCreate(&plan_, max_batch_size_), "ToDecibels");
+  }
+  ~ToDecibels() override { dalib200SignalPlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_FLOAT, "b200.to_decibels: float input");
+    const int n = in.num_samples();
+    std::vector<int64_t> vol(n);
+    for (int i = 0; i < n; i++) vol[i] = in.tensor_shape(i).num_elements();
+    Check(dalib200ToDecibelsSetup(plan_, &db_, n, vol.data()), "ToDecibels");
+    out.resize(1);
+    out[0].shape = in.shape(); out[0].type = DALI_FLOAT;
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200SignalLaunch(plan_, ip.data(), op.data(), ws.stream()), "ToDecibels");
+  }
+
+ private:
+  dalib200ToDecibelsArgs db_{};
+  dalib200SignalPlan *plan_ = nullptr;
+};
+
+class MFCC : public ::dali::MFCC<GPUBackend> {
+ public:
+  explicit MFCC(const OpSpec &spec) : ::dali::MFCC<GPUBackend>(spec) {
+    Check(dalib200SignalPlanCreate(&plan_, max_batch_size_), "MFCC");
+  }
+  ~MFCC() override { dalib200SignalPlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    GetArguments(ws);                                                               // mfcc.h:95-118 (reference code)
+    DALI_ENFORCE(in.type() == DALI_FLOAT && in.shape().sample_dim() == 2 && axis_ == 0,
+                 "b200.mfcc: float (features, frames) input, transform along axis 0");
+    const int n = in.num_samples();
+    dalib200MfccArgs a{ args_[0].ndct, args_[0].dct_type, args_[0].normalize ? 1 : 0, lifter_ };
+    std::vector<int64_t> shp(2 * static_cast<size_t>(n));
+    for (int i = 0; i < n; i++) {
+      auto sh = in.shape().tensor_shape_span(i);
+      shp[2 * i] = sh[0]; shp[2 * i + 1] = sh[1];
+    }
+    Check(dalib200MfccSetup(plan_, &a, n, shp.data()), "MFCC");
+    out.resize(1);
+    out[0].type = DALI_FLOAT;
+    out[0].shape.resize(n, 2);
+    for (int i = 0; i < n; i++)
+      out[0].shape.set_tensor_shape(i, TensorShape<>{std::min<int64_t>(a.n_mfcc, shp[2 * i]), shp[2 * i + 1]});
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200SignalLaunch(plan_, ip.data(), op.data(), ws.stream()), "MFCC");
+  }
+
+ private:
+  dalib200SignalPlan *plan_ = nullptr;
+};
+
 }  // namespace b200
 
 namespace dali {       // the registration macros expect the dali namespace (operator.h:327-333)
@@ -580,5 +879,19 @@ DALI_SCHEMA(b200__AudioResample).NumInput(1).NumOutput(1).AddParent("AudioResamp
 DALI_SCHEMA(b200__NonsilentRegion).NumInput(1).NumOutput(2).AddParent("NonsilentRegion");
 DALI_REGISTER_OPERATOR(b200__AudioResample, b200::AudioResample, GPU);
 DALI_REGISTER_OPERATOR(b200__NonsilentRegion, b200::NonsilentRegion, GPU);
+DALI_SCHEMA(b200__ColorTwist).NumInput(1).NumOutput(1).AddParent("ColorTwist");
+DALI_SCHEMA(b200__BrightnessContrast).NumInput(1).NumOutput(1).AddParent("BrightnessContrast");
+DALI_SCHEMA(b200__Flip).NumInput(1).NumOutput(1).AddParent("Flip");
+DALI_SCHEMA(b200__Crop).NumInput(1).NumOutput(1).AddParent("Crop");
+DALI_SCHEMA(b200__RandomResizedCrop).NumInput(1).NumOutput(1).AddParent("RandomResizedCrop");
+DALI_SCHEMA(b200__ToDecibels).NumInput(1).NumOutput(1).AddParent("ToDecibels");
+DALI_SCHEMA(b200__MFCC).NumInput(1).NumOutput(1).AddParent("MFCC");
+DALI_REGISTER_OPERATOR(b200__ColorTwist, b200::ColorTwist, GPU);
+DALI_REGISTER_OPERATOR(b200__BrightnessContrast, b200::BrightnessContrast, GPU);
+DALI_REGISTER_OPERATOR(b200__Flip, b200::Flip, GPU);
+DALI_REGISTER_OPERATOR(b200__Crop, b200::Crop, GPU);
+DALI_REGISTER_OPERATOR(b200__RandomResizedCrop, b200::RandomResizedCrop, GPU);
+DALI_REGISTER_OPERATOR(b200__ToDecibels, b200::ToDecibels, GPU);
+DALI_REGISTER_OPERATOR(b200__MFCC, b200::MFCC, GPU);
 
 }  // namespace dali

@@ -1,4 +1,4 @@
-"""The plugin of INTEGRATION.md (integration/b200_ops.cc: the eight hot-path operators written against the REFERENCE's own headers --
+"""The plugin of INTEGRATION.md (integration/b200_ops.cc: the hot-path operators and their neighbours written against the REFERENCE's own headers --
 operator.h, crop_attr.h, resize_attr.h, resampling_attr.h -- plus AudioResample / NonsilentRegion derived from the reference's own
 operator bases (audio::ResampleBase, NonsilenceOperator: its argument handling and shape inference, our RunImpl), all over the C-ABI
 of include/dali_b200.h) must at least compile against those headers: `g++ -std=c++20 -fsyntax-only` where /root/reference exists (it
@@ -21,7 +21,8 @@ def test_plugin_compiles_against_reference_headers():
     assert r.returncode == 0, r.stderr[-4000:]
     src = open(os.path.join(ROOT, "integration", "b200_ops.cc")).read()
     for op in ("decoders__Image", "Resize", "CropMirrorNormalize", "WarpAffine", "Hsv", "ColorSpaceConversion", "Spectrogram", "MelFilterBank",
-               "AudioResample", "NonsilentRegion", "decoders__ImageCrop", "decoders__ImageRandomCrop"):
+               "AudioResample", "NonsilentRegion", "decoders__ImageCrop", "decoders__ImageRandomCrop", "ColorTwist", "BrightnessContrast",
+               "Flip", "Crop", "RandomResizedCrop", "ToDecibels", "MFCC"):
         assert f"DALI_REGISTER_OPERATOR(b200__{op}," in src, op
 
 

@@ -19,6 +19,8 @@
 #include "dali/operators/audio/nonsilence_op.h"
 #include "dali/operators/audio/resample.h"
 #include "dali/operators/generic/flip.h"
+#include "dali/operators/generic/slice/slice_attr.h"
+#include "dali/operators/image/remap/rotate_params.h"
 #include "dali/operators/image/color/brightness_contrast.h"
 #include "dali/operators/image/color/color_twist.h"
 #include "dali/operators/signal/decibel/to_decibels_op.h"
@@ -161,6 +163,12 @@ class ImageDecoderCrop : public ImageDecoderRoi<CropAttr> {
   void AcquireWindowArgs(const Workspace &ws) override { attr_.ProcessArguments(spec_, ws); }      // crop_attr.cc:100-245
 };
 using ImageDecoderRandomCrop = ImageDecoderRoi<RandomCropAttr>;
+class ImageDecoderSlice : public ImageDecoderRoi<SliceAttr> {                                     // roi_image_decoder.h:63-78
+ public:
+  using ImageDecoderRoi<SliceAttr>::ImageDecoderRoi;
+ protected:
+  void AcquireWindowArgs(const Workspace &ws) override { attr_.ProcessArguments(spec_, ws); }      // slice_attr.h:361-381
+};
 
 // ------------------------------------------------------------------------------------------------ Resize
 class Resize : public Operator<GPUBackend> {
@@ -705,6 +713,106 @@ class Crop : public WindowCopyBase {
   CropAttr crop_attr_;
 };
 
+class Slice : public WindowCopyBase {
+ public:
+  explicit Slice(const OpSpec &spec) : WindowCopyBase(spec), slice_attr_(spec) {}
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_UINT8 && in.shape().sample_dim() == 3, "b200.slice: uint8 HWC images");
+    const int n = in.num_samples();
+    slice_attr_.ProcessArguments(spec_, ws);                                        // slice_attr.h:361-381 (reference code)
+    auto layout = in.GetLayout();
+    if (layout.empty()) layout = "HWC";
+    win_.assign(n, dalib200WindowSample{});
+    out.resize(1);
+    out[0].type = DALI_UINT8;
+    out[0].shape.resize(n, 3);
+    for (int i = 0; i < n; i++) {
+      const CropWindow cw = slice_attr_.GetCropWindowGenerator(i)(in.shape()[i], layout);     // slice_base.h:68-72
+      auto sh = in.shape().tensor_shape_span(i);
+      DALI_ENFORCE(cw.anchor[2] == 0 && cw.shape[2] == sh[2], "b200.slice: the channel axis cannot be sliced");
+      auto &w = win_[i];
+      w.in_h = static_cast<int>(sh[0]); w.in_w = static_cast<int>(sh[1]); w.channels = static_cast<int>(sh[2]);
+      w.anchor_y = static_cast<int>(cw.anchor[0]); w.anchor_x = static_cast<int>(cw.anchor[1]);
+      w.out_h = static_cast<int>(cw.shape[0]); w.out_w = static_cast<int>(cw.shape[1]);
+      out[0].shape.set_tensor_shape(i, TensorShape<>{cw.shape[0], cw.shape[1], sh[2]});
+    }
+    Check(dalib200WindowCopySetup(plan_, n, win_.data()), "Slice");
+    return true;
+  }
+
+ private:
+  SliceAttr slice_attr_;
+};
+
+// ------------------------------------------------------------------------------------------------ Rotate
+// Output canvas and the destination -> source matrix from the reference's own geometry helpers (rotate_params.h:36-55
+// RotatedCanvasSize, :222-236 AdjustParams; include/dali/core/geom/transform.h), applied by the warp kernel.
+class Rotate : public Operator<GPUBackend> {
+ public:
+  explicit Rotate(const OpSpec &spec) : Operator<GPUBackend>(spec) {
+    interp_ = spec.GetArgument<DALIInterpType>("interp_type") == DALI_INTERP_LINEAR;
+    keep_size_ = spec.GetArgument<bool>("keep_size");
+    use_fill_ = spec.TryGetArgument(fill_, "fill_value");
+    Check(dalib200WarpPlanCreate(&plan_, max_batch_size_), "Rotate");
+  }
+  ~Rotate() override { dalib200WarpPlanDestroy(plan_); }
+
+ protected:
+  bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    DALI_ENFORCE(in.type() == DALI_UINT8 && in.shape().sample_dim() == 3, "b200.rotate: uint8 HWC images");
+    const int n = in.num_samples();
+    const bool has_size = spec_.ArgumentDefined("size");
+    samples_.resize(n);
+    out.resize(1);
+    out[0].type = DALI_UINT8;
+    out[0].shape.resize(n, 3);
+    for (int i = 0; i < n; i++) {
+      auto sh = in.shape().tensor_shape_span(i);
+      const int in_h = static_cast<int>(sh[0]), in_w = static_cast<int>(sh[1]);
+      const float a = deg2rad(-spec_.GetArgument<float>("angle", &ws, i));           // 2-D angles are negated (rotate_params.h SetParams)
+      int oh, ow;
+      if (has_size) {
+        std::vector<float> sz(2);
+        GetGeneralizedArg<float>(make_span(sz), "size", i, spec_, ws);
+        oh = std::max<int>(static_cast<int>(std::roundf(sz[0])), 1); ow = std::max<int>(static_cast<int>(std::roundf(sz[1])), 1);
+      } else if (keep_size_) {
+        oh = in_h; ow = in_w;
+      } else {
+        ivec2 shape, parity;
+        std::tie(shape, parity) = RotatedCanvasSize(TensorShape<2>(in_h, in_w), a);
+        shape += (shape % 2) ^ (2 * parity > 1);                                      // the parity vote of InferSize for one frame
+        ow = shape[0]; oh = shape[1];
+      }
+      const ivec2 in_size(in_w, in_h), out_size(ow, oh);
+      const mat3 T = translation(in_size * 0.5f) * rotation2D(-a) * translation(-out_size * 0.5f);
+      auto &s = samples_[i];
+      s.in_h = in_h; s.in_w = in_w; s.channels = static_cast<int>(sh[2]); s.out_h = oh; s.out_w = ow;
+      for (int r = 0; r < 2; r++) for (int c = 0; c < 3; c++) s.matrix[3 * r + c] = T(r, c);
+      out[0].shape.set_tensor_shape(i, TensorShape<>{oh, ow, sh[2]});
+    }
+    Check(dalib200WarpPlanSetup(plan_, n, samples_.data(), interp_, use_fill_, fill_, DALIB200_UINT8), "Rotate");
+    return true;
+  }
+  void RunImpl(Workspace &ws) override {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    auto ip = InPtrs(in);
+    auto op = OutPtrs(out);
+    Check(dalib200WarpLaunch(plan_, ip.data(), op.data(), ws.stream()), "Rotate");
+  }
+
+ private:
+  dalib200WarpPlan *plan_ = nullptr;
+  std::vector<dalib200WarpSample> samples_;
+  bool interp_ = true, keep_size_ = false, use_fill_ = false;
+  float fill_ = 0;
+};
+
 // ------------------------------------------------------------------------------------------------ RandomResizedCrop
 // Window from the reference's RandomCropAttr (Philox generator, random_crop_attr.h:36-72), filters from ResamplingFilterAttr; the
 // window becomes the resampling ROI exactly as in random_resized_crop.h:105-112.
@@ -879,6 +987,12 @@ DALI_SCHEMA(b200__AudioResample).NumInput(1).NumOutput(1).AddParent("AudioResamp
 DALI_SCHEMA(b200__NonsilentRegion).NumInput(1).NumOutput(2).AddParent("NonsilentRegion");
 DALI_REGISTER_OPERATOR(b200__AudioResample, b200::AudioResample, GPU);
 DALI_REGISTER_OPERATOR(b200__NonsilentRegion, b200::NonsilentRegion, GPU);
+DALI_SCHEMA(b200__decoders__ImageSlice).NumInput(1, 3).NumOutput(1).AddParent("decoders__ImageSlice");
+DALI_SCHEMA(b200__Slice).NumInput(1, 3).NumOutput(1).AddParent("Slice");
+DALI_SCHEMA(b200__Rotate).NumInput(1).NumOutput(1).AddParent("Rotate");
+DALI_REGISTER_OPERATOR(b200__decoders__ImageSlice, b200::ImageDecoderSlice, Mixed);
+DALI_REGISTER_OPERATOR(b200__Slice, b200::Slice, GPU);
+DALI_REGISTER_OPERATOR(b200__Rotate, b200::Rotate, GPU);
 DALI_SCHEMA(b200__ColorTwist).NumInput(1).NumOutput(1).AddParent("ColorTwist");
 DALI_SCHEMA(b200__BrightnessContrast).NumInput(1).NumOutput(1).AddParent("BrightnessContrast");
 DALI_SCHEMA(b200__Flip).NumInput(1).NumOutput(1).AddParent("Flip");

@@ -22,7 +22,7 @@ def test_plugin_compiles_against_reference_headers():
     src = open(os.path.join(ROOT, "integration", "b200_ops.cc")).read()
     for op in ("decoders__Image", "Resize", "CropMirrorNormalize", "WarpAffine", "Hsv", "ColorSpaceConversion", "Spectrogram", "MelFilterBank",
                "AudioResample", "NonsilentRegion", "decoders__ImageCrop", "decoders__ImageRandomCrop", "ColorTwist", "BrightnessContrast",
-               "Flip", "Crop", "RandomResizedCrop", "ToDecibels", "MFCC"):
+               "Flip", "Crop", "RandomResizedCrop", "ToDecibels", "MFCC", "decoders__ImageSlice", "Slice", "Rotate"):
         assert f"DALI_REGISTER_OPERATOR(b200__{op}," in src, op
 
 

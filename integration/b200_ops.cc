@@ -128,7 +128,8 @@ class ImageDecoderRoi : public Operator<MixedBackend> {
       Check(dalib200JpegGetInfo(ptrs[i], lens[i], &info), "decoders.image_crop");
       int64_t H = info.height, W = info.width;
       if (prm_.adjust_orientation && info.orientation >= 5) std::swap(H, W);       // image_decoder.h:678-681
-      const CropWindow win = attr_.GetCropWindowGenerator(i)(TensorShape<>{H, W}, "HW");
+      CropWindow win = attr_.GetCropWindowGenerator(i)(TensorShape<>{H, W}, "HW");
+      win.EnforceInRange(TensorShape<>{H, W});                                      // roi_image_decoder.h:36-40
       rois[i] = { 1, static_cast<int32_t>(win.anchor[1]), static_cast<int32_t>(win.anchor[0]),
                   static_cast<int32_t>(win.anchor[1] + win.shape[1]), static_cast<int32_t>(win.anchor[0] + win.shape[0]), 0 };
     }

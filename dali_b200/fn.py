@@ -2,7 +2,6 @@
 generates them from its schemas (dali/python/nvidia/dali/fn/__init__.py:66-115, ops/_names.py:24-72:
 `decoders__Image` -> fn.decoders.image, `CropMirrorNormalize` -> fn.crop_mirror_normalize).
 """
-import re
 import sys
 import types as _pytypes
 

@@ -608,7 +608,7 @@ void dalib200HannWindow(float *out, int n) {     // window_functions.h:26-33
   for (int t = 0; t < n; t++) out[t] = static_cast<float>(0.5 * (1.0 - std::cos(a * (t + 0.5))));
 }
 
-int dalib200SpectrogramPlanCreate(dalib200SpectrogramPlan **plan, int max_batch) {
+int dalib200SpectrogramPlanCreate(dalib200SpectrogramPlan **plan, int max_batch) try {
   DB_CHECK_ARG(plan && max_batch > 0, "SpectrogramPlanCreate: bad arguments");
   auto *p = new dalib200SpectrogramPlan();
   p->max_batch = max_batch;
@@ -619,9 +619,9 @@ int dalib200SpectrogramPlanCreate(dalib200SpectrogramPlan **plan, int max_batch)
   }
   *plan = p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200SpectrogramPlanDestroy(dalib200SpectrogramPlan *p) {
+int dalib200SpectrogramPlanDestroy(dalib200SpectrogramPlan *p) try {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   p->arena.Free();
@@ -629,10 +629,10 @@ int dalib200SpectrogramPlanDestroy(dalib200SpectrogramPlan *p) {
   if (p->d_twiddle) cudaFree(p->d_twiddle);
   delete p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 int dalib200SpectrogramPlanSetup(dalib200SpectrogramPlan *p, const dalib200SpectrogramArgs *a, const float *window_fn, int n,
-                                 const int64_t *lengths) {
+                                 const int64_t *lengths) try {
   DB_CHECK_ARG(p && a && lengths && n >= 0 && n <= p->max_batch, "SpectrogramPlanSetup: bad arguments");
   DB_CHECK_ARG(a->window_length > 0, "Spectrogram: invalid window length %d", a->window_length);
   DB_CHECK_ARG(a->window_step > 0, "Spectrogram: invalid window step %d", a->window_step);
@@ -677,7 +677,7 @@ int dalib200SpectrogramPlanSetup(dalib200SpectrogramPlan *p, const dalib200Spect
   }
   p->n = n; p->total_groups = groups;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 int64_t dalib200SpectrogramNumWindows(const dalib200SpectrogramPlan *p, int sample) {
   if (!p || sample < 0 || sample >= p->n) return -1;
@@ -783,26 +783,26 @@ static int SpectrogramLaunchImpl(dalib200SpectrogramPlan *p, const void *const *
   return DALIB200_SUCCESS;
 }
 
-int dalib200SpectrogramLaunch(dalib200SpectrogramPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+int dalib200SpectrogramLaunch(dalib200SpectrogramPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && in_ptrs && out_ptrs, "SpectrogramLaunch: null argument");
   return SpectrogramLaunchImpl(p, in_ptrs, out_ptrs, nullptr, nullptr, stream);
-}
+} DB_API_CATCH
 
-int dalib200SpectrogramMelSupported(const dalib200SpectrogramPlan *p, const dalib200MelPlan *m) {
+int dalib200SpectrogramMelSupported(const dalib200SpectrogramPlan *p, const dalib200MelPlan *m) try {
   if (!p || !m || p->P.nfft != 1024 || !p->P.layout_ft || m->nbin != p->P.nbin || m->n != p->n || m->tensor_cores) return 0;
   for (int i = 0; i < p->n; i++) if (m->descs[i].nwin != p->descs[i].nwin) return 0;
   return 1;
-}
+} DB_API_CATCH
 
 int dalib200SpectrogramMelLaunch(dalib200SpectrogramPlan *p, dalib200MelPlan *m, const void *const *in_ptrs, void *const *spec_out_ptrs,
-                                 void *const *mel_out_ptrs, dalib200Stream_t stream) {
+                                 void *const *mel_out_ptrs, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && m && in_ptrs && mel_out_ptrs, "SpectrogramMelLaunch: null argument");
   DB_CHECK_ARG(dalib200SpectrogramMelSupported(p, m), "SpectrogramMelLaunch: the fused kernel needs nfft = 1024, the (f, t) layout and a mel "
                "plan set up for the same batch (check dalib200SpectrogramMelSupported)");
   return SpectrogramLaunchImpl(p, in_ptrs, spec_out_ptrs, m, mel_out_ptrs, stream);
-}
+} DB_API_CATCH
 
-int dalib200MelPlanCreate(dalib200MelPlan **plan, int max_batch) {
+int dalib200MelPlanCreate(dalib200MelPlan **plan, int max_batch) try {
   DB_CHECK_ARG(plan && max_batch > 0, "MelPlanCreate: bad arguments");
   auto *p = new dalib200MelPlan();
   p->max_batch = max_batch;
@@ -813,28 +813,29 @@ int dalib200MelPlanCreate(dalib200MelPlan **plan, int max_batch) {
   }
   *plan = p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200MelPlanDestroy(dalib200MelPlan *p) {
+int dalib200MelPlanDestroy(dalib200MelPlan *p) try {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   p->arena.Free(); p->tables.Free(); p->dense.Free();
   delete p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200MelPlanSetTensorCores(dalib200MelPlan *p, int enable) {
+int dalib200MelPlanSetTensorCores(dalib200MelPlan *p, int enable) try {
   DB_CHECK_ARG(p, "MelPlanSetTensorCores: null plan");
   p->tensor_cores = enable != 0;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200MelPlanSetup(dalib200MelPlan *p, const dalib200MelArgs *args, int nbin, int n, const int64_t *nwin) {
+int dalib200MelPlanSetup(dalib200MelPlan *p, const dalib200MelArgs *args, int nbin, int n, const int64_t *nwin) try {
   DB_CHECK_ARG(p && args && nwin && n >= 0 && n <= p->max_batch, "MelPlanSetup: bad arguments");
   DB_CHECK_ARG(args->nfilter > 0, "MelFilterBank: nfilter must be positive");
-  DB_CHECK_ARG(nbin >= 2, "MelFilterBank: the frequency axis must have at least 2 bins");
+  DB_CHECK_ARG(nbin >= 2 && nbin <= (1 << 24), "MelFilterBank: the frequency axis must have 2 .. 2^24 bins (got %d)", nbin);
+  DB_CHECK_ARG(args->nfilter >= 1 && args->nfilter <= (1 << 20), "MelFilterBank: nfilter must be in 1 .. 2^20 (got %d)", args->nfilter);
   dalib200MelArgs a = *args;
-  DB_CHECK_ARG(a.sample_rate > 0, "MelFilterBank: sample_rate must be positive");
+  DB_CHECK_ARG(a.sample_rate > 0 && a.sample_rate <= 1e9f, "MelFilterBank: sample_rate must be positive and finite");
   if (a.freq_high <= 0) a.freq_high = a.sample_rate / 2;
   DB_CHECK_ARG(a.freq_low >= 0 && a.freq_low <= a.sample_rate / 2, "MelFilterBank: freq_low out of range");
   DB_CHECK_ARG(a.freq_high >= 0 && a.freq_high <= a.sample_rate / 2, "MelFilterBank: freq_high out of range");
@@ -862,7 +863,7 @@ int dalib200MelPlanSetup(dalib200MelPlan *p, const dalib200MelArgs *args, int nb
   p->total_items_mma = items2;
   p->n = n; p->total_items = items;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 static int MelUploadTables(dalib200MelPlan *p, dalib200Stream_t stream, size_t *o_up_out, size_t *o_down_out) {
   const size_t o_up = (p->h_ends.size() * 4 + 15) / 16 * 16, o_down = o_up + (p->h_up.size() * 4 + 15) / 16 * 16;
@@ -881,7 +882,7 @@ static int MelUploadTables(dalib200MelPlan *p, dalib200Stream_t stream, size_t *
   return DALIB200_SUCCESS;
 }
 
-int dalib200MelLaunch(dalib200MelPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+int dalib200MelLaunch(dalib200MelPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && in_ptrs && out_ptrs, "MelLaunch: null argument");
   if (p->n == 0 || p->total_items == 0) return DALIB200_SUCCESS;
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
@@ -941,6 +942,6 @@ int dalib200MelLaunch(dalib200MelPlan *p, const void *const *in_ptrs, void *cons
   CountLaunch();
   DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 }  // extern "C"

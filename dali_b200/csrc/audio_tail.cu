@@ -397,7 +397,7 @@ int UploadDescs(dalib200SignalPlan *p) {
 
 extern "C" {
 
-int dalib200SignalPlanCreate(dalib200SignalPlan **plan, int max_batch) {
+int dalib200SignalPlanCreate(dalib200SignalPlan **plan, int max_batch) try {
   DB_CHECK_ARG(plan && max_batch > 0, "SignalPlanCreate: bad arguments");
   auto *p = new dalib200SignalPlan();
   p->max_batch = max_batch;
@@ -406,9 +406,9 @@ int dalib200SignalPlanCreate(dalib200SignalPlan **plan, int max_batch) {
   }
   *plan = p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200SignalPlanDestroy(dalib200SignalPlan *p) {
+int dalib200SignalPlanDestroy(dalib200SignalPlan *p) try {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   p->arena.Free();
@@ -418,9 +418,9 @@ int dalib200SignalPlanDestroy(dalib200SignalPlan *p) {
   if (p->d_lookup) cudaFree(p->d_lookup);
   delete p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200ToDecibelsSetup(dalib200SignalPlan *p, const dalib200ToDecibelsArgs *a, int n, const int64_t *volumes) {
+int dalib200ToDecibelsSetup(dalib200SignalPlan *p, const dalib200ToDecibelsArgs *a, int n, const int64_t *volumes) try {
   DB_CHECK_ARG(p && a && (n == 0 || volumes) && n >= 0 && n <= p->max_batch, "ToDecibelsSetup: bad arguments");
   DB_CHECK_ARG(a->ref_max || a->reference != 0.0f, "`reference` argument can't be zero");
   p->kind = SIG_TODB; p->n = n;
@@ -439,14 +439,15 @@ int dalib200ToDecibelsSetup(dalib200SignalPlan *p, const dalib200ToDecibelsArgs 
   }
   p->total_items = items;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200MfccSetup(dalib200SignalPlan *p, const dalib200MfccArgs *a, int n, const int64_t *shapes) {
+int dalib200MfccSetup(dalib200SignalPlan *p, const dalib200MfccArgs *a, int n, const int64_t *shapes) try {
   DB_CHECK_ARG(p && a && (n == 0 || shapes) && n >= 0 && n <= p->max_batch, "MfccSetup: bad arguments");
   DB_CHECK_ARG(a->n_mfcc > 0, "number of MFCCs should be > 0");
   DB_CHECK_ARG(a->dct_type >= 1 && a->dct_type <= 4, "Unsupported DCT type: %d. Supported types are: 1, 2, 3, 4.", a->dct_type);
   DB_CHECK_ARG(!(a->normalize && a->dct_type == 1), "Ortho-normalization is not supported for DCT type I.");
   p->kind = SIG_MFCC; p->n = n;
+  DB_CHECK_ARG(n == 0 || (shapes[0] >= 1 && shapes[0] <= (1 << 16)), "MFCC: the transformed axis must have 1 .. 65536 elements");
   const int nfeat = n ? (int)shapes[0] : 1;
   int ndct = a->n_mfcc;
   if (ndct > nfeat) ndct = nfeat;                                 // dct_cpu.cc:56-58
@@ -455,6 +456,7 @@ int dalib200MfccSetup(dalib200SignalPlan *p, const dalib200MfccArgs *a, int n, c
   int64_t items = 0;
   for (int i = 0; i < n; i++) {
     DB_CHECK_ARG(shapes[2 * i] == nfeat, "MFCC: all samples of a batch must have the same extent along the transformed axis");
+    DB_CHECK_ARG(shapes[2 * i + 1] >= 0 && shapes[2 * i + 1] < (1ll << 31), "MFCC: sample %d has an unsupported number of frames", i);
     p->descs[i].rows = nfeat; p->descs[i].cols = shapes[2 * i + 1]; p->descs[i].n = nfeat * shapes[2 * i + 1];
     p->descs[i].first_item = items;
     items += (shapes[2 * i + 1] + 127) / 128;
@@ -471,11 +473,11 @@ int dalib200MfccSetup(dalib200SignalPlan *p, const dalib200MfccArgs *a, int n, c
   if (tab != p->h_table || nfeat != p->nfeat || ndct != p->ndct) { p->h_table = tab; p->table_dirty = true; }
   p->nfeat = nfeat; p->ndct = ndct;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 int dalib200SignalOutputRows(const dalib200SignalPlan *p) { return p ? p->ndct : 0; }
 
-int dalib200NormalizeSetup(dalib200SignalPlan *p, const dalib200NormalizeArgs *a, int n, const int64_t *shapes) {
+int dalib200NormalizeSetup(dalib200SignalPlan *p, const dalib200NormalizeArgs *a, int n, const int64_t *shapes) try {
   DB_CHECK_ARG(p && a && (n == 0 || shapes) && n >= 0 && n <= p->max_batch, "NormalizeSetup: bad arguments");
   DB_CHECK_ARG(a->mode >= 0 && a->mode <= 2, "NormalizeSetup: mode must be 0 (all axes), 1 (axis 1) or 2 (axis 0)");
   DB_CHECK_ARG(a->ddof >= 0, "Normalize: ddof must be non-negative");
@@ -484,15 +486,17 @@ int dalib200NormalizeSetup(dalib200SignalPlan *p, const dalib200NormalizeArgs *a
   p->descs.assign(n, SigDesc());
   int64_t items = 0;
   for (int i = 0; i < n; i++) {
+    DB_CHECK_ARG(shapes[2 * i] >= 0 && shapes[2 * i + 1] >= 0 && shapes[2 * i] < (1ll << 31) && shapes[2 * i + 1] < (1ll << 31),
+                 "Normalize: sample %d has an unsupported shape", i);
     p->descs[i].rows = shapes[2 * i]; p->descs[i].cols = shapes[2 * i + 1]; p->descs[i].n = shapes[2 * i] * shapes[2 * i + 1];
     p->descs[i].first_item = items;
     items += p->descs[i].n == 0 ? 0 : a->mode == 0 ? 1 : a->mode == 1 ? shapes[2 * i] : shapes[2 * i + 1];
   }
   p->total_items = items;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200AudioResampleSetup(dalib200SignalPlan *p, int n, const dalib200AudioResampleSample *samples, float quality) {
+int dalib200AudioResampleSetup(dalib200SignalPlan *p, int n, const dalib200AudioResampleSample *samples, float quality) try {
   DB_CHECK_ARG(p && n >= 0 && n <= p->max_batch && (n == 0 || samples), "AudioResampleSetup: bad arguments");
   DB_CHECK_ARG(quality >= 0 && quality <= 100, "``quality`` out of range: %g\nValid range is [0..100].", (double)quality);
   p->kind = SIG_RESAMPLE; p->n = n;
@@ -536,10 +540,10 @@ int dalib200AudioResampleSetup(dalib200SignalPlan *p, int n, const dalib200Audio
   }
   p->total_items = items;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 int dalib200NonsilentSetup(dalib200SignalPlan *p, int n, const int64_t *lengths, const dalib200NonsilentSample *args, int window_length,
-                           int reset_interval) {
+                           int reset_interval) try {
   DB_CHECK_ARG(p && n >= 0 && n <= p->max_batch && (n == 0 || (lengths && args)), "NonsilentSetup: bad arguments");
   DB_CHECK_ARG(window_length > 0, "NonsilentRegion: window_length must be positive, got %d", window_length);
   DB_CHECK_ARG(reset_interval == -1 || (reset_interval > 0 && reset_interval % window_length == 0),
@@ -567,10 +571,10 @@ int dalib200NonsilentSetup(dalib200SignalPlan *p, int n, const int64_t *lengths,
   }
   p->total_items = items; p->mms_total = total;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 int dalib200NonsilentLaunch(dalib200SignalPlan *p, const void *const *in_ptrs, void *const *begin_ptrs, void *const *length_ptrs,
-                            dalib200Stream_t stream) {
+                            dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && p->kind == SIG_NONSILENT && (p->n == 0 || (in_ptrs && begin_ptrs && length_ptrs)), "NonsilentLaunch: call NonsilentSetup first");
   if (p->n == 0) return DALIB200_SUCCESS;
   int rc = GrowF(p->d_mms, p->d_mms_cap, (size_t)p->mms_total);
@@ -595,7 +599,7 @@ int dalib200NonsilentLaunch(dalib200SignalPlan *p, const void *const *in_ptrs, v
   CountLaunch();
   DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 static int AudioResampleLaunch(dalib200SignalPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
   int rc = GrowF(p->d_lookup, p->d_lookup_cap, p->ar_lookup.size());
@@ -620,7 +624,7 @@ static int AudioResampleLaunch(dalib200SignalPlan *p, const void *const *in_ptrs
   return DALIB200_SUCCESS;
 }
 
-int dalib200SignalLaunch(dalib200SignalPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+int dalib200SignalLaunch(dalib200SignalPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && p->kind != SIG_NONE && p->kind != SIG_NONSILENT && (p->n == 0 || (in_ptrs && out_ptrs)),
                "SignalLaunch: call a ...Setup function first (NonsilentRegion has its own launch)");
   if (p->n == 0 || p->total_items == 0) return DALIB200_SUCCESS;
@@ -671,6 +675,6 @@ int dalib200SignalLaunch(dalib200SignalPlan *p, const void *const *in_ptrs, void
   }
   DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 }  // extern "C"

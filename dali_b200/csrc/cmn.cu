@@ -248,7 +248,7 @@ struct dalib200CmnPlan {
 
 extern "C" {
 
-int dalib200CmnPlanCreate(dalib200CmnPlan **plan, int max_batch) {
+int dalib200CmnPlanCreate(dalib200CmnPlan **plan, int max_batch) try {
   DB_CHECK_ARG(plan && max_batch > 0, "CmnPlanCreate: bad arguments");
   auto *p = new dalib200CmnPlan();
   p->max_batch = max_batch;
@@ -259,18 +259,18 @@ int dalib200CmnPlanCreate(dalib200CmnPlan **plan, int max_batch) {
   }
   *plan = p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200CmnPlanDestroy(dalib200CmnPlan *p) {
+int dalib200CmnPlanDestroy(dalib200CmnPlan *p) try {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   p->arena.Free();
   delete p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 int dalib200CmnPlanSetup(dalib200CmnPlan *p, int n, const dalib200CmnSample *samples, int out_dtype, int out_layout,
-                         int out_channels) {
+                         int out_channels) try {
   DB_CHECK_ARG(p && samples && n >= 0, "CmnPlanSetup: null argument");
   DB_CHECK_ARG(n <= p->max_batch, "CmnPlanSetup: batch %d exceeds plan capacity %d", n, p->max_batch);
   DB_CHECK_ARG(out_dtype == DALIB200_FLOAT || out_dtype == DALIB200_FLOAT16,
@@ -286,6 +286,8 @@ int dalib200CmnPlanSetup(dalib200CmnPlan *p, int n, const dalib200CmnSample *sam
                  "CropMirrorNormalize: sample %d has unsupported shape %dx%dx%d", i, s.in_h, s.in_w, s.channels);
     DB_CHECK_ARG(s.crop_h >= 0 && s.crop_w >= 0, "CropMirrorNormalize: sample %d negative crop", i);
     DB_CHECK_ARG(out_channels >= s.channels, "CropMirrorNormalize: out_channels < input channels");
+    DB_CHECK_ARG(ElementsFit31(s.in_h, s.in_w, s.channels) && ElementsFit31(s.crop_h, s.crop_w, out_channels),
+                 "CropMirrorNormalize: sample %d: inputs / outputs of 2^31 elements or more are not supported", i);
     CmnDesc &d = descs[i];
     memset(&d, 0, sizeof(d));
     d.in_h = s.in_h; d.in_w = s.in_w; d.C = s.channels;
@@ -303,9 +305,9 @@ int dalib200CmnPlanSetup(dalib200CmnPlan *p, int n, const dalib200CmnSample *sam
   p->n = n; p->out_dtype = out_dtype; p->out_layout = out_layout; p->out_c = out_channels;
   p->total_units = units; p->total_elems = elems;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200CmnLaunch(dalib200CmnPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+int dalib200CmnLaunch(dalib200CmnPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && in_ptrs && out_ptrs, "CmnLaunch: null argument");
   if (p->n == 0) return DALIB200_SUCCESS;
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
@@ -343,6 +345,6 @@ int dalib200CmnLaunch(dalib200CmnPlan *p, const void *const *in_ptrs, void *cons
   }
   DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 }  // extern "C"

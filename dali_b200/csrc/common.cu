@@ -109,7 +109,7 @@ extern "C" {
 
 // Test hook: compares the hardware-assisted float -> half (ties away) conversion of the kernels with the integer restatement of
 // include/dali/util/half.hpp on ALL 2^32 float bit patterns; *mismatches must come back 0.
-int dalib200DebugCheckHalfConversion(uint64_t *mismatches) {
+int dalib200DebugCheckHalfConversion(uint64_t *mismatches) try {
   DB_CHECK_ARG(mismatches, "DebugCheckHalfConversion: null pointer");
   unsigned long long *d = nullptr;
   DB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d), 8));
@@ -121,20 +121,20 @@ int dalib200DebugCheckHalfConversion(uint64_t *mismatches) {
   DB_CUDA(e);
   *mismatches = h;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200HostAlloc(void **ptr, size_t bytes) {
+int dalib200HostAlloc(void **ptr, size_t bytes) try {
   DB_CHECK_ARG(ptr, "HostAlloc: null pointer");
   *ptr = nullptr;
   if (bytes == 0) return DALIB200_SUCCESS;
   DB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 // The same for a caller thread whose current device is not the consumer's (e.g. a reader's read-ahead thread, whose thread-local
 // current device is still 0): the allocation is made with `device` current -- no context is created on another GPU as a side effect
 // -- and is portable (page-locked for every context).  The thread's current device is restored.
-int dalib200HostAllocOnDevice(void **ptr, size_t bytes, int device) {
+int dalib200HostAllocOnDevice(void **ptr, size_t bytes, int device) try {
   DB_CHECK_ARG(ptr && device >= 0, "HostAllocOnDevice: bad arguments");
   *ptr = nullptr;
   if (bytes == 0) return DALIB200_SUCCESS;
@@ -145,16 +145,16 @@ int dalib200HostAllocOnDevice(void **ptr, size_t bytes, int device) {
   if (have_prev && prev != device) cudaSetDevice(prev);
   DB_CUDA(e);
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200HostFree(void *ptr) {
+int dalib200HostFree(void *ptr) try {
   if (ptr) DB_CUDA(cudaFreeHost(ptr));
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 int dalib200ProfilingEnable(int on) { dalib200::g_prof_on = on != 0; return DALIB200_SUCCESS; }
 // Synchronises, writes up to `max` records (names: `name_stride` bytes each, NUL terminated) and clears the log.
-int dalib200ProfilingCollect(char *names, int name_stride, float *ms, int max, int *count) {
+int dalib200ProfilingCollect(char *names, int name_stride, float *ms, int max, int *count) try {
   using namespace dalib200;  // NOLINT
   std::lock_guard<std::mutex> lock(g_prof_mutex);
   int n = 0;
@@ -172,7 +172,7 @@ int dalib200ProfilingCollect(char *names, int name_stride, float *ms, int max, i
   g_prof.clear();
   if (count) *count = n;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 const char *dalib200GetLastError(void) { return dalib200::tls_error.c_str(); }
 int dalib200GetVersion(void) { return 100; }
 uint64_t dalib200GetLaunchCount(void) { return dalib200::g_launch_count.load(); }

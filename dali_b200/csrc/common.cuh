@@ -186,4 +186,25 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const void *tmap, int c0,
 #endif  // __CUDACC__
 
 }  // namespace dalib200
+
+// The C-ABI never lets a C++ exception escape (std::bad_alloc / std::length_error from a host-side table of absurd size would otherwise
+// terminate the caller's process): every entry point is a function-try-block closed by this handler.  (Kept at the end of the header
+// so that the line tables of the device code above do not move.)
+#include <exception>
+#include <new>
+namespace dalib200 {
+// a * b * c < 2^31 for non-negative extents, without overflowing on the way (the kernels index a sample with 32-bit arithmetic)
+inline bool ElementsFit31(int64_t a, int64_t b, int64_t c) {
+  const int64_t lim = (int64_t{1} << 31) - 1;
+  if (a < 0 || b < 0 || c < 0) return false;
+  if (a == 0 || b == 0 || c == 0) return true;
+  if (a > lim / b) return false;
+  return a * b <= lim / c;
+}
+}  // namespace dalib200
+#define DB_API_CATCH                                                                                                       \
+  catch (const std::bad_alloc &) { ::dalib200::SetLastError("out of host memory"); return DALIB200_ERROR_INTERNAL; }      \
+  catch (const std::exception &e__) { ::dalib200::SetLastError("unexpected C++ exception: %s", e__.what()); return DALIB200_ERROR_INTERNAL; } \
+  catch (...) { ::dalib200::SetLastError("unexpected C++ exception"); return DALIB200_ERROR_INTERNAL; }
+
 #endif  // DALI_B200_CSRC_COMMON_CUH_

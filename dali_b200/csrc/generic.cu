@@ -97,7 +97,7 @@ struct dalib200GenericPlan {
 
 extern "C" {
 
-int dalib200GenericPlanCreate(dalib200GenericPlan **plan, int max_batch) {
+int dalib200GenericPlanCreate(dalib200GenericPlan **plan, int max_batch) try {
   DB_CHECK_ARG(plan && max_batch > 0, "GenericPlanCreate: bad arguments");
   auto *p = new dalib200GenericPlan();
   p->max_batch = max_batch;
@@ -106,17 +106,17 @@ int dalib200GenericPlanCreate(dalib200GenericPlan **plan, int max_batch) {
   }
   *plan = p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200GenericPlanDestroy(dalib200GenericPlan *p) {
+int dalib200GenericPlanDestroy(dalib200GenericPlan *p) try {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   p->arena.Free();
   delete p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200MultiplyAddSetup(dalib200GenericPlan *p, int n, const int64_t *volumes, const float *multipliers, const float *addends, int out_dtype) {
+int dalib200MultiplyAddSetup(dalib200GenericPlan *p, int n, const int64_t *volumes, const float *multipliers, const float *addends, int out_dtype) try {
   DB_CHECK_ARG(p && n >= 0 && n <= p->max_batch && (n == 0 || (volumes && multipliers && addends)), "MultiplyAddSetup: bad arguments");
   DB_CHECK_ARG(out_dtype == DALIB200_UINT8 || out_dtype == DALIB200_FLOAT, "MultiplyAddSetup: output type must be UINT8 or FLOAT");
   p->kind = 1; p->n = n; p->out_dtype = out_dtype;
@@ -125,15 +125,16 @@ int dalib200MultiplyAddSetup(dalib200GenericPlan *p, int n, const int64_t *volum
   for (int i = 0; i < n; i++) {
     GenDesc &d = p->descs[i];
     memset(&d, 0, sizeof(d));
+    DB_CHECK_ARG(volumes[i] >= 0, "MultiplyAddSetup: sample %d has a negative size", i);
     d.n = volumes[i]; d.mul = multipliers[i]; d.add = addends[i];
     d.first_item = items;
     items += (d.n + kGenItem - 1) / kGenItem;
   }
   p->total_items = items;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200WindowCopySetup(dalib200GenericPlan *p, int n, const dalib200WindowSample *samples) {
+int dalib200WindowCopySetup(dalib200GenericPlan *p, int n, const dalib200WindowSample *samples) try {
   DB_CHECK_ARG(p && n >= 0 && n <= p->max_batch && (n == 0 || samples), "WindowCopySetup: bad arguments");
   p->kind = 2; p->n = n; p->out_dtype = DALIB200_UINT8;
   p->descs.assign(n, GenDesc());
@@ -147,16 +148,17 @@ int dalib200WindowCopySetup(dalib200GenericPlan *p, int n, const dalib200WindowS
     d.anchor_y = w.anchor_y; d.anchor_x = w.anchor_x; d.out_h = w.out_h; d.out_w = w.out_w;
     d.flip_x = w.flip_x != 0; d.flip_y = w.flip_y != 0;
     for (int k = 0; k < 4; k++) d.fill[k] = w.fill[k];
+    DB_CHECK_ARG(ElementsFit31(w.out_h, w.out_w, w.channels) && ElementsFit31(w.in_h, w.in_w, w.channels),
+                 "WindowCopySetup: sample %d: images of 2^31 elements or more are not supported", i);
     d.n = (int64_t)w.out_h * w.out_w * w.channels;
-    DB_CHECK_ARG(d.n < (1ll << 31), "WindowCopySetup: sample %d: outputs of 2^31 elements or more are not supported", i);
     d.first_item = items;
     items += (d.n + kGenItem - 1) / kGenItem;
   }
   p->total_items = items;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200GenericLaunch(dalib200GenericPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+int dalib200GenericLaunch(dalib200GenericPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && p->kind != 0 && (p->n == 0 || (in_ptrs && out_ptrs)), "GenericLaunch: call a ...Setup function first");
   if (p->n == 0 || p->total_items == 0) return DALIB200_SUCCESS;
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
@@ -180,6 +182,6 @@ int dalib200GenericLaunch(dalib200GenericPlan *p, const void *const *in_ptrs, vo
   CountLaunch();
   DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 }  // extern "C"

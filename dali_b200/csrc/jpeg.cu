@@ -1794,16 +1794,16 @@ void BuildWorkLists(dalib200JpegPlan *p) {
 
 extern "C" {
 
-int dalib200JpegGetInfo(const uint8_t *data, size_t len, dalib200JpegInfo *info) {
+int dalib200JpegGetInfo(const uint8_t *data, size_t len, dalib200JpegInfo *info) try {
   DB_CHECK_ARG(data && info, "JpegGetInfo: null argument");
   ParsedJpeg j;
   int rc = ParseHeaders(data, len, j, false);
   if (rc) return rc;
   FillInfo(j, info);
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200JpegPlanCreate(dalib200JpegPlan **plan, int max_batch) {
+int dalib200JpegPlanCreate(dalib200JpegPlan **plan, int max_batch) try {
   DB_CHECK_ARG(plan && max_batch > 0, "JpegPlanCreate: bad arguments");
   auto *p = new dalib200JpegPlan();
   p->max_batch = max_batch;
@@ -1813,9 +1813,9 @@ int dalib200JpegPlanCreate(dalib200JpegPlan **plan, int max_batch) {
   }
   *plan = p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200JpegPlanDestroy(dalib200JpegPlan *p) {
+int dalib200JpegPlanDestroy(dalib200JpegPlan *p) try {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   if (p->img_uploaded) { cudaEventSynchronize(p->img_uploaded); cudaEventDestroy(p->img_uploaded); }
@@ -1827,24 +1827,24 @@ int dalib200JpegPlanDestroy(dalib200JpegPlan *p) {
   for (void *b : bufs) if (b) cudaFree(b);
   delete p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200JpegPlanGetInfo(const dalib200JpegPlan *p, int sample, dalib200JpegInfo *info) {
+int dalib200JpegPlanGetInfo(const dalib200JpegPlan *p, int sample, dalib200JpegInfo *info) try {
   DB_CHECK_ARG(p && info && sample >= 0 && sample < p->n, "JpegPlanGetInfo: bad sample index");
   FillInfo(p->parsed[sample], info);
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 size_t dalib200JpegPlanStagedBytes(const dalib200JpegPlan *p) { return p ? p->desc_bytes + p->raw_bytes : 0; }
 
 int dalib200JpegPlanSetup(dalib200JpegPlan *p, int n, const uint8_t *const *streams, const size_t *lengths, int output_type,
-                          int fancy_upsampling) {
+                          int fancy_upsampling) try {
   dalib200JpegParams prm;
   prm.output_type = output_type; prm.fancy_upsampling = fancy_upsampling; prm.dtype = DALIB200_UINT8; prm.adjust_orientation = 0;
   return dalib200JpegPlanSetupEx(p, n, streams, lengths, &prm, nullptr);
-}
+} DB_API_CATCH
 
-int dalib200JpegPlanSetPlanesOnly(dalib200JpegPlan *p, const uint8_t *want, uint8_t *granted) {
+int dalib200JpegPlanSetPlanesOnly(dalib200JpegPlan *p, const uint8_t *want, uint8_t *granted) try {
   DB_CHECK_ARG(p && p->staged && want && granted, "JpegPlanSetPlanesOnly: call JpegPlanSetupEx first");
   for (int i = 0; i < p->n; i++) { granted[i] = want[i] && p->geo[i].planar_ok; p->planes_only[i] = granted[i]; }
   BuildWorkLists(p);
@@ -1852,9 +1852,9 @@ int dalib200JpegPlanSetPlanesOnly(dalib200JpegPlan *p, const uint8_t *want, uint
   memcpy(p->h_stage + p->off_items, p->first_item.data(), sizeof(int64_t) * p->n);
   memcpy(p->h_stage + p->off_work, p->first_work.data(), sizeof(int64_t) * p->n);
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200JpegPlanGetPlanes(const dalib200JpegPlan *p, int sample, dalib200PlanarImage *out) {
+int dalib200JpegPlanGetPlanes(const dalib200JpegPlan *p, int sample, dalib200PlanarImage *out) try {
   DB_CHECK_ARG(p && out && sample >= 0 && sample < p->n && p->d_planes, "JpegPlanGetPlanes: call JpegLaunch first");
   const JpegImage &im = p->images[sample];
   DB_CHECK_ARG(im.ncomp == 3, "JpegPlanGetPlanes: sample %d has %d components", sample, im.ncomp);
@@ -1863,16 +1863,16 @@ int dalib200JpegPlanGetPlanes(const dalib200JpegPlan *p, int sample, dalib200Pla
   out->width = im.width; out->height = im.height;
   out->crop_x = 0; out->crop_y = 0;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200JpegPlanGetOutputShape(const dalib200JpegPlan *p, int sample, int32_t *hwc) {
+int dalib200JpegPlanGetOutputShape(const dalib200JpegPlan *p, int sample, int32_t *hwc) try {
   DB_CHECK_ARG(p && hwc && sample >= 0 && sample < p->n, "JpegPlanGetOutputShape: bad sample index");
   for (int d = 0; d < 3; d++) hwc[d] = p->out_shape[3 * sample + d];
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *streams, const size_t *lengths,
-                            const dalib200JpegParams *prm, const dalib200JpegRoi *rois) {
+                            const dalib200JpegParams *prm, const dalib200JpegRoi *rois) try {
   DB_CHECK_ARG(p && prm && (n == 0 || (streams && lengths)) && n >= 0, "JpegPlanSetup: null argument");
   DB_CHECK_ARG(n <= p->max_batch, "JpegPlanSetup: batch %d exceeds plan capacity %d", n, p->max_batch);
   const int output_type = prm->output_type, fancy_upsampling = prm->fancy_upsampling;
@@ -2138,11 +2138,11 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
   }
   p->staged = true;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 // test / debug accessor: quantised coefficients of one sample after DC prediction, MCU order, natural order in
 // each block.  Synchronises the device.
-int dalib200JpegDebugGetCoefficients(dalib200JpegPlan *p, int sample, int16_t *out, size_t count) {
+int dalib200JpegDebugGetCoefficients(dalib200JpegPlan *p, int sample, int16_t *out, size_t count) try {
   DB_CHECK_ARG(p && out && sample >= 0 && sample < p->n && p->d_coef, "JpegDebugGetCoefficients: bad arguments");
   const JpegImage &im = p->images[sample];
   const size_t have = (size_t)im.mcux * im.mcuy * im.bpm * 64;
@@ -2154,19 +2154,19 @@ int dalib200JpegDebugGetCoefficients(dalib200JpegPlan *p, int sample, int16_t *o
   DB_CUDA(cudaMemcpy(dcs.data(), p->d_dc + im.coef_off / 64, dcs.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
   for (size_t b = 0; b * 64 < count; b++) out[b * 64] = dcs[b];
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 // per-sample decode status written by the device (0 = ok, 1 = entropy-coded data ended early).  Synchronises.
-int dalib200JpegGetStatus(dalib200JpegPlan *p, int32_t *status_out) {
+int dalib200JpegGetStatus(dalib200JpegPlan *p, int32_t *status_out) try {
   DB_CHECK_ARG(p && status_out && p->d_status, "JpegGetStatus: bad arguments");
   DB_CUDA(cudaDeviceSynchronize());
   DB_CUDA(cudaMemcpy(status_out, p->d_status, sizeof(int32_t) * p->n, cudaMemcpyDeviceToHost));
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 // Asynchronous variant: enqueues the copy of the per-sample status words into a pinned buffer of the plan; JpegStatusFetch reads
 // that buffer without synchronising (valid once the stream has been synchronised by the caller, e.g. at Pipeline outputs()).
-int dalib200JpegStatusAsync(dalib200JpegPlan *p, dalib200Stream_t stream) {
+int dalib200JpegStatusAsync(dalib200JpegPlan *p, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && p->d_status, "JpegStatusAsync: nothing has been launched");
   if ((size_t)p->n > p->h_status_cap) {
     if (p->h_status) cudaFreeHost(p->h_status);
@@ -2176,23 +2176,23 @@ int dalib200JpegStatusAsync(dalib200JpegPlan *p, dalib200Stream_t stream) {
   }
   DB_CUDA(cudaMemcpyAsync(p->h_status, p->d_status, sizeof(int32_t) * p->n, cudaMemcpyDeviceToHost, stream));
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200JpegStatusFetch(const dalib200JpegPlan *p, int32_t *status_out, int n) {
+int dalib200JpegStatusFetch(const dalib200JpegPlan *p, int32_t *status_out, int n) try {
   DB_CHECK_ARG(p && status_out && p->h_status && n <= (int)p->h_status_cap, "JpegStatusFetch: call JpegStatusAsync first");
   for (int i = 0; i < n; i++) status_out[i] = p->h_status[i];
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200JpegPlanSetSourceStable(dalib200JpegPlan *p, int stable) {
+int dalib200JpegPlanSetSourceStable(dalib200JpegPlan *p, int stable) try {
   DB_CHECK_ARG(p, "JpegPlanSetSourceStable: null plan");
   p->source_stable = stable != 0;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 int dalib200JpegPlanLastUploadDirect(const dalib200JpegPlan *p) { return p ? p->last_upload_direct : -1; }
 
-int dalib200JpegUpload(dalib200JpegPlan *p, dalib200Stream_t stream) {
+int dalib200JpegUpload(dalib200JpegPlan *p, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && p->staged, "JpegUpload: call JpegPlanSetup first");
   if (p->n == 0) return DALIB200_SUCCESS;
   const size_t total = p->desc_bytes + p->raw_bytes;
@@ -2300,9 +2300,9 @@ int dalib200JpegUpload(dalib200JpegPlan *p, dalib200Stream_t stream) {
   DB_CUDA(cudaEventRecord(p->uploaded, stream));
   p->pending = true;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Stream_t stream) {
+int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && p->staged && out_ptrs, "JpegLaunch: call JpegPlanSetup / JpegUpload first");
   if (p->n == 0) return DALIB200_SUCCESS;
   DB_CHECK_ARG(p->d_stage && p->d_stage_cap >= p->desc_bytes + p->raw_bytes, "JpegLaunch: JpegUpload has not been called for this batch");
@@ -2439,6 +2439,6 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   CountLaunch(5);
   DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 }  // extern "C"

@@ -289,7 +289,7 @@ void dalib200ColorTwistMatrix(float hue, float saturation, float value, float br
   T[0] = T[1] = T[2] = t;
 }
 
-int dalib200PointwisePlanCreate(dalib200PointwisePlan **plan, int max_batch) {
+int dalib200PointwisePlanCreate(dalib200PointwisePlan **plan, int max_batch) try {
   DB_CHECK_ARG(plan && max_batch > 0, "PointwisePlanCreate: bad arguments");
   auto *p = new dalib200PointwisePlan();
   p->max_batch = max_batch;
@@ -300,17 +300,17 @@ int dalib200PointwisePlanCreate(dalib200PointwisePlan **plan, int max_batch) {
   }
   *plan = p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200PointwisePlanDestroy(dalib200PointwisePlan *p) {
+int dalib200PointwisePlanDestroy(dalib200PointwisePlan *p) try {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   p->arena.Free();
   delete p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200LinearTransformSetup(dalib200PointwisePlan *p, int n, const dalib200ColorSample *samples, int out_dtype) {
+int dalib200LinearTransformSetup(dalib200PointwisePlan *p, int n, const dalib200ColorSample *samples, int out_dtype) try {
   DB_CHECK_ARG(p && samples && n >= 0 && n <= p->max_batch, "LinearTransformSetup: bad arguments");
   DB_CHECK_ARG(out_dtype == DALIB200_UINT8 || out_dtype == DALIB200_FLOAT, "Hsv/ColorTwist: output type %d not supported", out_dtype);
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
@@ -326,9 +326,9 @@ int dalib200LinearTransformSetup(dalib200PointwisePlan *p, int n, const dalib200
   }
   p->n = n; p->mode = PW_LINEAR; p->out_dtype = out_dtype; p->total_quads = quads;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200ColorSpaceSetup(dalib200PointwisePlan *p, int n, const int64_t *num_pixels, int in_type, int out_type) {
+int dalib200ColorSpaceSetup(dalib200PointwisePlan *p, int n, const int64_t *num_pixels, int in_type, int out_type) try {
   DB_CHECK_ARG(p && num_pixels && n >= 0 && n <= p->max_batch, "ColorSpaceSetup: bad arguments");
   DB_CHECK_ARG(in_type >= 0 && in_type <= 3 && out_type >= 0 && out_type <= 3, "ColorSpaceConversion: unknown image type");
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
@@ -337,14 +337,15 @@ int dalib200ColorSpaceSetup(dalib200PointwisePlan *p, int n, const int64_t *num_
   for (int i = 0; i < n; i++) {
     PwDesc &d = descs[i];
     memset(&d, 0, sizeof(d));
+    DB_CHECK_ARG(num_pixels[i] >= 0, "ColorSpaceConversion: negative sample size");
     d.npix = num_pixels[i]; d.first_quad = quads;
     quads += (d.npix + 3) / 4;
   }
   p->n = n; p->mode = PW_CSC; p->in_type = in_type; p->out_type = out_type; p->total_quads = quads;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200PointwiseLaunch(dalib200PointwisePlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+int dalib200PointwiseLaunch(dalib200PointwisePlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && in_ptrs && out_ptrs, "PointwiseLaunch: null argument");
   if (p->n == 0 || p->total_quads == 0) return DALIB200_SUCCESS;
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
@@ -366,6 +367,6 @@ int dalib200PointwiseLaunch(dalib200PointwisePlan *p, const void *const *in_ptrs
   CountLaunch();
   DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 }  // extern "C"

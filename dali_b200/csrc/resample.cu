@@ -1119,7 +1119,7 @@ int BuildHorzFlags(std::vector<int32_t> &arena, int idx_off, int ow, int iw, int
 
 extern "C" {
 
-int dalib200ResamplePlanCreate(dalib200ResamplePlan **plan, int max_batch) {
+int dalib200ResamplePlanCreate(dalib200ResamplePlan **plan, int max_batch) try {
   DB_CHECK_ARG(plan && max_batch > 0, "ResamplePlanCreate: bad arguments");
   auto *p = new dalib200ResamplePlan();
   p->max_batch = max_batch;
@@ -1130,27 +1130,27 @@ int dalib200ResamplePlanCreate(dalib200ResamplePlan **plan, int max_batch) {
   }
   *plan = p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200ResamplePlanDestroy(dalib200ResamplePlan *p) {
+int dalib200ResamplePlanDestroy(dalib200ResamplePlan *p) try {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   p->desc_arena.Free(); p->table_arena.Free(); p->item_arena.Free();
   delete p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200ResamplePlanGetPath(const dalib200ResamplePlan *p, int sample) {
+int dalib200ResamplePlanGetPath(const dalib200ResamplePlan *p, int sample) try {
   if (!p || sample < 0 || sample >= p->n) return -1;
   return p->path[sample];
-}
+} DB_API_CATCH
 
-int dalib200ResamplePlanGetOrder(const dalib200ResamplePlan *p, int sample) {
+int dalib200ResamplePlanGetOrder(const dalib200ResamplePlan *p, int sample) try {
   if (!p || sample < 0 || sample >= p->n) return -1;
   return p->order0[sample];
-}
+} DB_API_CATCH
 
-int dalib200ResamplePlanSetup(dalib200ResamplePlan *p, int n, const dalib200ResampleSample *samples, int in_dtype, int out_dtype) {
+int dalib200ResamplePlanSetup(dalib200ResamplePlan *p, int n, const dalib200ResampleSample *samples, int in_dtype, int out_dtype) try {
   DB_CHECK_ARG(p && samples && n >= 0, "ResamplePlanSetup: null argument");
   DB_CHECK_ARG(n <= p->max_batch, "ResamplePlanSetup: batch %d exceeds plan capacity %d", n, p->max_batch);
   DB_CHECK_ARG((in_dtype == DALIB200_UINT8 && (out_dtype == DALIB200_UINT8 || out_dtype == DALIB200_FLOAT)) ||
@@ -1169,6 +1169,16 @@ int dalib200ResamplePlanSetup(dalib200ResamplePlan *p, int n, const dalib200Resa
     DB_CHECK_ARG(s.in_h > 0 && s.in_w > 0 && s.channels >= 1 && s.channels <= 16,
                  "Resize: sample %d has unsupported input shape %dx%dx%d", i, s.in_h, s.in_w, s.channels);
     DB_CHECK_ARG(s.out_h >= 0 && s.out_w >= 0, "Resize: sample %d has negative output size", i);
+    DB_CHECK_ARG(ElementsFit31(s.in_h, s.in_w, s.channels) && ElementsFit31(s.out_h, s.out_w, s.channels),
+                 "Resize: sample %d: images of 2^31 elements or more are not supported", i);
+    for (int a = 0; a < 2; a++) {
+      for (const dalib200FilterDesc *f : { &s.min_filter[a], &s.mag_filter[a] })
+        DB_CHECK_ARG(f->type >= DALIB200_FILTER_NN && f->type <= DALIB200_FILTER_LANCZOS3 && f->radius >= 0 && f->radius <= 1e6f,
+                     "Resize: sample %d: invalid filter (type %d, radius %g)", i, f->type, static_cast<double>(f->radius));
+      DB_CHECK_ARG(!s.use_roi[a] || (std::isfinite(s.roi_start[a]) && std::isfinite(s.roi_end[a]) && std::fabs(s.roi_start[a]) <= 1e9f &&
+                                     std::fabs(s.roi_end[a]) <= 1e9f),
+                   "Resize: sample %d: the region of interest must be finite", i);
+    }
     RsDesc &d = p->descs[i];
     memset(&d, 0, sizeof(d));
     d.in_h = s.in_h; d.in_w = s.in_w; d.C = s.channels; d.out_h = s.out_h; d.out_w = s.out_w;
@@ -1196,6 +1206,12 @@ int dalib200ResamplePlanSetup(dalib200ResamplePlan *p, int n, const dalib200Resa
       auto it = p->cache.find(key);
       AxisTableRef ref;
       if (it == p->cache.end()) {
+        // index + coefficient tables are addressed with 32-bit offsets and live in one host / device arena: refuse absurd requests
+        // (e.g. a 2^31-wide source minified with antialiasing = millions of taps per output) instead of exhausting memory
+        DB_CHECK_ARG(static_cast<int64_t>(ax[a].out_size) * (static_cast<int64_t>(ax[a].support) + 1) + static_cast<int64_t>(p->tables.size()) <
+                         (int64_t{1} << 26),
+                     "Resize: sample %d needs %lld filter taps per output along axis %d (%d -> %d): the filter tables would exceed 256 MB", i,
+                     static_cast<long long>(ax[a].support), a, ax[a].in_size, ax[a].out_size);
         BuildTable(p->tables, ref, ax[a], a);
         p->cache[key] = ref;
       } else {
@@ -1315,9 +1331,9 @@ int dalib200ResamplePlanSetup(dalib200ResamplePlan *p, int n, const dalib200Resa
   // identical tables (the common fixed-size case) are not uploaded again
   p->tables_dirty = p->tables != p->uploaded_tables;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200ResamplePlanSetupPlanar(dalib200ResamplePlan *p, int n, const dalib200ResampleSample *samples, uint8_t *planar_ok) {
+int dalib200ResamplePlanSetupPlanar(dalib200ResamplePlan *p, int n, const dalib200ResampleSample *samples, uint8_t *planar_ok) try {
   DB_CHECK_ARG(p && samples && planar_ok, "ResamplePlanSetupPlanar: null argument");
   p->planar_mode = true;
   const int rc = dalib200ResamplePlanSetup(p, n, samples, DALIB200_UINT8, DALIB200_UINT8);
@@ -1331,9 +1347,9 @@ int dalib200ResamplePlanSetupPlanar(dalib200ResamplePlan *p, int n, const dalib2
   p->items.swap(keep);
   for (int i = 0; i < n; i++) p->stream_ok[i] = planar_ok[i];
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200ResampleLaunchPlanar(dalib200ResamplePlan *p, const dalib200PlanarImage *srcs, void *const *out_ptrs, dalib200Stream_t stream) {
+int dalib200ResampleLaunchPlanar(dalib200ResamplePlan *p, const dalib200PlanarImage *srcs, void *const *out_ptrs, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && srcs && out_ptrs, "ResampleLaunchPlanar: null argument");
   if (p->n == 0 || p->items.empty()) return DALIB200_SUCCESS;
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
@@ -1400,9 +1416,9 @@ int dalib200ResampleLaunchPlanar(dalib200ResamplePlan *p, const dalib200PlanarIm
   CountLaunch();
   DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200ResampleLaunch(dalib200ResamplePlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+int dalib200ResampleLaunch(dalib200ResamplePlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && in_ptrs && out_ptrs, "ResampleLaunch: null argument");
   if (p->n == 0 || p->total_tiles == 0) return DALIB200_SUCCESS;
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
@@ -1484,6 +1500,6 @@ int dalib200ResampleLaunch(dalib200ResamplePlan *p, const void *const *in_ptrs, 
   CountLaunch();
   DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 }  // extern "C"

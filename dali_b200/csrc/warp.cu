@@ -424,7 +424,7 @@ void dalib200AffineInverse(const float *M, float *out) {
   out[0] = m00; out[1] = m01; out[2] = t0; out[3] = m10; out[4] = m11; out[5] = t1;
 }
 
-int dalib200WarpPlanCreate(dalib200WarpPlan **plan, int max_batch) {
+int dalib200WarpPlanCreate(dalib200WarpPlan **plan, int max_batch) try {
   DB_CHECK_ARG(plan && max_batch > 0, "WarpPlanCreate: bad arguments");
   auto *p = new dalib200WarpPlan();
   p->max_batch = max_batch;
@@ -435,18 +435,18 @@ int dalib200WarpPlanCreate(dalib200WarpPlan **plan, int max_batch) {
   }
   *plan = p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200WarpPlanDestroy(dalib200WarpPlan *p) {
+int dalib200WarpPlanDestroy(dalib200WarpPlan *p) try {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   p->arena.Free();
   delete p;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 int dalib200WarpPlanSetup(dalib200WarpPlan *p, int n, const dalib200WarpSample *samples, int interp, int use_fill,
-                          float fill_value, int out_dtype) {
+                          float fill_value, int out_dtype) try {
   DB_CHECK_ARG(p && samples && n >= 0, "WarpPlanSetup: null argument");
   DB_CHECK_ARG(n <= p->max_batch, "WarpPlanSetup: batch %d exceeds plan capacity %d", n, p->max_batch);
   DB_CHECK_ARG(interp == 0 || interp == 1, "WarpAffine: only NN and LINEAR interpolation are supported (got %d)", interp);
@@ -462,8 +462,10 @@ int dalib200WarpPlanSetup(dalib200WarpPlan *p, int n, const dalib200WarpSample *
     WarpDesc &d = descs[i];
     memset(&d, 0, sizeof(d));
     d.in_h = s.in_h; d.in_w = s.in_w; d.C = s.channels; d.out_h = s.out_h; d.out_w = s.out_w;
-    d.tiles_x = (s.out_w + kWarpTileW - 1) / kWarpTileW;
-    d.tiles_y = (s.out_h + kWarpTileH - 1) / kWarpTileH;
+    DB_CHECK_ARG(ElementsFit31(s.in_h, s.in_w, s.channels) && ElementsFit31(s.out_h, s.out_w, s.channels),
+                 "WarpAffine: sample %d: images of 2^31 elements or more are not supported", i);
+    d.tiles_x = static_cast<int>((static_cast<int64_t>(s.out_w) + kWarpTileW - 1) / kWarpTileW);
+    d.tiles_y = static_cast<int>((static_cast<int64_t>(s.out_h) + kWarpTileH - 1) / kWarpTileH);
     d.first_tile = tiles;
     tiles += (int64_t)d.tiles_x * d.tiles_y;
     memcpy(d.m, s.matrix, sizeof(d.m));
@@ -473,9 +475,9 @@ int dalib200WarpPlanSetup(dalib200WarpPlan *p, int n, const dalib200WarpSample *
   float r = std::round(fill_value);
   p->border = r <= 0 ? 0.0f : r >= 255 ? 255.0f : r;
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
-int dalib200WarpLaunch(dalib200WarpPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) {
+int dalib200WarpLaunch(dalib200WarpPlan *p, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream) try {
   DB_CHECK_ARG(p && in_ptrs && out_ptrs, "WarpLaunch: null argument");
   if (p->n == 0 || p->total_tiles == 0) return DALIB200_SUCCESS;
   if (p->pending) { DB_CUDA(cudaEventSynchronize(p->uploaded)); p->pending = false; }
@@ -563,6 +565,6 @@ int dalib200WarpLaunch(dalib200WarpPlan *p, const void *const *in_ptrs, void *co
   CountLaunch();
   DB_CUDA(cudaGetLastError());
   return DALIB200_SUCCESS;
-}
+} DB_API_CATCH
 
 }  // extern "C"

@@ -22,3 +22,16 @@ cudaError_t cudaPeekAtLastError(void) { return 0; }
 cudaError_t cudaStreamSynchronize(void *s) { return 0; }
 cudaError_t cudaMemsetAsync(void *p, int v, size_t n, void *s) { return 0; }
 cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int kind, void *st) { return 0; }
+/* launch side: kernels are never run -- the host code in front of them (descriptor build, staging copies, arena growth) is what is fuzzed */
+cudaError_t cudaLaunchKernel(const void *f, ...) { return 0; }
+cudaError_t cudaFuncSetAttribute(const void *f, int attr, int v) { return 0; }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, const void *f, int b, size_t s) { *n = 2; return 0; }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int *n, const void *f, int b, size_t s, unsigned fl) { *n = 2; return 0; }
+cudaError_t cudaMemcpy(void *d, const void *s, size_t n, int kind) { return 0; }
+cudaError_t cudaMemset(void *p, int v, size_t n) { return 0; }
+cudaError_t cudaDeviceSynchronize(void) { return 0; }
+cudaError_t cudaMemcpyBatchAsync(void **d, void **s, size_t *sz, size_t cnt, void *attrs, size_t *idx, size_t na, size_t *fail, void *st) { return 0; }
+struct stubPtrAttr { int type; int device; void *devp; void *hostp; };
+cudaError_t cudaPointerGetAttributes(struct stubPtrAttr *a, const void *p) { a->type = 0; a->device = 0; a->devp = 0; a->hostp = (void *)p; return 0; }
+cudaError_t cudaGetDriverEntryPoint(const char *sym, void **fn, unsigned long long flags, int *status) { *fn = 0; if (status) *status = 1; return 0; }
+cudaError_t cudaEventElapsedTime(float *ms, void *a, void *b) { *ms = 0; return 0; }

@@ -56,7 +56,14 @@ for it in range(n):
     rc = L.dalib200JpegPlanSetupEx(plan, len(bufs), ptrs, lens, prm, rois)
     if rc == 0:
         hwc = (C.c_int32 * 3)()
+        outs = (C.c_void_p * len(bufs))(*[0x10000 * (b + 1) for b in range(len(bufs))])       # never dereferenced on the host
         for b in range(len(bufs)):
             L.dalib200JpegPlanGetOutputShape(plan, b, hwc)
+        # the staging copy of the streams and the launch-side descriptor build (kernels are stubbed out)
+        L.dalib200JpegPlanSetSourceStable(plan, int(rng.integers(0, 2)))
+        rc2 = L.dalib200JpegUpload(plan, None)
+        if rc2 == 0:
+            rc2 = L.dalib200JpegLaunch(plan, outs, None)
+        rcs["launch", rc2] = rcs.get(("launch", rc2), 0) + 1
     rcs[rc] = rcs.get(rc, 0) + 1
 print("seed", sys.argv[2] if len(sys.argv) > 2 else 0, "iterations", n, "status histogram", rcs, "- no sanitizer report")

@@ -42,6 +42,16 @@ def plan(kind, n):
 hist = {}
 
 
+def fake_ptrs(m, base):
+    """Device pointers are never dereferenced on the host: aligned fake addresses (sometimes misaligned ones) are enough."""
+    return (C.c_void_p * m)(*[base + 0x1000000 * (i + 1) + (int(rng.integers(1, 16)) if rng.random() < 0.1 * MILD else 0) for i in range(m)])
+
+
+def launch(name, fn, *args):
+    """Launch-side host code (descriptor build, arena growth, path selection); the kernels themselves are stubbed out."""
+    note(name + "_launch", fn(*args))
+
+
 TRACE = os.environ.get("FUZZ_TRACE")
 
 
@@ -64,9 +74,22 @@ for it in range(N):
             s.roi_start[d], s.roi_end[d] = flt(-50, 3000), flt(-50, 3000)
             s.min_filter[d] = capi.FilterDesc(code(range(6)), int(rng.integers(0, 2)), flt(0, 8))
             s.mag_filter[d] = capi.FilterDesc(code(range(6)), int(rng.integers(0, 2)), flt(0, 8))
-    note("resample", L.dalib200ResamplePlanSetup(plans["Resample"].handle, n, S, code([0, 9]), code([0, 9])))
+    rc = L.dalib200ResamplePlanSetup(plans["Resample"].handle, n, S, code([0, 9]), code([0, 9]))
+    note("resample", rc)
+    if rc == 0:
+        launch("resample", L.dalib200ResampleLaunch, plans["Resample"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
+        for i in range(max(0, min(n, m))):
+            L.dalib200ResamplePlanGetOrder(plans["Resample"].handle, i), L.dalib200ResamplePlanGetPath(plans["Resample"].handle, i)
     ok = (C.c_uint8 * m)()
-    note("resample_planar", L.dalib200ResamplePlanSetupPlanar(plans["Resample"].handle, n, S, ok))
+    rc = L.dalib200ResamplePlanSetupPlanar(plans["Resample"].handle, n, S, ok)
+    note("resample_planar", rc)
+    if rc == 0:
+        PI = (capi.PlanarImage * m)()
+        for i, q in enumerate(PI):
+            q.y, q.cb, q.cr = 0x20000000 + 0x1000000 * i, 0x40000000 + 0x1000000 * i, 0x60000000 + 0x1000000 * i
+            q.pitch_y, q.pitch_c = int(rng.choice([16, 64, 1920, 1936, 17])), int(rng.choice([16, 64, 960, 976, 9]))
+            q.width, q.height, q.crop_x, q.crop_y = dim(), dim(), small(0, 64), small(0, 64)
+        launch("resample_planar", L.dalib200ResampleLaunchPlanar, plans["Resample"].handle, PI, fake_ptrs(m, 0x7000000000), None)
     # ---- cmn
     Cs = (capi.CmnSample * m)()
     for s in Cs:
@@ -74,14 +97,21 @@ for it in range(N):
         s.anchor_y, s.anchor_x, s.crop_h, s.crop_w, s.mirror = small(-50, 3000), small(-50, 3000), dim(0, 600), dim(0, 600), int(rng.integers(0, 2))
         for k in range(4):
             s.mean[k], s.inv_std[k], s.fill[k] = flt(0, 255), flt(0, 1), flt(0, 255)
-    note("cmn", L.dalib200CmnPlanSetup(plans["Cmn"].handle, n, Cs, code([9, 8, 0]), code([0, 1]), small(1, 5)))
+    rc = L.dalib200CmnPlanSetup(plans["Cmn"].handle, n, Cs, code([9, 8, 0]), code([0, 1]), small(1, 5))
+    note("cmn", rc)
+    if rc == 0:
+        launch("cmn", L.dalib200CmnLaunch, plans["Cmn"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
     # ---- warp
     W = (capi.WarpSample * m)()
     for s in W:
         s.in_h, s.in_w, s.channels, s.out_h, s.out_w = dim(), dim(), small(1, 5), dim(0, 600), dim(0, 600)
         for k in range(6):
             s.matrix[k] = flt(-3, 3)
-    note("warp", L.dalib200WarpPlanSetup(plans["Warp"].handle, n, W, code([0, 1]), int(rng.integers(0, 2)), C.c_float(flt(0, 255)), code([0, 9])))
+    rc = L.dalib200WarpPlanSetup(plans["Warp"].handle, n, W, code([0, 1]), int(rng.integers(0, 2)), C.c_float(flt(0, 255)), code([0, 9]))
+    note("warp", rc)
+    if rc == 0:
+        launch("warp", L.dalib200WarpLaunch, plans["Warp"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
+        L.dalib200WarpPlanGetPath(plans["Warp"].handle)
     # ---- pointwise
     P = (capi.ColorSample * m)()
     for s in P:
@@ -90,9 +120,15 @@ for it in range(N):
             s.matrix[k] = flt(-2, 2)
         for k in range(3):
             s.offset[k] = flt(-128, 128)
-    note("linear", L.dalib200LinearTransformSetup(plans["Pointwise"].handle, n, P, code([0, 9])))
+    rc = L.dalib200LinearTransformSetup(plans["Pointwise"].handle, n, P, code([0, 9]))
+    note("linear", rc)
+    if rc == 0:
+        launch("linear", L.dalib200PointwiseLaunch, plans["Pointwise"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
     npx = (C.c_int64 * m)(*[int(rng.choice([0, -1, 2 ** 40])) if rng.random() < 0.1 else int(rng.integers(0, 10 ** 7)) for _ in range(m)])
-    note("csc", L.dalib200ColorSpaceSetup(plans["Pointwise"].handle, n, npx, code(range(4)), code(range(4))))
+    rc = L.dalib200ColorSpaceSetup(plans["Pointwise"].handle, n, npx, code(range(4)), code(range(4)))
+    note("csc", rc)
+    if rc == 0:
+        launch("csc", L.dalib200PointwiseLaunch, plans["Pointwise"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
     # ---- spectrogram / mel
     a = capi.SpectrogramArgs(code([64, 128, 256, 400, 512, 1000, 1024, 2048, 4096, 8192]), code([16, 64, 400, 512, 1024, 5000]), code([1, 64, 160, 256]),
                              code([1, 2]), int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(0, 2)))
@@ -103,6 +139,7 @@ for it in range(N):
     rc = L.dalib200SpectrogramPlanSetup(plans["Spectrogram"].handle, C.byref(a), None if win is None else win.ctypes.data_as(C.c_void_p), n, lens)
     note("spectrogram", rc)
     if rc == 0:
+        launch("spectrogram", L.dalib200SpectrogramLaunch, plans["Spectrogram"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
         for i in range(max(0, min(n, m))):
             L.dalib200SpectrogramNumWindows(plans["Spectrogram"].handle, i)
     ma = capi.MelArgs(code([1, 40, 80, 128, 1000]), C.c_float(flt(8000, 48000)), C.c_float(flt(0, 4000)), C.c_float(flt(0, 24000)), int(rng.integers(0, 2)),
@@ -110,20 +147,32 @@ for it in range(N):
     nwin = (C.c_int64 * m)(*[int(rng.choice([0, -1, 2 ** 40])) if rng.random() < 0.1 else int(rng.integers(0, 2000)) for _ in range(m)])
     rc2 = L.dalib200MelPlanSetup(plans["Mel"].handle, C.byref(ma), code([1, 33, 129, 257, 513, 1025]), n, nwin)
     note("mel", rc2)
+    if rc2 == 0:
+        L.dalib200MelPlanSetTensorCores(plans["Mel"].handle, int(rng.integers(0, 2)))
+        launch("mel", L.dalib200MelLaunch, plans["Mel"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
     if rc == 0 and rc2 == 0:
-        L.dalib200SpectrogramMelSupported(plans["Spectrogram"].handle, plans["Mel"].handle)
+        if L.dalib200SpectrogramMelSupported(plans["Spectrogram"].handle, plans["Mel"].handle) == 1:
+            launch("spectrogram_mel", L.dalib200SpectrogramMelLaunch, plans["Spectrogram"].handle, plans["Mel"].handle, fake_ptrs(m, 0x10000000),
+                   fake_ptrs(m, 0x5000000000) if rng.random() < 0.5 else None, fake_ptrs(m, 0x7000000000), None)
     # ---- signal tail
     db = capi.ToDecibelsArgs(C.c_float(flt(1, 20)), C.c_float(flt(0, 2)), C.c_float(flt(-200, 0)), int(rng.integers(0, 2)))
     vol = (C.c_int64 * m)(*[int(rng.choice([0, -1, 2 ** 40])) if rng.random() < 0.1 else int(rng.integers(0, 10 ** 6)) for _ in range(m)])
-    note("todb", L.dalib200ToDecibelsSetup(plans["Signal"].handle, C.byref(db), n, vol))
+    rc = L.dalib200ToDecibelsSetup(plans["Signal"].handle, C.byref(db), n, vol)
+    note("todb", rc)
+    if rc == 0:
+        launch("todb", L.dalib200SignalLaunch, plans["Signal"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
     shp = (C.c_int64 * (2 * m))(*[int(rng.choice([0, -1, 2 ** 33])) if rng.random() < 0.08 else int(rng.integers(0, 600)) for _ in range(2 * m)])
     mf = capi.MfccArgs(code([1, 13, 40, 128, 1000]), code([1, 2, 3, 4]), int(rng.integers(0, 2)), C.c_float(flt(0, 30)))
     rc = L.dalib200MfccSetup(plans["Signal"].handle, C.byref(mf), n, shp)
     note("mfcc", rc)
     if rc == 0:
         L.dalib200SignalOutputRows(plans["Signal"].handle)
+        launch("mfcc", L.dalib200SignalLaunch, plans["Signal"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
     na = capi.NormalizeArgs(code([0, 1, 2]), small(0, 3), C.c_float(flt(0, 2)), C.c_float(flt(-1, 1)), C.c_float(flt(0, 1e-3)))
-    note("normalize", L.dalib200NormalizeSetup(plans["Signal"].handle, C.byref(na), n, shp))
+    rc = L.dalib200NormalizeSetup(plans["Signal"].handle, C.byref(na), n, shp)
+    note("normalize", rc)
+    if rc == 0:
+        launch("normalize", L.dalib200SignalLaunch, plans["Signal"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
 
     class AR(C.Structure):
         _fields_ = [("in_rate", C.c_double), ("out_rate", C.c_double), ("in_length", C.c_int64), ("out_length", C.c_int64), ("channels", C.c_int32)]
@@ -133,18 +182,27 @@ for it in range(N):
         s.in_length = int(rng.choice([0, -1, 2 ** 40])) if rng.random() < 0.1 else int(rng.integers(0, 200000))
         s.out_length = int(rng.choice([0, -1, 2 ** 40])) if rng.random() < 0.1 else int(rng.integers(0, 200000))
         s.channels = small(1, 9)
-    note("audio_resample", L.dalib200AudioResampleSetup(plans["Signal"].handle, n, ars, C.c_float(flt(0, 100))))
+    rc = L.dalib200AudioResampleSetup(plans["Signal"].handle, n, ars, C.c_float(flt(0, 100)))
+    note("audio_resample", rc)
+    if rc == 0:
+        launch("audio_resample", L.dalib200SignalLaunch, plans["Signal"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
 
     class NS(C.Structure):
         _fields_ = [("cutoff_db", C.c_float), ("reference_power", C.c_float), ("use_reference_power", C.c_int32)]
     nss = (NS * m)()
     for s in nss:
         s.cutoff_db, s.reference_power, s.use_reference_power = flt(-100, 0), flt(0, 1), int(rng.integers(0, 2))
-    note("nonsilent", L.dalib200NonsilentSetup(plans["Signal"].handle, n, lens, nss, code([1, 512, 2048, 8192]), code([-1, 512, 2048, 8192, 1000])))
+    rc = L.dalib200NonsilentSetup(plans["Signal"].handle, n, lens, nss, code([1, 512, 2048, 8192]), code([-1, 512, 2048, 8192, 1000]))
+    note("nonsilent", rc)
+    if rc == 0:
+        launch("nonsilent", L.dalib200NonsilentLaunch, plans["Signal"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x5000000000), fake_ptrs(m, 0x7000000000), None)
     # ---- generic
     mul = (C.c_float * m)(*[flt() for _ in range(m)])
     add = (C.c_float * m)(*[flt() for _ in range(m)])
-    note("multiply_add", L.dalib200MultiplyAddSetup(plans["Generic"].handle, n, vol, mul, add, code([0, 9])))
+    rc = L.dalib200MultiplyAddSetup(plans["Generic"].handle, n, vol, mul, add, code([0, 9]))
+    note("multiply_add", rc)
+    if rc == 0:
+        launch("multiply_add", L.dalib200GenericLaunch, plans["Generic"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
 
     class WS(C.Structure):
         _fields_ = [("in_h", C.c_int32), ("in_w", C.c_int32), ("channels", C.c_int32), ("anchor_y", C.c_int32), ("anchor_x", C.c_int32),
@@ -154,5 +212,8 @@ for it in range(N):
         s.in_h, s.in_w, s.channels = dim(0, 3000), dim(0, 3000), small(1, 5)
         s.anchor_y, s.anchor_x, s.out_h, s.out_w = small(-50, 3000), small(-50, 3000), dim(0, 3000), dim(0, 3000)
         s.flip_x, s.flip_y = int(rng.integers(0, 2)), int(rng.integers(0, 2))
-    note("window_copy", L.dalib200WindowCopySetup(plans["Generic"].handle, n, ws))
+    rc = L.dalib200WindowCopySetup(plans["Generic"].handle, n, ws)
+    note("window_copy", rc)
+    if rc == 0:
+        launch("window_copy", L.dalib200GenericLaunch, plans["Generic"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
 print("seed", sys.argv[1] if len(sys.argv) > 1 else 0, "iterations", N, "- no sanitizer report;", {f"{k[0]}:{k[1]}": v for k, v in sorted(hist.items())})

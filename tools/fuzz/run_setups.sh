@@ -17,6 +17,6 @@ SEEDS="${*:-1 2 3}"
 for s in $SEEDS; do
   for scale in 1 0.05; do
     DALIB200_LIB="$OUT/libfuzz_all.so" FUZZ_BAD_SCALE=$scale LD_PRELOAD="$(gcc -print-file-name=libasan.so) $OUT/cuda_stub.so" \
-      ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=halt_on_error=1:print_stacktrace=1 python "$HERE/fuzz_plan_setups.py" "$s" "$N" | cut -c1-160
+      ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=halt_on_error=1:print_stacktrace=1 python "$HERE/fuzz_plan_setups.py" "$s" "$N" | cut -c1-400
   done
 done

@@ -8,10 +8,10 @@ cudaError_t cudaEventDestroy(void *e) { free(e); return 0; }
 cudaError_t cudaEventSynchronize(void *e) { return 0; }
 cudaError_t cudaEventRecord(void *e, void *s) { return 0; }
 cudaError_t cudaEventQuery(void *e) { return 0; }
-cudaError_t cudaHostAlloc(void **p, size_t n, unsigned f) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
-cudaError_t cudaMallocHost(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+cudaError_t cudaHostAlloc(void **p, size_t n, unsigned f) { *p = calloc(n ? n : 1, 1); return *p ? 0 : 2; }
+cudaError_t cudaMallocHost(void **p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? 0 : 2; }
 cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
-cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? 0 : 2; }
 cudaError_t cudaFree(void *p) { free(p); return 0; }
 cudaError_t cudaGetDevice(int *d) { *d = 0; return 0; }
 cudaError_t cudaSetDevice(int d) { return 0; }
@@ -35,3 +35,8 @@ struct stubPtrAttr { int type; int device; void *devp; void *hostp; };
 cudaError_t cudaPointerGetAttributes(struct stubPtrAttr *a, const void *p) { a->type = 0; a->device = 0; a->devp = 0; a->hostp = (void *)p; return 0; }
 cudaError_t cudaGetDriverEntryPoint(const char *sym, void **fn, unsigned long long flags, int *status) { *fn = 0; if (status) *status = 1; return 0; }
 cudaError_t cudaEventElapsedTime(float *ms, void *a, void *b) { *ms = 0; return 0; }
+/* host library (executor): streams are opaque handles */
+cudaError_t cudaStreamCreateWithFlags(void **s, unsigned f) { *s = malloc(8); return 0; }
+cudaError_t cudaStreamCreate(void **s) { *s = malloc(8); return 0; }
+cudaError_t cudaStreamDestroy(void *s) { free(s); return 0; }
+cudaError_t cudaStreamWaitEvent(void *s, void *e, unsigned f) { return 0; }

@@ -28,6 +28,8 @@ EXPORTS = [
     "dalib200ResamplePlanCreate", "dalib200ResamplePlanDestroy", "dalib200ResamplePlanSetup", "dalib200ResampleLaunch",
     "dalib200ResamplePlanGetOrder",
     "dalib200ResamplePlanGetPath",
+    "dalib200Resample3DPlanCreate", "dalib200Resample3DPlanDestroy", "dalib200Resample3DPlanSetup", "dalib200Resample3DLaunch",
+    "dalib200Resample3DPlanGetOrder",
     "dalib200CmnPlanCreate", "dalib200CmnPlanDestroy", "dalib200CmnPlanSetup", "dalib200CmnLaunch",
     "dalib200WarpPlanCreate", "dalib200WarpPlanDestroy", "dalib200WarpPlanSetup", "dalib200WarpLaunch", "dalib200WarpPlanGetPath", "dalib200AffineInverse",
     "dalib200PointwisePlanCreate", "dalib200PointwisePlanDestroy", "dalib200LinearTransformSetup", "dalib200ColorSpaceSetup",
@@ -68,6 +70,12 @@ class ResampleSample(C.Structure):
     _fields_ = [("in_h", C.c_int32), ("in_w", C.c_int32), ("channels", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
                 ("use_roi", C.c_int32 * 2), ("roi_start", C.c_float * 2), ("roi_end", C.c_float * 2),
                 ("min_filter", FilterDesc * 2), ("mag_filter", FilterDesc * 2)]
+
+
+class Resample3DSample(C.Structure):
+    _fields_ = [("in_shape", C.c_int32 * 3), ("channels", C.c_int32), ("out_shape", C.c_int32 * 3),
+                ("use_roi", C.c_int32 * 3), ("roi_start", C.c_float * 3), ("roi_end", C.c_float * 3),
+                ("min_filter", FilterDesc * 3), ("mag_filter", FilterDesc * 3)]
 
 
 class CmnSample(C.Structure):

@@ -1503,3 +1503,41 @@ int dalib200ResampleLaunch(dalib200ResamplePlan *p, const void *const *in_ptrs, 
 } DB_API_CATCH
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// The per-axis host setup exported to the 3-D planner (resample_axis.h).  Appended at the end of the file so that the line tables of
+// the kernels above do not move.
+#include "resample_axis.h"
+namespace dalib200 {
+
+int AxisSetupShared(AxisShared *s, int in_size, int out_size, bool use_roi, float roi_start, float roi_end,
+                    dalib200FilterDesc min_filter, dalib200FilterDesc mag_filter) {
+  AxisSetup a;
+  int rc = SetupAxis(a, in_size, out_size, use_roi, roi_start, roi_end, min_filter, mag_filter);
+  if (rc) return rc;
+  s->in_size = a.in_size; s->out_size = a.out_size; s->ftype = a.ftype; s->support = a.support;
+  s->roi_lo = a.roi_lo; s->roi_hi = a.roi_hi; s->origin = a.origin; s->scale = a.scale;
+  s->coeffs = a.filter.coeffs; s->num_coeffs = a.filter.num_coeffs; s->anchor = a.filter.anchor; s->fscale = a.filter.scale;
+  return 0;
+}
+
+void AxisFirTableShared(const AxisShared *s, float origin, int32_t *idx, float *coef) {
+  AxisSetup a;
+  a.in_size = s->in_size; a.out_size = s->out_size; a.ftype = s->ftype; a.support = s->support;
+  a.roi_lo = s->roi_lo; a.roi_hi = s->roi_hi; a.origin = origin; a.scale = s->scale;
+  a.filter = { s->coeffs, s->num_coeffs, s->anchor, s->fscale };
+  a.base = 0; a.extent = s->in_size;
+  std::vector<int32_t> arena;
+  AxisTableRef ref;
+  BuildTable(arena, ref, a, 0);
+  memcpy(idx, arena.data() + ref.idx_off, sizeof(int32_t) * (size_t)s->out_size);
+  memcpy(coef, arena.data() + ref.coef_off, sizeof(float) * (size_t)s->out_size * s->support);
+}
+
+void HorzSimdFlagsShared(const int32_t *idx, int ow, int iw, int support, uint8_t *flags) {
+  std::vector<int32_t> arena(idx, idx + ow);
+  int off = BuildHorzFlags(arena, 0, ow, iw, support);
+  memcpy(flags, reinterpret_cast<const uint8_t *>(arena.data() + off), (size_t)ow);
+}
+
+}  // namespace dalib200

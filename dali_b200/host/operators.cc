@@ -15,6 +15,7 @@
 //   Spectrogram            dali/operators/signal/fft/spectrogram.cc:30-311
 //   MelFilterBank          dali/operators/audio/mel_scale/mel_filter_bank.cc:22-117
 // There is no CPU implementation: the ops are registered for GPU / Mixed only.
+#include <array>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -464,8 +465,8 @@ DALI_SCHEMA(Resize)
     .NumInput(1).NumOutput(1).AllowSequences()
     .AddOptionalArgNoDefault("resize_x", "Length of the X dimension of the resized image (0 = keep aspect).", true)
     .AddOptionalArgNoDefault("resize_y", "Length of the Y dimension of the resized image (0 = keep aspect).", true)
-    .AddOptionalArgNoDefault("resize_z", "not supported by the GPU path (2-D images only)", true)
-    .AddOptionalArgNoDefault("size", "Desired output size (H, W).", true)
+    .AddOptionalArgNoDefault("resize_z", "Length of the Z dimension of the resized volume (DHWC / FDHWC inputs).", true)
+    .AddOptionalArgNoDefault("size", "Desired output size (H, W) or (D, H, W).", true)
     .AddOptionalArgNoDefault("resize_shorter", "Length of the shorter dimension of the resized image.", true)
     .AddOptionalArgNoDefault("resize_longer", "Length of the longer dimension of the resized image.", true)
     .AddOptionalArgNoDefault("mode", "default | stretch | not_larger | not_smaller")
@@ -524,21 +525,21 @@ void AdjustOutputSize(float *out_size, const float *in_size, int ndim, Mode mode
   }
 }
 
-struct Params { int dst[2]; float lo[2], hi[2]; };
+struct Params { int dst[3]; float lo[3], hi[3]; };
 
-// resize_attr_base.h:51-119 (alignment = centre, size_round_fn = round_int)
-void CalculateSampleParams(Params &p, float req[2], float in_lo[2], float in_hi[2], bool adjust_roi, bool empty_input, Mode mode,
-                           const float *max_size) {
-  float in_size[2];
-  for (int d = 0; d < 2; d++) {
+// resize_attr_base.h:51-119 (alignment = centre, size_round_fn = round_int); ndim = 2 (images) or 3 (volumes)
+void CalculateSampleParams(Params &p, float *req, float *in_lo, float *in_hi, bool adjust_roi, bool empty_input, Mode mode,
+                           const float *max_size, int ndim = 2) {
+  float in_size[3];
+  for (int d = 0; d < ndim; d++) {
     float sz = in_hi[d] - in_lo[d];
     if (sz < 0) { std::swap(in_hi[d], in_lo[d]); req[d] = -req[d]; sz = -sz; }
     in_size[d] = sz;
   }
-  AdjustOutputSize(req, in_size, 2, mode, max_size);
-  for (int d = 0; d < 2; d++) DALI_ENFORCE(in_lo[d] != in_hi[d] || req[d] == 0, "Cannot produce non-empty output from empty input");
+  AdjustOutputSize(req, in_size, ndim, mode, max_size);
+  for (int d = 0; d < ndim; d++) DALI_ENFORCE(in_lo[d] != in_hi[d] || req[d] == 0, "Cannot produce non-empty output from empty input");
   const int min_size = empty_input ? 0 : 1;
-  for (int d = 0; d < 2; d++) {
+  for (int d = 0; d < ndim; d++) {
     p.lo[d] = in_lo[d]; p.hi[d] = in_hi[d];
     const float out_sz = req[d];
     const bool flip = out_sz < 0;
@@ -584,9 +585,9 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
     has_x_ = spec.ArgumentDefined("resize_x"); has_y_ = spec.ArgumentDefined("resize_y");
     has_size_ = spec.ArgumentDefined("size"); has_max_ = spec.ArgumentDefined("max_size");
     const bool has_mode = spec.ArgumentDefined("mode");
-    DALI_ENFORCE(!spec.ArgumentDefined("resize_z"), "Resize: `resize_z` (volumetric data) is not supported by the GPU path");
+    has_z_ = name == std::string("Resize") && spec.ArgumentDefined("resize_z");
     DALI_ENFORCE(!spec.GetArgument<bool>("save_attrs"), "Resize: `save_attrs` is not supported");
-    DALI_ENFORCE((has_x_ || has_y_) + has_size_ + has_shorter_ + has_longer_ == 1,
+    DALI_ENFORCE((has_x_ || has_y_ || has_z_) + has_size_ + has_shorter_ + has_longer_ == 1,
                  "Exactly one method of specifying size must be used. The available methods:\n"
                  "    - separate resize_x, resize_y, resize_z arguments\n    - size argument\n    - resize_longer\n    - resize_shorter");
     DALI_ENFORCE(has_shorter_ + has_longer_ + has_mode <= 1, "`resize_shorter`, ``resize_longer`` and ``mode`` arguments are mutually exclusive");
@@ -606,7 +607,11 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
     CheckStatus(dalib200ResamplePlanCreate(&plan_, max_batch_size_ * 64), "Resize");
     plan_cap_ = max_batch_size_ * 64;
   }
-  ~ResizeGPU() override { dalib200ResamplePlanDestroy(plan_); if (plan_planar_) dalib200ResamplePlanDestroy(plan_planar_); }
+  ~ResizeGPU() override {
+    dalib200ResamplePlanDestroy(plan_);
+    if (plan_planar_) dalib200ResamplePlanDestroy(plan_planar_);
+    if (plan3_) dalib200Resample3DPlanDestroy(plan3_);
+  }
 
  protected:
   bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
@@ -616,6 +621,8 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
     DALIDataType out_type = in.type();
     if (spec_.ArgumentDefined("dtype")) out_type = spec_.GetArgument<DALIDataType>("dtype");
     DALI_ENFORCE(out_type == in.type() || out_type == DALI_FLOAT, "Resize: output type must be the same as input or FLOAT");
+    volumes_ = in.GetLayout().str() == "DHWC" || in.GetLayout().str() == "FDHWC";
+    if (volumes_) return SetupVolumes(out, ws, out_type);
     frames_ = ExpandFrames(in.shape(), in.GetLayout(), "Resize");
     const int nf = frames_.num_frames();
     if (nf > plan_cap_) { dalib200ResamplePlanDestroy(plan_); plan_ = nullptr; plan_cap_ = nf; CheckStatus(dalib200ResamplePlanCreate(&plan_, nf), "Resize"); }
@@ -631,7 +638,7 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
       const int fs = frames_.first_spatial;
       const float in_h = static_cast<float>(s[fs]), in_w = static_cast<float>(s[fs + 1]);
       float req[2] = {0, 0};     // (H, W) order
-      if (has_x_ || has_y_) {
+      if (has_x_ || has_y_ || has_z_) {          // `resize_z` alone on 2-D data: both extents unspecified (resize_attr.cc:214-245)
         if (has_y_) req[0] = spec_.GetArgument<float>("resize_y", &ws, i);
         if (has_x_) req[1] = spec_.GetArgument<float>("resize_x", &ws, i);
       } else if (has_shorter_ || has_longer_) {
@@ -720,6 +727,7 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
   void RunImpl(Workspace &ws) override {
     const auto &in = ws.Input<GPUBackend>(0);
     auto &out = ws.Output<GPUBackend>(0);
+    if (volumes_) { RunVolumes(ws); return; }
     out.SetLayout(in.GetLayout().empty() ? TensorLayout(frames_.first_spatial ? "FHWC" : "HWC") : in.GetLayout());
     auto ip = FramePtrs(in, frames_, TypeSize(in.type()));
     std::vector<void *> op(frames_.num_frames());
@@ -755,7 +763,121 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
     }
   }
 
+  // ---- volumes (DHWC, FDHWC): ResizeAttr with spatial_ndim = 3 (resize_attr.cc:102-255) over dalib200Resample3D*; the frames of an
+  // FDHWC sample are independent volumes with the sample's parameters (SequenceOperator, sequence_operator.h:57-110)
+  bool SetupVolumes(std::vector<OutputDesc> &out, const Workspace &ws, DALIDataType out_type) {
+    const auto &in = ws.Input<GPUBackend>(0);
+    const int n = in.num_samples();
+    const int fs = in.GetLayout().str() == "FDHWC" ? 1 : 0;
+    DALI_ENFORCE(in.shape().sample_dim() == fs + 4, "Resize: layout \"", in.GetLayout().str(), "\" does not match a ", in.shape().sample_dim(), "-D input");
+    if (producer_) { std::vector<uint8_t> none(n, 0), granted; producer_->SelectPlanar(none, granted); }
+    std::vector<float> max_size(3, std::nextafter(static_cast<float>(std::numeric_limits<int>::max()), 0.0f));
+    if (has_max_) max_size = spec_.GetFloatVecArgument("max_size", &ws, 0, 3);
+    const bool has_interp = spec_.ArgumentDefined("interp_type"), has_min = spec_.ArgumentDefined("min_filter"),
+               has_mag = spec_.ArgumentDefined("mag_filter");
+    vsamples_.clear();
+    vol_sample_.clear(); vol_offset_.clear();
+    out_dhw_.assign(n, {0, 0, 0});
+    for (int i = 0; i < n; i++) {
+      const int64_t *s = in.shape().tensor_shape_span(i);
+      const float isz[3] = { static_cast<float>(s[fs]), static_cast<float>(s[fs + 1]), static_cast<float>(s[fs + 2]) };
+      float req[3] = {0, 0, 0};     // (D, H, W): the shape order of `size`
+      if (has_x_ || has_y_ || has_z_) {
+        if (has_z_) req[0] = spec_.GetArgument<float>("resize_z", &ws, i);
+        if (has_y_) req[1] = spec_.GetArgument<float>("resize_y", &ws, i);
+        if (has_x_) req[2] = spec_.GetArgument<float>("resize_x", &ws, i);
+      } else if (has_shorter_ || has_longer_) {
+        req[0] = req[1] = req[2] = spec_.GetArgument<float>(has_shorter_ ? "resize_shorter" : "resize_longer", &ws, i);
+      } else {
+        auto v = spec_.GetFloatVecArgument("size", &ws, i, 3);
+        req[0] = v[0]; req[1] = v[1]; req[2] = v[2];
+      }
+      float lo[3] = {0, 0, 0}, hi[3] = { isz[0], isz[1], isz[2] };
+      if (has_roi_) {          // resize_attr.cc:125-160
+        auto rs = spec_.GetFloatVecArgument("roi_start", &ws, i, 3), re = spec_.GetFloatVecArgument("roi_end", &ws, i, 3);
+        for (int d = 0; d < 3; d++) if (isz[d] > 0) {
+          double l = rs[d], h = re[d];
+          if (roi_relative_) { l *= isz[d]; h *= isz[d]; }
+          if (std::fabs(h - l) < 1e-3f) { float off = l <= h ? 0.5f * 1e-3f : -0.5f * 1e-3f; l -= off; h += off; }
+          lo[d] = static_cast<float>(l); hi[d] = static_cast<float>(h);
+        }
+      }
+      resize_detail::Params p;
+      const bool empty_input = in.shape().tensor_size(i) == 0;
+      resize_detail::CalculateSampleParams(p, req, lo, hi, subpixel_scale_, empty_input, mode_, has_max_ ? max_size.data() : nullptr, 3);
+      int interp = spec_.GetArgument<int>("interp_type", &ws, i);
+      int minf = DALIB200_FILTER_TRIANGULAR, magf = DALIB200_FILTER_LINEAR;
+      auto conv = [](int t, bool aa) {      // resampling_attr.cc:76-133
+        if (aa && t == DALI_INTERP_LINEAR) t = DALI_INTERP_TRIANGULAR; else if (!aa && t == DALI_INTERP_TRIANGULAR) t = DALI_INTERP_LINEAR;
+        return Interp2Filter(t);
+      };
+      if (has_min) minf = conv(spec_.GetArgument<int>("min_filter", &ws, i), antialias_); else if (has_interp) minf = conv(interp, antialias_);
+      if (has_mag) magf = conv(spec_.GetArgument<int>("mag_filter", &ws, i), false); else if (has_interp) magf = conv(interp, false);
+      out_dhw_[i] = { p.dst[0], p.dst[1], p.dst[2] };
+      const int64_t frames = fs ? s[0] : 1;
+      const int64_t in_vol = s[fs] * s[fs + 1] * s[fs + 2] * s[fs + 3];
+      for (int64_t k = 0; k < frames; k++) {
+        dalib200Resample3DSample r;
+        memset(&r, 0, sizeof(r));
+        r.channels = static_cast<int>(s[fs + 3]);
+        for (int d = 0; d < 3; d++) {
+          r.in_shape[d] = static_cast<int>(s[fs + d]); r.out_shape[d] = p.dst[d];
+          r.use_roi[d] = p.lo[d] != p.hi[d];
+          r.roi_start[d] = p.lo[d]; r.roi_end[d] = p.hi[d];
+          r.min_filter[d] = { minf, antialias_ ? 1 : 0, 0.0f };
+          r.mag_filter[d] = { magf, 0, 0.0f };
+        }
+        vsamples_.push_back(r);
+        vol_sample_.push_back(i);
+        vol_offset_.push_back(k * in_vol);
+      }
+    }
+    const int nv = static_cast<int>(vsamples_.size());
+    if (nv > plan3_cap_ || !plan3_) {
+      if (plan3_) dalib200Resample3DPlanDestroy(plan3_);
+      plan3_ = nullptr; plan3_cap_ = std::max(nv, max_batch_size_);
+      CheckStatus(dalib200Resample3DPlanCreate(&plan3_, plan3_cap_), "Resize");
+    }
+    CheckStatus(dalib200Resample3DPlanSetup(plan3_, nv, vsamples_.data(), in.type() == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT,
+                                            out_type == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT), "Resize");
+    out.resize(1);
+    out[0].type = out_type;
+    out[0].shape.resize(n, in.shape().sample_dim());
+    for (int i = 0; i < n; i++) {
+      TensorShape sh = in.shape().tensor_shape(i);
+      for (int d = 0; d < 3; d++) sh[fs + d] = out_dhw_[i][d];
+      out[0].shape.set_tensor_shape(i, sh);
+    }
+    out_type_ = out_type;
+    return true;
+  }
+
+  void RunVolumes(Workspace &ws) {
+    const auto &in = ws.Input<GPUBackend>(0);
+    auto &out = ws.Output<GPUBackend>(0);
+    out.SetLayout(in.GetLayout());
+    if (producer_) producer_->RunDeferred(ws.stream());
+    const size_t nv = vsamples_.size();
+    std::vector<const void *> ip(nv);
+    std::vector<void *> op(nv);
+    std::vector<int64_t> next(out.num_samples(), 0);
+    for (size_t k = 0; k < nv; k++) {
+      const int s = vol_sample_[k];
+      ip[k] = static_cast<const uint8_t *>(in.raw_tensor(s)) + vol_offset_[k] * TypeSize(in.type());
+      op[k] = static_cast<uint8_t *>(out.raw_mutable_tensor(s)) + next[s];
+      next[s] += static_cast<int64_t>(out_dhw_[s][0]) * out_dhw_[s][1] * out_dhw_[s][2] * vsamples_[k].channels * TypeSize(out_type_);
+    }
+    CheckStatus(dalib200Resample3DLaunch(plan3_, ip.data(), op.data(), ws.stream()), "Resize");
+  }
+
  private:
+  dalib200Resample3DPlan *plan3_ = nullptr;
+  int plan3_cap_ = 0;
+  bool volumes_ = false, has_z_ = false;
+  std::vector<dalib200Resample3DSample> vsamples_;
+  std::vector<int> vol_sample_;
+  std::vector<int64_t> vol_offset_;
+  std::vector<std::array<int, 3>> out_dhw_;
   dalib200ResamplePlan *plan_ = nullptr, *plan_planar_ = nullptr;
   int plan_cap_ = 0, planar_cap_ = 0;
   PlanarProducer *producer_ = nullptr;
@@ -2190,6 +2312,20 @@ extern "C" int dalihTestResizeParams(int mode, const float *requested_hw, const 
     dali::resize_detail::CalculateSampleParams(p, req, lo, hi, subpixel_scale != 0, false, static_cast<dali::resize_detail::Mode>(mode),
                                                max_size_hw_or_null);
     for (int d = 0; d < 2; d++) { dst_hw[d] = p.dst[d]; lo_hw[d] = p.lo[d]; hi_hw[d] = p.hi[d]; }
+    return 0;
+  } catch (...) { return 1; }
+}
+
+// The same for volumes (spatial_ndim = 3; arrays in shape order depth, height, width): resize_attr_test.cc Resize3D* vectors.
+extern "C" int dalihTestResizeParams3D(int mode, const float *requested_dhw, const float *in_lo_dhw, const float *in_hi_dhw,
+                                       int subpixel_scale, const float *max_size_dhw_or_null, int *dst_dhw, float *lo_dhw, float *hi_dhw) {
+  try {
+    float req[3], lo[3], hi[3];
+    for (int d = 0; d < 3; d++) { req[d] = requested_dhw[d]; lo[d] = in_lo_dhw[d]; hi[d] = in_hi_dhw[d]; }
+    dali::resize_detail::Params p;
+    dali::resize_detail::CalculateSampleParams(p, req, lo, hi, subpixel_scale != 0, false, static_cast<dali::resize_detail::Mode>(mode),
+                                               max_size_dhw_or_null, 3);
+    for (int d = 0; d < 3; d++) { dst_dhw[d] = p.dst[d]; lo_dhw[d] = p.lo[d]; hi_dhw[d] = p.hi[d]; }
     return 0;
   } catch (...) { return 1; }
 }

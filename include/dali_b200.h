@@ -184,6 +184,31 @@ int dalib200ResamplePlanGetOrder(const dalib200ResamplePlan *plan, int sample);
 int dalib200ResamplePlanGetPath(const dalib200ResamplePlan *plan, int sample);
 
 /* ------------------------------------------------------------------------------------------------
+ * Separable resampling of volumes (DHWC), three passes.  Replaces the spatial_ndim = 3 instances of kernels::ResampleGPU /
+ * SeparableResamplingGPUImpl (dali/kernels/imgproc/resample/separable_impl.h:110-203, resampling_setup.cc:232-337) behind
+ * ResizeBase<GPUBackend> (dali/operators/image/resize/resize_base.cc, resize_op_impl_gpu.h); numerics follow
+ * SeparableResampleCPU<Out, In, 3> (separable_cpu.h:124-249) -- the parity target. */
+typedef struct dalib200Resample3DPlan dalib200Resample3DPlan;
+
+typedef struct {
+  /* index [0] = depth (z), [1] = height (y), [2] = width (x): shape order = the reference's ResamplingParams3D order */
+  int32_t in_shape[3], channels;
+  int32_t out_shape[3];
+  int32_t use_roi[3];
+  float roi_start[3], roi_end[3];
+  dalib200FilterDesc min_filter[3], mag_filter[3];
+} dalib200Resample3DSample;
+
+int dalib200Resample3DPlanCreate(dalib200Resample3DPlan **plan, int max_batch);
+int dalib200Resample3DPlanDestroy(dalib200Resample3DPlan *plan);
+int dalib200Resample3DPlanSetup(dalib200Resample3DPlan *plan, int n, const dalib200Resample3DSample *samples,
+                                int in_dtype /* UINT8 | FLOAT */, int out_dtype /* UINT8 | FLOAT */);
+/* in_ptrs[i]: device DHWC in_dtype; out_ptrs[i]: device DHWC out_dtype [out_shape][channels] */
+int dalib200Resample3DLaunch(dalib200Resample3DPlan *plan, const void *const *in_ptrs, void *const *out_ptrs, dalib200Stream_t stream);
+/* introspection used by the tests: the pass order chosen for a sample, axes numbered 0 = x (width), 1 = y, 2 = z (depth) */
+int dalib200Resample3DPlanGetOrder(const dalib200Resample3DPlan *plan, int sample, int32_t order[3]);
+
+/* ------------------------------------------------------------------------------------------------
  * CropMirrorNormalize.  Replaces kernels::SliceHwc2HwcChwNormalizeGPU::Run
  * (dali/kernels/slice/slice_hwc2chw_normalize_gpu.cu:863-1020) and the generic SliceFlipNormalize kernels;
  * numerics follow SliceFlipNormalizePermutePadCpu (slice_flip_normalize_permute_pad_cpu.h:37-46). */

@@ -165,6 +165,42 @@ def ref_resample(img, out_hw, min_filter=(F_LINEAR, 1, 0.0), mag_filter=(F_LINEA
     return _resample(ref().ref_resample_hwc, img, out_hw, min_filter, mag_filter, out_dtype, roi, want_order)
 
 
+def _resample3(fn, vol, out_dhw, min_filter, mag_filter, out_dtype, roi, want_order):
+    vol = np.ascontiguousarray(vol)
+    assert vol.ndim == 4 and vol.dtype in (np.uint8, np.float32)
+    Cn = vol.shape[3]
+    out_dtype = np.dtype(out_dtype or vol.dtype)
+    out = np.empty(tuple(int(v) for v in out_dhw) + (Cn,), out_dtype)
+    def triple(f):
+        return [_fd(x) for x in f] if isinstance(f, list) else [_fd(f)] * 3
+    minf = (FilterDesc * 3)(*triple(min_filter))
+    magf = (FilterDesc * 3)(*triple(mag_filter))
+    ish = (C.c_int * 3)(*vol.shape[:3])
+    osh = (C.c_int * 3)(*[int(v) for v in out_dhw])
+    use, rs, re = (C.c_int * 3)(0, 0, 0), (C.c_float * 3)(0, 0, 0), (C.c_float * 3)(0, 0, 0)
+    if roi is not None:  # ((z0, y0, x0), (z1, y1, x1)); None entries = no ROI on that axis
+        for d in range(3):
+            if roi[0][d] is not None:
+                use[d], rs[d], re[d] = 1, roi[0][d], roi[1][d]
+    dt = lambda a: 0 if a.dtype == np.uint8 else 1
+    order = (C.c_int * 3)(-1, -1, -1)
+    rc = fn(_p(vol), dt(vol), ish, Cn, _p(out), dt(out), osh, minf, magf, use, rs, re, order)
+    if rc != 0:
+        raise RuntimeError(f"resample3d rc={rc}")
+    return (out, list(order)) if want_order else out
+
+
+def resample3d(vol, out_dhw, min_filter=(F_LINEAR, 1, 0.0), mag_filter=(F_LINEAR, 1, 0.0), out_dtype=None, roi=None,
+               want_order=False):
+    """DHWC volume, separable_cpu.h with spatial_ndim = 3 (oracle/imgproc_oracle.c: oracle_resample_dhwc)."""
+    return _resample3(lib().oracle_resample_dhwc, vol, out_dhw, min_filter, mag_filter, out_dtype, roi, want_order)
+
+
+def ref_resample3d(vol, out_dhw, min_filter=(F_LINEAR, 1, 0.0), mag_filter=(F_LINEAR, 1, 0.0), out_dtype=None, roi=None,
+                   want_order=False):
+    return _resample3(ref().ref_resample_dhwc, vol, out_dhw, min_filter, mag_filter, out_dtype, roi, want_order)
+
+
 # ------------------------------------------------------------------------------------------- CMN
 def float2half(x):
     x = np.ascontiguousarray(x, np.float32)

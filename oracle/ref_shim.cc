@@ -101,9 +101,47 @@ int RunResample(const void *in, int H, int W, int C, void *out, int outH, int ou
   k.Run(ctx, tout, tin, params);
   return 0;
 }
+
+template <typename Out, typename In>
+int RunResample3D(const void *in, const int *ish, int C, void *out, const int *osh,
+                  const FilterDescC *minf, const FilterDescC *magf, const int *use_roi,
+                  const float *roi_start, const float *roi_end, int *order) {
+  resampling::SeparableResampleCPU<Out, In, 3> k;
+  KernelContext ctx;
+  MallocScratch scratch;
+  ctx.scratchpad = &scratch;
+  ResamplingParams3D p;
+  for (int d = 0; d < 3; d++) {
+    p[d].output_size = osh[d];
+    p[d].min_filter = FilterDesc(static_cast<ResamplingFilterType>(minf[d].type), minf[d].antialias != 0, minf[d].radius);
+    p[d].mag_filter = FilterDesc(static_cast<ResamplingFilterType>(magf[d].type), magf[d].antialias != 0, magf[d].radius);
+    if (use_roi && use_roi[d]) p[d].roi = ResamplingParams::ROI(roi_start[d], roi_end[d]);
+  }
+  InTensorCPU<In, 4> tin(static_cast<const In *>(in), TensorShape<4>(ish[0], ish[1], ish[2], C));
+  OutTensorCPU<Out, 4> tout(static_cast<Out *>(out), TensorShape<4>(osh[0], osh[1], osh[2], C));
+  k.Setup(ctx, tin, p);
+  if (order) for (int i = 0; i < 3; i++) order[i] = k.setup.desc.order[i];
+  k.Run(ctx, tout, tin, p);
+  return 0;
+}
 }  // namespace
 
 extern "C" {
+
+// 3-D (DHWC) volumes: shape arrays [0] = depth, [1] = height, [2] = width (ResamplingParams3D order); order[3] in vec numbering (0 = x)
+int ref_resample_dhwc(const void *in, int in_dtype, const int *in_shape, int C, void *out, int out_dtype, const int *out_shape,
+                      const FilterDescC *minf, const FilterDescC *magf, const int *use_roi, const float *roi_start,
+                      const float *roi_end, int *order) {
+  try {
+    if (in_dtype == 0 && out_dtype == 0)
+      return RunResample3D<uint8_t, uint8_t>(in, in_shape, C, out, out_shape, minf, magf, use_roi, roi_start, roi_end, order);
+    if (in_dtype == 0 && out_dtype == 1)
+      return RunResample3D<float, uint8_t>(in, in_shape, C, out, out_shape, minf, magf, use_roi, roi_start, roi_end, order);
+    if (in_dtype == 1 && out_dtype == 1)
+      return RunResample3D<float, float>(in, in_shape, C, out, out_shape, minf, magf, use_roi, roi_start, roi_end, order);
+    return -2;
+  } catch (...) { return -1; }
+}
 
 // dtype: 0 = u8, 1 = f32 ; arrays indexed [0] = y, [1] = x (the reference's params order)
 int ref_resample_hwc(const void *in, int in_dtype, int H, int W, int C, void *out, int out_dtype,

@@ -296,3 +296,39 @@ def spectrogram_mel_fused(sigs, nfilter=128, sample_rate=16000.0, freq_high=8000
                                                        capi.ptr_array(mels), capi.stream_handle()))
     torch.cuda.synchronize()
     return ([o.cpu().numpy() for o in specs] if keep_spectrogram else None), [o.cpu().numpy() for o in mels]
+
+
+def resample3d(vols, out_dhws, min_filter, mag_filter, out_dtype=None, rois=None, want_order=False, plan=None):
+    """DHWC volumes through dalib200Resample3D* (per-axis filter lists in shape order [z, y, x])."""
+    import ctypes as C
+    torch = _torch()
+    n = len(vols)
+    samples = (capi.Resample3DSample * n)()
+    for i, v in enumerate(vols):
+        s, roi = samples[i], rois[i] if rois else None
+        for d in range(3):
+            s.in_shape[d], s.out_shape[d] = int(v.shape[d]), int(out_dhws[i][d])
+            s.min_filter[d] = capi.FilterDesc(*[t(x) for t, x in zip((int, int, float), min_filter[d])])
+            s.mag_filter[d] = capi.FilterDesc(*[t(x) for t, x in zip((int, int, float), mag_filter[d])])
+            if roi is not None and roi[0][d] is not None:
+                s.use_roi[d], s.roi_start[d], s.roi_end[d] = 1, roi[0][d], roi[1][d]
+        s.channels = int(v.shape[3])
+    in_dt = capi.UINT8 if vols[0].dtype == np.uint8 else capi.FLOAT
+    out_dtype = np.dtype(out_dtype or vols[0].dtype)
+    out_dt = capi.UINT8 if out_dtype == np.uint8 else capi.FLOAT
+    plan = plan or capi.Plan("Resample3D", max(n, 1))
+    capi.check(capi.lib().dalib200Resample3DPlanSetup(plan.handle, n, samples, in_dt, out_dt))
+    din = to_dev(vols)
+    outs = [torch.empty(tuple(int(x) for x in o) + (v.shape[3],), dtype=torch.uint8 if out_dt == capi.UINT8 else torch.float32, device="cuda")
+            for o, v in zip(out_dhws, vols)]
+    capi.check(capi.lib().dalib200Resample3DLaunch(plan.handle, capi.ptr_array(din), capi.ptr_array(outs), capi.stream_handle()))
+    torch.cuda.synchronize()
+    res = [o.cpu().numpy() for o in outs]
+    if want_order:
+        orders = []
+        for i in range(n):
+            o = (C.c_int32 * 3)()
+            capi.check(capi.lib().dalib200Resample3DPlanGetOrder(plan.handle, i, o))
+            orders.append(list(o))
+        return res, orders
+    return res

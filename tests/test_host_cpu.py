@@ -111,6 +111,56 @@ def test_resize_subpixel_roi_adjustment():
     assert lo[0] > 0 and abs((hi[0] - lo[0]) - 30 * 75 / 75.3) < 1e-3 and abs((lo[0] + hi[0]) / 2 - 15) < 1e-4
 
 
+def _resize_params3(mode, req, hi, lo=(0, 0, 0), subpixel=True, max_size=None):
+    lib = backend.lib()
+    f3 = lambda v: (C.c_float * 3)(*v)
+    dst, olo, ohi = (C.c_int * 3)(), (C.c_float * 3)(), (C.c_float * 3)()
+    ms = f3(max_size) if max_size is not None else None
+    assert lib.dalihTestResizeParams3D(mode, f3(req), f3(lo), f3(hi), int(subpixel), ms, dst, olo, ohi) == 0
+    return list(dst), list(olo), list(ohi)
+
+
+def test_resize_size_rules_for_volumes_reference_kats():
+    """dali/operators/image/resize/resize_attr_test.cc, the Resize3D* cases (D, H, W order)."""
+    import math
+    # resize_z=480 alone (:129-143): the other extents follow the depth scale
+    assert _resize_params3(DEFAULT, (480, 0, 0), (512, 768, 1024))[0] == [480, 720, 960]
+    assert _resize_params3(DEFAULT, (480, 0, 0), (400, 320, 240))[0] == [480, 384, 288]
+    # separate arguments (:146-172)
+    assert _resize_params3(DEFAULT, (140, 130, 120), (123, 234, 345)) == ([140, 130, 120], [0.0, 0.0, 0.0], [123.0, 234.0, 345.0])
+    # missing y, default mode: geometric mean of the two scales; the ROI of the rounded axis shrinks about its centre (:174-229)
+    for (z, shape) in ((140, (123, 234, 345)), (150, (321, 432, 543))):
+        h = shape[1]
+        sub = h * math.sqrt(z / shape[0] * 120 / shape[2])
+        y = int(round(sub))
+        dst, lo, hi = _resize_params3(DEFAULT, (z, 0, 120), shape)
+        assert dst == [z, y, 120]
+        c = h * 0.5
+        assert lo[0] == 0 and lo[2] == 0 and hi[0] == shape[0] and hi[2] == shape[2]
+        assert abs(lo[1] - (c - c * y / sub)) < 1e-3 and abs(hi[1] - (c + c * y / sub)) < 1e-3
+        dst, lo, hi = _resize_params3(DEFAULT, (z, 0, 120), shape, subpixel=False)
+        assert dst == [z, y, 120] and lo == [0.0, 0.0, 0.0] and hi == [float(v) for v in shape]
+        # stretch: the missing extent is left alone (:231-258)
+        assert _resize_params3(STRETCH, (z, 0, 120), shape)[0] == [z, h, 120]
+    # flips (:303-333): negative sizes swap lo and hi
+    y0 = int(round(234 * math.sqrt(140.0 / 123 * 120 / 345)))
+    dst, lo, hi = _resize_params3(DEFAULT, (-140, 0, 120), (123, 234, 345), subpixel=False)
+    assert dst == [140, y0, 120] and lo == [123.0, 0.0, 0.0] and hi == [0.0, 234.0, 345.0]
+    dst, lo, hi = _resize_params3(STRETCH, (150, 0, -120), (321, 432, 543), subpixel=False)
+    assert dst == [150, 432, 120] and lo == [0.0, 0.0, 543.0] and hi == [321.0, 432.0, 0.0]
+    # not_larger (:335-366)
+    assert _resize_params3(NOT_LARGER, (0, 400, 500), (1536, 768, 1024))[0] == [750, 375, 500]
+    assert _resize_params3(NOT_LARGER, (0, 400, 500), (32, 320, 240))[0] == [40, 400, 300]
+    assert _resize_params3(NOT_LARGER, (600, 400, 500), (1536, 768, 1024))[0] == [600, 300, 400]
+    assert _resize_params3(NOT_LARGER, (600, 400, 500), (32, 320, 240))[0] == [40, 400, 300]
+    # not_smaller (:368-410), with max_size
+    assert _resize_params3(NOT_SMALLER, (0, 480, 600), (1536, 768, 1024))[0] == [960, 480, 640]
+    assert _resize_params3(NOT_SMALLER, (0, 480, 600), (32, 320, 240))[0] == [80, 800, 600]
+    assert _resize_params3(NOT_SMALLER, (160, 480, 600), (32, 320, 240))[0] == [160, 1600, 1200]
+    assert _resize_params3(NOT_SMALLER, (160, 480, 600), (1536, 768, 1024), max_size=(720, 720, 720))[0] == [720, 360, 480]
+    assert _resize_params3(NOT_SMALLER, (160, 480, 600), (32, 320, 240), max_size=(720, 720, 720))[0] == [72, 720, 540]
+
+
 def test_external_source_feeding_modes():
     calls = []
 

@@ -61,7 +61,7 @@ def note(name, rc):
     hist[(name, "ok" if rc == 0 else "err")] = hist.get((name, "ok" if rc == 0 else "err"), 0) + 1
 
 
-plans = {k: plan(k, 8) for k in ("Resample", "Cmn", "Warp", "Pointwise", "Spectrogram", "Mel", "Signal", "Generic")}
+plans = {k: plan(k, 8) for k in ("Resample", "Resample3D", "Cmn", "Warp", "Pointwise", "Spectrogram", "Mel", "Signal", "Generic")}
 for it in range(N):
     n = int(rng.integers(0, 9)) if rng.random() < 0.9 else int(rng.choice([9, 100, -1]))
     m = max(n, 1) if n < 64 else 8
@@ -90,6 +90,23 @@ for it in range(N):
             q.pitch_y, q.pitch_c = int(rng.choice([16, 64, 1920, 1936, 17])), int(rng.choice([16, 64, 960, 976, 9]))
             q.width, q.height, q.crop_x, q.crop_y = dim(), dim(), small(0, 64), small(0, 64)
         launch("resample_planar", L.dalib200ResampleLaunchPlanar, plans["Resample"].handle, PI, fake_ptrs(m, 0x7000000000), None)
+    # ---- resample (volumes)
+    V = (capi.Resample3DSample * m)()
+    for s in V:
+        s.channels = small(1, 5)
+        for d in range(3):
+            s.in_shape[d], s.out_shape[d] = dim(1, 200), dim(0, 120)
+            s.use_roi[d] = int(rng.integers(0, 2))
+            s.roi_start[d], s.roi_end[d] = flt(-50, 300), flt(-50, 300)
+            s.min_filter[d] = capi.FilterDesc(code(range(6)), int(rng.integers(0, 2)), flt(0, 8))
+            s.mag_filter[d] = capi.FilterDesc(code(range(6)), int(rng.integers(0, 2)), flt(0, 8))
+    rc = L.dalib200Resample3DPlanSetup(plans["Resample3D"].handle, n, V, code([0, 9]), code([0, 9]))
+    note("resample3d", rc)
+    if rc == 0:
+        launch("resample3d", L.dalib200Resample3DLaunch, plans["Resample3D"].handle, fake_ptrs(m, 0x10000000), fake_ptrs(m, 0x7000000000), None)
+        o3 = (C.c_int32 * 3)()
+        for i in range(max(0, min(n, m))):
+            L.dalib200Resample3DPlanGetOrder(plans["Resample3D"].handle, i, o3)
     # ---- cmn
     Cs = (capi.CmnSample * m)()
     for s in Cs:

@@ -1480,6 +1480,11 @@ using namespace dalib200;  // NOLINT
 namespace {
 
 struct HostHuff { uint8_t bits[17]; uint8_t vals[256]; bool present = false; };
+}  // namespace
+// progressive streams: planner + launch interface of jpeg_prog.cu (included here, behind the kernels, so that their line tables stay put)
+#include "jpeg_prog.h"
+#include "jpeg_prog_plan.h"
+namespace {
 
 struct ParsedJpeg {
   int width = 0, height = 0, ncomp = 0, precision = 8;
@@ -1728,6 +1733,16 @@ struct dalib200JpegPlan {
   cudaEvent_t uploaded = nullptr, img_uploaded = nullptr;
   uint8_t *h_images = nullptr; size_t h_images_cap = 0;
   bool pending = false, img_pending = false, staged = false, smem_opted = false;
+  // progressive (SOF2) samples: their entropy stage runs in jpeg_prog.cu, everything behind it is shared
+  std::vector<dalib200::ProgImage> prog_images;
+  std::vector<dalib200::ProgScan> prog_scans;     // sorted by wave
+  std::vector<dalib200::ProgHuff> prog_huff;
+  std::vector<int> prog_wave_begin;
+  std::vector<int64_t> prog_first_blk;
+  int64_t prog_total_blocks = 0;
+  dalib200::DescArena prog_arena;
+  cudaEvent_t prog_uploaded = nullptr;
+  bool prog_pending = false;
 };
 
 namespace {
@@ -1808,7 +1823,8 @@ int dalib200JpegPlanCreate(dalib200JpegPlan **plan, int max_batch) try {
   auto *p = new dalib200JpegPlan();
   p->max_batch = max_batch;
   if (cudaEventCreateWithFlags(&p->uploaded, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&p->img_uploaded, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&p->img_uploaded, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->prog_uploaded, cudaEventDisableTiming) != cudaSuccess) {
     SetLastError("JpegPlanCreate: cudaEventCreate failed"); delete p; return DALIB200_ERROR_CUDA;
   }
   *plan = p;
@@ -1819,6 +1835,8 @@ int dalib200JpegPlanDestroy(dalib200JpegPlan *p) try {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   if (p->img_uploaded) { cudaEventSynchronize(p->img_uploaded); cudaEventDestroy(p->img_uploaded); }
+  if (p->prog_uploaded) { cudaEventSynchronize(p->prog_uploaded); cudaEventDestroy(p->prog_uploaded); }
+  p->prog_arena.Free();
   if (p->h_stage) cudaFreeHost(p->h_stage);
   if (p->h_images) cudaFreeHost(p->h_images);
   if (p->h_status) cudaFreeHost(p->h_status);
@@ -1893,7 +1911,9 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
   p->units.clear(); p->tables.clear(); p->quants.clear(); p->src_ptr.clear(); p->block_image.clear(); p->wblock_image.clear();
   p->first_quad.assign(n, 0);
   p->first_item.assign(n, 0);
-  std::map<std::string, int> table_cache, quant_cache;
+  p->prog_images.clear(); p->prog_scans.clear(); p->prog_huff.clear(); p->prog_wave_begin.clear(); p->prog_first_blk.clear();
+  p->prog_total_blocks = 0;
+  std::map<std::string, int> table_cache, quant_cache, prog_table_cache;
   size_t raw = 0, clean = 0;
   uint32_t chunks = 0;
   int64_t subseq = 0, coefs = 0, planes = 0;
@@ -1913,7 +1933,13 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
     int rc = ParseHeaders(streams[i], lengths[i], j, true);
     if (rc) { std::string m = dalib200GetLastError(); SetLastError("decoders.image: sample %d: %s", i, m.c_str()); return rc; }
     auto unsupported = [&](const char *what) { SetLastError("decoders.image: sample %d: %s", i, what); return DALIB200_ERROR_UNSUPPORTED; };
-    if (j.progressive) return unsupported("progressive JPEG is not supported by the GPU decoder yet");
+    const bool prog = j.progressive;
+    if (prog) {
+      // the frame layout comes from the frame header: the first scan of a progressive stream need not name every component, and its
+      // Huffman tables are only the first of several snapshots (jpeg_prog_plan.h walks all scans below)
+      j.scan_ncomp = j.ncomp;
+      for (int c = 0; c < j.ncomp; c++) { j.scan_comp[c] = c; j.td[c] = j.ta[c] = 0; }
+    }
     if ((int64_t)j.width * j.height >= (1ll << 31)) return unsupported("images of 2^31 pixels or more are not supported");
     if (j.precision != 8) return unsupported("only 8-bit baseline JPEG is supported");
     if (j.ncomp != 1 && j.ncomp != 3) return unsupported("only 1- or 3-component JPEG is supported");
@@ -1928,7 +1954,7 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
     im.hmax = j.hmax; im.vmax = j.vmax;
     im.mcux = (j.width + 8 * j.hmax - 1) / (8 * j.hmax);
     im.mcuy = (j.height + 8 * j.vmax - 1) / (8 * j.vmax);
-    im.restart_interval = j.restart_interval;
+    im.restart_interval = prog ? 0 : j.restart_interval;      // progressive: the DC values arrive as one run of differences (jpeg_prog_core.h)
     im.out_type = output_type; im.fancy = p->fancy;
     im.is_rgb = j.ncomp == 3 && (j.adobe_transform == 0 ||
                 (j.adobe_transform < 0 && !j.jfif && j.cid[0] == 'R' && j.cid[1] == 'G' && j.cid[2] == 'B'));
@@ -1938,7 +1964,7 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
       im.hs[c] = j.hs[c]; im.vs[c] = j.vs[c]; im.tq[c] = j.tq[c];
       if (!j.qt_present[j.tq[c]]) { SetLastError("decoders.image: sample %d: missing quantisation table", i); return DALIB200_ERROR_BAD_DATA; }
       if (j.td[si] > 1 || j.ta[si] > 1) return unsupported("Huffman table ids above 1 are not supported (baseline allows 0..1)");
-      if (!j.dc[j.td[si]].present || !j.ac[j.ta[si]].present) { SetLastError("decoders.image: sample %d: missing Huffman table", i); return DALIB200_ERROR_BAD_DATA; }
+      if (!prog && (!j.dc[j.td[si]].present || !j.ac[j.ta[si]].present)) { SetLastError("decoders.image: sample %d: missing Huffman table", i); return DALIB200_ERROR_BAD_DATA; }
       for (int v = 0; v < j.vs[c]; v++)
         for (int h = 0; h < j.hs[c]; h++) {
           if (bpm >= kMaxBlocksPerMcu) return unsupported("too many blocks per MCU");
@@ -1950,11 +1976,16 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
     // Huffman tables (dedup by content)
     {
       std::string key;
+      if (prog) key = "progressive";            // never read by a kernel: the image has no units; one zeroed set keeps the index valid
+      else
       for (int t = 0; t < 2; t++) { key.append(reinterpret_cast<const char *>(j.dc[t].bits), 17); key.append(reinterpret_cast<const char *>(j.dc[t].vals), 256); key.push_back(j.dc[t].present); }
+      if (!prog)
       for (int t = 0; t < 2; t++) { key.append(reinterpret_cast<const char *>(j.ac[t].bits), 17); key.append(reinterpret_cast<const char *>(j.ac[t].vals), 256); key.push_back(j.ac[t].present); }
       auto it = table_cache.find(key);
       if (it == table_cache.end()) {
         TableSet ts;
+        if (prog) memset(&ts, 0, sizeof(ts));
+        else
         for (int t = 0; t < 2; t++) {
           BuildDeviceTable(j.dc[t], ts.lut + LutOffset(t), ts.lut16 + LutOffset(t), ts.slow[t], true);
           BuildDeviceTable(j.ac[t], ts.lut + LutOffset(2 + t), ts.lut16 + LutOffset(2 + t), ts.slow[2 + t], false);
@@ -2001,7 +2032,31 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
       local_sub += u.nsub_max;
       p->units.push_back(u);
     };
-    if (j.restart_interval == 0) {
+    if (prog) {
+      // no units: the scans are planned from the whole stream; their bytes are the staged range [scan_begin, scan_end) like a baseline
+      // sample's, so JpegUpload needs no special case
+      dalib200::ProgImage pim;
+      memset(&pim, 0, sizeof(pim));
+      std::string perr;
+      const size_t first_new = p->prog_scans.size();
+      rc = dalib200::PlanProgressive(d, lengths[i], sb, (int)p->prog_images.size(), &pim, p->prog_scans, p->prog_huff, prog_table_cache, &perr);
+      if (rc) { SetLastError("decoders.image: sample %d: %s", i, perr.c_str()); return rc; }
+      for (size_t k = first_new; k < p->prog_scans.size(); k++)
+        if ((size_t)p->prog_scans[k].data_off + p->prog_scans[k].data_len > se - sb) {
+          // a scan that runs into the trimmed end-of-image marker ends in front of it
+          auto &sc = p->prog_scans[k];
+          sc.data_len = sc.data_off >= se - sb ? 0 : (uint32_t)(se - sb - sc.data_off);
+        }
+      if (pim.ncomp != im.ncomp || pim.mcux != im.mcux || pim.mcuy != im.mcuy || pim.bpm != bpm) {
+        SetLastError("decoders.image: sample %d: internal error (progressive frame layout)", i); return DALIB200_ERROR_INTERNAL;
+      }
+      pim.sample = i;
+      pim.raw_off = (int64_t)raw;
+      pim.coef_off = coefs;
+      p->prog_first_blk.push_back(p->prog_total_blocks);
+      p->prog_total_blocks += nmcu * bpm;
+      p->prog_images.push_back(pim);
+    } else if (j.restart_interval == 0) {
       add_unit(sb, se, 0, nmcu);
     } else {
       // split at RSTn markers (host scan; only images that carry DRI pay for it)
@@ -2095,6 +2150,13 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
     }
   }
   BuildWorkLists(p);
+  if (!p->prog_scans.empty()) {
+    std::stable_sort(p->prog_scans.begin(), p->prog_scans.end(), [](const dalib200::ProgScan &a, const dalib200::ProgScan &b) { return a.wave < b.wave; });
+    const int nw = p->prog_scans.back().wave + 1;
+    p->prog_wave_begin.assign(nw + 1, 0);
+    for (const auto &sc : p->prog_scans) p->prog_wave_begin[sc.wave + 1]++;
+    for (int w = 0; w < nw; w++) p->prog_wave_begin[w + 1] += p->prog_wave_begin[w];
+  }
   DB_CHECK_ARG(raw < (1ull << 32) && clean < (1ull << 32), "decoders.image: batch of encoded data exceeds 4 GiB");
   p->raw_bytes = raw; p->clean_bytes = clean; p->nchunks = chunks;
   p->total_subseq = subseq; p->total_coefs = coefs; p->total_plane_bytes = planes;
@@ -2369,7 +2431,8 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   // (the clean stream is zero-padded behind every unit by the scatter kernel itself: no memset of the 129 MB buffer)
   DB_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * p->n, s));
   DB_CUDA(cudaMemsetAsync(p->d_chain_count, 0, sizeof(uint32_t) * 8, s));
-  {
+  const bool any_units = nunits > 0 && p->nchunks > 0 && p->total_blocks_sync > 0;      // false: every sample of the batch is progressive
+  if (any_units) {
     const int grid = (int)std::min<uint32_t>(p->nchunks, (uint32_t)sms * 16);
     { ProfScope ps_("jpeg_unstuff_count", s); unstuff_count_kernel<<<grid, 256, 0, s>>>(d_raw, d_units, nunits, p->nchunks, p->d_chunk); }
     { ProfScope ps_("jpeg_unstuff_scan", s); unstuff_scan_kernel<<<(nunits + 7) / 8, 256, 0, s>>>(d_units, nunits, p->d_chunk, p->d_unit_len); }
@@ -2394,8 +2457,8 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
     p->walk_max_grid = std::max(1, per_sm) * sms * 4;
     p->smem_opted = true;
   }
-  { ProfScope ps_("jpeg_huff_sync_intra", s); huff_sync_intra_kernel<<<p->total_blocks_sync, kSyncThreads, hsmem, s>>>(cx); }
-  {
+  if (any_units) { ProfScope ps_("jpeg_huff_sync_intra", s); huff_sync_intra_kernel<<<p->total_blocks_sync, kSyncThreads, hsmem, s>>>(cx); }
+  if (any_units) {
     // chain walk: grids sized for the expected list lengths (about 30 % / 8 % / 2.5 % of the subsequences carry a live chain
     // after 1 / 2 / 3 visits); CTAs beyond the actual length return at once, grid-stride loops cover longer lists
     auto walk_grid = [&](double frac) {
@@ -2409,7 +2472,32 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   }
   { ProfScope ps_("jpeg_huff_scan", s); huff_scan_kernel<<<p->n, 1024, 0, s>>>(cx); }
   CountLaunch();
-  { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_write, kWriteThreads, wsmem, s>>>(cx); }
+  if (any_units && p->total_blocks_write > 0) { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_write, kWriteThreads, wsmem, s>>>(cx); }
+  if (!p->prog_images.empty()) {
+    // progressive samples: scans wave by wave into the same coefficient arena, DC left as differences for dc_scan (jpeg_prog.cu)
+    using namespace dalib200;
+    if (p->prog_pending) { DB_CUDA(cudaEventSynchronize(p->prog_uploaded)); p->prog_pending = false; }
+    const size_t npi = p->prog_images.size(), nsc = p->prog_scans.size(), nh = p->prog_huff.size();
+    const size_t o_img = 0, o_scan = Align(o_img + sizeof(ProgImage) * npi, 16), o_huff = Align(o_scan + sizeof(ProgScan) * nsc, 16),
+                 o_blk = Align(o_huff + sizeof(ProgHuff) * nh, 16), pbytes = Align(o_blk + sizeof(int64_t) * npi, 16);
+    if ((rc = p->prog_arena.Reserve(pbytes))) return rc;
+    memcpy(p->prog_arena.host + o_img, p->prog_images.data(), sizeof(ProgImage) * npi);
+    memcpy(p->prog_arena.host + o_scan, p->prog_scans.data(), sizeof(ProgScan) * nsc);
+    memcpy(p->prog_arena.host + o_huff, p->prog_huff.data(), sizeof(ProgHuff) * nh);
+    memcpy(p->prog_arena.host + o_blk, p->prog_first_blk.data(), sizeof(int64_t) * npi);
+    if ((rc = p->prog_arena.Upload(pbytes, s))) return rc;
+    DB_CUDA(cudaEventRecord(p->prog_uploaded, s));
+    p->prog_pending = true;
+    ProgLaunch a;
+    a.d_images = reinterpret_cast<const ProgImage *>(p->prog_arena.dev + o_img); a.nimages = (int)npi;
+    a.d_scans = reinterpret_cast<const ProgScan *>(p->prog_arena.dev + o_scan);
+    a.d_huff = reinterpret_cast<const ProgHuff *>(p->prog_arena.dev + o_huff);
+    a.d_first_blk = reinterpret_cast<const int64_t *>(p->prog_arena.dev + o_blk);
+    a.total_blocks = p->prog_total_blocks;
+    a.wave_begin = &p->prog_wave_begin; a.h_images = &p->prog_images;
+    a.d_raw = d_raw; a.d_coef = p->d_coef; a.d_dc = p->d_dc; a.d_status = p->d_status;
+    if ((rc = LaunchProgressive(a, s))) return rc;
+  }
   { ProfScope ps_("jpeg_dc_scan", s); dc_scan_kernel<<<p->n, 1024, 0, s>>>(d_images, p->d_dc); }
   { ProfScope ps_("jpeg_truncation_fixup", s); truncation_fixup_kernel<<<p->n, 256, 0, s>>>(cx); }
   CountLaunch();

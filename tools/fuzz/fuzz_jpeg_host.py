@@ -5,15 +5,17 @@ L.dalib200GetLastError.restype = C.c_char_p
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from oracle import pyoracle as po
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-def synth(h, w, q=90, sub=None, rst=0, gray=False):
+def synth(h, w, q=90, sub=None, rst=0, gray=False, prog=False):
     img = rng.integers(0, 255, (h, w) if gray else (h, w, 3)).astype(np.uint8)
-    p = [cv2.IMWRITE_JPEG_QUALITY, q]
+    p = [cv2.IMWRITE_JPEG_QUALITY, q] + ([cv2.IMWRITE_JPEG_PROGRESSIVE, 1] if prog else [])
     if sub is not None: p += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sub]
     if rst: p += [cv2.IMWRITE_JPEG_RST_INTERVAL, rst]
     ok, e = cv2.imencode(".jpg", img, p)
     return bytearray(e.tobytes())
 seeds = [synth(33, 47), synth(64, 64, sub=cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444), synth(40, 24, rst=2), synth(17, 19, gray=True), synth(48, 80, rst=1, sub=cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422)]
 seeds += [bytearray(po.with_exif_orientation(bytes(seeds[0]), o)) for o in (3, 6, 8)]
+seeds += [synth(33, 47, prog=True), synth(40, 24, rst=2, prog=True), synth(17, 19, gray=True, prog=True),
+          synth(48, 40, sub=cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, prog=True)]
 info = (C.c_int32 * 32)()
 plan = C.c_void_p()
 assert L.dalib200JpegPlanCreate(C.byref(plan), 4) == 0, L.dalib200GetLastError()

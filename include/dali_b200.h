@@ -52,7 +52,8 @@ int dalib200ProfilingEnable(int on);
 int dalib200ProfilingCollect(char *names, int name_stride, float *ms, int max, int *count);
 
 /* ------------------------------------------------------------------------------------------------
- * JPEG decode (Huffman + dequant + IDCT + chroma upsampling + YCbCr->RGB), baseline sequential.
+ * JPEG decode (Huffman + dequant + IDCT + chroma upsampling + YCbCr->RGB): baseline sequential (self-synchronising parallel entropy
+ * decode) and progressive (SOF2: scans in dependency waves, one warp per scan; spectral selection + successive approximation).
  * Replaces: imgcodec::ImageDecoder<MixedBackend>::RunImplImpl -> nvimgcodecDecoderDecode
  *           (dali/operators/imgcodec/image_decoder.h:613-882) and ParseSample (:473-499).
  * Host work: marker/table parse only.  Device work: everything arithmetic. */

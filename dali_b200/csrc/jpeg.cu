@@ -1741,7 +1741,8 @@ struct dalib200JpegPlan {
   std::vector<int64_t> prog_first_blk;
   int64_t prog_total_blocks = 0;
   dalib200::DescArena prog_arena;
-  cudaEvent_t prog_uploaded = nullptr;
+  cudaEvent_t prog_uploaded = nullptr, prog_fork = nullptr, prog_join = nullptr;
+  cudaStream_t prog_stream = nullptr;      // the scans are serial chains on one warp each: they run beside the baseline entropy stage
   bool prog_pending = false;
 };
 
@@ -1824,7 +1825,9 @@ int dalib200JpegPlanCreate(dalib200JpegPlan **plan, int max_batch) try {
   p->max_batch = max_batch;
   if (cudaEventCreateWithFlags(&p->uploaded, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->img_uploaded, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&p->prog_uploaded, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&p->prog_uploaded, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->prog_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->prog_join, cudaEventDisableTiming) != cudaSuccess) {
     SetLastError("JpegPlanCreate: cudaEventCreate failed"); delete p; return DALIB200_ERROR_CUDA;
   }
   *plan = p;
@@ -1835,7 +1838,10 @@ int dalib200JpegPlanDestroy(dalib200JpegPlan *p) try {
   if (!p) return DALIB200_SUCCESS;
   if (p->uploaded) { cudaEventSynchronize(p->uploaded); cudaEventDestroy(p->uploaded); }
   if (p->img_uploaded) { cudaEventSynchronize(p->img_uploaded); cudaEventDestroy(p->img_uploaded); }
+  if (p->prog_stream) { cudaStreamSynchronize(p->prog_stream); cudaStreamDestroy(p->prog_stream); }
   if (p->prog_uploaded) { cudaEventSynchronize(p->prog_uploaded); cudaEventDestroy(p->prog_uploaded); }
+  if (p->prog_fork) cudaEventDestroy(p->prog_fork);
+  if (p->prog_join) cudaEventDestroy(p->prog_join);
   p->prog_arena.Free();
   if (p->h_stage) cudaFreeHost(p->h_stage);
   if (p->h_images) cudaFreeHost(p->h_images);
@@ -2431,6 +2437,39 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   // (the clean stream is zero-padded behind every unit by the scatter kernel itself: no memset of the 129 MB buffer)
   DB_CUDA(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t) * p->n, s));
   DB_CUDA(cudaMemsetAsync(p->d_chain_count, 0, sizeof(uint32_t) * 8, s));
+  if (!p->prog_images.empty()) {
+    // progressive samples: scans wave by wave into the same coefficient arena, DC left as differences for dc_scan (jpeg_prog.cu).
+    // A scan is a serial chain on ONE warp (milliseconds for a large image) that leaves the GPU empty: the stage is forked onto a
+    // stream of its own here, behind the upload and the status clear, runs beside the baseline samples' entropy kernels and is joined
+    // in front of dc_scan.  It touches only the progressive samples' ranges of the coefficient / DC arenas and their status words.
+    using namespace dalib200;
+    if (!p->prog_stream) DB_CUDA(cudaStreamCreateWithFlags(&p->prog_stream, cudaStreamNonBlocking));
+    cudaStream_t ps = p->prog_stream;
+    DB_CUDA(cudaEventRecord(p->prog_fork, s));
+    DB_CUDA(cudaStreamWaitEvent(ps, p->prog_fork, 0));
+    if (p->prog_pending) { DB_CUDA(cudaEventSynchronize(p->prog_uploaded)); p->prog_pending = false; }
+    const size_t npi = p->prog_images.size(), nsc = p->prog_scans.size(), nh = p->prog_huff.size();
+    const size_t o_img = 0, o_scan = Align(o_img + sizeof(ProgImage) * npi, 16), o_huff = Align(o_scan + sizeof(ProgScan) * nsc, 16),
+                 o_blk = Align(o_huff + sizeof(ProgHuff) * nh, 16), pbytes = Align(o_blk + sizeof(int64_t) * npi, 16);
+    if ((rc = p->prog_arena.Reserve(pbytes))) return rc;
+    memcpy(p->prog_arena.host + o_img, p->prog_images.data(), sizeof(ProgImage) * npi);
+    memcpy(p->prog_arena.host + o_scan, p->prog_scans.data(), sizeof(ProgScan) * nsc);
+    memcpy(p->prog_arena.host + o_huff, p->prog_huff.data(), sizeof(ProgHuff) * nh);
+    memcpy(p->prog_arena.host + o_blk, p->prog_first_blk.data(), sizeof(int64_t) * npi);
+    if ((rc = p->prog_arena.Upload(pbytes, ps))) return rc;
+    DB_CUDA(cudaEventRecord(p->prog_uploaded, ps));
+    p->prog_pending = true;
+    ProgLaunch a;
+    a.d_images = reinterpret_cast<const ProgImage *>(p->prog_arena.dev + o_img); a.nimages = (int)npi;
+    a.d_scans = reinterpret_cast<const ProgScan *>(p->prog_arena.dev + o_scan);
+    a.d_huff = reinterpret_cast<const ProgHuff *>(p->prog_arena.dev + o_huff);
+    a.d_first_blk = reinterpret_cast<const int64_t *>(p->prog_arena.dev + o_blk);
+    a.total_blocks = p->prog_total_blocks;
+    a.wave_begin = &p->prog_wave_begin; a.h_images = &p->prog_images;
+    a.d_raw = d_raw; a.d_coef = p->d_coef; a.d_dc = p->d_dc; a.d_status = p->d_status;
+    if ((rc = LaunchProgressive(a, ps))) return rc;
+    DB_CUDA(cudaEventRecord(p->prog_join, ps));
+  }
   const bool any_units = nunits > 0 && p->nchunks > 0 && p->total_blocks_sync > 0;      // false: every sample of the batch is progressive
   if (any_units) {
     const int grid = (int)std::min<uint32_t>(p->nchunks, (uint32_t)sms * 16);
@@ -2473,31 +2512,7 @@ int dalib200JpegLaunch(dalib200JpegPlan *p, void *const *out_ptrs, dalib200Strea
   { ProfScope ps_("jpeg_huff_scan", s); huff_scan_kernel<<<p->n, 1024, 0, s>>>(cx); }
   CountLaunch();
   if (any_units && p->total_blocks_write > 0) { ProfScope ps_("jpeg_huff_write", s); huff_write_kernel<<<p->total_blocks_write, kWriteThreads, wsmem, s>>>(cx); }
-  if (!p->prog_images.empty()) {
-    // progressive samples: scans wave by wave into the same coefficient arena, DC left as differences for dc_scan (jpeg_prog.cu)
-    using namespace dalib200;
-    if (p->prog_pending) { DB_CUDA(cudaEventSynchronize(p->prog_uploaded)); p->prog_pending = false; }
-    const size_t npi = p->prog_images.size(), nsc = p->prog_scans.size(), nh = p->prog_huff.size();
-    const size_t o_img = 0, o_scan = Align(o_img + sizeof(ProgImage) * npi, 16), o_huff = Align(o_scan + sizeof(ProgScan) * nsc, 16),
-                 o_blk = Align(o_huff + sizeof(ProgHuff) * nh, 16), pbytes = Align(o_blk + sizeof(int64_t) * npi, 16);
-    if ((rc = p->prog_arena.Reserve(pbytes))) return rc;
-    memcpy(p->prog_arena.host + o_img, p->prog_images.data(), sizeof(ProgImage) * npi);
-    memcpy(p->prog_arena.host + o_scan, p->prog_scans.data(), sizeof(ProgScan) * nsc);
-    memcpy(p->prog_arena.host + o_huff, p->prog_huff.data(), sizeof(ProgHuff) * nh);
-    memcpy(p->prog_arena.host + o_blk, p->prog_first_blk.data(), sizeof(int64_t) * npi);
-    if ((rc = p->prog_arena.Upload(pbytes, s))) return rc;
-    DB_CUDA(cudaEventRecord(p->prog_uploaded, s));
-    p->prog_pending = true;
-    ProgLaunch a;
-    a.d_images = reinterpret_cast<const ProgImage *>(p->prog_arena.dev + o_img); a.nimages = (int)npi;
-    a.d_scans = reinterpret_cast<const ProgScan *>(p->prog_arena.dev + o_scan);
-    a.d_huff = reinterpret_cast<const ProgHuff *>(p->prog_arena.dev + o_huff);
-    a.d_first_blk = reinterpret_cast<const int64_t *>(p->prog_arena.dev + o_blk);
-    a.total_blocks = p->prog_total_blocks;
-    a.wave_begin = &p->prog_wave_begin; a.h_images = &p->prog_images;
-    a.d_raw = d_raw; a.d_coef = p->d_coef; a.d_dc = p->d_dc; a.d_status = p->d_status;
-    if ((rc = LaunchProgressive(a, s))) return rc;
-  }
+  if (!p->prog_images.empty()) DB_CUDA(cudaStreamWaitEvent(s, p->prog_join, 0));      // the progressive samples' coefficients and DC differences are in place
   { ProfScope ps_("jpeg_dc_scan", s); dc_scan_kernel<<<p->n, 1024, 0, s>>>(d_images, p->d_dc); }
   { ProfScope ps_("jpeg_truncation_fixup", s); truncation_fixup_kernel<<<p->n, 256, 0, s>>>(cx); }
   CountLaunch();

@@ -62,6 +62,34 @@ static FrameList ExpandFrames(const TensorListShape &shape, const TensorLayout &
   return f;
 }
 
+// Resize takes every layout of the reference's schema (resize.cc:28-29): the dimensions in front of the spatial ones collapse into
+// frames -- which covers channel-first data: a CHW image is C one-channel frames --, those behind them into channels
+// (resize_op_impl.h:56-101).  2-D layouts here; the volumetric ones go through SetupVolumes.
+static FrameList ExpandFramesAnyLayout(const TensorListShape &shape, const TensorLayout &layout, const char *op) {
+  FrameList f;
+  const int nd = shape.sample_dim();
+  std::string l = layout.str();
+  if (l.empty()) l = nd == 3 ? "HWC" : nd == 4 ? "FHWC" : "";
+  DALI_ENFORCE(l == "HWC" || l == "FHWC" || l == "CHW" || l == "FCHW" || l == "CFHW", op, ": unsupported layout \"", l, "\" (", nd,
+               "-D); expected one of HWC, FHWC, CHW, FCHW, CFHW, DHWC, FDHWC, CDHW, FCDHW, CFDHW");
+  DALI_ENFORCE(static_cast<int>(l.size()) == nd, op, ": layout \"", l, "\" does not match a ", nd, "-D input");
+  const int fs = static_cast<int>(l.find('H'));
+  f.first_spatial = fs;
+  for (int i = 0; i < shape.num_samples(); i++) {
+    const int64_t *s = shape.tensor_shape_span(i);
+    int64_t frames = 1, C = 1;
+    for (int d = 0; d < fs; d++) frames *= s[d];
+    for (int d = fs + 2; d < nd; d++) C *= s[d];
+    const int64_t H = s[fs], W = s[fs + 1];
+    for (int64_t k = 0; k < frames; k++) {
+      f.sample_of_frame.push_back(i);
+      f.frame_offset_elems.push_back(k * H * W * C);
+      f.h.push_back(static_cast<int>(H)); f.w.push_back(static_cast<int>(W)); f.c.push_back(static_cast<int>(C));
+    }
+  }
+  return f;
+}
+
 template <typename TL>
 static std::vector<const void *> FramePtrs(const TL &tl, const FrameList &f, size_t elem_size) {
   std::vector<const void *> p(f.num_frames());
@@ -621,9 +649,9 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
     DALIDataType out_type = in.type();
     if (spec_.ArgumentDefined("dtype")) out_type = spec_.GetArgument<DALIDataType>("dtype");
     DALI_ENFORCE(out_type == in.type() || out_type == DALI_FLOAT, "Resize: output type must be the same as input or FLOAT");
-    volumes_ = in.GetLayout().str() == "DHWC" || in.GetLayout().str() == "FDHWC";
+    volumes_ = in.GetLayout().str().find('D') != std::string::npos;
     if (volumes_) return SetupVolumes(out, ws, out_type);
-    frames_ = ExpandFrames(in.shape(), in.GetLayout(), "Resize");
+    frames_ = ExpandFramesAnyLayout(in.shape(), in.GetLayout(), "Resize");
     const int nf = frames_.num_frames();
     if (nf > plan_cap_) { dalib200ResamplePlanDestroy(plan_); plan_ = nullptr; plan_cap_ = nf; CheckStatus(dalib200ResamplePlanCreate(&plan_, nf), "Resize"); }
     std::vector<float> max_size(2, std::nextafter(static_cast<float>(std::numeric_limits<int>::max()), 0.0f));
@@ -672,10 +700,12 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
       if (has_min) minf = conv(spec_.GetArgument<int>("min_filter", &ws, i), antialias_); else if (has_interp) minf = conv(interp, antialias_);
       if (has_mag) magf = conv(spec_.GetArgument<int>("mag_filter", &ws, i), false); else if (has_interp) magf = conv(interp, false);
       out_hw_[i] = { p.dst[0], p.dst[1] };
-      const int64_t frames = fs ? s[0] : 1;
+      int64_t frames = 1, chans = 1;            // leading dimensions are frames, trailing ones channels (CHW: C frames of one channel)
+      for (int d = 0; d < fs; d++) frames *= s[d];
+      for (int d = fs + 2; d < in.shape().sample_dim(); d++) chans *= s[d];
       for (int64_t k = 0; k < frames; k++, fk++) {
         auto &r = samples_[fk];
-        r.in_h = static_cast<int>(s[fs]); r.in_w = static_cast<int>(s[fs + 1]); r.channels = static_cast<int>(s[fs + 2]);
+        r.in_h = static_cast<int>(s[fs]); r.in_w = static_cast<int>(s[fs + 1]); r.channels = static_cast<int>(chans);
         r.out_h = p.dst[0]; r.out_w = p.dst[1];
         for (int d = 0; d < 2; d++) {
           r.use_roi[d] = p.lo[d] != p.hi[d];            // GetResamplingParams: roi only when non-degenerate
@@ -768,8 +798,12 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
   bool SetupVolumes(std::vector<OutputDesc> &out, const Workspace &ws, DALIDataType out_type) {
     const auto &in = ws.Input<GPUBackend>(0);
     const int n = in.num_samples();
-    const int fs = in.GetLayout().str() == "FDHWC" ? 1 : 0;
-    DALI_ENFORCE(in.shape().sample_dim() == fs + 4, "Resize: layout \"", in.GetLayout().str(), "\" does not match a ", in.shape().sample_dim(), "-D input");
+    const std::string lay = in.GetLayout().str();
+    const int nd = in.shape().sample_dim();
+    DALI_ENFORCE(lay == "DHWC" || lay == "FDHWC" || lay == "CDHW" || lay == "FCDHW" || lay == "CFDHW", "Resize: unsupported layout \"", lay,
+                 "\"; expected one of HWC, FHWC, CHW, FCHW, CFHW, DHWC, FDHWC, CDHW, FCDHW, CFDHW");
+    DALI_ENFORCE(nd == static_cast<int>(lay.size()), "Resize: layout \"", lay, "\" does not match a ", nd, "-D input");
+    const int fs = static_cast<int>(lay.find('D'));
     if (producer_) { std::vector<uint8_t> none(n, 0), granted; producer_->SelectPlanar(none, granted); }
     std::vector<float> max_size(3, std::nextafter(static_cast<float>(std::numeric_limits<int>::max()), 0.0f));
     if (has_max_) max_size = spec_.GetFloatVecArgument("max_size", &ws, 0, 3);
@@ -814,12 +848,14 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
       if (has_min) minf = conv(spec_.GetArgument<int>("min_filter", &ws, i), antialias_); else if (has_interp) minf = conv(interp, antialias_);
       if (has_mag) magf = conv(spec_.GetArgument<int>("mag_filter", &ws, i), false); else if (has_interp) magf = conv(interp, false);
       out_dhw_[i] = { p.dst[0], p.dst[1], p.dst[2] };
-      const int64_t frames = fs ? s[0] : 1;
-      const int64_t in_vol = s[fs] * s[fs + 1] * s[fs + 2] * s[fs + 3];
+      int64_t frames = 1, chans = 1;            // leading dimensions are frames, trailing ones channels (CDHW: C volumes of one channel)
+      for (int d = 0; d < fs; d++) frames *= s[d];
+      for (int d = fs + 3; d < nd; d++) chans *= s[d];
+      const int64_t in_vol = s[fs] * s[fs + 1] * s[fs + 2] * chans;
       for (int64_t k = 0; k < frames; k++) {
         dalib200Resample3DSample r;
         memset(&r, 0, sizeof(r));
-        r.channels = static_cast<int>(s[fs + 3]);
+        r.channels = static_cast<int>(chans);
         for (int d = 0; d < 3; d++) {
           r.in_shape[d] = static_cast<int>(s[fs + d]); r.out_shape[d] = p.dst[d];
           r.use_roi[d] = p.lo[d] != p.hi[d];

@@ -4,7 +4,7 @@ resample3d_pass_kernel / prog_scan_kernel / prog_dc_kernel run on the host, bloc
 host/device functions the device code consists of.  Everything in front of and behind the launch is the library's real code
 (descriptor upload, temporaries, stage order, grid-stride loops, wave ranges, arena offsets, the operator and the executor), so the
 value comparisons below are real:
-  * the whole tests/test_zzy_gpu_resize3d.py (C-ABI and fn.resize on DHWC / FDHWC) runs with its assertions intact;
+  * the whole tests/test_zzy_gpu_resize3d.py (C-ABI and fn.resize on DHWC / FDHWC / CDHW / FCDHW) runs with its assertions intact;
   * progressive JPEG batches (alone and mixed with baseline samples, whose kernels are no-ops here) must leave the baseline twin's
     coefficients in the arena and the DC differences the shared dc_scan stage expects, and report truncated / incomplete streams."""
 import os
@@ -35,7 +35,7 @@ def test_volume_resize_gpu_tests_pass_on_the_emulated_launch_path(emul_env):
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) == 5 and "failed" not in r.stdout, tail
+    assert m and int(m.group(1)) == 6 and "failed" not in r.stdout, tail
 
 
 PROGRESSIVE = r"""

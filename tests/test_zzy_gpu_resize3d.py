@@ -140,3 +140,28 @@ def test_fn_resize_on_sequences_of_volumes_with_roi():
         for f in range(s.shape[0]):
             want = po.resample3d(np.ascontiguousarray(s[f]), (6, 9, 11), f_min, f_mag, np.uint8, roi)
             assert np.array_equal(got[f], want), (i, f)
+
+
+def test_fn_resize_on_channel_first_volumes():
+    """CDHW / FCDHW: the dimensions in front of the spatial ones are frames (resize_op_impl.h:56-101) -- C volumes of one channel"""
+    from dali_b200 import types
+    rng = np.random.default_rng(35)
+    vols = [rng.integers(0, 256, s, dtype=np.uint8) for s in ((2, 10, 14, 18), (3, 8, 8, 8))]
+    f_min, f_mag = [(T, 1, 0.0)] * 3, [(L, 0, 0.0)] * 3
+    a, b = _run_volumes(vols, lambda fn, x: (fn.resize(x, size=[6, 9, 11]), fn.resize(x, resize_x=12, resize_y=7, resize_z=5, dtype=types.FLOAT)),
+                        layout="CDHW")
+    for i, v in enumerate(vols):
+        ga, gb = np.asarray(a[i]), np.asarray(b[i])
+        assert ga.shape == (v.shape[0], 6, 9, 11) and gb.shape == (v.shape[0], 5, 7, 12)
+        for c in range(v.shape[0]):
+            plane = np.ascontiguousarray(v[c][..., None])
+            assert np.array_equal(ga[c], po.resample3d(plane, (6, 9, 11), f_min, f_mag, np.uint8)[..., 0]), (i, c)
+            assert np.array_equal(_bits(gb[c]), _bits(po.resample3d(plane, (5, 7, 12), f_min, f_mag, np.float32)[..., 0])), (i, c)
+    seqs = [rng.integers(0, 256, (2, 2, 6, 7, 8), dtype=np.uint8)]
+    (c5,) = _run_volumes(seqs, lambda fn, x: (fn.resize(x, size=[3, 4, 5]),), layout="FCDHW")
+    got = np.asarray(c5[0])
+    assert got.shape == (2, 2, 3, 4, 5)
+    for f in range(2):
+        for c in range(2):
+            want = po.resample3d(np.ascontiguousarray(seqs[0][f, c][..., None]), (3, 4, 5), f_min, f_mag, np.uint8)[..., 0]
+            assert np.array_equal(got[f, c], want), (f, c)

@@ -55,9 +55,10 @@ R3_HD float r3_load(const R3Pass &p, int64_t i) {
 }
 
 R3_HD void r3_element(const R3Pass &p, const int32_t *tab, int64_t e) {
-  const int C = p.C, X = p.osz[0], Y = p.osz[1];
-  const int c = (int)(e % C);
-  int64_t t = e / C;
+  // a pass has fewer than 2^31 output elements (the planner checks): 32-bit index arithmetic (a 64-bit division costs ~100 instructions)
+  const uint32_t C = (uint32_t)p.C, X = (uint32_t)p.osz[0], Y = (uint32_t)p.osz[1];
+  uint32_t t = (uint32_t)e;
+  const int c = (int)(t % C); t /= C;
   const int x = (int)(t % X); t /= X;
   const int y = (int)(t % Y);
   const int z = (int)(t / Y);
@@ -75,12 +76,13 @@ R3_HD void r3_element(const R3Pass &p, const int32_t *tab, int64_t e) {
   }
   const int a = p.axis;
   const int o = a == 0 ? x : a == 1 ? y : z;
-  const int lim = p.isz[a] - 1;
+  // selects instead of indexing the descriptor with `a`: the struct stays in registers / constant bank instead of a local-memory copy
+  const int lim = (a == 0 ? p.isz[0] : a == 1 ? p.isz[1] : p.isz[2]) - 1;
   int64_t base = p.in_offset + c;
   if (a != 0) base += x * p.in_stride[0];
   if (a != 1) base += y * p.in_stride[1];
   if (a != 2) base += z * p.in_stride[2];
-  const int64_t step = p.in_stride[a];
+  const int64_t step = a == 0 ? p.in_stride[0] : a == 1 ? p.in_stride[1] : p.in_stride[2];
   const int i0 = tab[p.idx_off + o];
   const int32_t *cf = tab + p.coef_off + (int64_t)o * p.support;
   float sum = 0.0f;
@@ -95,8 +97,8 @@ R3_HD void r3_element(const R3Pass &p, const int32_t *tab, int64_t e) {
   if (!p.out_u8) { static_cast<float *>(p.out)[e] = sum; return; }
   bool even;
   if (a == 0) even = reinterpret_cast<const uint8_t *>(tab + p.flags_off)[x] != 0;
-  else if (a == 1) even = (uint32_t)(x * C + c) < p.simd_end;
-  else even = (uint64_t)((int64_t)y * X + x) * C + c < p.simd_end;
+  else if (a == 1) even = (uint32_t)x * C + (uint32_t)c < p.simd_end;
+  else even = ((uint32_t)y * X + (uint32_t)x) * C + (uint32_t)c < p.simd_end;
   static_cast<uint8_t *>(p.out)[e] = even ? r3_u8_even(sum) : r3_u8_away(sum);
 }
 

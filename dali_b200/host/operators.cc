@@ -613,7 +613,9 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
     has_x_ = spec.ArgumentDefined("resize_x"); has_y_ = spec.ArgumentDefined("resize_y");
     has_size_ = spec.ArgumentDefined("size"); has_max_ = spec.ArgumentDefined("max_size");
     const bool has_mode = spec.ArgumentDefined("mode");
-    has_z_ = name == std::string("Resize") && spec.ArgumentDefined("resize_z");
+    plain_resize_ = name == std::string("Resize");      // derived operators (ResizeCropMirror) stay 2-D
+    DALI_ENFORCE(plain_resize_ || !spec.ArgumentDefined("resize_z"), name, ": `resize_z` (volumetric data) is not supported by the GPU path");
+    has_z_ = plain_resize_ && spec.ArgumentDefined("resize_z");
     DALI_ENFORCE(!spec.GetArgument<bool>("save_attrs"), "Resize: `save_attrs` is not supported");
     DALI_ENFORCE((has_x_ || has_y_ || has_z_) + has_size_ + has_shorter_ + has_longer_ == 1,
                  "Exactly one method of specifying size must be used. The available methods:\n"
@@ -650,6 +652,7 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
     if (spec_.ArgumentDefined("dtype")) out_type = spec_.GetArgument<DALIDataType>("dtype");
     DALI_ENFORCE(out_type == in.type() || out_type == DALI_FLOAT, "Resize: output type must be the same as input or FLOAT");
     volumes_ = in.GetLayout().str().find('D') != std::string::npos;
+    DALI_ENFORCE(!volumes_ || plain_resize_, "ResizeCropMirror: volumetric inputs are not supported by the GPU path");
     if (volumes_) return SetupVolumes(out, ws, out_type);
     frames_ = ExpandFramesAnyLayout(in.shape(), in.GetLayout(), "Resize");
     const int nf = frames_.num_frames();
@@ -909,7 +912,7 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
  private:
   dalib200Resample3DPlan *plan3_ = nullptr;
   int plan3_cap_ = 0;
-  bool volumes_ = false, has_z_ = false;
+  bool volumes_ = false, has_z_ = false, plain_resize_ = true;
   std::vector<dalib200Resample3DSample> vsamples_;
   std::vector<int> vol_sample_;
   std::vector<int64_t> vol_offset_;

@@ -1939,7 +1939,9 @@ int dalib200JpegPlanSetupEx(dalib200JpegPlan *p, int n, const uint8_t *const *st
     int rc = ParseHeaders(streams[i], lengths[i], j, true);
     if (rc) { std::string m = dalib200GetLastError(); SetLastError("decoders.image: sample %d: %s", i, m.c_str()); return rc; }
     auto unsupported = [&](const char *what) { SetLastError("decoders.image: sample %d: %s", i, what); return DALIB200_ERROR_UNSUPPORTED; };
-    const bool prog = j.progressive;
+    // multi-scan streams -- progressive, or a sequential frame whose components come in separate scans -- take the scan-by-scan entropy
+    // stage (jpeg_prog.cu); `prog` below means exactly that
+    const bool prog = j.progressive || (j.ncomp > 1 && j.scan_ncomp != j.ncomp);
     if (prog) {
       // the frame layout comes from the frame header: the first scan of a progressive stream need not name every component, and its
       // Huffman tables are only the first of several snapshots (jpeg_prog_plan.h walks all scans below)

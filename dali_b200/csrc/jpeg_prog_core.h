@@ -34,6 +34,8 @@ struct ProgScan {
   int32_t image;               // index into the ProgImage array
   int32_t ncomp, comp[4];      // components of the scan (frame component indices)
   int32_t dc_tbl[4], ac_tbl;   // indices into the ProgHuff array (DC scans: per component; AC scans: ac_tbl)
+  int32_t seq_ac_tbl[4];       // sequential scans (below): the AC table of each component
+  int32_t seq;                 // 1: a scan of a SEQUENTIAL (SOF0 / SOF1) frame that is coded in several scans: whole blocks, DC + AC
   int32_t ss, se, ah, al;
   int32_t restart_interval;    // MCUs of THIS scan between restart markers, 0 = none
   int32_t wave;
@@ -157,7 +159,34 @@ PG_HD int prog_decode_scan(const ProgScan &s, const ProgImage &im, const ProgHuf
       to_restart--;
     }
     if (!insufficient) {
-      if (s.ss == 0) {                                       // ---- DC scans: every block of the MCU
+      if (s.seq) {                                           // ---- sequential scan (jdhuff.c decode_mcu): whole blocks
+        for (int ci = 0; ci < s.ncomp; ci++) {
+          const int c = s.comp[ci];
+          const int nb = single ? 1 : im.hs[c] * im.vs[c];
+          const ProgHuff &hd = huff[s.dc_tbl[ci]], &ha = huff[s.seq_ac_tbl[ci]];
+          for (int k = 0; k < nb; k++) {
+            const int64_t blk = single ? prog_block_single(im, c, mx, my) : m * im.bpm + im.blk0[c] + k;
+            int16_t *q = coef + blk * 64;
+            int t = pb_huff(b, hd) & 15;
+            if (t) t = pb_extend(pb_get(b, t), t);
+            last_dc[ci] += t;
+            q[0] = (int16_t)last_dc[ci];
+            for (int z = 1; z < 64; z++) {
+              int rs = pb_huff(b, ha);
+              const int r = rs >> 4;
+              rs &= 15;
+              if (rs) {
+                z += r;
+                q[prog_natural(z & 63)] = (int16_t)pb_extend(pb_get(b, rs), rs);
+              } else if (r == 15) {
+                z += 15;
+              } else {
+                break;
+              }
+            }
+          }
+        }
+      } else if (s.ss == 0) {                                // ---- DC scans: every block of the MCU
         for (int ci = 0; ci < s.ncomp; ci++) {
           const int c = s.comp[ci];
           const int nb = single ? 1 : im.hs[c] * im.vs[c];

@@ -1,4 +1,5 @@
-// dali_b200/csrc/jpeg_prog_plan.h -- host-side planning of a PROGRESSIVE (SOF2) JPEG: the marker walk over the whole stream (the
+// dali_b200/csrc/jpeg_prog_plan.h -- host-side planning of a multi-scan JPEG -- PROGRESSIVE (SOF2), or a sequential frame (SOF0 / SOF1)
+// whose components are coded in separate scans: the marker walk over the whole stream (the
 // Huffman tables may be redefined between scans), one ProgScan per SOS with the table snapshot it decodes with, the extent of its
 // entropy-coded bytes, and the dependency wave it runs in.  Plain C++ (no CUDA types): jpeg.cu calls it from JpegPlanSetup,
 // tools/emul/jpeg_prog_emul.cc from the CPU emulation test.
@@ -58,7 +59,7 @@ inline int PlanProgressive(const uint8_t *d, size_t n, size_t base, int image, P
   if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return bad("not a JPEG stream (missing SOI)");
   RawHuff dc[4], ac[4];
   int width = 0, height = 0, ncomp = 0, cid[4] = { 0 }, hs[4] = { 0 }, vs[4] = { 0 }, hmax = 1, vmax = 1;
-  bool got_sof = false;
+  bool got_sof = false, sequential = false;
   int dri = 0;
   const size_t first_scan = scans.size();
   int coef_bits[4][64];                              // libjpeg's coef_bits: the Al each coefficient has reached, -1 = never sent
@@ -107,8 +108,9 @@ inline int PlanProgressive(const uint8_t *d, size_t n, size_t base, int image, P
         memcpy(h.vals, s + o, cnt); o += cnt;
         h.present = true;
       }
-    } else if (m == 0xC2) {
+    } else if (m == 0xC2 || m == 0xC0 || m == 0xC1) {
       if (got_sof) return bad("JPEG: two frame headers");
+      sequential = m != 0xC2;                          // a sequential frame coded in several scans (one per component)
       if (sl < 6) return bad("JPEG: bad SOF");
       height = Rd16(s + 1); width = Rd16(s + 3); ncomp = s[5];
       if (s[0] != 8) return unsup("only 8-bit JPEG is supported");
@@ -143,12 +145,18 @@ inline int PlanProgressive(const uint8_t *d, size_t n, size_t base, int image, P
       sc.ss = t[0]; sc.se = t[1]; sc.ah = t[2] >> 4; sc.al = t[2] & 15;
       // G.1.1.1: DC scans carry Ss = Se = 0 and may interleave components; AC scans one component, 1 <= Ss <= Se <= 63; a refinement
       // scan sends exactly the next lower bit
-      if (sc.ss > sc.se || sc.se > 63 || sc.al > 13 || sc.ah > 13) return bad("JPEG: bad progression parameters");
-      if (sc.ss == 0 ? sc.se != 0 : sc.ncomp != 1) return bad("JPEG: bad progression parameters");
-      if (sc.ah != 0 && sc.ah != sc.al + 1) return bad("JPEG: bad successive approximation");
+      if (sequential) {
+        if (sc.ss != 0 || sc.se != 63 || sc.ah != 0 || sc.al != 0) return bad("JPEG: bad scan parameters in a sequential frame");
+        sc.seq = 1;
+      } else {
+        if (sc.ss > sc.se || sc.se > 63 || sc.al > 13 || sc.ah > 13) return bad("JPEG: bad progression parameters");
+        if (sc.ss == 0 ? sc.se != 0 : sc.ncomp != 1) return bad("JPEG: bad progression parameters");
+        if (sc.ah != 0 && sc.ah != sc.al + 1) return bad("JPEG: bad successive approximation");
+      }
       if (sc.ncomp != 1 && sc.ncomp != ncomp) return unsup("scans that interleave a subset of the components are not supported");
       for (int i = 0; i < sc.ncomp; i++) {
-        if (sc.ss == 0) { if (sc.ah == 0 && !table_index(dc[td[i]], &sc.dc_tbl[i])) return bad("JPEG: missing or invalid Huffman table"); }
+        if (sc.seq) { if (!table_index(dc[td[i]], &sc.dc_tbl[i]) || !table_index(ac[ta[i]], &sc.seq_ac_tbl[i])) return bad("JPEG: missing or invalid Huffman table"); }
+        else if (sc.ss == 0) { if (sc.ah == 0 && !table_index(dc[td[i]], &sc.dc_tbl[i])) return bad("JPEG: missing or invalid Huffman table"); }
         else if (!table_index(ac[ta[i]], &sc.ac_tbl)) return bad("JPEG: missing or invalid Huffman table");
       }
       for (int i = 0; i < sc.ncomp; i++) for (int k = sc.ss; k <= sc.se; k++) coef_bits[sc.comp[i]][k] = sc.al;
@@ -172,7 +180,7 @@ inline int PlanProgressive(const uint8_t *d, size_t n, size_t base, int image, P
       pos = e;
       continue;
     } else if (m >= 0xC0 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
-      return unsup("not a progressive Huffman-coded JPEG");
+      return unsup("not a Huffman-coded DCT JPEG (lossless / arithmetic / hierarchical)");
     }
     pos += L;
   }

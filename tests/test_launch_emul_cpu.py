@@ -83,8 +83,24 @@ base, prog = cases[3]
 last = prog.rfind(b"\xff\xda")
 outs, status = g.jpeg_decode([prog, prog[: (last + len(prog)) // 2], prog[: last - 3]])
 assert status == [0, 1, 1], status
+# sequential frames coded in several scans take the same stage (one wave); the blocks such a scan does not code stay zero
+import cv2
+from test_jpeg_prog_cpu import multiscan_expected, synth, to_multiscan_baseline, twins
+base, _ = twins(synth(97, 61, 611), 85, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420)
+multi, hblk, wblk = to_multiscan_baseline(base, 5)
+outs, status, plan2 = g.jpeg_decode([multi, cases[0][1]], want_coefs=True)
+want = multiscan_expected(base, hblk, wblk)
+got = g.jpeg_coefs(plan2, 0, want.size).reshape(want.shape)
+assert status == [0, 0] and np.array_equal(got[:, 1:], want[:, 1:])
+info = po.jpeg_info(base)
+b0 = 0
+for c in range(3):
+    nb = info["hs"][c] * info["vs"][c]
+    idx = (np.arange(info["mcux"] * info["mcuy"])[:, None] * 6 + b0 + np.arange(nb)[None, :]).reshape(-1)
+    assert np.array_equal(np.cumsum(got[idx, 0].astype(np.int64)), want[idx, 0].astype(np.int64)), ("DC", c)
+    b0 += nb
 n_scan, n_dc = stub.emul_launch_count(1), stub.emul_launch_count(2)
-assert n_scan == 3 * 4 and n_dc == 4, (n_scan, n_dc)        # three waves per launch, one DC pass
+assert n_scan == 3 * 5 and n_dc == 5, (n_scan, n_dc)        # three waves per launch (the last batch: progressive + sequential), one DC pass
 print("progressive-emul-ok")
 """
 

@@ -98,3 +98,27 @@ def test_decoders_image_accepts_progressive_files():
             want = po.jpeg_decode(twin[i])
             assert np.array_equal(np.asarray(img[i]), want), i
             assert np.array_equal(np.asarray(small[i]), po.resample(want, (64, 80), (po.F_TRIANGULAR, 1, 0.0), (po.F_LINEAR, 0, 0.0))), i
+
+
+def test_sequential_frames_coded_in_several_scans():
+    """SOF0 streams whose components come in separate scans (re-coded from interleaved baseline streams by the test encoder of
+    tests/test_jpeg_prog_cpu.py, which libjpeg-turbo accepts): one wave, a warp per component"""
+    import cv2
+    import gpu_helpers as g
+    from test_jpeg_prog_cpu import multiscan_expected, synth, to_multiscan_baseline, twins
+    streams, bases, exp = [], [], []
+    for k, (h, w, s, rst) in enumerate([(48, 64, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, 0), (97, 61, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, 5),
+                                        (33, 47, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, 0), (240, 320, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, 7)]):
+        base, _ = twins(synth(h, w, 600 + k), 85, s)
+        multi, hblk, wblk = to_multiscan_baseline(base, rst)
+        streams.append(multi)
+        bases.append(base)
+        exp.append(multiscan_expected(base, hblk, wblk).reshape(-1))
+    outs, status, plan = g.jpeg_decode(streams + [bases[0]], want_coefs=True)
+    assert status == [0] * 5
+    for i, multi in enumerate(streams):
+        assert np.array_equal(g.jpeg_coefs(plan, i, exp[i].size), exp[i]), f"coefficients of stream {i}"
+        want = cv2.imdecode(np.frombuffer(multi, np.uint8), cv2.IMREAD_COLOR)[..., ::-1]
+        assert np.array_equal(outs[i], want), f"pixels of stream {i} vs libjpeg-turbo"
+        assert np.array_equal(outs[i], po.jpeg_decode(bases[i])), f"pixels of stream {i} vs the oracle's decode of the interleaved twin"
+    assert np.array_equal(outs[4], outs[0])

@@ -12,6 +12,12 @@ def synth(h, w, q=90, sub=None, rst=0, gray=False):
     return bytearray(cv2.imencode(".jpg", img, p)[1].tobytes())
 seeds = [synth(33, 47), synth(64, 64, sub=cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444), synth(40, 24, rst=2), synth(17, 19, gray=True),
          synth(48, 80, rst=1, sub=cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422), synth(24, 24, q=30, sub=cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411)]
+import os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "tests"))
+from test_jpeg_prog_cpu import to_multiscan_baseline          # sequential frames coded in several scans (test encoder)
+for rst in (0, 3):
+    img = rng.integers(0, 255, (40, 56, 3)).astype(np.uint8)
+    seeds.append(bytearray(to_multiscan_baseline(cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 80])[1].tobytes(), rst)[0]))
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 2000
 hist = {}
 info = (C.c_int * 8)()

@@ -130,7 +130,7 @@ def test_unsupported_streams_fail_loudly():
     img = g.synth_image(64, 64, 13)
     ok, enc = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])
     arith = bytearray(enc.tobytes())
-    arith[arith.find(b"\xff\xc0") + 1] = 0xC9           # SOF9: arithmetic coding (progressive streams are decoded: test_zzy_gpu_jpeg_progressive.py)
+    arith[arith.find(b"\xff\xc0") + 1] = 0xC9           # SOF9: arithmetic coding (progressive streams are decoded: test_zzy_c_gpu_jpeg_multiscan.py)
     with pytest.raises(capi.DaliB200Error, match="not supported"):
         g.jpeg_decode([bytes(arith)])
     with pytest.raises(capi.DaliB200Error):

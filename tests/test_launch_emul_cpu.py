@@ -4,7 +4,7 @@ resample3d_pass_kernel / prog_scan_kernel / prog_dc_kernel run on the host, bloc
 host/device functions the device code consists of.  Everything in front of and behind the launch is the library's real code
 (descriptor upload, temporaries, stage order, grid-stride loops, wave ranges, arena offsets, the operator and the executor), so the
 value comparisons below are real:
-  * the whole tests/test_zzy_gpu_resize3d.py (C-ABI and fn.resize on DHWC / FDHWC / CDHW / FCDHW) runs with its assertions intact;
+  * the whole tests/test_zzy_a_gpu_resize3d.py (C-ABI and fn.resize on DHWC / FDHWC / CDHW / FCDHW) runs with its assertions intact;
   * progressive JPEG batches (alone and mixed with baseline samples, whose kernels are no-ops here) must leave the baseline twin's
     coefficients in the arena and the DC differences the shared dc_scan stage expects, and report truncated / incomplete streams."""
 import os
@@ -30,7 +30,7 @@ def emul_env(tmp_path_factory):
 
 
 def test_volume_resize_gpu_tests_pass_on_the_emulated_launch_path(emul_env):
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_zzy_gpu_resize3d.py"), "-q", "-m", "gpu",
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_zzy_a_gpu_resize3d.py"), "-q", "-m", "gpu",
                         "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=1500, env=emul_env, cwd=ROOT)
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0, tail
@@ -47,7 +47,7 @@ import gpu_helpers as g
 from dali_b200 import capi
 from oracle import pyoracle as po
 from test_jpeg_prog_cpu import mcu_order
-from test_zzy_gpu_jpeg_progressive import _cases
+from test_zzy_c_gpu_jpeg_multiscan import _cases
 
 stub = C.CDLL(os.environ["EMUL_STUB"]); stub.emul_launch_count.restype = C.c_long
 cases = _cases()

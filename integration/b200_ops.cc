@@ -172,12 +172,15 @@ class ImageDecoderSlice : public ImageDecoderRoi<SliceAttr> {                   
 };
 
 // ------------------------------------------------------------------------------------------------ Resize
+// Images and volumes: the reference's ResizeAttr parses the layout (spatial_ndim_ 2 or 3, first_spatial_dim_), computes sizes and ROIs
+// (resize_attr.cc:102-259); the dimensions in front of the spatial ones are frames, those behind them channels (resize_op_impl.h:56-101).
 class Resize : public Operator<GPUBackend> {
  public:
   explicit Resize(const OpSpec &spec) : Operator<GPUBackend>(spec) {
-    Check(dalib200ResamplePlanCreate(&plan_, max_batch_size_), "Resize");
+    Check(dalib200ResamplePlanCreate(&plan_, max_batch_size_ * 64), "Resize");
+    Check(dalib200Resample3DPlanCreate(&plan3_, max_batch_size_ * 16), "Resize");
   }
-  ~Resize() override { dalib200ResamplePlanDestroy(plan_); }
+  ~Resize() override { dalib200ResamplePlanDestroy(plan_); dalib200Resample3DPlanDestroy(plan3_); }
 
  protected:
   bool SetupImpl(std::vector<OutputDesc> &out, const Workspace &ws) override {
@@ -186,43 +189,77 @@ class Resize : public Operator<GPUBackend> {
     const auto &shape = in.shape();
     resize_attr_.PrepareResizeParams(spec_, ws, shape, in.GetLayout());            // resize_attr.cc:178-259 (reference code)
     resampling_attr_.PrepareFilterParams(spec_, ws, n);                             // resampling_attr.cc:76-133
-    std::vector<kernels::ResamplingParams> rp(static_cast<size_t>(n) * 2);
+    const int sd = resize_attr_.spatial_ndim_, fs = resize_attr_.first_spatial_dim_, nd = shape.sample_dim();
+    DALI_ENFORCE(sd == 2 || sd == 3, "Resize: 2 or 3 spatial dimensions expected");
+    std::vector<kernels::ResamplingParams> rp(static_cast<size_t>(n) * sd);
     resampling_attr_.GetResamplingParams(make_span(rp), make_cspan(resize_attr_.params_));
-    samples_.resize(n);
     out.resize(1);
     out[0].type = resampling_attr_.GetOutputType(in.type());
     resize_attr_.GetResizedShape(out[0].shape, shape);
-    const int fs = resize_attr_.first_spatial_dim_;
+    samples_.clear(); samples3_.clear(); frame_sample_.clear(); frame_in_elems_.clear(); frame_out_elems_.clear();
     for (int i = 0; i < n; i++) {
       auto sh = shape.tensor_shape_span(i);
-      auto &s = samples_[i];
-      s.in_h = static_cast<int>(sh[fs]); s.in_w = static_cast<int>(sh[fs + 1]); s.channels = static_cast<int>(sh[fs + 2]);
-      s.out_h = rp[2 * i].output_size; s.out_w = rp[2 * i + 1].output_size;
-      for (int d = 0; d < 2; d++) {
-        const auto &p = rp[2 * i + d];
-        s.use_roi[d] = p.roi.use_roi; s.roi_start[d] = p.roi.start; s.roi_end[d] = p.roi.end;
-        s.min_filter[d] = { static_cast<int>(p.min_filter.type), p.min_filter.antialias, p.min_filter.radius };
-        s.mag_filter[d] = { static_cast<int>(p.mag_filter.type), p.mag_filter.antialias, p.mag_filter.radius };
+      auto osh = out[0].shape.tensor_shape_span(i);
+      int64_t frames = 1, channels = 1, in_vol = 1, out_vol = 1;
+      for (int d = 0; d < fs; d++) frames *= sh[d];
+      for (int d = fs + sd; d < nd; d++) channels *= sh[d];
+      for (int d = fs; d < nd; d++) { in_vol *= sh[d]; out_vol *= osh[d]; }
+      dalib200ResampleSample s2{};
+      dalib200Resample3DSample s3{};
+      for (int d = 0; d < sd; d++) {
+        const auto &p = rp[static_cast<size_t>(sd) * i + d];
+        const dalib200FilterDesc fmin = { static_cast<int>(p.min_filter.type), p.min_filter.antialias, p.min_filter.radius };
+        const dalib200FilterDesc fmag = { static_cast<int>(p.mag_filter.type), p.mag_filter.antialias, p.mag_filter.radius };
+        if (sd == 2) {
+          s2.use_roi[d] = p.roi.use_roi; s2.roi_start[d] = p.roi.start; s2.roi_end[d] = p.roi.end; s2.min_filter[d] = fmin; s2.mag_filter[d] = fmag;
+        } else {
+          s3.in_shape[d] = static_cast<int>(sh[fs + d]); s3.out_shape[d] = p.output_size;
+          s3.use_roi[d] = p.roi.use_roi; s3.roi_start[d] = p.roi.start; s3.roi_end[d] = p.roi.end; s3.min_filter[d] = fmin; s3.mag_filter[d] = fmag;
+        }
+      }
+      if (sd == 2) {
+        s2.in_h = static_cast<int>(sh[fs]); s2.in_w = static_cast<int>(sh[fs + 1]); s2.channels = static_cast<int>(channels);
+        s2.out_h = rp[2 * i].output_size; s2.out_w = rp[2 * i + 1].output_size;
+      } else {
+        s3.channels = static_cast<int>(channels);
+      }
+      for (int64_t k = 0; k < frames; k++) {
+        if (sd == 2) samples_.push_back(s2); else samples3_.push_back(s3);
+        frame_sample_.push_back(i); frame_in_elems_.push_back(k * in_vol); frame_out_elems_.push_back(k * out_vol);
       }
     }
-    Check(dalib200ResamplePlanSetup(plan_, n, samples_.data(), in.type() == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT,
-                                    out[0].type == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT), "Resize");
+    volumes_ = sd == 3;
+    const int it = in.type() == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT, ot = out[0].type == DALI_UINT8 ? DALIB200_UINT8 : DALIB200_FLOAT;
+    if (volumes_) Check(dalib200Resample3DPlanSetup(plan3_, static_cast<int>(samples3_.size()), samples3_.data(), it, ot), "Resize");
+    else Check(dalib200ResamplePlanSetup(plan_, static_cast<int>(samples_.size()), samples_.data(), it, ot), "Resize");
+    in_esize_ = TypeTable::GetTypeInfo(in.type()).size(); out_esize_ = TypeTable::GetTypeInfo(out[0].type).size();
     return true;
   }
   void RunImpl(Workspace &ws) override {
     const auto &in = ws.Input<GPUBackend>(0);
     auto &out = ws.Output<GPUBackend>(0);
     out.SetLayout(in.GetLayout());
-    auto ip = InPtrs(in);
-    auto op = OutPtrs(out);
-    Check(dalib200ResampleLaunch(plan_, ip.data(), op.data(), ws.stream()), "Resize");
+    std::vector<const void *> ip(frame_sample_.size());
+    std::vector<void *> op(frame_sample_.size());
+    for (size_t k = 0; k < frame_sample_.size(); k++) {
+      ip[k] = static_cast<const uint8_t *>(in.raw_tensor(frame_sample_[k])) + frame_in_elems_[k] * in_esize_;
+      op[k] = static_cast<uint8_t *>(out.raw_mutable_tensor(frame_sample_[k])) + frame_out_elems_[k] * out_esize_;
+    }
+    if (volumes_) Check(dalib200Resample3DLaunch(plan3_, ip.data(), op.data(), ws.stream()), "Resize");
+    else Check(dalib200ResampleLaunch(plan_, ip.data(), op.data(), ws.stream()), "Resize");
   }
 
  private:
   ResizeAttr resize_attr_;
   ResamplingFilterAttr resampling_attr_;
   dalib200ResamplePlan *plan_ = nullptr;
+  dalib200Resample3DPlan *plan3_ = nullptr;
+  bool volumes_ = false;
+  size_t in_esize_ = 1, out_esize_ = 1;
   std::vector<dalib200ResampleSample> samples_;
+  std::vector<dalib200Resample3DSample> samples3_;
+  std::vector<int> frame_sample_;
+  std::vector<int64_t> frame_in_elems_, frame_out_elems_;
 };
 
 // ------------------------------------------------------------------------------------------------ CropMirrorNormalize

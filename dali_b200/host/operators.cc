@@ -65,15 +65,26 @@ static FrameList ExpandFrames(const TensorListShape &shape, const TensorLayout &
 // Resize takes every layout of the reference's schema (resize.cc:28-29): the dimensions in front of the spatial ones collapse into
 // frames -- which covers channel-first data: a CHW image is C one-channel frames --, those behind them into channels
 // (resize_op_impl.h:56-101).  2-D layouts here; the volumetric ones go through SetupVolumes.
+// ResizeAttr::ParseLayout (resize_attr.cc:102-123) over the layouts of the schema: number of spatial dimensions and index of the first
+static void ParseResizeLayout(const std::string &l, int *spatial_ndim, int *first_spatial) {
+  static const char *const kLayouts[] = { "HWC", "FHWC", "CHW", "FCHW", "CFHW", "DHWC", "FDHWC", "CDHW", "FCDHW", "CFDHW" };
+  bool known = false;
+  for (const char *k : kLayouts) known |= l == k;
+  DALI_ENFORCE(known, "Resize: unsupported layout \"", l, "\"; expected one of HWC, FHWC, CHW, FCHW, CFHW, DHWC, FDHWC, CDHW, FCDHW, CFDHW");
+  const size_t d = l.find('D');
+  *spatial_ndim = d == std::string::npos ? 2 : 3;
+  *first_spatial = static_cast<int>(d == std::string::npos ? l.find('H') : d);
+}
+
 static FrameList ExpandFramesAnyLayout(const TensorListShape &shape, const TensorLayout &layout, const char *op) {
   FrameList f;
   const int nd = shape.sample_dim();
   std::string l = layout.str();
   if (l.empty()) l = nd == 3 ? "HWC" : nd == 4 ? "FHWC" : "";
-  DALI_ENFORCE(l == "HWC" || l == "FHWC" || l == "CHW" || l == "FCHW" || l == "CFHW", op, ": unsupported layout \"", l, "\" (", nd,
-               "-D); expected one of HWC, FHWC, CHW, FCHW, CFHW, DHWC, FDHWC, CDHW, FCDHW, CFDHW");
+  int sd = 2, fs = 0;
+  ParseResizeLayout(l, &sd, &fs);
+  DALI_ENFORCE(sd == 2, op, ": a 2-D layout is expected here, got \"", l, "\"");
   DALI_ENFORCE(static_cast<int>(l.size()) == nd, op, ": layout \"", l, "\" does not match a ", nd, "-D input");
-  const int fs = static_cast<int>(l.find('H'));
   f.first_spatial = fs;
   for (int i = 0; i < shape.num_samples(); i++) {
     const int64_t *s = shape.tensor_shape_span(i);
@@ -803,10 +814,9 @@ class ResizeGPU : public Operator<GPUBackend>, public PlanarConsumer {
     const int n = in.num_samples();
     const std::string lay = in.GetLayout().str();
     const int nd = in.shape().sample_dim();
-    DALI_ENFORCE(lay == "DHWC" || lay == "FDHWC" || lay == "CDHW" || lay == "FCDHW" || lay == "CFDHW", "Resize: unsupported layout \"", lay,
-                 "\"; expected one of HWC, FHWC, CHW, FCHW, CFHW, DHWC, FDHWC, CDHW, FCDHW, CFDHW");
+    int sd = 3, fs = 0;
+    ParseResizeLayout(lay, &sd, &fs);
     DALI_ENFORCE(nd == static_cast<int>(lay.size()), "Resize: layout \"", lay, "\" does not match a ", nd, "-D input");
-    const int fs = static_cast<int>(lay.find('D'));
     if (producer_) { std::vector<uint8_t> none(n, 0), granted; producer_->SelectPlanar(none, granted); }
     std::vector<float> max_size(3, std::nextafter(static_cast<float>(std::numeric_limits<int>::max()), 0.0f));
     if (has_max_) max_size = spec_.GetFloatVecArgument("max_size", &ws, 0, 3);
@@ -2353,6 +2363,11 @@ extern "C" int dalihTestResizeParams(int mode, const float *requested_hw, const 
     for (int d = 0; d < 2; d++) { dst_hw[d] = p.dst[d]; lo_hw[d] = p.lo[d]; hi_hw[d] = p.hi[d]; }
     return 0;
   } catch (...) { return 1; }
+}
+
+// Layout parsing of Resize (resize_attr_test.cc:22-51): returns 0 and (spatial_ndim, first_spatial_dim), or 1 for a layout it rejects.
+extern "C" int dalihTestResizeLayout(const char *layout, int *spatial_ndim, int *first_spatial) {
+  try { dali::ParseResizeLayout(layout, spatial_ndim, first_spatial); return 0; } catch (...) { return 1; }
 }
 
 // The same for volumes (spatial_ndim = 3; arrays in shape order depth, height, width): resize_attr_test.cc Resize3D* vectors.

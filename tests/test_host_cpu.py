@@ -159,6 +159,24 @@ def test_resize_size_rules_for_volumes_reference_kats():
     assert _resize_params3(NOT_SMALLER, (160, 480, 600), (32, 320, 240))[0] == [160, 1600, 1200]
     assert _resize_params3(NOT_SMALLER, (160, 480, 600), (1536, 768, 1024), max_size=(720, 720, 720))[0] == [720, 360, 480]
     assert _resize_params3(NOT_SMALLER, (160, 480, 600), (32, 320, 240), max_size=(720, 720, 720))[0] == [72, 720, 540]
+    # per-axis max_size (:410-423): the depth of the second sample rounds 38.4 -> 38 and its ROI shrinks about the centre
+    dst, lo, hi = _resize_params3(NOT_SMALLER, (160, 480, 600), (32, 320, 240), max_size=(720, 384, 400))
+    assert dst == [38, 384, 288] and lo[1:] == [0.0, 0.0] and hi[1:] == [320.0, 240.0]
+    assert abs(lo[0] - 0.166667) < 1e-5 and abs(hi[0] - 31.83333) < 1e-4
+
+
+def test_resize_layout_parsing_reference_kats():
+    """resize_attr_test.cc:22-51: layout -> (spatial_ndim, first_spatial_dim); layouts outside the schema are rejected."""
+    lib = backend.lib()
+    def parse(l):
+        sd, fs = C.c_int(), C.c_int()
+        return (sd.value, fs.value) if lib.dalihTestResizeLayout(l.encode(), C.byref(sd), C.byref(fs)) == 0 else None
+    want = {"HWC": (2, 0), "CHW": (2, 1), "DHWC": (3, 0), "CDHW": (3, 1), "FHWC": (2, 1), "FCHW": (2, 2), "FDHWC": (3, 1), "FCDHW": (3, 2),
+            "CFHW": (2, 2), "CFDHW": (3, 2)}
+    for l, v in want.items():
+        assert parse(l) == v, l
+    for l in ("HCW", "FWCH", "HW", "", "DHW"):
+        assert parse(l) is None, l
 
 
 def test_external_source_feeding_modes():
